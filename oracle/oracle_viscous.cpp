@@ -1,0 +1,477 @@
+// TEST INFRASTRUCTURE ONLY -- CPU oracle, part 2: Green-Gauss gradients + ghost-gradient BC, viscosity /
+// eddy viscosity / F1, viscous fluxes (laminar + SST), SST source, time step, update, residual norm.
+// PARITY UNPINNED (see oracle_abi.h).
+#include "oracle_core.hpp"
+
+namespace orc {
+
+static inline bool is_sst(const Block& B) { return B.c.turbulence == ORC_TURB_SST || B.c.turbulence == ORC_TURB_SST2003; }
+
+// gradients.f90:405-482 compute_gradient_G (dir 0/1/2 = x/y/z); var is a full-size (-2:imx+2..) field
+template <class Var>
+static void gradient_G(Block& B, Arr4& grad, int comp, const Var& var, int dir) {
+  const Rec4 &If = B.If, &Jf = B.Jf, &Kf = B.Kf;
+  auto n = [dir](const Rec4& f, int i, int j, int k) { return f.at(i, j, k)[1 + dir]; };
+  for (int k = 0; k <= B.kmx; ++k)
+    for (int j = 0; j <= B.jmx; ++j)
+      for (int i = 0; i <= B.imx; ++i) {
+        double v = var(i, j, k);
+        double g = (-(var(i - 1, j, k) + v) * n(If, i, j, k) * If.A(i, j, k)
+                    - (var(i, j - 1, k) + v) * n(Jf, i, j, k) * Jf.A(i, j, k)
+                    - (var(i, j, k - 1) + v) * n(Kf, i, j, k) * Kf.A(i, j, k)
+                    + (var(i + 1, j, k) + v) * n(If, i + 1, j, k) * If.A(i + 1, j, k)
+                    + (var(i, j + 1, k) + v) * n(Jf, i, j + 1, k) * Jf.A(i, j + 1, k)
+                    + (var(i, j, k + 1) + v) * n(Kf, i, j, k + 1) * Kf.A(i, j, k + 1)) /
+                   (2 * B.cells.vol(i, j, k));
+        grad(i, j, k, comp) = g;
+        if (std::isnan(g)) B.error |= 2;
+      }
+}
+
+// gradients.f90:594-676 apply_gradient_bc_face.  KEPT DEFECT: the dummy `faces` is declared with the
+// Ifaces shape (-2:imx+3,-2:jmx+2,-2:kmx+2) but receives Jfaces / Kfaces (:549,562,575,588), so element
+// (i,j,k) is fetched by sequence association at linear offset (i+2)+(imx+6)*((j+2)+(jmx+5)*(k+2)).
+static void gradient_bc_face(Block& B, const Rec4& faces, int imin, int imax, int jmin, int jmax, int kmin, int kmax,
+                             int il, int jl, int kl, int iu, int ju, int ku, int sig, int bc_id, double fixed_temp) {
+  const int n0 = B.imx + 6, n1 = B.jmx + 5;
+  const int ng = B.n_grad;
+  for (int k = kmin; k <= kmax; ++k)
+    for (int j = jmin; j <= jmax; ++j)
+      for (int i = imin; i <= imax; ++i) {
+        const double* fr = &faces.d[4 * ((size_t)(i + 2) + (size_t)n0 * ((size_t)(j + 2) + (size_t)n1 * (size_t)(k + 2)))];
+        double nx = fr[1], ny = fr[2], nz = fr[3];
+        double vol = B.cells.vol(i - iu, j - ju, k - ku);
+        double c_x = fr[0] * nx / vol, c_y = fr[0] * ny / vol, c_z = fr[0] * nz / vol;
+        double T_I = B.Temp(i - iu, j - ju, k - ku), T_G = B.Temp(i - il, j - jl, k - kl);
+        const int gi = i - il, gj = j - jl, gk = k - kl;   // ghost cell
+        const int ci = i - iu, cj = j - ju, ck = k - ku;   // interior cell
+        for (int l = 1; l <= ng; ++l) {   // qp_I = qp(...,2:n_var) -> slot l holds variable l+1
+          double qI = B.qp(ci, cj, ck, l + 1), qG = B.qp(gi, gj, gk, l + 1);
+          B.gx(gi, gj, gk, l) = sig * (qI - qG) * c_x;
+          B.gy(gi, gj, gk, l) = sig * (qI - qG) * c_y;
+          B.gz(gi, gj, gk, l) = sig * (qI - qG) * c_z;
+        }
+        B.gx(gi, gj, gk, 4) = sig * (T_I - T_G) * c_x;
+        B.gy(gi, gj, gk, 4) = sig * (T_I - T_G) * c_y;
+        B.gz(gi, gj, gk, 4) = sig * (T_I - T_G) * c_z;
+        if (bc_id == -5 && (fixed_temp < 1. && fixed_temp >= 0.)) {
+          B.gx(gi, gj, gk, 4) = -B.gx(ci, cj, ck, 4);
+          B.gy(gi, gj, gk, 4) = -B.gy(ci, cj, ck, 4);
+          B.gz(gi, gj, gk, 4) = -B.gz(ci, cj, ck, 4);
+        }
+        for (int l = 1; l <= ng; ++l) {
+          double dot = (B.gx(ci, cj, ck, l) * nx) + (B.gy(ci, cj, ck, l) * ny) + (B.gz(ci, cj, ck, l) * nz);
+          B.gx(gi, gj, gk, l) = B.gx(gi, gj, gk, l) + (B.gx(ci, cj, ck, l) - dot * nx);
+          B.gy(gi, gj, gk, l) = B.gy(gi, gj, gk, l) + (B.gy(ci, cj, ck, l) - dot * ny);
+          B.gz(gi, gj, gk, l) = B.gz(gi, gj, gk, l) + (B.gz(ci, cj, ck, l) - dot * nz);
+        }
+      }
+}
+
+struct QpVar {
+  const Arr4& q; int l;
+  inline double operator()(int i, int j, int k) const { return q(i, j, k, l); }
+};
+
+// gradients.f90:276-402 evaluate_all_gradients
+void Block::evaluate_all_gradients() {
+  Block& B = *this;
+  QpVar u{qp, 2}, v{qp, 3}, w{qp, 4};
+  gradient_G(B, gx, 1, u, 0); gradient_G(B, gx, 2, v, 0); gradient_G(B, gx, 3, w, 0); gradient_G(B, gx, 4, Temp, 0);
+  gradient_G(B, gy, 1, u, 1); gradient_G(B, gy, 2, v, 1); gradient_G(B, gy, 3, w, 1); gradient_G(B, gy, 4, Temp, 1);
+  if (kmx > 2) {
+    gradient_G(B, gz, 1, u, 2); gradient_G(B, gz, 2, v, 2); gradient_G(B, gz, 3, w, 2); gradient_G(B, gz, 4, Temp, 2);
+  } else {
+    std::fill(gz.d.begin(), gz.d.end(), 0.0);   // gradqp_z = 0.0 (:336)
+  }
+  if (is_sst(B)) {
+    QpVar tk{qp, 6}, tw{qp, 7};
+    gradient_G(B, gx, 5, tk, 0); gradient_G(B, gx, 6, tw, 0);
+    gradient_G(B, gy, 5, tk, 1); gradient_G(B, gy, 6, tw, 1);
+    if (kmx > 2) { gradient_G(B, gz, 5, tk, 2); gradient_G(B, gz, 6, tw, 2); }
+  }
+  // apply_gradient_bc :486-592
+  const double* wt = c.fixed[ORC_FIX_WALL_TEMP];
+  if (c.bc_id[0] < 0) gradient_bc_face(B, If, 1, 1, 1, jmx - 1, 1, kmx - 1, 1, 0, 0, 0, 0, 0, 1, c.bc_id[0], wt[0]);
+  if (c.bc_id[1] < 0) gradient_bc_face(B, If, imx, imx, 1, jmx - 1, 1, kmx - 1, 0, 0, 0, 1, 0, 0, -1, c.bc_id[1], wt[1]);
+  if (c.bc_id[2] < 0) gradient_bc_face(B, Jf, 1, imx - 1, 1, 1, 1, kmx - 1, 0, 1, 0, 0, 0, 0, 1, c.bc_id[2], wt[2]);
+  if (c.bc_id[3] < 0) gradient_bc_face(B, Jf, 1, imx - 1, jmx, jmx, 1, kmx - 1, 0, 0, 0, 0, 1, 0, -1, c.bc_id[3], wt[3]);
+  if (c.bc_id[4] < 0) gradient_bc_face(B, Kf, 1, imx - 1, 1, jmx - 1, 1, 1, 0, 0, 1, 0, 0, 0, 1, c.bc_id[4], wt[4]);
+  if (c.bc_id[5] < 0) gradient_bc_face(B, Kf, 1, imx - 1, 1, jmx - 1, kmx, kmx, 0, 0, 0, 0, 0, 1, -1, c.bc_id[5], wt[5]);
+}
+
+// viscosity.f90:52-546 calculate_viscosity (Sutherland; sst :343-465; sst2003 :215-341)
+void Block::calculate_viscosity() {
+  Block& B = *this;
+  if (c.mu_ref != 0. && c.mu_variation == 1) {
+    for (int k = 0; k <= kmx; ++k)
+      for (int j = 0; j <= jmx; ++j)
+        for (int i = 0; i <= imx; ++i) {
+          double T = qp(i, j, k, 5) / (qp(i, j, k, 1) * c.R_gas);
+          mu(i, j, k) = c.mu_ref * (std::pow(T / c.T_ref, 1.5)) * ((c.T_ref + c.Sutherland_temp) / (T + c.Sutherland_temp));
+        }
+  }
+  if (is_sst(B)) {
+    const bool s2003 = c.turbulence == ORC_TURB_SST2003;
+    const double floor_v = s2003 ? 1.0e-10 : 1.e-20;
+    for (int k = 0; k <= kmx; ++k)
+      for (int j = 0; j <= jmx; ++j)
+        for (int i = 0; i <= imx; ++i) {
+          double density = qp(i, j, k, 1), tk = qp(i, j, k, 6), tw = qp(i, j, k, 7);
+          double d = dist(i, j, k);
+          double var1 = std::sqrt(tk) / (bstar * tw * d);
+          double var2 = 500 * (mu(i, j, k) / density) / ((d * d) * tw);
+          double arg2 = std::fmax(2 * var1, var2);
+          double Fb = std::tanh(arg2 * arg2);
+          double rate;
+          if (!s2003) {
+            double wx = (gy(i, j, k, 3) - gz(i, j, k, 2));
+            double wy = (gz(i, j, k, 1) - gx(i, j, k, 3));
+            double wz = (gx(i, j, k, 2) - gy(i, j, k, 1));
+            rate = std::sqrt(wx * wx + wy * wy + wz * wz);
+          } else {
+            double sxx = gx(i, j, k, 1), syy = gy(i, j, k, 2), szz = gz(i, j, k, 3);
+            double syz = (gy(i, j, k, 3) + gz(i, j, k, 2));
+            double szx = (gz(i, j, k, 1) + gx(i, j, k, 3));
+            double sxy = (gx(i, j, k, 2) + gy(i, j, k, 1));
+            rate = std::sqrt((2.0 * (sxx * sxx)) + (2.0 * (syy * syy)) + (2.0 * (szz * szz)) + syz * syz + szx * szx + sxy * sxy);
+          }
+          double NUM = density * a1_sst * tk;
+          double DENOM = std::fmax(std::fmax((a1_sst * tw), rate * Fb), floor_v);
+          mu_t(i, j, k) = NUM / DENOM;
+          double CD = std::fmax(2 * density * sigma_w2 * (gx(i, j, k, 5) * gx(i, j, k, 6) + gy(i, j, k, 5) * gy(i, j, k, 6) + gz(i, j, k, 5) * gz(i, j, k, 6)) / tw, floor_v);
+          double right = 4 * (density * sigma_w2 * tk) / (CD * (d * d));
+          double left = std::fmax(var1, var2);
+          double arg1 = std::fmin(left, right);
+          F1(i, j, k) = std::tanh((arg1 * arg1) * (arg1 * arg1));
+        }
+    // ghost mu_t / F1 per BC id (:408-465)
+    for (int face = 1; face <= 6; ++face) {
+      int id = c.bc_id[face - 1];
+      if (id >= 0 || id == -10) continue;
+      double sgn;
+      if (id == -5) sgn = -1.0;
+      else if (id == -1 || id == -2 || id == -3 || id == -4 || id == -6 || id == -7 || id == -8 || id == -9) sgn = 1.0;
+      else continue;
+      int na = face <= 2 ? jmx - 1 : imx - 1, nb = face <= 4 ? kmx - 1 : jmx - 1;
+      for (int b = 1; b <= nb; ++b)
+        for (int a = 1; a <= na; ++a) {
+          int i, j, k, ig, jg, kg;
+          switch (face) {
+            case 1: i = 1; j = a; k = b; ig = 0; jg = a; kg = b; break;
+            case 2: i = imx - 1; j = a; k = b; ig = imx; jg = a; kg = b; break;
+            case 3: i = a; j = 1; k = b; ig = a; jg = 0; kg = b; break;
+            case 4: i = a; j = jmx - 1; k = b; ig = a; jg = jmx; kg = b; break;
+            case 5: i = a; j = b; k = 1; ig = a; jg = b; kg = 0; break;
+            default: i = a; j = b; k = kmx - 1; ig = a; jg = b; kg = kmx; break;
+          }
+          mu_t(ig, jg, kg) = sgn * mu_t(i, j, k);
+          F1(ig, jg, kg) = F1(i, j, k);
+        }
+    }
+  }
+  for (double m : mu.d) if (std::isnan(m)) { error |= 4; break; }
+}
+
+// viscous.f90:144-325 compute_viscous_fluxes_laminar
+static void viscous_laminar(Block& B, Arr4& F, const Rec4& faces, int ii, int jj, int kk) {
+  const OracleConfig& c = B.c;
+  const bool turb = c.turbulence != ORC_TURB_NONE;
+  for (int k = 1; k <= B.kmx - 1 + kk; ++k)
+    for (int j = 1; j <= B.jmx - 1 + jj; ++j)
+      for (int i = 1; i <= B.imx - 1 + ii; ++i) {
+        const int im = i - ii, jm = j - jj, km = k - kk;
+        double dudx = 0.5 * (B.gx(im, jm, km, 1) + B.gx(i, j, k, 1));
+        double dudy = 0.5 * (B.gy(im, jm, km, 1) + B.gy(i, j, k, 1));
+        double dudz = 0.5 * (B.gz(im, jm, km, 1) + B.gz(i, j, k, 1));
+        double dvdx = 0.5 * (B.gx(im, jm, km, 2) + B.gx(i, j, k, 2));
+        double dvdy = 0.5 * (B.gy(im, jm, km, 2) + B.gy(i, j, k, 2));
+        double dvdz = 0.5 * (B.gz(im, jm, km, 2) + B.gz(i, j, k, 2));
+        double dwdx = 0.5 * (B.gx(im, jm, km, 3) + B.gx(i, j, k, 3));
+        double dwdy = 0.5 * (B.gy(im, jm, km, 3) + B.gy(i, j, k, 3));
+        double dwdz = 0.5 * (B.gz(im, jm, km, 3) + B.gz(i, j, k, 3));
+        double dTdx = 0.5 * (B.gx(im, jm, km, 4) + B.gx(i, j, k, 4));
+        double dTdy = 0.5 * (B.gy(im, jm, km, 4) + B.gy(i, j, k, 4));
+        double dTdz = 0.5 * (B.gz(im, jm, km, 4) + B.gz(i, j, k, 4));
+        double delx = B.cells.cx(i, j, k) - B.cells.cx(im, jm, km);
+        double dely = B.cells.cy(i, j, k) - B.cells.cy(im, jm, km);
+        double delz = B.cells.cz(i, j, k) - B.cells.cz(im, jm, km);
+        double d_LR = std::sqrt(delx * delx + dely * dely + delz * delz);
+        double T_LE = B.qp(im, jm, km, 5) / (B.qp(im, jm, km, 1) * c.R_gas);
+        double T_RE = B.qp(i, j, k, 5) / (B.qp(i, j, k, 1) * c.R_gas);
+        double delu = B.qp(i, j, k, 2) - B.qp(im, jm, km, 2);
+        double delv = B.qp(i, j, k, 3) - B.qp(im, jm, km, 3);
+        double delw = B.qp(i, j, k, 4) - B.qp(im, jm, km, 4);
+        double delT = T_RE - T_LE;
+        double normal_comp = (delu - (dudx * delx + dudy * dely + dudz * delz)) / d_LR;
+        dudx = dudx + (normal_comp * delx / d_LR);
+        dudy = dudy + (normal_comp * dely / d_LR);
+        dudz = dudz + (normal_comp * delz / d_LR);
+        normal_comp = (delv - (dvdx * delx + dvdy * dely + dvdz * delz)) / d_LR;
+        dvdx = dvdx + (normal_comp * delx / d_LR);
+        dvdy = dvdy + (normal_comp * dely / d_LR);
+        dvdz = dvdz + (normal_comp * delz / d_LR);
+        normal_comp = (delw - (dwdx * delx + dwdy * dely + dwdz * delz)) / d_LR;
+        dwdx = dwdx + (normal_comp * delx / d_LR);
+        dwdy = dwdy + (normal_comp * dely / d_LR);
+        dwdz = dwdz + (normal_comp * delz / d_LR);
+        normal_comp = (delT - (dTdx * delx + dTdy * dely + dTdz * delz)) / d_LR;
+        dTdx = dTdx + (normal_comp * delx / d_LR);
+        dTdy = dTdy + (normal_comp * dely / d_LR);
+        dTdz = dTdz + (normal_comp * delz / d_LR);
+        double mu_f = 0.5 * (B.mu(im, jm, km) + B.mu(i, j, k));
+        double mut_f = turb ? 0.5 * (B.mu_t(im, jm, km) + B.mu_t(i, j, k)) : 0.0;
+        double total_mu = mu_f + mut_f;
+        double Tau_xx = 2. * total_mu * (dudx - ((dudx + dvdy + dwdz) / 3.));
+        double Tau_yy = 2. * total_mu * (dvdy - ((dudx + dvdy + dwdz) / 3.));
+        double Tau_zz = 2. * total_mu * (dwdz - ((dudx + dvdy + dwdz) / 3.));
+        double Tau_xy = total_mu * (dvdx + dudy);
+        double Tau_xz = total_mu * (dwdx + dudz);
+        double Tau_yz = total_mu * (dwdy + dvdz);
+        double Tau_yx = Tau_xy, Tau_zx = Tau_xz, Tau_zy = Tau_yz;
+        double K_heat = (mu_f / c.Pr + mut_f / c.tPr) * c.gm * c.R_gas / (c.gm - 1);
+        double Qx = K_heat * dTdx, Qy = K_heat * dTdy, Qz = K_heat * dTdz;
+        double nx = faces.nx(i, j, k), ny = faces.ny(i, j, k), nz = faces.nz(i, j, k), area = faces.A(i, j, k);
+        double uface = 0.5 * (B.qp(im, jm, km, 2) + B.qp(i, j, k, 2));
+        double vface = 0.5 * (B.qp(im, jm, km, 3) + B.qp(i, j, k, 3));
+        double wface = 0.5 * (B.qp(im, jm, km, 4) + B.qp(i, j, k, 4));
+        F(i, j, k, 2) = F(i, j, k, 2) - ((Tau_xx * nx + Tau_xy * ny + Tau_xz * nz) * area);
+        F(i, j, k, 3) = F(i, j, k, 3) - ((Tau_yx * nx + Tau_yy * ny + Tau_yz * nz) * area);
+        F(i, j, k, 4) = F(i, j, k, 4) - ((Tau_zx * nx + Tau_zy * ny + Tau_zz * nz) * area);
+        F(i, j, k, 5) = F(i, j, k, 5) - (area * (((Tau_xx * uface + Tau_xy * vface + Tau_xz * wface + Qx) * nx) +
+                                                ((Tau_yx * uface + Tau_yy * vface + Tau_yz * wface + Qy) * ny) +
+                                                ((Tau_zx * uface + Tau_zy * vface + Tau_zz * wface + Qz) * nz)));
+      }
+}
+
+// viscous.f90:328-447 compute_viscous_fluxes_sst
+static void viscous_sst(Block& B, Arr4& F, const Rec4& faces, int ii, int jj, int kk) {
+  for (int k = 1; k <= B.kmx - 1 + kk; ++k)
+    for (int j = 1; j <= B.jmx - 1 + jj; ++j)
+      for (int i = 1; i <= B.imx - 1 + ii; ++i) {
+        const int im = i - ii, jm = j - jj, km = k - kk;
+        double dtkdx = 0.5 * (B.gx(im, jm, km, 5) + B.gx(i, j, k, 5));
+        double dtkdy = 0.5 * (B.gy(im, jm, km, 5) + B.gy(i, j, k, 5));
+        double dtkdz = 0.5 * (B.gz(im, jm, km, 5) + B.gz(i, j, k, 5));
+        double dtwdx = 0.5 * (B.gx(im, jm, km, 6) + B.gx(i, j, k, 6));
+        double dtwdy = 0.5 * (B.gy(im, jm, km, 6) + B.gy(i, j, k, 6));
+        double dtwdz = 0.5 * (B.gz(im, jm, km, 6) + B.gz(i, j, k, 6));
+        double delx = B.cells.cx(i, j, k) - B.cells.cx(im, jm, km);
+        double dely = B.cells.cy(i, j, k) - B.cells.cy(im, jm, km);
+        double delz = B.cells.cz(i, j, k) - B.cells.cz(im, jm, km);
+        double d_LR = std::sqrt(delx * delx + dely * dely + delz * delz);
+        double deltk = B.qp(i, j, k, 6) - B.qp(im, jm, km, 6);
+        double deltw = B.qp(i, j, k, 7) - B.qp(im, jm, km, 7);
+        double normal_comp = (deltk - (dtkdx * delx + dtkdy * dely + dtkdz * delz)) / d_LR;
+        dtkdx = dtkdx + (normal_comp * delx / d_LR);
+        dtkdy = dtkdy + (normal_comp * dely / d_LR);
+        dtkdz = dtkdz + (normal_comp * delz / d_LR);
+        normal_comp = (deltw - (dtwdx * delx + dtwdy * dely + dtwdz * delz)) / d_LR;
+        dtwdx = dtwdx + (normal_comp * delx / d_LR);
+        dtwdy = dtwdy + (normal_comp * dely / d_LR);
+        dtwdz = dtwdz + (normal_comp * delz / d_LR);
+        double mu_f = 0.5 * (B.mu(im, jm, km) + B.mu(i, j, k));
+        double mut_f = 0.5 * (B.mu_t(im, jm, km) + B.mu_t(i, j, k));
+        double F1f = 0.5 * (B.F1(im, jm, km) + B.F1(i, j, k));
+        double sigma_kf = sigma_k1 * F1f + sigma_k2 * (1.0 - F1f);
+        double sigma_wf = sigma_w1 * F1f + sigma_w2 * (1.0 - F1f);
+        double rhoface = 0.5 * (B.qp(im, jm, km, 1) + B.qp(i, j, k, 1));
+        double tkface = 0.5 * (B.qp(im, jm, km, 6) + B.qp(i, j, k, 6));
+        double Tau_xx = -2.0 * rhoface * tkface / 3.0;
+        double Tau_yy = Tau_xx, Tau_zz = Tau_xx;
+        double nx = faces.nx(i, j, k), ny = faces.ny(i, j, k), nz = faces.nz(i, j, k), area = faces.A(i, j, k);
+        F(i, j, k, 2) = F(i, j, k, 2) - (Tau_xx * nx * area);
+        F(i, j, k, 3) = F(i, j, k, 3) - (Tau_yy * ny * area);
+        F(i, j, k, 4) = F(i, j, k, 4) - (Tau_zz * nz * area);
+        F(i, j, k, 5) = F(i, j, k, 5) - (area * ((mu_f + sigma_kf * mut_f) * (dtkdx * nx + dtkdy * ny + dtkdz * nz)));
+        F(i, j, k, 6) = F(i, j, k, 6) - (area * ((mu_f + sigma_kf * mut_f) * (dtkdx * nx + dtkdy * ny + dtkdz * nz)));
+        F(i, j, k, 7) = F(i, j, k, 7) - (area * ((mu_f + sigma_wf * mut_f) * (dtwdx * nx + dtwdy * ny + dtwdz * nz)));
+      }
+}
+
+// viscous.f90:55-142: laminar on F,G,H always (also the K flux when kmx==2), SST K flux skipped when kmx==2
+void Block::compute_viscous_fluxes() {
+  viscous_laminar(*this, F, If, 1, 0, 0);
+  viscous_laminar(*this, G, Jf, 0, 1, 0);
+  viscous_laminar(*this, H, Kf, 0, 0, 1);
+  if (is_sst(*this)) {
+    viscous_sst(*this, F, If, 1, 0, 0);
+    viscous_sst(*this, G, Jf, 0, 1, 0);
+    if (kmx != 2) viscous_sst(*this, H, Kf, 0, 0, 1);
+  }
+  auto has_nan = [](const Arr4& a) { for (double v : a.d) if (std::isnan(v)) return true; return false; };
+  if (has_nan(F) || has_nan(G) || has_nan(H)) error |= 1;
+}
+
+// source.f90:158-270 add_sst_source
+void Block::add_source_term_residue() {
+  if (!is_sst(*this)) return;
+  int limiter;
+  if (c.turbulence == ORC_TURB_SST2003) { limiter = 10; gama1 = 5.0 / 9.0; gama2 = 0.44; }
+  else limiter = 20;
+  const double cd_floor = (limiter == 20) ? 1.0e-20 : 1.0e-10;   // 10.0**(-limiter)
+  for (int k = 1; k <= kmx - 1; ++k)
+    for (int j = 1; j <= jmx - 1; ++j)
+      for (int i = 1; i <= imx - 1; ++i) {
+        double density = qp(i, j, k, 1), tk = qp(i, j, k, 6), tw = qp(i, j, k, 7);
+        double a = (gy(i, j, k, 3) - gz(i, j, k, 2)), b = (gz(i, j, k, 1) - gx(i, j, k, 3)), cc = (gx(i, j, k, 2) - gy(i, j, k, 1));
+        double vort = std::sqrt(a * a + b * b + cc * cc);
+        double CD = 2 * density * sigma_w2 * (gx(i, j, k, 5) * gx(i, j, k, 6) + gy(i, j, k, 5) * gy(i, j, k, 6) + gz(i, j, k, 5) * gz(i, j, k, 6)) / tw;
+        CD = std::fmax(CD, cd_floor);
+        double F1c = F1(i, j, k);
+        double gama = gama1 * F1c + gama2 * (1. - F1c);
+        double beta = beta1 * F1c + beta2 * (1. - F1c);
+        double D_k = bstar * density * tw * tk;
+        double D_w = beta * density * (tw * tw);
+        double divergence = gx(i, j, k, 1) + gy(i, j, k, 2) + gz(i, j, k, 3);
+        double P_k = mu_t(i, j, k) * (vort * vort) - ((2.0 / 3.0) * density * tk * divergence);
+        P_k = std::fmin(P_k, limiter * D_k);
+        double P_w = (density * gama / mu_t(i, j, k)) * P_k;
+        double lamda = (1. - F1c) * CD;
+        double S_k = P_k - D_k;
+        double S_w = P_w - D_w + lamda;
+        S_k = S_k * cells.vol(i, j, k);
+        S_w = S_w * cells.vol(i, j, k);
+        residue(i, j, k, 6) = residue(i, j, k, 6) - S_k;
+        residue(i, j, k, 7) = residue(i, j, k, 7) - S_w;
+      }
+}
+
+// update.f90:495-547 (everything after apply_interface)
+void Block::total_residue() {
+  populate_ghost_primitive();
+  compute_face_interpolant();
+  reconstruct_boundary_state();
+  compute_fluxes();
+  if (c.mu_ref != 0.0) {
+    evaluate_all_gradients();
+    calculate_viscosity();
+    compute_viscous_fluxes();
+  }
+  compute_residue();
+  add_source_term_residue();
+}
+
+// time.f90:122-246 compute_local_time_step, :366-448 add_viscous_time, :450-531 add_turbulent_time,
+// :248-289 compute_global_time_step (block-local minval)
+static void add_diffusive_time(Block& B, const Arr3& m, double prandtl) {
+  const Rec4 &cl = B.cells, &If = B.If, &Jf = B.Jf, &Kf = B.Kf;
+  const double CFL = B.c.CFL;
+  auto term = [&](double muv, double rho, int ia, int ja, int ka, int ib, int jb, int kb, const Rec4& f, int fi, int fj, int fk) {
+    return muv / (rho * std::fabs(((cl.cx(ia, ja, ka) - cl.cx(ib, jb, kb)) * f.nx(fi, fj, fk)) +
+                                   ((cl.cy(ia, ja, ka) - cl.cy(ib, jb, kb)) * f.ny(fi, fj, fk)) +
+                                   ((cl.cz(ia, ja, ka) - cl.cz(ib, jb, kb)) * f.nz(fi, fj, fk))));
+  };
+  for (int k = 1; k <= B.kmx - 1; ++k)
+    for (int j = 1; j <= B.jmx - 1; ++j)
+      for (int i = 1; i <= B.imx - 1; ++i) {
+        double lmx1 = term(m(i, j, k), B.qp(i, j, k, 1), i - 1, j, k, i, j, k, If, i, j, k);
+        double lmx2 = term(m(i, j, k), B.qp(i, j, k, 1), i, j - 1, k, i, j, k, Jf, i, j, k);
+        double lmx3 = term(m(i, j, k), B.qp(i, j, k, 1), i, j, k - 1, i, j, k, Kf, i, j, k);
+        double lmx4 = term(m(i + 1, j, k), B.qp(i + 1, j, k, 1), i, j, k, i + 1, j, k, If, i + 1, j, k);
+        double lmx5 = term(m(i, j + 1, k), B.qp(i, j + 1, k, 1), i, j, k, i, j + 1, k, Jf, i, j + 1, k);
+        double lmx6 = term(m(i, j, k + 1), B.qp(i, j, k + 1, 1), i, j, k, i, j, k + 1, Kf, i, j, k + 1);
+        double lmxsum = (If.A(i, j, k) * lmx1) + (Jf.A(i, j, k) * lmx2) + (Kf.A(i, j, k) * lmx3) +
+                        (If.A(i + 1, j, k) * lmx4) + (Jf.A(i, j + 1, k) * lmx5) + (Kf.A(i, j, k + 1) * lmx6);
+        lmxsum = B.c.gm * lmxsum / prandtl;
+        lmxsum = 2. / (lmxsum + (2. * CFL * cl.vol(i, j, k) / B.delta_t(i, j, k)));
+        B.delta_t(i, j, k) = CFL * (lmxsum * cl.vol(i, j, k));
+      }
+}
+
+void Block::compute_time_step() {
+  const double gm = c.gm;
+  if (c.time_stepping == 1 && c.global_time_step > 0) {
+    std::fill(delta_t.d.begin(), delta_t.d.end(), c.global_time_step);
+    return;
+  }
+  auto cavg = [gm](const Arr4& l, const Arr4& r, int i, int j, int k) {
+    return 0.5 * (std::sqrt(gm * l(i, j, k, 5) / l(i, j, k, 1)) + std::sqrt(gm * r(i, j, k, 5) / r(i, j, k, 1)));
+  };
+  auto vn = [this](int i, int j, int k, const Rec4& f, int fi, int fj, int fk) {
+    return std::fabs((qp(i, j, k, 2) * f.nx(fi, fj, fk)) + (qp(i, j, k, 3) * f.ny(fi, fj, fk)) + (qp(i, j, k, 4) * f.nz(fi, fj, fk)));
+  };
+  for (int k = 1; k <= kmx - 1; ++k)
+    for (int j = 1; j <= jmx - 1; ++j)
+      for (int i = 1; i <= imx - 1; ++i) {
+        double lmx1 = vn(i, j, k, If, i, j, k) + cavg(xl, xr, i, j, k);
+        double lmx2 = vn(i, j, k, Jf, i, j, k) + cavg(yl, yr, i, j, k);
+        double lmx3 = vn(i, j, k, Kf, i, j, k) + cavg(zl, zr, i, j, k);
+        double lmx4 = vn(i + 1, j, k, If, i + 1, j, k) + cavg(xl, xr, i + 1, j, k);
+        double lmx5 = vn(i, j + 1, k, Jf, i, j + 1, k) + cavg(yl, yr, i, j + 1, k);
+        double lmx6 = vn(i, j, k + 1, Kf, i, j, k + 1) + cavg(zl, zr, i, j, k + 1);
+        double lmxsum = (If.A(i, j, k) * lmx1) + (Jf.A(i, j, k) * lmx2) + (Kf.A(i, j, k) * lmx3) +
+                        (If.A(i + 1, j, k) * lmx4) + (Jf.A(i, j + 1, k) * lmx5) + (Kf.A(i, j, k + 1) * lmx6);
+        double dt = 1. / lmxsum;
+        delta_t(i, j, k) = dt * cells.vol(i, j, k) * c.CFL;
+      }
+  if (c.mu_ref != 0.0) add_diffusive_time(*this, mu, c.Pr);
+  if (c.mu_ref != 0 && c.turbulence != ORC_TURB_NONE) add_diffusive_time(*this, mu_t, c.tPr);
+  if (c.time_stepping == 1) {
+    double m = *std::min_element(delta_t.d.begin(), delta_t.d.end());
+    std::fill(delta_t.d.begin(), delta_t.d.end(), m);
+  }
+}
+
+// update.f90:228-491 update_with, "conservative" branch (:367-485)
+void Block::update_with(double TF, double SF, bool TU, bool have_store) {
+  const Arr4& Quse = have_store ? U_store : qp;
+  const double gm = c.gm;
+  double u1[8], u2[8], R[8];
+  for (int k = 1; k <= kmx - 1; ++k)
+    for (int j = 1; j <= jmx - 1; ++j)
+      for (int i = 1; i <= imx - 1; ++i) {
+        u1[0] = Quse(i, j, k, 1);
+        for (int l = 2; l <= nv; ++l) u1[l - 1] = Quse(i, j, k, l) * u1[0];
+        const double KE = 0.;
+        u1[4] = (u1[4] / (gm - 1.) + 0.5 * (u1[1] * u1[1] + u1[2] * u1[2] + u1[3] * u1[3])) / u1[0] + KE;
+        for (int l = 1; l <= nv; ++l) R[l - 1] = residue(i, j, k, l);
+        if (is_sst(*this)) {
+          double beta = beta1 * F1(i, j, k) + (1. - F1(i, j, k)) * beta2;
+          R[5] = R[5] / (1 + (beta * qp(i, j, k, 7) * delta_t(i, j, k)));
+          R[6] = R[6] / (1 + (2 * beta * qp(i, j, k, 7) * delta_t(i, j, k)));
+        }
+        if (have_store && R_store.size()) {
+          for (int l = 1; l <= nv; ++l) R_store(i, j, k, l) = R_store(i, j, k, l) + SF * R[l - 1];
+          if (TU) for (int l = 1; l <= nv; ++l) R[l - 1] = R_store(i, j, k, l);
+        }
+        const double fac = (TF * delta_t(i, j, k) / cells.vol(i, j, k));
+        for (int l = 0; l < nv; ++l) u2[l] = u1[l] - R[l] * fac;
+        for (int l = 1; l < nv; ++l) u2[l] = u2[l] / u2[0];
+        u2[4] = (gm - 1.) * u2[0] * (u2[4] - (0.5 * (u2[1] * u2[1] + u2[2] * u2[2] + u2[3] * u2[3])) - KE);
+        bool bad = (u2[0] < 0.) || (u2[4] < 0.);
+        for (int l = 0; l < nv; ++l) if (std::isnan(u2[l])) bad = true;
+        if (bad) { error |= 8; continue; }   // reference: Fatal_error (STOP)
+        for (int l = 1; l <= 5; ++l) qp(i, j, k, l) = u2[l - 1];
+        if (is_sst(*this)) {
+          if (u2[5] >= 0.) qp(i, j, k, 6) = u2[5];
+          if (u2[6] >= 0.) qp(i, j, k, 7) = u2[6];
+        }
+      }
+}
+
+// resnorm.f90:136-150 setup_scale, :171-199 get_absolute_resnorm (block-local part)
+void Block::absolute_resnorm() {
+  double scale[9];
+  scale[0] = 1.;
+  scale[1] = c.density_inf * c.vel_mag;
+  scale[2] = scale[3] = scale[4] = c.density_inf * c.vel_mag * c.vel_mag;
+  scale[5] = (0.5 * c.density_inf * (c.vel_mag * c.vel_mag * c.vel_mag) + ((c.gm / (c.gm - 1.)) * c.pressure_inf));
+  if (is_sst(*this)) { scale[6] = c.density_inf * c.vel_mag * c.tk_inf; scale[7] = c.density_inf * c.vel_mag * c.tw_inf; }
+  for (int l = 1; l <= nv; ++l) {
+    double s = 0.;
+    for (int k = 1; k <= kmx - 1; ++k) for (int j = 1; j <= jmx - 1; ++j) for (int i = 1; i <= imx - 1; ++i) { double r = residue(i, j, k, l); s += r * r; }
+    res_abs_local[l] = (s / (scale[l] * scale[l]));
+  }
+  auto psum = [](const Arr4& a, int i0, int i1, int j0, int j1, int k0, int k1) {
+    double s = 0.;
+    for (int k = k0; k <= k1; ++k) for (int j = j0; j <= j1; ++j) for (int i = i0; i <= i1; ++i) s += a(i, j, k, 1);
+    return s;
+  };
+  double merror = (psum(F, 1, 1, 1, jmx - 1, 1, kmx - 1) - psum(F, imx, imx, 1, jmx - 1, 1, kmx - 1)
+                   + psum(G, 1, imx - 1, 1, 1, 1, kmx - 1) - psum(G, 1, imx - 1, jmx, jmx, 1, kmx - 1)
+                   + psum(H, 1, imx - 1, 1, jmx - 1, 1, 1) - psum(H, 1, imx - 1, 1, jmx - 1, kmx, kmx));
+  res_abs_local[0] = (merror / scale[0]);
+}
+
+}  // namespace orc
