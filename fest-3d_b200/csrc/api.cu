@@ -1,0 +1,592 @@
+// C ABI of the device path (include/fest3d_gpu.h): context life cycle, host <-> device layout conversion, the stage
+// sequencing of get_next_solution (src/update.f90:129-226), the halo exchange that replaces apply_interface's
+// MPI_SENDRECVs (src/interface1.f90:96-493) and the norm assembly of find_resnorm (src/resnorm.f90:171-225).
+#include <dlfcn.h>
+#include <algorithm>
+#include <tuple>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include "ctx.hpp"
+
+using namespace f3d;
+
+namespace f3d {
+int upload_records(Ctx* ctx, const double* host, int n0, int n1, int n2, double* field0);
+int residual_grid_ctas(const Layout& L);
+}
+
+// ---- NCCL through dlopen (the library must load on hosts without NCCL; multi-rank entry points fail loudly there) ----
+namespace {
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+struct Nccl {
+  void* h = nullptr;
+  int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  bool load() {
+    if (h) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) { h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+    if (!h) return false;
+#define SYM(f, s) f = (decltype(f))dlsym(h, s); if (!f) return false;
+    SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
+    SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(AllReduce, "ncclAllReduce") SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd")
+#undef SYM
+    return true;
+  }
+} g_nccl;
+constexpr int kNcclFloat64 = 8, kNcclSum = 0;
+}  // namespace
+
+static int fail(Fest3dGpuCtx* ctx, int cls) { if (ctx) ctx->last_error.flags |= cls; return cls; }
+
+extern "C" const char* fest3d_gpu_version(void) { return "fest3d-b200 0.1 (sm_100a)"; }
+
+extern "C" int fest3d_gpu_create(Fest3dGpuCtx** out, const Fest3dGpuConfig* cfg, int device) {
+  if (!out || !cfg) return F3D_ERR_ARGUMENT;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    fprintf(stderr, "fest3d_gpu: no CUDA device available -- this library has no CPU fallback\n");
+    return F3D_ERR_CUDA;
+  }
+  // scope check: only what this path implements; everything else is an explicit error, never a silent fallback
+  const bool sst = cfg->turbulence == F3D_TURB_SST || cfg->turbulence == F3D_TURB_SST2003;
+  if (cfg->turbulence != F3D_TURB_NONE && !sst) return F3D_ERR_UNSUPPORTED;
+  if (cfg->transition != F3D_TRANS_NONE) return F3D_ERR_UNSUPPORTED;
+  if (cfg->time_accuracy >= F3D_T_IMPLICIT || cfg->time_accuracy < 0) return F3D_ERR_UNSUPPORTED;
+  if (cfg->pb_switch[0] || cfg->pb_switch[1] || cfg->pb_switch[2]) return F3D_ERR_UNSUPPORTED;
+  if (cfg->scheme < 0 || cfg->scheme > F3D_SLAU || cfg->interpolant < 0 || cfg->interpolant > F3D_WENO_NM) return F3D_ERR_ARGUMENT;
+  if (cfg->n_var != (sst ? 7 : 5)) return F3D_ERR_ARGUMENT;
+  if (sst && cfg->mu_ref == 0.0) return F3D_ERR_UNSUPPORTED;
+  for (int f = 0; f < 6; ++f) if (cfg->bc_id[f] == -11) return F3D_ERR_UNSUPPORTED;   // total_pressure: next round
+  if (cfg->imx < 2 || cfg->jmx < 2 || cfg->kmx < 2) return F3D_ERR_ARGUMENT;
+
+  Fest3dGpuCtx* ctx = new Fest3dGpuCtx();
+  ctx->cfg = *cfg;
+  ctx->device = device;
+  F3D_CUDA(cudaSetDevice(device));
+  Params& P = ctx->P;
+  memset(&P, 0, sizeof(P));
+  Layout& L = P.L;
+  L.imx = cfg->imx; L.jmx = cfg->jmx; L.kmx = cfg->kmx; L.nv = cfg->n_var; L.ng = sst ? 6 : 4;
+  L.pi = ((cfg->imx + 6 + 15) / 16) * 16; L.pj = cfg->jmx + 6; L.pk = cfg->kmx + 6;
+  L.sj = L.pi; L.sk = (long long)L.pi * L.pj;
+  L.base = 13 + 2 + 2 * L.sj + 2 * L.sk;
+  L.fs = ((13 + L.sk * L.pk + 31) / 32) * 32;
+  P.scheme = cfg->scheme; P.interpolant = cfg->interpolant; P.turbulence = cfg->turbulence;
+  P.time_stepping = cfg->time_stepping; P.mu_variation = cfg->mu_variation;
+  for (int d = 0; d < 3; ++d) { P.limiter[d] = cfg->limiter[d]; P.tlimiter[d] = cfg->tlimiter[d]; }
+  P.ppm_flag = (cfg->interpolant == F3D_PPM || cfg->interpolant == F3D_WENO || cfg->interpolant == F3D_WENO_NM) ? 1 : 0;
+  for (int f = 0; f < 6; ++f) {
+    int id = cfg->bc_id[f];
+    if (cfg->pbc_id[f] >= 0) id = -10;                      // bc.f90:26-31
+    P.bc_id[f] = id;
+    P.phys[f] = (id < 0 && id != -10) ? 1 : 0;
+    P.farlike[f] = (id == -8 || id == -9) ? 1 : 0;
+    if (id == -7) P.ppm_flag = 1;                           // boundary_state_reconstruction.f90:46-47
+  }
+  auto wallish = [](int id) { return id == -5 || id == -6 || id == -7; };
+  for (int d = 0; d < 3; ++d) { P.zlo[d] = wallish(P.bc_id[2 * d]) ? 0.0 : 1.0; P.zhi[d] = wallish(P.bc_id[2 * d + 1]) ? 0.0 : 1.0; }
+  P.c2 = 1 + cfg->accur; P.c3 = 0.5 * cfg->accur; P.c1 = P.c2 - P.c3;
+  P.current_iter = 1;
+  P.viscous = cfg->mu_ref != 0.0; P.sst = sst ? 1 : 0;
+  P.CFL = cfg->CFL; P.global_time_step = cfg->global_time_step;
+  P.gm = cfg->gm; P.R_gas = cfg->R_gas; P.mu_ref = cfg->mu_ref; P.T_ref = cfg->T_ref; P.Sutherland_temp = cfg->Sutherland_temp;
+  P.Pr = cfg->Pr; P.tPr = cfg->tPr;
+  P.density_inf = cfg->density_inf; P.x_speed_inf = cfg->x_speed_inf; P.y_speed_inf = cfg->y_speed_inf; P.z_speed_inf = cfg->z_speed_inf;
+  P.pressure_inf = cfg->pressure_inf; P.tk_inf = cfg->tk_inf; P.tw_inf = cfg->tw_inf; P.MInf = cfg->MInf;
+  const double kappa = 0.41;
+  if (cfg->turbulence == F3D_TURB_SST2003) {   // source.f90:205-211, viscosity.f90:243,251
+    P.gama1 = 5.0 / 9.0; P.gama2 = 0.44; P.cd_floor = 1.0e-10; P.mut_floor = 1.0e-10; P.pk_limiter = 10;
+  } else {                                      // global_sst.f90:15-16
+    P.gama1 = (0.075 / 0.09) - ((0.5 * (kappa * kappa)) / sqrt(0.09));
+    P.gama2 = (0.0828 / 0.09) - ((0.856 * (kappa * kappa)) / sqrt(0.09));
+    P.cd_floor = 1.0e-20; P.mut_floor = 1.e-20; P.pk_limiter = 20;
+  }
+  memcpy(P.fixed, cfg->fixed, sizeof(P.fixed));
+  // Res_scale (resnorm.f90:136-150); slot 0 is the mass imbalance scale (1)
+  double sc[9] = {1, 1, 1, 1, 1, 1, 1, 1, 1};
+  sc[1] = cfg->density_inf * cfg->vel_mag;
+  sc[2] = sc[3] = sc[4] = cfg->density_inf * cfg->vel_mag * cfg->vel_mag;
+  sc[5] = (0.5 * cfg->density_inf * (cfg->vel_mag * cfg->vel_mag * cfg->vel_mag) + ((cfg->gm / (cfg->gm - 1.)) * cfg->pressure_inf));
+  if (sst) { sc[6] = cfg->density_inf * cfg->vel_mag * cfg->tk_inf; sc[7] = cfg->density_inf * cfg->vel_mag * cfg->tw_inf; }
+
+  F3D_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+  ctx->stream = ctx->own_stream;
+  const size_t fb = (size_t)L.fs * sizeof(double);
+  const int nv = L.nv;
+  auto dalloc = [&](double** p, size_t nfields) -> cudaError_t {
+    cudaError_t e = cudaMalloc((void**)p, nfields * fb);
+    if (e == cudaSuccess) e = cudaMemsetAsync(*p, 0, nfields * fb, ctx->stream);
+    return e;
+  };
+  F3D_CUDA(dalloc(&ctx->qp, nv)); F3D_CUDA(dalloc(&ctx->qp2, nv)); F3D_CUDA(dalloc(&ctx->residue, nv));
+  F3D_CUDA(dalloc(&ctx->temp, 1)); F3D_CUDA(dalloc(&ctx->dt, 1)); F3D_CUDA(dalloc(&ctx->geom, G_NFIELDS));
+  if (cfg->time_accuracy != F3D_T_NONE) F3D_CUDA(dalloc(&ctx->ustore, nv));
+  if (cfg->time_accuracy == F3D_T_RK2 || cfg->time_accuracy == F3D_T_RK4) F3D_CUDA(dalloc(&ctx->rstore, nv));
+  if (P.viscous) { F3D_CUDA(dalloc(&ctx->grad, 3 * L.ng)); F3D_CUDA(dalloc(&ctx->mu, 3)); }
+  // staging for the AoS records: the largest face array
+  const size_t rec_max = (size_t)4 * (L.imx + 6) * (L.jmx + 6) * (L.kmx + 6) * sizeof(double);
+  F3D_CUDA(cudaMalloc((void**)&ctx->staging, rec_max));
+  ctx->red_blocks = residual_grid_ctas(L);
+  F3D_CUDA(cudaMalloc((void**)&ctx->red, sizeof(double) * (size_t)std::max(ctx->red_blocks * (nv + 1), 256)));
+  F3D_CUDA(cudaMalloc((void**)&ctx->norms_dev, sizeof(double) * (1024 + 64)));
+  F3D_CUDA(cudaMemcpyAsync(ctx->norms_dev + 1024, sc, sizeof(double) * 9, cudaMemcpyHostToDevice, ctx->stream));
+  F3D_CUDA(cudaMallocHost((void**)&ctx->norms_host, sizeof(double) * 1024));
+  F3D_CUDA(cudaMalloc((void**)&ctx->err_dev, sizeof(int) * 4));
+  F3D_CUDA(cudaMemsetAsync(ctx->err_dev, 0, sizeof(int) * 4, ctx->stream));
+  F3D_CUDA(cudaMallocHost((void**)&ctx->err_host, sizeof(int) * 4));
+  // ghost-gradient face records
+  if (P.viscous) {
+    size_t tot = 0;
+    const int mx[3] = {L.imx, L.jmx, L.kmx};
+    for (int f = 0; f < 6; ++f) {
+      const int ax = f / 2, a_ax = (ax == 0) ? 1 : 0, b_ax = (ax == 2) ? 1 : 2;
+      ctx->gbc_off[f] = (long long)tot;
+      tot += (size_t)4 * (mx[a_ax] - 1) * (mx[b_ax] - 1);
+    }
+    F3D_CUDA(cudaMalloc((void**)&ctx->gbc, tot * sizeof(double)));
+  }
+  // halo buffers for interface faces
+  {
+    const int mx[3] = {L.imx, L.jmx, L.kmx};
+    for (int f = 0; f < 6; ++f) {
+      if (!(cfg->bc_id[f] >= 0 || cfg->pbc_id[f] >= 0)) continue;
+      const int ax = f / 2, a_ax = (ax == 0) ? 1 : 0, b_ax = (ax == 2) ? 1 : 2;
+      ctx->buf_elems[f] = (size_t)(mx[a_ax] - 1) * (mx[b_ax] - 1) * 3 * nv;
+      F3D_CUDA(cudaMalloc((void**)&ctx->sendbuf[f], ctx->buf_elems[f] * sizeof(double)));
+      F3D_CUDA(cudaMalloc((void**)&ctx->recvbuf[f], ctx->buf_elems[f] * sizeof(double)));
+      ctx->link[f].neighbour_block = cfg->bc_id[f] >= 0 ? cfg->bc_id[f] : cfg->pbc_id[f];
+    }
+  }
+  F3D_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->last_error.block_id = cfg->block_id;
+  *out = ctx;
+  return 0;
+}
+
+extern "C" int fest3d_gpu_destroy(Fest3dGpuCtx* ctx) {
+  if (!ctx) return F3D_ERR_ARGUMENT;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  double* bufs[] = {ctx->qp, ctx->qp2, ctx->ustore, ctx->rstore, ctx->residue, ctx->temp, ctx->dt, ctx->geom, ctx->grad, ctx->mu, ctx->gbc,
+                    ctx->red, ctx->norms_dev, ctx->staging};
+  for (double* b : bufs) if (b) cudaFree(b);
+  for (int f = 0; f < 6; ++f) { if (ctx->sendbuf[f]) cudaFree(ctx->sendbuf[f]); if (ctx->recvbuf[f]) cudaFree(ctx->recvbuf[f]); }
+  if (ctx->err_dev) cudaFree(ctx->err_dev);
+  if (ctx->norms_host) cudaFreeHost(ctx->norms_host);
+  if (ctx->err_host) cudaFreeHost(ctx->err_host);
+  for (auto& e : ctx->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  if (ctx->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)ctx->nccl);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+  return 0;
+}
+
+extern "C" int fest3d_gpu_set_stream(Fest3dGpuCtx* ctx, void* s) {
+  if (!ctx) return F3D_ERR_ARGUMENT;
+  ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+  return 0;
+}
+
+extern "C" int fest3d_gpu_sync(Fest3dGpuCtx* ctx) {
+  if (!ctx) return F3D_ERR_ARGUMENT;
+  F3D_CUDA(cudaSetDevice(ctx->device));
+  F3D_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// host (reference layout) <-> device (padded SoA) copies of cell-shaped arrays: one strided 3-D copy per variable
+static int copy_cells(Fest3dGpuCtx* ctx, double* dev_field, double* host, int nfields, bool to_device, int lo, int e0, int e1, int e2) {
+  const Layout& L = ctx->P.L;
+  for (int v = 0; v < nfields; ++v) {
+    cudaMemcpy3DParms p;
+    memset(&p, 0, sizeof(p));
+    double* d = dev_field + (long long)v * L.fs + L.idx(lo, lo, lo);
+    double* h = host + (size_t)v * e0 * e1 * e2;
+    cudaPitchedPtr dp = make_cudaPitchedPtr(d, (size_t)L.sj * sizeof(double), L.sj, L.pj);
+    cudaPitchedPtr hp = make_cudaPitchedPtr(h, (size_t)e0 * sizeof(double), e0, e1);
+    p.srcPtr = to_device ? hp : dp;
+    p.dstPtr = to_device ? dp : hp;
+    p.extent = make_cudaExtent((size_t)e0 * sizeof(double), e1, e2);
+    p.kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    F3D_CUDA(cudaMemcpy3DAsync(&p, ctx->stream));
+  }
+  return 0;
+}
+
+extern "C" int fest3d_gpu_set_geometry(Fest3dGpuCtx* ctx, const double* cells, const double* Ifaces, const double* Jfaces,
+                                       const double* Kfaces, const double* dist) {
+  if (!ctx || !cells || !Ifaces || !Jfaces || !Kfaces) return fail(ctx, F3D_ERR_ARGUMENT);
+  if (ctx->P.sst && !dist) return fail(ctx, F3D_ERR_ARGUMENT);
+  F3D_CUDA(cudaSetDevice(ctx->device));
+  const Layout& L = ctx->P.L;
+  const long long fs = L.fs;
+  int rc;
+  if ((rc = upload_records(ctx, cells, L.imx + 5, L.jmx + 5, L.kmx + 5, ctx->geom + (long long)G_VOL * fs))) return rc;
+  if ((rc = upload_records(ctx, Ifaces, L.imx + 6, L.jmx + 5, L.kmx + 5, ctx->geom + (long long)G_IA * fs))) return rc;
+  if ((rc = upload_records(ctx, Jfaces, L.imx + 5, L.jmx + 6, L.kmx + 5, ctx->geom + (long long)G_JA * fs))) return rc;
+  if ((rc = upload_records(ctx, Kfaces, L.imx + 5, L.jmx + 5, L.kmx + 6, ctx->geom + (long long)G_KA * fs))) return rc;
+  if (dist) {
+    if ((rc = copy_cells(ctx, ctx->geom + (long long)G_DIST * fs, const_cast<double*>(dist), 1, true, -2, L.imx + 5, L.jmx + 5, L.kmx + 5))) return rc;
+  }
+  if (ctx->P.viscous) {
+    // mu = mu_ref everywhere (viscosity.f90:527); face records for the ghost-gradient rule.  The reference passes
+    // Jfaces / Kfaces to a dummy declared with the Ifaces shape (gradients.f90:549-612): element (i,j,k) is then read at
+    // record offset (i+2) + (imx+6)*((j+2) + (jmx+5)*(k+2)) of the actual array.  Reproduced here on the host, once.
+    std::vector<double> mu0((size_t)fs, ctx->cfg.mu_ref);
+    F3D_CUDA(cudaMemcpyAsync(ctx->mu, mu0.data(), fs * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    F3D_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int mx[3] = {L.imx, L.jmx, L.kmx};
+    const double* arrs[3] = {Ifaces, Jfaces, Kfaces};
+    std::vector<double> rec;
+    for (int f = 0; f < 6; ++f) {
+      const int ax = f / 2, a_ax = (ax == 0) ? 1 : 0, b_ax = (ax == 2) ? 1 : 2;
+      const int na = mx[a_ax] - 1, nb = mx[b_ax] - 1;
+      rec.resize((size_t)4 * na * nb);
+      for (int b = 0; b < nb; ++b)
+        for (int a = 0; a < na; ++a) {
+          int idx[3]; idx[a_ax] = a + 1; idx[b_ax] = b + 1; idx[ax] = (f % 2 == 0) ? 1 : mx[ax];
+          const size_t off = (size_t)(idx[0] + 2) + (size_t)(L.imx + 6) * ((size_t)(idx[1] + 2) + (size_t)(L.jmx + 5) * (size_t)(idx[2] + 2));
+          memcpy(&rec[4 * ((size_t)b * na + a)], arrs[ax] + 4 * off, 4 * sizeof(double));
+        }
+      F3D_CUDA(cudaMemcpy(ctx->gbc + ctx->gbc_off[f], rec.data(), rec.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+  }
+  F3D_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->geometry_set = true;
+  return 0;
+}
+
+extern "C" int fest3d_gpu_set_state(Fest3dGpuCtx* ctx, const double* qp) {
+  if (!ctx || !qp) return fail(ctx, F3D_ERR_ARGUMENT);
+  F3D_CUDA(cudaSetDevice(ctx->device));
+  const Layout& L = ctx->P.L;
+  int rc = copy_cells(ctx, ctx->qp, const_cast<double*>(qp), L.nv, true, -2, L.imx + 5, L.jmx + 5, L.kmx + 5);
+  if (rc) return rc;
+  F3D_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->state_set = true;
+  return 0;
+}
+
+extern "C" int fest3d_gpu_get_state(Fest3dGpuCtx* ctx, double* qp) {
+  if (!ctx || !qp) return fail(ctx, F3D_ERR_ARGUMENT);
+  F3D_CUDA(cudaSetDevice(ctx->device));
+  const Layout& L = ctx->P.L;
+  int rc = copy_cells(ctx, ctx->qp, qp, L.nv, false, -2, L.imx + 5, L.jmx + 5, L.kmx + 5);
+  if (rc) return rc;
+  F3D_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int fest3d_gpu_get_residue(Fest3dGpuCtx* ctx, double* out) {
+  if (!ctx || !out) return fail(ctx, F3D_ERR_ARGUMENT);
+  F3D_CUDA(cudaSetDevice(ctx->device));
+  const Layout& L = ctx->P.L;
+  int rc = copy_cells(ctx, ctx->residue, out, L.nv, false, 1, L.imx - 1, L.jmx - 1, L.kmx - 1);
+  if (rc) return rc;
+  F3D_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int fest3d_gpu_get_aux(Fest3dGpuCtx* ctx, int which, double* out) {
+  if (!ctx || !out) return fail(ctx, F3D_ERR_ARGUMENT);
+  F3D_CUDA(cudaSetDevice(ctx->device));
+  const Layout& L = ctx->P.L;
+  int rc = F3D_ERR_ARGUMENT;
+  if (which == 0) rc = copy_cells(ctx, ctx->dt, out, 1, false, 1, L.imx - 1, L.jmx - 1, L.kmx - 1);
+  else if (which >= 1 && which <= 3 && ctx->mu) rc = copy_cells(ctx, ctx->mu + (long long)(which - 1) * L.fs, out, 1, false, -2, L.imx + 5, L.jmx + 5, L.kmx + 5);
+  else if (which == 4) rc = copy_cells(ctx, ctx->temp, out, 1, false, -2, L.imx + 5, L.jmx + 5, L.kmx + 5);
+  else if (which >= 30 && which <= 32 && ctx->grad) {
+    // gradqp_d(0:imx,0:jmx,0:kmx,1:n_grad): component c of direction d lives in field 3*c+d
+    const int d = which - 30;
+    rc = 0;
+    for (int c = 0; c < L.ng && !rc; ++c)
+      rc = copy_cells(ctx, ctx->grad + (long long)(3 * c + d) * L.fs, out + (size_t)c * (L.imx + 1) * (L.jmx + 1) * (L.kmx + 1), 1, false, 0, L.imx + 1, L.jmx + 1, L.kmx + 1);
+  }
+  if (rc) return fail(ctx, rc);
+  F3D_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int fest3d_gpu_error(Fest3dGpuCtx* ctx, Fest3dGpuError* info) {
+  if (!ctx || !info) return F3D_ERR_ARGUMENT;
+  *info = ctx->last_error;
+  return 0;
+}
+
+extern "C" long long fest3d_gpu_launch_count(Fest3dGpuCtx* ctx) { return ctx ? ctx->launches : -1; }
+
+extern "C" int fest3d_gpu_kernel_timing(Fest3dGpuCtx* ctx, int enable) {
+  if (!ctx) return F3D_ERR_ARGUMENT;
+  ctx->timing = enable;
+  return 0;
+}
+
+extern "C" double fest3d_gpu_kernel_time_ms(Fest3dGpuCtx* ctx, long long* n, int reset) {
+  if (!ctx) return -1.0;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (size_t e = 0; e < ctx->ev_used; ++e) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev_pool[e].first, ctx->ev_pool[e].second) == cudaSuccess) { ctx->ktime_ms += ms; ctx->ktime_n++; }
+  }
+  ctx->ev_used = 0;
+  const double t = ctx->ktime_ms;
+  if (n) *n = ctx->ktime_n;
+  if (reset) { ctx->ktime_ms = 0.0; ctx->ktime_n = 0; }
+  return t;
+}
+
+// ---- multi-block plumbing -------------------------------------------------------------------------------------------
+extern "C" int fest3d_gpu_comm_unique_id(char id_out[128]) {
+  if (!g_nccl.load()) { fprintf(stderr, "fest3d_gpu: libnccl.so.2 not found\n"); return F3D_ERR_UNSUPPORTED; }
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != 0) return F3D_ERR_CUDA;
+  memcpy(id_out, id.internal, 128);
+  return 0;
+}
+
+extern "C" int fest3d_gpu_comm_init(Fest3dGpuCtx* ctx, int n_ranks, int rank, const char id[128], const int* block_to_rank) {
+  if (!ctx || !id || !block_to_rank) return fail(ctx, F3D_ERR_ARGUMENT);
+  if (!g_nccl.load()) { fprintf(stderr, "fest3d_gpu: libnccl.so.2 not found\n"); return fail(ctx, F3D_ERR_UNSUPPORTED); }
+  F3D_CUDA(cudaSetDevice(ctx->device));
+  ncclUniqueId uid;
+  memcpy(uid.internal, id, 128);
+  ncclComm_t comm;
+  if (g_nccl.CommInitRank(&comm, n_ranks, uid, rank) != 0) return fail(ctx, F3D_ERR_CUDA);
+  ctx->nccl = comm; ctx->n_ranks = n_ranks; ctx->rank = rank;
+  ctx->block_to_rank.assign(block_to_rank, block_to_rank + ctx->cfg.n_blocks);
+  for (int f = 0; f < 6; ++f) {
+    Link& lk = ctx->link[f];
+    if (lk.neighbour_block < 0 || lk.kind == 1) continue;
+    lk.rank = ctx->block_to_rank[lk.neighbour_block];
+    lk.kind = 2;
+  }
+  return 0;
+}
+
+extern "C" int fest3d_gpu_link_local(Fest3dGpuCtx* a, Fest3dGpuCtx* b) {
+  if (!a || !b) return F3D_ERR_ARGUMENT;
+  int n = 0;
+  for (int f = 0; f < 6; ++f) {
+    if (a->link[f].neighbour_block == b->cfg.block_id) { a->link[f].kind = 1; a->link[f].peer = b; ++n; }
+    if (b->link[f].neighbour_block == a->cfg.block_id) { b->link[f].kind = 1; b->link[f].peer = a; ++n; }
+  }
+  return n ? 0 : F3D_ERR_ARGUMENT;
+}
+
+namespace {
+
+struct Msg { int peer_rank, block, face; Fest3dGpuCtx* ctx; int my_face; };
+
+// apply_interface for every context of this process (interface1.f90:96-493)
+int exchange(Fest3dGpuCtx** cs, int n) {
+  bool any = false;
+  for (int c = 0; c < n; ++c)
+    for (int f = 0; f < 6; ++f)
+      if (cs[c]->sendbuf[f] && cs[c]->link[f].kind != 0) {
+        cudaSetDevice(cs[c]->device);
+        int rc = launch_pack(cs[c], f + 1);
+        if (rc) return rc;
+        any = true;
+      }
+  if (!any) return 0;
+  // remote messages over NCCL, posted in a canonical order per peer so that sends and receives pair up
+  std::vector<Msg> sends, recvs;
+  for (int c = 0; c < n; ++c)
+    for (int f = 0; f < 6; ++f) {
+      const Link& lk = cs[c]->link[f];
+      if (lk.kind != 2) continue;
+      sends.push_back({lk.rank, cs[c]->cfg.block_id, f + 1, cs[c], f + 1});
+      recvs.push_back({lk.rank, lk.neighbour_block, cs[c]->cfg.otherface[f], cs[c], f + 1});
+    }
+  if (!sends.empty()) {
+    auto key = [](const Msg& a, const Msg& b) { return std::tie(a.peer_rank, a.block, a.face) < std::tie(b.peer_rank, b.block, b.face); };
+    std::sort(sends.begin(), sends.end(), key);
+    std::sort(recvs.begin(), recvs.end(), key);
+    g_nccl.GroupStart();
+    for (const Msg& m : sends) {
+      cudaSetDevice(m.ctx->device);
+      g_nccl.Send(m.ctx->sendbuf[m.my_face - 1], m.ctx->buf_elems[m.my_face - 1], kNcclFloat64, m.peer_rank, (ncclComm_t)m.ctx->nccl, m.ctx->stream);
+    }
+    for (const Msg& m : recvs) {
+      cudaSetDevice(m.ctx->device);
+      g_nccl.Recv(m.ctx->recvbuf[m.my_face - 1], m.ctx->buf_elems[m.my_face - 1], kNcclFloat64, m.peer_rank, (ncclComm_t)m.ctx->nccl, m.ctx->stream);
+    }
+    if (g_nccl.GroupEnd() != 0) return F3D_ERR_CUDA;
+  }
+  // local links: make every packing visible, then read the peer's send buffer directly
+  bool local = false;
+  for (int c = 0; c < n; ++c) for (int f = 0; f < 6; ++f) local |= cs[c]->link[f].kind == 1;
+  if (local) for (int c = 0; c < n; ++c) { cudaSetDevice(cs[c]->device); cudaStreamSynchronize(cs[c]->stream); }
+  for (int c = 0; c < n; ++c)
+    for (int f = 0; f < 6; ++f) {
+      const Link& lk = cs[c]->link[f];
+      if (lk.kind == 0) continue;
+      cudaSetDevice(cs[c]->device);
+      const double* src = cs[c]->recvbuf[f];
+      if (lk.kind == 1) {
+        const int of = cs[c]->cfg.otherface[f];
+        const double* peer_buf = lk.peer->sendbuf[of - 1];
+        if (lk.peer->device != cs[c]->device) {
+          cudaMemcpyPeerAsync(cs[c]->recvbuf[f], cs[c]->device, peer_buf, lk.peer->device, cs[c]->buf_elems[f] * sizeof(double), cs[c]->stream);
+        } else {
+          src = peer_buf;
+        }
+      }
+      int rc = launch_unpack(cs[c], f + 1, src);
+      if (rc) return rc;
+    }
+  if (local) for (int c = 0; c < n; ++c) { cudaSetDevice(cs[c]->device); cudaStreamSynchronize(cs[c]->stream); }
+  return 0;
+}
+
+// one get_total_conservative_Residue (+ update) on every context
+int stage(Fest3dGpuCtx** cs, int n, bool update, double TF, double SF, int use_sum, int first, int last) {
+  int rc = exchange(cs, n);
+  if (rc) return rc;
+  for (int c = 0; c < n; ++c) {
+    Fest3dGpuCtx* ctx = cs[c];
+    F3D_CUDA(cudaSetDevice(ctx->device));
+    if ((rc = launch_bc(ctx))) return rc;
+    if (ctx->P.viscous && (rc = launch_gradients(ctx))) return rc;
+    if (!update) {
+      if ((rc = launch_residual(ctx, MODE_RESIDUE_ONLY, 1.0, 1.0, 0, 1, 0))) return rc;
+      continue;
+    }
+    const bool global_min = first && ctx->P.time_stepping == 1 && !(ctx->P.global_time_step > 0);
+    int fst = first;
+    if (global_min) {   // delta_t = minval(delta_t) needs the whole field before any cell is updated (time.f90:286)
+      if ((rc = launch_residual(ctx, MODE_RESIDUE_ONLY, 1.0, 1.0, 0, 1, 0))) return rc;
+      if ((rc = launch_global_dt(ctx))) return rc;
+      fst = 0;
+    }
+    if ((rc = launch_residual(ctx, MODE_UPDATE, TF, SF, use_sum, fst, last))) return rc;
+    if ((rc = launch_ghost_shell_copy(ctx, ctx->qp2, ctx->qp))) return rc;
+    std::swap(ctx->qp, ctx->qp2);
+  }
+  return 0;
+}
+
+int check_errors(Fest3dGpuCtx* ctx) {
+  F3D_CUDA(cudaSetDevice(ctx->device));
+  F3D_CUDA(cudaMemcpyAsync(ctx->err_host, ctx->err_dev, sizeof(int) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  F3D_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ctx->err_host[0]) {
+    ctx->last_error.flags |= ctx->err_host[0];
+    ctx->last_error.i = ctx->err_host[1]; ctx->last_error.j = ctx->err_host[2]; ctx->last_error.k = ctx->err_host[3];
+    return ctx->err_host[0];
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int fest3d_gpu_residual_group(Fest3dGpuCtx** cs, int n, int current_iter) {
+  if (!cs || n < 1) return F3D_ERR_ARGUMENT;
+  for (int c = 0; c < n; ++c) {
+    Fest3dGpuCtx* ctx = cs[c];
+    if (!ctx->geometry_set || !ctx->state_set) return fail(ctx, F3D_ERR_ARGUMENT);
+    F3D_CUDA(cudaSetDevice(ctx->device));
+    ctx->P.current_iter = current_iter;
+    int rc = launch_temp(ctx);
+    if (rc) return rc;
+  }
+  int rc = stage(cs, n, false, 1.0, 1.0, 0, 1, 0);
+  if (rc) return rc;
+  int e = 0;
+  for (int c = 0; c < n; ++c) e |= check_errors(cs[c]);
+  return e;
+}
+
+extern "C" int fest3d_gpu_residual(Fest3dGpuCtx* ctx, int current_iter, double* residue_out) {
+  if (!ctx) return F3D_ERR_ARGUMENT;
+  Fest3dGpuCtx* one[1] = {ctx};
+  int rc = fest3d_gpu_residual_group(one, 1, current_iter);
+  if (residue_out) { int r2 = fest3d_gpu_get_residue(ctx, residue_out); if (r2) return r2; }
+  return rc;
+}
+
+extern "C" int fest3d_gpu_step_group(Fest3dGpuCtx** cs, int n, int current_iter, int n_iters, double* res_abs_out) {
+  if (!cs || n < 1 || n_iters < 1) return F3D_ERR_ARGUMENT;
+  const int nvp1 = cs[0]->P.L.nv + 1;
+  const int ta = cs[0]->cfg.time_accuracy;
+  for (int c = 0; c < n; ++c) if (!cs[c]->geometry_set || !cs[c]->state_set || cs[c]->cfg.time_accuracy != ta) return fail(cs[c], F3D_ERR_ARGUMENT);
+  const int chunk = 1024 / nvp1;
+  int rc = 0;
+  for (int it0 = 0; it0 < n_iters; it0 += chunk) {
+    const int nit = std::min(chunk, n_iters - it0);
+    for (int it = 0; it < nit; ++it) {
+      for (int c = 0; c < n; ++c) {
+        Fest3dGpuCtx* ctx = cs[c];
+        F3D_CUDA(cudaSetDevice(ctx->device));
+        ctx->P.current_iter = current_iter + it0 + it;
+        if ((rc = launch_temp(ctx))) return rc;   // update.f90:170
+        if (ta != F3D_T_NONE && (rc = launch_copy_fields(ctx, ctx->ustore, ctx->qp, ctx->P.L.nv))) return rc;       // U_store = qp
+        if ((ta == F3D_T_RK2 || ta == F3D_T_RK4) && (rc = launch_zero_fields(ctx, ctx->rstore, ctx->P.L.nv))) return rc;  // R_store = 0
+      }
+      auto blend_all = [&](double a, double b) { for (int c = 0; c < n && !rc; ++c) { cudaSetDevice(cs[c]->device); rc = launch_blend(cs[c], a, b); } return rc; };
+      switch (ta) {   // update.f90:171-215
+        case F3D_T_NONE:
+          rc = stage(cs, n, true, 1., 1., 0, 1, 1); break;
+        case F3D_T_RK4:
+          if ((rc = stage(cs, n, true, 0.5, 1., 0, 1, 0))) break;
+          if ((rc = stage(cs, n, true, 0.5, 2., 0, 0, 0))) break;
+          if ((rc = stage(cs, n, true, 1.0, 2., 0, 0, 0))) break;
+          rc = stage(cs, n, true, 1. / 6., 1., 1, 0, 1); break;
+        case F3D_T_RK2:
+          if ((rc = stage(cs, n, true, 0.5, 1., 0, 1, 0))) break;
+          rc = stage(cs, n, true, 0.5, 1., 1, 0, 1); break;
+        case F3D_T_TVDRK3:
+          if ((rc = stage(cs, n, true, 1.0, 1., 0, 1, 0))) break;
+          if ((rc = stage(cs, n, true, 1.0, 1., 0, 0, 0))) break;
+          if ((rc = blend_all(0.75, 0.25))) break;
+          if ((rc = stage(cs, n, true, 1.0, 1., 0, 0, 1))) break;
+          rc = blend_all((1. / 3.), (2. / 3.)); break;
+        case F3D_T_TVDRK2:
+          if ((rc = stage(cs, n, true, 1.0, 1., 0, 1, 0))) break;
+          if ((rc = stage(cs, n, true, 1.0, 1., 0, 0, 1))) break;
+          rc = blend_all(0.5, 0.5); break;
+        default: rc = F3D_ERR_UNSUPPORTED;
+      }
+      if (rc) return rc;
+      for (int c = 0; c < n; ++c) { cudaSetDevice(cs[c]->device); if ((rc = launch_norms(cs[c], it))) return rc; }
+    }
+    // find_resnorm: sum over all blocks (MPI_ALLGATHER + sum, resnorm.f90:201-225), then sqrt / abs
+    for (int c = 0; c < n; ++c) {
+      Fest3dGpuCtx* ctx = cs[c];
+      F3D_CUDA(cudaSetDevice(ctx->device));
+      if (ctx->nccl && ctx->n_ranks > 1) {
+        if (g_nccl.AllReduce(ctx->norms_dev, ctx->norms_dev, (size_t)nit * nvp1, kNcclFloat64, kNcclSum, (ncclComm_t)ctx->nccl, ctx->stream) != 0) return fail(ctx, F3D_ERR_CUDA);
+      }
+      if (res_abs_out) F3D_CUDA(cudaMemcpyAsync(ctx->norms_host, ctx->norms_dev, sizeof(double) * nit * nvp1, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    int e = 0;
+    for (int c = 0; c < n; ++c) e |= check_errors(cs[c]);   // also synchronises the stream
+    if (res_abs_out) {
+      for (int it = 0; it < nit; ++it)
+        for (int l = 0; l < nvp1; ++l) {
+          double s = 0.0;
+          for (int c = 0; c < n; ++c) s = s + cs[c]->norms_host[it * nvp1 + l];
+          res_abs_out[(size_t)(it0 + it) * nvp1 + l] = (l == 0) ? fabs(s) : sqrt(s);
+        }
+    }
+    if (e) return e;
+  }
+  return 0;
+}
+
+extern "C" int fest3d_gpu_step(Fest3dGpuCtx* ctx, int current_iter, int n_iters, double* res_abs_out) {
+  if (!ctx) return F3D_ERR_ARGUMENT;
+  Fest3dGpuCtx* one[1] = {ctx};
+  return fest3d_gpu_step_group(one, 1, current_iter, n_iters, res_abs_out);
+}

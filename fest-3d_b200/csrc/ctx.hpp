@@ -1,0 +1,126 @@
+// Internal device context of one block.  HBM layout: every field (primitive variable, metric, work array) is one
+// padded scalar array of FS doubles with the SAME strides, so cell (i,j,k) and face (i,j,k) of any direction share
+// one linear index:  idx = base + i + sj*j + sk*k   (Fortran indices, i fastest -- the reference's qp(i,j,k,n) is
+// already variable-major, src/vartypes.f90:21-26).  Row pitch sj is a multiple of 16 doubles and the allocation is
+// shifted by 13 doubles so that interior cell i=1 of every row starts a 128-byte line.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <vector>
+#include "../../include/fest3d_gpu.h"
+
+namespace f3d {
+
+struct Layout {
+  int imx, jmx, kmx, nv, ng;        // ng = number of gradient components (4 or 6)
+  int pi, pj, pk;                   // padded extents
+  long long sj, sk, base, fs;       // strides, index of cell (0,0,0), doubles per field
+  __host__ __device__ inline long long idx(int i, int j, int k) const { return base + i + sj * j + sk * (long long)k; }
+};
+
+// geometry field order inside Ctx::geom
+enum { G_VOL = 0, G_CX, G_CY, G_CZ, G_IA, G_INX, G_INY, G_INZ, G_JA, G_JNX, G_JNY, G_JNZ, G_KA, G_KNX, G_KNY, G_KNZ, G_DIST, G_NFIELDS };
+
+// parameters every kernel needs, passed by value (fits the 4 KB kernel-parameter space comfortably)
+struct Params {
+  Layout L;
+  int scheme, interpolant, turbulence, time_stepping, mu_variation;
+  int limiter[3], tlimiter[3];
+  int bc_id[6];
+  int phys[6];            // 1 when the face is a physical boundary that gets the boundary-state override (id<0 && id!=-10)
+  int farlike[6];         // 1 when id is -8 or -9 (face state = ghost value)
+  int ppm_flag;           // boundary re-reconstruction active (ppm / weno / weno_NM or a pole face)
+  int current_iter;
+  int viscous, sst;
+  double zlo[3], zhi[3];  // make_{F,G,H}_flux_zero at the first / last face of each direction (bc.f90:53-66)
+  double c1, c2, c3;
+  double CFL, global_time_step;
+  double gm, R_gas, mu_ref, T_ref, Sutherland_temp, Pr, tPr;
+  double density_inf, x_speed_inf, y_speed_inf, z_speed_inf, pressure_inf, tk_inf, tw_inf, MInf;
+  double gama1, gama2, cd_floor, mut_floor, pk_limiter;
+  double fixed[F3D_NFIX][6];
+  double res_scale[8];    // Res_scale(1:n_var) (resnorm.f90:136-150)
+};
+
+struct Link {             // what sits behind an interface face
+  int kind = 0;           // 0 none, 1 local context (same process), 2 remote rank (NCCL)
+  struct Ctx* peer = nullptr;
+  int rank = -1;
+  int neighbour_block = -1;
+};
+
+struct Ctx {
+  Fest3dGpuConfig cfg;
+  Params P;
+  int device = 0;
+  cudaStream_t stream = nullptr, own_stream = nullptr, comm_stream = nullptr;
+  // device memory
+  double* qp = nullptr;       // nv fields (current state)
+  double* qp2 = nullptr;      // nv fields (next state of the fused update; swapped with qp)
+  double* ustore = nullptr;   // nv fields
+  double* rstore = nullptr;   // nv fields
+  double* residue = nullptr;  // nv fields
+  double* temp = nullptr;     // 1 field
+  double* dt = nullptr;       // 1 field
+  double* geom = nullptr;     // G_NFIELDS fields
+  double* grad = nullptr;     // 3*ng fields: component c, direction d -> field 3*c+d
+  double* mu = nullptr;       // mu, mu_t, F1 (3 fields)
+  double* gbc = nullptr;      // per-face (A,nx,ny,nz) records the ghost-gradient rule reads (mis-indexed for J/K faces)
+  long long gbc_off[6];
+  double* red = nullptr;      // reduction partials
+  int red_blocks = 0;
+  double* norms_dev = nullptr;   // (nv+1) per iteration slot
+  double* norms_host = nullptr;  // pinned
+  int* err_dev = nullptr;        // sticky error word + first offending cell
+  int* err_host = nullptr;
+  double* sendbuf[6] = {nullptr};
+  double* recvbuf[6] = {nullptr};
+  size_t buf_elems[6] = {0};
+  double* staging = nullptr;     // host<->device staging for AoS geometry upload
+  Link link[6];
+  void* nccl = nullptr;          // ncclComm_t
+  int n_ranks = 1, rank = 0;
+  std::vector<int> block_to_rank;
+  // instrumentation
+  long long launches = 0;
+  int timing = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+  size_t ev_used = 0;
+  double ktime_ms = 0.0;
+  long long ktime_n = 0;
+  Fest3dGpuError last_error{};
+  bool geometry_set = false, state_set = false;
+};
+
+#define F3D_CUDA(call)                                                                       \
+  do {                                                                                       \
+    cudaError_t e_ = (call);                                                                 \
+    if (e_ != cudaSuccess) {                                                                 \
+      ctx->last_error.flags |= F3D_ERR_CUDA;                                                 \
+      ctx->last_error.cuda_error = (int)e_;                                                  \
+      fprintf(stderr, "fest3d_gpu: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return F3D_ERR_CUDA;                                                                   \
+    }                                                                                        \
+  } while (0)
+
+// kernel launchers (each returns a CUDA error code through the context)
+int launch_temp(Ctx* ctx);
+int launch_bc(Ctx* ctx);
+int launch_gradients(Ctx* ctx);
+int launch_residual(Ctx* ctx, int mode, double TF, double SF, int use_store_sum, int first_stage, int last_stage);
+int launch_blend(Ctx* ctx, double a, double b);
+int launch_copy_fields(Ctx* ctx, double* dst, const double* src, int nfields);
+int launch_zero_fields(Ctx* ctx, double* dst, int nfields);
+int launch_norms(Ctx* ctx, int slot);
+int launch_pack(Ctx* ctx, int face);
+int launch_unpack(Ctx* ctx, int face, const double* buf);
+int launch_global_dt(Ctx* ctx);
+int launch_ghost_shell_copy(Ctx* ctx, double* dst, const double* src);
+
+// residual modes
+enum { MODE_RESIDUE_ONLY = 0, MODE_UPDATE = 1 };
+
+}  // namespace f3d
+
+struct Fest3dGpuCtx : f3d::Ctx {};

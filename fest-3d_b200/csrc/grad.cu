@@ -1,0 +1,157 @@
+// Green-Gauss cell gradients of (u,v,w,T[,k,omega]) on cells 0..imx x 0..jmx x 0..kmx fused with the molecular
+// (Sutherland) and eddy viscosity / SST blending function F1 of the same cell, then the ghost-gradient rule and the
+// ghost mu_t / F1 copies on physical faces.
+//
+// Reference: src/gradients.f90:276-402 (evaluate_all_gradients), :405-482 (compute_gradient_G), :486-676
+// (apply_gradient_bc, incl. the Ifaces-shaped dummy that mis-indexes Jfaces/Kfaces -- those records are gathered on the
+// host into ctx->gbc with the reference's linear offset); src/viscosity.f90:109-138 (Sutherland), :343-388 (sst),
+// :215-263 (sst2003), :408-465 (ghost mu_t / F1).
+#include "ctx.hpp"
+#include "physics.cuh"
+
+namespace f3d {
+
+template <int NG>
+__global__ void __launch_bounds__(128) k_gradients(const Params P, const double* __restrict__ q, const double* __restrict__ temp,
+                                                   const double* __restrict__ geom, double* __restrict__ grad, double* __restrict__ mu3, int* err) {
+  const Layout& L = P.L;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int k = blockIdx.z;
+  if (i > L.imx || j > L.jmx) return;
+  const long long fs = L.fs, c = L.idx(i, j, k), sj = L.sj, sk = L.sk;
+  const double* gI = geom + (long long)G_IA * fs;
+  const double* gJ = geom + (long long)G_JA * fs;
+  const double* gK = geom + (long long)G_KA * fs;
+  // face area vectors n*A of the six faces, per direction component
+  double wlo[3][3], whi[3][3];   // [face dir][component]
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    wlo[0][d] = gI[(1 + d) * fs + c]; whi[0][d] = gI[(1 + d) * fs + c + 1];
+    wlo[1][d] = gJ[(1 + d) * fs + c]; whi[1][d] = gJ[(1 + d) * fs + c + sj];
+    wlo[2][d] = gK[(1 + d) * fs + c]; whi[2][d] = gK[(1 + d) * fs + c + sk];
+  }
+  const double AIl = gI[c], AIh = gI[c + 1], AJl = gJ[c], AJh = gJ[c + sj], AKl = gK[c], AKh = gK[c + sk];
+  const double vol2 = 2 * geom[(long long)G_VOL * fs + c];
+  const bool zgrad = L.kmx > 2;   // gradqp_z = 0 when kmx == 2 (gradients.f90:328-336)
+  double g[NG][3];
+  bool bad = false;
+#pragma unroll
+  for (int cc = 0; cc < NG; ++cc) {
+    const double* __restrict__ var = (cc < 3) ? (q + (long long)(cc + 1) * fs) : (cc == 3 ? temp : (q + (long long)(cc + 1) * fs));
+    const double v0 = var[c];
+    const double sIl = var[c - 1] + v0, sJl = var[c - sj] + v0, sKl = var[c - sk] + v0;
+    const double sIh = var[c + 1] + v0, sJh = var[c + sj] + v0, sKh = var[c + sk] + v0;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      double r = (-sIl * wlo[0][d] * AIl - sJl * wlo[1][d] * AJl - sKl * wlo[2][d] * AKl + sIh * whi[0][d] * AIh + sJh * whi[1][d] * AJh +
+                  sKh * whi[2][d] * AKh) / vol2;
+      if (d == 2 && !zgrad) r = 0.0;
+      else bad |= isnan(r);
+      g[cc][d] = r;
+      grad[(3 * cc + d) * fs + c] = r;
+    }
+  }
+  if (bad) { atomicOr(err, F3D_ERR_NAN_GRADIENT); }
+  // molecular viscosity on 0..imx (elsewhere it keeps mu_ref from set-up)
+  double mu = mu3[c];
+  if (P.mu_variation == 1) {
+    const double T = q[4 * fs + c] / (q[c] * P.R_gas);
+    mu = P.mu_ref * (pow(T / P.T_ref, 1.5)) * ((P.T_ref + P.Sutherland_temp) / (T + P.Sutherland_temp));
+    mu3[c] = mu;
+    if (isnan(mu)) atomicOr(err, F3D_ERR_NAN_VISCOSITY);
+  }
+  if (NG == 6) {
+    const double density = q[c], tk = q[5 * fs + c], tw = q[6 * fs + c];
+    const double d = geom[(long long)G_DIST * fs + c];
+    const double var1 = sqrt(tk) / (kBstar * tw * d);
+    const double var2 = 500 * (mu / density) / ((d * d) * tw);
+    const double arg2 = fmax(2 * var1, var2);
+    const double Fb = tanh(arg2 * arg2);
+    double rate;
+    if (P.turbulence == F3D_TURB_SST) {
+      const double wx = g[2][1] - g[1][2], wy = g[0][2] - g[2][0], wz = g[1][0] - g[0][1];
+      rate = sqrt(wx * wx + wy * wy + wz * wz);
+    } else {
+      const double sxx = g[0][0], syy = g[1][1], szz = g[2][2];
+      const double syz = g[2][1] + g[1][2], szx = g[0][2] + g[2][0], sxy = g[1][0] + g[0][1];
+      rate = sqrt((2.0 * (sxx * sxx)) + (2.0 * (syy * syy)) + (2.0 * (szz * szz)) + syz * syz + szx * szx + sxy * sxy);
+    }
+    const double NUM = density * kA1 * tk;
+    const double DENOM = fmax(fmax((kA1 * tw), rate * Fb), P.mut_floor);
+    mu3[fs + c] = NUM / DENOM;
+    const double CD = fmax(2 * density * kSigmaW2 * (g[4][0] * g[5][0] + g[4][1] * g[5][1] + g[4][2] * g[5][2]) / tw, P.mut_floor);
+    const double right = 4 * (density * kSigmaW2 * tk) / (CD * (d * d));
+    const double left = fmax(var1, var2);
+    const double arg1 = fmin(left, right);
+    mu3[2 * fs + c] = tanh((arg1 * arg1) * (arg1 * arg1));
+  }
+}
+
+// ghost-gradient rule + ghost mu_t/F1 on one physical face (gradients.f90:638-674, viscosity.f90:408-465)
+template <int NG>
+__global__ void k_gradient_bc(const Params P, const double* __restrict__ q, const double* __restrict__ temp, const double* __restrict__ geom,
+                              double* __restrict__ grad, double* __restrict__ mu3, const double* __restrict__ rec, int face) {
+  const Layout& L = P.L;
+  const int ax = (face - 1) / 2;
+  const bool lo = (face % 2) == 1;
+  const int a_ax = (ax == 0) ? 1 : 0, b_ax = (ax == 2) ? 1 : 2;
+  const int mx[3] = {L.imx, L.jmx, L.kmx};
+  const long long st[3] = {1, L.sj, L.sk};
+  const int a = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y * blockDim.y + threadIdx.y;
+  const int na = mx[a_ax] - 1, nb = mx[b_ax] - 1;
+  if (a >= na || b >= nb) return;
+  int idx[3]; idx[a_ax] = a + 1; idx[b_ax] = b + 1; idx[ax] = lo ? 1 : mx[ax] - 1;
+  const long long ci = L.idx(idx[0], idx[1], idx[2]);       // interior cell
+  const long long cg = lo ? ci - st[ax] : ci + st[ax];       // ghost cell
+  const long long fs = L.fs;
+  const double* r = rec + 4 * ((long long)b * na + a);
+  const double A = r[0], nx = r[1], ny = r[2], nz = r[3];
+  const double vol = geom[(long long)G_VOL * fs + ci];
+  const double c_x = A * nx / vol, c_y = A * ny / vol, c_z = A * nz / vol;
+  const double sig = lo ? 1.0 : -1.0;
+  const int id = P.bc_id[face - 1];
+  const double ft = P.fixed[F3D_FIX_WALL_TEMP][face - 1];
+#pragma unroll
+  for (int cc = 0; cc < NG; ++cc) {
+    // slot cc holds variable cc+2 of qp(2:n_var): u,v,w,p,[k,omega]; slot 4 (cc == 3) is then overwritten with T
+    const double qI = (cc == 3) ? temp[ci] : q[(long long)(cc + 1) * fs + ci];
+    const double qG = (cc == 3) ? temp[cg] : q[(long long)(cc + 1) * fs + cg];
+    const double gIx = grad[(3 * cc + 0) * fs + ci], gIy = grad[(3 * cc + 1) * fs + ci], gIz = grad[(3 * cc + 2) * fs + ci];
+    double gx = sig * (qI - qG) * c_x, gy = sig * (qI - qG) * c_y, gz = sig * (qI - qG) * c_z;
+    if (cc == 3 && id == -5 && (ft < 1. && ft >= 0.)) { gx = -gIx; gy = -gIy; gz = -gIz; }   // adiabatic wall
+    const double dot = (gIx * nx) + (gIy * ny) + (gIz * nz);
+    grad[(3 * cc + 0) * fs + cg] = gx + (gIx - dot * nx);
+    grad[(3 * cc + 1) * fs + cg] = gy + (gIy - dot * ny);
+    grad[(3 * cc + 2) * fs + cg] = gz + (gIz - dot * nz);
+  }
+  if (NG == 6) {
+    if (id == -5) { mu3[fs + cg] = -mu3[fs + ci]; mu3[2 * fs + cg] = mu3[2 * fs + ci]; }
+    else if (id == -1 || id == -2 || id == -3 || id == -4 || id == -6 || id == -7 || id == -8 || id == -9) {
+      mu3[fs + cg] = mu3[fs + ci]; mu3[2 * fs + cg] = mu3[2 * fs + ci];
+    }
+  }
+}
+
+int launch_gradients(Ctx* ctx) {
+  const Layout& L = ctx->P.L;
+  dim3 block(32, 4, 1);
+  dim3 grid((L.imx + 1 + 31) / 32, (L.jmx + 1 + 3) / 4, L.kmx + 1);
+  if (ctx->P.sst) k_gradients<6><<<grid, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->err_dev);
+  else k_gradients<4><<<grid, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->err_dev);
+  ctx->launches++;
+  const int mx[3] = {L.imx, L.jmx, L.kmx};
+  for (int face = 1; face <= 6; ++face) {
+    if (ctx->P.bc_id[face - 1] >= 0) continue;   // "if (bc%imin_id < 0)" -- includes -10
+    const int ax = (face - 1) / 2;
+    const int a_ax = (ax == 0) ? 1 : 0, b_ax = (ax == 2) ? 1 : 2;
+    dim3 g2((mx[a_ax] - 1 + 31) / 32, (mx[b_ax] - 1 + 3) / 4);
+    if (ctx->P.sst) k_gradient_bc<6><<<g2, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->gbc + ctx->gbc_off[face - 1], face);
+    else k_gradient_bc<4><<<g2, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->gbc + ctx->gbc_off[face - 1], face);
+    ctx->launches++;
+  }
+  F3D_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace f3d

@@ -1,0 +1,307 @@
+// Per-face / per-cell device physics of the explicit path.  Everything is FP64 (reference: wp => real64,
+// src/vartypes.f90:3).  Each function cites the reference routine whose arithmetic it reproduces; the code is
+// organised for registers (state vectors as fixed-size arrays, switches as selects), not as array sweeps.
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/fest3d_gpu.h"
+
+namespace f3d {
+
+// SST closure constants (src/global/global_sst.f90:6-16)
+__device__ constexpr double kSigmaK1 = 0.85, kSigmaK2 = 1.0, kSigmaW1 = 0.5, kSigmaW2 = 0.856;
+__device__ constexpr double kBeta1 = 0.075, kBeta2 = 0.0828, kBstar = 0.09, kA1 = 0.31;
+
+__device__ __forceinline__ double sgn1(double x) { return copysign(1.0, x); }          // sign(1.0, x)
+__device__ __forceinline__ double sq(double x) { return x * x; }
+// max(0, 1 - floor(abs(M))) of the Mach splittings: 1 inside |M| < 1, else 0
+__device__ __forceinline__ double subsonic(double M) { return fabs(M) < 1.0 ? 1.0 : 0.0; }
+
+// ------------------------------------------------------------------------------------------------------------
+// Face reconstruction: given the line of cell values around cell c, return the value this cell contributes to
+// its high face (the "left" state there) and to its low face (the "right" state there).
+//   muscl.f90:161-196 (Koren limiter, kappa = 1/3); weno.f90:55-91; weno_NM.f90:66-118; ppm.f90:44-105;
+//   face_interpolant.f90:61-77 (first order).  q[0..6] = cells c-3 .. c+3 (only the used part need be valid).
+template <int INTERP>
+__device__ __forceinline__ void cell_face_values(const double* q, const double* vol, int limiter, double& to_hi, double& to_lo) {
+  const double qm2 = q[1], qm1 = q[2], q0 = q[3], qp1 = q[4], qp2 = q[5];
+  if (INTERP == F3D_INTERP_NONE) {
+    to_hi = q0; to_lo = q0;
+  } else if (INTERP == F3D_MUSCL) {
+    const double fd = qp1 - q0, bd = q0 - qm1;
+    double r = fd / (bd + copysign(1e-14, bd));
+    double psi1 = fmax(0., fmin(fmin(2 * r, (2. / 3.) * (r - 1.0) + 1.0), 2.));
+    r = bd / (fd + copysign(1e-14, fd));
+    double psi2 = fmax(0., fmin(fmin(2 * r, (2. / 3.) * (r - 1.0) + 1.0), 2.));
+    psi1 = (1 - (1 - psi1) * limiter);
+    psi2 = (1 - (1 - psi2) * limiter);
+    const double kappa = 1. / 3.;
+    to_hi = q0 + 0.25 * (((1. - kappa) * psi1 * bd) + ((1. + kappa) * psi2 * fd));
+    to_lo = q0 - 0.25 * (((1. + kappa) * psi1 * bd) + ((1. - kappa) * psi2 * fd));
+  } else if (INTERP == F3D_WENO) {
+    const double eps = 1e-6;
+    double t, s;
+    t = (qm2 - 2.0 * qm1 + q0); s = (qm2 - 4.0 * qm1 + 3.0 * q0);
+    const double B1 = (13.0 / 12.0) * (t * t) + (1.0 / 4.0) * (s * s);
+    t = (qm1 - 2.0 * q0 + qp1); s = (qm1 - qp1);
+    const double B2 = (13.0 / 12.0) * (t * t) + (1.0 / 4.0) * (s * s);
+    t = (q0 - 2.0 * qp1 + qp2); s = (3.0 * q0 - 4.0 * qp1 + qp2);
+    const double B3 = (13.0 / 12.0) * (t * t) + (1.0 / 4.0) * (s * s);
+    const double i1 = 1.0 / sq(eps + B1), i2 = 1.0 / sq(eps + B2), i3 = 1.0 / sq(eps + B3);
+    {
+      const double P1 = (2.0 * qm2 - 7.0 * qm1 + 11.0 * q0) / 6.0;
+      const double P2 = (-1.0 * qm1 + 5.0 * q0 + 2.0 * qp1) / 6.0;
+      const double P3 = (2.0 * q0 + 5.0 * qp1 - 1.0 * qp2) / 6.0;
+      const double w1 = 0.1 * i1, w2 = 0.6 * i2, w3 = 0.3 * i3;
+      to_hi = ((w1 * P1 + w2 * P2) + w3 * P3) / ((w1 + w2) + w3);
+    }
+    {  // the low-face value reuses the same smoothness indicators with mirrored linear weights (weno.f90:84-86)
+      const double P1 = (2.0 * qp2 - 7.0 * qp1 + 11.0 * q0) / 6.0;
+      const double P2 = (-1.0 * qp1 + 5.0 * q0 + 2.0 * qm1) / 6.0;
+      const double P3 = (2.0 * q0 + 5.0 * qm1 - 1.0 * qm2) / 6.0;
+      const double w1 = 0.1 * i3, w2 = 0.6 * i2, w3 = 0.3 * i1;
+      to_lo = ((w1 * P1 + w2 * P2) + w3 * P3) / ((w1 + w2) + w3);
+    }
+  } else if (INTERP == F3D_WENO_NM) {
+    const double eps = 1e-6;
+    const double vm2 = vol[1], vm1 = vol[2], v0 = vol[3], vp1 = vol[4], vp2 = vol[5];
+    const double alpha12 = vp2 / (vp1 + vp2), alpha01 = vp1 / (v0 + vp1);
+    const double alpha10 = v0 / (vm1 + v0), alpha21 = vm1 / (vm2 + vm1);
+    const double U01 = (1.0 - alpha01) * q0 + alpha01 * qp1;
+    const double U12 = (1.0 - alpha12) * qp1 + alpha12 * qp2;
+    const double U10 = (1.0 - alpha10) * qm1 + alpha10 * q0;
+    const double U21 = (1.0 - alpha21) * qm2 + alpha21 * qm1;
+    const double U00 = qm1 + (1.0 - alpha21) * (qm1 - qm2);
+    const double U11 = qp1 + alpha12 * (qp1 - qp2);
+    double t, s;
+    {
+      const double P1 = (6.0 * q0 - 1.0 * U10 - 2.0 * U00) / 3.0;
+      const double P2 = (-1.0 * U10 + 2.0 * q0 + 2.0 * U01) / 3.0;
+      const double P3 = (2.0 * U01 + 2.0 * qp1 - 1.0 * U12) / 3.0;
+      t = (2 * U10 - 2.0 * U00); s = (4 * q0 - 2.0 * U10 - 2.0 * U00);
+      const double B1 = (13.0 / 12.0) * (t * t) + (1.0 / 4.0) * (s * s);
+      t = (2 * U10 - 4.0 * q0 + 2 * U01); s = (-2 * U10 + 2.0 * U01);
+      const double B2 = (13.0 / 12.0) * (t * t) + (1.0 / 4.0) * (s * s);
+      t = (2 * U01 - 4.0 * qp1 + 2 * U12); s = (-6 * U01 + 8.0 * qp1 - 2.0 * U12);
+      const double B3 = (13.0 / 12.0) * (t * t) + (1.0 / 4.0) * (s * s);
+      const double w1 = 0.1 / sq(eps + B1), w2 = 0.6 / sq(eps + B2), w3 = 0.3 / sq(eps + B3);
+      to_hi = ((w1 * P1 + w2 * P2) + w3 * P3) / ((w1 + w2) + w3);
+    }
+    {
+      const double P1 = (6.0 * q0 - 1.0 * U01 - 2.0 * U11) / 3.0;
+      const double P2 = (-1.0 * U01 + 2.0 * q0 + 2.0 * U10) / 3.0;
+      const double P3 = (2.0 * U10 + 2.0 * qm1 - 1.0 * U21) / 3.0;
+      t = (2 * U01 - 2.0 * U11); s = (4 * q0 - 2.0 * U01 - 2.0 * U11);
+      const double B1 = (13.0 / 12.0) * (t * t) + (1.0 / 4.0) * (s * s);
+      t = (2 * U01 - 4.0 * q0 + 2 * U10); s = (-2 * U01 + 2.0 * U10);
+      const double B2 = (13.0 / 12.0) * (t * t) + (1.0 / 4.0) * (s * s);
+      t = (2 * U10 - 4.0 * qm1 + 2 * U21); s = (-6 * U10 + 8.0 * qm1 - 2.0 * U21);
+      const double B3 = (13.0 / 12.0) * (t * t) + (1.0 / 4.0) * (s * s);
+      const double w1 = 0.1 / sq(eps + B1), w2 = 0.6 / sq(eps + B2), w3 = 0.3 / sq(eps + B3);
+      to_lo = ((w1 * P1 + w2 * P2) + w3 * P3) / ((w1 + w2) + w3);
+    }
+  } else {  // PPM: 4-point face estimates on both faces of the cell, then the monotonicity fix of the cell
+    double R = (7. * (q0 + qm1) - (qp1 + qm2)) / 12.;         // estimate at the low face
+    double L = (7. * (qp1 + q0) - (qp2 + qm1)) / 12.;         // estimate at the high face
+    if (limiter == 1) {
+      if ((L - q0) * (q0 - R) <= 0) { L = q0; R = q0; }
+      else {
+        const double dqrl = L - R;
+        const double dq6 = 6. * (q0 - 0.5 * (L + R));
+        if (dqrl * dq6 > dqrl * dqrl) R = 3. * q0 - 2. * L;
+        else if (-dqrl * dqrl > dqrl * dq6) L = 3. * q0 - 2. * R;
+      }
+    }
+    to_hi = L; to_lo = R;
+  }
+}
+
+// Boundary re-reconstruction of the first/last interior cell (boundary_state_reconstruction.f90:93-123):
+// third-order MUSCL with the *unguarded* ratio fd/bd.  Fortran min/max with a NaN operand are taken with
+// fmin/fmax semantics (0/0 on a uniform field picks the finite operand), as the oracle does.
+__device__ __forceinline__ void boundary_cell_face_values(double qm1, double q0, double qp1, int limiter, double& to_hi, double& to_lo) {
+  const double fd = qp1 - q0, bd = q0 - qm1;
+  double r = fd / bd;
+  double psi1 = fmax(0., fmin(fmin(2 * r, (2 + r) / 3.), 2.));
+  psi1 = (1 - (1 - psi1) * limiter);
+  r = bd / fd;
+  double psi2 = fmax(0., fmin(fmin(2 * r, (2 + r) / 3.), 2.));
+  psi2 = (1 - (1 - psi2) * limiter);
+  const double kappa = 1. / 3.;
+  to_hi = q0 + 0.25 * (((1. - kappa) * psi1 * bd) + ((1. + kappa) * psi2 * fd));
+  to_lo = q0 - 0.25 * (((1. + kappa) * psi1 * bd) + ((1. - kappa) * psi2 * fd));
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Inviscid flux through one face, times the face area.  L/R = primitive (rho,u,v,w,p[,k,omega]).
+//   van_leer.f90:56-146, ldfss0.f90:57-161, ausm.f90:56-154, ausmP.f90:77-198, ausmUP.f90:88-216, slau.f90:82-204.
+// mask = make_{F,G,H}_flux_zero of the face (0 on wall / slip-wall / pole faces, bc.f90:53-66).
+template <int NV>
+__device__ __forceinline__ void inviscid_flux(int scheme, double gm, double MInf, const double (&L)[NV], const double (&R)[NV],
+                                              double A, double nx, double ny, double nz, double mask, double (&F)[NV]) {
+  const double g1 = gm / (gm - 1.);
+  if (scheme <= F3D_AUSM) {  // van Leer, LDFSS(0), AUSM: shared Mach / pressure splitting
+    const double cbar = 0.5 * (sqrt(gm * L[4] / L[0]) + sqrt(gm * R[4] / R[0]));
+    const double ML = (L[1] * nx + L[2] * ny + L[3] * nz) / cbar;
+    const double MR = (R[1] * nx + R[2] * ny + R[3] * nz) / cbar;
+    const double aP = 0.5 * (1.0 + sgn1(ML)), bL = -subsonic(ML);
+    const double Mp = 0.25 * sq(1. + ML), Dp = 0.25 * sq(1. + ML) * (2. - ML);
+    double cP = (aP * (1.0 + bL) * ML) - bL * Mp;
+    const double sDp = (aP * (1. + bL)) - (bL * Dp);
+    const double aM = 0.5 * (1.0 - sgn1(MR)), bR = -subsonic(MR);
+    const double Mm = -0.25 * sq(1. - MR), Dm = 0.25 * sq(1. - MR) * (2. + MR);
+    double cM = (aM * (1.0 + bR) * MR) - bR * Mm;
+    const double sDm = (aM * (1. + bR)) - (bR * Dm);
+    if (scheme == F3D_AUSM) {
+      const double t = cP + cM;
+      cP = fmax(0., t); cM = fmin(0., t);
+    } else if (scheme == F3D_LDFSS0) {
+      const double Ml = 0.25 * bL * bR * sq(sqrt((ML * ML + MR * MR) * 0.5) - 1);
+      const double dp = L[4] - R[4];
+      cP = cP - Ml * (1 - dp / (2 * L[0] * (cbar * cbar)));
+      cM = cM + Ml * (1 - dp / (2 * R[0] * (cbar * cbar)));
+    }
+    const double mP = (L[0] * cbar * cP) * mask;
+    const double mM = (R[0] * cbar * cM) * mask;
+    F[0] = mP * A + mM * A;
+    F[1] = ((mP * L[1]) + (sDp * L[4] * nx)) * A + ((mM * R[1]) + (sDm * R[4] * nx)) * A;
+    F[2] = ((mP * L[2]) + (sDp * L[4] * ny)) * A + ((mM * R[2]) + (sDm * R[4] * ny)) * A;
+    F[3] = ((mP * L[3]) + (sDp * L[4] * nz)) * A + ((mM * R[3]) + (sDm * R[4] * nz)) * A;
+    F[4] = (mP * ((0.5 * (L[1] * L[1] + L[2] * L[2] + L[3] * L[3])) + (g1 * L[4] / L[0]))) * A +
+           (mM * ((0.5 * (R[1] * R[1] + R[2] * R[2] + R[3] * R[3])) + (g1 * R[4] / R[0]))) * A;
+#pragma unroll
+    for (int l = 5; l < NV; ++l) F[l] = (mP * L[l]) * A + (mM * R[l]) * A;
+    return;
+  }
+  const double HL = (0.5 * (L[1] * L[1] + L[2] * L[2] + L[3] * L[3])) + (g1 * L[4] / L[0]);
+  const double HR = (0.5 * (R[1] * R[1] + R[2] * R[2] + R[3] * R[3])) + (g1 * R[4] / R[0]);
+  const double VnL = L[1] * nx + L[2] * ny + L[3] * nz;
+  const double VnR = R[1] * nx + R[2] * ny + R[3] * nz;
+  double mass, pbar;
+  if (scheme == F3D_SLAU) {
+    const double C = 0.5 * (sqrt(gm * L[4] / L[0]) + sqrt(gm * R[4] / R[0]));
+    const double ML = VnL / C, MR = VnR / C;
+    const double aL = subsonic(ML), aR = subsonic(MR);
+    const double bL = (1.0 - aL) * 0.5 * (1.0 + sgn1(ML)) + aL * 0.25 * (2.0 - ML) * sq(ML + 1.0);
+    const double bR = (1.0 - aR) * 0.5 * (1.0 - sgn1(MR)) + aR * 0.25 * (2.0 + MR) * sq(MR - 1.0);
+    const double vt = sqrt(0.5 * ((L[1] * L[1]) + (L[2] * L[2]) + (L[3] * L[3]) + (R[1] * R[1]) + (R[2] * R[2]) + (R[3] * R[3])));
+    const double Xi = sq(1.0 - fmin(1.0, vt / C));
+    const double Vnabs = (L[0] * fabs(VnL) + R[0] * fabs(VnR)) / (L[0] + R[0]);
+    const double fnG = -1.0 * fmax(fmin(ML, 0.0), -1.0) * fmin(fmax(MR, 0.0), 1.0);
+    pbar = 0.5 * ((L[4] + R[4]) + (bL - bR) * (L[4] - R[4]) + (1.0 - Xi) * (bL + bR - 1.0) * (L[4] + R[4]));
+    const double VaL = (1.0 - fnG) * Vnabs + fnG * fabs(VnL);
+    const double VaR = (1.0 - fnG) * Vnabs + fnG * fabs(VnR);
+    mass = 0.5 * ((L[0] * (VnL + VaL) + R[0] * (VnR - VaR)) - (Xi * (R[4] - L[4]) / C));
+  } else {  // AUSM+ and AUSM+-up
+    const double cs = sqrt(2.0 * (gm - 1.0) * (0.5 * (HL + HR)) / (gm + 1.0));
+    const bool up = scheme == F3D_AUSMUP;
+    const double cL = cs * cs / fmax(cs, up ? VnL : fabs(VnL));
+    const double cR = cs * cs / fmax(cs, up ? -VnR : fabs(VnR));
+    const double C = fmin(cL, cR);
+    const double ML = VnL / C, MR = VnR / C;
+    double alfa = 0.1875, fna = 1.0, Mb2 = 0.0;
+    if (up) {
+      const double Mb = sqrt(0.5 * ((VnL * VnL) + (VnR * VnR)) / (C * C));
+      Mb2 = Mb * Mb;
+      const double Mo = sqrt(fmin(1.0, fmax(Mb2, MInf * MInf)));
+      fna = Mo * (2.0 - Mo);
+      alfa = 3.0 * (-4.0 + (5.0 * fna * fna)) / 16.0;
+    }
+    const double aL = subsonic(ML), aR = subsonic(MR);
+    double FmL = (0.5 * (1.0 + sgn1(ML)) * (1.0 - aL) * ML) + aL * 0.25 * sq(1.0 + ML);
+    double bL = (0.5 * (1.0 + sgn1(ML)) * (1.0 - aL)) + aL * 0.25 * sq(1.0 + ML) * (2.0 - ML);
+    double FmR = (0.5 * (1.0 - sgn1(MR)) * (1.0 - aR) * MR) - aR * 0.25 * sq(1.0 - MR);
+    double bR = (0.5 * (1.0 - sgn1(MR)) * (1.0 - aR)) + aR * 0.25 * sq(1.0 - MR) * (2.0 + MR);
+    const double tL = sq(ML * ML - 1.0), tR = sq(MR * MR - 1.0);
+    FmL = FmL + aL * 0.125 * tL;
+    bL = bL + aL * alfa * tL * ML;
+    FmR = FmR - aR * 0.125 * tR;
+    bR = bR - aR * alfa * tR * MR;
+    double Mface = FmL + FmR;
+    pbar = bL * L[4] + bR * R[4];
+    if (up) {
+      const double Pu = -0.75 * bL * bR * (L[0] + R[0]) * fna * C * (VnR - VnL);
+      const double Mp = -2.0 * 0.25 * fmax(1.0 - (1.0 * Mb2), 0.0) * (R[4] - L[4]) / (fna * (L[0] + R[0]) * C * C);
+      Mface = FmL + FmR + Mp;
+      pbar = bL * L[4] + bR * R[4] + Pu;
+    }
+    mass = (Mface > 0.0) ? Mface * C * L[0] : Mface * C * R[0];
+  }
+  mass = mass * mask;
+  const double mP = 0.5 * (mass + fabs(mass)), mM = 0.5 * (mass - fabs(mass));
+  F[0] = (mP + mM) * A;
+  F[1] = (((mP * L[1]) + (mM * R[1])) + (pbar * nx)) * A;
+  F[2] = (((mP * L[2]) + (mM * R[2])) + (pbar * ny)) * A;
+  F[3] = (((mP * L[3]) + (mM * R[3])) + (pbar * nz)) * A;
+  F[4] = ((mP * HL) + (mM * HR)) * A;
+#pragma unroll
+  for (int l = 5; l < NV; ++l) F[l] = ((mP * L[l]) + (mM * R[l])) * A;
+}
+
+// face-averaged speed of sound used by the local time step (time.f90:159-175)
+template <int NV>
+__device__ __forceinline__ double face_sound_speed(double gm, const double (&L)[NV], const double (&R)[NV]) {
+  return 0.5 * (sqrt(gm * L[4] / L[0]) + sqrt(gm * R[4] / R[0]));
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Viscous flux through one face (already multiplied by the area), subtracted from the inviscid flux by the caller.
+//   viscous.f90:209-323 (laminar part, with mu_t in the stress when a turbulence model is on) and
+//   viscous.f90:378-446 (SST k / omega diffusion and the -2/3 rho k normal stress).
+// gl/gr = gradients (d/dx,d/dy,d/dz) of (u,v,w,T[,k,omega]) in the low/high cell; ql/qr their primitive states.
+struct FaceGeom { double A, nx, ny, nz, dx, dy, dz; };   // dx,dy,dz = centre(high) - centre(low)
+
+template <int NV, bool SST>
+__device__ __forceinline__ void viscous_flux(const FaceGeom& g, const double (&ql)[NV], const double (&qr)[NV],
+                                             const double (*gl)[3], const double (*gr)[3],
+                                             double mu_l, double mu_r, double mut_l, double mut_r, double F1_l, double F1_r,
+                                             double gm, double R_gas, double Pr, double tPr, bool sst_flux, double (&Fv)[NV]) {
+  constexpr int NG = SST ? 6 : 4;
+  const double d_LR = sqrt(g.dx * g.dx + g.dy * g.dy + g.dz * g.dz);
+  double del[NG];
+  del[0] = qr[1] - ql[1]; del[1] = qr[2] - ql[2]; del[2] = qr[3] - ql[3];
+  del[3] = qr[4] / (qr[0] * R_gas) - ql[4] / (ql[0] * R_gas);
+  if (SST) { del[4] = qr[5] - ql[5]; del[5] = qr[6] - ql[6]; }
+  double G[NG][3];
+#pragma unroll
+  for (int c = 0; c < NG; ++c) {
+    double ax = 0.5 * (gl[c][0] + gr[c][0]), ay = 0.5 * (gl[c][1] + gr[c][1]), az = 0.5 * (gl[c][2] + gr[c][2]);
+    const double nc = (del[c] - (ax * g.dx + ay * g.dy + az * g.dz)) / d_LR;
+    G[c][0] = ax + (nc * g.dx / d_LR);
+    G[c][1] = ay + (nc * g.dy / d_LR);
+    G[c][2] = az + (nc * g.dz / d_LR);
+  }
+  const double mu_f = 0.5 * (mu_l + mu_r);
+  const double mut_f = 0.5 * (mut_l + mut_r);
+  const double tmu = mu_f + mut_f;
+  const double div3 = (G[0][0] + G[1][1] + G[2][2]) / 3.;
+  const double Txx = 2. * tmu * (G[0][0] - div3), Tyy = 2. * tmu * (G[1][1] - div3), Tzz = 2. * tmu * (G[2][2] - div3);
+  const double Txy = tmu * (G[1][0] + G[0][1]), Txz = tmu * (G[2][0] + G[0][2]), Tyz = tmu * (G[2][1] + G[1][2]);
+  const double Kh = (mu_f / Pr + mut_f / tPr) * gm * R_gas / (gm - 1);
+  const double Qx = Kh * G[3][0], Qy = Kh * G[3][1], Qz = Kh * G[3][2];
+  const double uf = 0.5 * (ql[1] + qr[1]), vf = 0.5 * (ql[2] + qr[2]), wf = 0.5 * (ql[3] + qr[3]);
+  Fv[0] = 0.0;
+  Fv[1] = ((Txx * g.nx + Txy * g.ny + Txz * g.nz) * g.A);
+  Fv[2] = ((Txy * g.nx + Tyy * g.ny + Tyz * g.nz) * g.A);
+  Fv[3] = ((Txz * g.nx + Tyz * g.ny + Tzz * g.nz) * g.A);
+  Fv[4] = (g.A * (((Txx * uf + Txy * vf + Txz * wf + Qx) * g.nx) + ((Txy * uf + Tyy * vf + Tyz * wf + Qy) * g.ny) +
+                  ((Txz * uf + Tyz * vf + Tzz * wf + Qz) * g.nz)));
+  if (SST) {
+    Fv[5] = 0.0; Fv[6] = 0.0;
+    if (sst_flux) {
+      const double F1 = 0.5 * (F1_l + F1_r);
+      const double sk = kSigmaK1 * F1 + kSigmaK2 * (1.0 - F1);
+      const double sw = kSigmaW1 * F1 + kSigmaW2 * (1.0 - F1);
+      const double rhof = 0.5 * (ql[0] + qr[0]), tkf = 0.5 * (ql[5] + qr[5]);
+      const double Tk = -2.0 * rhof * tkf / 3.0;
+      // the reference applies the laminar and the SST contribution as two separate in-place subtractions
+      // F = (F - lam) - sst (viscous.f90:87-105); callers keep that order by subtracting Fv and Fv2 in turn.
+      const double dk = (g.A * ((mu_f + sk * mut_f) * (G[4][0] * g.nx + G[4][1] * g.ny + G[4][2] * g.nz)));
+      const double dw = (g.A * ((mu_f + sw * mut_f) * (G[5][0] * g.nx + G[5][1] * g.ny + G[5][2] * g.nz)));
+      Fv[5] = dk; Fv[6] = dw;
+      // second-pass terms returned through the spare slots: momentum (Tk n A) and energy (dk)
+      Fv[0] = Tk;   // caller applies (Tk * n * A) to momentum and dk to energy after the laminar subtraction
+    }
+  }
+}
+
+}  // namespace f3d

@@ -1,0 +1,194 @@
+"""Host-side mirror of the reference interface for the accelerated path.
+
+``GpuBlock`` is one block (= one MPI rank of the reference) living on one GPU.  ``Solver`` owns the blocks of this
+process and exposes the two calls the reference's driver makes every iteration (src/solver.f90:184-185):
+
+    get_next_solution()   <- src/update.f90:129   (all RK variants, halo exchange, BCs, residual, dt, update)
+    find_resnorm()        <- src/resnorm.f90:62   (Res_abs(0:n_var), summed over all blocks)
+
+fused into ``iterate(n)`` because the device path reduces the norms inside the last stage's kernel.  Everything
+goes through the C ABI (capi.py); nothing here computes on the host.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from . import case as case_mod
+
+
+class Fest3dError(RuntimeError):
+    """The library's replacement of the reference's Fatal_error (message + STOP, src/error.h:1)."""
+
+    def __init__(self, rc, info=None):
+        self.rc = rc
+        self.info = info
+        names = {1: "NaN in flux", 2: "NaN in gradient", 4: "NaN in viscosity", 8: "negative density/pressure or NaN after update",
+                 64: "configuration not supported by the device path", 128: "CUDA error", 256: "bad argument"}
+        msg = ", ".join(v for k, v in names.items() if rc & k) or "error %d" % rc
+        if info is not None and (info.i or info.j or info.k):
+            msg += " at block %d cell (%d,%d,%d)" % (info.block_id, info.i, info.j, info.k)
+        super().__init__(msg)
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+def fill_config(cfg, blk):
+    s, f, c = blk.scheme, blk.flow, blk.control
+    cfg.imx, cfg.jmx, cfg.kmx, cfg.n_var = blk.imx, blk.jmx, blk.kmx, blk.n_var
+    cfg.scheme = case_mod.SCHEMES[s.scheme_name]; cfg.interpolant = case_mod.INTERPOLANTS[s.interpolant]
+    cfg.turbulence = case_mod.TURBULENCE[s.turbulence]; cfg.transition = case_mod.TRANSITION[s.transition]
+    cfg.time_accuracy = case_mod.TIME_ACCURACY[s.time_step_accuracy]
+    cfg.time_stepping = 1 if s.time_stepping_method == "g" else 0
+    for d in range(3):
+        cfg.limiter[d] = s.limiter[d]; cfg.tlimiter[d] = s.tlimiter[d]; cfg.pb_switch[d] = s.pb_switch[d]
+    cfg.accur = s.accur
+    cfg.mu_variation = 1 if f.mu_variation == "sutherland_law" else 0
+    for i in range(6):
+        cfg.bc_id[i] = blk.bc_id[i]; cfg.pbc_id[i] = blk.pbc_id[i]
+        cfg.dir_switch[i] = blk.dir_switch[i]; cfg.otherface[i] = blk.otherface[i]
+        for t in range(2):
+            cfg.plo[i][t] = blk.plo[i][t]; cfg.phi[i][t] = blk.phi[i][t]; cfg.pdir[i][t] = blk.pdir[i][t]
+    cfg.block_id, cfg.n_blocks = blk.block_id, blk.n_blocks
+    cfg.CFL = c.CFL; cfg.global_time_step = s.global_time_step
+    for k in ("gm", "R_gas", "mu_ref", "T_ref", "Sutherland_temp", "Pr", "tPr", "density_inf", "x_speed_inf",
+              "y_speed_inf", "z_speed_inf", "pressure_inf", "tk_inf", "tw_inf", "vel_mag", "MInf"):
+        setattr(cfg, k, getattr(f, k))
+    for sl in range(capi.NFIX):
+        for i in range(6):
+            cfg.fixed[sl][i] = float(blk.fixed[sl, i])
+    return cfg
+
+
+class GpuBlock:
+    def __init__(self, blk, device=0):
+        self.L = capi.lib()
+        self.blk = blk
+        self.device = device
+        self.cfg = fill_config(capi.Fest3dGpuConfig(), blk)
+        self.h = C.c_void_p()
+        rc = self.L.fest3d_gpu_create(C.byref(self.h), C.byref(self.cfg), device)
+        if rc:
+            raise Fest3dError(rc)
+        dist = np.ascontiguousarray(blk.dist) if blk.dist is not None else None
+        self._check(self.L.fest3d_gpu_set_geometry(self.h, _dp(blk.cells), _dp(blk.Ifaces), _dp(blk.Jfaces), _dp(blk.Kfaces), _dp(dist)))
+        self.set_state(blk.qp)
+
+    def _check(self, rc):
+        if rc:
+            info = capi.Fest3dGpuError()
+            self.L.fest3d_gpu_error(self.h, C.byref(info))
+            raise Fest3dError(rc, info)
+
+    def close(self):
+        if self.h:
+            self.L.fest3d_gpu_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- data in / out (host arrays in the reference layout) --
+    def set_state(self, qp):
+        q = np.ascontiguousarray(qp, dtype=np.float64)
+        self._check(self.L.fest3d_gpu_set_state(self.h, _dp(q)))
+
+    def get_state(self, out=None):
+        b = self.blk
+        q = out if out is not None else np.empty((b.n_var, b.kmx + 5, b.jmx + 5, b.imx + 5))
+        self._check(self.L.fest3d_gpu_get_state(self.h, _dp(q)))
+        return q
+
+    def get_residue(self):
+        b = self.blk
+        r = np.empty((b.n_var, b.kmx - 1, b.jmx - 1, b.imx - 1))
+        self._check(self.L.fest3d_gpu_get_residue(self.h, _dp(r)))
+        return r
+
+    def aux(self, which, shape):
+        a = np.empty(shape)
+        self._check(self.L.fest3d_gpu_get_aux(self.h, which, _dp(a)))
+        return a
+
+    def set_stream(self, cuda_stream_handle):
+        self._check(self.L.fest3d_gpu_set_stream(self.h, C.c_void_p(cuda_stream_handle)))
+
+    def sync(self):
+        self._check(self.L.fest3d_gpu_sync(self.h))
+
+    def launch_count(self):
+        return int(self.L.fest3d_gpu_launch_count(self.h))
+
+    def kernel_timing(self, on=True):
+        self.L.fest3d_gpu_kernel_timing(self.h, 1 if on else 0)
+
+    def kernel_time_ms(self, reset=True):
+        n = C.c_longlong(0)
+        t = self.L.fest3d_gpu_kernel_time_ms(self.h, C.byref(n), 1 if reset else 0)
+        return float(t), int(n.value)
+
+
+class Solver:
+    """The blocks of this process, stepped in lock step (drop-in for the reference's per-iteration calls)."""
+
+    def __init__(self, blocks, devices=None):
+        self.L = capi.lib()
+        devices = devices or [0] * len(blocks)
+        self.blocks = [GpuBlock(b, d) for b, d in zip(blocks, devices)]
+        for i, a in enumerate(self.blocks):
+            for b in self.blocks[i + 1:]:
+                ids_a = set(a.blk.bc_id) | set(a.blk.pbc_id)
+                if b.blk.block_id in ids_a:
+                    self.L.fest3d_gpu_link_local(a.h, b.h)
+        self.n_var = blocks[0].n_var
+        self.current_iter = 1   # control%current_iter after setup (solver.f90:140)
+        self._handles = (C.c_void_p * len(self.blocks))(*[b.h for b in self.blocks])
+
+    def close(self):
+        for b in self.blocks:
+            b.close()
+
+    def init_comm(self, n_ranks, rank, unique_id, block_to_rank):
+        arr = (C.c_int * len(block_to_rank))(*block_to_rank)
+        for b in self.blocks:
+            b._check(self.L.fest3d_gpu_comm_init(b.h, n_ranks, rank, unique_id, arr))
+
+    @staticmethod
+    def unique_id():
+        buf = C.create_string_buffer(128)
+        rc = capi.lib().fest3d_gpu_comm_unique_id(buf)
+        if rc:
+            raise Fest3dError(rc)
+        return buf.raw
+
+    def residual(self):
+        """get_total_conservative_Residue on every block (update.f90:495); returns the per-block residue arrays."""
+        rc = self.L.fest3d_gpu_residual_group(self._handles, len(self.blocks), self.current_iter)
+        if rc:
+            self.blocks[0]._check(rc)
+        return [b.get_residue() for b in self.blocks]
+
+    def iterate(self, n_iters=1, want_norms=True):
+        """n iterations of get_next_solution + find_resnorm.  Returns Res_abs[n_iters, n_var+1] (or None)."""
+        res = np.zeros((n_iters, self.n_var + 1)) if want_norms else None
+        rc = self.L.fest3d_gpu_step_group(self._handles, len(self.blocks), self.current_iter, n_iters, _dp(res))
+        if rc:
+            for b in self.blocks:
+                b._check(rc)
+        self.current_iter += n_iters
+        return res
+
+    # names of the reference, for hosts written against them
+    def get_next_solution(self):
+        self._last = self.iterate(1)
+        return self
+
+    def find_resnorm(self):
+        return self._last[0]

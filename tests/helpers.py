@@ -36,3 +36,32 @@ def unit_cube_geometry(blk, h=1.0):
 def interior(q, blk):
     """Interior view of a [nv, kmx+5, jmx+5, imx+5] state."""
     return q[:, 3:3 + blk.kmx - 1, 3:3 + blk.jmx - 1, 3:3 + blk.imx - 1]
+
+
+def flux_scale(world, b, blk):
+    """Per-cell flux scale |F(i)|+|F(i+1)|+|G(j)|+|G(j+1)|+|H(k)|+|H(k+1)| from the oracle's face fluxes."""
+    nv = blk.n_var
+    F = world.aux(b, 20, (nv, blk.kmx - 1, blk.jmx - 1, blk.imx))
+    G = world.aux(b, 21, (nv, blk.kmx - 1, blk.jmx, blk.imx - 1))
+    H = world.aux(b, 22, (nv, blk.kmx, blk.jmx - 1, blk.imx - 1))
+    s = (np.abs(F[..., :-1]) + np.abs(F[..., 1:]) + np.abs(G[:, :, :-1, :]) + np.abs(G[:, :, 1:, :])
+         + np.abs(H[:, :-1]) + np.abs(H[:, 1:]))
+    return s
+
+
+def residual_parity(r_gpu, r_orc, scale):
+    """max over cells of |dR| / flux scale (per variable).  Variables whose flux scale is identically zero must agree exactly."""
+    out = []
+    for v in range(r_gpu.shape[0]):
+        sc = scale[v]
+        floor = max(sc.max(), 1e-300) * 1e-6   # cells with (near-)vanishing flux take the block's scale
+        out.append(float((np.abs(r_gpu[v] - r_orc[v]) / np.maximum(sc, floor)).max()))
+    return out
+
+
+def state_rel_diff(a, b):
+    out = []
+    for v in range(a.shape[0]):
+        den = max(np.abs(b[v]).max(), 1e-300)
+        out.append(float(np.abs(a[v] - b[v]).max() / den))
+    return out

@@ -1,0 +1,222 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle on the same inputs.
+
+Tolerances (BASELINE.json north_star): per-cell residual after one evaluation within 1e-12 relative to the cell's flux
+scale; residual-norm history and final flow field within 1e-10 relative.  Reference cases live under /root/reference,
+which does not exist on the GPU box -- their inputs are committed as fixtures under tests/golden/ (see
+tests/golden/make_fixtures.py)."""
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+RES_TOL = 1e-12
+HIST_TOL = 1e-10
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _solver(pkg_mod, blocks):
+    import importlib
+    solver = importlib.import_module("fest-3d_b200.solver")
+    return solver.Solver(blocks)
+
+
+def _load_fixture(case_mod, name, **over):
+    import fixtures
+    return fixtures.load(case_mod, os.path.join(GOLDEN, name), **over)
+
+
+def _check_residual(oracle, s, blocks, tol=RES_TOL):
+    w = oracle.OracleWorld(blocks)
+    err, r_orc = w.residual(1)
+    assert err == 0
+    r_gpu = s.residual()
+    worst = 0.0
+    for b, blk in enumerate(blocks):
+        par = helpers.residual_parity(r_gpu[b], r_orc[b], helpers.flux_scale(w, b, blk))
+        worst = max(worst, max(par))
+        assert max(par) < tol, (b, par)
+    return worst, w
+
+
+def _check_history(oracle, s, blocks, n_iter, tol=HIST_TOL):
+    w = oracle.OracleWorld(blocks)
+    hist_o = []
+    for it in range(1, n_iter + 1):
+        err, r = w.step(it)
+        assert err == 0
+        hist_o.append(r)
+    hist_o = np.array(hist_o)
+    hist_g = s.iterate(n_iter)
+    # mass-imbalance column is a difference of O(1) sums: compare it on the scale of the continuity norm
+    floor = np.abs(hist_o[:, 1:]).max(axis=0) * 1e-3
+    rel = np.abs(hist_g[:, 1:] - hist_o[:, 1:]) / np.maximum(np.abs(hist_o[:, 1:]), floor)
+    assert rel.max() < tol, rel.max(axis=0)
+    for b, blk in enumerate(blocks):
+        qg = s.blocks[b].get_state()
+        qo = w.get_state(b)
+        d = helpers.state_rel_diff(helpers.interior(qg, blk), helpers.interior(qo, blk))
+        assert max(d) < tol, (b, d)
+        # ghost cells too: the whole array is part of the state the reference carries between iterations
+        dg = helpers.state_rel_diff(qg, qo)
+        assert max(dg) < tol, (b, "ghost", dg)
+    return rel.max()
+
+
+# ---- BASELINE config 1: SmoothBump, MUSCL + AUSM, explicit RK ------------------------------------------------------
+def test_smoothbump_two_blocks(pkg, case_mod, oracle):
+    blocks = _load_fixture(case_mod, "smoothbump", scheme=dict(time_step_accuracy="RK4"), control=dict(CFL=0.5))
+    s = _solver(pkg, blocks)
+    _check_residual(oracle, s, blocks)
+    _check_history(oracle, s, blocks, 25)
+    s.close()
+
+
+def test_smoothbump_single_block_none(pkg, case_mod, oracle):
+    blocks = _load_fixture(case_mod, "smoothbump", scheme=dict(time_step_accuracy="none"), control=dict(CFL=0.4))
+    merged = [case_mod.merge_blocks_i(blocks)]
+    s = _solver(pkg, merged)
+    _check_residual(oracle, s, merged)
+    _check_history(oracle, s, merged, 30)
+    s.close()
+
+
+# ---- BASELINE config 2: Lfp laminar flat plate, MUSCL + SLAU --------------------------------------------------------
+def test_lfp_laminar_slau(pkg, case_mod, oracle):
+    blocks = _load_fixture(case_mod, "lfp", scheme=dict(scheme_name="slau", interpolant="muscl", time_step_accuracy="RK4"), control=dict(CFL=0.5))
+    s = _solver(pkg, blocks)
+    _check_residual(oracle, s, blocks)
+    _check_history(oracle, s, blocks, 20)
+    s.close()
+
+
+# ---- BASELINE config 3: Tfp turbulent flat plate from the shipped restart, SST, MUSCL + AUSM+-up --------------------
+def test_tfp_sst_ausmup(pkg, case_mod, oracle):
+    blocks = _load_fixture(case_mod, "tfp", scheme=dict(scheme_name="ausmUP", interpolant="muscl", time_step_accuracy="RK4"), control=dict(CFL=0.5))
+    s = _solver(pkg, blocks)
+    _check_residual(oracle, s, blocks)
+    _check_history(oracle, s, blocks, 15)
+    s.close()
+
+
+# ---- every flux scheme x interpolant on the synthetic SST duct (config 4 at a size the oracle finishes in seconds) ---
+@pytest.mark.parametrize("scheme_name", ["van_leer", "ldfss0", "ausm", "ausmP", "ausmUP", "slau"])
+@pytest.mark.parametrize("interpolant", ["none", "muscl", "ppm", "weno", "weno_NM"])
+def test_duct_sst_residual(pkg, case_mod, oracle, scheme_name, interpolant):
+    import importlib
+    syn = importlib.import_module("fest-3d_b200.synthetic")
+    blocks = syn.make_duct_blocks(None, n3=(20, 12, 10), scheme_name=scheme_name, interpolant=interpolant, turbulence="sst")
+    s = _solver(pkg, blocks)
+    _check_residual(oracle, s, blocks)
+    s.close()
+
+
+@pytest.mark.parametrize("turbulence,mu_ref", [("none", 0.0), ("none", None), ("sst", None), ("sst2003", None)])
+@pytest.mark.parametrize("ta", ["none", "RK2", "RK4", "TVDRK2", "TVDRK3"])
+def test_duct_time_integrators(pkg, case_mod, oracle, turbulence, mu_ref, ta):
+    import importlib
+    syn = importlib.import_module("fest-3d_b200.synthetic")
+    blocks = syn.make_duct_blocks(None, n3=(14, 10, 9), turbulence=turbulence, mu_ref=mu_ref, time_step_accuracy=ta, CFL=0.6)
+    s = _solver(pkg, blocks)
+    _check_history(oracle, s, blocks, 6)
+    s.close()
+
+
+def test_duct_multiblock_local_links(pkg, case_mod, oracle):
+    import importlib
+    syn = importlib.import_module("fest-3d_b200.synthetic")
+    blocks = syn.make_duct_blocks(None, n3=(10, 8, 6), nb=(2, 2, 2), time_step_accuracy="RK4")
+    s = _solver(pkg, blocks)
+    _check_residual(oracle, s, blocks)
+    _check_history(oracle, s, blocks, 5)
+    s.close()
+
+
+def test_global_time_step_and_weno_history(pkg, case_mod, oracle):
+    import importlib
+    syn = importlib.import_module("fest-3d_b200.synthetic")
+    blocks = syn.make_duct_blocks(None, n3=(12, 9, 8), interpolant="weno", scheme_name="ausmP", time_step_accuracy="TVDRK3", CFL=0.4)
+    for b in blocks:
+        b.scheme.time_stepping_method = "g"; b.scheme.global_time_step = -1.0   # computed: block-local minval
+    s = _solver(pkg, blocks)
+    _check_history(oracle, s, blocks, 5)
+    s.close()
+
+
+# ---- edge cases: one-cell-thick k (kmx = 2), tiny blocks, every physical BC id, higher-order BC, periodic --------------
+@pytest.mark.parametrize("bc", [[-1, -2, -6, -6, -6, -6], [-3, -4, -5, -6, -6, -6], [-8, -8, -8, -8, -6, -6],
+                                [-9, -9, -5, -5, -6, -6], [-8, -4, -7, -6, -9, -9], [-3, -4, -5, -5, -5, -5]])
+@pytest.mark.parametrize("shape", [(6, 5, 1), (4, 3, 3), (9, 7, 5)])
+@pytest.mark.parametrize("accur", [0, 1])
+def test_boundary_conditions(pkg, case_mod, oracle, bc, shape, accur):
+    import importlib
+    syn = importlib.import_module("fest-3d_b200.synthetic")
+    if (-9 in bc[4:]) and shape[2] < 3:
+        pytest.skip("periodic slab copy needs 3 interior layers")
+    if (-9 in bc[:2]) and shape[0] < 3:
+        pytest.skip("periodic slab copy needs 3 interior layers")
+    blocks = syn.make_duct_blocks(None, n3=shape, turbulence="sst", time_step_accuracy="RK2", interpolant="muscl")
+    blk = blocks[0]
+    blk.bc_id = list(bc)
+    blk.scheme.accur = accur
+    blk.fixed[7, 2] = 350.0   # isothermal wall at jmin, adiabatic elsewhere
+    blk.build_geometry()      # pole faces change the metrics
+    s = _solver(pkg, blocks)
+    _check_residual(oracle, s, blocks)
+    _check_history(oracle, s, blocks, 4)
+    s.close()
+
+
+def test_unsupported_is_an_error_not_a_fallback(pkg, case_mod):
+    import importlib
+    syn = importlib.import_module("fest-3d_b200.synthetic")
+    solver = importlib.import_module("fest-3d_b200.solver")
+    blocks = syn.make_duct_blocks(None, n3=(6, 5, 4), turbulence="none", mu_ref=0.0, time_step_accuracy="implicit")
+    with pytest.raises(solver.Fest3dError):
+        solver.Solver(blocks)
+
+
+def test_negative_pressure_is_reported(pkg, case_mod):
+    import importlib
+    syn = importlib.import_module("fest-3d_b200.synthetic")
+    solver = importlib.import_module("fest-3d_b200.solver")
+    blocks = syn.make_duct_blocks(None, n3=(8, 6, 5), turbulence="none", mu_ref=0.0, CFL=50.0)
+    blocks[0].qp[4, 5, 5, 5] *= 40.0   # a blast the explicit step at CFL 50 cannot survive
+    s = solver.Solver(blocks)
+    with pytest.raises(solver.Fest3dError) as e:
+        s.iterate(40)
+    assert e.value.rc & (8 | 1)
+    s.close()
+
+
+# ---- full-size, size-independent properties (256^3, BASELINE config sizes; no oracle at this size) ---------------------
+def test_fullsize_freestream_preservation_and_telescoping(pkg, case_mod):
+    import importlib
+    syn = importlib.import_module("fest-3d_b200.synthetic")
+    n = int(os.environ.get("FEST3D_FULLSIZE_N", "256"))
+    blocks = syn.make_duct_blocks(n, turbulence="none", mu_ref=0.0, time_step_accuracy="none", interpolant="muscl")
+    blk = blocks[0]
+    blk.bc_id = [-9] * 6                       # fully periodic box on the warped grid
+    blk.init_state()                           # exact free stream
+    s = _solver(pkg, blocks)
+    r = s.residual()[0]
+    fl = blk.flow
+    # closed cells: sum of area vectors is zero to round-off, so a uniform state has zero residual relative to the flux
+    area = 1.0 / n ** 2
+    flux_scale = np.array([fl.density_inf * fl.vel_mag, fl.pressure_inf, fl.pressure_inf, fl.pressure_inf,
+                           fl.vel_mag * 3.5 * fl.pressure_inf]) * area
+    for v in range(5):
+        assert np.abs(r[v]).max() / flux_scale[v] < 1e-11, v
+    s.close()
+    # telescoping: the sum of the mass residual over all cells equals the net boundary mass flux
+    blocks = syn.make_duct_blocks(n, turbulence="none", mu_ref=0.0, time_step_accuracy="none")
+    s = _solver(pkg, blocks)
+    r = s.residual()[0]
+    total = float(np.sum(r[0], dtype=np.longdouble))
+    res = s.iterate(1)
+    scale = float(np.sum(np.abs(r[0]), dtype=np.longdouble))
+    assert abs(abs(total) - res[0, 0]) < 1e-9 * scale
+    s.close()
