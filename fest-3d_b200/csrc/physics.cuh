@@ -117,7 +117,7 @@ __device__ __forceinline__ void cell_face_values(const double* q, const double* 
 
 // Boundary re-reconstruction of the first/last interior cell (boundary_state_reconstruction.f90:93-123):
 // third-order MUSCL with the *unguarded* ratio fd/bd.  Fortran min/max with a NaN operand are taken with
-// fmin/fmax semantics (0/0 on a uniform field picks the finite operand), as the oracle does.
+// fmin/fmax semantics (0/0 on a uniform field picks the finite operand).
 __device__ __forceinline__ void boundary_cell_face_values(double qm1, double q0, double qp1, int limiter, double& to_hi, double& to_lo) {
   const double fd = qp1 - q0, bd = q0 - qm1;
   double r = fd / bd;
@@ -241,67 +241,6 @@ __device__ __forceinline__ void inviscid_flux(int scheme, double gm, double MInf
 template <int NV>
 __device__ __forceinline__ double face_sound_speed(double gm, const double (&L)[NV], const double (&R)[NV]) {
   return 0.5 * (sqrt(gm * L[4] / L[0]) + sqrt(gm * R[4] / R[0]));
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// Viscous flux through one face (already multiplied by the area), subtracted from the inviscid flux by the caller.
-//   viscous.f90:209-323 (laminar part, with mu_t in the stress when a turbulence model is on) and
-//   viscous.f90:378-446 (SST k / omega diffusion and the -2/3 rho k normal stress).
-// gl/gr = gradients (d/dx,d/dy,d/dz) of (u,v,w,T[,k,omega]) in the low/high cell; ql/qr their primitive states.
-struct FaceGeom { double A, nx, ny, nz, dx, dy, dz; };   // dx,dy,dz = centre(high) - centre(low)
-
-template <int NV, bool SST>
-__device__ __forceinline__ void viscous_flux(const FaceGeom& g, const double (&ql)[NV], const double (&qr)[NV],
-                                             const double (*gl)[3], const double (*gr)[3],
-                                             double mu_l, double mu_r, double mut_l, double mut_r, double F1_l, double F1_r,
-                                             double gm, double R_gas, double Pr, double tPr, bool sst_flux, double (&Fv)[NV]) {
-  constexpr int NG = SST ? 6 : 4;
-  const double d_LR = sqrt(g.dx * g.dx + g.dy * g.dy + g.dz * g.dz);
-  double del[NG];
-  del[0] = qr[1] - ql[1]; del[1] = qr[2] - ql[2]; del[2] = qr[3] - ql[3];
-  del[3] = qr[4] / (qr[0] * R_gas) - ql[4] / (ql[0] * R_gas);
-  if (SST) { del[4] = qr[5] - ql[5]; del[5] = qr[6] - ql[6]; }
-  double G[NG][3];
-#pragma unroll
-  for (int c = 0; c < NG; ++c) {
-    double ax = 0.5 * (gl[c][0] + gr[c][0]), ay = 0.5 * (gl[c][1] + gr[c][1]), az = 0.5 * (gl[c][2] + gr[c][2]);
-    const double nc = (del[c] - (ax * g.dx + ay * g.dy + az * g.dz)) / d_LR;
-    G[c][0] = ax + (nc * g.dx / d_LR);
-    G[c][1] = ay + (nc * g.dy / d_LR);
-    G[c][2] = az + (nc * g.dz / d_LR);
-  }
-  const double mu_f = 0.5 * (mu_l + mu_r);
-  const double mut_f = 0.5 * (mut_l + mut_r);
-  const double tmu = mu_f + mut_f;
-  const double div3 = (G[0][0] + G[1][1] + G[2][2]) / 3.;
-  const double Txx = 2. * tmu * (G[0][0] - div3), Tyy = 2. * tmu * (G[1][1] - div3), Tzz = 2. * tmu * (G[2][2] - div3);
-  const double Txy = tmu * (G[1][0] + G[0][1]), Txz = tmu * (G[2][0] + G[0][2]), Tyz = tmu * (G[2][1] + G[1][2]);
-  const double Kh = (mu_f / Pr + mut_f / tPr) * gm * R_gas / (gm - 1);
-  const double Qx = Kh * G[3][0], Qy = Kh * G[3][1], Qz = Kh * G[3][2];
-  const double uf = 0.5 * (ql[1] + qr[1]), vf = 0.5 * (ql[2] + qr[2]), wf = 0.5 * (ql[3] + qr[3]);
-  Fv[0] = 0.0;
-  Fv[1] = ((Txx * g.nx + Txy * g.ny + Txz * g.nz) * g.A);
-  Fv[2] = ((Txy * g.nx + Tyy * g.ny + Tyz * g.nz) * g.A);
-  Fv[3] = ((Txz * g.nx + Tyz * g.ny + Tzz * g.nz) * g.A);
-  Fv[4] = (g.A * (((Txx * uf + Txy * vf + Txz * wf + Qx) * g.nx) + ((Txy * uf + Tyy * vf + Tyz * wf + Qy) * g.ny) +
-                  ((Txz * uf + Tyz * vf + Tzz * wf + Qz) * g.nz)));
-  if (SST) {
-    Fv[5] = 0.0; Fv[6] = 0.0;
-    if (sst_flux) {
-      const double F1 = 0.5 * (F1_l + F1_r);
-      const double sk = kSigmaK1 * F1 + kSigmaK2 * (1.0 - F1);
-      const double sw = kSigmaW1 * F1 + kSigmaW2 * (1.0 - F1);
-      const double rhof = 0.5 * (ql[0] + qr[0]), tkf = 0.5 * (ql[5] + qr[5]);
-      const double Tk = -2.0 * rhof * tkf / 3.0;
-      // the reference applies the laminar and the SST contribution as two separate in-place subtractions
-      // F = (F - lam) - sst (viscous.f90:87-105); callers keep that order by subtracting Fv and Fv2 in turn.
-      const double dk = (g.A * ((mu_f + sk * mut_f) * (G[4][0] * g.nx + G[4][1] * g.ny + G[4][2] * g.nz)));
-      const double dw = (g.A * ((mu_f + sw * mut_f) * (G[5][0] * g.nx + G[5][1] * g.ny + G[5][2] * g.nz)));
-      Fv[5] = dk; Fv[6] = dw;
-      // second-pass terms returned through the spare slots: momentum (Tk n A) and energy (dk)
-      Fv[0] = Tk;   // caller applies (Tk * n * A) to momentum and dk to energy after the laminar subtraction
-    }
-  }
 }
 
 }  // namespace f3d

@@ -39,14 +39,34 @@ def interior(q, blk):
 
 
 def flux_scale(world, b, blk):
-    """Per-cell flux scale |F(i)|+|F(i+1)|+|G(j)|+|G(j+1)|+|H(k)|+|H(k+1)| from the oracle's face fluxes."""
+    """Per-cell, per-variable flux scale used to normalise residual differences.
+
+    The residual is a difference of six face fluxes, and every upwind face flux is itself a sum of split contributions
+    F+ + F- of magnitude  A * rho * (|V| + c) * phi  (phi = 1, velocity scale, total enthalpy, k, omega) that cancel almost
+    completely where the face-normal Mach number is small (e.g. the large wall-parallel faces of a boundary-layer cell).
+    Round-off (FMA contraction on the GPU vs none in the oracle) is proportional to those split magnitudes, so the scale is
+        max( sum_faces |flux_l| ,  sum_faces A_f * rho (|V|+c) phi_l ).
+    """
     nv = blk.n_var
     F = world.aux(b, 20, (nv, blk.kmx - 1, blk.jmx - 1, blk.imx))
     G = world.aux(b, 21, (nv, blk.kmx - 1, blk.jmx, blk.imx - 1))
     H = world.aux(b, 22, (nv, blk.kmx, blk.jmx - 1, blk.imx - 1))
     s = (np.abs(F[..., :-1]) + np.abs(F[..., 1:]) + np.abs(G[:, :, :-1, :]) + np.abs(G[:, :, 1:, :])
          + np.abs(H[:, :-1]) + np.abs(H[:, 1:]))
-    return s
+    q = interior(world.get_state(b), blk)
+    K, J, I = slice(3, 3 + blk.kmx - 1), slice(3, 3 + blk.jmx - 1), slice(3, 3 + blk.imx - 1)
+    K1, J1, I1 = slice(4, 4 + blk.kmx - 1), slice(4, 4 + blk.jmx - 1), slice(4, 4 + blk.imx - 1)
+    area = (blk.Ifaces[K, J, I, 0] + blk.Ifaces[K, J, I1, 0] + blk.Jfaces[K, J, I, 0] + blk.Jfaces[K, J1, I, 0]
+            + blk.Kfaces[K, J, I, 0] + blk.Kfaces[K1, J, I, 0])
+    gm = blk.flow.gm
+    rho, p = q[0], q[4]
+    c = np.sqrt(gm * p / rho)
+    vm = np.sqrt(q[1] ** 2 + q[2] ** 2 + q[3] ** 2)
+    Ht = gm / (gm - 1.0) * p / rho + 0.5 * vm ** 2
+    m = area * rho * (vm + c)
+    phi = [np.ones_like(m), vm + c, vm + c, vm + c, Ht] + [np.abs(q[v]) for v in range(5, nv)]
+    ac = np.stack([m * f for f in phi])
+    return np.maximum(s, ac)
 
 
 def residual_parity(r_gpu, r_orc, scale):
