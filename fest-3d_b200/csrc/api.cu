@@ -101,6 +101,7 @@ extern "C" int fest3d_gpu_create(Fest3dGpuCtx** out, const Fest3dGpuConfig* cfg,
   P.CFL = cfg->CFL; P.global_time_step = cfg->global_time_step;
   P.gm = cfg->gm; P.R_gas = cfg->R_gas; P.mu_ref = cfg->mu_ref; P.T_ref = cfg->T_ref; P.Sutherland_temp = cfg->Sutherland_temp;
   P.Pr = cfg->Pr; P.tPr = cfg->tPr;
+  P.inv_Pr = 1.0 / cfg->Pr; P.inv_tPr = 1.0 / cfg->tPr; P.inv_gm1 = 1.0 / (cfg->gm - 1.0);
   P.density_inf = cfg->density_inf; P.x_speed_inf = cfg->x_speed_inf; P.y_speed_inf = cfg->y_speed_inf; P.z_speed_inf = cfg->z_speed_inf;
   P.pressure_inf = cfg->pressure_inf; P.tk_inf = cfg->tk_inf; P.tw_inf = cfg->tw_inf; P.MInf = cfg->MInf;
   const double kappa = 0.41;

@@ -37,6 +37,7 @@ struct Params {
   double c1, c2, c3;
   double CFL, global_time_step;
   double gm, R_gas, mu_ref, T_ref, Sutherland_temp, Pr, tPr;
+  double inv_Pr, inv_tPr, inv_gm1;   // reciprocals of Pr, tPr, gm-1
   double density_inf, x_speed_inf, y_speed_inf, z_speed_inf, pressure_inf, tk_inf, tw_inf, MInf;
   double gama1, gama2, cd_floor, mut_floor, pk_limiter;
   double fixed[F3D_NFIX][6];

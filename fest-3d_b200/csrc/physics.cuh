@@ -13,6 +13,39 @@ __device__ constexpr double kBeta1 = 0.075, kBeta2 = 0.0828, kBstar = 0.09, kA1 
 
 __device__ __forceinline__ double sgn1(double x) { return copysign(1.0, x); }          // sign(1.0, x)
 __device__ __forceinline__ double sq(double x) { return x * x; }
+
+// FP64 reciprocal / reciprocal square root without the IEEE slow path: MUFU seed (>= 20 bits) + two Newton steps
+// (-> < 1 ulp before the final rounding).  An IEEE divide costs 14.4 DFMA issue slots on B200, this costs 5
+// (profiles/r01_fp64_ops_microbench.txt); results differ from a/b by <= ~1.5 ulp, five orders below the 1e-12 parity
+// tolerance.  Operands on this path are finite and far from the subnormal / overflow range; the places where the
+// reference relies on IEEE 0/0 or x/0 semantics (boundary_cell_face_values) keep the IEEE divide.
+__device__ __forceinline__ double rcp64(double b) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+  double e = fma(-b, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-b, r, 1.0);
+  return fma(r, e, r);
+}
+__device__ __forceinline__ double fdiv(double a, double b) { return a * rcp64(b); }
+// x > 0 only (rsqrt(0) = inf)
+__device__ __forceinline__ double rsqrt64(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  double e = fma(-hx * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-hx * y, y, 0.5);
+  return fma(y, e, y);
+}
+__device__ __forceinline__ double sqrt64(double x) {   // x > 0 only
+  const double y = rsqrt64(x);
+  const double s = x * y;
+  return fma(fma(-s, s, x), 0.5 * y, s);
+}
+// min / max as compare + select (no NaN operands on these call sites)
+__device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
+__device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
 // max(0, 1 - floor(abs(M))) of the Mach splittings: 1 inside |M| < 1, else 0
 __device__ __forceinline__ double subsonic(double M) { return fabs(M) < 1.0 ? 1.0 : 0.0; }
 
@@ -28,15 +61,20 @@ __device__ __forceinline__ void cell_face_values(const double* q, const double* 
     to_hi = q0; to_lo = q0;
   } else if (INTERP == F3D_MUSCL) {
     const double fd = qp1 - q0, bd = q0 - qm1;
-    double r = fd / (bd + copysign(1e-14, bd));
-    double psi1 = fmax(0., fmin(fmin(2 * r, (2. / 3.) * (r - 1.0) + 1.0), 2.));
-    r = bd / (fd + copysign(1e-14, fd));
-    double psi2 = fmax(0., fmin(fmin(2 * r, (2. / 3.) * (r - 1.0) + 1.0), 2.));
-    psi1 = (1 - (1 - psi1) * limiter);
-    psi2 = (1 - (1 - psi2) * limiter);
     const double kappa = 1. / 3.;
-    to_hi = q0 + 0.25 * (((1. - kappa) * psi1 * bd) + ((1. + kappa) * psi2 * fd));
-    to_lo = q0 - 0.25 * (((1. + kappa) * psi1 * bd) + ((1. - kappa) * psi2 * fd));
+    if (limiter == 0) {   // psi = 1 - (1 - psi)*0 = 1 exactly
+      to_hi = q0 + 0.25 * (((1. - kappa) * bd) + ((1. + kappa) * fd));
+      to_lo = q0 - 0.25 * (((1. + kappa) * bd) + ((1. - kappa) * fd));
+    } else {
+      double r = fd * rcp64(bd + copysign(1e-14, bd));
+      double psi1 = dmax(0., dmin(dmin(2 * r, (2. / 3.) * (r - 1.0) + 1.0), 2.));
+      r = bd * rcp64(fd + copysign(1e-14, fd));
+      double psi2 = dmax(0., dmin(dmin(2 * r, (2. / 3.) * (r - 1.0) + 1.0), 2.));
+      psi1 = (1 - (1 - psi1) * limiter);
+      psi2 = (1 - (1 - psi2) * limiter);
+      to_hi = q0 + 0.25 * (((1. - kappa) * psi1 * bd) + ((1. + kappa) * psi2 * fd));
+      to_lo = q0 - 0.25 * (((1. + kappa) * psi1 * bd) + ((1. - kappa) * psi2 * fd));
+    }
   } else if (INTERP == F3D_WENO) {
     const double eps = 1e-6;
     double t, s;
@@ -135,14 +173,28 @@ __device__ __forceinline__ void boundary_cell_face_values(double qm1, double q0,
 // Inviscid flux through one face, times the face area.  L/R = primitive (rho,u,v,w,p[,k,omega]).
 //   van_leer.f90:56-146, ldfss0.f90:57-161, ausm.f90:56-154, ausmP.f90:77-198, ausmUP.f90:88-216, slau.f90:82-204.
 // mask = make_{F,G,H}_flux_zero of the face (0 on wall / slip-wall / pole faces, bc.f90:53-66).
+// Returns the face-averaged speed of sound 0.5*(c_L + c_R) that the local time step uses (time.f90:159-175).
+// Divisions go through rcp64 (one reciprocal of each density and of the interface sound speed, reused).
 template <int NV>
-__device__ __forceinline__ void inviscid_flux(int scheme, double gm, double MInf, const double (&L)[NV], const double (&R)[NV],
-                                              double A, double nx, double ny, double nz, double mask, double (&F)[NV]) {
+__device__ __forceinline__ double inviscid_flux(int scheme, double gm, double MInf, const double (&L)[NV], const double (&R)[NV],
+                                                double A, double nx, double ny, double nz, double mask, bool flux_on, bool need_c,
+                                                double (&F)[NV]) {
   const double g1 = gm / (gm - 1.);
+  const double iL = rcp64(L[0]), iR = rcp64(R[0]);
+  double cbar = 0.0;
+  if (need_c || scheme <= F3D_AUSM || scheme == F3D_SLAU) cbar = 0.5 * (sqrt64(gm * L[4] * iL) + sqrt64(gm * R[4] * iR));
+  if (!flux_on) {
+#pragma unroll
+    for (int l = 0; l < NV; ++l) F[l] = 0.0;
+    return cbar;
+  }
+  const double VnL = L[1] * nx + L[2] * ny + L[3] * nz;
+  const double VnR = R[1] * nx + R[2] * ny + R[3] * nz;
+  const double HL = (0.5 * (L[1] * L[1] + L[2] * L[2] + L[3] * L[3])) + (g1 * L[4] * iL);
+  const double HR = (0.5 * (R[1] * R[1] + R[2] * R[2] + R[3] * R[3])) + (g1 * R[4] * iR);
   if (scheme <= F3D_AUSM) {  // van Leer, LDFSS(0), AUSM: shared Mach / pressure splitting
-    const double cbar = 0.5 * (sqrt(gm * L[4] / L[0]) + sqrt(gm * R[4] / R[0]));
-    const double ML = (L[1] * nx + L[2] * ny + L[3] * nz) / cbar;
-    const double MR = (R[1] * nx + R[2] * ny + R[3] * nz) / cbar;
+    const double ic = rcp64(cbar);
+    const double ML = VnL * ic, MR = VnR * ic;
     const double aP = 0.5 * (1.0 + sgn1(ML)), bL = -subsonic(ML);
     const double Mp = 0.25 * sq(1. + ML), Dp = 0.25 * sq(1. + ML) * (2. - ML);
     double cP = (aP * (1.0 + bL) * ML) - bL * Mp;
@@ -153,12 +205,13 @@ __device__ __forceinline__ void inviscid_flux(int scheme, double gm, double MInf
     const double sDm = (aM * (1. + bR)) - (bR * Dm);
     if (scheme == F3D_AUSM) {
       const double t = cP + cM;
-      cP = fmax(0., t); cM = fmin(0., t);
+      cP = dmax(0., t); cM = dmin(0., t);
     } else if (scheme == F3D_LDFSS0) {
       const double Ml = 0.25 * bL * bR * sq(sqrt((ML * ML + MR * MR) * 0.5) - 1);
       const double dp = L[4] - R[4];
-      cP = cP - Ml * (1 - dp / (2 * L[0] * (cbar * cbar)));
-      cM = cM + Ml * (1 - dp / (2 * R[0] * (cbar * cbar)));
+      const double ic2 = ic * ic;
+      cP = cP - Ml * (1 - dp * 0.5 * iL * ic2);
+      cM = cM + Ml * (1 - dp * 0.5 * iR * ic2);
     }
     const double mP = (L[0] * cbar * cP) * mask;
     const double mM = (R[0] * cbar * cM) * mask;
@@ -166,61 +219,58 @@ __device__ __forceinline__ void inviscid_flux(int scheme, double gm, double MInf
     F[1] = ((mP * L[1]) + (sDp * L[4] * nx)) * A + ((mM * R[1]) + (sDm * R[4] * nx)) * A;
     F[2] = ((mP * L[2]) + (sDp * L[4] * ny)) * A + ((mM * R[2]) + (sDm * R[4] * ny)) * A;
     F[3] = ((mP * L[3]) + (sDp * L[4] * nz)) * A + ((mM * R[3]) + (sDm * R[4] * nz)) * A;
-    F[4] = (mP * ((0.5 * (L[1] * L[1] + L[2] * L[2] + L[3] * L[3])) + (g1 * L[4] / L[0]))) * A +
-           (mM * ((0.5 * (R[1] * R[1] + R[2] * R[2] + R[3] * R[3])) + (g1 * R[4] / R[0]))) * A;
+    F[4] = (mP * HL) * A + (mM * HR) * A;
 #pragma unroll
     for (int l = 5; l < NV; ++l) F[l] = (mP * L[l]) * A + (mM * R[l]) * A;
-    return;
+    return cbar;
   }
-  const double HL = (0.5 * (L[1] * L[1] + L[2] * L[2] + L[3] * L[3])) + (g1 * L[4] / L[0]);
-  const double HR = (0.5 * (R[1] * R[1] + R[2] * R[2] + R[3] * R[3])) + (g1 * R[4] / R[0]);
-  const double VnL = L[1] * nx + L[2] * ny + L[3] * nz;
-  const double VnR = R[1] * nx + R[2] * ny + R[3] * nz;
   double mass, pbar;
   if (scheme == F3D_SLAU) {
-    const double C = 0.5 * (sqrt(gm * L[4] / L[0]) + sqrt(gm * R[4] / R[0]));
-    const double ML = VnL / C, MR = VnR / C;
-    const double aL = subsonic(ML), aR = subsonic(MR);
-    const double bL = (1.0 - aL) * 0.5 * (1.0 + sgn1(ML)) + aL * 0.25 * (2.0 - ML) * sq(ML + 1.0);
-    const double bR = (1.0 - aR) * 0.5 * (1.0 - sgn1(MR)) + aR * 0.25 * (2.0 + MR) * sq(MR - 1.0);
+    const double C = cbar;
+    const double iC = rcp64(C);
+    const double ML = VnL * iC, MR = VnR * iC;
+    const double sL = subsonic(ML), sR = subsonic(MR);
+    const double bL = (1.0 - sL) * 0.5 * (1.0 + sgn1(ML)) + sL * 0.25 * (2.0 - ML) * sq(ML + 1.0);
+    const double bR = (1.0 - sR) * 0.5 * (1.0 - sgn1(MR)) + sR * 0.25 * (2.0 + MR) * sq(MR - 1.0);
     const double vt = sqrt(0.5 * ((L[1] * L[1]) + (L[2] * L[2]) + (L[3] * L[3]) + (R[1] * R[1]) + (R[2] * R[2]) + (R[3] * R[3])));
-    const double Xi = sq(1.0 - fmin(1.0, vt / C));
-    const double Vnabs = (L[0] * fabs(VnL) + R[0] * fabs(VnR)) / (L[0] + R[0]);
-    const double fnG = -1.0 * fmax(fmin(ML, 0.0), -1.0) * fmin(fmax(MR, 0.0), 1.0);
+    const double Xi = sq(1.0 - dmin(1.0, vt * iC));
+    const double Vnabs = (L[0] * fabs(VnL) + R[0] * fabs(VnR)) * rcp64(L[0] + R[0]);
+    const double fnG = -1.0 * dmax(dmin(ML, 0.0), -1.0) * dmin(dmax(MR, 0.0), 1.0);
     pbar = 0.5 * ((L[4] + R[4]) + (bL - bR) * (L[4] - R[4]) + (1.0 - Xi) * (bL + bR - 1.0) * (L[4] + R[4]));
     const double VaL = (1.0 - fnG) * Vnabs + fnG * fabs(VnL);
     const double VaR = (1.0 - fnG) * Vnabs + fnG * fabs(VnR);
-    mass = 0.5 * ((L[0] * (VnL + VaL) + R[0] * (VnR - VaR)) - (Xi * (R[4] - L[4]) / C));
+    mass = 0.5 * ((L[0] * (VnL + VaL) + R[0] * (VnR - VaR)) - (Xi * (R[4] - L[4]) * iC));
   } else {  // AUSM+ and AUSM+-up
-    const double cs = sqrt(2.0 * (gm - 1.0) * (0.5 * (HL + HR)) / (gm + 1.0));
+    const double cs2 = 2.0 * (gm - 1.0) * (0.5 * (HL + HR)) / (gm + 1.0);
+    const double cs = sqrt64(cs2);
     const bool up = scheme == F3D_AUSMUP;
-    const double cL = cs * cs / fmax(cs, up ? VnL : fabs(VnL));
-    const double cR = cs * cs / fmax(cs, up ? -VnR : fabs(VnR));
-    const double C = fmin(cL, cR);
-    const double ML = VnL / C, MR = VnR / C;
+    const double cL = cs2 * rcp64(dmax(cs, up ? VnL : fabs(VnL)));
+    const double cR = cs2 * rcp64(dmax(cs, up ? -VnR : fabs(VnR)));
+    const double C = dmin(cL, cR);
+    const double iC = rcp64(C);
+    const double ML = VnL * iC, MR = VnR * iC;
     double alfa = 0.1875, fna = 1.0, Mb2 = 0.0;
     if (up) {
-      const double Mb = sqrt(0.5 * ((VnL * VnL) + (VnR * VnR)) / (C * C));
-      Mb2 = Mb * Mb;
-      const double Mo = sqrt(fmin(1.0, fmax(Mb2, MInf * MInf)));
+      Mb2 = 0.5 * ((VnL * VnL) + (VnR * VnR)) * (iC * iC);
+      const double Mo = sqrt(dmin(1.0, dmax(Mb2, MInf * MInf)));
       fna = Mo * (2.0 - Mo);
       alfa = 3.0 * (-4.0 + (5.0 * fna * fna)) / 16.0;
     }
-    const double aL = subsonic(ML), aR = subsonic(MR);
-    double FmL = (0.5 * (1.0 + sgn1(ML)) * (1.0 - aL) * ML) + aL * 0.25 * sq(1.0 + ML);
-    double bL = (0.5 * (1.0 + sgn1(ML)) * (1.0 - aL)) + aL * 0.25 * sq(1.0 + ML) * (2.0 - ML);
-    double FmR = (0.5 * (1.0 - sgn1(MR)) * (1.0 - aR) * MR) - aR * 0.25 * sq(1.0 - MR);
-    double bR = (0.5 * (1.0 - sgn1(MR)) * (1.0 - aR)) + aR * 0.25 * sq(1.0 - MR) * (2.0 + MR);
+    const double sL = subsonic(ML), sR = subsonic(MR);
+    double FmL = (0.5 * (1.0 + sgn1(ML)) * (1.0 - sL) * ML) + sL * 0.25 * sq(1.0 + ML);
+    double bL = (0.5 * (1.0 + sgn1(ML)) * (1.0 - sL)) + sL * 0.25 * sq(1.0 + ML) * (2.0 - ML);
+    double FmR = (0.5 * (1.0 - sgn1(MR)) * (1.0 - sR) * MR) - sR * 0.25 * sq(1.0 - MR);
+    double bR = (0.5 * (1.0 - sgn1(MR)) * (1.0 - sR)) + sR * 0.25 * sq(1.0 - MR) * (2.0 + MR);
     const double tL = sq(ML * ML - 1.0), tR = sq(MR * MR - 1.0);
-    FmL = FmL + aL * 0.125 * tL;
-    bL = bL + aL * alfa * tL * ML;
-    FmR = FmR - aR * 0.125 * tR;
-    bR = bR - aR * alfa * tR * MR;
+    FmL = FmL + sL * 0.125 * tL;
+    bL = bL + sL * alfa * tL * ML;
+    FmR = FmR - sR * 0.125 * tR;
+    bR = bR - sR * alfa * tR * MR;
     double Mface = FmL + FmR;
     pbar = bL * L[4] + bR * R[4];
     if (up) {
       const double Pu = -0.75 * bL * bR * (L[0] + R[0]) * fna * C * (VnR - VnL);
-      const double Mp = -2.0 * 0.25 * fmax(1.0 - (1.0 * Mb2), 0.0) * (R[4] - L[4]) / (fna * (L[0] + R[0]) * C * C);
+      const double Mp = -2.0 * 0.25 * dmax(1.0 - (1.0 * Mb2), 0.0) * (R[4] - L[4]) * rcp64(fna * (L[0] + R[0]) * C * C);
       Mface = FmL + FmR + Mp;
       pbar = bL * L[4] + bR * R[4] + Pu;
     }
@@ -235,12 +285,7 @@ __device__ __forceinline__ void inviscid_flux(int scheme, double gm, double MInf
   F[4] = ((mP * HL) + (mM * HR)) * A;
 #pragma unroll
   for (int l = 5; l < NV; ++l) F[l] = ((mP * L[l]) + (mM * R[l])) * A;
-}
-
-// face-averaged speed of sound used by the local time step (time.f90:159-175)
-template <int NV>
-__device__ __forceinline__ double face_sound_speed(double gm, const double (&L)[NV], const double (&R)[NV]) {
-  return 0.5 * (sqrt(gm * L[4] / L[0]) + sqrt(gm * R[4] / R[0]));
+  return cbar;
 }
 
 }  // namespace f3d

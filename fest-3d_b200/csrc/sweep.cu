@@ -102,14 +102,15 @@ __device__ __forceinline__ void viscous_face(const Params& P, const KArgs& a, lo
   const double* __restrict__ q = a.q;
   const double* __restrict__ gc = a.geom + (long long)G_CX * fs;
   const double dx = gc[hi] - gc[lo], dy = gc[fs + hi] - gc[fs + lo], dz = gc[2 * fs + hi] - gc[2 * fs + lo];
-  const double d_LR = sqrt(dx * dx + dy * dy + dz * dz);
+  const double inv_d = rsqrt64(dx * dx + dy * dy + dz * dz);   // 1 / d_LR
+  const double ex = dx * inv_d, ey = dy * inv_d, ez = dz * inv_d;
   double ql[NV], qh[NV];
 #pragma unroll
   for (int v = 0; v < NV; ++v) { ql[v] = q[v * fs + lo]; qh[v] = q[v * fs + hi]; }
   double del[NG];
   del[0] = qh[1] - ql[1]; del[1] = qh[2] - ql[2]; del[2] = qh[3] - ql[3];
   {
-    const double T_LE = ql[4] / (ql[0] * P.R_gas), T_RE = qh[4] / (qh[0] * P.R_gas);
+    const double T_LE = ql[4] * rcp64(ql[0] * P.R_gas), T_RE = qh[4] * rcp64(qh[0] * P.R_gas);
     del[3] = T_RE - T_LE;
   }
   if (SST) { del[4] = qh[5] - ql[5]; del[5] = qh[6] - ql[6]; }
@@ -118,20 +119,20 @@ __device__ __forceinline__ void viscous_face(const Params& P, const KArgs& a, lo
   for (int c = 0; c < NG; ++c) {
     const double* __restrict__ g0 = a.grad + (long long)(3 * c) * fs;
     const double ax = 0.5 * (g0[lo] + g0[hi]), ay = 0.5 * (g0[fs + lo] + g0[fs + hi]), az = 0.5 * (g0[2 * fs + lo] + g0[2 * fs + hi]);
-    const double nc = (del[c] - (ax * dx + ay * dy + az * dz)) / d_LR;
-    G[c][0] = ax + (nc * dx / d_LR);
-    G[c][1] = ay + (nc * dy / d_LR);
-    G[c][2] = az + (nc * dz / d_LR);
+    const double nc = (del[c] - (ax * dx + ay * dy + az * dz)) * inv_d;
+    G[c][0] = ax + (nc * ex);
+    G[c][1] = ay + (nc * ey);
+    G[c][2] = az + (nc * ez);
   }
   const double mu_hi = a.mu[hi];
   const double mu_f = 0.5 * (a.mu[lo] + mu_hi);
   const double mut_hi = SST ? a.mu[fs + hi] : 0.0;
   const double mut_f = SST ? 0.5 * (a.mu[fs + lo] + mut_hi) : 0.0;
   const double tmu = mu_f + mut_f;
-  const double div3 = (G[0][0] + G[1][1] + G[2][2]) / 3.;
+  const double div3 = (G[0][0] + G[1][1] + G[2][2]) * (1. / 3.);
   const double Txx = 2. * tmu * (G[0][0] - div3), Tyy = 2. * tmu * (G[1][1] - div3), Tzz = 2. * tmu * (G[2][2] - div3);
   const double Txy = tmu * (G[1][0] + G[0][1]), Txz = tmu * (G[2][0] + G[0][2]), Tyz = tmu * (G[2][1] + G[1][2]);
-  const double Kh = (mu_f / P.Pr + mut_f / P.tPr) * P.gm * P.R_gas / (P.gm - 1);
+  const double Kh = (mu_f * P.inv_Pr + mut_f * P.inv_tPr) * P.gm * P.R_gas * P.inv_gm1;
   const double Qx = Kh * G[3][0], Qy = Kh * G[3][1], Qz = Kh * G[3][2];
   const double uf = 0.5 * (ql[1] + qh[1]), vf = 0.5 * (ql[2] + qh[2]), wf = 0.5 * (ql[3] + qh[3]);
   F[1] = F[1] - ((Txx * nx + Txy * ny + Txz * nz) * A);
@@ -145,7 +146,7 @@ __device__ __forceinline__ void viscous_face(const Params& P, const KArgs& a, lo
     const double sw = kSigmaW1 * F1 + kSigmaW2 * (1.0 - F1);
     const double rhof = 0.5 * (ql[0] + qh[0]);
     const double tkf = 0.5 * (ql[NV - 2] + qh[NV - 2]);
-    const double Tk = -2.0 * rhof * tkf / 3.0;
+    const double Tk = -2.0 * rhof * tkf * (1. / 3.);
     const double dk = (A * ((mu_f + sk * mut_f) * (G[NG - 2][0] * nx + G[NG - 2][1] * ny + G[NG - 2][2] * nz)));
     const double dw = (A * ((mu_f + sw * mut_f) * (G[NG - 1][0] * nx + G[NG - 1][1] * ny + G[NG - 1][2] * nz)));
     F[1] = F[1] - (Tk * nx * A);
@@ -157,8 +158,9 @@ __device__ __forceinline__ void viscous_face(const Params& P, const KArgs& a, lo
   }
   if (need_dt) {
     const double dn = fabs(((-dx) * nx) + ((-dy) * ny) + ((-dz) * nz));
-    vis = A * (mu_hi / (qh[0] * dn));
-    if (SST) tur = A * (mut_hi / (qh[0] * dn));
+    const double w = A * rcp64(qh[0] * dn);
+    vis = w * mu_hi;
+    if (SST) tur = w * mut_hi;
   }
 }
 
@@ -190,15 +192,11 @@ __device__ __forceinline__ void face_eval(const Params& P, const KArgs& a, int d
   }
   const double* __restrict__ gA = a.geom + (long long)(G_IA + 4 * d) * fs;
   const double A = gA[X], nx = gA[fs + X], ny = gA[2 * fs + X], nz = gA[3 * fs + X];
-#pragma unroll
-  for (int v = 0; v < NV; ++v) F[v] = 0.0;
-  if (flux_on) {
-    const double mask = (f == 1) ? P.zlo[d] : ((f == m) ? P.zhi[d] : 1.0);
-    inviscid_flux<NV>(SCHEME >= 0 ? SCHEME : P.scheme, P.gm, P.MInf, L, R, A, nx, ny, nz, mask, F);
-  }
+  const double mask = (f == 1) ? P.zlo[d] : ((f == m) ? P.zhi[d] : 1.0);
+  const double cbar = inviscid_flux<NV>(SCHEME >= 0 ? SCHEME : P.scheme, P.gm, P.MInf, L, R, A, nx, ny, nz, mask, flux_on, need_dt, F);
   if (need_dt) {   // time.f90:159-237: both cells of a face use the velocity of the cell on its high side
     const double vn = fabs((q[1 * fs + X] * nx) + (q[2 * fs + X] * ny) + (q[3 * fs + X] * nz));
-    lam = A * (vn + face_sound_speed<NV>(P.gm, L, R));
+    lam = A * (vn + cbar);
   }
   if (VISC) viscous_face<NV>(P, a, X - s, X, A, nx, ny, nz, (NV == 7) && flux_on, need_dt, F, vis, tur);
 }
@@ -359,8 +357,8 @@ __global__ void __launch_bounds__(NT, 1) k_sweep(const Params P, const KArgs a) 
       const double density = qc[0], tk = qc[5], tw = qc[6];
       const double wx = g[2][1] - g[1][2], wy = g[0][2] - g[2][0], wz = g[1][0] - g[0][1];
       const double vort = sqrt(wx * wx + wy * wy + wz * wz);
-      double CD = 2 * density * kSigmaW2 * (g[4][0] * g[5][0] + g[4][1] * g[5][1] + g[4][2] * g[5][2]) / tw;
-      CD = fmax(CD, P.cd_floor);
+      double CD = 2 * density * kSigmaW2 * (g[4][0] * g[5][0] + g[4][1] * g[5][1] + g[4][2] * g[5][2]) * rcp64(tw);
+      CD = dmax(CD, P.cd_floor);
       const double F1 = a.mu[2 * fs + c];
       const double gama = P.gama1 * F1 + P.gama2 * (1. - F1);
       const double beta = kBeta1 * F1 + kBeta2 * (1. - F1);
@@ -368,8 +366,8 @@ __global__ void __launch_bounds__(NT, 1) k_sweep(const Params P, const KArgs a) 
       const double D_w = beta * density * (tw * tw);
       const double divergence = g[0][0] + g[1][1] + g[2][2];
       double P_k = mut * (vort * vort) - ((2.0 / 3.0) * density * tk * divergence);
-      P_k = fmin(P_k, P.pk_limiter * D_k);
-      const double P_w = (density * gama / mut) * P_k;
+      P_k = dmin(P_k, P.pk_limiter * D_k);
+      const double P_w = (density * gama * rcp64(mut)) * P_k;
       const double lamda = (1. - F1) * CD;
       const double S_k = (P_k - D_k) * volc;
       const double S_w = (P_w - D_w + lamda) * volc;
@@ -384,19 +382,19 @@ __global__ void __launch_bounds__(NT, 1) k_sweep(const Params P, const KArgs a) 
       } else {
         const double* lamv = sm_F + NV * SLOT_HF;
         const double lmxsum = lamv[sl[0]] + lamv[sl[1]] + lamv[sl[2]] + lamv[sh[0]] + lamv[sh[1]] + lamv[sh[2]];
-        dtc = 1. / lmxsum;
+        dtc = rcp64(lmxsum);
         dtc = dtc * volc * P.CFL;
         if (VISC) {
           const double* visv = sm_F + (NV + 1) * SLOT_HF;
           double s = visv[sl[0]] + visv[sl[1]] + visv[sl[2]] + visv[sh[0]] + visv[sh[1]] + visv[sh[2]];
-          s = P.gm * s / P.Pr;
-          s = 2. / (s + (2. * P.CFL * volc / dtc));
+          s = P.gm * s * P.inv_Pr;
+          s = 2. * rcp64(s + (2. * P.CFL * volc * rcp64(dtc)));
           dtc = P.CFL * (s * volc);
           if (SST) {
             const double* turv = sm_F + (NV + 2) * SLOT_HF;
             double t = turv[sl[0]] + turv[sl[1]] + turv[sl[2]] + turv[sh[0]] + turv[sh[1]] + turv[sh[2]];
-            t = P.gm * t / P.tPr;
-            t = 2. / (t + (2. * P.CFL * volc / dtc));
+            t = P.gm * t * P.inv_tPr;
+            t = 2. * rcp64(t + (2. * P.CFL * volc * rcp64(dtc)));
             dtc = P.CFL * (t * volc);
           }
         }
@@ -416,12 +414,12 @@ __global__ void __launch_bounds__(NT, 1) k_sweep(const Params P, const KArgs a) 
       u1[0] = a.quse[c];
 #pragma unroll
       for (int v = 1; v < NV; ++v) u1[v] = a.quse[v * fs + c] * u1[0];
-      u1[4] = (u1[4] / (P.gm - 1.) + 0.5 * (u1[1] * u1[1] + u1[2] * u1[2] + u1[3] * u1[3])) / u1[0] + 0.;
+      u1[4] = (u1[4] * P.inv_gm1 + 0.5 * (u1[1] * u1[1] + u1[2] * u1[2] + u1[3] * u1[3])) * rcp64(u1[0]) + 0.;
       if (SST) {
         const double F1 = a.mu[2 * fs + c];
         const double beta = kBeta1 * F1 + (1. - F1) * kBeta2;
-        R[5] = R[5] / (1 + (beta * qc[6] * dtc));
-        R[6] = R[6] / (1 + (2 * beta * qc[6] * dtc));
+        R[5] = R[5] * rcp64(1 + (beta * qc[6] * dtc));
+        R[6] = R[6] * rcp64(1 + (2 * beta * qc[6] * dtc));
       }
       if (a.have_store) {
 #pragma unroll
@@ -431,11 +429,12 @@ __global__ void __launch_bounds__(NT, 1) k_sweep(const Params P, const KArgs a) 
           if (a.use_store_sum) R[v] = rn;
         }
       }
-      const double fac_ = (a.TF * dtc / volc);
+      const double fac_ = (a.TF * dtc * rcp64(volc));
 #pragma unroll
       for (int v = 0; v < NV; ++v) u2[v] = u1[v] - R[v] * fac_;
+      const double iu = 1.0 / u2[0];   // IEEE: u2[0] may be <= 0 or NaN here and must reach the check below unchanged
 #pragma unroll
-      for (int v = 1; v < NV; ++v) u2[v] = u2[v] / u2[0];
+      for (int v = 1; v < NV; ++v) u2[v] = u2[v] * iu;
       u2[4] = (P.gm - 1.) * u2[0] * (u2[4] - (0.5 * (u2[1] * u2[1] + u2[2] * u2[2] + u2[3] * u2[3])) - 0.);
       bool bad = (u2[0] < 0.) || (u2[4] < 0.);
 #pragma unroll
