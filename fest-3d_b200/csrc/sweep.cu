@@ -1,21 +1,22 @@
-// Fused residual / time-step / update kernel, generation 1 ("plane sweep").
+// Fused residual / time-step / update kernel, generation 2 ("plane sweep with staged cell records").
 //
-// One CTA owns a TX x TY column of cells and marches through a chunk of k planes.  Per plane every cell reconstructs its
-// own face values ONCE per direction, every face flux (inviscid + viscous + the face terms of the local time step) is
-// evaluated ONCE by the thread of the cell on its high side, and the results are exchanged through shared memory:
+// One CTA owns a TX x TY column of cells and marches through a chunk of k planes.  The per-cell record of a plane
+// (primitive state, Green-Gauss gradients, mu / mu_t / F1, cell centre) is staged ONCE in shared memory -- the tile plus a
+// one-cell ring, two planes deep (k and k+1), filled by cp.async while the previous plane is being worked on -- so every
+// neighbour access of the reconstruction, of the viscous face flux and of the time-step terms is an LDS with an
+// immediate offset instead of a dependent global load (generation 1 was stalled on exactly those: profiles/r01_g1_*).
+// Per plane every cell reconstructs its face values ONCE per direction, every face flux (inviscid + viscous + the face
+// terms of the local time step) is evaluated ONCE by the thread of the cell on its high side:
 //
-//   phase 1  reconstruct (cell -> value at its high face "hi", value at its low face "lo")        -> smem hi / lo
-//   phase 2  face flux   (L = hi of the low neighbour, R = lo of this cell)                        -> smem F
-//   phase 3  cell        residual = (F(i+1)-F(i)) + (G(j+1)-G(j)) + (H(k+1)-H(k)), SST source, local time step,
-//                        point-implicit k/omega scaling, RK accumulate, conservative update, norms
+//   i, j   reconstruct -> hi value to smem | barrier | L = hi of the low neighbour, R = own lo -> flux -> smem
+//   k      same thread: hi value and low-face flux of the previous plane are carried in registers
+//   cell   residual = (F(i+1)-F(i)) + (G(j+1)-G(j)) + (H(k+1)-H(k)), SST source, local time step, point-implicit k/omega
+//          scaling, RK accumulate, conservative update, norm partials
 //
-// The k direction needs no neighbour thread: the hi value and the low-face flux of the previous plane stay in a
-// thread-private ping-pong slot.  Cells just outside the tile in i and j are served by three extra "halo" warps
-// (one for the two i columns, one for the low j row, one for the high j row), so no face is computed twice inside a
-// tile and only (TX+1)/TX, (TY+1)/TY of the faces are computed twice across tiles.  The direction loop is NOT
-// unrolled: one instance of the reconstruction and one of the flux code (the v0 kernel had 0.58 MB of SASS and was
-// instruction-fetch bound, profiles/r01_v0_summary.md).  No face-state, flux or residual array reaches HBM on the
-// update path; the residual-norm partials are reduced in-kernel (warp shuffle + block).
+// Cells just outside the tile in i and j are served by three extra "halo" warps (the two i columns, the low j row, the
+// high j row), so no face is computed twice inside a tile.  The i/j direction loop is NOT unrolled (one code instance;
+// the v0 kernel had 0.58 MB of SASS and was instruction-fetch bound, profiles/r01_v0_summary.md).  No face-state, flux
+// or residual array reaches HBM on the update path.
 //
 // Reference pipeline reproduced (src/update.f90:534-545, 228-491; src/face/state/*.f90;
 // src/boundary/boundary_state_reconstruction.f90:93-131; src/face/flux/convective/*.f90 and scheme.f90:111-141;
@@ -25,23 +26,46 @@
 
 namespace f3d {
 
-constexpr int TX = 32, TY = 8;
+#ifndef F3D_TY
+#define F3D_TY 5
+#endif
+constexpr int TX = 32, TY = F3D_TY;
 constexpr int NMAIN = TX * TY;
 constexpr int NT = NMAIN + 96;   // + i-halo warp, low-j-halo warp, high-j-halo warp
 
-// shared-memory slot counts per direction (slots are [variable][slot], variable-major)
+// staged plane: (TX+2) x (TY+2) slots, slot = (ty+1)*PW + (tx+1); the q fields carry NOUT extra slots for the second
+// ring cells the halo threads' own reconstruction reads
+constexpr int PW = TX + 2;
+constexpr int PS = PW * (TY + 2);
+constexpr int NOUT = 2 * TY + 2 * TX;
+constexpr int PSQ = PS + NOUT;
+// exchange buffers ([variable][slot]): i faces TY x (TX+1), j faces (TY+1) x TX
 constexpr int SLOT_I = TY * (TX + 1);
 constexpr int SLOT_J = (TY + 1) * TX;
-constexpr int SLOT_K = 2 * NMAIN;
-constexpr int SLOT_HF = SLOT_I + SLOT_J + SLOT_K;   // slots of one hi (or F) buffer family
-constexpr int SLOT_LO = 3 * NMAIN + 64;             // private lo slots: main threads x 3 directions + the halo-high tasks
+constexpr int EX = SLOT_I + SLOT_J;
 
-__host__ __device__ constexpr int sweep_smem_doubles(int nv) { return nv * SLOT_HF + nv * SLOT_LO + (nv + 3) * SLOT_HF; }
+template <int NV, bool VISC>
+struct Rec {   // fields of the non-q part of a cell record
+  static constexpr bool SST = (NV == 7);
+  static constexpr int NG = SST ? 6 : 4;
+  static constexpr int NGF = VISC ? 3 * NG : 0;            // gradient component c, direction d -> field 3*c+d
+  static constexpr int NMU = VISC ? (SST ? 3 : 1) : 0;     // mu, mu_t, F1
+  static constexpr int OFF_MU = NGF, OFF_C = NGF + NMU;    // then the cell centre x,y,z
+  static constexpr int NR = VISC ? NGF + NMU + 3 : 0;
+  static constexpr int PLANE = NV * PSQ + NR * PS;         // doubles per staged plane
+  static constexpr int SMEM = 2 * PLANE + NV * EX + (NV + 3) * EX;
+};
 
 __device__ __forceinline__ void flag_error(int* err, int cls, int i, int j, int k) {
   int old = atomicOr(&err[0], cls);
   if ((old & cls) == 0) { err[1] = i; err[2] = j; err[3] = k; }
 }
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 struct KArgs {
   const double* __restrict__ q;       // nv fields, ghost-filled
@@ -90,23 +114,44 @@ __device__ __forceinline__ void line_cell_values(const Params& P, const double* 
   }
 }
 
+
+// MUSCL / first-order values of one cell along one direction from three staged values per variable
+// (muscl.f90:161-196; boundary_state_reconstruction.f90:93-123 for the first / last interior cell when ppm_flag is set)
+template <int NV, int INTERP>
+__device__ __forceinline__ void recon3(const Params& P, const double (&qm)[NV], const double (&q0)[NV], const double (&qp)[NV], int pos, int mx,
+                                       int dir, double (&to_hi)[NV], double (&to_lo)[NV]) {
+  const bool redo = (INTERP != F3D_INTERP_NONE) && P.ppm_flag && ((pos == 1 && P.phys[2 * dir]) || (pos == mx - 1 && P.phys[2 * dir + 1]));
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int lim = (v >= 5) ? P.tlimiter[dir] : P.limiter[dir];
+    if (redo) {
+      boundary_cell_face_values(qm[v], q0[v], qp[v], lim, to_hi[v], to_lo[v]);
+    } else {
+      double ql[7];
+      ql[2] = qm[v]; ql[3] = q0[v]; ql[4] = qp[v];
+      cell_face_values<INTERP>(ql, ql, lim, to_hi[v], to_lo[v]);
+    }
+  }
+}
+
 // F <- (F - laminar) - sst for the face between cells lo and hi (viscous.f90:209-323, 378-446); also the face terms
 // A*mu/(rho*|dr.n|), A*mu_t/(rho*|dr.n|) of the viscous / turbulent time-step corrections (time.f90:396-421, 479-504:
-// both cells that share a face use the mu and density of the cell on its high side).
+// both cells that share a face use the mu and density of the cell on its high side).  ql/qh: staged q of the two cells
+// (field stride PSQ), rl/rh: their staged records (field stride PS).
 template <int NV>
-__device__ __forceinline__ void viscous_face(const Params& P, const KArgs& a, long long lo, long long hi, double A, double nx, double ny,
+__device__ __forceinline__ void viscous_face(const Params& P, const double* __restrict__ ql_, const double* __restrict__ qh_,
+                                             const double* __restrict__ rl, const double* __restrict__ rh, double A, double nx, double ny,
                                              double nz, bool sst_on, bool need_dt, double (&F)[NV], double& vis, double& tur) {
+  using R = Rec<NV, true>;
   constexpr bool SST = (NV == 7);
-  constexpr int NG = SST ? 6 : 4;
-  const long long fs = P.L.fs;
-  const double* __restrict__ q = a.q;
-  const double* __restrict__ gc = a.geom + (long long)G_CX * fs;
-  const double dx = gc[hi] - gc[lo], dy = gc[fs + hi] - gc[fs + lo], dz = gc[2 * fs + hi] - gc[2 * fs + lo];
+  constexpr int NG = R::NG;
+  const double dx = rh[(R::OFF_C + 0) * PS] - rl[(R::OFF_C + 0) * PS], dy = rh[(R::OFF_C + 1) * PS] - rl[(R::OFF_C + 1) * PS],
+               dz = rh[(R::OFF_C + 2) * PS] - rl[(R::OFF_C + 2) * PS];
   const double inv_d = rsqrt64(dx * dx + dy * dy + dz * dz);   // 1 / d_LR
   const double ex = dx * inv_d, ey = dy * inv_d, ez = dz * inv_d;
   double ql[NV], qh[NV];
 #pragma unroll
-  for (int v = 0; v < NV; ++v) { ql[v] = q[v * fs + lo]; qh[v] = q[v * fs + hi]; }
+  for (int v = 0; v < NV; ++v) { ql[v] = ql_[v * PSQ]; qh[v] = qh_[v * PSQ]; }
   double del[NG];
   del[0] = qh[1] - ql[1]; del[1] = qh[2] - ql[2]; del[2] = qh[3] - ql[3];
   {
@@ -117,17 +162,17 @@ __device__ __forceinline__ void viscous_face(const Params& P, const KArgs& a, lo
   double G[NG][3];
 #pragma unroll
   for (int c = 0; c < NG; ++c) {
-    const double* __restrict__ g0 = a.grad + (long long)(3 * c) * fs;
-    const double ax = 0.5 * (g0[lo] + g0[hi]), ay = 0.5 * (g0[fs + lo] + g0[fs + hi]), az = 0.5 * (g0[2 * fs + lo] + g0[2 * fs + hi]);
+    const double ax = 0.5 * (rl[(3 * c) * PS] + rh[(3 * c) * PS]), ay = 0.5 * (rl[(3 * c + 1) * PS] + rh[(3 * c + 1) * PS]),
+                 az = 0.5 * (rl[(3 * c + 2) * PS] + rh[(3 * c + 2) * PS]);
     const double nc = (del[c] - (ax * dx + ay * dy + az * dz)) * inv_d;
     G[c][0] = ax + (nc * ex);
     G[c][1] = ay + (nc * ey);
     G[c][2] = az + (nc * ez);
   }
-  const double mu_hi = a.mu[hi];
-  const double mu_f = 0.5 * (a.mu[lo] + mu_hi);
-  const double mut_hi = SST ? a.mu[fs + hi] : 0.0;
-  const double mut_f = SST ? 0.5 * (a.mu[fs + lo] + mut_hi) : 0.0;
+  const double mu_hi = rh[R::OFF_MU * PS];
+  const double mu_f = 0.5 * (rl[R::OFF_MU * PS] + mu_hi);
+  const double mut_hi = SST ? rh[(R::OFF_MU + 1) * PS] : 0.0;
+  const double mut_f = SST ? 0.5 * (rl[(R::OFF_MU + 1) * PS] + mut_hi) : 0.0;
   const double tmu = mu_f + mut_f;
   const double div3 = (G[0][0] + G[1][1] + G[2][2]) * (1. / 3.);
   const double Txx = 2. * tmu * (G[0][0] - div3), Tyy = 2. * tmu * (G[1][1] - div3), Tzz = 2. * tmu * (G[2][2] - div3);
@@ -141,7 +186,7 @@ __device__ __forceinline__ void viscous_face(const Params& P, const KArgs& a, lo
   F[4] = F[4] - (A * (((Txx * uf + Txy * vf + Txz * wf + Qx) * nx) + ((Txy * uf + Tyy * vf + Tyz * wf + Qy) * ny) +
                       ((Txz * uf + Tyz * vf + Tzz * wf + Qz) * nz)));
   if (SST && sst_on) {
-    const double F1 = 0.5 * (a.mu[2 * fs + lo] + a.mu[2 * fs + hi]);
+    const double F1 = 0.5 * (rl[(R::OFF_MU + 2) * PS] + rh[(R::OFF_MU + 2) * PS]);
     const double sk = kSigmaK1 * F1 + kSigmaK2 * (1.0 - F1);
     const double sw = kSigmaW1 * F1 + kSigmaW2 * (1.0 - F1);
     const double rhof = 0.5 * (ql[0] + qh[0]);
@@ -165,19 +210,23 @@ __device__ __forceinline__ void viscous_face(const Params& P, const KArgs& a, lo
 }
 
 // One face: boundary overrides of the states (boundary_state_reconstruction.f90:124-131), inviscid flux times area
-// (scheme.f90:68-109), viscous flux, and the face terms of the time step.  X = cell on the high side, f = its index
-// along direction d (the face index), m = node count along d.
+// (scheme.f90:68-109), viscous flux, and the face terms of the time step.  ql/qh, rl/rh: staged q / record of the cells on
+// the low / high side; X = global index of the high cell (= of the face in the face arrays), f = the face index along
+// direction d, m = node count along d.
 template <int NV, int SCHEME, bool VISC>
-__device__ __forceinline__ void face_eval(const Params& P, const KArgs& a, int d, long long X, long long s, int f, int m, double (&L)[NV],
-                                          double (&R)[NV], bool flux_on, bool need_dt, double (&F)[NV], double& lam, double& vis, double& tur) {
+__device__ __forceinline__ void face_eval(const Params& P, const KArgs& a, int d, const double* __restrict__ ql, const double* __restrict__ qh,
+                                          const double* __restrict__ rl, const double* __restrict__ rh, long long X, int f, int m,
+                                          double (&L)[NV], double (&R)[NV], bool flux_on, bool need_dt, double (&F)[NV], double& lam,
+                                          double& vis, double& tur) {
   const long long fs = P.L.fs;
-  const double* __restrict__ q = a.q;
+  const double* __restrict__ gA = a.geom + (long long)(G_IA + 4 * d) * fs;
+  const double A = gA[X], nx = gA[fs + X], ny = gA[2 * fs + X], nz = gA[3 * fs + X];
   if (P.interpolant != F3D_INTERP_NONE) {
     if (f == 1 && P.phys[2 * d]) {
       const bool far = P.farlike[2 * d] != 0;
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
-        const double g = q[v * fs + X - s], in = q[v * fs + X];
+        const double g = ql[v * PSQ], in = qh[v * PSQ];
         if (far) { L[v] = g; R[v] = g; } else { L[v] = 0.5 * (g + in); }
       }
     }
@@ -185,30 +234,28 @@ __device__ __forceinline__ void face_eval(const Params& P, const KArgs& a, int d
       const bool far = P.farlike[2 * d + 1] != 0;
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
-        const double in = q[v * fs + X - s], g = q[v * fs + X];
+        const double in = ql[v * PSQ], g = qh[v * PSQ];
         if (far) { L[v] = g; R[v] = g; } else { R[v] = 0.5 * (in + g); }
       }
     }
   }
-  const double* __restrict__ gA = a.geom + (long long)(G_IA + 4 * d) * fs;
-  const double A = gA[X], nx = gA[fs + X], ny = gA[2 * fs + X], nz = gA[3 * fs + X];
   const double mask = (f == 1) ? P.zlo[d] : ((f == m) ? P.zhi[d] : 1.0);
   const double cbar = inviscid_flux<NV>(SCHEME >= 0 ? SCHEME : P.scheme, P.gm, P.MInf, L, R, A, nx, ny, nz, mask, flux_on, need_dt, F);
   if (need_dt) {   // time.f90:159-237: both cells of a face use the velocity of the cell on its high side
-    const double vn = fabs((q[1 * fs + X] * nx) + (q[2 * fs + X] * ny) + (q[3 * fs + X] * nz));
+    const double vn = fabs((qh[1 * PSQ] * nx) + (qh[2 * PSQ] * ny) + (qh[3 * PSQ] * nz));
     lam = A * (vn + cbar);
   }
-  if (VISC) viscous_face<NV>(P, a, X - s, X, A, nx, ny, nz, (NV == 7) && flux_on, need_dt, F, vis, tur);
+  if (VISC) viscous_face<NV>(P, ql, qh, rl, rh, A, nx, ny, nz, (NV == 7) && flux_on, need_dt, F, vis, tur);
 }
 
 template <int NV, int INTERP, int SCHEME, bool VISC>
 __global__ void __launch_bounds__(NT, 1) k_sweep(const Params P, const KArgs a) {
+  using RC = Rec<NV, VISC>;
   constexpr bool SST = (NV == 7);
-  constexpr int NF = NV + 3;
+  constexpr bool SMQ = (INTERP == F3D_MUSCL || INTERP == F3D_INTERP_NONE);   // 3-point stencils read the staged planes
   extern __shared__ double smem[];
-  double* const sm_hi = smem;                          // [NV][SLOT_HF]
-  double* const sm_lo = sm_hi + NV * SLOT_HF;          // [NV][SLOT_LO]
-  double* const sm_F = sm_lo + NV * SLOT_LO;           // [NF][SLOT_HF]
+  double* const sm_hi = smem + 2 * RC::PLANE;          // [NV][EX]
+  double* const sm_F = sm_hi + NV * EX;                // [NV+3][EX]
   const Layout& Ly = P.L;
   const long long fs = Ly.fs;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -219,244 +266,335 @@ __global__ void __launch_bounds__(NT, 1) k_sweep(const Params P, const KArgs a) 
   const bool k_active = flux_on_k || VISC || need_dt;
 
   // ---- role of this thread ------------------------------------------------------------------------------------------
-  int i, j;
-  bool own = false;                 // finishes a cell in phase 3
-  bool rec[2] = {false, false};     // reconstructs along i / j
-  bool fac[2] = {false, false};     // evaluates its low face along i / j
-  int whi[2] = {0, 0}, rhi[2] = {0, 0}, wf[2] = {0, 0}, plo[2] = {0, 0};   // smem slots (relative to the direction's base)
+  int i, j, s0;                     // cell of this thread in the plane and its staged slot
+  int dirh = -1;                    // halo threads: the one direction they serve
+  bool act, stg, own = false;       // act: reconstructs / evaluates faces; stg: stages its cell record (a superset)
+  bool rec0 = false, rec1 = false, fac0 = false, fac1 = false, wr_hi = true;
+  int sminus = 0, splus = 0;        // halo threads: staged slots of the two neighbours along dirh (one of them an outer slot)
+  int xhi = 0, xlo = 0;             // exchange slots: where the hi value / flux is written, where L / the high-face flux is read
+  long long outer_off = 0;          // global offset (relative to the own cell) of the outer neighbour a halo thread stages
+  int outer_slot = 0;
   if (wid < TY) {
     const int tx = lane, ty = wid;
     i = i0 + tx; j = j0 + ty;
     own = (i <= Ly.imx - 1) && (j <= Ly.jmx - 1);
-    rec[0] = fac[0] = (j <= Ly.jmx - 1) && (i <= Ly.imx);
-    rec[1] = fac[1] = (i <= Ly.imx - 1) && (j <= Ly.jmx);
-    whi[0] = ty * (TX + 1) + tx + 1; rhi[0] = ty * (TX + 1) + tx; wf[0] = ty * (TX + 1) + tx; plo[0] = tid;
-    whi[1] = (ty + 1) * TX + tx; rhi[1] = ty * TX + tx; wf[1] = ty * TX + tx; plo[1] = NMAIN + tid;
+    rec0 = fac0 = (j <= Ly.jmx - 1) && (i <= Ly.imx);
+    rec1 = fac1 = (i <= Ly.imx - 1) && (j <= Ly.jmx);
+    act = rec0 || rec1;
+    stg = (i <= Ly.imx + 1) && (j <= Ly.jmx + 1);   // the ghost cells next to the last faces feed the reconstruction there
+    s0 = (ty + 1) * PW + tx + 1;
   } else if (wid == TY) {           // the two i columns next to the tile: lanes 0..TY-1 low side, TY..2TY-1 high side
     const int r = lane % TY, side = lane / TY;
     i = (side == 0) ? i0 - 1 : i0 + TX; j = j0 + r;
-    const bool act = (side < 2) && (j <= Ly.jmx - 1) && (i <= Ly.imx);
-    rec[0] = act; fac[0] = act && side == 1;
-    whi[0] = r * (TX + 1) + 0;      // only the low side's hi value is read by anybody (slot 0 of the row)
-    rhi[0] = r * (TX + 1) + TX; wf[0] = r * (TX + 1) + TX; plo[0] = 3 * NMAIN + r;
-    if (i > Ly.imx) i = Ly.imx;
-    if (j > Ly.jmx) j = Ly.jmx;
+    act = (side < 2) && (j <= Ly.jmx - 1) && (i <= Ly.imx);
+    stg = (side < 2) && (j <= Ly.jmx + 1) && (i <= Ly.imx + 1);
+    dirh = 0; rec0 = act; fac0 = act && side == 1; wr_hi = side == 0;
+    s0 = (r + 1) * PW + (side == 0 ? 0 : TX + 1);
+    outer_slot = PS + side * TY + r;
+    outer_off = (side == 0) ? -1 : 1;
+    sminus = (side == 0) ? outer_slot : s0 - 1; splus = (side == 0) ? s0 + 1 : outer_slot;
+    xhi = r * (TX + 1) + (side == 0 ? 0 : TX); xlo = r * (TX + 1) + TX;
   } else {                          // low (wid == TY+1) and high (wid == TY+2) j rows next to the tile
     const bool high = wid == TY + 2;
     i = i0 + lane; j = high ? j0 + TY : j0 - 1;
-    const bool act = (i <= Ly.imx - 1) && (j <= Ly.jmx);
-    rec[1] = act; fac[1] = act && high;
-    whi[1] = lane;                  // low row: slot row 0
-    rhi[1] = TY * TX + lane; wf[1] = TY * TX + lane; plo[1] = 3 * NMAIN + 32 + lane;
-    if (i > Ly.imx) i = Ly.imx;
-    if (j > Ly.jmx) j = Ly.jmx;
+    act = (i <= Ly.imx - 1) && (j <= Ly.jmx);
+    stg = (i <= Ly.imx + 1) && (j <= Ly.jmx + 1);
+    dirh = 1; rec1 = act; fac1 = act && high; wr_hi = !high;
+    s0 = (high ? TY + 1 : 0) * PW + lane + 1;
+    outer_slot = PS + 2 * TY + (high ? TX : 0) + lane;
+    outer_off = high ? Ly.sj : -Ly.sj;
+    sminus = high ? s0 - PW : outer_slot; splus = high ? outer_slot : s0 + PW;
+    xhi = SLOT_I + (high ? TY * TX : 0) + lane; xlo = SLOT_I + TY * TX + lane;
   }
-  if (wid < TY) { if (i > Ly.imx) i = Ly.imx; if (j > Ly.jmx) j = Ly.jmx; }
-  const bool hi_side_halo = (wid == TY && (lane / TY) == 1) || (wid == TY + 2);   // its own hi value is never read
+  if (i > Ly.imx + 1) i = Ly.imx + 1;
+  if (j > Ly.jmx + 1) j = Ly.jmx + 1;
+  const bool main_thr = wid < TY;
 
   const double* __restrict__ q = a.q;
   const double* __restrict__ vol = a.geom + (long long)G_VOL * fs;
+
+  // stage the record of this thread's cell at plane kk into ring buffer kk & 1 (asynchronously)
+  auto stage = [&](int kk) {
+    if (!stg) return;
+    double* pl = smem + (kk & 1) * RC::PLANE;
+    const long long c1 = Ly.idx(i, j, kk);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) cp_async8(pl + v * PSQ + s0, q + v * fs + c1);
+    if (!main_thr && SMQ && act) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) cp_async8(pl + v * PSQ + outer_slot, q + v * fs + c1 + outer_off);
+    }
+    if (VISC) {
+      double* pr = pl + NV * PSQ;
+#pragma unroll
+      for (int f = 0; f < RC::NGF; ++f) cp_async8(pr + f * PS + s0, a.grad + f * fs + c1);
+#pragma unroll
+      for (int f = 0; f < RC::NMU; ++f) cp_async8(pr + (RC::OFF_MU + f) * PS + s0, a.mu + f * fs + c1);
+#pragma unroll
+      for (int f = 0; f < 3; ++f) cp_async8(pr + (RC::OFF_C + f) * PS + s0, a.geom + (long long)(G_CX + f) * fs + c1);
+    }
+  };
+
   double nrm[NV + 1];
 #pragma unroll
   for (int v = 0; v <= NV; ++v) nrm[v] = 0.0;
+  double hi_k[NV], F_k[NV + 3];     // carried along k: value at the high k face of the current plane, flux of its low k face
+#pragma unroll
+  for (int v = 0; v < NV; ++v) hi_k[v] = 0.0;
+#pragma unroll
+  for (int v = 0; v < NV + 3; ++v) F_k[v] = 0.0;
 
-  for (int k = kb - 2; k < ke; ++k) {
-    const int par = (k - kb) & 1;                   // ping-pong slot of the k direction
+  if (main_thr) stage(kb - 1);
+
+  for (int k = kb - 1; k < ke; ++k) {
     const bool inplane = k >= kb;
     const long long c = Ly.idx(i, j, k);
-    // ---- phase 1: reconstruction --------------------------------------------------------------------------------------
-#pragma unroll 1
-    for (int d = 0; d < 3; ++d) {
-      bool doit, need_lo = true;
-      long long cr, s;
-      int pos, mx, slot_hi, slot_lo;
-      if (d == 0) { doit = inplane && rec[0]; need_lo = fac[0]; cr = c; s = 1; pos = i; mx = Ly.imx; slot_hi = whi[0]; slot_lo = plo[0]; }
-      else if (d == 1) { doit = inplane && rec[1]; need_lo = fac[1]; cr = c; s = Ly.sj; pos = j; mx = Ly.jmx; slot_hi = SLOT_I + whi[1]; slot_lo = plo[1]; }
-      else { doit = own && k_active; cr = c + Ly.sk; s = Ly.sk; pos = k + 1; mx = Ly.kmx; slot_hi = SLOT_I + SLOT_J + par * NMAIN + tid; slot_lo = 2 * NMAIN + tid; }
-      if (!doit) continue;
-      double hi[NV], lo[NV];
-      line_cell_values<NV, INTERP>(P, q, vol, cr, s, pos, mx, d, hi, lo);
-      if (!(hi_side_halo && d < 2)) {
+    double* const plA = smem + (k & 1) * RC::PLANE;          // plane k
+    double* const plB = smem + ((k + 1) & 1) * RC::PLANE;    // plane k+1
+    const double* const qA = plA + s0;                       // staged q of this thread's cell, field stride PSQ
+    const double* const rA = plA + NV * PSQ + s0;            // its record, field stride PS
+    stage(k + 1);                                            // overlaps with the in-plane work below
+    double q2[NV];
+    if (own && k_active && SMQ) {
 #pragma unroll
-        for (int v = 0; v < NV; ++v) sm_hi[v * SLOT_HF + slot_hi] = hi[v];
-      }
-      if (need_lo) {
-#pragma unroll
-        for (int v = 0; v < NV; ++v) sm_lo[v * SLOT_LO + slot_lo] = lo[v];
-      }
+      for (int v = 0; v < NV; ++v) q2[v] = q[v * fs + c + 2 * Ly.sk];
     }
-    __syncthreads();
-    // ---- phase 2: faces --------------------------------------------------------------------------------------------------
+
+    // ---- i and j: reconstruct, exchange, flux -------------------------------------------------------------------------
 #pragma unroll 1
-    for (int d = 0; d < 3; ++d) {
-      bool doit, flux_on = true;
-      long long X, s;
-      int f, m, slot_L, slot_R, slot_F;
-      if (d == 0) { doit = inplane && fac[0]; X = c; s = 1; f = i; m = Ly.imx; slot_L = rhi[0]; slot_R = plo[0]; slot_F = wf[0]; }
-      else if (d == 1) { doit = inplane && fac[1]; X = c; s = Ly.sj; f = j; m = Ly.jmx; slot_L = SLOT_I + rhi[1]; slot_R = plo[1]; slot_F = SLOT_I + wf[1]; }
-      else {
-        doit = own && k_active && k >= kb - 1; X = c + Ly.sk; s = Ly.sk; f = k + 1; m = Ly.kmx; flux_on = flux_on_k;
-        slot_L = SLOT_I + SLOT_J + (par ^ 1) * NMAIN + tid; slot_R = 2 * NMAIN + tid; slot_F = SLOT_I + SLOT_J + par * NMAIN + tid;
+    for (int d = 0; d < 2; ++d) {
+      const bool dorec = inplane && (d == 0 ? rec0 : rec1), doface = inplane && (d == 0 ? fac0 : fac1);
+      const int pos = (d == 0) ? i : j, mx = (d == 0) ? Ly.imx : Ly.jmx;
+      const int nb = (d == 0) ? 1 : PW;                       // staged-slot stride of the direction
+      int exw, exr;                                           // exchange slots (hi value written / L read; flux written)
+      if (main_thr) {
+        const int tx = lane, ty = wid;
+        exw = (d == 0) ? ty * (TX + 1) + tx + 1 : SLOT_I + (ty + 1) * TX + tx;
+        exr = (d == 0) ? ty * (TX + 1) + tx : SLOT_I + ty * TX + tx;
+      } else { exw = xhi; exr = xlo; }
+      double lo[NV];
+      if (dorec) {
+        double hi[NV];
+        if (SMQ) {
+          const int om = main_thr ? -nb : sminus - s0, op = main_thr ? nb : splus - s0;
+          double qm[NV], q0[NV], qp[NV];
+#pragma unroll
+          for (int v = 0; v < NV; ++v) { qm[v] = qA[v * PSQ + om]; q0[v] = qA[v * PSQ]; qp[v] = qA[v * PSQ + op]; }
+          recon3<NV, INTERP>(P, qm, q0, qp, pos, mx, d, hi, lo);
+        } else {
+          line_cell_values<NV, INTERP>(P, q, vol, c, (d == 0) ? 1 : Ly.sj, pos, mx, d, hi, lo);
+        }
+        if (wr_hi) {
+#pragma unroll
+          for (int v = 0; v < NV; ++v) sm_hi[v * EX + exw] = hi[v];
+        }
       }
-      if (!doit) continue;
-      double L[NV], R[NV], F[NV], lam = 0.0, vis = 0.0, tur = 0.0;
+      __syncthreads();
+      if (doface) {
+        double L[NV], F[NV], lam = 0.0, vis = 0.0, tur = 0.0;
+        const int exl = main_thr ? exr : ((d == 0) ? (exr - 0) : exr);   // L sits at the slot of the low neighbour's hi value
 #pragma unroll
-      for (int v = 0; v < NV; ++v) { L[v] = sm_hi[v * SLOT_HF + slot_L]; R[v] = sm_lo[v * SLOT_LO + slot_R]; }
-      face_eval<NV, SCHEME, VISC>(P, a, d, X, s, f, m, L, R, flux_on, need_dt, F, lam, vis, tur);
+        for (int v = 0; v < NV; ++v) L[v] = sm_hi[v * EX + exl];
+        face_eval<NV, SCHEME, VISC>(P, a, d, qA - nb, qA, rA - nb, rA, c, pos, mx, L, lo, true, need_dt, F, lam, vis, tur);
 #pragma unroll
-      for (int v = 0; v < NV; ++v) sm_F[v * SLOT_HF + slot_F] = F[v];
-      if (need_dt) {
-        sm_F[NV * SLOT_HF + slot_F] = lam;
-        if (VISC) sm_F[(NV + 1) * SLOT_HF + slot_F] = vis;
-        if (VISC && SST) sm_F[(NV + 2) * SLOT_HF + slot_F] = tur;
-      }
-    }
-    __syncthreads();
-    // ---- phase 3: the cell ---------------------------------------------------------------------------------------------------
-    if (!(inplane && own)) continue;
-    const int tx = lane, ty = wid;
-    const int sl[3] = {ty * (TX + 1) + tx, SLOT_I + ty * TX + tx, SLOT_I + SLOT_J + (par ^ 1) * NMAIN + tid};        // low faces
-    const int sh[3] = {ty * (TX + 1) + tx + 1, SLOT_I + (ty + 1) * TX + tx, SLOT_I + SLOT_J + par * NMAIN + tid};    // high faces
-    double res[NV];
-    double merr = 0.0;
-#pragma unroll
-    for (int v = 0; v < NV; ++v) res[v] = 0.0;
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      if (d == 2 && !k_active) continue;
-      const int p = (d == 0) ? i : (d == 1 ? j : k);
-      const int m = (d == 0) ? Ly.imx : (d == 1 ? Ly.jmx : Ly.kmx);
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        const double Fl = sm_F[v * SLOT_HF + sl[d]], Fh = sm_F[v * SLOT_HF + sh[d]];
-        res[v] = res[v] + (Fh - Fl);   // scheme.f90:133-135
-        if (v == 0) {                  // resnorm.f90:190-198
-          if (p == 1) merr += Fl;
-          if (p == m - 1) merr -= Fh;
+        for (int v = 0; v < NV; ++v) sm_F[v * EX + exr] = F[v];
+        if (need_dt) {
+          sm_F[NV * EX + exr] = lam;
+          if (VISC) sm_F[(NV + 1) * EX + exr] = vis;
+          if (VISC && SST) sm_F[(NV + 2) * EX + exr] = tur;
         }
       }
     }
-    {
-      bool bad = false;
-#pragma unroll
-      for (int v = 0; v < NV; ++v) bad |= isnan(res[v]);
-      if (bad) flag_error(a.err, F3D_ERR_NAN_FLUX, i, j, k);
-    }
-    const double volc = vol[c];
-    double qc[NV];
-#pragma unroll
-    for (int v = 0; v < NV; ++v) qc[v] = q[v * fs + c];
-    if (SST && VISC) {   // source.f90:214-268
-      double g[6][3];
-#pragma unroll
-      for (int cc = 0; cc < 6; ++cc) {
-        if (cc == 3) continue;
-        g[cc][0] = a.grad[(3 * cc + 0) * fs + c]; g[cc][1] = a.grad[(3 * cc + 1) * fs + c]; g[cc][2] = a.grad[(3 * cc + 2) * fs + c];
-      }
-      const double mut = a.mu[fs + c];
-      const double density = qc[0], tk = qc[5], tw = qc[6];
-      const double wx = g[2][1] - g[1][2], wy = g[0][2] - g[2][0], wz = g[1][0] - g[0][1];
-      const double vort = sqrt(wx * wx + wy * wy + wz * wz);
-      double CD = 2 * density * kSigmaW2 * (g[4][0] * g[5][0] + g[4][1] * g[5][1] + g[4][2] * g[5][2]) * rcp64(tw);
-      CD = dmax(CD, P.cd_floor);
-      const double F1 = a.mu[2 * fs + c];
-      const double gama = P.gama1 * F1 + P.gama2 * (1. - F1);
-      const double beta = kBeta1 * F1 + kBeta2 * (1. - F1);
-      const double D_k = kBstar * density * tw * tk;
-      const double D_w = beta * density * (tw * tw);
-      const double divergence = g[0][0] + g[1][1] + g[2][2];
-      double P_k = mut * (vort * vort) - ((2.0 / 3.0) * density * tk * divergence);
-      P_k = dmin(P_k, P.pk_limiter * D_k);
-      const double P_w = (density * gama * rcp64(mut)) * P_k;
-      const double lamda = (1. - F1) * CD;
-      const double S_k = (P_k - D_k) * volc;
-      const double S_w = (P_w - D_w + lamda) * volc;
-      res[5] = res[5] - S_k;
-      res[6] = res[6] - S_w;
-    }
 
-    double dtc = 0.0;
-    if (need_dt) {
-      if (P.time_stepping == 1 && P.global_time_step > 0) {
-        dtc = P.global_time_step;
+    // ---- k: the plane k+1 record of this column has landed ---------------------------------------------------------------
+    cp_async_wait_all();
+    double hi_n[NV], F_n[NV + 3];
+#pragma unroll
+    for (int v = 0; v < NV + 3; ++v) F_n[v] = 0.0;
+    if (own && k_active) {
+      const double* const qB = plB + s0;
+      const double* const rB = plB + NV * PSQ + s0;
+      if (k == kb - 1) {   // prime the carried hi value: cell kb-1 reconstructed along k
+        double lo_[NV];
+        if (SMQ) {
+          double qm[NV], q0[NV], qp[NV];
+#pragma unroll
+          for (int v = 0; v < NV; ++v) { qm[v] = q[v * fs + c - Ly.sk]; q0[v] = qA[v * PSQ]; qp[v] = qB[v * PSQ]; }
+          recon3<NV, INTERP>(P, qm, q0, qp, k, Ly.kmx, 2, hi_k, lo_);
+        } else {
+          line_cell_values<NV, INTERP>(P, q, vol, c, Ly.sk, k, Ly.kmx, 2, hi_k, lo_);
+        }
+      }
+      double lo[NV];
+      if (SMQ) {
+        double qm[NV], q0[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) { qm[v] = qA[v * PSQ]; q0[v] = qB[v * PSQ]; }
+        recon3<NV, INTERP>(P, qm, q0, q2, k + 1, Ly.kmx, 2, hi_n, lo);
       } else {
-        const double* lamv = sm_F + NV * SLOT_HF;
-        const double lmxsum = lamv[sl[0]] + lamv[sl[1]] + lamv[sl[2]] + lamv[sh[0]] + lamv[sh[1]] + lamv[sh[2]];
-        dtc = rcp64(lmxsum);
-        dtc = dtc * volc * P.CFL;
-        if (VISC) {
-          const double* visv = sm_F + (NV + 1) * SLOT_HF;
-          double s = visv[sl[0]] + visv[sl[1]] + visv[sl[2]] + visv[sh[0]] + visv[sh[1]] + visv[sh[2]];
-          s = P.gm * s * P.inv_Pr;
-          s = 2. * rcp64(s + (2. * P.CFL * volc * rcp64(dtc)));
-          dtc = P.CFL * (s * volc);
-          if (SST) {
-            const double* turv = sm_F + (NV + 2) * SLOT_HF;
-            double t = turv[sl[0]] + turv[sl[1]] + turv[sl[2]] + turv[sh[0]] + turv[sh[1]] + turv[sh[2]];
-            t = P.gm * t * P.inv_tPr;
-            t = 2. * rcp64(t + (2. * P.CFL * volc * rcp64(dtc)));
-            dtc = P.CFL * (t * volc);
+        line_cell_values<NV, INTERP>(P, q, vol, c + Ly.sk, Ly.sk, k + 1, Ly.kmx, 2, hi_n, lo);
+      }
+      double L[NV], F[NV], lam = 0.0, vis = 0.0, tur = 0.0;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) L[v] = hi_k[v];
+      face_eval<NV, SCHEME, VISC>(P, a, 2, qA, qB, rA, rB, c + Ly.sk, k + 1, Ly.kmx, L, lo, flux_on_k, need_dt, F, lam, vis, tur);
+#pragma unroll
+      for (int v = 0; v < NV; ++v) F_n[v] = F[v];
+      F_n[NV] = lam; F_n[NV + 1] = vis; F_n[NV + 2] = tur;
+    }
+    __syncthreads();
+
+    // ---- the cell -----------------------------------------------------------------------------------------------------------
+    if (inplane && own) {
+      const int tx = lane, ty = wid;
+      const int sl0 = ty * (TX + 1) + tx, sh0 = sl0 + 1, sl1 = SLOT_I + ty * TX + tx, sh1 = sl1 + TX;
+      double res[NV];
+      double merr = 0.0;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const double Fl0 = sm_F[v * EX + sl0], Fh0 = sm_F[v * EX + sh0], Fl1 = sm_F[v * EX + sl1], Fh1 = sm_F[v * EX + sh1];
+        double r = 0.0;
+        r = r + (Fh0 - Fl0);   // scheme.f90:133-135
+        r = r + (Fh1 - Fl1);
+        if (k_active) r = r + (F_n[v] - F_k[v]);
+        res[v] = r;
+        if (v == 0) {          // resnorm.f90:190-198
+          if (i == 1) merr += Fl0;
+          if (i == Ly.imx - 1) merr -= Fh0;
+          if (j == 1) merr += Fl1;
+          if (j == Ly.jmx - 1) merr -= Fh1;
+          if (k_active) {
+            if (k == 1) merr += F_k[0];
+            if (k == Ly.kmx - 1) merr -= F_n[0];
           }
         }
       }
-      a.dt[c] = dtc;
-    } else if (a.mode == MODE_UPDATE) {
-      dtc = a.dt[c];
-    }
+      {
+        bool bad = false;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) bad |= isnan(res[v]);
+        if (bad) flag_error(a.err, F3D_ERR_NAN_FLUX, i, j, k);
+      }
+      const double volc = vol[c];
+      double qc[NV];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) qc[v] = qA[v * PSQ];
+      if (SST && VISC) {   // source.f90:214-268
+        double g[6][3];
+#pragma unroll
+        for (int cc = 0; cc < 6; ++cc) {
+          if (cc == 3) continue;
+          g[cc][0] = rA[(3 * cc + 0) * PS]; g[cc][1] = rA[(3 * cc + 1) * PS]; g[cc][2] = rA[(3 * cc + 2) * PS];
+        }
+        const double mut = rA[(RC::OFF_MU + 1) * PS];
+        const double density = qc[0], tk = qc[5], tw = qc[6];
+        const double wx = g[2][1] - g[1][2], wy = g[0][2] - g[2][0], wz = g[1][0] - g[0][1];
+        const double vort = sqrt(wx * wx + wy * wy + wz * wz);
+        double CD = 2 * density * kSigmaW2 * (g[4][0] * g[5][0] + g[4][1] * g[5][1] + g[4][2] * g[5][2]) * rcp64(tw);
+        CD = dmax(CD, P.cd_floor);
+        const double F1 = rA[(RC::OFF_MU + 2) * PS];
+        const double gama = P.gama1 * F1 + P.gama2 * (1. - F1);
+        const double beta = kBeta1 * F1 + kBeta2 * (1. - F1);
+        const double D_k = kBstar * density * tw * tk;
+        const double D_w = beta * density * (tw * tw);
+        const double divergence = g[0][0] + g[1][1] + g[2][2];
+        double P_k = mut * (vort * vort) - ((2.0 / 3.0) * density * tk * divergence);
+        P_k = dmin(P_k, P.pk_limiter * D_k);
+        const double P_w = (density * gama * rcp64(mut)) * P_k;
+        const double lamda = (1. - F1) * CD;
+        const double S_k = (P_k - D_k) * volc;
+        const double S_w = (P_w - D_w + lamda) * volc;
+        res[5] = res[5] - S_k;
+        res[6] = res[6] - S_w;
+      }
 
-    if (a.mode == MODE_RESIDUE_ONLY) {
-#pragma unroll
-      for (int v = 0; v < NV; ++v) a.residue[v * fs + c] = res[v];
-    } else {   // update.f90:371-485
-      double u1[NV], R[NV], u2[NV];
-#pragma unroll
-      for (int v = 0; v < NV; ++v) R[v] = res[v];
-      u1[0] = a.quse[c];
-#pragma unroll
-      for (int v = 1; v < NV; ++v) u1[v] = a.quse[v * fs + c] * u1[0];
-      u1[4] = (u1[4] * P.inv_gm1 + 0.5 * (u1[1] * u1[1] + u1[2] * u1[2] + u1[3] * u1[3])) * rcp64(u1[0]) + 0.;
-      if (SST) {
-        const double F1 = a.mu[2 * fs + c];
-        const double beta = kBeta1 * F1 + (1. - F1) * kBeta2;
-        R[5] = R[5] * rcp64(1 + (beta * qc[6] * dtc));
-        R[6] = R[6] * rcp64(1 + (2 * beta * qc[6] * dtc));
-      }
-      if (a.have_store) {
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          const double rn = a.rstore[v * fs + c] + a.SF * R[v];
-          a.rstore[v * fs + c] = rn;
-          if (a.use_store_sum) R[v] = rn;
+      double dtc = 0.0;
+      if (need_dt) {
+        if (P.time_stepping == 1 && P.global_time_step > 0) {
+          dtc = P.global_time_step;
+        } else {
+          const double* lamv = sm_F + NV * EX;
+          const double lmxsum = lamv[sl0] + lamv[sl1] + F_k[NV] + lamv[sh0] + lamv[sh1] + F_n[NV];
+          dtc = rcp64(lmxsum);
+          dtc = dtc * volc * P.CFL;
+          if (VISC) {
+            const double* visv = sm_F + (NV + 1) * EX;
+            double s = visv[sl0] + visv[sl1] + F_k[NV + 1] + visv[sh0] + visv[sh1] + F_n[NV + 1];
+            s = P.gm * s * P.inv_Pr;
+            s = 2. * rcp64(s + (2. * P.CFL * volc * rcp64(dtc)));
+            dtc = P.CFL * (s * volc);
+            if (SST) {
+              const double* turv = sm_F + (NV + 2) * EX;
+              double t = turv[sl0] + turv[sl1] + F_k[NV + 2] + turv[sh0] + turv[sh1] + F_n[NV + 2];
+              t = P.gm * t * P.inv_tPr;
+              t = 2. * rcp64(t + (2. * P.CFL * volc * rcp64(dtc)));
+              dtc = P.CFL * (t * volc);
+            }
+          }
         }
+        a.dt[c] = dtc;
+      } else if (a.mode == MODE_UPDATE) {
+        dtc = a.dt[c];
       }
-      const double fac_ = (a.TF * dtc * rcp64(volc));
+
+      if (a.mode == MODE_RESIDUE_ONLY) {
 #pragma unroll
-      for (int v = 0; v < NV; ++v) u2[v] = u1[v] - R[v] * fac_;
-      const double iu = 1.0 / u2[0];   // IEEE: u2[0] may be <= 0 or NaN here and must reach the check below unchanged
+        for (int v = 0; v < NV; ++v) a.residue[v * fs + c] = res[v];
+      } else {   // update.f90:371-485
+        double u1[NV], R[NV], u2[NV];
 #pragma unroll
-      for (int v = 1; v < NV; ++v) u2[v] = u2[v] * iu;
-      u2[4] = (P.gm - 1.) * u2[0] * (u2[4] - (0.5 * (u2[1] * u2[1] + u2[2] * u2[2] + u2[3] * u2[3])) - 0.);
-      bool bad = (u2[0] < 0.) || (u2[4] < 0.);
+        for (int v = 0; v < NV; ++v) R[v] = res[v];
+        u1[0] = a.quse[c];
 #pragma unroll
-      for (int v = 0; v < NV; ++v) bad |= isnan(u2[v]);
-      if (bad) {
-        flag_error(a.err, F3D_ERR_NEGATIVE_STATE, i, j, k);
-#pragma unroll
-        for (int v = 0; v < NV; ++v) a.qnew[v * fs + c] = qc[v];
-      } else {
-#pragma unroll
-        for (int v = 0; v < 5; ++v) a.qnew[v * fs + c] = u2[v];
+        for (int v = 1; v < NV; ++v) u1[v] = a.quse[v * fs + c] * u1[0];
+        u1[4] = (u1[4] * P.inv_gm1 + 0.5 * (u1[1] * u1[1] + u1[2] * u1[2] + u1[3] * u1[3])) * rcp64(u1[0]) + 0.;
         if (SST) {
-          a.qnew[5 * fs + c] = (u2[5] >= 0.) ? u2[5] : qc[5];
-          a.qnew[6 * fs + c] = (u2[6] >= 0.) ? u2[6] : qc[6];
+          const double F1 = rA[(RC::OFF_MU + 2) * PS];
+          const double beta = kBeta1 * F1 + (1. - F1) * kBeta2;
+          R[5] = R[5] * rcp64(1 + (beta * qc[6] * dtc));
+          R[6] = R[6] * rcp64(1 + (2 * beta * qc[6] * dtc));
+        }
+        if (a.have_store) {
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            const double rn = a.rstore[v * fs + c] + a.SF * R[v];
+            a.rstore[v * fs + c] = rn;
+            if (a.use_store_sum) R[v] = rn;
+          }
+        }
+        const double fac_ = (a.TF * dtc * rcp64(volc));
+#pragma unroll
+        for (int v = 0; v < NV; ++v) u2[v] = u1[v] - R[v] * fac_;
+        const double iu = 1.0 / u2[0];   // IEEE: u2[0] may be <= 0 or NaN here and must reach the check below unchanged
+#pragma unroll
+        for (int v = 1; v < NV; ++v) u2[v] = u2[v] * iu;
+        u2[4] = (P.gm - 1.) * u2[0] * (u2[4] - (0.5 * (u2[1] * u2[1] + u2[2] * u2[2] + u2[3] * u2[3])) - 0.);
+        bool bad = (u2[0] < 0.) || (u2[4] < 0.);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) bad |= isnan(u2[v]);
+        if (bad) {
+          flag_error(a.err, F3D_ERR_NEGATIVE_STATE, i, j, k);
+#pragma unroll
+          for (int v = 0; v < NV; ++v) a.qnew[v * fs + c] = qc[v];
+        } else {
+#pragma unroll
+          for (int v = 0; v < 5; ++v) a.qnew[v * fs + c] = u2[v];
+          if (SST) {
+            a.qnew[5 * fs + c] = (u2[5] >= 0.) ? u2[5] : qc[5];
+            a.qnew[6 * fs + c] = (u2[6] >= 0.) ? u2[6] : qc[6];
+          }
         }
       }
-    }
-    if (a.want_norms) {   // resnorm.f90:187-198
-      nrm[0] += merr;
+      if (a.want_norms) {   // resnorm.f90:187-198
+        nrm[0] += merr;
 #pragma unroll
-      for (int v = 0; v < NV; ++v) nrm[v + 1] += res[v] * res[v];
+        for (int v = 0; v < NV; ++v) nrm[v + 1] += res[v] * res[v];
+      }
     }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) hi_k[v] = hi_n[v];
+#pragma unroll
+    for (int v = 0; v < NV + 3; ++v) F_k[v] = F_n[v];
   }
 
   if (a.want_norms) {   // per-CTA partial: warp shuffle, then the block
@@ -514,7 +652,7 @@ static int launch_one(Ctx* ctx, KArgs& a) {
   const Layout& L = ctx->P.L;
   a.kchunk = pick_kchunk(L);
   dim3 grid((L.imx - 1 + TX - 1) / TX, (L.jmx - 1 + TY - 1) / TY, (L.kmx - 1 + a.kchunk - 1) / a.kchunk);
-  const size_t shm = sizeof(double) * sweep_smem_doubles(NV);
+  const size_t shm = sizeof(double) * Rec<NV, VISC>::SMEM;
   static bool attr_set[64] = {false};   // per instantiation and device
   if (!attr_set[ctx->device & 63]) {
     cudaError_t e = cudaFuncSetAttribute(k_sweep<NV, INTERP, SCHEME, VISC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
