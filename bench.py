@@ -41,7 +41,16 @@ def algorithmic_bytes_per_cell_update(nv, viscous, sst, stages_rk):
 
 
 def block_grid(n_ranks):
-    return {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(n_ranks, (n_ranks, 1, 1))
+    return importlib.import_module("fest-3d_b200.parallel").block_grid(n_ranks)
+
+
+def cpu_block_lattice(cores):
+    """One oracle thread per block (the reference runs one MPI rank per block): the largest lattice that fits the host cores."""
+    best = (1, 1, 1)
+    for nb in [(2, 1, 1), (2, 2, 1), (2, 2, 2), (4, 2, 2), (4, 4, 2), (4, 4, 4), (8, 4, 4)]:
+        if nb[0] * nb[1] * nb[2] <= cores:
+            best = nb
+    return best
 
 
 class ClockSampler(threading.Thread):
@@ -82,8 +91,8 @@ def run_reference(args, n, rank, world):
         return
     import oracle_py
     syn = importlib.import_module("fest-3d_b200.synthetic")
-    cores = os.cpu_count() or 1
-    nb = (2, 2, 2) if cores >= 8 else ((2, 2, 1) if cores >= 4 else (1, 1, 1))
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    nb = cpu_block_lattice(cores)
     nblk = nb[0] * nb[1] * nb[2]
     m = args.cpu_cells
     blocks = syn.make_duct_blocks(m, nb=nb, scheme_name="ausm", interpolant="muscl", turbulence="sst", time_step_accuracy="none", CFL=0.5)
@@ -101,7 +110,7 @@ def run_reference(args, n, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": n, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(n, args),
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": min(cores, nblk), "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": min(cores, nblk), "host_cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
@@ -116,8 +125,8 @@ def cpu_baseline_sample(args):
     """Oracle port timed on a bounded sample on this box's host cores (reported baseline, not the target)."""
     import oracle_py
     syn = importlib.import_module("fest-3d_b200.synthetic")
-    cores = os.cpu_count() or 1
-    nb = (2, 2, 2) if cores >= 8 else ((2, 2, 1) if cores >= 4 else (1, 1, 1))
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    nb = cpu_block_lattice(cores)
     nblk = nb[0] * nb[1] * nb[2]
     m = args.cpu_cells
     blocks = syn.make_duct_blocks(m, nb=nb, turbulence="sst", time_step_accuracy="none", CFL=0.5)
@@ -128,14 +137,14 @@ def cpu_baseline_sample(args):
     for it in range(2, 2 + steps):
         w.step(it)
     dt = time.perf_counter() - t0
-    return {"value": nblk * m ** 3 * steps / dt, "unit": UNIT, "cores": min(cores, nblk), "kind": "port",
+    return {"value": nblk * m ** 3 * steps / dt, "unit": UNIT, "cores": min(cores, nblk), "host_cores": cores, "kind": "port",
             "sample": "%d blocks of %d^3 cells, one thread per block, %d steps of the same MUSCL+AUSM+SST duct" % (nblk, m, steps)}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cells", type=int, default=256, help="cells per block edge per GPU")
@@ -170,10 +179,9 @@ def main():
     s = solver_mod.Solver(blocks, devices=[local_rank])
     gb = s.blocks[0]
     if world > 1:
-        uid = solver_mod.Solver.unique_id() if rank == 0 else bytes(128)
-        t = torch.tensor(list(uid), dtype=torch.uint8, device="cuda")
-        dist.broadcast(t, 0)
-        s.init_comm(world, rank, bytes(t.cpu().tolist()), list(range(world)))
+        par = importlib.import_module("fest-3d_b200.parallel")
+        uid = par.broadcast_unique_id(dist, solver_mod.Solver.unique_id, rank, device="cuda")
+        s.init_comm(world, rank, uid, par.block_to_rank(world, world))
     stream = torch.cuda.Stream()          # a real (non-default) stream, so CUDA events bracket exactly our launches
     torch.cuda.set_stream(stream)
     gb.set_stream(stream.cuda_stream)
@@ -187,13 +195,13 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ("value") ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     s.iterate(args.warmup, want_norms=False)
     launches0 = gb.launch_count()
     gb.kernel_timing(True)
     gb.kernel_time_ms(reset=True)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -201,7 +209,6 @@ def main():
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
-    sampler.stop_flag = True
     launches = gb.launch_count() - launches0
     k_ms, k_n = gb.kernel_time_ms(reset=True)
     gb.kernel_timing(False)
@@ -227,6 +234,7 @@ def main():
     e1.record(stream)
     barrier()
     ms_e2e = e0.elapsed_time(e1)
+    sampler.stop_flag = True
     tm2 = torch.tensor([ms_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tm2, op=dist.ReduceOp.MAX)
@@ -256,7 +264,7 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(world, args),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "k_residual<7,MUSCL,viscous> (fused residual + dt + update)", "kernel_ms": k_avg_ms,
+                         "kernel": "k_sweep<7,MUSCL,AUSM,viscous> (fused reconstruction + flux + source + dt + update)", "kernel_ms": k_avg_ms,
                          "kernel_share_of_step": k_ms / ms, "algorithmic_bytes_per_cell_update": bpc, "peak_source": peak_src},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes + nvp1 * 8,
                     "steps": e2e_steps},

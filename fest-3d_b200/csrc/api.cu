@@ -179,7 +179,7 @@ extern "C" int fest3d_gpu_destroy(Fest3dGpuCtx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   double* bufs[] = {ctx->qp, ctx->qp2, ctx->ustore, ctx->rstore, ctx->residue, ctx->temp, ctx->dt, ctx->geom, ctx->grad, ctx->mu, ctx->gbc,
-                    ctx->red, ctx->norms_dev, ctx->staging};
+                    ctx->red, ctx->norms_dev, ctx->staging, ctx->state_staging};
   for (double* b : bufs) if (b) cudaFree(b);
   for (int f = 0; f < 6; ++f) { if (ctx->sendbuf[f]) cudaFree(ctx->sendbuf[f]); if (ctx->recvbuf[f]) cudaFree(ctx->recvbuf[f]); }
   if (ctx->err_dev) cudaFree(ctx->err_dev);
@@ -267,12 +267,25 @@ extern "C" int fest3d_gpu_set_geometry(Fest3dGpuCtx* ctx, const double* cells, c
   return 0;
 }
 
+// Full-state transfers: one contiguous DMA between the host array (reference layout) and a device staging buffer, plus a
+// re-layout kernel (pitched per-row DMA of the padded fields reaches only about half of the PCIe rate).
+static int ensure_state_staging(Fest3dGpuCtx* ctx) {
+  if (ctx->state_staging) return 0;
+  const Layout& L = ctx->P.L;
+  const size_t n = (size_t)L.nv * (L.imx + 5) * (L.jmx + 5) * (L.kmx + 5);
+  F3D_CUDA(cudaMalloc((void**)&ctx->state_staging, n * sizeof(double)));
+  return 0;
+}
+
 extern "C" int fest3d_gpu_set_state(Fest3dGpuCtx* ctx, const double* qp) {
   if (!ctx || !qp) return fail(ctx, F3D_ERR_ARGUMENT);
   F3D_CUDA(cudaSetDevice(ctx->device));
   const Layout& L = ctx->P.L;
-  int rc = copy_cells(ctx, ctx->qp, const_cast<double*>(qp), L.nv, true, -2, L.imx + 5, L.jmx + 5, L.kmx + 5);
+  int rc = ensure_state_staging(ctx);
   if (rc) return rc;
+  const size_t n = (size_t)L.nv * (L.imx + 5) * (L.jmx + 5) * (L.kmx + 5);
+  F3D_CUDA(cudaMemcpyAsync(ctx->state_staging, qp, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = launch_state_relayout(ctx, ctx->qp, ctx->state_staging, 1))) return rc;
   F3D_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->state_set = true;
   return 0;
@@ -282,8 +295,11 @@ extern "C" int fest3d_gpu_get_state(Fest3dGpuCtx* ctx, double* qp) {
   if (!ctx || !qp) return fail(ctx, F3D_ERR_ARGUMENT);
   F3D_CUDA(cudaSetDevice(ctx->device));
   const Layout& L = ctx->P.L;
-  int rc = copy_cells(ctx, ctx->qp, qp, L.nv, false, -2, L.imx + 5, L.jmx + 5, L.kmx + 5);
+  int rc = ensure_state_staging(ctx);
   if (rc) return rc;
+  const size_t n = (size_t)L.nv * (L.imx + 5) * (L.jmx + 5) * (L.kmx + 5);
+  if ((rc = launch_state_relayout(ctx, ctx->qp, ctx->state_staging, 0))) return rc;
+  F3D_CUDA(cudaMemcpyAsync(qp, ctx->state_staging, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   F3D_CUDA(cudaStreamSynchronize(ctx->stream));
   return 0;
 }

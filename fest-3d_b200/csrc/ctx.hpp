@@ -79,6 +79,7 @@ struct Ctx {
   double* recvbuf[6] = {nullptr};
   size_t buf_elems[6] = {0};
   double* staging = nullptr;     // host<->device staging for AoS geometry upload
+  double* state_staging = nullptr;   // contiguous copy of qp in the reference layout (set_state / get_state)
   Link link[6];
   void* nccl = nullptr;          // ncclComm_t
   int n_ranks = 1, rank = 0;
@@ -118,6 +119,7 @@ int launch_pack(Ctx* ctx, int face);
 int launch_unpack(Ctx* ctx, int face, const double* buf);
 int launch_global_dt(Ctx* ctx);
 int launch_ghost_shell_copy(Ctx* ctx, double* dst, const double* src);
+int launch_state_relayout(Ctx* ctx, double* fields, double* flat, int to_fields);
 
 // residual modes
 enum { MODE_RESIDUE_ONLY = 0, MODE_UPDATE = 1 };

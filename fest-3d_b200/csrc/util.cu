@@ -185,6 +185,29 @@ int launch_global_dt(Ctx* ctx) {
   return 0;
 }
 
+// reference layout qp(-2:imx+2,-2:jmx+2,-2:kmx+2,nv) (contiguous) <-> padded SoA fields
+__global__ void k_state_relayout(const Params P, double* __restrict__ fields, double* __restrict__ flat, int to_fields) {
+  const Layout& L = P.L;
+  const int n0 = L.imx + 5, n1 = L.jmx + 5, n2 = L.kmx + 5;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y, k = blockIdx.z;
+  if (i >= n0 || j >= n1) return;
+  const long long c = L.idx(i - 2, j - 2, k - 2);
+  const size_t per = (size_t)n0 * n1 * n2, t = (size_t)i + (size_t)n0 * ((size_t)j + (size_t)n1 * k);
+  for (int v = 0; v < L.nv; ++v) {
+    if (to_fields) fields[v * L.fs + c] = flat[v * per + t];
+    else flat[v * per + t] = fields[v * L.fs + c];
+  }
+}
+
+int launch_state_relayout(Ctx* ctx, double* fields, double* flat, int to_fields) {
+  const Layout& L = ctx->P.L;
+  dim3 block(64, 4), grid((L.imx + 5 + 63) / 64, (L.jmx + 5 + 3) / 4, L.kmx + 5);
+  k_state_relayout<<<grid, block, 0, ctx->stream>>>(ctx->P, fields, flat, to_fields);
+  ctx->launches++;
+  F3D_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // ---- one-time layout conversions ----------------------------------------------------------------------------------
 // AoS records (4 doubles, reference extents n0 x n1 x n2, lower bound -2) -> four SoA padded fields
 __global__ void k_rec_to_fields(const Params P, const double* __restrict__ rec, int n0, int n1, int n2, double* __restrict__ f0, long long fstride) {
