@@ -1,0 +1,52 @@
+"""Run under torchrun with N ranks (one GPU each): every rank owns one block of an N-block SST duct, the halo swap goes
+through ncclSend/ncclRecv and the norms through ncclAllReduce inside the library; rank 0 compares the residual-norm
+history and every rank its final block state with the CPU oracle stepping all blocks in lock step.
+Exit code 0 = parity (history and state within 1e-10)."""
+import importlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import helpers
+    import oracle_py
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    par = importlib.import_module("fest-3d_b200.parallel")
+    syn = importlib.import_module("fest-3d_b200.synthetic")
+    solver = importlib.import_module("fest-3d_b200.solver")
+    nb = par.block_grid(world)
+    kw = dict(n3=(12, 10, 8), nb=nb, turbulence="sst", time_step_accuracy="RK4", CFL=0.5)
+    all_blocks = syn.make_duct_blocks(None, **kw)
+    mine = [b for b in all_blocks if b.block_id == rank]
+    s = solver.Solver(mine, devices=[local])
+    uid = par.broadcast_unique_id(dist, solver.Solver.unique_id, rank, device="cuda")
+    s.init_comm(world, rank, uid, par.block_to_rank(world, world))
+    n_it = 6
+    hist = s.iterate(n_it)
+    w = oracle_py.OracleWorld(all_blocks)
+    ho = np.array([w.step(it)[1] for it in range(1, n_it + 1)])
+    floor = np.abs(ho[:, 1:]).max(axis=0) * 1e-3
+    rel = (np.abs(hist[:, 1:] - ho[:, 1:]) / np.maximum(np.abs(ho[:, 1:]), floor)).max()
+    d = max(helpers.state_rel_diff(s.blocks[0].get_state(), w.get_state(rank)))
+    ok = rel < 1e-10 and d < 1e-10
+    print("rank %d: history %.2e state %.2e %s" % (rank, rel, d, "ok" if ok else "FAIL"), flush=True)
+    t = torch.tensor([0 if ok else 1], device="cuda")
+    dist.all_reduce(t)
+    s.close()
+    dist.destroy_process_group()
+    sys.exit(int(t.item() != 0))
+
+
+if __name__ == "__main__":
+    main()

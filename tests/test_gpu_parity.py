@@ -140,6 +140,21 @@ def test_duct_multiblock_local_links(pkg, case_mod, oracle):
     s.close()
 
 
+def test_nccl_halo_exchange_multi_rank():
+    """One rank per GPU, one block per rank, halos over ncclSend/ncclRecv, norms over ncclAllReduce (needs >= 2 GPUs)."""
+    import subprocess
+    import sys
+    import torch
+    n = min(torch.cuda.device_count(), 8)
+    n = 8 if n >= 8 else (4 if n >= 4 else (2 if n >= 2 else 1))
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "mp_nccl_check.py")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
+                        "--master-port", "29631", script], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_global_time_step_and_weno_history(pkg, case_mod, oracle):
     import importlib
     syn = importlib.import_module("fest-3d_b200.synthetic")
