@@ -155,6 +155,8 @@ extern "C" int fest3d_gpu_create(Fest3dGpuCtx** out, const Fest3dGpuConfig* cfg,
       tot += (size_t)4 * (mx[a_ax] - 1) * (mx[b_ax] - 1);
     }
     F3D_CUDA(cudaMalloc((void**)&ctx->gbc, tot * sizeof(double)));
+    F3D_CUDA(cudaMalloc((void**)&ctx->gbc_off_dev, 6 * sizeof(long long)));
+    F3D_CUDA(cudaMemcpy(ctx->gbc_off_dev, ctx->gbc_off, 6 * sizeof(long long), cudaMemcpyHostToDevice));
   }
   // halo buffers for interface faces
   {
@@ -183,6 +185,7 @@ extern "C" int fest3d_gpu_destroy(Fest3dGpuCtx* ctx) {
   for (double* b : bufs) if (b) cudaFree(b);
   for (int f = 0; f < 6; ++f) { if (ctx->sendbuf[f]) cudaFree(ctx->sendbuf[f]); if (ctx->recvbuf[f]) cudaFree(ctx->recvbuf[f]); }
   if (ctx->err_dev) cudaFree(ctx->err_dev);
+  if (ctx->gbc_off_dev) cudaFree(ctx->gbc_off_dev);
   if (ctx->norms_host) cudaFreeHost(ctx->norms_host);
   if (ctx->err_host) cudaFreeHost(ctx->err_host);
   for (auto& e : ctx->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }

@@ -8,6 +8,7 @@
 // src/boundary/copy_bc.f90:58-131 (copy3); src/boundary/FT_bc.f90:15-107 (flow_tangency, incl. its Ifaces-normal defect).
 #include "ctx.hpp"
 #include "physics.cuh"
+#include <algorithm>
 
 namespace f3d {
 
@@ -79,7 +80,15 @@ __device__ __forceinline__ void far_field_state(const Params& P, const double* _
   Cb = 0.25 * (P.gm - 1.) * (Rexp - Rinf);
 }
 
-__global__ void k_bc_face(const Params P, double* __restrict__ q, const double* __restrict__ geom, int face) {
+// face_or_mask > 0: that face; < 0: -mask of faces processed together (blockIdx.z = face-1).  Faces whose fill only reads
+// interior cells and only writes their own ghost cells (every id except far-field -8 and periodic -9 / -10) are independent
+// of each other and go in one launch.
+__global__ void k_bc_face(const Params P, double* __restrict__ q, const double* __restrict__ geom, int face_or_mask) {
+  int face = face_or_mask;
+  if (face_or_mask < 0) {
+    face = blockIdx.z + 1;
+    if (!((-face_or_mask) >> (face - 1) & 1)) return;
+  }
   const FaceFrame fr = make_frame(P.L, face);
   const int a = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y * blockDim.y + threadIdx.y;
   if (a >= fr.na || b >= fr.nb) return;
@@ -279,7 +288,27 @@ __global__ void k_edges(const Params P, double* __restrict__ q, int phase) {
 int launch_bc(Ctx* ctx) {
   const Layout& L = ctx->P.L;
   const int mx[3] = {L.imx, L.jmx, L.kmx};
+  // order-independent faces in one launch; far-field / periodic faces keep the reference order imin..kmax among themselves
+  // and run after it (their whole-plane copies read ghost rows the other faces have filled: bc_primitive.f90:762-763, 1948-1978)
+  int mask = 0, nmax_a = 1, nmax_b = 1;
+  bool ordered = false;
   for (int face = 1; face <= 6; ++face) {
+    const int id = ctx->P.bc_id[face - 1];
+    if (id == -8 || id == -9) ordered = true;
+  }
+  for (int face = 1; face <= 6; ++face) {
+    const int id = ctx->P.bc_id[face - 1];
+    if (id >= 0 || id == -10 || ordered) continue;
+    const int ax = (face - 1) / 2, a_ax = (ax == 0) ? 1 : 0, b_ax = (ax == 2) ? 1 : 2;
+    mask |= 1 << (face - 1);
+    nmax_a = std::max(nmax_a, mx[a_ax] - 1); nmax_b = std::max(nmax_b, mx[b_ax] - 1);
+  }
+  if (mask) {
+    dim3 block(32, 4), grid((nmax_a + 31) / 32, (nmax_b + 3) / 4, 6);
+    k_bc_face<<<grid, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->geom, -mask);
+    ctx->launches++;
+  }
+  for (int face = 1; face <= 6 && ordered; ++face) {
     const int id = ctx->P.bc_id[face - 1];
     if (id >= 0 || id == -10) continue;
     const int ax = (face - 1) / 2;

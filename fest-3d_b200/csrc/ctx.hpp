@@ -69,6 +69,7 @@ struct Ctx {
   double* mu = nullptr;       // mu, mu_t, F1 (3 fields)
   double* gbc = nullptr;      // per-face (A,nx,ny,nz) records the ghost-gradient rule reads (mis-indexed for J/K faces)
   long long gbc_off[6];
+  long long* gbc_off_dev = nullptr;   // the same offsets on the device
   double* red = nullptr;      // reduction partials
   int red_blocks = 0;
   double* norms_dev = nullptr;   // (nv+1) per iteration slot

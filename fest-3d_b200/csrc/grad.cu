@@ -8,6 +8,7 @@
 // :215-263 (sst2003), :408-465 (ghost mu_t / F1).
 #include "ctx.hpp"
 #include "physics.cuh"
+#include <algorithm>
 
 namespace f3d {
 
@@ -35,7 +36,15 @@ __global__ void __launch_bounds__(128) k_gradients(const Params P, const double*
   const double ivol2 = rcp64(2 * geom[(long long)G_VOL * fs + c]);
   const bool zgrad = L.kmx > 2;   // gradqp_z = 0 when kmx == 2 (gradients.f90:328-336)
   double g[NG][3];
-  bool bad = false;
+  // face weights n*A once per face and direction (18 products), then 6 FMAs per gradient component: branch-free so the
+  // NG*3 independent chains interleave
+  double wl[3][3], wh[3][3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    wl[0][d] = wlo[0][d] * AIl; wl[1][d] = wlo[1][d] * AJl; wl[2][d] = wlo[2][d] * AKl;
+    wh[0][d] = whi[0][d] * AIh; wh[1][d] = whi[1][d] * AJh; wh[2][d] = whi[2][d] * AKh;
+  }
+  double nan_probe = 0.0;
 #pragma unroll
   for (int cc = 0; cc < NG; ++cc) {
     const double* __restrict__ var = (cc < 3) ? (q + (long long)(cc + 1) * fs) : (cc == 3 ? temp : (q + (long long)(cc + 1) * fs));
@@ -44,14 +53,14 @@ __global__ void __launch_bounds__(128) k_gradients(const Params P, const double*
     const double sIh = var[c + 1] + v0, sJh = var[c + sj] + v0, sKh = var[c + sk] + v0;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-      double r = (-sIl * wlo[0][d] * AIl - sJl * wlo[1][d] * AJl - sKl * wlo[2][d] * AKl + sIh * whi[0][d] * AIh + sJh * whi[1][d] * AJh +
-                  sKh * whi[2][d] * AKh) * ivol2;
-      if (d == 2 && !zgrad) r = 0.0;
-      else bad |= isnan(r);
+      double r = (-sIl * wl[0][d] - sJl * wl[1][d] - sKl * wl[2][d] + sIh * wh[0][d] + sJh * wh[1][d] + sKh * wh[2][d]) * ivol2;
+      if (d == 2) r = zgrad ? r : 0.0;
+      nan_probe += r;
       g[cc][d] = r;
       grad[(3 * cc + d) * fs + c] = r;
     }
   }
+  const bool bad = isnan(nan_probe);
   if (bad) { atomicOr(err, F3D_ERR_NAN_GRADIENT); }
   // molecular viscosity on 0..imx (elsewhere it keeps mu_ref from set-up)
   double mu = mu3[c];
@@ -92,7 +101,12 @@ __global__ void __launch_bounds__(128) k_gradients(const Params P, const double*
 // ghost-gradient rule + ghost mu_t/F1 on one physical face (gradients.f90:638-674, viscosity.f90:408-465)
 template <int NG>
 __global__ void k_gradient_bc(const Params P, const double* __restrict__ q, const double* __restrict__ temp, const double* __restrict__ geom,
-                              double* __restrict__ grad, double* __restrict__ mu3, const double* __restrict__ rec, int face) {
+                              double* __restrict__ grad, double* __restrict__ mu3, const double* __restrict__ rec_all, const long long* rec_off,
+                              int face_mask) {
+  // one launch for all physical faces (blockIdx.z = face-1): each face reads interior gradients and writes its own ghost cells
+  const int face = blockIdx.z + 1;
+  if (!(face_mask >> (face - 1) & 1)) return;
+  const double* __restrict__ rec = rec_all + rec_off[face - 1];
   const Layout& L = P.L;
   const int ax = (face - 1) / 2;
   const bool lo = (face % 2) == 1;
@@ -142,13 +156,18 @@ int launch_gradients(Ctx* ctx) {
   else k_gradients<4><<<grid, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->err_dev);
   ctx->launches++;
   const int mx[3] = {L.imx, L.jmx, L.kmx};
+  int mask = 0, na = 1, nb = 1;
   for (int face = 1; face <= 6; ++face) {
     if (ctx->P.bc_id[face - 1] >= 0) continue;   // "if (bc%imin_id < 0)" -- includes -10
     const int ax = (face - 1) / 2;
     const int a_ax = (ax == 0) ? 1 : 0, b_ax = (ax == 2) ? 1 : 2;
-    dim3 g2((mx[a_ax] - 1 + 31) / 32, (mx[b_ax] - 1 + 3) / 4);
-    if (ctx->P.sst) k_gradient_bc<6><<<g2, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->gbc + ctx->gbc_off[face - 1], face);
-    else k_gradient_bc<4><<<g2, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->gbc + ctx->gbc_off[face - 1], face);
+    mask |= 1 << (face - 1);
+    na = std::max(na, mx[a_ax] - 1); nb = std::max(nb, mx[b_ax] - 1);
+  }
+  if (mask) {
+    dim3 g2((na + 31) / 32, (nb + 3) / 4, 6);
+    if (ctx->P.sst) k_gradient_bc<6><<<g2, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->gbc, ctx->gbc_off_dev, mask);
+    else k_gradient_bc<4><<<g2, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->gbc, ctx->gbc_off_dev, mask);
     ctx->launches++;
   }
   F3D_CUDA(cudaGetLastError());

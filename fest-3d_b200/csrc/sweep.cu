@@ -23,8 +23,20 @@
 // src/viscous.f90:144-447; src/source.f90:158-270; src/time.f90:122-246,366-531; src/resnorm.f90:171-199).
 #include "ctx.hpp"
 #include "physics.cuh"
+#include <cstring>
 
 namespace f3d {
+
+#ifdef F3D_PHASE_TIMING   // development aid: per-phase clock64 totals of one main warp per CTA (scratch/phase_timing.py)
+__device__ unsigned long long g_phase[16];
+#define PT_DECL unsigned long long pt_t = clock64(), pt_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define PT_MARK(n) { const unsigned long long t_ = clock64(); pt_acc[n] += t_ - pt_t; pt_t = t_; }
+#define PT_FLUSH if (tid == 32) { for (int n_ = 0; n_ < 8; ++n_) atomicAdd(&g_phase[n_], pt_acc[n_]); }
+#else
+#define PT_DECL
+#define PT_MARK(n)
+#define PT_FLUSH
+#endif
 
 #ifndef F3D_TY
 #define F3D_TY 5
@@ -53,7 +65,11 @@ struct Rec {   // fields of the non-q part of a cell record
   static constexpr int OFF_MU = NGF, OFF_C = NGF + NMU;    // then the cell centre x,y,z
   static constexpr int NR = VISC ? NGF + NMU + 3 : 0;
   static constexpr int PLANE = NV * PSQ + NR * PS;         // doubles per staged plane
-  static constexpr int SMEM = 2 * PLANE + NV * EX + (NV + 3) * EX;
+  // thread-private slots of the main threads ([field][NMAIN]): carried k-direction state hi_k (NV) and F_k (NV+3), norm
+  // partials (NV+1), q of plane k+2 (NV), volume of planes k / k+1 (2).  Kept out of registers so that the i/j phases have room
+  // for interleaved dependency chains (a DFMA has 8.4 cycles of latency, the pipe takes one per 2.1).
+  static constexpr int OFF_PHI = 0, OFF_PF = NV, OFF_PN = 2 * NV + 3, OFF_PQ2 = 3 * NV + 4, OFF_PVOL = 4 * NV + 4, NPRIV = 4 * NV + 6;
+  static constexpr int SMEM = 2 * PLANE + NV * EX + (NV + 3) * EX + NPRIV * NMAIN;
 };
 
 __device__ __forceinline__ void flag_error(int* err, int cls, int i, int j, int k) {
@@ -115,21 +131,55 @@ __device__ __forceinline__ void line_cell_values(const Params& P, const double* 
 }
 
 
+// Koren-limited kappa = 1/3 MUSCL values of variables [V0, V1) of one cell (muscl.f90:161-196), branch-free inside the
+// variable loop so that the V1-V0 independent dependency chains interleave (a DFMA has 8.4 cycles of latency and the
+// pipe takes one every 2.1: profiles/r01_fp64_ops_microbench.txt)
+template <int NV, int V0, int V1>
+__device__ __forceinline__ void muscl_group(const double (&qm)[NV], const double (&q0)[NV], const double (&qp)[NV], int lim, double (&to_hi)[NV],
+                                            double (&to_lo)[NV]) {
+  const double kappa = 1. / 3.;
+  if (lim == 0) {   // psi = 1 - (1 - psi)*0 = 1 exactly
+#pragma unroll
+    for (int v = V0; v < V1; ++v) {
+      const double fd = qp[v] - q0[v], bd = q0[v] - qm[v];
+      to_hi[v] = q0[v] + 0.25 * (((1. - kappa) * bd) + ((1. + kappa) * fd));
+      to_lo[v] = q0[v] - 0.25 * (((1. + kappa) * bd) + ((1. - kappa) * fd));
+    }
+  } else {
+#pragma unroll
+    for (int v = V0; v < V1; ++v) {
+      const double fd = qp[v] - q0[v], bd = q0[v] - qm[v];
+      double r = fd * rcp64(bd + copysign(1e-14, bd));
+      double psi1 = dmax(0., dmin(dmin(2 * r, (2. / 3.) * (r - 1.0) + 1.0), 2.));
+      r = bd * rcp64(fd + copysign(1e-14, fd));
+      double psi2 = dmax(0., dmin(dmin(2 * r, (2. / 3.) * (r - 1.0) + 1.0), 2.));
+      psi1 = (1 - (1 - psi1) * lim);
+      psi2 = (1 - (1 - psi2) * lim);
+      to_hi[v] = q0[v] + 0.25 * (((1. - kappa) * psi1 * bd) + ((1. + kappa) * psi2 * fd));
+      to_lo[v] = q0[v] - 0.25 * (((1. + kappa) * psi1 * bd) + ((1. - kappa) * psi2 * fd));
+    }
+  }
+}
+
 // MUSCL / first-order values of one cell along one direction from three staged values per variable
 // (muscl.f90:161-196; boundary_state_reconstruction.f90:93-123 for the first / last interior cell when ppm_flag is set)
 template <int NV, int INTERP>
 __device__ __forceinline__ void recon3(const Params& P, const double (&qm)[NV], const double (&q0)[NV], const double (&qp)[NV], int pos, int mx,
                                        int dir, double (&to_hi)[NV], double (&to_lo)[NV]) {
   const bool redo = (INTERP != F3D_INTERP_NONE) && P.ppm_flag && ((pos == 1 && P.phys[2 * dir]) || (pos == mx - 1 && P.phys[2 * dir + 1]));
+  if (redo) {
 #pragma unroll
-  for (int v = 0; v < NV; ++v) {
-    const int lim = (v >= 5) ? P.tlimiter[dir] : P.limiter[dir];
-    if (redo) {
-      boundary_cell_face_values(qm[v], q0[v], qp[v], lim, to_hi[v], to_lo[v]);
+    for (int v = 0; v < NV; ++v) boundary_cell_face_values(qm[v], q0[v], qp[v], (v >= 5) ? P.tlimiter[dir] : P.limiter[dir], to_hi[v], to_lo[v]);
+  } else if (INTERP == F3D_INTERP_NONE) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) { to_hi[v] = q0[v]; to_lo[v] = q0[v]; }
+  } else {
+    const int lim = P.limiter[dir], tlim = P.tlimiter[dir];
+    if (NV > 5 && tlim == lim) {
+      muscl_group<NV, 0, NV>(qm, q0, qp, lim, to_hi, to_lo);
     } else {
-      double ql[7];
-      ql[2] = qm[v]; ql[3] = q0[v]; ql[4] = qp[v];
-      cell_face_values<INTERP>(ql, ql, lim, to_hi[v], to_lo[v]);
+      muscl_group<NV, 0, 5>(qm, q0, qp, lim, to_hi, to_lo);
+      if (NV > 5) muscl_group<NV, 5, NV>(qm, q0, qp, tlim, to_hi, to_lo);
     }
   }
 }
@@ -211,16 +261,12 @@ __device__ __forceinline__ void viscous_face(const Params& P, const double* __re
 
 // One face: boundary overrides of the states (boundary_state_reconstruction.f90:124-131), inviscid flux times area
 // (scheme.f90:68-109), viscous flux, and the face terms of the time step.  ql/qh, rl/rh: staged q / record of the cells on
-// the low / high side; X = global index of the high cell (= of the face in the face arrays), f = the face index along
-// direction d, m = node count along d.
+// the low / high side; A, n = metrics of the face; f = the face index along direction d, m = node count along d.
 template <int NV, int SCHEME, bool VISC>
-__device__ __forceinline__ void face_eval(const Params& P, const KArgs& a, int d, const double* __restrict__ ql, const double* __restrict__ qh,
-                                          const double* __restrict__ rl, const double* __restrict__ rh, long long X, int f, int m,
-                                          double (&L)[NV], double (&R)[NV], bool flux_on, bool need_dt, double (&F)[NV], double& lam,
-                                          double& vis, double& tur) {
-  const long long fs = P.L.fs;
-  const double* __restrict__ gA = a.geom + (long long)(G_IA + 4 * d) * fs;
-  const double A = gA[X], nx = gA[fs + X], ny = gA[2 * fs + X], nz = gA[3 * fs + X];
+__device__ __forceinline__ void face_eval(const Params& P, int d, const double* __restrict__ ql, const double* __restrict__ qh,
+                                          const double* __restrict__ rl, const double* __restrict__ rh, double A, double nx, double ny,
+                                          double nz, int f, int m, double (&L)[NV], double (&R)[NV], bool flux_on, bool need_dt,
+                                          double (&F)[NV], double& lam, double& vis, double& tur) {
   if (P.interpolant != F3D_INTERP_NONE) {
     if (f == 1 && P.phys[2 * d]) {
       const bool far = P.farlike[2 * d] != 0;
@@ -256,6 +302,7 @@ __global__ void __launch_bounds__(NT, 1) k_sweep(const Params P, const KArgs a) 
   extern __shared__ double smem[];
   double* const sm_hi = smem + 2 * RC::PLANE;          // [NV][EX]
   double* const sm_F = sm_hi + NV * EX;                // [NV+3][EX]
+  double* const priv = sm_F + (NV + 3) * EX + (threadIdx.x < NMAIN ? threadIdx.x : 0);   // [NPRIV][NMAIN], this thread's column
   const Layout& Ly = P.L;
   const long long fs = Ly.fs;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -333,18 +380,17 @@ __global__ void __launch_bounds__(NT, 1) k_sweep(const Params P, const KArgs a) 
 #pragma unroll
       for (int f = 0; f < 3; ++f) cp_async8(pr + (RC::OFF_C + f) * PS + s0, a.geom + (long long)(G_CX + f) * fs + c1);
     }
+    if (own) cp_async8(priv + (RC::OFF_PVOL + (kk & 1)) * NMAIN, vol + c1);
   };
 
-  double nrm[NV + 1];
+  // carried along k (thread-private smem): hi_k = value at the high k face of the current plane, F_k = flux of its low k face
+  if (main_thr) {
 #pragma unroll
-  for (int v = 0; v <= NV; ++v) nrm[v] = 0.0;
-  double hi_k[NV], F_k[NV + 3];     // carried along k: value at the high k face of the current plane, flux of its low k face
-#pragma unroll
-  for (int v = 0; v < NV; ++v) hi_k[v] = 0.0;
-#pragma unroll
-  for (int v = 0; v < NV + 3; ++v) F_k[v] = 0.0;
+    for (int f = 0; f < RC::OFF_PQ2; ++f) priv[f * NMAIN] = 0.0;
+  }
 
   if (main_thr) stage(kb - 1);
+  PT_DECL
 
   for (int k = kb - 1; k < ke; ++k) {
     const bool inplane = k >= kb;
@@ -353,11 +399,12 @@ __global__ void __launch_bounds__(NT, 1) k_sweep(const Params P, const KArgs a) 
     double* const plB = smem + ((k + 1) & 1) * RC::PLANE;    // plane k+1
     const double* const qA = plA + s0;                       // staged q of this thread's cell, field stride PSQ
     const double* const rA = plA + NV * PSQ + s0;            // its record, field stride PS
+    PT_MARK(7)
     stage(k + 1);                                            // overlaps with the in-plane work below
-    double q2[NV];
+    PT_MARK(0)
     if (own && k_active && SMQ) {
 #pragma unroll
-      for (int v = 0; v < NV; ++v) q2[v] = q[v * fs + c + 2 * Ly.sk];
+      for (int v = 0; v < NV; ++v) cp_async8(priv + (RC::OFF_PQ2 + v) * NMAIN, q + v * fs + c + 2 * Ly.sk);
     }
 
     // ---- i and j: reconstruct, exchange, flux -------------------------------------------------------------------------
@@ -372,6 +419,11 @@ __global__ void __launch_bounds__(NT, 1) k_sweep(const Params P, const KArgs a) 
         exw = (d == 0) ? ty * (TX + 1) + tx + 1 : SLOT_I + (ty + 1) * TX + tx;
         exr = (d == 0) ? ty * (TX + 1) + tx : SLOT_I + ty * TX + tx;
       } else { exw = xhi; exr = xlo; }
+      double gA_ = 0.0, gnx = 0.0, gny = 0.0, gnz = 0.0;   // face metrics, requested before the reconstruction so their latency overlaps it
+      if (doface) {
+        const double* __restrict__ gp = a.geom + (long long)(G_IA + 4 * d) * fs + c;
+        gA_ = gp[0]; gnx = gp[fs]; gny = gp[2 * fs]; gnz = gp[3 * fs];
+      }
       double lo[NV];
       if (dorec) {
         double hi[NV];
@@ -389,13 +441,15 @@ __global__ void __launch_bounds__(NT, 1) k_sweep(const Params P, const KArgs a) 
           for (int v = 0; v < NV; ++v) sm_hi[v * EX + exw] = hi[v];
         }
       }
+      PT_MARK(1)
       __syncthreads();
+      PT_MARK(2)
       if (doface) {
         double L[NV], F[NV], lam = 0.0, vis = 0.0, tur = 0.0;
         const int exl = main_thr ? exr : ((d == 0) ? (exr - 0) : exr);   // L sits at the slot of the low neighbour's hi value
 #pragma unroll
         for (int v = 0; v < NV; ++v) L[v] = sm_hi[v * EX + exl];
-        face_eval<NV, SCHEME, VISC>(P, a, d, qA - nb, qA, rA - nb, rA, c, pos, mx, L, lo, true, need_dt, F, lam, vis, tur);
+        face_eval<NV, SCHEME, VISC>(P, d, qA - nb, qA, rA - nb, rA, gA_, gnx, gny, gnz, pos, mx, L, lo, true, need_dt, F, lam, vis, tur);
 #pragma unroll
         for (int v = 0; v < NV; ++v) sm_F[v * EX + exr] = F[v];
         if (need_dt) {
@@ -404,45 +458,58 @@ __global__ void __launch_bounds__(NT, 1) k_sweep(const Params P, const KArgs a) 
           if (VISC && SST) sm_F[(NV + 2) * EX + exr] = tur;
         }
       }
+      PT_MARK(3)
     }
 
     // ---- k: the plane k+1 record of this column has landed ---------------------------------------------------------------
+    double kA = 0.0, knx = 0.0, kny = 0.0, knz = 0.0;
+    if (own && k_active) {   // metrics of the k face, requested before the wait so their latency overlaps it
+      const double* __restrict__ gp = a.geom + (long long)G_KA * fs + c + Ly.sk;
+      kA = gp[0]; knx = gp[fs]; kny = gp[2 * fs]; knz = gp[3 * fs];
+    }
     cp_async_wait_all();
-    double hi_n[NV], F_n[NV + 3];
+    PT_MARK(4)
+    double F_n[NV + 3];
 #pragma unroll
     for (int v = 0; v < NV + 3; ++v) F_n[v] = 0.0;
     if (own && k_active) {
       const double* const qB = plB + s0;
       const double* const rB = plB + NV * PSQ + s0;
+      double L[NV];
       if (k == kb - 1) {   // prime the carried hi value: cell kb-1 reconstructed along k
         double lo_[NV];
         if (SMQ) {
           double qm[NV], q0[NV], qp[NV];
 #pragma unroll
           for (int v = 0; v < NV; ++v) { qm[v] = q[v * fs + c - Ly.sk]; q0[v] = qA[v * PSQ]; qp[v] = qB[v * PSQ]; }
-          recon3<NV, INTERP>(P, qm, q0, qp, k, Ly.kmx, 2, hi_k, lo_);
+          recon3<NV, INTERP>(P, qm, q0, qp, k, Ly.kmx, 2, L, lo_);
         } else {
-          line_cell_values<NV, INTERP>(P, q, vol, c, Ly.sk, k, Ly.kmx, 2, hi_k, lo_);
+          line_cell_values<NV, INTERP>(P, q, vol, c, Ly.sk, k, Ly.kmx, 2, L, lo_);
         }
-      }
-      double lo[NV];
-      if (SMQ) {
-        double qm[NV], q0[NV];
+      } else {
 #pragma unroll
-        for (int v = 0; v < NV; ++v) { qm[v] = qA[v * PSQ]; q0[v] = qB[v * PSQ]; }
+        for (int v = 0; v < NV; ++v) L[v] = priv[(RC::OFF_PHI + v) * NMAIN];
+      }
+      double lo[NV], hi_n[NV];
+      if (SMQ) {
+        double qm[NV], q0[NV], q2[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) { qm[v] = qA[v * PSQ]; q0[v] = qB[v * PSQ]; q2[v] = priv[(RC::OFF_PQ2 + v) * NMAIN]; }
         recon3<NV, INTERP>(P, qm, q0, q2, k + 1, Ly.kmx, 2, hi_n, lo);
       } else {
         line_cell_values<NV, INTERP>(P, q, vol, c + Ly.sk, Ly.sk, k + 1, Ly.kmx, 2, hi_n, lo);
       }
-      double L[NV], F[NV], lam = 0.0, vis = 0.0, tur = 0.0;
 #pragma unroll
-      for (int v = 0; v < NV; ++v) L[v] = hi_k[v];
-      face_eval<NV, SCHEME, VISC>(P, a, 2, qA, qB, rA, rB, c + Ly.sk, k + 1, Ly.kmx, L, lo, flux_on_k, need_dt, F, lam, vis, tur);
+      for (int v = 0; v < NV; ++v) priv[(RC::OFF_PHI + v) * NMAIN] = hi_n[v];
+      double F[NV], lam = 0.0, vis = 0.0, tur = 0.0;
+      face_eval<NV, SCHEME, VISC>(P, 2, qA, qB, rA, rB, kA, knx, kny, knz, k + 1, Ly.kmx, L, lo, flux_on_k, need_dt, F, lam, vis, tur);
 #pragma unroll
       for (int v = 0; v < NV; ++v) F_n[v] = F[v];
       F_n[NV] = lam; F_n[NV + 1] = vis; F_n[NV + 2] = tur;
     }
+    PT_MARK(5)
     __syncthreads();
+    PT_MARK(2)
 
     // ---- the cell -----------------------------------------------------------------------------------------------------------
     if (inplane && own) {
@@ -450,6 +517,9 @@ __global__ void __launch_bounds__(NT, 1) k_sweep(const Params P, const KArgs a) 
       const int sl0 = ty * (TX + 1) + tx, sh0 = sl0 + 1, sl1 = SLOT_I + ty * TX + tx, sh1 = sl1 + TX;
       double res[NV];
       double merr = 0.0;
+      double F_k[NV + 3];
+#pragma unroll
+      for (int v = 0; v < NV + 3; ++v) F_k[v] = priv[(RC::OFF_PF + v) * NMAIN];
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
         const double Fl0 = sm_F[v * EX + sl0], Fh0 = sm_F[v * EX + sh0], Fl1 = sm_F[v * EX + sl1], Fh1 = sm_F[v * EX + sh1];
@@ -475,7 +545,7 @@ __global__ void __launch_bounds__(NT, 1) k_sweep(const Params P, const KArgs a) 
         for (int v = 0; v < NV; ++v) bad |= isnan(res[v]);
         if (bad) flag_error(a.err, F3D_ERR_NAN_FLUX, i, j, k);
       }
-      const double volc = vol[c];
+      const double volc = priv[(RC::OFF_PVOL + (k & 1)) * NMAIN];
       double qc[NV];
 #pragma unroll
       for (int v = 0; v < NV; ++v) qc[v] = qA[v * PSQ];
@@ -544,9 +614,15 @@ __global__ void __launch_bounds__(NT, 1) k_sweep(const Params P, const KArgs a) 
         double u1[NV], R[NV], u2[NV];
 #pragma unroll
         for (int v = 0; v < NV; ++v) R[v] = res[v];
-        u1[0] = a.quse[c];
+        if (a.have_store || a.quse != a.q) {
+          u1[0] = a.quse[c];
 #pragma unroll
-        for (int v = 1; v < NV; ++v) u1[v] = a.quse[v * fs + c] * u1[0];
+          for (int v = 1; v < NV; ++v) u1[v] = a.quse[v * fs + c] * u1[0];
+        } else {   // the state the update starts from is the staged one
+          u1[0] = qc[0];
+#pragma unroll
+          for (int v = 1; v < NV; ++v) u1[v] = qc[v] * u1[0];
+        }
         u1[4] = (u1[4] * P.inv_gm1 + 0.5 * (u1[1] * u1[1] + u1[2] * u1[2] + u1[3] * u1[3])) * rcp64(u1[0]) + 0.;
         if (SST) {
           const double F1 = rA[(RC::OFF_MU + 2) * PS];
@@ -586,23 +662,25 @@ __global__ void __launch_bounds__(NT, 1) k_sweep(const Params P, const KArgs a) 
         }
       }
       if (a.want_norms) {   // resnorm.f90:187-198
-        nrm[0] += merr;
+        priv[RC::OFF_PN * NMAIN] += merr;
 #pragma unroll
-        for (int v = 0; v < NV; ++v) nrm[v + 1] += res[v] * res[v];
+        for (int v = 0; v < NV; ++v) priv[(RC::OFF_PN + 1 + v) * NMAIN] += res[v] * res[v];
       }
     }
+    if (own && k_active) {
 #pragma unroll
-    for (int v = 0; v < NV; ++v) hi_k[v] = hi_n[v];
-#pragma unroll
-    for (int v = 0; v < NV + 3; ++v) F_k[v] = F_n[v];
+      for (int v = 0; v < NV + 3; ++v) priv[(RC::OFF_PF + v) * NMAIN] = F_n[v];
+    }
+    PT_MARK(6)
   }
 
+  PT_FLUSH
   if (a.want_norms) {   // per-CTA partial: warp shuffle, then the block
     __syncthreads();
     double* sred = smem;   // [NV+1][NT/32]
 #pragma unroll
     for (int v = 0; v <= NV; ++v) {
-      double x = nrm[v];
+      double x = main_thr ? priv[(RC::OFF_PN + v) * NMAIN] : 0.0;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
       if (lane == 0) sred[v * (NT / 32) + wid] = x;
@@ -713,6 +791,19 @@ int launch_residual(Ctx* ctx, int mode, double TF, double SF, int use_store_sum,
   F3D_CUDA(cudaGetLastError());
   return 0;
 }
+
+#ifdef F3D_PHASE_TIMING
+extern "C" void fest3d_gpu_phase_dump() {
+  unsigned long long h[16];
+  cudaMemcpyFromSymbol(h, g_phase, sizeof(h));
+  const char* nm[8] = {"stage issue", "recon i/j", "barrier wait", "face i/j", "cp.async wait", "k recon+face", "cell (update)", "loop top"};
+  unsigned long long tot = 0;
+  for (int n = 0; n < 8; ++n) tot += h[n];
+  for (int n = 0; n < 8; ++n) printf("phase %-14s %6.2f %%\n", nm[n], 100.0 * h[n] / (double)tot);
+  memset(h, 0, sizeof(h));
+  cudaMemcpyToSymbol(g_phase, h, sizeof(h));
+}
+#endif
 
 int launch_norms(Ctx* ctx, int slot) {
   const int nvp1 = ctx->P.L.nv + 1;
