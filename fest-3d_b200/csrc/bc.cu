@@ -296,6 +296,9 @@ int launch_bc(Ctx* ctx) {
     const int id = ctx->P.bc_id[face - 1];
     if (id == -8 || id == -9) ordered = true;
   }
+  // a fill reads interior layers 1..4 along its normal: with fewer than 4 cells there (quasi-2-D blocks, kmx == 2) those are the
+  // ghost cells of the opposite face, so the reference order (low face first, then the high face reading its fresh ghosts) matters
+  if (std::min(std::min(L.imx, L.jmx), L.kmx) - 1 < 4) ordered = true;
   for (int face = 1; face <= 6; ++face) {
     const int id = ctx->P.bc_id[face - 1];
     if (id >= 0 || id == -10 || ordered) continue;
