@@ -1,0 +1,552 @@
+// Fused residual / time-step / update kernel, generation 3 ("direction-specialised warps").
+//
+// Same data flow as generation 2 (sweep.cu): one CTA owns a TX x TY column of cells and marches through a chunk of k
+// planes, the per-cell records (q, Green-Gauss gradients, mu / mu_t / F1, centre) of planes k and k+1 are staged in shared
+// memory by cp.async, every reconstruction and every face flux is evaluated once.  What changed is WHO does the work.
+// Generation 2 ran all three directions in every "main" thread (188 registers, 8 warps per SM, 5 main warps on 4 SM
+// sub-partitions, three CTA-wide barriers per plane: 32 % FP64 pipe, profiles/r01_g2_summary.md).  Here the three
+// directions of the SAME tile are given to three different warp groups that run concurrently:
+//
+//   I rows   (TY warps)  reconstruct along i, exchange through smem (named barrier 1, I group only), i-face fluxes
+//   J rows   (TY warps)  the same along j (named barrier 2)
+//   K rows   (TY warps)  own the cells: k reconstruction and k-face flux with the k state carried privately, and the
+//                        cell work (residual assembly, SST source, local time step, update, norm partials) of the
+//                        PREVIOUS plane, whose i/j fluxes the other groups left in a double-buffered exchange area
+//   3 halo warps         the i columns / j rows just outside the tile (as in generation 2)
+//
+// so an SM sub-partition holds one I, one J, one K warp (+ at most one halo warp): 3.75 warps per sub-partition instead
+// of 2, each with a third of the live state (<= 136 registers), equal work per sub-partition, and ONE CTA-wide barrier
+// per plane.  The groups only meet at that barrier; the i/j fluxes of plane k are consumed one iteration later.
+//
+// Reference pipeline reproduced: as listed in sweep.cu (src/update.f90:534-545, 228-491; src/face/state/*.f90;
+// src/boundary/boundary_state_reconstruction.f90:93-131; src/face/flux/convective/*.f90, scheme.f90:111-141;
+// src/viscous.f90:144-447; src/source.f90:158-270; src/time.f90:122-246,366-531; src/resnorm.f90:171-199).
+#include "sweep_common.cuh"
+
+namespace f3d {
+namespace g3 {
+
+constexpr int TX = 32, TY = 4;
+constexpr int NMAIN = TX * TY;
+constexpr int NW = 3 * TY + 3;
+constexpr int NT = 32 * NW;
+constexpr int W_IH = 3 * TY, W_JH = 3 * TY + 1, W_JL = 3 * TY + 2;
+constexpr int N_IGRP = 32 * (TY + 1), N_JGRP = 32 * (TY + 2);   // threads on named barriers 1 and 2
+
+// staged plane: (TX+2) x (TY+2) slots, slot = (ty+1)*PW + (tx+1); the q fields carry NOUT extra slots for the second
+// ring cells the halo threads' own reconstruction reads
+constexpr int PW = TX + 2;
+constexpr int PS = PW * (TY + 2);
+constexpr int NOUT = 2 * TY + 2 * TX;
+constexpr int PSQ = PS + NOUT;
+// exchange area ([field][slot], slot = face): i faces TY x (TX+1), j faces (TY+1) x TX
+constexpr int SLOT_I = TY * (TX + 1);
+constexpr int SLOT_J = (TY + 1) * TX;
+constexpr int EX = SLOT_I + SLOT_J;
+
+template <int NV, bool VISC>
+struct Sm : RecF<NV, VISC> {
+  using RecF<NV, VISC>::NR;
+  static constexpr int NF = NV + 3;                       // flux + the lambda / viscous / turbulent face terms of the time step
+  static constexpr int PLANE = NV * PSQ + NR * PS;        // doubles per staged plane
+  static constexpr int OFF_X = 2 * PLANE;                 // exchange area [2][NF][EX]: hi values, then fluxes (same slot)
+  static constexpr int OFF_PRIV = OFF_X + 2 * NF * EX;    // private slots of the K threads, [field][NMAIN]:
+  static constexpr int P_FK = 0;                          //   [2][NF] k-face flux; the face below plane p sits in half p & 1
+  static constexpr int P_HI = 2 * NF;                     //   [NV] value at the high k face of the newest reconstructed cell
+  static constexpr int P_N = P_HI + NV;                   //   [NV+1] norm partials
+  static constexpr int P_Q2 = P_N + NV + 1;               //   [NV] q of plane k+2
+  static constexpr int P_VOL = P_Q2 + NV;                 //   [2] volume of planes (p & 1)
+  static constexpr int NPRIV = P_VOL + 2;
+  static constexpr int TOTAL = OFF_PRIV + NPRIV * NMAIN;
+};
+
+__device__ __forceinline__ void bar_all() { asm volatile("bar.sync 0;" ::: "memory"); }
+__device__ __forceinline__ void bar_group(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+template <int NV, int INTERP, int SCHEME, bool VISC>
+__global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a) {
+  using S = Sm<NV, VISC>;
+  constexpr bool SST = (NV == 7);
+  constexpr bool SMQ = (INTERP == F3D_MUSCL || INTERP == F3D_INTERP_NONE);   // 3-point stencils read the staged planes
+  constexpr int NF = S::NF;
+  extern __shared__ double smem[];
+  const Layout& Ly = P.L;
+  const long long fs = Ly.fs;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int i0 = 1 + blockIdx.x * TX, j0 = 1 + blockIdx.y * TY;
+  const int kb = 1 + blockIdx.z * a.kchunk, ke = min(kb + a.kchunk, Ly.kmx);   // planes kb .. ke-1
+  const bool need_dt = a.first_stage != 0;
+  const bool flux_on_k = Ly.kmx != 2;   // H = 0 when kmx == 2 (ausm.f90:205-210)
+  const bool k_active = flux_on_k || VISC || need_dt;
+  const double* __restrict__ q = a.q;
+  const double* __restrict__ vol = a.geom + (long long)G_VOL * fs;
+
+  if (wid >= 2 * TY && wid < 3 * TY) {
+    // =============================================== K rows: the cells ===============================================
+    const int tx = lane, ty = wid - 2 * TY;
+    int i = i0 + tx, j = j0 + ty;
+    const bool own = (i <= Ly.imx - 1) && (j <= Ly.jmx - 1);
+    const bool stg = (i <= Ly.imx + 1) && (j <= Ly.jmx + 1);   // ghost cells next to the last faces feed the i/j faces there
+    if (i > Ly.imx + 1) i = Ly.imx + 1;
+    if (j > Ly.jmx + 1) j = Ly.jmx + 1;
+    const int s0 = (ty + 1) * PW + tx + 1;
+    double* const priv = smem + S::OFF_PRIV + ty * TX + tx;
+    const int sl0 = ty * (TX + 1) + tx, sh0 = sl0 + 1, sl1 = SLOT_I + ty * TX + tx, sh1 = sl1 + TX;
+
+    auto stage_own = [&](int kk) {   // record of this thread's cell at plane kk -> ring buffer kk & 1
+      if (!stg) return;
+      double* pl = smem + (kk & 1) * S::PLANE;
+      const long long c1 = Ly.idx(i, j, kk);
+#pragma unroll
+      for (int v = 0; v < NV; ++v) cp_async8(pl + v * PSQ + s0, q + v * fs + c1);
+      if (VISC) {
+        double* pr = pl + NV * PSQ;
+#pragma unroll
+        for (int f = 0; f < S::NGF; ++f) cp_async8(pr + f * PS + s0, a.grad + f * fs + c1);
+#pragma unroll
+        for (int f = 0; f < S::NMU; ++f) cp_async8(pr + (S::OFF_MU + f) * PS + s0, a.mu + f * fs + c1);
+#pragma unroll
+        for (int f = 0; f < 3; ++f) cp_async8(pr + (S::OFF_C + f) * PS + s0, a.geom + (long long)(G_CX + f) * fs + c1);
+      }
+      if (own) cp_async8(priv + (S::P_VOL + (kk & 1)) * NMAIN, vol + c1);
+    };
+
+#pragma unroll
+    for (int f = 0; f < S::P_Q2; ++f) priv[f * NMAIN] = 0.0;
+    stage_own(kb - 1);
+    cp_async_wait_all();
+
+    for (int k = kb - 1; k <= ke; ++k) {
+      bar_all();   // plane k is staged; the i/j fluxes of plane k-1 are in exchange half (k-1) & 1
+      const int kc = k - 1;                                   // plane of the cell work
+      const bool cell_on = own && kc >= kb;
+      const bool more = k <= ke - 1;                          // a k face above plane k is still to be evaluated
+      const long long c = Ly.idx(i, j, k);
+      const double* const plA = smem + (k & 1) * S::PLANE;          // plane k
+      double* const plB = smem + ((k + 1) & 1) * S::PLANE;          // plane k-1 now, plane k+1 after the staging below
+
+      // ---- cell work of plane k-1, part 1: everything that reads this thread's record of plane k-1 ---------------------
+      double qc[NV], S_k = 0.0, S_w = 0.0, F1c = 0.0, volc = 0.0;
+      if (cell_on) {
+        const double* const qC = plB + s0;
+        const double* const rC = plB + NV * PSQ + s0;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) qc[v] = qC[v * PSQ];
+        volc = priv[(S::P_VOL + (kc & 1)) * NMAIN];
+        if (SST && VISC) {   // source.f90:214-268
+          double g[6][3];
+#pragma unroll
+          for (int cc = 0; cc < 6; ++cc) {
+            if (cc == 3) continue;
+            g[cc][0] = rC[(3 * cc + 0) * PS]; g[cc][1] = rC[(3 * cc + 1) * PS]; g[cc][2] = rC[(3 * cc + 2) * PS];
+          }
+          const double mut = rC[(S::OFF_MU + 1) * PS];
+          F1c = rC[(S::OFF_MU + 2) * PS];
+          const double density = qc[0], tk = qc[5], tw = qc[6];
+          const double wx = g[2][1] - g[1][2], wy = g[0][2] - g[2][0], wz = g[1][0] - g[0][1];
+          const double vort = sqrt(wx * wx + wy * wy + wz * wz);
+          double CD = 2 * density * kSigmaW2 * (g[4][0] * g[5][0] + g[4][1] * g[5][1] + g[4][2] * g[5][2]) * rcp64(tw);
+          CD = dmax(CD, P.cd_floor);
+          const double gama = P.gama1 * F1c + P.gama2 * (1. - F1c);
+          const double beta = kBeta1 * F1c + kBeta2 * (1. - F1c);
+          const double D_k = kBstar * density * tw * tk;
+          const double D_w = beta * density * (tw * tw);
+          const double divergence = g[0][0] + g[1][1] + g[2][2];
+          double P_k = mut * (vort * vort) - ((2.0 / 3.0) * density * tk * divergence);
+          P_k = dmin(P_k, P.pk_limiter * D_k);
+          const double P_w = (density * gama * rcp64(mut)) * P_k;
+          const double lamda = (1. - F1c) * CD;
+          S_k = (P_k - D_k) * volc;
+          S_w = (P_w - D_w + lamda) * volc;
+        }
+      }
+
+      // ---- stage this thread's record of plane k+1 over the one just consumed; q of plane k+2 for the k stencil ----------
+      if (more) {
+        stage_own(k + 1);
+        if (own && k_active && SMQ) {
+#pragma unroll
+          for (int v = 0; v < NV; ++v) cp_async8(priv + (S::P_Q2 + v) * NMAIN, q + v * fs + c + 2 * Ly.sk);
+        }
+      }
+
+      // ---- cell work of plane k-1, part 2 -------------------------------------------------------------------------------------
+      if (cell_on) {
+        const long long cc = c - Ly.sk;
+        const double* const xF = smem + S::OFF_X + (kc & 1) * NF * EX;     // i/j face fluxes of plane k-1
+        const double* const Flo = priv + (S::P_FK + (kc & 1) * NF) * NMAIN;   // k face below the cell
+        const double* const Fhi = priv + (S::P_FK + (k & 1) * NF) * NMAIN;    // k face above it
+        double res[NV];
+        double merr = 0.0;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const double Fl0 = xF[v * EX + sl0], Fh0 = xF[v * EX + sh0], Fl1 = xF[v * EX + sl1], Fh1 = xF[v * EX + sh1];
+          double r = 0.0;
+          r = r + (Fh0 - Fl0);   // scheme.f90:133-135
+          r = r + (Fh1 - Fl1);
+          if (k_active) r = r + (Fhi[v * NMAIN] - Flo[v * NMAIN]);
+          res[v] = r;
+          if (v == 0) {          // resnorm.f90:190-198
+            if (i == 1) merr += Fl0;
+            if (i == Ly.imx - 1) merr -= Fh0;
+            if (j == 1) merr += Fl1;
+            if (j == Ly.jmx - 1) merr -= Fh1;
+            if (k_active) {
+              if (kc == 1) merr += Flo[0];
+              if (kc == Ly.kmx - 1) merr -= Fhi[0];
+            }
+          }
+        }
+        {
+          bool bad = false;
+#pragma unroll
+          for (int v = 0; v < NV; ++v) bad |= isnan(res[v]);
+          if (bad) flag_error(a.err, F3D_ERR_NAN_FLUX, i, j, kc);
+        }
+        if (SST && VISC) {
+          res[5] = res[5] - S_k;
+          res[6] = res[6] - S_w;
+        }
+
+        double dtc = 0.0;
+        if (need_dt) {
+          if (P.time_stepping == 1 && P.global_time_step > 0) {
+            dtc = P.global_time_step;
+          } else {
+            const double* lamv = xF + NV * EX;
+            const double lmxsum = lamv[sl0] + lamv[sl1] + Flo[NV * NMAIN] + lamv[sh0] + lamv[sh1] + Fhi[NV * NMAIN];
+            dtc = rcp64(lmxsum);
+            dtc = dtc * volc * P.CFL;
+            if (VISC) {
+              const double* visv = xF + (NV + 1) * EX;
+              double s = visv[sl0] + visv[sl1] + Flo[(NV + 1) * NMAIN] + visv[sh0] + visv[sh1] + Fhi[(NV + 1) * NMAIN];
+              s = P.gm * s * P.inv_Pr;
+              s = 2. * rcp64(s + (2. * P.CFL * volc * rcp64(dtc)));
+              dtc = P.CFL * (s * volc);
+              if (SST) {
+                const double* turv = xF + (NV + 2) * EX;
+                double t = turv[sl0] + turv[sl1] + Flo[(NV + 2) * NMAIN] + turv[sh0] + turv[sh1] + Fhi[(NV + 2) * NMAIN];
+                t = P.gm * t * P.inv_tPr;
+                t = 2. * rcp64(t + (2. * P.CFL * volc * rcp64(dtc)));
+                dtc = P.CFL * (t * volc);
+              }
+            }
+          }
+          a.dt[cc] = dtc;
+        } else if (a.mode == MODE_UPDATE) {
+          dtc = a.dt[cc];
+        }
+
+        if (a.mode == MODE_RESIDUE_ONLY) {
+#pragma unroll
+          for (int v = 0; v < NV; ++v) a.residue[v * fs + cc] = res[v];
+        } else {   // update.f90:371-485
+          double u1[NV], R[NV], u2[NV];
+#pragma unroll
+          for (int v = 0; v < NV; ++v) R[v] = res[v];
+          if (a.have_store || a.quse != a.q) {
+            u1[0] = a.quse[cc];
+#pragma unroll
+            for (int v = 1; v < NV; ++v) u1[v] = a.quse[v * fs + cc] * u1[0];
+          } else {   // the state the update starts from is the staged one
+            u1[0] = qc[0];
+#pragma unroll
+            for (int v = 1; v < NV; ++v) u1[v] = qc[v] * u1[0];
+          }
+          u1[4] = (u1[4] * P.inv_gm1 + 0.5 * (u1[1] * u1[1] + u1[2] * u1[2] + u1[3] * u1[3])) * rcp64(u1[0]) + 0.;
+          if (SST) {
+            const double F1 = VISC ? F1c : 0.0;
+            const double beta = kBeta1 * F1 + (1. - F1) * kBeta2;
+            R[5] = R[5] * rcp64(1 + (beta * qc[6] * dtc));
+            R[6] = R[6] * rcp64(1 + (2 * beta * qc[6] * dtc));
+          }
+          if (a.have_store) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+              const double rn = a.rstore[v * fs + cc] + a.SF * R[v];
+              a.rstore[v * fs + cc] = rn;
+              if (a.use_store_sum) R[v] = rn;
+            }
+          }
+          const double fac_ = (a.TF * dtc * rcp64(volc));
+#pragma unroll
+          for (int v = 0; v < NV; ++v) u2[v] = u1[v] - R[v] * fac_;
+          const double iu = 1.0 / u2[0];   // IEEE: u2[0] may be <= 0 or NaN here and must reach the check below unchanged
+#pragma unroll
+          for (int v = 1; v < NV; ++v) u2[v] = u2[v] * iu;
+          u2[4] = (P.gm - 1.) * u2[0] * (u2[4] - (0.5 * (u2[1] * u2[1] + u2[2] * u2[2] + u2[3] * u2[3])) - 0.);
+          bool bad = (u2[0] < 0.) || (u2[4] < 0.);
+#pragma unroll
+          for (int v = 0; v < NV; ++v) bad |= isnan(u2[v]);
+          if (bad) {
+            flag_error(a.err, F3D_ERR_NEGATIVE_STATE, i, j, kc);
+#pragma unroll
+            for (int v = 0; v < NV; ++v) a.qnew[v * fs + cc] = qc[v];
+          } else {
+#pragma unroll
+            for (int v = 0; v < 5; ++v) a.qnew[v * fs + cc] = u2[v];
+            if (SST) {
+              a.qnew[5 * fs + cc] = (u2[5] >= 0.) ? u2[5] : qc[5];
+              a.qnew[6 * fs + cc] = (u2[6] >= 0.) ? u2[6] : qc[6];
+            }
+          }
+        }
+        if (a.want_norms) {   // resnorm.f90:187-198
+          priv[S::P_N * NMAIN] += merr;
+#pragma unroll
+          for (int v = 0; v < NV; ++v) priv[(S::P_N + 1 + v) * NMAIN] += res[v] * res[v];
+        }
+      }
+
+      // ---- k face between planes k and k+1 ---------------------------------------------------------------------------------
+      if (more) {
+        double kA = 0.0, knx = 0.0, kny = 0.0, knz = 0.0;
+        if (own && k_active) {   // metrics of the k face, requested before the wait so their latency overlaps it
+          const double* __restrict__ gp = a.geom + (long long)G_KA * fs + c + Ly.sk;
+          kA = gp[0]; knx = gp[fs]; kny = gp[2 * fs]; knz = gp[3 * fs];
+        }
+        cp_async_wait_all();
+        if (own && k_active) {
+          const double* const qA = plA + s0;
+          const double* const rA = plA + NV * PSQ + s0;
+          const double* const qB = plB + s0;
+          const double* const rB = plB + NV * PSQ + s0;
+          double L[NV];
+          if (k == kb - 1) {   // prime the carried hi value: cell kb-1 reconstructed along k
+            double lo_[NV];
+            if (SMQ) {
+              double qm[NV], q0[NV], qp[NV];
+#pragma unroll
+              for (int v = 0; v < NV; ++v) { qm[v] = q[v * fs + c - Ly.sk]; q0[v] = qA[v * PSQ]; qp[v] = qB[v * PSQ]; }
+              recon3<NV, INTERP>(P, qm, q0, qp, k, Ly.kmx, 2, L, lo_);
+            } else {
+              line_cell_values<NV, INTERP>(P, q, vol, c, Ly.sk, k, Ly.kmx, 2, L, lo_);
+            }
+          } else {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) L[v] = priv[(S::P_HI + v) * NMAIN];
+          }
+          double lo[NV];
+          {
+            double hi_n[NV];
+            if (SMQ) {
+              double qm[NV], q0[NV], q2[NV];
+#pragma unroll
+              for (int v = 0; v < NV; ++v) { qm[v] = qA[v * PSQ]; q0[v] = qB[v * PSQ]; q2[v] = priv[(S::P_Q2 + v) * NMAIN]; }
+              recon3<NV, INTERP>(P, qm, q0, q2, k + 1, Ly.kmx, 2, hi_n, lo);
+            } else {
+              line_cell_values<NV, INTERP>(P, q, vol, c + Ly.sk, Ly.sk, k + 1, Ly.kmx, 2, hi_n, lo);
+            }
+#pragma unroll
+            for (int v = 0; v < NV; ++v) priv[(S::P_HI + v) * NMAIN] = hi_n[v];
+          }
+          double F[NV], lam = 0.0, vis = 0.0, tur = 0.0;
+          face_eval<NV, SCHEME, VISC, PS, PSQ>(P, 2, qA, qB, rA, rB, kA, knx, kny, knz, k + 1, Ly.kmx, L, lo, flux_on_k, need_dt, F, lam, vis, tur);
+          double* const Fn = priv + (S::P_FK + ((k + 1) & 1) * NF) * NMAIN;
+#pragma unroll
+          for (int v = 0; v < NV; ++v) Fn[v * NMAIN] = F[v];
+          Fn[NV * NMAIN] = lam; Fn[(NV + 1) * NMAIN] = vis; Fn[(NV + 2) * NMAIN] = tur;
+        }
+      }
+    }
+  } else {
+    // ===================================== I rows, J rows and the three halo warps =====================================
+    int i, j, s0, d;
+    bool rec, fac, stg = false, wr_hi = true;
+    int om, op;                       // staged-slot offsets of the two neighbours along d
+    int exw, exr;                     // exchange slots: where the hi value goes; where L is read and the flux written
+    long long outer_off = 0;          // halo threads: global offset of the outer neighbour they stage, and its slot
+    int outer_slot = 0;
+    if (wid < TY) {                   // I row
+      const int tx = lane, ty = wid;
+      d = 0; i = i0 + tx; j = j0 + ty;
+      rec = fac = (j <= Ly.jmx - 1) && (i <= Ly.imx);
+      s0 = (ty + 1) * PW + tx + 1; om = -1; op = 1;
+      exw = ty * (TX + 1) + tx + 1; exr = ty * (TX + 1) + tx;
+    } else if (wid < 2 * TY) {        // J row
+      const int tx = lane, ty = wid - TY;
+      d = 1; i = i0 + tx; j = j0 + ty;
+      rec = fac = (i <= Ly.imx - 1) && (j <= Ly.jmx);
+      s0 = (ty + 1) * PW + tx + 1; om = -PW; op = PW;
+      exw = SLOT_I + (ty + 1) * TX + tx; exr = SLOT_I + ty * TX + tx;
+    } else if (wid == W_IH) {         // the two i columns next to the tile: lanes 0..TY-1 low side, TY..2TY-1 high side
+      const int r = lane % TY, side = lane / TY;
+      d = 0; i = (side == 0) ? i0 - 1 : i0 + TX; j = j0 + r;
+      rec = (side < 2) && (j <= Ly.jmx - 1) && (i <= Ly.imx);
+      stg = (side < 2) && (j <= Ly.jmx + 1) && (i <= Ly.imx + 1);
+      fac = rec && side == 1; wr_hi = side == 0;
+      s0 = (r + 1) * PW + (side == 0 ? 0 : TX + 1);
+      outer_slot = PS + (side & 1) * TY + r;
+      outer_off = (side == 0) ? -1 : 1;
+      om = (side == 0) ? outer_slot - s0 : -1; op = (side == 0) ? 1 : outer_slot - s0;
+      exw = r * (TX + 1) + (side == 0 ? 0 : TX); exr = r * (TX + 1) + TX;
+    } else {                          // high (W_JH) and low (W_JL) j rows next to the tile
+      const bool high = wid == W_JH;
+      d = 1; i = i0 + lane; j = high ? j0 + TY : j0 - 1;
+      rec = (i <= Ly.imx - 1) && (j <= Ly.jmx);
+      stg = (i <= Ly.imx + 1) && (j <= Ly.jmx + 1);
+      fac = rec && high; wr_hi = !high;
+      s0 = (high ? TY + 1 : 0) * PW + lane + 1;
+      outer_slot = PS + 2 * TY + (high ? TX : 0) + lane;
+      outer_off = high ? Ly.sj : -Ly.sj;
+      om = high ? -PW : outer_slot - s0; op = high ? outer_slot - s0 : PW;
+      exw = SLOT_I + (high ? TY * TX : 0) + lane; exr = SLOT_I + TY * TX + lane;
+    }
+    if (i > Ly.imx + 1) i = Ly.imx + 1;
+    if (j > Ly.jmx + 1) j = Ly.jmx + 1;
+    const int pos = (d == 0) ? i : j, mx = (d == 0) ? Ly.imx : Ly.jmx;
+    const int nb = (d == 0) ? 1 : PW;
+    const int bar_id = 1 + d, bar_n = (d == 0) ? N_IGRP : N_JGRP;
+
+    auto stage_ring = [&](int kk) {   // halo threads: their ring cell (+ the outer neighbour's q) of plane kk
+      if (!stg) return;
+      double* pl = smem + (kk & 1) * S::PLANE;
+      const long long c1 = Ly.idx(i, j, kk);
+#pragma unroll
+      for (int v = 0; v < NV; ++v) cp_async8(pl + v * PSQ + s0, q + v * fs + c1);
+      if (SMQ && rec) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) cp_async8(pl + v * PSQ + outer_slot, q + v * fs + c1 + outer_off);
+      }
+      if (VISC) {
+        double* pr = pl + NV * PSQ;
+#pragma unroll
+        for (int f = 0; f < S::NGF; ++f) cp_async8(pr + f * PS + s0, a.grad + f * fs + c1);
+#pragma unroll
+        for (int f = 0; f < S::NMU; ++f) cp_async8(pr + (S::OFF_MU + f) * PS + s0, a.mu + f * fs + c1);
+#pragma unroll
+        for (int f = 0; f < 3; ++f) cp_async8(pr + (S::OFF_C + f) * PS + s0, a.geom + (long long)(G_CX + f) * fs + c1);
+      }
+    };
+
+    for (int k = kb - 1; k <= ke; ++k) {
+      bar_all();
+      if (k + 1 <= ke - 1) stage_ring(k + 1);
+      if (k >= kb && k <= ke - 1) {
+        const long long c = Ly.idx(i, j, k);
+        double* const pl = smem + (k & 1) * S::PLANE;
+        const double* const qA = pl + s0;
+        const double* const rA = pl + NV * PSQ + s0;
+        double* const xH = smem + S::OFF_X + (k & 1) * NF * EX;
+        double gA_ = 0.0, gnx = 0.0, gny = 0.0, gnz = 0.0;   // face metrics, requested before the reconstruction
+        if (fac) {
+          const double* __restrict__ gp = a.geom + (long long)(G_IA + 4 * d) * fs + c;
+          gA_ = gp[0]; gnx = gp[fs]; gny = gp[2 * fs]; gnz = gp[3 * fs];
+        }
+        double lo[NV];
+        if (rec) {
+          double hi[NV];
+          if (SMQ) {
+            double qm[NV], q0[NV], qp[NV];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) { qm[v] = qA[v * PSQ + om]; q0[v] = qA[v * PSQ]; qp[v] = qA[v * PSQ + op]; }
+            recon3<NV, INTERP>(P, qm, q0, qp, pos, mx, d, hi, lo);
+          } else {
+            line_cell_values<NV, INTERP>(P, q, vol, c, (d == 0) ? 1 : Ly.sj, pos, mx, d, hi, lo);
+          }
+          if (wr_hi) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) xH[v * EX + exw] = hi[v];
+          }
+        }
+        bar_group(bar_id, bar_n);
+        if (fac) {
+          double L[NV], F[NV], lam = 0.0, vis = 0.0, tur = 0.0;
+#pragma unroll
+          for (int v = 0; v < NV; ++v) L[v] = xH[v * EX + exr];
+          face_eval<NV, SCHEME, VISC, PS, PSQ>(P, d, qA - nb, qA, rA - nb, rA, gA_, gnx, gny, gnz, pos, mx, L, lo, true, need_dt, F, lam, vis, tur);
+#pragma unroll
+          for (int v = 0; v < NV; ++v) xH[v * EX + exr] = F[v];
+          if (need_dt) {
+            xH[NV * EX + exr] = lam;
+            if (VISC) xH[(NV + 1) * EX + exr] = vis;
+            if (VISC && SST) xH[(NV + 2) * EX + exr] = tur;
+          }
+        }
+      }
+      cp_async_wait_all();
+    }
+  }
+
+  if (a.want_norms) {   // per-CTA partial: warp shuffle inside the K rows, then across them
+    bar_all();
+    double* sred = smem;   // [NV+1][TY]
+    const bool krow = wid >= 2 * TY && wid < 3 * TY;
+    if (krow) {
+      const double* priv = smem + S::OFF_PRIV + (wid - 2 * TY) * TX + lane;
+      double x[NV + 1];
+#pragma unroll
+      for (int v = 0; v <= NV; ++v) x[v] = priv[(S::P_N + v) * NMAIN];
+#pragma unroll
+      for (int v = 0; v <= NV; ++v) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x[v] += __shfl_down_sync(0xffffffffu, x[v], o);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int v = 0; v <= NV; ++v) sred[v * TY + (wid - 2 * TY)] = x[v];
+      }
+    }
+    bar_all();
+    if (tid <= NV) {
+      double x = 0.0;
+      for (int w = 0; w < TY; ++w) x += sred[tid * TY + w];
+      const long long cta = blockIdx.x + (long long)gridDim.x * (blockIdx.y + (long long)gridDim.y * blockIdx.z);
+      a.red[cta * (NV + 1) + tid] = x;
+    }
+  }
+}
+
+// k planes per CTA: long enough to amortise the two extra iterations, short enough for >= ~4 waves of CTAs
+static int pick_kchunk(const Layout& L) {
+  const int nk = L.kmx - 1;
+  const long long tiles = (long long)((L.imx - 1 + TX - 1) / TX) * ((L.jmx - 1 + TY - 1) / TY);
+  int chunk = nk;
+  while (chunk > 16 && tiles * ((nk + chunk - 1) / chunk) < 148 * 4) chunk = (chunk + 1) / 2;
+  return chunk;
+}
+
+template <int NV, int INTERP, int SCHEME, bool VISC>
+static int launch_one(Ctx* ctx, KArgs& a) {
+  const Layout& L = ctx->P.L;
+  a.kchunk = pick_kchunk(L);
+  dim3 grid((L.imx - 1 + TX - 1) / TX, (L.jmx - 1 + TY - 1) / TY, (L.kmx - 1 + a.kchunk - 1) / a.kchunk);
+  const size_t shm = sizeof(double) * Sm<NV, VISC>::TOTAL;
+  static bool attr_set[64] = {false};   // per instantiation and device
+  if (!attr_set[ctx->device & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(k_sweep3<NV, INTERP, SCHEME, VISC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+    if (e != cudaSuccess) return F3D_ERR_CUDA;
+    attr_set[ctx->device & 63] = true;
+  }
+  k_sweep3<NV, INTERP, SCHEME, VISC><<<grid, NT, shm, ctx->stream>>>(ctx->P, a);
+  ctx->launches++;
+  return 0;
+}
+
+template <int NV, bool VISC>
+static int launch_interp(Ctx* ctx, KArgs& a) {
+  switch (ctx->P.interpolant) {
+    case F3D_INTERP_NONE: return launch_one<NV, F3D_INTERP_NONE, -1, VISC>(ctx, a);
+    case F3D_MUSCL:
+      if (ctx->P.scheme == F3D_AUSM) return launch_one<NV, F3D_MUSCL, F3D_AUSM, VISC>(ctx, a);   // the headline configuration
+      return launch_one<NV, F3D_MUSCL, -1, VISC>(ctx, a);
+    case F3D_PPM: return launch_one<NV, F3D_PPM, -1, VISC>(ctx, a);
+    case F3D_WENO: return launch_one<NV, F3D_WENO, -1, VISC>(ctx, a);
+    case F3D_WENO_NM: return launch_one<NV, F3D_WENO_NM, -1, VISC>(ctx, a);
+  }
+  return F3D_ERR_UNSUPPORTED;
+}
+
+}  // namespace g3
+
+int sweep3_grid_ctas(const Layout& L) {
+  const int chunk = g3::pick_kchunk(L);
+  return ((L.imx - 1 + g3::TX - 1) / g3::TX) * ((L.jmx - 1 + g3::TY - 1) / g3::TY) * ((L.kmx - 1 + chunk - 1) / chunk);
+}
+
+int launch_sweep3(Ctx* ctx, KArgs& a) {
+  if (ctx->P.viscous) return ctx->P.sst ? g3::launch_interp<7, true>(ctx, a) : g3::launch_interp<5, true>(ctx, a);
+  return g3::launch_interp<5, false>(ctx, a);
+}
+
+}  // namespace f3d

@@ -1,0 +1,243 @@
+// Device helpers shared by the generations of the fused sweep kernel (sweep.cu: generation 2, sweep3.cu: generation 3):
+// kernel arguments, the field order of a staged cell record, face reconstruction from staged values, the viscous face flux
+// and the per-face evaluation.  Tile-dependent strides (PS: slots of a staged record plane, PSQ: slots of a staged q plane)
+// are template parameters.
+#pragma once
+#include "ctx.hpp"
+#include "physics.cuh"
+
+namespace f3d {
+
+template <int NV, bool VISC>
+struct RecF {   // fields of the non-q part of a cell record
+  static constexpr bool SST = (NV == 7);
+  static constexpr int NG = SST ? 6 : 4;
+  static constexpr int NGF = VISC ? 3 * NG : 0;            // gradient component c, direction d -> field 3*c+d
+  static constexpr int NMU = VISC ? (SST ? 3 : 1) : 0;     // mu, mu_t, F1
+  static constexpr int OFF_MU = NGF, OFF_C = NGF + NMU;    // then the cell centre x,y,z
+  static constexpr int NR = VISC ? NGF + NMU + 3 : 0;
+};
+
+__device__ __forceinline__ void flag_error(int* err, int cls, int i, int j, int k) {
+  int old = atomicOr(&err[0], cls);
+  if ((old & cls) == 0) { err[1] = i; err[2] = j; err[3] = k; }
+}
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+struct KArgs {
+  const double* __restrict__ q;       // nv fields, ghost-filled
+  const double* __restrict__ quse;    // U_store or q
+  double* __restrict__ qnew;          // nv fields (update mode)
+  double* __restrict__ residue;       // nv fields (residue mode)
+  double* __restrict__ rstore;        // nv fields or nullptr
+  double* __restrict__ dt;            // 1 field
+  const double* __restrict__ geom;
+  const double* __restrict__ grad;
+  const double* __restrict__ mu;      // mu, mu_t, F1
+  double* __restrict__ red;           // per-CTA partials [(nv+1) * n_cta]
+  int* err;
+  int mode, first_stage, want_norms, have_store, use_store_sum, kchunk;
+  double TF, SF;
+};
+
+// Values a cell contributes to its two faces along one direction, all variables.  `pos` is the cell's index along the
+// direction; the first / last interior cell next to a physical boundary is re-done with the boundary formula when
+// ppm_flag is set (boundary_state_reconstruction.f90:93-123).
+template <int NV, int INTERP>
+__device__ __forceinline__ void line_cell_values(const Params& P, const double* __restrict__ q, const double* __restrict__ vol,
+                                                 long long c, long long s, int pos, int mx, int dir, double (&to_hi)[NV], double (&to_lo)[NV]) {
+  const bool redo = (INTERP != F3D_INTERP_NONE) && P.ppm_flag && ((pos == 1 && P.phys[2 * dir]) || (pos == mx - 1 && P.phys[2 * dir + 1]));
+  double vl[7];
+  if (INTERP == F3D_WENO_NM) {
+#pragma unroll
+    for (int m = 1; m <= 5; ++m) vl[m] = vol[c + (m - 3) * s];
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const double* __restrict__ qv = q + (long long)v * P.L.fs;
+    const int lim = (v >= 5) ? P.tlimiter[dir] : P.limiter[dir];
+    if (redo) {
+      boundary_cell_face_values(qv[c - s], qv[c], qv[c + s], lim, to_hi[v], to_lo[v]);
+    } else {
+      double ql[7];
+      if (INTERP == F3D_INTERP_NONE) { ql[3] = qv[c]; }
+      else if (INTERP == F3D_MUSCL) { ql[2] = qv[c - s]; ql[3] = qv[c]; ql[4] = qv[c + s]; }
+      else {
+#pragma unroll
+        for (int m = 1; m <= 5; ++m) ql[m] = qv[c + (m - 3) * s];
+      }
+      cell_face_values<INTERP>(ql, vl, lim, to_hi[v], to_lo[v]);
+    }
+  }
+}
+
+
+// Koren-limited kappa = 1/3 MUSCL values of variables [V0, V1) of one cell (muscl.f90:161-196), branch-free inside the
+// variable loop so that the V1-V0 independent dependency chains interleave (a DFMA has 8.4 cycles of latency and the
+// pipe takes one every 2.1: profiles/r01_fp64_ops_microbench.txt)
+template <int NV, int V0, int V1>
+__device__ __forceinline__ void muscl_group(const double (&qm)[NV], const double (&q0)[NV], const double (&qp)[NV], int lim, double (&to_hi)[NV],
+                                            double (&to_lo)[NV]) {
+  const double kappa = 1. / 3.;
+  if (lim == 0) {   // psi = 1 - (1 - psi)*0 = 1 exactly
+#pragma unroll
+    for (int v = V0; v < V1; ++v) {
+      const double fd = qp[v] - q0[v], bd = q0[v] - qm[v];
+      to_hi[v] = q0[v] + 0.25 * (((1. - kappa) * bd) + ((1. + kappa) * fd));
+      to_lo[v] = q0[v] - 0.25 * (((1. + kappa) * bd) + ((1. - kappa) * fd));
+    }
+  } else {
+#pragma unroll
+    for (int v = V0; v < V1; ++v) {
+      const double fd = qp[v] - q0[v], bd = q0[v] - qm[v];
+      double r = fd * rcp64(bd + copysign(1e-14, bd));
+      double psi1 = dmax(0., dmin(dmin(2 * r, (2. / 3.) * (r - 1.0) + 1.0), 2.));
+      r = bd * rcp64(fd + copysign(1e-14, fd));
+      double psi2 = dmax(0., dmin(dmin(2 * r, (2. / 3.) * (r - 1.0) + 1.0), 2.));
+      psi1 = (1 - (1 - psi1) * lim);
+      psi2 = (1 - (1 - psi2) * lim);
+      to_hi[v] = q0[v] + 0.25 * (((1. - kappa) * psi1 * bd) + ((1. + kappa) * psi2 * fd));
+      to_lo[v] = q0[v] - 0.25 * (((1. + kappa) * psi1 * bd) + ((1. - kappa) * psi2 * fd));
+    }
+  }
+}
+
+// MUSCL / first-order values of one cell along one direction from three staged values per variable
+// (muscl.f90:161-196; boundary_state_reconstruction.f90:93-123 for the first / last interior cell when ppm_flag is set)
+template <int NV, int INTERP>
+__device__ __forceinline__ void recon3(const Params& P, const double (&qm)[NV], const double (&q0)[NV], const double (&qp)[NV], int pos, int mx,
+                                       int dir, double (&to_hi)[NV], double (&to_lo)[NV]) {
+  const bool redo = (INTERP != F3D_INTERP_NONE) && P.ppm_flag && ((pos == 1 && P.phys[2 * dir]) || (pos == mx - 1 && P.phys[2 * dir + 1]));
+  if (redo) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) boundary_cell_face_values(qm[v], q0[v], qp[v], (v >= 5) ? P.tlimiter[dir] : P.limiter[dir], to_hi[v], to_lo[v]);
+  } else if (INTERP == F3D_INTERP_NONE) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) { to_hi[v] = q0[v]; to_lo[v] = q0[v]; }
+  } else {
+    const int lim = P.limiter[dir], tlim = P.tlimiter[dir];
+    if (NV > 5 && tlim == lim) {
+      muscl_group<NV, 0, NV>(qm, q0, qp, lim, to_hi, to_lo);
+    } else {
+      muscl_group<NV, 0, 5>(qm, q0, qp, lim, to_hi, to_lo);
+      if (NV > 5) muscl_group<NV, 5, NV>(qm, q0, qp, tlim, to_hi, to_lo);
+    }
+  }
+}
+
+// F <- (F - laminar) - sst for the face between cells lo and hi (viscous.f90:209-323, 378-446); also the face terms
+// A*mu/(rho*|dr.n|), A*mu_t/(rho*|dr.n|) of the viscous / turbulent time-step corrections (time.f90:396-421, 479-504:
+// both cells that share a face use the mu and density of the cell on its high side).  ql/qh: staged q of the two cells
+// (field stride PSQ), rl/rh: their staged records (field stride PS).
+template <int NV, int PS, int PSQ>
+__device__ __forceinline__ void viscous_face(const Params& P, const double* __restrict__ ql_, const double* __restrict__ qh_,
+                                             const double* __restrict__ rl, const double* __restrict__ rh, double A, double nx, double ny,
+                                             double nz, bool sst_on, bool need_dt, double (&F)[NV], double& vis, double& tur) {
+  using R = RecF<NV, true>;
+  constexpr bool SST = (NV == 7);
+  constexpr int NG = R::NG;
+  const double dx = rh[(R::OFF_C + 0) * PS] - rl[(R::OFF_C + 0) * PS], dy = rh[(R::OFF_C + 1) * PS] - rl[(R::OFF_C + 1) * PS],
+               dz = rh[(R::OFF_C + 2) * PS] - rl[(R::OFF_C + 2) * PS];
+  const double inv_d = rsqrt64(dx * dx + dy * dy + dz * dz);   // 1 / d_LR
+  const double ex = dx * inv_d, ey = dy * inv_d, ez = dz * inv_d;
+  double ql[NV], qh[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) { ql[v] = ql_[v * PSQ]; qh[v] = qh_[v * PSQ]; }
+  double del[NG];
+  del[0] = qh[1] - ql[1]; del[1] = qh[2] - ql[2]; del[2] = qh[3] - ql[3];
+  {
+    const double T_LE = ql[4] * rcp64(ql[0] * P.R_gas), T_RE = qh[4] * rcp64(qh[0] * P.R_gas);
+    del[3] = T_RE - T_LE;
+  }
+  if (SST) { del[4] = qh[5] - ql[5]; del[5] = qh[6] - ql[6]; }
+  double G[NG][3];
+#pragma unroll
+  for (int c = 0; c < NG; ++c) {
+    const double ax = 0.5 * (rl[(3 * c) * PS] + rh[(3 * c) * PS]), ay = 0.5 * (rl[(3 * c + 1) * PS] + rh[(3 * c + 1) * PS]),
+                 az = 0.5 * (rl[(3 * c + 2) * PS] + rh[(3 * c + 2) * PS]);
+    const double nc = (del[c] - (ax * dx + ay * dy + az * dz)) * inv_d;
+    G[c][0] = ax + (nc * ex);
+    G[c][1] = ay + (nc * ey);
+    G[c][2] = az + (nc * ez);
+  }
+  const double mu_hi = rh[R::OFF_MU * PS];
+  const double mu_f = 0.5 * (rl[R::OFF_MU * PS] + mu_hi);
+  const double mut_hi = SST ? rh[(R::OFF_MU + 1) * PS] : 0.0;
+  const double mut_f = SST ? 0.5 * (rl[(R::OFF_MU + 1) * PS] + mut_hi) : 0.0;
+  const double tmu = mu_f + mut_f;
+  const double div3 = (G[0][0] + G[1][1] + G[2][2]) * (1. / 3.);
+  const double Txx = 2. * tmu * (G[0][0] - div3), Tyy = 2. * tmu * (G[1][1] - div3), Tzz = 2. * tmu * (G[2][2] - div3);
+  const double Txy = tmu * (G[1][0] + G[0][1]), Txz = tmu * (G[2][0] + G[0][2]), Tyz = tmu * (G[2][1] + G[1][2]);
+  const double Kh = (mu_f * P.inv_Pr + mut_f * P.inv_tPr) * P.gm * P.R_gas * P.inv_gm1;
+  const double Qx = Kh * G[3][0], Qy = Kh * G[3][1], Qz = Kh * G[3][2];
+  const double uf = 0.5 * (ql[1] + qh[1]), vf = 0.5 * (ql[2] + qh[2]), wf = 0.5 * (ql[3] + qh[3]);
+  F[1] = F[1] - ((Txx * nx + Txy * ny + Txz * nz) * A);
+  F[2] = F[2] - ((Txy * nx + Tyy * ny + Tyz * nz) * A);
+  F[3] = F[3] - ((Txz * nx + Tyz * ny + Tzz * nz) * A);
+  F[4] = F[4] - (A * (((Txx * uf + Txy * vf + Txz * wf + Qx) * nx) + ((Txy * uf + Tyy * vf + Tyz * wf + Qy) * ny) +
+                      ((Txz * uf + Tyz * vf + Tzz * wf + Qz) * nz)));
+  if (SST && sst_on) {
+    const double F1 = 0.5 * (rl[(R::OFF_MU + 2) * PS] + rh[(R::OFF_MU + 2) * PS]);
+    const double sk = kSigmaK1 * F1 + kSigmaK2 * (1.0 - F1);
+    const double sw = kSigmaW1 * F1 + kSigmaW2 * (1.0 - F1);
+    const double rhof = 0.5 * (ql[0] + qh[0]);
+    const double tkf = 0.5 * (ql[NV - 2] + qh[NV - 2]);
+    const double Tk = -2.0 * rhof * tkf * (1. / 3.);
+    const double dk = (A * ((mu_f + sk * mut_f) * (G[NG - 2][0] * nx + G[NG - 2][1] * ny + G[NG - 2][2] * nz)));
+    const double dw = (A * ((mu_f + sw * mut_f) * (G[NG - 1][0] * nx + G[NG - 1][1] * ny + G[NG - 1][2] * nz)));
+    F[1] = F[1] - (Tk * nx * A);
+    F[2] = F[2] - (Tk * ny * A);
+    F[3] = F[3] - (Tk * nz * A);
+    F[4] = F[4] - dk;
+    F[NV - 2] = F[NV - 2] - dk;
+    F[NV - 1] = F[NV - 1] - dw;
+  }
+  if (need_dt) {
+    const double dn = fabs(((-dx) * nx) + ((-dy) * ny) + ((-dz) * nz));
+    const double w = A * rcp64(qh[0] * dn);
+    vis = w * mu_hi;
+    if (SST) tur = w * mut_hi;
+  }
+}
+
+// One face: boundary overrides of the states (boundary_state_reconstruction.f90:124-131), inviscid flux times area
+// (scheme.f90:68-109), viscous flux, and the face terms of the time step.  ql/qh, rl/rh: staged q / record of the cells on
+// the low / high side; A, n = metrics of the face; f = the face index along direction d, m = node count along d.
+template <int NV, int SCHEME, bool VISC, int PS, int PSQ>
+__device__ __forceinline__ void face_eval(const Params& P, int d, const double* __restrict__ ql, const double* __restrict__ qh,
+                                          const double* __restrict__ rl, const double* __restrict__ rh, double A, double nx, double ny,
+                                          double nz, int f, int m, double (&L)[NV], double (&R)[NV], bool flux_on, bool need_dt,
+                                          double (&F)[NV], double& lam, double& vis, double& tur) {
+  if (P.interpolant != F3D_INTERP_NONE) {
+    if (f == 1 && P.phys[2 * d]) {
+      const bool far = P.farlike[2 * d] != 0;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const double g = ql[v * PSQ], in = qh[v * PSQ];
+        if (far) { L[v] = g; R[v] = g; } else { L[v] = 0.5 * (g + in); }
+      }
+    }
+    if (f == m && P.phys[2 * d + 1]) {
+      const bool far = P.farlike[2 * d + 1] != 0;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const double in = ql[v * PSQ], g = qh[v * PSQ];
+        if (far) { L[v] = g; R[v] = g; } else { R[v] = 0.5 * (in + g); }
+      }
+    }
+  }
+  const double mask = (f == 1) ? P.zlo[d] : ((f == m) ? P.zhi[d] : 1.0);
+  const double cbar = inviscid_flux<NV>(SCHEME >= 0 ? SCHEME : P.scheme, P.gm, P.MInf, L, R, A, nx, ny, nz, mask, flux_on, need_dt, F);
+  if (need_dt) {   // time.f90:159-237: both cells of a face use the velocity of the cell on its high side
+    const double vn = fabs((qh[1 * PSQ] * nx) + (qh[2 * PSQ] * ny) + (qh[3 * PSQ] * nz));
+    lam = A * (vn + cbar);
+  }
+  if (VISC) viscous_face<NV, PS, PSQ>(P, ql, qh, rl, rh, A, nx, ny, nz, (NV == 7) && flux_on, need_dt, F, vis, tur);
+}
+
+}  // namespace f3d

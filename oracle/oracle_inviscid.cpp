@@ -214,6 +214,7 @@ static void temp_based_density(Block& B, int face) {
 
 // bc_primitive.f90:645-1234  far_field (Riemann invariants).  The whole-face copy3/fix calls made
 // from inside the per-cell loop (:700-757) are re-stated literally, including the flag logic.
+static void ghost_plane_copy(Block& B, int face);
 static void far_field(Block& B, int face) {
   Frame f = make_frame(B, face);
   const OracleConfig& c = B.c;
@@ -261,7 +262,11 @@ static void far_field(Block& B, int face) {
         already_fixed = 1;
       }
     }
-  // qp(-1,:,:,:) = qp(0,:,:,:) ; qp(-2,:,:,:) = qp(0,:,:,:)  -- whole planes incl. ghost rows (:762-763)
+  ghost_plane_copy(B, face);
+}
+
+// qp(-1,:,:,:) = qp(0,:,:,:) ; qp(-2,:,:,:) = qp(0,:,:,:)  -- whole planes incl. ghost rows (:762-763, :1344-1345)
+static void ghost_plane_copy(Block& B, int face) {
   int lo[3] = {-2, -2, -2}, hi[3] = {B.imx + 2, B.jmx + 2, B.kmx + 2};
   int ax = (face - 1) / 2, t1 = (ax + 1) % 3, t2 = (ax + 2) % 3;
   int g0 = (face % 2 == 1) ? 0 : hi[ax] - 2;          // first ghost index along ax
@@ -276,6 +281,55 @@ static void far_field(Block& B, int face) {
           B.qp(idx[0], idx[1], idx[2], l) = B.qp(src[0], src[1], src[2], l);
         }
     }
+}
+
+// bc_primitive.f90:1237-1776  total_pressure (id -11): far-field Riemann velocity, then p from the fixed total
+// pressure at the boundary Mach number and rho = gm*p/Cb^2.  Mb is taken from the ghost velocity on every face except
+// kmin, which reads the INTERIOR cell (:1678 "x_speed(i,j,k)" instead of "(i,j,k-1)") -- reproduced.  The whole-face
+// copy3 / fix calls sit inside the per-cell loop without the far-field's already_fixed flag (:1286-1336).
+static void total_pressure(Block& B, int face) {
+  Frame f = make_frame(B, face);
+  const OracleConfig& c = B.c;
+  const Rec4& Fd = (face <= 2) ? B.If : (face <= 4 ? B.Jf : B.Kf);
+  const double sgn = (face % 2 == 1) ? -1.0 : 1.0;  // outward normal = -n on min faces
+  for (int b = 1; b <= f.nb; ++b)
+    for (int a = 1; a <= f.na; ++a) {
+      int i, j, k, ig, jg, kg, fi, fj, fk;
+      f.interior(1, a, b, i, j, k);
+      f.ghost(1, a, b, ig, jg, kg);
+      if (face % 2 == 1) { fi = i; fj = j; fk = k; } else { fi = ig; fj = jg; fk = kg; }
+      double nx = sgn * Fd.nx(fi, fj, fk), ny = sgn * Fd.ny(fi, fj, fk), nz = sgn * Fd.nz(fi, fj, fk);
+      double u = B.qp(i, j, k, 2), v = B.qp(i, j, k, 3), w = B.qp(i, j, k, 4);
+      double uf = c.x_speed_inf, vf = c.y_speed_inf, wf = c.z_speed_inf;
+      double cexp = std::sqrt(c.gm * B.qp(i, j, k, 5) / B.qp(i, j, k, 1));
+      double cinf = std::sqrt(c.gm * c.pressure_inf / c.density_inf);
+      double Unexp = u * nx + v * ny + w * nz;
+      double Uninf = uf * nx + vf * ny + wf * nz;
+      double Rinf = Uninf - 2 * cinf / (c.gm - 1.);
+      double Rexp = Unexp + 2 * cexp / (c.gm - 1.);
+      double Unb = 0.5 * (Rexp + Rinf);
+      double Cb = 0.25 * (c.gm - 1.) * (Rexp - Rinf);
+      if (Unb > 0.) {
+        double vel_diff = Unb - Unexp;
+        B.qp(ig, jg, kg, 2) = B.qp(i, j, k, 2) + vel_diff * nx;
+        B.qp(ig, jg, kg, 3) = B.qp(i, j, k, 3) + vel_diff * ny;
+        B.qp(ig, jg, kg, 4) = B.qp(i, j, k, 4) + vel_diff * nz;
+        if (is_sst(B)) { copy3(B, 6, FLAT, face); copy3(B, 7, FLAT, face); }
+      } else {
+        double vel_diff = Unb - Uninf;
+        B.qp(ig, jg, kg, 2) = c.x_speed_inf + vel_diff * nx;
+        B.qp(ig, jg, kg, 3) = c.y_speed_inf + vel_diff * ny;
+        B.qp(ig, jg, kg, 4) = c.z_speed_inf + vel_diff * nz;
+        if (is_sst(B)) { fix(B, 6, ORC_FIX_TK, face); fix(B, 7, ORC_FIX_TW, face); }
+      }
+      int im = ig, jm = jg, km = kg;
+      if (face == 5) { im = i; jm = j; km = k; }
+      double Mb = std::sqrt(B.qp(im, jm, km, 2) * B.qp(im, jm, km, 2) + B.qp(im, jm, km, 3) * B.qp(im, jm, km, 3) +
+                            B.qp(im, jm, km, 4) * B.qp(im, jm, km, 4)) / Cb;
+      B.qp(ig, jg, kg, 5) = c.fixed[ORC_FIX_TPRESSURE][face - 1] / std::pow((1 + 0.5 * (c.gm - 1.) * Mb * Mb), c.gm / (c.gm - 1.));
+      B.qp(ig, jg, kg, 1) = c.gm * B.qp(ig, jg, kg, 5) / (Cb * Cb);
+    }
+  ghost_plane_copy(B, face);
 }
 
 // bc_primitive.f90:1948-1978 periodic_bc (single-block periodicity, id -9): whole slabs
@@ -348,6 +402,7 @@ void Block::populate_ghost_primitive() {
         break;
       case -8: far_field(B, face); break;
       case -9: periodic_bc(B, face); break;
+      case -11: total_pressure(B, face); break;
       default: break;  // interface (>=0) or -10
     }
   }
