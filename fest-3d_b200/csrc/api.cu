@@ -66,7 +66,6 @@ extern "C" int fest3d_gpu_create(Fest3dGpuCtx** out, const Fest3dGpuConfig* cfg,
   if (cfg->scheme < 0 || cfg->scheme > F3D_SLAU || cfg->interpolant < 0 || cfg->interpolant > F3D_WENO_NM) return F3D_ERR_ARGUMENT;
   if (cfg->n_var != (sst ? 7 : 5)) return F3D_ERR_ARGUMENT;
   if (sst && cfg->mu_ref == 0.0) return F3D_ERR_UNSUPPORTED;
-  for (int f = 0; f < 6; ++f) if (cfg->bc_id[f] == -11) return F3D_ERR_UNSUPPORTED;   // total_pressure: next round
   if (cfg->imx < 2 || cfg->jmx < 2 || cfg->kmx < 2) return F3D_ERR_ARGUMENT;
 
   Fest3dGpuCtx* ctx = new Fest3dGpuCtx();

@@ -202,11 +202,37 @@ __global__ void k_bc_face(const Params P, double* __restrict__ q, const double* 
       }
       break;
     }
+    case -11: {  // total_pressure (bc_primitive.f90:1237-1776): far-field Riemann velocity, p from the fixed total pressure
+      const double* gn = geom + (long long)(G_IA + 4 * ax) * fs;
+      double Unb, Cb, Unexp, Uninf, nx, ny, nz;
+      far_field_state(P, q, gn, fr, o, Unb, Cb, Unexp, Uninf, nx, ny, nz);
+      const long long c = INT_(1), g = GHO_(1);
+      if (Unb > 0.) {
+        const double vd = Unb - Unexp;
+        u[g] = u[c] + vd * nx; v[g] = v[c] + vd * ny; w[g] = w[c] + vd * nz;
+      } else {
+        const double vd = Unb - Uninf;
+        u[g] = P.x_speed_inf + vd * nx; v[g] = P.y_speed_inf + vd * ny; w[g] = P.z_speed_inf + vd * nz;
+      }
+      const long long m = (face == 5) ? c : g;   // kmin takes Mb from the interior cell (:1678), the other faces from the ghost
+      const double Mb = sqrt(u[m] * u[m] + v[m] * v[m] + w[m] * w[m]) / Cb;
+      p[g] = fx[F3D_FIX_TPRESSURE][fi] / pow((1 + 0.5 * (P.gm - 1.) * Mb * Mb), P.gm / (P.gm - 1.));
+      rho[g] = P.gm * p[g] / (Cb * Cb);
+      if (sst) {   // whole-face copy3("flat") / fix() from inside the per-cell loop: the LAST cell of the loop decides
+        const long long olast = (long long)(fr.na - 1) * fr.sa + (long long)(fr.nb - 1) * fr.sb;
+        double Ub2, Cb2, a2, b2, x2, y2, z2;
+        far_field_state(P, q, gn, fr, olast, Ub2, Cb2, a2, b2, x2, y2, z2);
+        if (Ub2 > 0.) { copy3_flat(tk, fr, o); copy3_flat(tw, fr, o); }
+        else { fix3(tk, fr, o, fx[F3D_FIX_TK][fi]); fix3(tw, fr, o, fx[F3D_FIX_TW][fi]); }
+      }
+      break;
+    }
     default: break;   // interface (>= 0), -10 (multi-block periodic), -9 handled by the slab kernel
   }
 }
 
-// far_field: qp(-1,:,:,:) = qp(0,:,:,:); qp(-2,:,:,:) = qp(0,:,:,:) over the WHOLE plane incl. ghost rows (:762-763)
+// far_field / total_pressure: qp(-1,:,:,:) = qp(0,:,:,:); qp(-2,:,:,:) = qp(0,:,:,:) over the WHOLE plane incl. ghost rows
+// (:762-763, :1344-1345)
 __global__ void k_plane_copy(const Params P, double* __restrict__ q, int face) {
   const Layout& L = P.L;
   const int ax = (face - 1) / 2;
@@ -294,7 +320,7 @@ int launch_bc(Ctx* ctx) {
   bool ordered = false;
   for (int face = 1; face <= 6; ++face) {
     const int id = ctx->P.bc_id[face - 1];
-    if (id == -8 || id == -9) ordered = true;
+    if (id == -8 || id == -9 || id == -11) ordered = true;
   }
   // a fill reads interior layers 1..4 along its normal: with fewer than 4 cells there (quasi-2-D blocks, kmx == 2) those are the
   // ghost cells of the opposite face, so the reference order (low face first, then the high face reading its fresh ghosts) matters
@@ -326,7 +352,7 @@ int launch_bc(Ctx* ctx) {
     dim3 grid((mx[a_ax] - 1 + 31) / 32, (mx[b_ax] - 1 + 3) / 4);
     k_bc_face<<<grid, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->geom, face);
     ctx->launches++;
-    if (id == -8) {
+    if (id == -8 || id == -11) {
       dim3 g2((mx[a_ax] + 5 + 31) / 32, (mx[b_ax] + 5 + 3) / 4);
       k_plane_copy<<<g2, block, 0, ctx->stream>>>(ctx->P, ctx->qp, face);
       ctx->launches++;

@@ -83,15 +83,26 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a)
 
   if (wid >= 2 * TY && wid < 3 * TY) {
     // =============================================== K rows: the cells ===============================================
-    const int tx = lane, ty = wid - 2 * TY;
-    int i = i0 + tx, j = j0 + ty;
-    const bool own = (i <= Ly.imx - 1) && (j <= Ly.jmx - 1);
-    const bool stg = (i <= Ly.imx + 1) && (j <= Ly.jmx + 1);   // ghost cells next to the last faces feed the i/j faces there
-    if (i > Ly.imx + 1) i = Ly.imx + 1;
-    if (j > Ly.jmx + 1) j = Ly.jmx + 1;
-    const int s0 = (ty + 1) * PW + tx + 1;
-    double* const priv = smem + S::OFF_PRIV + ty * TX + tx;
-    const int sl0 = ty * (TX + 1) + tx, sh0 = sl0 + 1, sl1 = SLOT_I + ty * TX + tx, sh1 = sl1 + TX;
+    // The few values that define this thread's role are re-derived from the thread index at the top of every plane (the
+    // empty asm keeps the compiler from hoisting them out of the loop): generation-3 bring-up spilled them to local memory
+    // and 27 % of all stall samples were waits on those reloads (profiles/r01_g3_summary.md).
+    int tx, ty, i, j, s0, sl0, sh0, sl1, sh1;
+    bool own, stg;
+    double* priv;
+    auto role = [&]() {
+      int t_ = tid;
+      asm volatile("" : "+r"(t_));
+      tx = t_ & 31; ty = (t_ >> 5) - 2 * TY;
+      i = i0 + tx; j = j0 + ty;
+      own = (i <= Ly.imx - 1) && (j <= Ly.jmx - 1);
+      stg = (i <= Ly.imx + 1) && (j <= Ly.jmx + 1);   // ghost cells next to the last faces feed the i/j faces there
+      if (i > Ly.imx + 1) i = Ly.imx + 1;
+      if (j > Ly.jmx + 1) j = Ly.jmx + 1;
+      s0 = (ty + 1) * PW + tx + 1;
+      priv = smem + S::OFF_PRIV + ty * TX + tx;
+      sl0 = ty * (TX + 1) + tx; sh0 = sl0 + 1; sl1 = SLOT_I + ty * TX + tx; sh1 = sl1 + TX;
+    };
+    role();
 
     auto stage_own = [&](int kk) {   // record of this thread's cell at plane kk -> ring buffer kk & 1
       if (!stg) return;
@@ -118,6 +129,7 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a)
 
     for (int k = kb - 1; k <= ke; ++k) {
       bar_all();   // plane k is staged; the i/j fluxes of plane k-1 are in exchange half (k-1) & 1
+      role();
       const int kc = k - 1;                                   // plane of the cell work
       const bool cell_on = own && kc >= kb;
       const bool more = k <= ke - 1;                          // a k face above plane k is still to be evaluated
@@ -352,51 +364,57 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a)
   } else {
     // ===================================== I rows, J rows and the three halo warps =====================================
     int i, j, s0, d;
-    bool rec, fac, stg = false, wr_hi = true;
+    bool rec, fac, stg, wr_hi;
     int om, op;                       // staged-slot offsets of the two neighbours along d
     int exw, exr;                     // exchange slots: where the hi value goes; where L is read and the flux written
-    long long outer_off = 0;          // halo threads: global offset of the outer neighbour they stage, and its slot
-    int outer_slot = 0;
-    if (wid < TY) {                   // I row
-      const int tx = lane, ty = wid;
-      d = 0; i = i0 + tx; j = j0 + ty;
-      rec = fac = (j <= Ly.jmx - 1) && (i <= Ly.imx);
-      s0 = (ty + 1) * PW + tx + 1; om = -1; op = 1;
-      exw = ty * (TX + 1) + tx + 1; exr = ty * (TX + 1) + tx;
-    } else if (wid < 2 * TY) {        // J row
-      const int tx = lane, ty = wid - TY;
-      d = 1; i = i0 + tx; j = j0 + ty;
-      rec = fac = (i <= Ly.imx - 1) && (j <= Ly.jmx);
-      s0 = (ty + 1) * PW + tx + 1; om = -PW; op = PW;
-      exw = SLOT_I + (ty + 1) * TX + tx; exr = SLOT_I + ty * TX + tx;
-    } else if (wid == W_IH) {         // the two i columns next to the tile: lanes 0..TY-1 low side, TY..2TY-1 high side
-      const int r = lane % TY, side = lane / TY;
-      d = 0; i = (side == 0) ? i0 - 1 : i0 + TX; j = j0 + r;
-      rec = (side < 2) && (j <= Ly.jmx - 1) && (i <= Ly.imx);
-      stg = (side < 2) && (j <= Ly.jmx + 1) && (i <= Ly.imx + 1);
-      fac = rec && side == 1; wr_hi = side == 0;
-      s0 = (r + 1) * PW + (side == 0 ? 0 : TX + 1);
-      outer_slot = PS + (side & 1) * TY + r;
-      outer_off = (side == 0) ? -1 : 1;
-      om = (side == 0) ? outer_slot - s0 : -1; op = (side == 0) ? 1 : outer_slot - s0;
-      exw = r * (TX + 1) + (side == 0 ? 0 : TX); exr = r * (TX + 1) + TX;
-    } else {                          // high (W_JH) and low (W_JL) j rows next to the tile
-      const bool high = wid == W_JH;
-      d = 1; i = i0 + lane; j = high ? j0 + TY : j0 - 1;
-      rec = (i <= Ly.imx - 1) && (j <= Ly.jmx);
-      stg = (i <= Ly.imx + 1) && (j <= Ly.jmx + 1);
-      fac = rec && high; wr_hi = !high;
-      s0 = (high ? TY + 1 : 0) * PW + lane + 1;
-      outer_slot = PS + 2 * TY + (high ? TX : 0) + lane;
-      outer_off = high ? Ly.sj : -Ly.sj;
-      om = high ? -PW : outer_slot - s0; op = high ? outer_slot - s0 : PW;
-      exw = SLOT_I + (high ? TY * TX : 0) + lane; exr = SLOT_I + TY * TX + lane;
-    }
-    if (i > Ly.imx + 1) i = Ly.imx + 1;
-    if (j > Ly.jmx + 1) j = Ly.jmx + 1;
-    const int pos = (d == 0) ? i : j, mx = (d == 0) ? Ly.imx : Ly.jmx;
-    const int nb = (d == 0) ? 1 : PW;
-    const int bar_id = 1 + d, bar_n = (d == 0) ? N_IGRP : N_JGRP;
+    int outer_off;                    // halo threads: global offset of the outer neighbour they stage, and its slot
+    int outer_slot;
+    int pos, mx, nb;
+    auto role = [&]() {               // re-derived every plane, see the K rows above
+      int t_ = tid;
+      asm volatile("" : "+r"(t_));
+      const int ln = t_ & 31, w = t_ >> 5;
+      stg = false; wr_hi = true; outer_off = 0; outer_slot = 0;
+      if (w < TY) {                   // I row
+        const int tx = ln, ty = w;
+        d = 0; i = i0 + tx; j = j0 + ty;
+        rec = fac = (j <= Ly.jmx - 1) && (i <= Ly.imx);
+        s0 = (ty + 1) * PW + tx + 1; om = -1; op = 1;
+        exw = ty * (TX + 1) + tx + 1; exr = ty * (TX + 1) + tx;
+      } else if (w < 2 * TY) {        // J row
+        const int tx = ln, ty = w - TY;
+        d = 1; i = i0 + tx; j = j0 + ty;
+        rec = fac = (i <= Ly.imx - 1) && (j <= Ly.jmx);
+        s0 = (ty + 1) * PW + tx + 1; om = -PW; op = PW;
+        exw = SLOT_I + (ty + 1) * TX + tx; exr = SLOT_I + ty * TX + tx;
+      } else if (w == W_IH) {         // the two i columns next to the tile: lanes 0..TY-1 low side, TY..2TY-1 high side
+        const int r = ln % TY, side = ln / TY;
+        d = 0; i = (side == 0) ? i0 - 1 : i0 + TX; j = j0 + r;
+        rec = (side < 2) && (j <= Ly.jmx - 1) && (i <= Ly.imx);
+        stg = (side < 2) && (j <= Ly.jmx + 1) && (i <= Ly.imx + 1);
+        fac = rec && side == 1; wr_hi = side == 0;
+        s0 = (r + 1) * PW + (side == 0 ? 0 : TX + 1);
+        outer_slot = PS + (side & 1) * TY + r;
+        outer_off = (side == 0) ? -1 : 1;
+        om = (side == 0) ? outer_slot - s0 : -1; op = (side == 0) ? 1 : outer_slot - s0;
+        exw = r * (TX + 1) + (side == 0 ? 0 : TX); exr = r * (TX + 1) + TX;
+      } else {                        // high (W_JH) and low (W_JL) j rows next to the tile
+        const bool high = w == W_JH;
+        d = 1; i = i0 + ln; j = high ? j0 + TY : j0 - 1;
+        rec = (i <= Ly.imx - 1) && (j <= Ly.jmx);
+        stg = (i <= Ly.imx + 1) && (j <= Ly.jmx + 1);
+        fac = rec && high; wr_hi = !high;
+        s0 = (high ? TY + 1 : 0) * PW + ln + 1;
+        outer_slot = PS + 2 * TY + (high ? TX : 0) + ln;
+        outer_off = high ? (int)Ly.sj : -(int)Ly.sj;
+        om = high ? -PW : outer_slot - s0; op = high ? outer_slot - s0 : PW;
+        exw = SLOT_I + (high ? TY * TX : 0) + ln; exr = SLOT_I + TY * TX + ln;
+      }
+      if (i > Ly.imx + 1) i = Ly.imx + 1;
+      if (j > Ly.jmx + 1) j = Ly.jmx + 1;
+      pos = (d == 0) ? i : j; mx = (d == 0) ? Ly.imx : Ly.jmx;
+      nb = (d == 0) ? 1 : PW;
+    };
 
     auto stage_ring = [&](int kk) {   // halo threads: their ring cell (+ the outer neighbour's q) of plane kk
       if (!stg) return;
@@ -421,6 +439,7 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a)
 
     for (int k = kb - 1; k <= ke; ++k) {
       bar_all();
+      role();
       if (k + 1 <= ke - 1) stage_ring(k + 1);
       if (k >= kb && k <= ke - 1) {
         const long long c = Ly.idx(i, j, k);
@@ -449,7 +468,7 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a)
             for (int v = 0; v < NV; ++v) xH[v * EX + exw] = hi[v];
           }
         }
-        bar_group(bar_id, bar_n);
+        bar_group(1 + d, (d == 0) ? N_IGRP : N_JGRP);
         if (fac) {
           double L[NV], F[NV], lam = 0.0, vis = 0.0, tur = 0.0;
 #pragma unroll

@@ -168,7 +168,8 @@ def test_global_time_step_and_weno_history(pkg, case_mod, oracle):
 
 # ---- edge cases: one-cell-thick k (kmx = 2), tiny blocks, every physical BC id, higher-order BC, periodic --------------
 @pytest.mark.parametrize("bc", [[-1, -2, -6, -6, -6, -6], [-3, -4, -5, -6, -6, -6], [-8, -8, -8, -8, -6, -6],
-                                [-9, -9, -5, -5, -6, -6], [-8, -4, -7, -6, -9, -9], [-3, -4, -5, -5, -5, -5]])
+                                [-9, -9, -5, -5, -6, -6], [-8, -4, -7, -6, -9, -9], [-3, -4, -5, -5, -5, -5],
+                                [-11, -4, -5, -6, -6, -6], [-11, -11, -6, -6, -11, -11]])
 @pytest.mark.parametrize("shape", [(6, 5, 1), (4, 3, 3), (9, 7, 5)])
 @pytest.mark.parametrize("accur", [0, 1])
 def test_boundary_conditions(pkg, case_mod, oracle, bc, shape, accur):
@@ -183,6 +184,9 @@ def test_boundary_conditions(pkg, case_mod, oracle, bc, shape, accur):
     blk.bc_id = list(bc)
     blk.scheme.accur = accur
     blk.fixed[7, 2] = 350.0   # isothermal wall at jmin, adiabatic elsewhere
+    fl = blk.flow                # total-pressure faces (-11): isentropic total pressure of the free stream, a little off per face
+    M2 = fl.x_speed_inf ** 2 / (fl.gm * fl.pressure_inf / fl.density_inf)
+    blk.fixed[8, :] = fl.pressure_inf * (1 + 0.5 * (fl.gm - 1.0) * M2) ** (fl.gm / (fl.gm - 1.0)) * (1.0 + 1e-3 * np.arange(6))
     blk.build_geometry()      # pole faces change the metrics
     s = _solver(pkg, blocks)
     _check_residual(oracle, s, blocks)

@@ -149,3 +149,28 @@ def test_bc_mask_kat(oracle, case_mod):
     err, _ = w.residual(1)
     G = w.aux(0, 21, (5, blk.kmx - 1, blk.jmx, blk.imx - 1))
     assert np.all(G[0, :, 0, :] == 0.0) and np.all(G[0, :, 1, :] != 0.0)
+
+
+def test_total_pressure_bc_free_stream(oracle, case_mod):
+    """BC -11 (bc_primitive.f90:1237-1776) has no known answer in the reference's tests; analytic one instead: with the
+    exact free stream inside, a planar inlet normal to it and the isentropic total pressure of the free stream fixed on the
+    face, the Riemann state is the free stream itself (Unb = -u_inf, Cb = c_inf, Mb = M_inf), so the ghost cells of the
+    face must reproduce it."""
+    import importlib
+    syn = importlib.import_module("fest-3d_b200.synthetic")
+    blocks = syn.make_duct_blocks(None, n3=(6, 5, 4), turbulence="sst", interpolant="muscl")
+    blk = blocks[0]
+    blk.bc_id = [-11, -4, -6, -6, -6, -6]
+    blk.init_state()
+    fl = blk.flow
+    M2 = (fl.x_speed_inf ** 2) / (fl.gm * fl.pressure_inf / fl.density_inf)
+    blk.fixed[8, :] = fl.pressure_inf * (1 + 0.5 * (fl.gm - 1.0) * M2) ** (fl.gm / (fl.gm - 1.0))
+    w = oracle.OracleWorld(blocks)
+    err, _ = w.residual(1)
+    assert err == 0
+    q = w.get_state(0)
+    ref = [fl.density_inf, fl.x_speed_inf, 0.0, 0.0, fl.pressure_inf, fl.tk_inf, fl.tw_inf]
+    J, K = slice(3, 3 + blk.jmx - 1), slice(3, 3 + blk.kmx - 1)
+    for v, r in enumerate(ref):
+        g = q[v, K, J, 0:3]
+        assert np.abs(g - r).max() <= 1e-12 * max(abs(r), fl.x_speed_inf), (v, g.ravel()[:3], r)
