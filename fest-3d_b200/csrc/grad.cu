@@ -13,7 +13,7 @@
 namespace f3d {
 
 template <int NG>
-__global__ void __launch_bounds__(128) k_gradients(const Params P, const double* __restrict__ q, const double* __restrict__ temp,
+__global__ void __launch_bounds__(128, 5) k_gradients(const Params P, const double* __restrict__ q, const double* __restrict__ temp,
                                                    const double* __restrict__ geom, double* __restrict__ grad, double* __restrict__ mu3, int* err) {
   const Layout& L = P.L;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -98,13 +98,14 @@ __global__ void __launch_bounds__(128) k_gradients(const Params P, const double*
   }
 }
 
-// ghost-gradient rule + ghost mu_t/F1 on one physical face (gradients.f90:638-674, viscosity.f90:408-465)
+// ghost-gradient rule + ghost mu_t/F1 on the physical faces (gradients.f90:638-674, viscosity.f90:408-465).  One launch:
+// blockIdx.z = (face-1)*NG + gradient component, one thread per boundary cell and component (six times the threads of a
+// per-cell version, each with a sixth of the dependent loads: the i faces touch one 32-byte sector per value)
 template <int NG>
 __global__ void k_gradient_bc(const Params P, const double* __restrict__ q, const double* __restrict__ temp, const double* __restrict__ geom,
                               double* __restrict__ grad, double* __restrict__ mu3, const double* __restrict__ rec_all, const long long* rec_off,
                               int face_mask) {
-  // one launch for all physical faces (blockIdx.z = face-1): each face reads interior gradients and writes its own ghost cells
-  const int face = blockIdx.z + 1;
+  const int face = blockIdx.z / NG + 1, cc = blockIdx.z % NG;
   if (!(face_mask >> (face - 1) & 1)) return;
   const double* __restrict__ rec = rec_all + rec_off[face - 1];
   const Layout& L = P.L;
@@ -127,8 +128,7 @@ __global__ void k_gradient_bc(const Params P, const double* __restrict__ q, cons
   const double sig = lo ? 1.0 : -1.0;
   const int id = P.bc_id[face - 1];
   const double ft = P.fixed[F3D_FIX_WALL_TEMP][face - 1];
-#pragma unroll
-  for (int cc = 0; cc < NG; ++cc) {
+  {
     // slot cc holds variable cc+2 of qp(2:n_var): u,v,w,p,[k,omega]; slot 4 (cc == 3) is then overwritten with T
     const double qI = (cc == 3) ? temp[ci] : q[(long long)(cc + 1) * fs + ci];
     const double qG = (cc == 3) ? temp[cg] : q[(long long)(cc + 1) * fs + cg];
@@ -140,7 +140,7 @@ __global__ void k_gradient_bc(const Params P, const double* __restrict__ q, cons
     grad[(3 * cc + 1) * fs + cg] = gy + (gIy - dot * ny);
     grad[(3 * cc + 2) * fs + cg] = gz + (gIz - dot * nz);
   }
-  if (NG == 6) {
+  if (NG == 6 && cc == 0) {
     if (id == -5) { mu3[fs + cg] = -mu3[fs + ci]; mu3[2 * fs + cg] = mu3[2 * fs + ci]; }
     else if (id == -1 || id == -2 || id == -3 || id == -4 || id == -6 || id == -7 || id == -8 || id == -9) {
       mu3[fs + cg] = mu3[fs + ci]; mu3[2 * fs + cg] = mu3[2 * fs + ci];
@@ -165,7 +165,7 @@ int launch_gradients(Ctx* ctx) {
     na = std::max(na, mx[a_ax] - 1); nb = std::max(nb, mx[b_ax] - 1);
   }
   if (mask) {
-    dim3 g2((na + 31) / 32, (nb + 3) / 4, 6);
+    dim3 g2((na + 31) / 32, (nb + 3) / 4, 6 * (ctx->P.sst ? 6 : 4));
     if (ctx->P.sst) k_gradient_bc<6><<<g2, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->gbc, ctx->gbc_off_dev, mask);
     else k_gradient_bc<4><<<g2, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->gbc, ctx->gbc_off_dev, mask);
     ctx->launches++;

@@ -14,29 +14,27 @@ __device__ constexpr double kBeta1 = 0.075, kBeta2 = 0.0828, kBstar = 0.09, kA1 
 __device__ __forceinline__ double sgn1(double x) { return copysign(1.0, x); }          // sign(1.0, x)
 __device__ __forceinline__ double sq(double x) { return x * x; }
 
-// FP64 reciprocal / reciprocal square root without the IEEE slow path: MUFU seed (>= 20 bits) + two Newton steps
-// (-> < 1 ulp before the final rounding).  An IEEE divide costs 14.4 DFMA issue slots on B200, this costs 5
-// (profiles/r01_fp64_ops_microbench.txt); results differ from a/b by <= ~1.5 ulp, five orders below the 1e-12 parity
-// tolerance.  Operands on this path are finite and far from the subnormal / overflow range; the places where the
-// reference relies on IEEE 0/0 or x/0 semantics (boundary_cell_face_values) keep the IEEE divide.
+// FP64 reciprocal / reciprocal square root without the IEEE slow path: MUFU seed (>= 20 good bits, relative error e with
+// |e| < 2^-20) and ONE third-order correction r0*(1 + e + e^2) (error e^3 < 2^-60, i.e. < 1 ulp before the final rounding)
+// -- 3 dependent DFMA instead of the 4 of two Newton steps, and a shorter chain.  An IEEE divide costs 14.4 DFMA issue
+// slots on B200 (profiles/r01_fp64_ops_microbench.txt); results differ from a/b by <= ~1.5 ulp, five orders below the
+// 1e-12 parity tolerance.  Operands on this path are finite and far from the subnormal / overflow range; the places where
+// the reference relies on IEEE 0/0 or x/0 semantics (boundary_cell_face_values) keep the IEEE divide.
 __device__ __forceinline__ double rcp64(double b) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
-  double e = fma(-b, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-b, r, 1.0);
-  return fma(r, e, r);
+  const double e = fma(-b, r, 1.0);
+  const double t = fma(e, e, e);
+  return fma(r, t, r);
 }
 __device__ __forceinline__ double fdiv(double a, double b) { return a * rcp64(b); }
-// x > 0 only (rsqrt(0) = inf)
+// x > 0 only (rsqrt(0) = inf): y0*(1 + h/2 + 3h^2/8) with h = 1 - x*y0^2 (|h| < 2^-19 -> error < 2^-58)
 __device__ __forceinline__ double rsqrt64(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  const double hx = 0.5 * x;
-  double e = fma(-hx * y, y, 0.5);
-  y = fma(y, e, y);
-  e = fma(-hx * y, y, 0.5);
-  return fma(y, e, y);
+  const double h = fma(-(x * y), y, 1.0);
+  const double p = fma(0.375, h, 0.5) * h;
+  return fma(y, p, y);
 }
 __device__ __forceinline__ double sqrt64(double x) {   // x > 0 only
   const double y = rsqrt64(x);

@@ -50,7 +50,8 @@ struct Sm : RecF<NV, VISC> {
   static constexpr int NF = NV + 3;                       // flux + the lambda / viscous / turbulent face terms of the time step
   static constexpr int PLANE = NV * PSQ + NR * PS;        // doubles per staged plane
   static constexpr int OFF_X = 2 * PLANE;                 // exchange area [2][NF][EX]: hi values, then fluxes (same slot)
-  static constexpr int OFF_PRIV = OFF_X + 2 * NF * EX;    // private slots of the K threads, [field][NMAIN]:
+  static constexpr int OFF_S = OFF_X + 2 * NF * EX;       // SST source terms of the cells [2][2][NMAIN], written by the I rows
+  static constexpr int OFF_PRIV = OFF_S + 4 * NMAIN;      // private slots of the K threads, [field][NMAIN]:
   static constexpr int P_FK = 0;                          //   [2][NF] k-face flux; the face below plane p sits in half p & 1
   static constexpr int P_HI = 2 * NF;                     //   [NV] value at the high k face of the newest reconstructed cell
   static constexpr int P_N = P_HI + NV;                   //   [NV+1] norm partials
@@ -145,31 +146,10 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a)
 #pragma unroll
         for (int v = 0; v < NV; ++v) qc[v] = qC[v * PSQ];
         volc = priv[(S::P_VOL + (kc & 1)) * NMAIN];
-        if (SST && VISC) {   // source.f90:214-268
-          double g[6][3];
-#pragma unroll
-          for (int cc = 0; cc < 6; ++cc) {
-            if (cc == 3) continue;
-            g[cc][0] = rC[(3 * cc + 0) * PS]; g[cc][1] = rC[(3 * cc + 1) * PS]; g[cc][2] = rC[(3 * cc + 2) * PS];
-          }
-          const double mut = rC[(S::OFF_MU + 1) * PS];
+        if (SST && VISC) {   // the I row of this cell evaluated the source terms while plane k-1 was its current plane
           F1c = rC[(S::OFF_MU + 2) * PS];
-          const double density = qc[0], tk = qc[5], tw = qc[6];
-          const double wx = g[2][1] - g[1][2], wy = g[0][2] - g[2][0], wz = g[1][0] - g[0][1];
-          const double vort = sqrt(wx * wx + wy * wy + wz * wz);
-          double CD = 2 * density * kSigmaW2 * (g[4][0] * g[5][0] + g[4][1] * g[5][1] + g[4][2] * g[5][2]) * rcp64(tw);
-          CD = dmax(CD, P.cd_floor);
-          const double gama = P.gama1 * F1c + P.gama2 * (1. - F1c);
-          const double beta = kBeta1 * F1c + kBeta2 * (1. - F1c);
-          const double D_k = kBstar * density * tw * tk;
-          const double D_w = beta * density * (tw * tw);
-          const double divergence = g[0][0] + g[1][1] + g[2][2];
-          double P_k = mut * (vort * vort) - ((2.0 / 3.0) * density * tk * divergence);
-          P_k = dmin(P_k, P.pk_limiter * D_k);
-          const double P_w = (density * gama * rcp64(mut)) * P_k;
-          const double lamda = (1. - F1c) * CD;
-          S_k = (P_k - D_k) * volc;
-          S_w = (P_w - D_w + lamda) * volc;
+          const double* xs = smem + S::OFF_S + (kc & 1) * 2 * NMAIN + ty * TX + tx;
+          S_k = xs[0]; S_w = xs[NMAIN];
         }
       }
 
@@ -363,8 +343,8 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a)
     }
   } else {
     // ===================================== I rows, J rows and the three halo warps =====================================
-    int i, j, s0, d;
-    bool rec, fac, stg, wr_hi;
+    int i, j, s0, d, cell;
+    bool rec, fac, stg, wr_hi, irow;
     int om, op;                       // staged-slot offsets of the two neighbours along d
     int exw, exr;                     // exchange slots: where the hi value goes; where L is read and the flux written
     int outer_off;                    // halo threads: global offset of the outer neighbour they stage, and its slot
@@ -374,10 +354,10 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a)
       int t_ = tid;
       asm volatile("" : "+r"(t_));
       const int ln = t_ & 31, w = t_ >> 5;
-      stg = false; wr_hi = true; outer_off = 0; outer_slot = 0;
+      stg = false; wr_hi = true; irow = false; outer_off = 0; outer_slot = 0; cell = 0;
       if (w < TY) {                   // I row
         const int tx = ln, ty = w;
-        d = 0; i = i0 + tx; j = j0 + ty;
+        d = 0; i = i0 + tx; j = j0 + ty; irow = true; cell = ty * TX + tx;
         rec = fac = (j <= Ly.jmx - 1) && (i <= Ly.imx);
         s0 = (ty + 1) * PW + tx + 1; om = -1; op = 1;
         exw = ty * (TX + 1) + tx + 1; exr = ty * (TX + 1) + tx;
@@ -481,6 +461,34 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a)
             if (VISC) xH[(NV + 1) * EX + exr] = vis;
             if (VISC && SST) xH[(NV + 2) * EX + exr] = tur;
           }
+        }
+        if (SST && VISC && irow && rec && i <= Ly.imx - 1) {   // I rows: SST source of the own cell (source.f90:214-268)
+          double g[6][3];
+#pragma unroll
+          for (int cc = 0; cc < 6; ++cc) {
+            if (cc == 3) continue;
+            g[cc][0] = rA[(3 * cc + 0) * PS]; g[cc][1] = rA[(3 * cc + 1) * PS]; g[cc][2] = rA[(3 * cc + 2) * PS];
+          }
+          const double volc = smem[S::OFF_PRIV + (S::P_VOL + (k & 1)) * NMAIN + cell];
+          const double mut = rA[(S::OFF_MU + 1) * PS];
+          const double F1c = rA[(S::OFF_MU + 2) * PS];
+          const double density = qA[0], tk = qA[5 * PSQ], tw = qA[6 * PSQ];
+          const double wx = g[2][1] - g[1][2], wy = g[0][2] - g[2][0], wz = g[1][0] - g[0][1];
+          const double vort = sqrt(wx * wx + wy * wy + wz * wz);
+          double CD = 2 * density * kSigmaW2 * (g[4][0] * g[5][0] + g[4][1] * g[5][1] + g[4][2] * g[5][2]) * rcp64(tw);
+          CD = dmax(CD, P.cd_floor);
+          const double gama = P.gama1 * F1c + P.gama2 * (1. - F1c);
+          const double beta = kBeta1 * F1c + kBeta2 * (1. - F1c);
+          const double D_k = kBstar * density * tw * tk;
+          const double D_w = beta * density * (tw * tw);
+          const double divergence = g[0][0] + g[1][1] + g[2][2];
+          double P_k = mut * (vort * vort) - ((2.0 / 3.0) * density * tk * divergence);
+          P_k = dmin(P_k, P.pk_limiter * D_k);
+          const double P_w = (density * gama * rcp64(mut)) * P_k;
+          const double lamda = (1. - F1c) * CD;
+          double* xs = smem + S::OFF_S + (k & 1) * 2 * NMAIN + cell;
+          xs[0] = (P_k - D_k) * volc;
+          xs[NMAIN] = (P_w - D_w + lamda) * volc;
         }
       }
       cp_async_wait_all();

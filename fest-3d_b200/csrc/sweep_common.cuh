@@ -83,13 +83,16 @@ __device__ __forceinline__ void line_cell_values(const Params& P, const double* 
 template <int NV, int V0, int V1>
 __device__ __forceinline__ void muscl_group(const double (&qm)[NV], const double (&q0)[NV], const double (&qp)[NV], int lim, double (&to_hi)[NV],
                                             double (&to_lo)[NV]) {
+  // q0 +- 0.25*((1 -+ kappa) psi1 bd + (1 +- kappa) psi2 fd) with the constant factors folded: ca = 0.25 (1 - kappa),
+  // cb = 0.25 (1 + kappa), and the two limited differences p1 = psi1 bd, p2 = psi2 fd shared by both faces
   const double kappa = 1. / 3.;
+  const double ca = 0.25 * (1. - kappa), cb = 0.25 * (1. + kappa);
   if (lim == 0) {   // psi = 1 - (1 - psi)*0 = 1 exactly
 #pragma unroll
     for (int v = V0; v < V1; ++v) {
       const double fd = qp[v] - q0[v], bd = q0[v] - qm[v];
-      to_hi[v] = q0[v] + 0.25 * (((1. - kappa) * bd) + ((1. + kappa) * fd));
-      to_lo[v] = q0[v] - 0.25 * (((1. + kappa) * bd) + ((1. - kappa) * fd));
+      to_hi[v] = fma(ca, bd, fma(cb, fd, q0[v]));
+      to_lo[v] = fma(-cb, bd, fma(-ca, fd, q0[v]));
     }
   } else {
 #pragma unroll
@@ -99,10 +102,13 @@ __device__ __forceinline__ void muscl_group(const double (&qm)[NV], const double
       double psi1 = dmax(0., dmin(dmin(2 * r, (2. / 3.) * (r - 1.0) + 1.0), 2.));
       r = bd * rcp64(fd + copysign(1e-14, fd));
       double psi2 = dmax(0., dmin(dmin(2 * r, (2. / 3.) * (r - 1.0) + 1.0), 2.));
-      psi1 = (1 - (1 - psi1) * lim);
-      psi2 = (1 - (1 - psi2) * lim);
-      to_hi[v] = q0[v] + 0.25 * (((1. - kappa) * psi1 * bd) + ((1. + kappa) * psi2 * fd));
-      to_lo[v] = q0[v] - 0.25 * (((1. + kappa) * psi1 * bd) + ((1. - kappa) * psi2 * fd));
+      if (lim != 1) {   // 1 - (1 - psi)*1 is psi to within an ulp; the general switch value keeps the reference form
+        psi1 = (1 - (1 - psi1) * lim);
+        psi2 = (1 - (1 - psi2) * lim);
+      }
+      const double p1 = psi1 * bd, p2 = psi2 * fd;
+      to_hi[v] = fma(ca, p1, fma(cb, p2, q0[v]));
+      to_lo[v] = fma(-cb, p1, fma(-ca, p2, q0[v]));
     }
   }
 }
