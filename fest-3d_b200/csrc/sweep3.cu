@@ -28,9 +28,10 @@ namespace g3 {
 
 constexpr int TX = 32, TY = 4;
 constexpr int NMAIN = TX * TY;
-constexpr int NW = 3 * TY + 3;
+constexpr int NW = 3 * TY + 4;
 constexpr int NT = 32 * NW;
-constexpr int W_IH = 3 * TY, W_JH = 3 * TY + 1, W_JL = 3 * TY + 2;
+constexpr int W_IH = 3 * TY, W_JH = 3 * TY + 1, W_JL = 3 * TY + 2, W_C = 3 * TY + 3;
+constexpr int ROWS_JL = TY / 2;   // rows whose cell work the low-j halo warp does after its (short) reconstruction; W_C does the rest
 constexpr int N_IGRP = 32 * (TY + 1), N_JGRP = 32 * (TY + 2);   // threads on named barriers 1 and 2
 
 // staged plane: (TX+2) x (TY+2) slots, slot = (ty+1)*PW + (tx+1); the q fields carry NOUT extra slots for the second
@@ -50,19 +51,166 @@ struct Sm : RecF<NV, VISC> {
   static constexpr int NF = NV + 3;                       // flux + the lambda / viscous / turbulent face terms of the time step
   static constexpr int PLANE = NV * PSQ + NR * PS;        // doubles per staged plane
   static constexpr int OFF_X = 2 * PLANE;                 // exchange area [2][NF][EX]: hi values, then fluxes (same slot)
-  static constexpr int OFF_S = OFF_X + 2 * NF * EX;       // SST source terms of the cells [2][2][NMAIN], written by the I rows
-  static constexpr int OFF_PRIV = OFF_S + 4 * NMAIN;      // private slots of the K threads, [field][NMAIN]:
-  static constexpr int P_FK = 0;                          //   [2][NF] k-face flux; the face below plane p sits in half p & 1
-  static constexpr int P_HI = 2 * NF;                     //   [NV] value at the high k face of the newest reconstructed cell
-  static constexpr int P_N = P_HI + NV;                   //   [NV+1] norm partials
-  static constexpr int P_Q2 = P_N + NV + 1;               //   [NV] q of plane k+2
+  static constexpr int NPK = NV + 4;                      // cell packet: q[NV], volume, F1, SST sources S_k, S_w
+  static constexpr int OFF_PK = OFF_X + 2 * NF * EX;      // cell packets [2][NPK][NMAIN], written by the I rows
+  static constexpr int OFF_PRIV = OFF_PK + 2 * NPK * NMAIN;   // private slots of the K threads, [field][NMAIN]:
+  static constexpr int P_FK = 0;                          //   [3][NF] k-face flux; the face below plane p sits in third p % 3
+  static constexpr int P_HI = 3 * NF;                     //   [NV] value at the high k face of the newest reconstructed cell
+  static constexpr int P_Q2 = P_HI + NV;                  //   [NV] q of plane k+2
   static constexpr int P_VOL = P_Q2 + NV;                 //   [2] volume of planes (p & 1)
   static constexpr int NPRIV = P_VOL + 2;
-  static constexpr int TOTAL = OFF_PRIV + NPRIV * NMAIN;
+  static constexpr int OFF_NRM = OFF_PRIV + NPRIV * NMAIN;   // norm partials of the 64 threads that do cell work, [NV+1][64]
+  static constexpr int TOTAL = OFF_NRM + (NV + 1) * 64;
 };
 
 __device__ __forceinline__ void bar_all() { asm volatile("bar.sync 0;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const double* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void bar_group(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// Cell work of one cell (row r of the tile, plane kc): residual assembly from the six face fluxes, SST source, local time
+// step, point-implicit k/omega scaling, RK accumulation, conservative update, norm partials.  Everything it needs was left in
+// shared memory during the previous iteration: i/j fluxes (exchange half kc & 1), k fluxes (thirds kc % 3 and (kc+1) % 3 of
+// the K threads' ring), and the cell packet of the I rows (q, volume, F1, source terms).
+template <int NV, bool VISC>
+__device__ __forceinline__ void cell_work(const Params& P, const KArgs& a, double* __restrict__ smem, int tx, int r, int i, int j, int kc,
+                                          bool need_dt, bool k_active, double* __restrict__ nrm /* [NV+1], stride 64 */) {
+  using S = Sm<NV, VISC>;
+  constexpr bool SST = (NV == 7);
+  constexpr int NF = S::NF;
+  const Layout& Ly = P.L;
+  const long long fs = Ly.fs;
+  const long long cc = Ly.idx(i, j, kc);
+  const int cell = r * TX + tx;
+  const int sl0 = r * (TX + 1) + tx, sh0 = sl0 + 1, sl1 = SLOT_I + r * TX + tx, sh1 = sl1 + TX;
+  const double* const xF = smem + S::OFF_X + (kc & 1) * NF * EX;                                  // i/j face fluxes of plane kc
+  const double* const pk = smem + S::OFF_PK + (kc & 1) * S::NPK * NMAIN + cell;                   // cell packet
+  const double* const Flo = smem + S::OFF_PRIV + (S::P_FK + (kc % 3) * NF) * NMAIN + cell;        // k face below the cell
+  const double* const Fhi = smem + S::OFF_PRIV + (S::P_FK + ((kc + 1) % 3) * NF) * NMAIN + cell;  // k face above it
+  double qc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) qc[v] = pk[v * NMAIN];
+  const double volc = pk[NV * NMAIN];
+  double res[NV];
+  double merr = 0.0;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const double Fl0 = xF[v * EX + sl0], Fh0 = xF[v * EX + sh0], Fl1 = xF[v * EX + sl1], Fh1 = xF[v * EX + sh1];
+    double rr = 0.0;
+    rr = rr + (Fh0 - Fl0);   // scheme.f90:133-135
+    rr = rr + (Fh1 - Fl1);
+    if (k_active) rr = rr + (Fhi[v * NMAIN] - Flo[v * NMAIN]);
+    res[v] = rr;
+    if (v == 0) {          // resnorm.f90:190-198
+      if (i == 1) merr += Fl0;
+      if (i == Ly.imx - 1) merr -= Fh0;
+      if (j == 1) merr += Fl1;
+      if (j == Ly.jmx - 1) merr -= Fh1;
+      if (k_active) {
+        if (kc == 1) merr += Flo[0];
+        if (kc == Ly.kmx - 1) merr -= Fhi[0];
+      }
+    }
+  }
+  {
+    bool bad = false;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) bad |= isnan(res[v]);
+    if (bad) flag_error(a.err, F3D_ERR_NAN_FLUX, i, j, kc);
+  }
+  if (SST && VISC) {
+    res[5] = res[5] - pk[(NV + 2) * NMAIN];
+    res[6] = res[6] - pk[(NV + 3) * NMAIN];
+  }
+
+  double dtc = 0.0;
+  if (need_dt) {
+    if (P.time_stepping == 1 && P.global_time_step > 0) {
+      dtc = P.global_time_step;
+    } else {
+      const double* lamv = xF + NV * EX;
+      const double lmxsum = lamv[sl0] + lamv[sl1] + Flo[NV * NMAIN] + lamv[sh0] + lamv[sh1] + Fhi[NV * NMAIN];
+      dtc = rcp64(lmxsum);
+      dtc = dtc * volc * P.CFL;
+      if (VISC) {
+        const double* visv = xF + (NV + 1) * EX;
+        double s = visv[sl0] + visv[sl1] + Flo[(NV + 1) * NMAIN] + visv[sh0] + visv[sh1] + Fhi[(NV + 1) * NMAIN];
+        s = P.gm * s * P.inv_Pr;
+        s = 2. * rcp64(s + (2. * P.CFL * volc * rcp64(dtc)));
+        dtc = P.CFL * (s * volc);
+        if (SST) {
+          const double* turv = xF + (NV + 2) * EX;
+          double tt = turv[sl0] + turv[sl1] + Flo[(NV + 2) * NMAIN] + turv[sh0] + turv[sh1] + Fhi[(NV + 2) * NMAIN];
+          tt = P.gm * tt * P.inv_tPr;
+          tt = 2. * rcp64(tt + (2. * P.CFL * volc * rcp64(dtc)));
+          dtc = P.CFL * (tt * volc);
+        }
+      }
+    }
+    a.dt[cc] = dtc;
+  } else if (a.mode == MODE_UPDATE) {
+    dtc = a.dt[cc];
+  }
+
+  if (a.mode == MODE_RESIDUE_ONLY) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) a.residue[v * fs + cc] = res[v];
+  } else {   // update.f90:371-485
+    double u1[NV], R[NV], u2[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) R[v] = res[v];
+    if (a.have_store || a.quse != a.q) {
+      u1[0] = a.quse[cc];
+#pragma unroll
+      for (int v = 1; v < NV; ++v) u1[v] = a.quse[v * fs + cc] * u1[0];
+    } else {   // the state the update starts from is the staged one
+      u1[0] = qc[0];
+#pragma unroll
+      for (int v = 1; v < NV; ++v) u1[v] = qc[v] * u1[0];
+    }
+    u1[4] = (u1[4] * P.inv_gm1 + 0.5 * (u1[1] * u1[1] + u1[2] * u1[2] + u1[3] * u1[3])) * rcp64(u1[0]) + 0.;
+    if (SST) {
+      const double F1 = VISC ? pk[(NV + 1) * NMAIN] : 0.0;
+      const double beta = kBeta1 * F1 + (1. - F1) * kBeta2;
+      R[5] = R[5] * rcp64(1 + (beta * qc[6] * dtc));
+      R[6] = R[6] * rcp64(1 + (2 * beta * qc[6] * dtc));
+    }
+    if (a.have_store) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const double rn = a.rstore[v * fs + cc] + a.SF * R[v];
+        a.rstore[v * fs + cc] = rn;
+        if (a.use_store_sum) R[v] = rn;
+      }
+    }
+    const double fac_ = (a.TF * dtc * rcp64(volc));
+#pragma unroll
+    for (int v = 0; v < NV; ++v) u2[v] = u1[v] - R[v] * fac_;
+    const double iu = 1.0 / u2[0];   // IEEE: u2[0] may be <= 0 or NaN here and must reach the check below unchanged
+#pragma unroll
+    for (int v = 1; v < NV; ++v) u2[v] = u2[v] * iu;
+    u2[4] = (P.gm - 1.) * u2[0] * (u2[4] - (0.5 * (u2[1] * u2[1] + u2[2] * u2[2] + u2[3] * u2[3])) - 0.);
+    bool bad = (u2[0] < 0.) || (u2[4] < 0.);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) bad |= isnan(u2[v]);
+    if (bad) {
+      flag_error(a.err, F3D_ERR_NEGATIVE_STATE, i, j, kc);
+#pragma unroll
+      for (int v = 0; v < NV; ++v) a.qnew[v * fs + cc] = qc[v];
+    } else {
+#pragma unroll
+      for (int v = 0; v < 5; ++v) a.qnew[v * fs + cc] = u2[v];
+      if (SST) {
+        a.qnew[5 * fs + cc] = (u2[5] >= 0.) ? u2[5] : qc[5];
+        a.qnew[6 * fs + cc] = (u2[6] >= 0.) ? u2[6] : qc[6];
+      }
+    }
+  }
+  if (a.want_norms) {   // resnorm.f90:187-198
+    nrm[0] += merr;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) nrm[(1 + v) * 64] += res[v] * res[v];
+  }
+}
 
 template <int NV, int INTERP, int SCHEME, bool VISC>
 __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a) {
@@ -81,13 +229,17 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a)
   const bool k_active = flux_on_k || VISC || need_dt;
   const double* __restrict__ q = a.q;
   const double* __restrict__ vol = a.geom + (long long)G_VOL * fs;
+  if (tid < 64) {       // norm partials of the threads that do cell work
+#pragma unroll
+    for (int v = 0; v <= NV; ++v) smem[S::OFF_NRM + v * 64 + tid] = 0.0;
+  }
 
   if (wid >= 2 * TY && wid < 3 * TY) {
-    // =============================================== K rows: the cells ===============================================
+    // ================================ K rows: k reconstruction and k-face flux of their column ================================
     // The few values that define this thread's role are re-derived from the thread index at the top of every plane (the
     // empty asm keeps the compiler from hoisting them out of the loop): generation-3 bring-up spilled them to local memory
     // and 27 % of all stall samples were waits on those reloads (profiles/r01_g3_summary.md).
-    int tx, ty, i, j, s0, sl0, sh0, sl1, sh1;
+    int tx, ty, i, j, s0;
     bool own, stg;
     double* priv;
     auto role = [&]() {
@@ -101,7 +253,6 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a)
       if (j > Ly.jmx + 1) j = Ly.jmx + 1;
       s0 = (ty + 1) * PW + tx + 1;
       priv = smem + S::OFF_PRIV + ty * TX + tx;
-      sl0 = ty * (TX + 1) + tx; sh0 = sl0 + 1; sl1 = SLOT_I + ty * TX + tx; sh1 = sl1 + TX;
     };
     role();
 
@@ -122,6 +273,16 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a)
       }
       if (own) cp_async8(priv + (S::P_VOL + (kk & 1)) * NMAIN, vol + c1);
     };
+    auto prefetch_own = [&](int kk) {   // pull the record of plane kk into L2 one plane before it is staged (q came with the k stencil)
+      if (!stg || !VISC) return;
+      const long long c1 = Ly.idx(i, j, kk);
+#pragma unroll
+      for (int f = 0; f < S::NGF; ++f) prefetch_l2(a.grad + f * fs + c1);
+#pragma unroll
+      for (int f = 0; f < S::NMU; ++f) prefetch_l2(a.mu + f * fs + c1);
+#pragma unroll
+      for (int f = 0; f < 3; ++f) prefetch_l2(a.geom + (long long)(G_CX + f) * fs + c1);
+    };
 
 #pragma unroll
     for (int f = 0; f < S::P_Q2; ++f) priv[f * NMAIN] = 0.0;
@@ -129,169 +290,19 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a)
     cp_async_wait_all();
 
     for (int k = kb - 1; k <= ke; ++k) {
-      bar_all();   // plane k is staged; the i/j fluxes of plane k-1 are in exchange half (k-1) & 1
+      bar_all();   // plane k is staged
       role();
-      const int kc = k - 1;                                   // plane of the cell work
-      const bool cell_on = own && kc >= kb;
-      const bool more = k <= ke - 1;                          // a k face above plane k is still to be evaluated
-      const long long c = Ly.idx(i, j, k);
-      const double* const plA = smem + (k & 1) * S::PLANE;          // plane k
-      double* const plB = smem + ((k + 1) & 1) * S::PLANE;          // plane k-1 now, plane k+1 after the staging below
-
-      // ---- cell work of plane k-1, part 1: everything that reads this thread's record of plane k-1 ---------------------
-      double qc[NV], S_k = 0.0, S_w = 0.0, F1c = 0.0, volc = 0.0;
-      if (cell_on) {
-        const double* const qC = plB + s0;
-        const double* const rC = plB + NV * PSQ + s0;
-#pragma unroll
-        for (int v = 0; v < NV; ++v) qc[v] = qC[v * PSQ];
-        volc = priv[(S::P_VOL + (kc & 1)) * NMAIN];
-        if (SST && VISC) {   // the I row of this cell evaluated the source terms while plane k-1 was its current plane
-          F1c = rC[(S::OFF_MU + 2) * PS];
-          const double* xs = smem + S::OFF_S + (kc & 1) * 2 * NMAIN + ty * TX + tx;
-          S_k = xs[0]; S_w = xs[NMAIN];
-        }
-      }
-
-      // ---- stage this thread's record of plane k+1 over the one just consumed; q of plane k+2 for the k stencil ----------
-      if (more) {
+      if (k <= ke - 1) {   // the k face between planes k and k+1
+        const long long c = Ly.idx(i, j, k);
+        const double* const plA = smem + (k & 1) * S::PLANE;          // plane k
+        const double* const plB = smem + ((k + 1) & 1) * S::PLANE;    // plane k+1 after the staging below
+        // nobody reads plane k-1 any more (the cell work takes what it needs from the cell packets): stage plane k+1 over it
         stage_own(k + 1);
         if (own && k_active && SMQ) {
 #pragma unroll
           for (int v = 0; v < NV; ++v) cp_async8(priv + (S::P_Q2 + v) * NMAIN, q + v * fs + c + 2 * Ly.sk);
         }
-      }
-
-      // ---- cell work of plane k-1, part 2 -------------------------------------------------------------------------------------
-      if (cell_on) {
-        const long long cc = c - Ly.sk;
-        const double* const xF = smem + S::OFF_X + (kc & 1) * NF * EX;     // i/j face fluxes of plane k-1
-        const double* const Flo = priv + (S::P_FK + (kc & 1) * NF) * NMAIN;   // k face below the cell
-        const double* const Fhi = priv + (S::P_FK + (k & 1) * NF) * NMAIN;    // k face above it
-        double res[NV];
-        double merr = 0.0;
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          const double Fl0 = xF[v * EX + sl0], Fh0 = xF[v * EX + sh0], Fl1 = xF[v * EX + sl1], Fh1 = xF[v * EX + sh1];
-          double r = 0.0;
-          r = r + (Fh0 - Fl0);   // scheme.f90:133-135
-          r = r + (Fh1 - Fl1);
-          if (k_active) r = r + (Fhi[v * NMAIN] - Flo[v * NMAIN]);
-          res[v] = r;
-          if (v == 0) {          // resnorm.f90:190-198
-            if (i == 1) merr += Fl0;
-            if (i == Ly.imx - 1) merr -= Fh0;
-            if (j == 1) merr += Fl1;
-            if (j == Ly.jmx - 1) merr -= Fh1;
-            if (k_active) {
-              if (kc == 1) merr += Flo[0];
-              if (kc == Ly.kmx - 1) merr -= Fhi[0];
-            }
-          }
-        }
-        {
-          bool bad = false;
-#pragma unroll
-          for (int v = 0; v < NV; ++v) bad |= isnan(res[v]);
-          if (bad) flag_error(a.err, F3D_ERR_NAN_FLUX, i, j, kc);
-        }
-        if (SST && VISC) {
-          res[5] = res[5] - S_k;
-          res[6] = res[6] - S_w;
-        }
-
-        double dtc = 0.0;
-        if (need_dt) {
-          if (P.time_stepping == 1 && P.global_time_step > 0) {
-            dtc = P.global_time_step;
-          } else {
-            const double* lamv = xF + NV * EX;
-            const double lmxsum = lamv[sl0] + lamv[sl1] + Flo[NV * NMAIN] + lamv[sh0] + lamv[sh1] + Fhi[NV * NMAIN];
-            dtc = rcp64(lmxsum);
-            dtc = dtc * volc * P.CFL;
-            if (VISC) {
-              const double* visv = xF + (NV + 1) * EX;
-              double s = visv[sl0] + visv[sl1] + Flo[(NV + 1) * NMAIN] + visv[sh0] + visv[sh1] + Fhi[(NV + 1) * NMAIN];
-              s = P.gm * s * P.inv_Pr;
-              s = 2. * rcp64(s + (2. * P.CFL * volc * rcp64(dtc)));
-              dtc = P.CFL * (s * volc);
-              if (SST) {
-                const double* turv = xF + (NV + 2) * EX;
-                double t = turv[sl0] + turv[sl1] + Flo[(NV + 2) * NMAIN] + turv[sh0] + turv[sh1] + Fhi[(NV + 2) * NMAIN];
-                t = P.gm * t * P.inv_tPr;
-                t = 2. * rcp64(t + (2. * P.CFL * volc * rcp64(dtc)));
-                dtc = P.CFL * (t * volc);
-              }
-            }
-          }
-          a.dt[cc] = dtc;
-        } else if (a.mode == MODE_UPDATE) {
-          dtc = a.dt[cc];
-        }
-
-        if (a.mode == MODE_RESIDUE_ONLY) {
-#pragma unroll
-          for (int v = 0; v < NV; ++v) a.residue[v * fs + cc] = res[v];
-        } else {   // update.f90:371-485
-          double u1[NV], R[NV], u2[NV];
-#pragma unroll
-          for (int v = 0; v < NV; ++v) R[v] = res[v];
-          if (a.have_store || a.quse != a.q) {
-            u1[0] = a.quse[cc];
-#pragma unroll
-            for (int v = 1; v < NV; ++v) u1[v] = a.quse[v * fs + cc] * u1[0];
-          } else {   // the state the update starts from is the staged one
-            u1[0] = qc[0];
-#pragma unroll
-            for (int v = 1; v < NV; ++v) u1[v] = qc[v] * u1[0];
-          }
-          u1[4] = (u1[4] * P.inv_gm1 + 0.5 * (u1[1] * u1[1] + u1[2] * u1[2] + u1[3] * u1[3])) * rcp64(u1[0]) + 0.;
-          if (SST) {
-            const double F1 = VISC ? F1c : 0.0;
-            const double beta = kBeta1 * F1 + (1. - F1) * kBeta2;
-            R[5] = R[5] * rcp64(1 + (beta * qc[6] * dtc));
-            R[6] = R[6] * rcp64(1 + (2 * beta * qc[6] * dtc));
-          }
-          if (a.have_store) {
-#pragma unroll
-            for (int v = 0; v < NV; ++v) {
-              const double rn = a.rstore[v * fs + cc] + a.SF * R[v];
-              a.rstore[v * fs + cc] = rn;
-              if (a.use_store_sum) R[v] = rn;
-            }
-          }
-          const double fac_ = (a.TF * dtc * rcp64(volc));
-#pragma unroll
-          for (int v = 0; v < NV; ++v) u2[v] = u1[v] - R[v] * fac_;
-          const double iu = 1.0 / u2[0];   // IEEE: u2[0] may be <= 0 or NaN here and must reach the check below unchanged
-#pragma unroll
-          for (int v = 1; v < NV; ++v) u2[v] = u2[v] * iu;
-          u2[4] = (P.gm - 1.) * u2[0] * (u2[4] - (0.5 * (u2[1] * u2[1] + u2[2] * u2[2] + u2[3] * u2[3])) - 0.);
-          bool bad = (u2[0] < 0.) || (u2[4] < 0.);
-#pragma unroll
-          for (int v = 0; v < NV; ++v) bad |= isnan(u2[v]);
-          if (bad) {
-            flag_error(a.err, F3D_ERR_NEGATIVE_STATE, i, j, kc);
-#pragma unroll
-            for (int v = 0; v < NV; ++v) a.qnew[v * fs + cc] = qc[v];
-          } else {
-#pragma unroll
-            for (int v = 0; v < 5; ++v) a.qnew[v * fs + cc] = u2[v];
-            if (SST) {
-              a.qnew[5 * fs + cc] = (u2[5] >= 0.) ? u2[5] : qc[5];
-              a.qnew[6 * fs + cc] = (u2[6] >= 0.) ? u2[6] : qc[6];
-            }
-          }
-        }
-        if (a.want_norms) {   // resnorm.f90:187-198
-          priv[S::P_N * NMAIN] += merr;
-#pragma unroll
-          for (int v = 0; v < NV; ++v) priv[(S::P_N + 1 + v) * NMAIN] += res[v] * res[v];
-        }
-      }
-
-      // ---- k face between planes k and k+1 ---------------------------------------------------------------------------------
-      if (more) {
+        if (k + 2 <= ke) prefetch_own(k + 2);
         double kA = 0.0, knx = 0.0, kny = 0.0, knz = 0.0;
         if (own && k_active) {   // metrics of the k face, requested before the wait so their latency overlaps it
           const double* __restrict__ gp = a.geom + (long long)G_KA * fs + c + Ly.sk;
@@ -334,7 +345,7 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a)
           }
           double F[NV], lam = 0.0, vis = 0.0, tur = 0.0;
           face_eval<NV, SCHEME, VISC, PS, PSQ>(P, 2, qA, qB, rA, rB, kA, knx, kny, knz, k + 1, Ly.kmx, L, lo, flux_on_k, need_dt, F, lam, vis, tur);
-          double* const Fn = priv + (S::P_FK + ((k + 1) & 1) * NF) * NMAIN;
+          double* const Fn = priv + (S::P_FK + ((k + 1) % 3) * NF) * NMAIN;   // read by the cell work of planes k and k+1
 #pragma unroll
           for (int v = 0; v < NV; ++v) Fn[v * NMAIN] = F[v];
           Fn[NV * NMAIN] = lam; Fn[(NV + 1) * NMAIN] = vis; Fn[(NV + 2) * NMAIN] = tur;
@@ -342,8 +353,8 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a)
       }
     }
   } else {
-    // ===================================== I rows, J rows and the three halo warps =====================================
-    int i, j, s0, d, cell;
+    // ============== I rows, J rows, the three halo warps, and the cell work (low-j halo warp and warp W_C) ==============
+    int i, j, s0, d, cell, r_lo, r_hi;
     bool rec, fac, stg, wr_hi, irow;
     int om, op;                       // staged-slot offsets of the two neighbours along d
     int exw, exr;                     // exchange slots: where the hi value goes; where L is read and the flux written
@@ -354,7 +365,8 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a)
       int t_ = tid;
       asm volatile("" : "+r"(t_));
       const int ln = t_ & 31, w = t_ >> 5;
-      stg = false; wr_hi = true; irow = false; outer_off = 0; outer_slot = 0; cell = 0;
+      stg = false; wr_hi = true; irow = false; outer_off = 0; outer_slot = 0; cell = 0; r_lo = 0; r_hi = 0;
+      rec = fac = false; d = 0; i = i0 + ln; j = j0; s0 = PW + 1; om = op = 0; exw = exr = 0;
       if (w < TY) {                   // I row
         const int tx = ln, ty = w;
         d = 0; i = i0 + tx; j = j0 + ty; irow = true; cell = ty * TX + tx;
@@ -378,6 +390,8 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a)
         outer_off = (side == 0) ? -1 : 1;
         om = (side == 0) ? outer_slot - s0 : -1; op = (side == 0) ? 1 : outer_slot - s0;
         exw = r * (TX + 1) + (side == 0 ? 0 : TX); exr = r * (TX + 1) + TX;
+      } else if (w == W_C) {          // cell work only
+        r_lo = ROWS_JL; r_hi = TY;
       } else {                        // high (W_JH) and low (W_JL) j rows next to the tile
         const bool high = w == W_JH;
         d = 1; i = i0 + ln; j = high ? j0 + TY : j0 - 1;
@@ -389,6 +403,7 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a)
         outer_off = high ? (int)Ly.sj : -(int)Ly.sj;
         om = high ? -PW : outer_slot - s0; op = high ? outer_slot - s0 : PW;
         exw = SLOT_I + (high ? TY * TX : 0) + ln; exr = SLOT_I + TY * TX + ln;
+        if (!high) { r_lo = 0; r_hi = ROWS_JL; }
       }
       if (i > Ly.imx + 1) i = Ly.imx + 1;
       if (j > Ly.jmx + 1) j = Ly.jmx + 1;
@@ -421,7 +436,7 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a)
       bar_all();
       role();
       if (k + 1 <= ke - 1) stage_ring(k + 1);
-      if (k >= kb && k <= ke - 1) {
+      if (wid != W_C && k >= kb && k <= ke - 1) {
         const long long c = Ly.idx(i, j, k);
         double* const pl = smem + (k & 1) * S::PLANE;
         const double* const qA = pl + s0;
@@ -462,48 +477,63 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a)
             if (VISC && SST) xH[(NV + 2) * EX + exr] = tur;
           }
         }
-        if (SST && VISC && irow && rec && i <= Ly.imx - 1) {   // I rows: SST source of the own cell (source.f90:214-268)
-          double g[6][3];
-#pragma unroll
-          for (int cc = 0; cc < 6; ++cc) {
-            if (cc == 3) continue;
-            g[cc][0] = rA[(3 * cc + 0) * PS]; g[cc][1] = rA[(3 * cc + 1) * PS]; g[cc][2] = rA[(3 * cc + 2) * PS];
-          }
+        if (irow && rec && i <= Ly.imx - 1) {   // I rows: the cell packet of the own cell for next iteration's cell work
+          double* const pk = smem + S::OFF_PK + (k & 1) * S::NPK * NMAIN + cell;
           const double volc = smem[S::OFF_PRIV + (S::P_VOL + (k & 1)) * NMAIN + cell];
-          const double mut = rA[(S::OFF_MU + 1) * PS];
-          const double F1c = rA[(S::OFF_MU + 2) * PS];
-          const double density = qA[0], tk = qA[5 * PSQ], tw = qA[6 * PSQ];
-          const double wx = g[2][1] - g[1][2], wy = g[0][2] - g[2][0], wz = g[1][0] - g[0][1];
-          const double vort = sqrt(wx * wx + wy * wy + wz * wz);
-          double CD = 2 * density * kSigmaW2 * (g[4][0] * g[5][0] + g[4][1] * g[5][1] + g[4][2] * g[5][2]) * rcp64(tw);
-          CD = dmax(CD, P.cd_floor);
-          const double gama = P.gama1 * F1c + P.gama2 * (1. - F1c);
-          const double beta = kBeta1 * F1c + kBeta2 * (1. - F1c);
-          const double D_k = kBstar * density * tw * tk;
-          const double D_w = beta * density * (tw * tw);
-          const double divergence = g[0][0] + g[1][1] + g[2][2];
-          double P_k = mut * (vort * vort) - ((2.0 / 3.0) * density * tk * divergence);
-          P_k = dmin(P_k, P.pk_limiter * D_k);
-          const double P_w = (density * gama * rcp64(mut)) * P_k;
-          const double lamda = (1. - F1c) * CD;
-          double* xs = smem + S::OFF_S + (k & 1) * 2 * NMAIN + cell;
-          xs[0] = (P_k - D_k) * volc;
-          xs[NMAIN] = (P_w - D_w + lamda) * volc;
+#pragma unroll
+          for (int v = 0; v < NV; ++v) pk[v * NMAIN] = qA[v * PSQ];
+          pk[NV * NMAIN] = volc;
+          if (SST && VISC) {   // SST source terms (source.f90:214-268)
+            double g[6][3];
+#pragma unroll
+            for (int cc = 0; cc < 6; ++cc) {
+              if (cc == 3) continue;
+              g[cc][0] = rA[(3 * cc + 0) * PS]; g[cc][1] = rA[(3 * cc + 1) * PS]; g[cc][2] = rA[(3 * cc + 2) * PS];
+            }
+            const double mut = rA[(S::OFF_MU + 1) * PS];
+            const double F1c = rA[(S::OFF_MU + 2) * PS];
+            const double density = qA[0], tk = qA[5 * PSQ], tw = qA[6 * PSQ];
+            const double wx = g[2][1] - g[1][2], wy = g[0][2] - g[2][0], wz = g[1][0] - g[0][1];
+            const double vort = sqrt(wx * wx + wy * wy + wz * wz);
+            double CD = 2 * density * kSigmaW2 * (g[4][0] * g[5][0] + g[4][1] * g[5][1] + g[4][2] * g[5][2]) * rcp64(tw);
+            CD = dmax(CD, P.cd_floor);
+            const double gama = P.gama1 * F1c + P.gama2 * (1. - F1c);
+            const double beta = kBeta1 * F1c + kBeta2 * (1. - F1c);
+            const double D_k = kBstar * density * tw * tk;
+            const double D_w = beta * density * (tw * tw);
+            const double divergence = g[0][0] + g[1][1] + g[2][2];
+            double P_k = mut * (vort * vort) - ((2.0 / 3.0) * density * tk * divergence);
+            P_k = dmin(P_k, P.pk_limiter * D_k);
+            const double P_w = (density * gama * rcp64(mut)) * P_k;
+            const double lamda = (1. - F1c) * CD;
+            pk[(NV + 1) * NMAIN] = F1c;
+            pk[(NV + 2) * NMAIN] = (P_k - D_k) * volc;
+            pk[(NV + 3) * NMAIN] = (P_w - D_w + lamda) * volc;
+          }
+        }
+      }
+      // ---- cell work of plane k-1 (low-j halo warp: rows 0..ROWS_JL-1, W_C: the rest) ------------------------------------------
+      if (r_hi > r_lo && k - 1 >= kb) {
+        const int ic = i0 + lane;
+#pragma unroll 1
+        for (int r = r_lo; r < r_hi; ++r) {
+          const int jc = j0 + r;
+          if (ic <= Ly.imx - 1 && jc <= Ly.jmx - 1)
+            cell_work<NV, VISC>(P, a, smem, lane, r, ic, jc, k - 1, need_dt, k_active, smem + S::OFF_NRM + (wid == W_C ? 32 : 0) + lane);
         }
       }
       cp_async_wait_all();
     }
   }
 
-  if (a.want_norms) {   // per-CTA partial: warp shuffle inside the K rows, then across them
+  if (a.want_norms) {   // per-CTA partial: warp shuffle inside the two warps that did the cell work, then across them
     bar_all();
-    double* sred = smem;   // [NV+1][TY]
-    const bool krow = wid >= 2 * TY && wid < 3 * TY;
-    if (krow) {
-      const double* priv = smem + S::OFF_PRIV + (wid - 2 * TY) * TX + lane;
+    double* sred = smem;   // [NV+1][2]
+    const bool cw = wid == W_JL || wid == W_C;
+    if (cw) {
       double x[NV + 1];
 #pragma unroll
-      for (int v = 0; v <= NV; ++v) x[v] = priv[(S::P_N + v) * NMAIN];
+      for (int v = 0; v <= NV; ++v) x[v] = smem[S::OFF_NRM + v * 64 + (wid == W_C ? 32 : 0) + lane];
 #pragma unroll
       for (int v = 0; v <= NV; ++v) {
 #pragma unroll
@@ -511,13 +541,12 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a)
       }
       if (lane == 0) {
 #pragma unroll
-        for (int v = 0; v <= NV; ++v) sred[v * TY + (wid - 2 * TY)] = x[v];
+        for (int v = 0; v <= NV; ++v) sred[v * 2 + (wid == W_C ? 1 : 0)] = x[v];
       }
     }
     bar_all();
     if (tid <= NV) {
-      double x = 0.0;
-      for (int w = 0; w < TY; ++w) x += sred[tid * TY + w];
+      const double x = sred[tid * 2] + sred[tid * 2 + 1];
       const long long cta = blockIdx.x + (long long)gridDim.x * (blockIdx.y + (long long)gridDim.y * blockIdx.z);
       a.red[cta * (NV + 1) + tid] = x;
     }
