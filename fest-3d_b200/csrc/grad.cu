@@ -1,7 +1,6 @@
 // Green-Gauss cell gradients of (u,v,w,T[,k,omega]) on cells 0..imx x 0..jmx x 0..kmx fused with the molecular
-// (Sutherland) and eddy viscosity / SST blending function F1 of the same cell, and with the ghost-gradient rule and the
-// ghost mu_t / F1 copies on physical faces (written by the thread of the interior cell next to the ghost cell: the
-// separate boundary kernel of the first generations cost 0.24 ms per stage at 256^3 on strided i faces).
+// (Sutherland) and eddy viscosity / SST blending function F1 of the same cell, then the ghost-gradient rule and the
+// ghost mu_t / F1 copies on physical faces.
 //
 // Reference: src/gradients.f90:276-402 (evaluate_all_gradients), :405-482 (compute_gradient_G), :486-676
 // (apply_gradient_bc, incl. the Ifaces-shaped dummy that mis-indexes Jfaces/Kfaces -- those records are gathered on the
@@ -15,8 +14,7 @@ namespace f3d {
 
 template <int NG>
 __global__ void __launch_bounds__(128, 5) k_gradients(const Params P, const double* __restrict__ q, const double* __restrict__ temp,
-                                                   const double* __restrict__ geom, double* __restrict__ grad, double* __restrict__ mu3, int* err,
-                                                   const double* __restrict__ rec_all, const long long* __restrict__ rec_off) {
+                                                   const double* __restrict__ geom, double* __restrict__ grad, double* __restrict__ mu3, int* err) {
   const Layout& L = P.L;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
@@ -37,24 +35,6 @@ __global__ void __launch_bounds__(128, 5) k_gradients(const Params P, const doub
   const double AIl = gI[c], AIh = gI[c + 1], AJl = gJ[c], AJh = gJ[c + sj], AKl = gK[c], AKh = gK[c + sk];
   const double ivol2 = rcp64(2 * geom[(long long)G_VOL * fs + c]);
   const bool zgrad = L.kmx > 2;   // gradqp_z = 0 when kmx == 2 (gradients.f90:328-336)
-  // Ghost cells of a physical face (one index outside the interior, the other two inside) get their gradient -- and for most
-  // BC ids their mu_t / F1 -- from the boundary rule below, written by the thread of the interior cell next to them; the
-  // Green-Gauss value the reference first computes there is overwritten (gradients.f90:486-676 runs after :405-482).
-  auto sel3 = [](int ax, long long x0, long long x1, long long x2) { return ax == 0 ? x0 : (ax == 1 ? x1 : x2); };   // no local arrays
-  int n_out = 0, gface = 0;
-  if (i == 0) { ++n_out; gface = 1; }
-  if (i == L.imx) { ++n_out; gface = 2; }
-  if (j == 0) { ++n_out; gface = 3; }
-  if (j == L.jmx) { ++n_out; gface = 4; }
-  if (k == 0) { ++n_out; gface = 5; }
-  if (k == L.kmx) { ++n_out; gface = 6; }
-  const bool interior = n_out == 0;
-  const bool ruled_ghost = (n_out == 1) && (P.bc_id[gface - 1] < 0);
-  bool ghost_keeps_mut = true;   // ids outside the two lists of viscosity.f90:408-465 leave the computed ghost mu_t / F1
-  if (ruled_ghost) {
-    const int id = P.bc_id[gface - 1];
-    ghost_keeps_mut = !(id == -5 || id == -1 || id == -2 || id == -3 || id == -4 || id == -6 || id == -7 || id == -8 || id == -9);
-  }
   double g[NG][3];
   // face weights n*A once per face and direction (18 products), then 6 FMAs per gradient component: branch-free so the
   // NG*3 independent chains interleave
@@ -77,7 +57,7 @@ __global__ void __launch_bounds__(128, 5) k_gradients(const Params P, const doub
       if (d == 2) r = zgrad ? r : 0.0;
       nan_probe += r;
       g[cc][d] = r;
-      if (!ruled_ghost) grad[(3 * cc + d) * fs + c] = r;
+      grad[(3 * cc + d) * fs + c] = r;
     }
   }
   const bool bad = isnan(nan_probe);
@@ -91,7 +71,6 @@ __global__ void __launch_bounds__(128, 5) k_gradients(const Params P, const doub
     mu3[c] = mu;
     if (isnan(mu)) atomicOr(err, F3D_ERR_NAN_VISCOSITY);
   }
-  double mut_v = 0.0, F1_c = 0.0;
   if (NG == 6) {
     const double density = q[c], tk = q[5 * fs + c], tw = q[6 * fs + c];
     const double d = geom[(long long)G_DIST * fs + c];
@@ -110,55 +89,61 @@ __global__ void __launch_bounds__(128, 5) k_gradients(const Params P, const doub
     }
     const double NUM = density * kA1 * tk;
     const double DENOM = dmax(dmax((kA1 * tw), rate * Fb), P.mut_floor);
-    const double mut_c = NUM * rcp64(DENOM);
-    if (ghost_keeps_mut) mu3[fs + c] = mut_c;
+    mu3[fs + c] = NUM * rcp64(DENOM);
     const double CD = dmax(2 * density * kSigmaW2 * (g[4][0] * g[5][0] + g[4][1] * g[5][1] + g[4][2] * g[5][2]) * rcp64(tw), P.mut_floor);
     const double right = 4 * (density * kSigmaW2 * tk) * rcp64(CD * (d * d));
     const double left = dmax(var1, var2);
     const double arg1 = dmin(left, right);
-    F1_c = tanh((arg1 * arg1) * (arg1 * arg1));
-    if (ghost_keeps_mut) mu3[2 * fs + c] = F1_c;
-    mut_v = mut_c;
+    mu3[2 * fs + c] = tanh((arg1 * arg1) * (arg1 * arg1));
   }
-  // ---- ghost-gradient rule + ghost mu_t / F1 of the physical faces this interior cell touches (gradients.f90:638-674,
-  //      viscosity.f90:408-465); the face records come from the reference's (mis-)indexed gather (api.cu:set_geometry)
-  if (interior) {
-    const double vol = geom[(long long)G_VOL * fs + c];
-#pragma unroll 1
-    for (int face = 1; face <= 6; ++face) {
-      const int ax = (face - 1) / 2;
-      const bool lo = (face % 2) == 1;
-      if ((int)sel3(ax, i, j, k) != (lo ? 1 : (int)sel3(ax, L.imx, L.jmx, L.kmx) - 1)) continue;
-      const int id = P.bc_id[face - 1];
-      if (id >= 0) continue;   // "if (bc%imin_id < 0)" -- includes -10
-      const int a_ax = (ax == 0) ? 1 : 0, b_ax = (ax == 2) ? 1 : 2;
-      const int na = (int)sel3(a_ax, L.imx, L.jmx, L.kmx) - 1;
-      const double* r = rec_all + rec_off[face - 1] + 4 * ((sel3(b_ax, i, j, k) - 1) * na + (sel3(a_ax, i, j, k) - 1));
-      const double A = r[0], nx = r[1], ny = r[2], nz = r[3];
-      const double c_x = A * nx / vol, c_y = A * ny / vol, c_z = A * nz / vol;
-      const double sig = lo ? 1.0 : -1.0;
-      const long long stx = sel3(ax, 1, sj, sk);
-      const long long cg = lo ? c - stx : c + stx;
-      const double ft = P.fixed[F3D_FIX_WALL_TEMP][face - 1];
+}
+
+// ghost-gradient rule + ghost mu_t/F1 on one physical face (gradients.f90:638-674, viscosity.f90:408-465)
+template <int NG>
+__global__ void k_gradient_bc(const Params P, const double* __restrict__ q, const double* __restrict__ temp, const double* __restrict__ geom,
+                              double* __restrict__ grad, double* __restrict__ mu3, const double* __restrict__ rec_all, const long long* rec_off,
+                              int face_mask) {
+  // one launch for all physical faces (blockIdx.z = face-1): each face reads interior gradients and writes its own ghost cells
+  const int face = blockIdx.z + 1;
+  if (!(face_mask >> (face - 1) & 1)) return;
+  const double* __restrict__ rec = rec_all + rec_off[face - 1];
+  const Layout& L = P.L;
+  const int ax = (face - 1) / 2;
+  const bool lo = (face % 2) == 1;
+  const int a_ax = (ax == 0) ? 1 : 0, b_ax = (ax == 2) ? 1 : 2;
+  const int mx[3] = {L.imx, L.jmx, L.kmx};
+  const long long st[3] = {1, L.sj, L.sk};
+  const int a = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y * blockDim.y + threadIdx.y;
+  const int na = mx[a_ax] - 1, nb = mx[b_ax] - 1;
+  if (a >= na || b >= nb) return;
+  int idx[3]; idx[a_ax] = a + 1; idx[b_ax] = b + 1; idx[ax] = lo ? 1 : mx[ax] - 1;
+  const long long ci = L.idx(idx[0], idx[1], idx[2]);       // interior cell
+  const long long cg = lo ? ci - st[ax] : ci + st[ax];       // ghost cell
+  const long long fs = L.fs;
+  const double* r = rec + 4 * ((long long)b * na + a);
+  const double A = r[0], nx = r[1], ny = r[2], nz = r[3];
+  const double vol = geom[(long long)G_VOL * fs + ci];
+  const double c_x = A * nx / vol, c_y = A * ny / vol, c_z = A * nz / vol;
+  const double sig = lo ? 1.0 : -1.0;
+  const int id = P.bc_id[face - 1];
+  const double ft = P.fixed[F3D_FIX_WALL_TEMP][face - 1];
 #pragma unroll
-      for (int cc = 0; cc < NG; ++cc) {
-        // slot cc holds variable cc+2 of qp(2:n_var): u,v,w,p,[k,omega]; slot 4 (cc == 3) is then overwritten with T
-        const double qI = (cc == 3) ? temp[c] : q[(long long)(cc + 1) * fs + c];
-        const double qG = (cc == 3) ? temp[cg] : q[(long long)(cc + 1) * fs + cg];
-        const double gIx = g[cc][0], gIy = g[cc][1], gIz = g[cc][2];
-        double gx = sig * (qI - qG) * c_x, gy = sig * (qI - qG) * c_y, gz = sig * (qI - qG) * c_z;
-        if (cc == 3 && id == -5 && (ft < 1. && ft >= 0.)) { gx = -gIx; gy = -gIy; gz = -gIz; }   // adiabatic wall
-        const double dot = (gIx * nx) + (gIy * ny) + (gIz * nz);
-        grad[(3 * cc + 0) * fs + cg] = gx + (gIx - dot * nx);
-        grad[(3 * cc + 1) * fs + cg] = gy + (gIy - dot * ny);
-        grad[(3 * cc + 2) * fs + cg] = gz + (gIz - dot * nz);
-      }
-      if (NG == 6) {
-        if (id == -5) { mu3[fs + cg] = -mut_v; mu3[2 * fs + cg] = F1_c; }
-        else if (id == -1 || id == -2 || id == -3 || id == -4 || id == -6 || id == -7 || id == -8 || id == -9) {
-          mu3[fs + cg] = mut_v; mu3[2 * fs + cg] = F1_c;
-        }
-      }
+  for (int cc = 0; cc < NG; ++cc) {
+    // slot cc holds variable cc+2 of qp(2:n_var): u,v,w,p,[k,omega]; slot 4 (cc == 3) is then overwritten with T
+    const double qI = (cc == 3) ? temp[ci] : q[(long long)(cc + 1) * fs + ci];
+    const double qG = (cc == 3) ? temp[cg] : q[(long long)(cc + 1) * fs + cg];
+    const double gIx = grad[(3 * cc + 0) * fs + ci], gIy = grad[(3 * cc + 1) * fs + ci], gIz = grad[(3 * cc + 2) * fs + ci];
+    double gx = sig * (qI - qG) * c_x, gy = sig * (qI - qG) * c_y, gz = sig * (qI - qG) * c_z;
+    if (cc == 3 && id == -5 && (ft < 1. && ft >= 0.)) { gx = -gIx; gy = -gIy; gz = -gIz; }   // adiabatic wall
+    const double dot = (gIx * nx) + (gIy * ny) + (gIz * nz);
+    grad[(3 * cc + 0) * fs + cg] = gx + (gIx - dot * nx);
+    grad[(3 * cc + 1) * fs + cg] = gy + (gIy - dot * ny);
+    grad[(3 * cc + 2) * fs + cg] = gz + (gIz - dot * nz);
+  }
+  if (NG == 6) {
+    if (id == -5) { mu3[fs + cg] = -mu3[fs + ci]; mu3[2 * fs + cg] = mu3[2 * fs + ci]; }
+    else if (id == -1 || id == -2 || id == -3 || id == -4 || id == -6 || id == -7 || id == -8 || id == -9) {
+      mu3[fs + cg] = mu3[fs + ci]; mu3[2 * fs + cg] = mu3[2 * fs + ci];
     }
   }
 }
@@ -167,9 +152,24 @@ int launch_gradients(Ctx* ctx) {
   const Layout& L = ctx->P.L;
   dim3 block(32, 4, 1);
   dim3 grid((L.imx + 1 + 31) / 32, (L.jmx + 1 + 3) / 4, L.kmx + 1);
-  if (ctx->P.sst) k_gradients<6><<<grid, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->err_dev, ctx->gbc, ctx->gbc_off_dev);
-  else k_gradients<4><<<grid, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->err_dev, ctx->gbc, ctx->gbc_off_dev);
+  if (ctx->P.sst) k_gradients<6><<<grid, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->err_dev);
+  else k_gradients<4><<<grid, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->err_dev);
   ctx->launches++;
+  const int mx[3] = {L.imx, L.jmx, L.kmx};
+  int mask = 0, na = 1, nb = 1;
+  for (int face = 1; face <= 6; ++face) {
+    if (ctx->P.bc_id[face - 1] >= 0) continue;   // "if (bc%imin_id < 0)" -- includes -10
+    const int ax = (face - 1) / 2;
+    const int a_ax = (ax == 0) ? 1 : 0, b_ax = (ax == 2) ? 1 : 2;
+    mask |= 1 << (face - 1);
+    na = std::max(na, mx[a_ax] - 1); nb = std::max(nb, mx[b_ax] - 1);
+  }
+  if (mask) {
+    dim3 g2((na + 31) / 32, (nb + 3) / 4, 6);
+    if (ctx->P.sst) k_gradient_bc<6><<<g2, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->gbc, ctx->gbc_off_dev, mask);
+    else k_gradient_bc<4><<<g2, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->gbc, ctx->gbc_off_dev, mask);
+    ctx->launches++;
+  }
   F3D_CUDA(cudaGetLastError());
   return 0;
 }

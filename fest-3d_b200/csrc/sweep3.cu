@@ -51,12 +51,12 @@ struct Sm : RecF<NV, VISC> {
   static constexpr int NF = NV + 3;                       // flux + the lambda / viscous / turbulent face terms of the time step
   static constexpr int PLANE = NV * PSQ + NR * PS;        // doubles per staged plane
   static constexpr int OFF_X = 2 * PLANE;                 // exchange area [2][NF][EX]: hi values, then fluxes (same slot)
-  static constexpr int NPK = NV + 4;                      // cell packet: q[NV], volume, F1, SST sources S_k, S_w
+  static constexpr int NPK = 4;                           // cell packet: volume, F1, SST sources S_k, S_w
   static constexpr int OFF_PK = OFF_X + 2 * NF * EX;      // cell packets [2][NPK][NMAIN], written by the I rows
   static constexpr int OFF_PRIV = OFF_PK + 2 * NPK * NMAIN;   // private slots of the K threads, [field][NMAIN]:
   static constexpr int P_FK = 0;                          //   [3][NF] k-face flux; the face below plane p sits in third p % 3
-  static constexpr int P_HI = 3 * NF;                     //   [NV] value at the high k face of the newest reconstructed cell
-  static constexpr int P_Q2 = P_HI + NV;                  //   [NV] q of plane k+2
+  static constexpr int P_HI = 3 * NF;                     //   [2][NV] value at the high k face of the cell of plane p: half p & 1
+  static constexpr int P_Q2 = P_HI + 2 * NV;              //   [NV] q of plane k+2
   static constexpr int P_VOL = P_Q2 + NV;                 //   [2] volume of planes (p & 1)
   static constexpr int NPRIV = P_VOL + 2;
   static constexpr int OFF_NRM = OFF_PRIV + NPRIV * NMAIN;   // norm partials of the 64 threads that do cell work, [NV+1][64]
@@ -86,10 +86,10 @@ __device__ __forceinline__ void cell_work(const Params& P, const KArgs& a, doubl
   const double* const pk = smem + S::OFF_PK + (kc & 1) * S::NPK * NMAIN + cell;                   // cell packet
   const double* const Flo = smem + S::OFF_PRIV + (S::P_FK + (kc % 3) * NF) * NMAIN + cell;        // k face below the cell
   const double* const Fhi = smem + S::OFF_PRIV + (S::P_FK + ((kc + 1) % 3) * NF) * NMAIN + cell;  // k face above it
-  double qc[NV];
+  double qc[NV];   // the state of the cell: read again from global memory (L2: it was staged two planes ago)
 #pragma unroll
-  for (int v = 0; v < NV; ++v) qc[v] = pk[v * NMAIN];
-  const double volc = pk[NV * NMAIN];
+  for (int v = 0; v < NV; ++v) qc[v] = a.q[v * fs + cc];
+  const double volc = pk[0];
   double res[NV];
   double merr = 0.0;
 #pragma unroll
@@ -118,8 +118,8 @@ __device__ __forceinline__ void cell_work(const Params& P, const KArgs& a, doubl
     if (bad) flag_error(a.err, F3D_ERR_NAN_FLUX, i, j, kc);
   }
   if (SST && VISC) {
-    res[5] = res[5] - pk[(NV + 2) * NMAIN];
-    res[6] = res[6] - pk[(NV + 3) * NMAIN];
+    res[5] = res[5] - pk[2 * NMAIN];
+    res[6] = res[6] - pk[3 * NMAIN];
   }
 
   double dtc = 0.0;
@@ -169,7 +169,7 @@ __device__ __forceinline__ void cell_work(const Params& P, const KArgs& a, doubl
     }
     u1[4] = (u1[4] * P.inv_gm1 + 0.5 * (u1[1] * u1[1] + u1[2] * u1[2] + u1[3] * u1[3])) * rcp64(u1[0]) + 0.;
     if (SST) {
-      const double F1 = VISC ? pk[(NV + 1) * NMAIN] : 0.0;
+      const double F1 = VISC ? pk[NMAIN] : 0.0;
       const double beta = kBeta1 * F1 + (1. - F1) * kBeta2;
       R[5] = R[5] * rcp64(1 + (beta * qc[6] * dtc));
       R[6] = R[6] * rcp64(1 + (2 * beta * qc[6] * dtc));
@@ -234,296 +234,247 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a)
     for (int v = 0; v <= NV; ++v) smem[S::OFF_NRM + v * 64 + tid] = 0.0;
   }
 
-  if (wid >= 2 * TY && wid < 3 * TY) {
-    // ================================ K rows: k reconstruction and k-face flux of their column ================================
-    // The few values that define this thread's role are re-derived from the thread index at the top of every plane (the
-    // empty asm keeps the compiler from hoisting them out of the loop): generation-3 bring-up spilled them to local memory
-    // and 27 % of all stall samples were waits on those reloads (profiles/r01_g3_summary.md).
-    int tx, ty, i, j, s0;
-    bool own, stg;
-    double* priv;
-    auto role = [&]() {
-      int t_ = tid;
-      asm volatile("" : "+r"(t_));
-      tx = t_ & 31; ty = (t_ >> 5) - 2 * TY;
-      i = i0 + tx; j = j0 + ty;
+  // ---- role of this thread.  The values are re-derived from the thread index at the top of every plane (the empty asm keeps
+  // the compiler from hoisting them out of the loop and spilling them: that cost 27 % of all stall samples during bring-up).
+  // All flux warps -- I rows, J rows, K rows, halo warps -- then run ONE instruction stream, parameterised by these values:
+  // separate code copies per direction made the SM fetch-bound (24 % no_instruction stalls, profiles/r01_g3_summary.md).
+  int i, j, s0, d, cell, r_lo, r_hi;
+  bool rec, fac, stg, wr_hi, irow, krow, own;
+  int om, op;                       // I/J: staged-slot offsets of the two neighbours along d
+  int exw, exr;                     // I/J: exchange slots: where the hi value goes; where L is read and the flux written
+  int outer_off, outer_slot;        // halo threads: global offset of the outer neighbour they stage, and its slot
+  int pos, mx;
+  auto role = [&]() {
+    int t_ = tid;
+    asm volatile("" : "+r"(t_));
+    const int ln = t_ & 31, w = t_ >> 5;
+    stg = false; wr_hi = true; irow = false; krow = false; own = false; outer_off = 0; outer_slot = 0; cell = 0; r_lo = 0; r_hi = 0;
+    rec = fac = false; d = 0; i = i0 + ln; j = j0; s0 = PW + 1; om = op = 0; exw = exr = 0;
+    if (w < TY) {                   // I row
+      const int tx = ln, ty = w;
+      d = 0; i = i0 + tx; j = j0 + ty; irow = true; cell = ty * TX + tx;
+      rec = fac = (j <= Ly.jmx - 1) && (i <= Ly.imx);
+      s0 = (ty + 1) * PW + tx + 1; om = -1; op = 1;
+      exw = ty * (TX + 1) + tx + 1; exr = ty * (TX + 1) + tx;
+    } else if (w < 2 * TY) {        // J row
+      const int tx = ln, ty = w - TY;
+      d = 1; i = i0 + tx; j = j0 + ty;
+      rec = fac = (i <= Ly.imx - 1) && (j <= Ly.jmx);
+      s0 = (ty + 1) * PW + tx + 1; om = -PW; op = PW;
+      exw = SLOT_I + (ty + 1) * TX + tx; exr = SLOT_I + ty * TX + tx;
+    } else if (w < 3 * TY) {        // K row: the column of its cell
+      const int tx = ln, ty = w - 2 * TY;
+      d = 2; i = i0 + tx; j = j0 + ty; krow = true; cell = ty * TX + tx;
       own = (i <= Ly.imx - 1) && (j <= Ly.jmx - 1);
       stg = (i <= Ly.imx + 1) && (j <= Ly.jmx + 1);   // ghost cells next to the last faces feed the i/j faces there
-      if (i > Ly.imx + 1) i = Ly.imx + 1;
-      if (j > Ly.jmx + 1) j = Ly.jmx + 1;
+      rec = fac = own && k_active;
       s0 = (ty + 1) * PW + tx + 1;
-      priv = smem + S::OFF_PRIV + ty * TX + tx;
-    };
-    role();
+    } else if (w == W_IH) {         // the two i columns next to the tile: lanes 0..TY-1 low side, TY..2TY-1 high side
+      const int r = ln % TY, side = ln / TY;
+      d = 0; i = (side == 0) ? i0 - 1 : i0 + TX; j = j0 + r;
+      rec = (side < 2) && (j <= Ly.jmx - 1) && (i <= Ly.imx);
+      stg = (side < 2) && (j <= Ly.jmx + 1) && (i <= Ly.imx + 1);
+      fac = rec && side == 1; wr_hi = side == 0;
+      s0 = (r + 1) * PW + (side == 0 ? 0 : TX + 1);
+      outer_slot = PS + (side & 1) * TY + r;
+      outer_off = (side == 0) ? -1 : 1;
+      om = (side == 0) ? outer_slot - s0 : -1; op = (side == 0) ? 1 : outer_slot - s0;
+      exw = r * (TX + 1) + (side == 0 ? 0 : TX); exr = r * (TX + 1) + TX;
+    } else if (w == W_C) {          // cell work only
+      r_lo = ROWS_JL; r_hi = TY;
+    } else {                        // high (W_JH) and low (W_JL) j rows next to the tile
+      const bool high = w == W_JH;
+      d = 1; i = i0 + ln; j = high ? j0 + TY : j0 - 1;
+      rec = (i <= Ly.imx - 1) && (j <= Ly.jmx);
+      stg = (i <= Ly.imx + 1) && (j <= Ly.jmx + 1);
+      fac = rec && high; wr_hi = !high;
+      s0 = (high ? TY + 1 : 0) * PW + ln + 1;
+      outer_slot = PS + 2 * TY + (high ? TX : 0) + ln;
+      outer_off = high ? (int)Ly.sj : -(int)Ly.sj;
+      om = high ? -PW : outer_slot - s0; op = high ? outer_slot - s0 : PW;
+      exw = SLOT_I + (high ? TY * TX : 0) + ln; exr = SLOT_I + TY * TX + ln;
+      if (!high) { r_lo = 0; r_hi = ROWS_JL; }
+    }
+    if (i > Ly.imx + 1) i = Ly.imx + 1;
+    if (j > Ly.jmx + 1) j = Ly.jmx + 1;
+    pos = (d == 0) ? i : j; mx = (d == 0) ? Ly.imx : ((d == 1) ? Ly.jmx : Ly.kmx);
+  };
 
-    auto stage_own = [&](int kk) {   // record of this thread's cell at plane kk -> ring buffer kk & 1
-      if (!stg) return;
-      double* pl = smem + (kk & 1) * S::PLANE;
-      const long long c1 = Ly.idx(i, j, kk);
+  // record of this thread's cell at plane kk -> ring buffer kk & 1 (K rows: their cell; halo threads: their ring cell and the
+  // q of the outer neighbour their reconstruction reads)
+  auto stage_cell = [&](int kk) {
+    if (!stg) return;
+    double* pl = smem + (kk & 1) * S::PLANE;
+    const long long c1 = Ly.idx(i, j, kk);
 #pragma unroll
-      for (int v = 0; v < NV; ++v) cp_async8(pl + v * PSQ + s0, q + v * fs + c1);
-      if (VISC) {
-        double* pr = pl + NV * PSQ;
+    for (int v = 0; v < NV; ++v) cp_async8(pl + v * PSQ + s0, q + v * fs + c1);
+    if (SMQ && rec && !krow) {
 #pragma unroll
-        for (int f = 0; f < S::NGF; ++f) cp_async8(pr + f * PS + s0, a.grad + f * fs + c1);
+      for (int v = 0; v < NV; ++v) cp_async8(pl + v * PSQ + outer_slot, q + v * fs + c1 + outer_off);
+    }
+    if (VISC) {
+      double* pr = pl + NV * PSQ;
 #pragma unroll
-        for (int f = 0; f < S::NMU; ++f) cp_async8(pr + (S::OFF_MU + f) * PS + s0, a.mu + f * fs + c1);
+      for (int f = 0; f < S::NGF; ++f) cp_async8(pr + f * PS + s0, a.grad + f * fs + c1);
 #pragma unroll
-        for (int f = 0; f < 3; ++f) cp_async8(pr + (S::OFF_C + f) * PS + s0, a.geom + (long long)(G_CX + f) * fs + c1);
-      }
-      if (own) cp_async8(priv + (S::P_VOL + (kk & 1)) * NMAIN, vol + c1);
-    };
-    auto prefetch_own = [&](int kk) {   // pull the record of plane kk into L2 one plane before it is staged (q came with the k stencil)
-      if (!stg || !VISC) return;
-      const long long c1 = Ly.idx(i, j, kk);
+      for (int f = 0; f < S::NMU; ++f) cp_async8(pr + (S::OFF_MU + f) * PS + s0, a.mu + f * fs + c1);
 #pragma unroll
-      for (int f = 0; f < S::NGF; ++f) prefetch_l2(a.grad + f * fs + c1);
-#pragma unroll
-      for (int f = 0; f < S::NMU; ++f) prefetch_l2(a.mu + f * fs + c1);
-#pragma unroll
-      for (int f = 0; f < 3; ++f) prefetch_l2(a.geom + (long long)(G_CX + f) * fs + c1);
-    };
+      for (int f = 0; f < 3; ++f) cp_async8(pr + (S::OFF_C + f) * PS + s0, a.geom + (long long)(G_CX + f) * fs + c1);
+    }
+    if (krow && own) cp_async8(smem + S::OFF_PRIV + (S::P_VOL + (kk & 1)) * NMAIN + cell, vol + c1);
+  };
 
+  role();
+  if (krow) {   // K rows: clear the k-face ring, stage plane kb-1, prime the carried value of cell kb-1 (from global memory)
+    double* const priv = smem + S::OFF_PRIV + cell;
 #pragma unroll
     for (int f = 0; f < S::P_Q2; ++f) priv[f * NMAIN] = 0.0;
-    stage_own(kb - 1);
+    stage_cell(kb - 1);
+    if (rec) {
+      const long long c = Ly.idx(i, j, kb - 1);
+      double L[NV], lo_[NV];
+      if (SMQ) {
+        double qm[NV], q0[NV], qp[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) { qm[v] = q[v * fs + c - Ly.sk]; q0[v] = q[v * fs + c]; qp[v] = q[v * fs + c + Ly.sk]; }
+        recon3<NV, INTERP>(P, qm, q0, qp, kb - 1, Ly.kmx, 2, L, lo_);
+      } else {
+        line_cell_values<NV, INTERP>(P, q, vol, c, Ly.sk, kb - 1, Ly.kmx, 2, L, lo_);
+      }
+#pragma unroll
+      for (int v = 0; v < NV; ++v) priv[(S::P_HI + ((kb - 1) & 1) * NV + v) * NMAIN] = L[v];
+    }
     cp_async_wait_all();
+  }
 
-    for (int k = kb - 1; k <= ke; ++k) {
-      bar_all();   // plane k is staged
-      role();
-      if (k <= ke - 1) {   // the k face between planes k and k+1
-        const long long c = Ly.idx(i, j, k);
-        const double* const plA = smem + (k & 1) * S::PLANE;          // plane k
-        const double* const plB = smem + ((k + 1) & 1) * S::PLANE;    // plane k+1 after the staging below
-        // nobody reads plane k-1 any more (the cell work takes what it needs from the cell packets): stage plane k+1 over it
-        stage_own(k + 1);
-        if (own && k_active && SMQ) {
+  for (int k = kb - 1; k <= ke; ++k) {
+    bar_all();   // plane k is staged; the fluxes and cell packets of plane k-1 are complete
+    role();
+    // ---- staging of plane k+1 (nobody reads plane k-1 any more: the cell work takes what it needs from the cell packets) ----
+    if (krow) {
+      if (k <= ke - 1) {
+        stage_cell(k + 1);
+        if (rec && SMQ) {
+          const long long c2 = Ly.idx(i, j, k + 2);
 #pragma unroll
-          for (int v = 0; v < NV; ++v) cp_async8(priv + (S::P_Q2 + v) * NMAIN, q + v * fs + c + 2 * Ly.sk);
+          for (int v = 0; v < NV; ++v) cp_async8(smem + S::OFF_PRIV + (S::P_Q2 + v) * NMAIN + cell, q + v * fs + c2);
         }
-        if (k + 2 <= ke) prefetch_own(k + 2);
-        double kA = 0.0, knx = 0.0, kny = 0.0, knz = 0.0;
-        if (own && k_active) {   // metrics of the k face, requested before the wait so their latency overlaps it
-          const double* __restrict__ gp = a.geom + (long long)G_KA * fs + c + Ly.sk;
-          kA = gp[0]; knx = gp[fs]; kny = gp[2 * fs]; knz = gp[3 * fs];
+        if (VISC && stg && k + 2 <= ke) {   // pull the record of plane k+2 into L2 one plane before it is staged
+          const long long c2 = Ly.idx(i, j, k + 2);
+#pragma unroll
+          for (int f = 0; f < S::NGF; ++f) prefetch_l2(a.grad + f * fs + c2);
+#pragma unroll
+          for (int f = 0; f < S::NMU; ++f) prefetch_l2(a.mu + f * fs + c2);
+#pragma unroll
+          for (int f = 0; f < 3; ++f) prefetch_l2(a.geom + (long long)(G_CX + f) * fs + c2);
         }
-        cp_async_wait_all();
-        if (own && k_active) {
-          const double* const qA = plA + s0;
-          const double* const rA = plA + NV * PSQ + s0;
-          const double* const qB = plB + s0;
-          const double* const rB = plB + NV * PSQ + s0;
-          double L[NV];
-          if (k == kb - 1) {   // prime the carried hi value: cell kb-1 reconstructed along k
-            double lo_[NV];
-            if (SMQ) {
-              double qm[NV], q0[NV], qp[NV];
+      }
+    } else if (k + 1 <= ke - 1) {
+      stage_cell(k + 1);
+    }
+
+    // ---- flux work: one reconstruction and one face per thread, the same code for every direction --------------------------------
+    const bool active = (wid != W_C) && (k <= ke - 1) && (krow || k >= kb);
+    if (active) {
+      // I/J: cell (i,j,k), face below it along d.  K: cell (i,j,k+1), face between planes k and k+1.
+      const int pA = (k & 1) * S::PLANE, pB = ((k + 1) & 1) * S::PLANE;
+      const int nb = (d == 0) ? 1 : PW;
+      const int o_m = krow ? pA + s0 : pA + s0 + om;                 // stencil: low neighbour, cell, high neighbour (q field 0)
+      const int o_0 = krow ? pB + s0 : pA + s0;
+      const int o_p = krow ? S::OFF_PRIV + S::P_Q2 * NMAIN + cell : pA + s0 + op;
+      const int f_p = krow ? NMAIN : PSQ;                            // field stride of the high neighbour
+      const int o_ql = krow ? pA + s0 : pA + s0 - nb;                // the two cells of the face (q field 0; records follow at + NV*PSQ)
+      const int o_qh = o_0;
+      const int f_x = krow ? NMAIN : EX;                             // field stride of the hi / L / flux slots
+      const int o_hw = krow ? S::OFF_PRIV + (S::P_HI + ((k + 1) & 1) * NV) * NMAIN + cell : S::OFF_X + (k & 1) * NF * EX + exw;
+      const int o_lr = krow ? S::OFF_PRIV + (S::P_HI + (k & 1) * NV) * NMAIN + cell : S::OFF_X + (k & 1) * NF * EX + exr;
+      const int o_fw = krow ? S::OFF_PRIV + (S::P_FK + ((k + 1) % 3) * NF) * NMAIN + cell : o_lr;
+      const int cpos = krow ? k + 1 : pos;                           // index of the cell and of the face along d
+      const long long c = Ly.idx(i, j, k);
+      const long long cg = krow ? c + Ly.sk : c;                     // global index of the cell / face
+      double gA_ = 0.0, gnx = 0.0, gny = 0.0, gnz = 0.0;   // face metrics, requested before the reconstruction
+      if (fac) {
+        const double* __restrict__ gp = a.geom + (long long)(G_IA + 4 * d) * fs + cg;
+        gA_ = gp[0]; gnx = gp[fs]; gny = gp[2 * fs]; gnz = gp[3 * fs];
+      }
+      if (krow) cp_async_wait_all();   // the K rows read what they have just staged (plane k+1 of their own column)
+      double lo[NV];
+      if (rec) {
+        double hi[NV];
+        if (SMQ) {
+          double qm[NV], q0[NV], qp[NV];
 #pragma unroll
-              for (int v = 0; v < NV; ++v) { qm[v] = q[v * fs + c - Ly.sk]; q0[v] = qA[v * PSQ]; qp[v] = qB[v * PSQ]; }
-              recon3<NV, INTERP>(P, qm, q0, qp, k, Ly.kmx, 2, L, lo_);
-            } else {
-              line_cell_values<NV, INTERP>(P, q, vol, c, Ly.sk, k, Ly.kmx, 2, L, lo_);
-            }
-          } else {
+          for (int v = 0; v < NV; ++v) { qm[v] = smem[o_m + v * PSQ]; q0[v] = smem[o_0 + v * PSQ]; qp[v] = smem[o_p + v * f_p]; }
+          recon3<NV, INTERP>(P, qm, q0, qp, cpos, mx, d, hi, lo);
+        } else {
+          line_cell_values<NV, INTERP>(P, q, vol, cg, (d == 0) ? 1 : ((d == 1) ? Ly.sj : Ly.sk), cpos, mx, d, hi, lo);
+        }
+        if (wr_hi) {
 #pragma unroll
-            for (int v = 0; v < NV; ++v) L[v] = priv[(S::P_HI + v) * NMAIN];
+          for (int v = 0; v < NV; ++v) smem[o_hw + v * f_x] = hi[v];
+        }
+      }
+      if (!krow) bar_group(1 + d, (d == 0) ? N_IGRP : N_JGRP);
+      if (fac) {
+        double L[NV], F[NV], lam = 0.0, vis = 0.0, tur = 0.0;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) L[v] = smem[o_lr + v * f_x];
+        face_eval<NV, SCHEME, VISC, PS, PSQ>(P, d, smem + o_ql, smem + o_qh, smem + o_ql + NV * PSQ, smem + o_qh + NV * PSQ, gA_, gnx, gny, gnz, cpos, mx, L, lo,
+                                             krow ? flux_on_k : true, need_dt, F, lam, vis, tur);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) smem[o_fw + v * f_x] = F[v];
+        if (need_dt || krow) {
+          smem[o_fw + NV * f_x] = lam;
+          if (VISC) smem[o_fw + (NV + 1) * f_x] = vis;
+          if (VISC && SST) smem[o_fw + (NV + 2) * f_x] = tur;
+        }
+      }
+      if (irow && rec && i <= Ly.imx - 1) {   // I rows: the cell packet of the own cell for next iteration's cell work
+        const double* const rA = smem + o_0 + NV * PSQ;
+        const double* const qA = smem + o_0;
+        double* const pk = smem + S::OFF_PK + (k & 1) * S::NPK * NMAIN + cell;
+        const double volc = smem[S::OFF_PRIV + (S::P_VOL + (k & 1)) * NMAIN + cell];
+        pk[0] = volc;
+        if (SST && VISC) {   // SST source terms (source.f90:214-268)
+          double g[6][3];
+#pragma unroll
+          for (int cc = 0; cc < 6; ++cc) {
+            if (cc == 3) continue;
+            g[cc][0] = rA[(3 * cc + 0) * PS]; g[cc][1] = rA[(3 * cc + 1) * PS]; g[cc][2] = rA[(3 * cc + 2) * PS];
           }
-          double lo[NV];
-          {
-            double hi_n[NV];
-            if (SMQ) {
-              double qm[NV], q0[NV], q2[NV];
-#pragma unroll
-              for (int v = 0; v < NV; ++v) { qm[v] = qA[v * PSQ]; q0[v] = qB[v * PSQ]; q2[v] = priv[(S::P_Q2 + v) * NMAIN]; }
-              recon3<NV, INTERP>(P, qm, q0, q2, k + 1, Ly.kmx, 2, hi_n, lo);
-            } else {
-              line_cell_values<NV, INTERP>(P, q, vol, c + Ly.sk, Ly.sk, k + 1, Ly.kmx, 2, hi_n, lo);
-            }
-#pragma unroll
-            for (int v = 0; v < NV; ++v) priv[(S::P_HI + v) * NMAIN] = hi_n[v];
-          }
-          double F[NV], lam = 0.0, vis = 0.0, tur = 0.0;
-          face_eval<NV, SCHEME, VISC, PS, PSQ>(P, 2, qA, qB, rA, rB, kA, knx, kny, knz, k + 1, Ly.kmx, L, lo, flux_on_k, need_dt, F, lam, vis, tur);
-          double* const Fn = priv + (S::P_FK + ((k + 1) % 3) * NF) * NMAIN;   // read by the cell work of planes k and k+1
-#pragma unroll
-          for (int v = 0; v < NV; ++v) Fn[v * NMAIN] = F[v];
-          Fn[NV * NMAIN] = lam; Fn[(NV + 1) * NMAIN] = vis; Fn[(NV + 2) * NMAIN] = tur;
+          const double mut = rA[(S::OFF_MU + 1) * PS];
+          const double F1c = rA[(S::OFF_MU + 2) * PS];
+          const double density = qA[0], tk = qA[5 * PSQ], tw = qA[6 * PSQ];
+          const double wx = g[2][1] - g[1][2], wy = g[0][2] - g[2][0], wz = g[1][0] - g[0][1];
+          const double vort = sqrt(wx * wx + wy * wy + wz * wz);
+          double CD = 2 * density * kSigmaW2 * (g[4][0] * g[5][0] + g[4][1] * g[5][1] + g[4][2] * g[5][2]) * rcp64(tw);
+          CD = dmax(CD, P.cd_floor);
+          const double gama = P.gama1 * F1c + P.gama2 * (1. - F1c);
+          const double beta = kBeta1 * F1c + kBeta2 * (1. - F1c);
+          const double D_k = kBstar * density * tw * tk;
+          const double D_w = beta * density * (tw * tw);
+          const double divergence = g[0][0] + g[1][1] + g[2][2];
+          double P_k = mut * (vort * vort) - ((2.0 / 3.0) * density * tk * divergence);
+          P_k = dmin(P_k, P.pk_limiter * D_k);
+          const double P_w = (density * gama * rcp64(mut)) * P_k;
+          const double lamda = (1. - F1c) * CD;
+          pk[NMAIN] = F1c;
+          pk[2 * NMAIN] = (P_k - D_k) * volc;
+          pk[3 * NMAIN] = (P_w - D_w + lamda) * volc;
         }
       }
     }
-  } else {
-    // ============== I rows, J rows, the three halo warps, and the cell work (low-j halo warp and warp W_C) ==============
-    int i, j, s0, d, cell, r_lo, r_hi;
-    bool rec, fac, stg, wr_hi, irow;
-    int om, op;                       // staged-slot offsets of the two neighbours along d
-    int exw, exr;                     // exchange slots: where the hi value goes; where L is read and the flux written
-    int outer_off;                    // halo threads: global offset of the outer neighbour they stage, and its slot
-    int outer_slot;
-    int pos, mx, nb;
-    auto role = [&]() {               // re-derived every plane, see the K rows above
-      int t_ = tid;
-      asm volatile("" : "+r"(t_));
-      const int ln = t_ & 31, w = t_ >> 5;
-      stg = false; wr_hi = true; irow = false; outer_off = 0; outer_slot = 0; cell = 0; r_lo = 0; r_hi = 0;
-      rec = fac = false; d = 0; i = i0 + ln; j = j0; s0 = PW + 1; om = op = 0; exw = exr = 0;
-      if (w < TY) {                   // I row
-        const int tx = ln, ty = w;
-        d = 0; i = i0 + tx; j = j0 + ty; irow = true; cell = ty * TX + tx;
-        rec = fac = (j <= Ly.jmx - 1) && (i <= Ly.imx);
-        s0 = (ty + 1) * PW + tx + 1; om = -1; op = 1;
-        exw = ty * (TX + 1) + tx + 1; exr = ty * (TX + 1) + tx;
-      } else if (w < 2 * TY) {        // J row
-        const int tx = ln, ty = w - TY;
-        d = 1; i = i0 + tx; j = j0 + ty;
-        rec = fac = (i <= Ly.imx - 1) && (j <= Ly.jmx);
-        s0 = (ty + 1) * PW + tx + 1; om = -PW; op = PW;
-        exw = SLOT_I + (ty + 1) * TX + tx; exr = SLOT_I + ty * TX + tx;
-      } else if (w == W_IH) {         // the two i columns next to the tile: lanes 0..TY-1 low side, TY..2TY-1 high side
-        const int r = ln % TY, side = ln / TY;
-        d = 0; i = (side == 0) ? i0 - 1 : i0 + TX; j = j0 + r;
-        rec = (side < 2) && (j <= Ly.jmx - 1) && (i <= Ly.imx);
-        stg = (side < 2) && (j <= Ly.jmx + 1) && (i <= Ly.imx + 1);
-        fac = rec && side == 1; wr_hi = side == 0;
-        s0 = (r + 1) * PW + (side == 0 ? 0 : TX + 1);
-        outer_slot = PS + (side & 1) * TY + r;
-        outer_off = (side == 0) ? -1 : 1;
-        om = (side == 0) ? outer_slot - s0 : -1; op = (side == 0) ? 1 : outer_slot - s0;
-        exw = r * (TX + 1) + (side == 0 ? 0 : TX); exr = r * (TX + 1) + TX;
-      } else if (w == W_C) {          // cell work only
-        r_lo = ROWS_JL; r_hi = TY;
-      } else {                        // high (W_JH) and low (W_JL) j rows next to the tile
-        const bool high = w == W_JH;
-        d = 1; i = i0 + ln; j = high ? j0 + TY : j0 - 1;
-        rec = (i <= Ly.imx - 1) && (j <= Ly.jmx);
-        stg = (i <= Ly.imx + 1) && (j <= Ly.jmx + 1);
-        fac = rec && high; wr_hi = !high;
-        s0 = (high ? TY + 1 : 0) * PW + ln + 1;
-        outer_slot = PS + 2 * TY + (high ? TX : 0) + ln;
-        outer_off = high ? (int)Ly.sj : -(int)Ly.sj;
-        om = high ? -PW : outer_slot - s0; op = high ? outer_slot - s0 : PW;
-        exw = SLOT_I + (high ? TY * TX : 0) + ln; exr = SLOT_I + TY * TX + ln;
-        if (!high) { r_lo = 0; r_hi = ROWS_JL; }
-      }
-      if (i > Ly.imx + 1) i = Ly.imx + 1;
-      if (j > Ly.jmx + 1) j = Ly.jmx + 1;
-      pos = (d == 0) ? i : j; mx = (d == 0) ? Ly.imx : Ly.jmx;
-      nb = (d == 0) ? 1 : PW;
-    };
-
-    auto stage_ring = [&](int kk) {   // halo threads: their ring cell (+ the outer neighbour's q) of plane kk
-      if (!stg) return;
-      double* pl = smem + (kk & 1) * S::PLANE;
-      const long long c1 = Ly.idx(i, j, kk);
-#pragma unroll
-      for (int v = 0; v < NV; ++v) cp_async8(pl + v * PSQ + s0, q + v * fs + c1);
-      if (SMQ && rec) {
-#pragma unroll
-        for (int v = 0; v < NV; ++v) cp_async8(pl + v * PSQ + outer_slot, q + v * fs + c1 + outer_off);
-      }
-      if (VISC) {
-        double* pr = pl + NV * PSQ;
-#pragma unroll
-        for (int f = 0; f < S::NGF; ++f) cp_async8(pr + f * PS + s0, a.grad + f * fs + c1);
-#pragma unroll
-        for (int f = 0; f < S::NMU; ++f) cp_async8(pr + (S::OFF_MU + f) * PS + s0, a.mu + f * fs + c1);
-#pragma unroll
-        for (int f = 0; f < 3; ++f) cp_async8(pr + (S::OFF_C + f) * PS + s0, a.geom + (long long)(G_CX + f) * fs + c1);
-      }
-    };
-
-    for (int k = kb - 1; k <= ke; ++k) {
-      bar_all();
-      role();
-      if (k + 1 <= ke - 1) stage_ring(k + 1);
-      if (wid != W_C && k >= kb && k <= ke - 1) {
-        const long long c = Ly.idx(i, j, k);
-        double* const pl = smem + (k & 1) * S::PLANE;
-        const double* const qA = pl + s0;
-        const double* const rA = pl + NV * PSQ + s0;
-        double* const xH = smem + S::OFF_X + (k & 1) * NF * EX;
-        double gA_ = 0.0, gnx = 0.0, gny = 0.0, gnz = 0.0;   // face metrics, requested before the reconstruction
-        if (fac) {
-          const double* __restrict__ gp = a.geom + (long long)(G_IA + 4 * d) * fs + c;
-          gA_ = gp[0]; gnx = gp[fs]; gny = gp[2 * fs]; gnz = gp[3 * fs];
-        }
-        double lo[NV];
-        if (rec) {
-          double hi[NV];
-          if (SMQ) {
-            double qm[NV], q0[NV], qp[NV];
-#pragma unroll
-            for (int v = 0; v < NV; ++v) { qm[v] = qA[v * PSQ + om]; q0[v] = qA[v * PSQ]; qp[v] = qA[v * PSQ + op]; }
-            recon3<NV, INTERP>(P, qm, q0, qp, pos, mx, d, hi, lo);
-          } else {
-            line_cell_values<NV, INTERP>(P, q, vol, c, (d == 0) ? 1 : Ly.sj, pos, mx, d, hi, lo);
-          }
-          if (wr_hi) {
-#pragma unroll
-            for (int v = 0; v < NV; ++v) xH[v * EX + exw] = hi[v];
-          }
-        }
-        bar_group(1 + d, (d == 0) ? N_IGRP : N_JGRP);
-        if (fac) {
-          double L[NV], F[NV], lam = 0.0, vis = 0.0, tur = 0.0;
-#pragma unroll
-          for (int v = 0; v < NV; ++v) L[v] = xH[v * EX + exr];
-          face_eval<NV, SCHEME, VISC, PS, PSQ>(P, d, qA - nb, qA, rA - nb, rA, gA_, gnx, gny, gnz, pos, mx, L, lo, true, need_dt, F, lam, vis, tur);
-#pragma unroll
-          for (int v = 0; v < NV; ++v) xH[v * EX + exr] = F[v];
-          if (need_dt) {
-            xH[NV * EX + exr] = lam;
-            if (VISC) xH[(NV + 1) * EX + exr] = vis;
-            if (VISC && SST) xH[(NV + 2) * EX + exr] = tur;
-          }
-        }
-        if (irow && rec && i <= Ly.imx - 1) {   // I rows: the cell packet of the own cell for next iteration's cell work
-          double* const pk = smem + S::OFF_PK + (k & 1) * S::NPK * NMAIN + cell;
-          const double volc = smem[S::OFF_PRIV + (S::P_VOL + (k & 1)) * NMAIN + cell];
-#pragma unroll
-          for (int v = 0; v < NV; ++v) pk[v * NMAIN] = qA[v * PSQ];
-          pk[NV * NMAIN] = volc;
-          if (SST && VISC) {   // SST source terms (source.f90:214-268)
-            double g[6][3];
-#pragma unroll
-            for (int cc = 0; cc < 6; ++cc) {
-              if (cc == 3) continue;
-              g[cc][0] = rA[(3 * cc + 0) * PS]; g[cc][1] = rA[(3 * cc + 1) * PS]; g[cc][2] = rA[(3 * cc + 2) * PS];
-            }
-            const double mut = rA[(S::OFF_MU + 1) * PS];
-            const double F1c = rA[(S::OFF_MU + 2) * PS];
-            const double density = qA[0], tk = qA[5 * PSQ], tw = qA[6 * PSQ];
-            const double wx = g[2][1] - g[1][2], wy = g[0][2] - g[2][0], wz = g[1][0] - g[0][1];
-            const double vort = sqrt(wx * wx + wy * wy + wz * wz);
-            double CD = 2 * density * kSigmaW2 * (g[4][0] * g[5][0] + g[4][1] * g[5][1] + g[4][2] * g[5][2]) * rcp64(tw);
-            CD = dmax(CD, P.cd_floor);
-            const double gama = P.gama1 * F1c + P.gama2 * (1. - F1c);
-            const double beta = kBeta1 * F1c + kBeta2 * (1. - F1c);
-            const double D_k = kBstar * density * tw * tk;
-            const double D_w = beta * density * (tw * tw);
-            const double divergence = g[0][0] + g[1][1] + g[2][2];
-            double P_k = mut * (vort * vort) - ((2.0 / 3.0) * density * tk * divergence);
-            P_k = dmin(P_k, P.pk_limiter * D_k);
-            const double P_w = (density * gama * rcp64(mut)) * P_k;
-            const double lamda = (1. - F1c) * CD;
-            pk[(NV + 1) * NMAIN] = F1c;
-            pk[(NV + 2) * NMAIN] = (P_k - D_k) * volc;
-            pk[(NV + 3) * NMAIN] = (P_w - D_w + lamda) * volc;
-          }
-        }
-      }
-      // ---- cell work of plane k-1 (low-j halo warp: rows 0..ROWS_JL-1, W_C: the rest) ------------------------------------------
-      if (r_hi > r_lo && k - 1 >= kb) {
-        const int ic = i0 + lane;
+    // ---- cell work of plane k-1 (low-j halo warp: rows 0..ROWS_JL-1, W_C: the rest) --------------------------------------------
+    if (r_hi > r_lo && k - 1 >= kb) {
+      const int ic = i0 + lane;
 #pragma unroll 1
-        for (int r = r_lo; r < r_hi; ++r) {
-          const int jc = j0 + r;
-          if (ic <= Ly.imx - 1 && jc <= Ly.jmx - 1)
-            cell_work<NV, VISC>(P, a, smem, lane, r, ic, jc, k - 1, need_dt, k_active, smem + S::OFF_NRM + (wid == W_C ? 32 : 0) + lane);
-        }
+      for (int r = r_lo; r < r_hi; ++r) {
+        const int jc = j0 + r;
+        if (ic <= Ly.imx - 1 && jc <= Ly.jmx - 1)
+          cell_work<NV, VISC>(P, a, smem, lane, r, ic, jc, k - 1, need_dt, k_active, smem + S::OFF_NRM + (wid == W_C ? 32 : 0) + lane);
       }
-      cp_async_wait_all();
     }
+    cp_async_wait_all();
   }
 
   if (a.want_norms) {   // per-CTA partial: warp shuffle inside the two warps that did the cell work, then across them
