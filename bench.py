@@ -264,7 +264,7 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(world, args),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "k_sweep<7,MUSCL,AUSM,viscous> (fused reconstruction + flux + source + dt + update)", "kernel_ms": k_avg_ms,
+                         "kernel": "g3::k_sweep3<7,MUSCL,AUSM,viscous> (fused reconstruction + flux + source + dt + update, generation %s)" % os.environ.get("F3D_SWEEP_GEN", "3"), "kernel_ms": k_avg_ms,
                          "kernel_share_of_step": k_ms / ms, "algorithmic_bytes_per_cell_update": bpc, "peak_source": peak_src},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes + nvp1 * 8,
                     "steps": e2e_steps},
