@@ -59,13 +59,14 @@ extern "C" int fest3d_gpu_create(Fest3dGpuCtx** out, const Fest3dGpuConfig* cfg,
   }
   // scope check: only what this path implements; everything else is an explicit error, never a silent fallback
   const bool sst = cfg->turbulence == F3D_TURB_SST || cfg->turbulence == F3D_TURB_SST2003;
-  if (cfg->turbulence != F3D_TURB_NONE && !sst) return F3D_ERR_UNSUPPORTED;
+  const bool sa = cfg->turbulence == F3D_TURB_SA;   // 'saBC' has no case in the reference's source dispatcher (source.f90:119-153)
+  if (cfg->turbulence != F3D_TURB_NONE && !sst && !sa) return F3D_ERR_UNSUPPORTED;
   if (cfg->transition != F3D_TRANS_NONE) return F3D_ERR_UNSUPPORTED;
   if (cfg->time_accuracy >= F3D_T_IMPLICIT || cfg->time_accuracy < 0) return F3D_ERR_UNSUPPORTED;
   if (cfg->pb_switch[0] || cfg->pb_switch[1] || cfg->pb_switch[2]) return F3D_ERR_UNSUPPORTED;
   if (cfg->scheme < 0 || cfg->scheme > F3D_SLAU || cfg->interpolant < 0 || cfg->interpolant > F3D_WENO_NM) return F3D_ERR_ARGUMENT;
-  if (cfg->n_var != (sst ? 7 : 5)) return F3D_ERR_ARGUMENT;
-  if (sst && cfg->mu_ref == 0.0) return F3D_ERR_UNSUPPORTED;
+  if (cfg->n_var != (sst ? 7 : (sa ? 6 : 5))) return F3D_ERR_ARGUMENT;
+  if ((sst || sa) && cfg->mu_ref == 0.0) return F3D_ERR_UNSUPPORTED;
   if (cfg->imx < 2 || cfg->jmx < 2 || cfg->kmx < 2) return F3D_ERR_ARGUMENT;
 
   Fest3dGpuCtx* ctx = new Fest3dGpuCtx();
@@ -75,7 +76,7 @@ extern "C" int fest3d_gpu_create(Fest3dGpuCtx** out, const Fest3dGpuConfig* cfg,
   Params& P = ctx->P;
   memset(&P, 0, sizeof(P));
   Layout& L = P.L;
-  L.imx = cfg->imx; L.jmx = cfg->jmx; L.kmx = cfg->kmx; L.nv = cfg->n_var; L.ng = sst ? 6 : 4;
+  L.imx = cfg->imx; L.jmx = cfg->jmx; L.kmx = cfg->kmx; L.nv = cfg->n_var; L.ng = sst ? 6 : (sa ? 5 : 4);
   L.pi = ((cfg->imx + 6 + 15) / 16) * 16; L.pj = cfg->jmx + 6; L.pk = cfg->kmx + 6;
   L.sj = L.pi; L.sk = (long long)L.pi * L.pj;
   L.base = 13 + 2 + 2 * L.sj + 2 * L.sk;
@@ -96,13 +97,13 @@ extern "C" int fest3d_gpu_create(Fest3dGpuCtx** out, const Fest3dGpuConfig* cfg,
   for (int d = 0; d < 3; ++d) { P.zlo[d] = wallish(P.bc_id[2 * d]) ? 0.0 : 1.0; P.zhi[d] = wallish(P.bc_id[2 * d + 1]) ? 0.0 : 1.0; }
   P.c2 = 1 + cfg->accur; P.c3 = 0.5 * cfg->accur; P.c1 = P.c2 - P.c3;
   P.current_iter = 1;
-  P.viscous = cfg->mu_ref != 0.0; P.sst = sst ? 1 : 0;
+  P.viscous = cfg->mu_ref != 0.0; P.sst = sst ? 1 : 0; P.sa = sa ? 1 : 0;
   P.CFL = cfg->CFL; P.global_time_step = cfg->global_time_step;
   P.gm = cfg->gm; P.R_gas = cfg->R_gas; P.mu_ref = cfg->mu_ref; P.T_ref = cfg->T_ref; P.Sutherland_temp = cfg->Sutherland_temp;
   P.Pr = cfg->Pr; P.tPr = cfg->tPr;
   P.inv_Pr = 1.0 / cfg->Pr; P.inv_tPr = 1.0 / cfg->tPr; P.inv_gm1 = 1.0 / (cfg->gm - 1.0);
   P.density_inf = cfg->density_inf; P.x_speed_inf = cfg->x_speed_inf; P.y_speed_inf = cfg->y_speed_inf; P.z_speed_inf = cfg->z_speed_inf;
-  P.pressure_inf = cfg->pressure_inf; P.tk_inf = cfg->tk_inf; P.tw_inf = cfg->tw_inf; P.MInf = cfg->MInf;
+  P.pressure_inf = cfg->pressure_inf; P.tk_inf = cfg->tk_inf; P.tw_inf = cfg->tw_inf; P.tv_inf = cfg->tv_inf; P.MInf = cfg->MInf;
   const double kappa = 0.41;
   if (cfg->turbulence == F3D_TURB_SST2003) {   // source.f90:205-211, viscosity.f90:243,251
     P.gama1 = 5.0 / 9.0; P.gama2 = 0.44; P.cd_floor = 1.0e-10; P.mut_floor = 1.0e-10; P.pk_limiter = 10;
@@ -118,6 +119,7 @@ extern "C" int fest3d_gpu_create(Fest3dGpuCtx** out, const Fest3dGpuConfig* cfg,
   sc[2] = sc[3] = sc[4] = cfg->density_inf * cfg->vel_mag * cfg->vel_mag;
   sc[5] = (0.5 * cfg->density_inf * (cfg->vel_mag * cfg->vel_mag * cfg->vel_mag) + ((cfg->gm / (cfg->gm - 1.)) * cfg->pressure_inf));
   if (sst) { sc[6] = cfg->density_inf * cfg->vel_mag * cfg->tk_inf; sc[7] = cfg->density_inf * cfg->vel_mag * cfg->tw_inf; }
+  if (sa) sc[6] = cfg->density_inf * cfg->vel_mag * cfg->tv_inf;   // resnorm.f90:157-158
 
   F3D_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
   ctx->stream = ctx->own_stream;
@@ -229,7 +231,7 @@ static int copy_cells(Fest3dGpuCtx* ctx, double* dev_field, double* host, int nf
 extern "C" int fest3d_gpu_set_geometry(Fest3dGpuCtx* ctx, const double* cells, const double* Ifaces, const double* Jfaces,
                                        const double* Kfaces, const double* dist) {
   if (!ctx || !cells || !Ifaces || !Jfaces || !Kfaces) return fail(ctx, F3D_ERR_ARGUMENT);
-  if (ctx->P.sst && !dist) return fail(ctx, F3D_ERR_ARGUMENT);
+  if ((ctx->P.sst || ctx->P.sa) && !dist) return fail(ctx, F3D_ERR_ARGUMENT);
   F3D_CUDA(cudaSetDevice(ctx->device));
   const Layout& L = ctx->P.L;
   const long long fs = L.fs;

@@ -96,6 +96,7 @@ __global__ void k_bc_face(const Params P, double* __restrict__ q, const double* 
   const long long fs = P.L.fs;
   const int id = P.bc_id[face - 1];
   const bool sst = P.sst != 0;
+  const bool sa = P.sa != 0;   // the SA variable (field 5) follows the pattern of tk on every face (bc_primitive.f90:246 ... 543)
   double* rho = q; double* u = q + fs; double* v = q + 2 * fs; double* w = q + 3 * fs; double* p = q + 4 * fs;
   double* tk = q + 5 * fs; double* tw = q + 6 * fs;
   const double(*fx)[6] = P.fixed;
@@ -107,17 +108,20 @@ __global__ void k_bc_face(const Params P, double* __restrict__ q, const double* 
         fix3(rho, fr, o, fx[F3D_FIX_DENSITY][fi]); fix3(u, fr, o, fx[F3D_FIX_X_SPEED][fi]); fix3(v, fr, o, fx[F3D_FIX_Y_SPEED][fi]);
         fix3(w, fr, o, fx[F3D_FIX_Z_SPEED][fi]); fix3(p, fr, o, fx[F3D_FIX_PRESSURE][fi]);
         if (sst) { fix3(tk, fr, o, fx[F3D_FIX_TK][fi]); fix3(tw, fr, o, fx[F3D_FIX_TW][fi]); }
+        if (sa) fix3(tk, fr, o, fx[F3D_FIX_TV][fi]);
       }
       break;
     case -2: case -7:   // supersonic_outlet, pole: everything flat
       copy3_flat(rho, fr, o); copy3_flat(u, fr, o); copy3_flat(v, fr, o); copy3_flat(w, fr, o); copy3_flat(p, fr, o);
       if (sst) { copy3_flat(tk, fr, o); copy3_flat(tw, fr, o); }
+      if (sa) copy3_flat(tk, fr, o);
       break;
     case -3:   // subsonic_inlet
       if (P.current_iter <= 2) {
         fix3(rho, fr, o, fx[F3D_FIX_DENSITY][fi]); fix3(u, fr, o, fx[F3D_FIX_X_SPEED][fi]); fix3(v, fr, o, fx[F3D_FIX_Y_SPEED][fi]);
         fix3(w, fr, o, fx[F3D_FIX_Z_SPEED][fi]);
         if (sst) { fix3(tk, fr, o, fx[F3D_FIX_TK][fi]); fix3(tw, fr, o, fx[F3D_FIX_TW][fi]); }
+        if (sa) fix3(tk, fr, o, fx[F3D_FIX_TV][fi]);
       }
       copy3_flat(p, fr, o);
       break;
@@ -125,6 +129,7 @@ __global__ void k_bc_face(const Params P, double* __restrict__ q, const double* 
       copy3_flat(rho, fr, o); copy3_flat(u, fr, o); copy3_flat(v, fr, o); copy3_flat(w, fr, o);
       if (P.current_iter <= 2) fix3(p, fr, o, fx[F3D_FIX_PRESSURE][fi]);
       if (sst) { copy3_flat(tk, fr, o); copy3_flat(tw, fr, o); }
+      if (sa) copy3_flat(tk, fr, o);
       break;
     case -5: {  // wall: pressure symm, temp_based_density, no_slip (+ omega at wall)
       copy3_symm(p, fr, o, P.c1, P.c2, P.c3);
@@ -141,6 +146,7 @@ __global__ void k_bc_face(const Params P, double* __restrict__ q, const double* 
         copy3_symm(rho, fr, o, P.c1, P.c2, P.c3);
       }
       copy3_anti(u, fr, o); copy3_anti(v, fr, o); copy3_anti(w, fr, o);
+      if (sa) copy3_anti(tk, fr, o);
       if (sst) {
         copy3_anti(tk, fr, o);
         const double* dist = geom + (long long)G_DIST * fs;
@@ -157,6 +163,7 @@ __global__ void k_bc_face(const Params P, double* __restrict__ q, const double* 
     case -6: {  // slip_wall
       copy3_symm(rho, fr, o, P.c1, P.c2, P.c3); copy3_symm(p, fr, o, P.c1, P.c2, P.c3);
       if (sst) { copy3_symm(tk, fr, o, P.c1, P.c2, P.c3); copy3_symm(tw, fr, o, P.c1, P.c2, P.c3); }
+      if (sa) copy3_symm(tk, fr, o, P.c1, P.c2, P.c3);
       // flow_tangency: dot with this direction's face normal, reflection with the I-face normal at the same index
       const double* gd = geom + (long long)(G_IA + 4 * ax) * fs;
       const double* gi = geom + (long long)G_IA * fs;
@@ -191,14 +198,15 @@ __global__ void k_bc_face(const Params P, double* __restrict__ q, const double* 
         rho[g] = pow(Cb * Cb / (P.gm * s), 1. / (P.gm - 1.));
         p[g] = (rho[g] * Cb * Cb / P.gm);
       }
-      if (sst) {
+      if (sst || sa) {
         // The reference calls whole-face copy3("flat") / fix() from inside the per-cell loop (:700-757); the ghost k,omega
         // of the whole face therefore end up decided by the LAST cell of the loop: outflow there -> flat copy, else fixed.
         const long long olast = (long long)(fr.na - 1) * fr.sa + (long long)(fr.nb - 1) * fr.sb;
         double Ub2, Cb2, a2, b2, x2, y2, z2;
         far_field_state(P, q, gn, fr, olast, Ub2, Cb2, a2, b2, x2, y2, z2);
-        if (Ub2 > 0.) { copy3_flat(tk, fr, o); copy3_flat(tw, fr, o); }
-        else { fix3(tk, fr, o, fx[F3D_FIX_TK][fi]); fix3(tw, fr, o, fx[F3D_FIX_TW][fi]); }
+        if (Ub2 > 0.) { copy3_flat(tk, fr, o); if (sst) copy3_flat(tw, fr, o); }
+        else if (sst) { fix3(tk, fr, o, fx[F3D_FIX_TK][fi]); fix3(tw, fr, o, fx[F3D_FIX_TW][fi]); }
+        else fix3(tk, fr, o, fx[F3D_FIX_TV][fi]);
       }
       break;
     }
@@ -218,12 +226,13 @@ __global__ void k_bc_face(const Params P, double* __restrict__ q, const double* 
       const double Mb = sqrt(u[m] * u[m] + v[m] * v[m] + w[m] * w[m]) / Cb;
       p[g] = fx[F3D_FIX_TPRESSURE][fi] / pow((1 + 0.5 * (P.gm - 1.) * Mb * Mb), P.gm / (P.gm - 1.));
       rho[g] = P.gm * p[g] / (Cb * Cb);
-      if (sst) {   // whole-face copy3("flat") / fix() from inside the per-cell loop: the LAST cell of the loop decides
+      if (sst || sa) {   // whole-face copy3("flat") / fix() from inside the per-cell loop: the LAST cell of the loop decides
         const long long olast = (long long)(fr.na - 1) * fr.sa + (long long)(fr.nb - 1) * fr.sb;
         double Ub2, Cb2, a2, b2, x2, y2, z2;
         far_field_state(P, q, gn, fr, olast, Ub2, Cb2, a2, b2, x2, y2, z2);
-        if (Ub2 > 0.) { copy3_flat(tk, fr, o); copy3_flat(tw, fr, o); }
-        else { fix3(tk, fr, o, fx[F3D_FIX_TK][fi]); fix3(tw, fr, o, fx[F3D_FIX_TW][fi]); }
+        if (Ub2 > 0.) { copy3_flat(tk, fr, o); if (sst) copy3_flat(tw, fr, o); }
+        else if (sst) { fix3(tk, fr, o, fx[F3D_FIX_TK][fi]); fix3(tw, fr, o, fx[F3D_FIX_TW][fi]); }
+        else fix3(tk, fr, o, fx[F3D_FIX_TV][fi]);
       }
       break;
     }

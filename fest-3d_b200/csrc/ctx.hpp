@@ -13,7 +13,7 @@
 namespace f3d {
 
 struct Layout {
-  int imx, jmx, kmx, nv, ng;        // ng = number of gradient components (4 or 6)
+  int imx, jmx, kmx, nv, ng;        // ng = number of gradient components (4, 5 with sa, 6 with sst)
   int pi, pj, pk;                   // padded extents
   long long sj, sk, base, fs;       // strides, index of cell (0,0,0), doubles per field
   __host__ __device__ inline long long idx(int i, int j, int k) const { return base + i + sj * j + sk * (long long)k; }
@@ -32,13 +32,13 @@ struct Params {
   int farlike[6];         // 1 when id is -8 or -9 (face state = ghost value)
   int ppm_flag;           // boundary re-reconstruction active (ppm / weno / weno_NM or a pole face)
   int current_iter;
-  int viscous, sst;
+  int viscous, sst, sa;   // sa: Spalart-Allmaras (n_var 6)
   double zlo[3], zhi[3];  // make_{F,G,H}_flux_zero at the first / last face of each direction (bc.f90:53-66)
   double c1, c2, c3;
   double CFL, global_time_step;
   double gm, R_gas, mu_ref, T_ref, Sutherland_temp, Pr, tPr;
   double inv_Pr, inv_tPr, inv_gm1;   // reciprocals of Pr, tPr, gm-1
-  double density_inf, x_speed_inf, y_speed_inf, z_speed_inf, pressure_inf, tk_inf, tw_inf, MInf;
+  double density_inf, x_speed_inf, y_speed_inf, z_speed_inf, pressure_inf, tk_inf, tw_inf, tv_inf, MInf;
   double gama1, gama2, cd_floor, mut_floor, pk_limiter;
   double fixed[F3D_NFIX][6];
   double res_scale[8];    // Res_scale(1:n_var) (resnorm.f90:136-150)

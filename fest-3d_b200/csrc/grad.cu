@@ -71,6 +71,12 @@ __global__ void __launch_bounds__(128, 5) k_gradients(const Params P, const doub
     mu3[c] = mu;
     if (isnan(mu)) atomicOr(err, F3D_ERR_NAN_VISCOSITY);
   }
+  if (NG == 5) {   // Spalart-Allmaras: mu_t = rho*tv*fv1 (viscosity.f90:149-163)
+    const double tv = q[5 * fs + c], density = q[c];
+    const double xi = tv * density / mu;
+    const double fv1 = (pow3(xi)) / ((pow3(xi)) + (pow3(kCv1)));
+    mu3[fs + c] = density * tv * fv1;
+  }
   if (NG == 6) {
     const double density = q[c], tk = q[5 * fs + c], tw = q[6 * fs + c];
     const double d = geom[(long long)G_DIST * fs + c];
@@ -140,6 +146,10 @@ __global__ void k_gradient_bc(const Params P, const double* __restrict__ q, cons
     grad[(3 * cc + 1) * fs + cg] = gy + (gIy - dot * ny);
     grad[(3 * cc + 2) * fs + cg] = gz + (gIz - dot * nz);
   }
+  if (NG == 5) {   // viscosity.f90:165-212
+    if (id == -5) mu3[fs + cg] = -mu3[fs + ci];
+    else if (id == -1 || id == -2 || id == -3 || id == -4 || id == -6 || id == -7 || id == -8 || id == -9) mu3[fs + cg] = mu3[fs + ci];
+  }
   if (NG == 6) {
     if (id == -5) { mu3[fs + cg] = -mu3[fs + ci]; mu3[2 * fs + cg] = mu3[2 * fs + ci]; }
     else if (id == -1 || id == -2 || id == -3 || id == -4 || id == -6 || id == -7 || id == -8 || id == -9) {
@@ -152,7 +162,8 @@ int launch_gradients(Ctx* ctx) {
   const Layout& L = ctx->P.L;
   dim3 block(32, 4, 1);
   dim3 grid((L.imx + 1 + 31) / 32, (L.jmx + 1 + 3) / 4, L.kmx + 1);
-  if (ctx->P.sst) k_gradients<6><<<grid, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->err_dev);
+  if (ctx->P.sa) k_gradients<5><<<grid, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->err_dev);
+  else if (ctx->P.sst) k_gradients<6><<<grid, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->err_dev);
   else k_gradients<4><<<grid, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->err_dev);
   ctx->launches++;
   const int mx[3] = {L.imx, L.jmx, L.kmx};
@@ -166,7 +177,8 @@ int launch_gradients(Ctx* ctx) {
   }
   if (mask) {
     dim3 g2((na + 31) / 32, (nb + 3) / 4, 6);
-    if (ctx->P.sst) k_gradient_bc<6><<<g2, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->gbc, ctx->gbc_off_dev, mask);
+    if (ctx->P.sa) k_gradient_bc<5><<<g2, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->gbc, ctx->gbc_off_dev, mask);
+    else if (ctx->P.sst) k_gradient_bc<6><<<g2, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->gbc, ctx->gbc_off_dev, mask);
     else k_gradient_bc<4><<<g2, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->gbc, ctx->gbc_off_dev, mask);
     ctx->launches++;
   }

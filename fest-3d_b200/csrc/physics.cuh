@@ -10,6 +10,16 @@ namespace f3d {
 // SST closure constants (src/global/global_sst.f90:6-16)
 __device__ constexpr double kSigmaK1 = 0.85, kSigmaK2 = 1.0, kSigmaW1 = 0.5, kSigmaW2 = 0.856;
 __device__ constexpr double kBeta1 = 0.075, kBeta2 = 0.0828, kBstar = 0.09, kA1 = 0.31;
+// SA closure constants (src/global/global_sa.f90:6-19)
+__device__ constexpr double kCb1 = 0.1355, kCb2 = 0.6220, kCw2 = 0.3, kCw3 = 2.0, kCv1 = 7.1, kSigmaSA = 2. / 3., kKappaSA = 0.41;
+__device__ constexpr double kCw1 = (kCb1 / (kKappaSA * kKappaSA)) + ((1 + kCb2) / kSigmaSA);
+__device__ __forceinline__ double pow3(double x) { return x * x * x; }
+__device__ __forceinline__ double pow6(double x) { const double x2 = x * x; return x2 * x2 * x2; }
+// SA wall function fw = g*((1+cw3^6)/(g^6+cw3^6))^(1/6) with g = r + cw2 (r^6 - r)   (source.f90:958-960, update.f90:416-418)
+__device__ __forceinline__ double sa_fw(double r) {
+  const double g = r + kCw2 * (pow6(r) - r);
+  return g * pow((1.0 + pow6(kCw3)) / (pow6(g) + pow6(kCw3)), (1.0 / 6.0));
+}
 
 __device__ __forceinline__ double sgn1(double x) { return copysign(1.0, x); }          // sign(1.0, x)
 __device__ __forceinline__ double sq(double x) { return x * x; }

@@ -51,7 +51,7 @@ struct Sm : RecF<NV, VISC> {
   static constexpr int NF = NV + 3;                       // flux + the lambda / viscous / turbulent face terms of the time step
   static constexpr int PLANE = NV * PSQ + NR * PS;        // doubles per staged plane
   static constexpr int OFF_X = 2 * PLANE;                 // exchange area [2][NF][EX]: hi values, then fluxes (same slot)
-  static constexpr int NPK = 4;                           // cell packet: volume, F1, SST sources S_k, S_w
+  static constexpr int NPK = (NV == 6) ? 5 : 4;           // cell packet: volume; sst: F1, S_k, S_w; sa: vorticity, S_v, mu, dist
   static constexpr int OFF_PK = OFF_X + 2 * NF * EX;      // cell packets [2][NPK][NMAIN], written by the I rows
   static constexpr int OFF_PRIV = OFF_PK + 2 * NPK * NMAIN;   // private slots of the K threads, [field][NMAIN]:
   static constexpr int P_FK = 0;                          //   [3][NF] k-face flux; the face below plane p sits in third p % 3
@@ -75,7 +75,7 @@ template <int NV, bool VISC>
 __device__ __forceinline__ void cell_work(const Params& P, const KArgs& a, double* __restrict__ smem, int tx, int r, int i, int j, int kc,
                                           bool need_dt, bool k_active, double* __restrict__ nrm /* [NV+1], stride 64 */) {
   using S = Sm<NV, VISC>;
-  constexpr bool SST = (NV == 7);
+  constexpr bool SST = (NV == 7), SA = (NV == 6), TURB = SST || SA;
   constexpr int NF = S::NF;
   const Layout& Ly = P.L;
   const long long fs = Ly.fs;
@@ -121,6 +121,7 @@ __device__ __forceinline__ void cell_work(const Params& P, const KArgs& a, doubl
     res[5] = res[5] - pk[2 * NMAIN];
     res[6] = res[6] - pk[3 * NMAIN];
   }
+  if (SA && VISC) res[5] = res[5] - pk[2 * NMAIN];
 
   double dtc = 0.0;
   if (need_dt) {
@@ -137,7 +138,7 @@ __device__ __forceinline__ void cell_work(const Params& P, const KArgs& a, doubl
         s = P.gm * s * P.inv_Pr;
         s = 2. * rcp64(s + (2. * P.CFL * volc * rcp64(dtc)));
         dtc = P.CFL * (s * volc);
-        if (SST) {
+        if (TURB) {
           const double* turv = xF + (NV + 2) * EX;
           double tt = turv[sl0] + turv[sl1] + Flo[(NV + 2) * NMAIN] + turv[sh0] + turv[sh1] + Fhi[(NV + 2) * NMAIN];
           tt = P.gm * tt * P.inv_tPr;
@@ -174,6 +175,17 @@ __device__ __forceinline__ void cell_work(const Params& P, const KArgs& a, doubl
       R[5] = R[5] * rcp64(1 + (beta * qc[6] * dtc));
       R[6] = R[6] * rcp64(1 + (2 * beta * qc[6] * dtc));
     }
+    if (SA && VISC) {   // update.f90:405-420: u1(6) is rho*tv here, used where the model has tv -- reproduced
+      const double vort = pk[NMAIN], mu_c = pk[3 * NMAIN], dist_c = pk[4 * NMAIN];
+      const double kd = kKappaSA * dist_c, kd2 = kd * kd;
+      const double xi = u1[5] * qc[0] / mu_c;
+      const double fv1 = pow3(xi) / (pow3(xi) + pow3(kCv1));
+      const double fv2 = 1.0 - xi / (1 + xi * fv1);
+      const double scap = vort + u1[5] * fv2 / (kd2);
+      const double rsa = fmin(u1[5] / (scap * kd2), 10.0);
+      const double fw = sa_fw(rsa);
+      R[5] = R[5] / (1. + ((-1.0 * u1[0] * kCb1 * scap) + (2.0 * u1[0] * kCw1 * fw * u1[5] / (dist_c * dist_c))) * dtc);
+    }
     if (a.have_store) {
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
@@ -203,6 +215,7 @@ __device__ __forceinline__ void cell_work(const Params& P, const KArgs& a, doubl
         a.qnew[5 * fs + cc] = (u2[5] >= 0.) ? u2[5] : qc[5];
         a.qnew[6 * fs + cc] = (u2[6] >= 0.) ? u2[6] : qc[6];
       }
+      if (SA) a.qnew[5 * fs + cc] = fmax(u2[5], 1.e-12);   // update.f90:474-475
     }
   }
   if (a.want_norms) {   // resnorm.f90:187-198
@@ -215,7 +228,7 @@ __device__ __forceinline__ void cell_work(const Params& P, const KArgs& a, doubl
 template <int NV, int INTERP, int SCHEME, bool VISC>
 __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a) {
   using S = Sm<NV, VISC>;
-  constexpr bool SST = (NV == 7);
+  constexpr bool SST = (NV == 7), SA = (NV == 6), TURB = SST || SA;
   constexpr bool SMQ = (INTERP == F3D_MUSCL || INTERP == F3D_INTERP_NONE);   // 3-point stencils read the staged planes
   constexpr int NF = S::NF;
   extern __shared__ double smem[];
@@ -426,7 +439,7 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a)
         if (need_dt || krow) {
           smem[o_fw + NV * f_x] = lam;
           if (VISC) smem[o_fw + (NV + 1) * f_x] = vis;
-          if (VISC && SST) smem[o_fw + (NV + 2) * f_x] = tur;
+          if (VISC && TURB) smem[o_fw + (NV + 2) * f_x] = tur;
         }
       }
       if (irow && rec && i <= Ly.imx - 1) {   // I rows: the cell packet of the own cell for next iteration's cell work
@@ -461,6 +474,49 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a)
           pk[NMAIN] = F1c;
           pk[2 * NMAIN] = (P_k - D_k) * volc;
           pk[3 * NMAIN] = (P_w - D_w + lamda) * volc;
+        }
+        if (SA && VISC) {   // SA source term (source.f90:835-983); the density gradient is built in place from the six neighbours
+          const double density = qA[0], tv = qA[5 * PSQ];
+          const long long cI = c;   // global index of the cell
+          const double rho_km = q[cI - Ly.sk], rho_kp = q[cI + Ly.sk];   // the k neighbours are not staged: global memory (L2)
+          const double RhoFace[6] = {qA[-1] + density, qA[-PW] + density, rho_km + density, qA[1] + density, qA[PW] + density, rho_kp + density};
+          const double* __restrict__ gI = a.geom + (long long)G_IA * fs;
+          const double* __restrict__ gJ = a.geom + (long long)G_JA * fs;
+          const double* __restrict__ gK = a.geom + (long long)G_KA * fs;
+          const long long cf[6] = {cI, cI, cI, cI + 1, cI + Ly.sj, cI + Ly.sk};
+          double gradrho[3];
+#pragma unroll
+          for (int dd = 0; dd < 3; ++dd) {
+            // KEPT DEFECT: the normal of the low K face is (nx,nx,nx) (source.f90:901)
+            const double n0 = gI[(1 + dd) * fs + cf[0]], n1 = gJ[(1 + dd) * fs + cf[1]], n2 = gK[fs + cf[2]];
+            const double n3 = gI[(1 + dd) * fs + cf[3]], n4 = gJ[(1 + dd) * fs + cf[4]], n5 = gK[(1 + dd) * fs + cf[5]];
+            gradrho[dd] = (-(RhoFace[0]) * n0 * gI[cf[0]] - (RhoFace[1]) * n1 * gJ[cf[1]] - (RhoFace[2]) * n2 * gK[cf[2]] +
+                           (RhoFace[3]) * n3 * gI[cf[3]] + (RhoFace[4]) * n4 * gJ[cf[4]] + (RhoFace[5]) * n5 * gK[cf[5]]) / (2.0 * volc);
+          }
+          const double wx = rA[(3 * 2 + 1) * PS] - rA[(3 * 1 + 2) * PS], wy = rA[(3 * 0 + 2) * PS] - rA[(3 * 2 + 0) * PS],
+                       wz = rA[(3 * 1 + 0) * PS] - rA[(3 * 0 + 1) * PS];
+          const double vort = sqrt(((wx * wx) + (wy * wy) + (wz * wz)));
+          const double tvx = rA[(3 * 4 + 0) * PS], tvy = rA[(3 * 4 + 1) * PS], tvz = rA[(3 * 4 + 2) * PS];
+          const double CD1 = kCb2 * ((tvx * tvx) + (tvy * tvy) + (tvz * tvz));
+          const double CD2 = ((gradrho[0] * tvx) + (gradrho[1] * tvy) + (gradrho[2] * tvz));
+          const double mu_c = rA[S::OFF_MU * PS];
+          const double dist_c = a.geom[(long long)G_DIST * fs + cI];
+          const double kd = kKappaSA * dist_c, kd2 = kd * kd;
+          const double nu = mu_c / density;
+          const double xi = tv / nu;
+          const double fv1 = (pow3(xi)) / ((pow3(xi)) + (pow3(kCv1)));
+          const double fv2 = 1.0 - xi / (1.0 + (xi * fv1));
+          const double scap = fmax(vort + (tv * fv2 / (kd2)), 0.3 * vort);
+          const double r = fmin(tv / (scap * kd2), 10.0);
+          const double fw = sa_fw(r);
+          const double td = tv / dist_c;
+          const double D_v = density * kCw1 * fw * (td * td);
+          const double P_v = density * kCb1 * scap * tv;
+          const double lamda = density * CD1 / kSigmaSA - CD2 * (nu + tv) / kSigmaSA;
+          pk[NMAIN] = vort;
+          pk[2 * NMAIN] = (P_v - D_v + lamda) * volc;
+          pk[3 * NMAIN] = mu_c;
+          pk[4 * NMAIN] = dist_c;
         }
       }
     }
@@ -552,6 +608,7 @@ int sweep3_grid_ctas(const Layout& L) {
 }
 
 int launch_sweep3(Ctx* ctx, KArgs& a) {
+  if (ctx->P.sa) return ctx->P.viscous ? g3::launch_interp<6, true>(ctx, a) : F3D_ERR_UNSUPPORTED;   // sa needs mu_ref /= 0
   if (ctx->P.viscous) return ctx->P.sst ? g3::launch_interp<7, true>(ctx, a) : g3::launch_interp<5, true>(ctx, a);
   return g3::launch_interp<5, false>(ctx, a);
 }

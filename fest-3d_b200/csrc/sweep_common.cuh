@@ -10,10 +10,11 @@ namespace f3d {
 
 template <int NV, bool VISC>
 struct RecF {   // fields of the non-q part of a cell record
-  static constexpr bool SST = (NV == 7);
-  static constexpr int NG = SST ? 6 : 4;
+  static constexpr bool SST = (NV == 7);                  // sst / sst2003 (k, omega)
+  static constexpr bool SA = (NV == 6);                    // Spalart-Allmaras (nu-tilde)
+  static constexpr int NG = SST ? 6 : (SA ? 5 : 4);        // u, v, w, T [, k, omega | nu-tilde]
   static constexpr int NGF = VISC ? 3 * NG : 0;            // gradient component c, direction d -> field 3*c+d
-  static constexpr int NMU = VISC ? (SST ? 3 : 1) : 0;     // mu, mu_t, F1
+  static constexpr int NMU = VISC ? (SST ? 3 : (SA ? 2 : 1)) : 0;   // mu, mu_t, F1
   static constexpr int OFF_MU = NGF, OFF_C = NGF + NMU;    // then the cell centre x,y,z
   static constexpr int NR = VISC ? NGF + NMU + 3 : 0;
 };
@@ -145,7 +146,7 @@ __device__ __forceinline__ void viscous_face(const Params& P, const double* __re
                                              const double* __restrict__ rl, const double* __restrict__ rh, double A, double nx, double ny,
                                              double nz, bool sst_on, bool need_dt, double (&F)[NV], double& vis, double& tur) {
   using R = RecF<NV, true>;
-  constexpr bool SST = (NV == 7);
+  constexpr bool SST = (NV == 7), SA = (NV == 6), TURB = SST || SA;
   constexpr int NG = R::NG;
   const double dx = rh[(R::OFF_C + 0) * PS] - rl[(R::OFF_C + 0) * PS], dy = rh[(R::OFF_C + 1) * PS] - rl[(R::OFF_C + 1) * PS],
                dz = rh[(R::OFF_C + 2) * PS] - rl[(R::OFF_C + 2) * PS];
@@ -161,6 +162,7 @@ __device__ __forceinline__ void viscous_face(const Params& P, const double* __re
     del[3] = T_RE - T_LE;
   }
   if (SST) { del[4] = qh[5] - ql[5]; del[5] = qh[6] - ql[6]; }
+  if (SA) del[4] = qh[5] - ql[5];
   double G[NG][3];
 #pragma unroll
   for (int c = 0; c < NG; ++c) {
@@ -173,8 +175,8 @@ __device__ __forceinline__ void viscous_face(const Params& P, const double* __re
   }
   const double mu_hi = rh[R::OFF_MU * PS];
   const double mu_f = 0.5 * (rl[R::OFF_MU * PS] + mu_hi);
-  const double mut_hi = SST ? rh[(R::OFF_MU + 1) * PS] : 0.0;
-  const double mut_f = SST ? 0.5 * (rl[(R::OFF_MU + 1) * PS] + mut_hi) : 0.0;
+  const double mut_hi = TURB ? rh[(R::OFF_MU + 1) * PS] : 0.0;
+  const double mut_f = TURB ? 0.5 * (rl[(R::OFF_MU + 1) * PS] + mut_hi) : 0.0;
   const double tmu = mu_f + mut_f;
   const double div3 = (G[0][0] + G[1][1] + G[2][2]) * (1. / 3.);
   const double Txx = 2. * tmu * (G[0][0] - div3), Tyy = 2. * tmu * (G[1][1] - div3), Tzz = 2. * tmu * (G[2][2] - div3);
@@ -203,11 +205,16 @@ __device__ __forceinline__ void viscous_face(const Params& P, const double* __re
     F[NV - 2] = F[NV - 2] - dk;
     F[NV - 1] = F[NV - 1] - dw;
   }
+  if (SA) {   // viscous.f90:570-656: its "mut_f" is rho_face * nu-tilde_face, not the eddy viscosity; K flux also when kmx == 2
+    const double rhof = 0.5 * (ql[0] + qh[0]);
+    const double mut_sa = 0.5 * (ql[5] + qh[5]) * rhof;
+    F[5] = F[5] - (A * ((mu_f + mut_sa) * (G[4][0] * nx + G[4][1] * ny + G[4][2] * nz))) * (1.0 / kSigmaSA);
+  }
   if (need_dt) {
     const double dn = fabs(((-dx) * nx) + ((-dy) * ny) + ((-dz) * nz));
     const double w = A * rcp64(qh[0] * dn);
     vis = w * mu_hi;
-    if (SST) tur = w * mut_hi;
+    if (TURB) tur = w * mut_hi;
   }
 }
 

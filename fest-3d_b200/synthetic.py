@@ -86,5 +86,7 @@ def make_duct_blocks(n, nb=(1, 1, 1), scheme_name="ausm", interpolant="muscl", t
                 if blk.n_var == 7:
                     q[5] *= 1 + 1e-3 * s2
                     q[6] *= 1 + 1e-3 * s1
+                elif blk.n_var == 6:
+                    q[5] *= 1 + 1e-3 * s2
                 blocks.append(blk)
     return blocks

@@ -43,7 +43,7 @@ enum { F3D_T_NONE = 0, F3D_T_RK2 = 1, F3D_T_RK4 = 2, F3D_T_TVDRK2 = 3, F3D_T_TVD
 /* slots of the per-face fixed values (src/vartypes.f90:307-334, src/boundary/read_bc.f90:28-147) */
 enum {
   F3D_FIX_DENSITY = 0, F3D_FIX_PRESSURE, F3D_FIX_X_SPEED, F3D_FIX_Y_SPEED, F3D_FIX_Z_SPEED,
-  F3D_FIX_TK, F3D_FIX_TW, F3D_FIX_WALL_TEMP, F3D_FIX_TPRESSURE, F3D_FIX_TTEMPERATURE,
+  F3D_FIX_TK, F3D_FIX_TW, F3D_FIX_WALL_TEMP, F3D_FIX_TPRESSURE, F3D_FIX_TTEMPERATURE, F3D_FIX_TV,
   F3D_NFIX
 };
 
@@ -53,13 +53,13 @@ enum {
   F3D_ERR_NAN_GRADIENT = 2,  /* any(isnan(grad))         gradients.f90:478 */
   F3D_ERR_NAN_VISCOSITY = 4, /* any(isnan(mu))           viscosity.f90:542 */
   F3D_ERR_NEGATIVE_STATE = 8,/* rho<0, p<0 or NaN after update   update.f90:448-452 */
-  F3D_ERR_UNSUPPORTED = 64,  /* implicit / plusgs / sa / kkl / lctm2015 / pressure switch: not on this path */
+  F3D_ERR_UNSUPPORTED = 64,  /* implicit / plusgs / saBC / kkl / lctm2015 / pressure switch: not on this path */
   F3D_ERR_CUDA = 128,
   F3D_ERR_ARGUMENT = 256
 };
 
 typedef struct {
-  int imx, jmx, kmx, n_var;            /* node counts of the block; n_var 5 (none) or 7 (sst)    vartypes.f90:21-26 */
+  int imx, jmx, kmx, n_var;            /* node counts of the block; n_var 5 (none), 6 (sa) or 7 (sst)    vartypes.f90:21-26 */
   int scheme, interpolant, turbulence, transition;
   int time_accuracy;                   /* F3D_T_*                                                update.f90:171 */
   int time_stepping;                   /* 0 = 'l' local, 1 = 'g' global                          time.f90:323-326 */
@@ -79,6 +79,7 @@ typedef struct {
   double gm, R_gas, mu_ref, T_ref, Sutherland_temp, Pr, tPr;
   double density_inf, x_speed_inf, y_speed_inf, z_speed_inf, pressure_inf;
   double tk_inf, tw_inf, vel_mag, MInf;
+  double tv_inf;                       /* free-stream nu-tilde of the SA model                   state.f90:105-106 */
   double fixed[F3D_NFIX][6];           /* fixed_density(6), fixed_pressure(6) ...                read_bc.f90 */
 } Fest3dGpuConfig;
 

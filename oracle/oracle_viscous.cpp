@@ -6,6 +6,13 @@
 namespace orc {
 
 static inline bool is_sst(const Block& B) { return B.c.turbulence == ORC_TURB_SST || B.c.turbulence == ORC_TURB_SST2003; }
+static inline bool is_sa(const Block& B) { return B.c.turbulence == ORC_TURB_SA; }
+
+// global_sa.f90:6-19
+constexpr double cb1 = 0.1355, cb2 = 0.6220, cw2 = 0.3, cw3 = 2.0, cv1 = 7.1, sigma_sa = 2. / 3., kappa_sa = 0.41;
+static const double cw1 = (cb1 / (kappa_sa * kappa_sa)) + ((1 + cb2) / sigma_sa);
+static inline double p3(double x) { return x * x * x; }                                  // x**3
+static inline double p6(double x) { const double x2 = x * x; return x2 * x2 * x2; }     // x**6 (gfortran: repeated squaring)
 
 // gradients.f90:405-482 compute_gradient_G (dir 0/1/2 = x/y/z); var is a full-size (-2:imx+2..) field
 template <class Var>
@@ -90,6 +97,12 @@ void Block::evaluate_all_gradients() {
     gradient_G(B, gy, 5, tk, 1); gradient_G(B, gy, 6, tw, 1);
     if (kmx > 2) { gradient_G(B, gz, 5, tk, 2); gradient_G(B, gz, 6, tw, 2); }
   }
+  if (is_sa(B)) {   // gradients.f90:344-350
+    QpVar tv{qp, 6};
+    gradient_G(B, gx, 5, tv, 0);
+    gradient_G(B, gy, 5, tv, 1);
+    if (kmx > 2) gradient_G(B, gz, 5, tv, 2);
+  }
   // apply_gradient_bc :486-592
   const double* wt = c.fixed[ORC_FIX_WALL_TEMP];
   if (c.bc_id[0] < 0) gradient_bc_face(B, If, 1, 1, 1, jmx - 1, 1, kmx - 1, 1, 0, 0, 0, 0, 0, 1, c.bc_id[0], wt[0]);
@@ -167,6 +180,38 @@ void Block::calculate_viscosity() {
           }
           mu_t(ig, jg, kg) = sgn * mu_t(i, j, k);
           F1(ig, jg, kg) = F1(i, j, k);
+        }
+    }
+  }
+  if (is_sa(B)) {   // viscosity.f90:149-212: mu_t = rho*tv*fv1 on 0..imx, ghost copy (anti on walls) per BC id
+    for (int k = 0; k <= kmx; ++k)
+      for (int j = 0; j <= jmx; ++j)
+        for (int i = 0; i <= imx; ++i) {
+          double tv = qp(i, j, k, 6), density = qp(i, j, k, 1);
+          double xi = tv * density / mu(i, j, k);
+          double fv1 = (p3(xi)) / ((p3(xi)) + (p3(cv1)));
+          mu_t(i, j, k) = density * tv * fv1;
+        }
+    for (int face = 1; face <= 6; ++face) {
+      int id = c.bc_id[face - 1];
+      if (id >= 0 || id == -10) continue;
+      double sgn;
+      if (id == -5) sgn = -1.0;
+      else if (id == -1 || id == -2 || id == -3 || id == -4 || id == -6 || id == -7 || id == -8 || id == -9) sgn = 1.0;
+      else continue;
+      int na = face <= 2 ? jmx - 1 : imx - 1, nb = face <= 4 ? kmx - 1 : jmx - 1;
+      for (int b = 1; b <= nb; ++b)
+        for (int a = 1; a <= na; ++a) {
+          int i, j, k, ig, jg, kg;
+          switch (face) {
+            case 1: i = 1; j = a; k = b; ig = 0; jg = a; kg = b; break;
+            case 2: i = imx - 1; j = a; k = b; ig = imx; jg = a; kg = b; break;
+            case 3: i = a; j = 1; k = b; ig = a; jg = 0; kg = b; break;
+            case 4: i = a; j = jmx - 1; k = b; ig = a; jg = jmx; kg = b; break;
+            case 5: i = a; j = b; k = 1; ig = a; jg = b; kg = 0; break;
+            default: i = a; j = b; k = kmx - 1; ig = a; jg = b; kg = kmx; break;
+          }
+          mu_t(ig, jg, kg) = sgn * mu_t(i, j, k);
         }
     }
   }
@@ -289,6 +334,32 @@ static void viscous_sst(Block& B, Arr4& F, const Rec4& faces, int ii, int jj, in
       }
 }
 
+// viscous.f90:570-656 compute_viscous_fluxes_sa: "mut_f" here is rho_face * tv_face, not the eddy viscosity
+static void viscous_sa(Block& B, Arr4& F, const Rec4& faces, int ii, int jj, int kk) {
+  for (int k = 1; k <= B.kmx - 1 + kk; ++k)
+    for (int j = 1; j <= B.jmx - 1 + jj; ++j)
+      for (int i = 1; i <= B.imx - 1 + ii; ++i) {
+        const int im = i - ii, jm = j - jj, km = k - kk;
+        double dtvdx = 0.5 * (B.gx(im, jm, km, 5) + B.gx(i, j, k, 5));
+        double dtvdy = 0.5 * (B.gy(im, jm, km, 5) + B.gy(i, j, k, 5));
+        double dtvdz = 0.5 * (B.gz(im, jm, km, 5) + B.gz(i, j, k, 5));
+        double delx = B.cells.cx(i, j, k) - B.cells.cx(im, jm, km);
+        double dely = B.cells.cy(i, j, k) - B.cells.cy(im, jm, km);
+        double delz = B.cells.cz(i, j, k) - B.cells.cz(im, jm, km);
+        double d_LR = std::sqrt(delx * delx + dely * dely + delz * delz);
+        double deltv = B.qp(i, j, k, 6) - B.qp(im, jm, km, 6);
+        double normal_comp = (deltv - (dtvdx * delx + dtvdy * dely + dtvdz * delz)) / d_LR;
+        dtvdx = dtvdx + (normal_comp * delx / d_LR);
+        dtvdy = dtvdy + (normal_comp * dely / d_LR);
+        dtvdz = dtvdz + (normal_comp * delz / d_LR);
+        double rhoface = 0.5 * (B.qp(im, jm, km, 1) + B.qp(i, j, k, 1));
+        double mu_f = 0.5 * (B.mu(im, jm, km) + B.mu(i, j, k));
+        double mut_f = 0.5 * (B.qp(im, jm, km, 6) + B.qp(i, j, k, 6)) * rhoface;
+        double nx = faces.nx(i, j, k), ny = faces.ny(i, j, k), nz = faces.nz(i, j, k), area = faces.A(i, j, k);
+        F(i, j, k, 6) = F(i, j, k, 6) - (area * ((mu_f + mut_f) * (dtvdx * nx + dtvdy * ny + dtvdz * nz))) / sigma_sa;
+      }
+}
+
 // viscous.f90:55-142: laminar on F,G,H always (also the K flux when kmx==2), SST K flux skipped when kmx==2
 void Block::compute_viscous_fluxes() {
   viscous_laminar(*this, F, If, 1, 0, 0);
@@ -299,12 +370,62 @@ void Block::compute_viscous_fluxes() {
     viscous_sst(*this, G, Jf, 0, 1, 0);
     if (kmx != 2) viscous_sst(*this, H, Kf, 0, 0, 1);
   }
+  if (is_sa(*this)) {   // the K flux too when kmx == 2 (:94-97)
+    viscous_sa(*this, F, If, 1, 0, 0);
+    viscous_sa(*this, G, Jf, 0, 1, 0);
+    viscous_sa(*this, H, Kf, 0, 0, 1);
+  }
   auto has_nan = [](const Arr4& a) { for (double v : a.d) if (std::isnan(v)) return true; return false; };
   if (has_nan(F) || has_nan(G) || has_nan(H)) error |= 1;
 }
 
+// source.f90:835-983 add_sa_source.  KEPT DEFECT: the normal of the low K face is (nx,nx,nx) (:901).
+static void add_sa_source(Block& B) {
+  const Rec4 &If = B.If, &Jf = B.Jf, &Kf = B.Kf;
+  for (int k = 1; k <= B.kmx - 1; ++k)
+    for (int j = 1; j <= B.jmx - 1; ++j)
+      for (int i = 1; i <= B.imx - 1; ++i) {
+        double density = B.qp(i, j, k, 1), tv = B.qp(i, j, k, 6);
+        double RhoFace[6] = {B.qp(i - 1, j, k, 1) + density, B.qp(i, j - 1, k, 1) + density, B.qp(i, j, k - 1, 1) + density,
+                             B.qp(i + 1, j, k, 1) + density, B.qp(i, j + 1, k, 1) + density, B.qp(i, j, k + 1, 1) + density};
+        double Area[6] = {If.A(i, j, k), Jf.A(i, j, k), Kf.A(i, j, k), If.A(i + 1, j, k), Jf.A(i, j + 1, k), Kf.A(i, j, k + 1)};
+        double Normal[6][3] = {{If.nx(i, j, k), If.ny(i, j, k), If.nz(i, j, k)},
+                               {Jf.nx(i, j, k), Jf.ny(i, j, k), Jf.nz(i, j, k)},
+                               {Kf.nx(i, j, k), Kf.nx(i, j, k), Kf.nx(i, j, k)},
+                               {If.nx(i + 1, j, k), If.ny(i + 1, j, k), If.nz(i + 1, j, k)},
+                               {Jf.nx(i, j + 1, k), Jf.ny(i, j + 1, k), Jf.nz(i, j + 1, k)},
+                               {Kf.nx(i, j, k + 1), Kf.ny(i, j, k + 1), Kf.nz(i, j, k + 1)}};
+        double gradrho[3];
+        for (int d = 0; d < 3; ++d)
+          gradrho[d] = (-(RhoFace[0]) * Normal[0][d] * Area[0] - (RhoFace[1]) * Normal[1][d] * Area[1] - (RhoFace[2]) * Normal[2][d] * Area[2] +
+                        (RhoFace[3]) * Normal[3][d] * Area[3] + (RhoFace[4]) * Normal[4][d] * Area[4] + (RhoFace[5]) * Normal[5][d] * Area[5]) /
+                       (2.0 * B.cells.vol(i, j, k));
+        double a = (B.gy(i, j, k, 3) - B.gz(i, j, k, 2)), b = (B.gz(i, j, k, 1) - B.gx(i, j, k, 3)), cc = (B.gx(i, j, k, 2) - B.gy(i, j, k, 1));
+        double vort = std::sqrt(((a * a) + (b * b) + (cc * cc)));
+        double CD1 = cb2 * ((B.gx(i, j, k, 5) * B.gx(i, j, k, 5)) + (B.gy(i, j, k, 5) * B.gy(i, j, k, 5)) + (B.gz(i, j, k, 5) * B.gz(i, j, k, 5)));
+        double CD2 = ((gradrho[0] * B.gx(i, j, k, 5)) + (gradrho[1] * B.gy(i, j, k, 5)) + (gradrho[2] * B.gz(i, j, k, 5)));
+        double kd = kappa_sa * B.dist(i, j, k);
+        double kd2 = kd * kd;
+        double nu = B.mu(i, j, k) / density;
+        double xi = tv / nu;
+        double fv1 = (p3(xi)) / ((p3(xi)) + (p3(cv1)));
+        double fv2 = 1.0 - xi / (1.0 + (xi * fv1));
+        double scap = std::fmax(vort + (tv * fv2 / (kd2)), 0.3 * vort);
+        double r = std::fmin(tv / (scap * kd2), 10.0);
+        double g = r + cw2 * ((p6(r)) - r);
+        double fw = g * std::pow((1.0 + (p6(cw3))) / ((p6(g)) + (p6(cw3))), (1.0 / 6.0));
+        double td = tv / B.dist(i, j, k);
+        double D_v = density * cw1 * fw * (td * td);
+        double P_v = density * cb1 * scap * tv;
+        double lamda = density * CD1 / sigma_sa - CD2 * (nu + tv) / sigma_sa;
+        double S_v = (P_v - D_v + lamda) * B.cells.vol(i, j, k);
+        B.residue(i, j, k, 6) = B.residue(i, j, k, 6) - S_v;
+      }
+}
+
 // source.f90:158-270 add_sst_source
 void Block::add_source_term_residue() {
+  if (is_sa(*this)) { add_sa_source(*this); return; }
   if (!is_sst(*this)) return;
   int limiter;
   if (c.turbulence == ORC_TURB_SST2003) { limiter = 10; gama1 = 5.0 / 9.0; gama2 = 0.44; }
@@ -431,6 +552,20 @@ void Block::update_with(double TF, double SF, bool TU, bool have_store) {
           R[5] = R[5] / (1 + (beta * qp(i, j, k, 7) * delta_t(i, j, k)));
           R[6] = R[6] / (1 + (2 * beta * qp(i, j, k, 7) * delta_t(i, j, k)));
         }
+        if (is_sa(*this)) {   // update.f90:405-420: u1(6) is rho*tv here, used where the model has tv -- reproduced
+          double a = (gy(i, j, k, 3) - gz(i, j, k, 2)), b = (gz(i, j, k, 1) - gx(i, j, k, 3)), cc = (gx(i, j, k, 2) - gy(i, j, k, 1));
+          double vort = std::sqrt(((a * a) + (b * b) + (cc * cc)));
+          double kd = kappa_sa * dist(i, j, k);
+          double kd2 = kd * kd;
+          double xi = u1[5] * qp(i, j, k, 1) / mu(i, j, k);
+          double fv1 = p3(xi) / (p3(xi) + p3(cv1));
+          double fv2 = 1.0 - xi / (1 + xi * fv1);
+          double scap = vort + u1[5] * fv2 / (kd2);
+          double rsa = std::fmin(u1[5] / (scap * kd2), 10.0);
+          double g = rsa + cw2 * (p6(rsa) - rsa);
+          double fw = g * std::pow((1.0 + p6(cw3)) / (p6(g) + p6(cw3)), (1.0 / 6.0));
+          R[5] = R[5] / (1. + ((-1.0 * u1[0] * cb1 * scap) + (2.0 * u1[0] * cw1 * fw * u1[5] / (dist(i, j, k) * dist(i, j, k)))) * delta_t(i, j, k));
+        }
         if (have_store && R_store.size()) {
           for (int l = 1; l <= nv; ++l) R_store(i, j, k, l) = R_store(i, j, k, l) + SF * R[l - 1];
           if (TU) for (int l = 1; l <= nv; ++l) R[l - 1] = R_store(i, j, k, l);
@@ -447,6 +582,7 @@ void Block::update_with(double TF, double SF, bool TU, bool have_store) {
           if (u2[5] >= 0.) qp(i, j, k, 6) = u2[5];
           if (u2[6] >= 0.) qp(i, j, k, 7) = u2[6];
         }
+        if (is_sa(*this)) qp(i, j, k, 6) = std::fmax(u2[5], 1.e-12);   // update.f90:474-475
       }
 }
 
@@ -458,6 +594,7 @@ void Block::absolute_resnorm() {
   scale[2] = scale[3] = scale[4] = c.density_inf * c.vel_mag * c.vel_mag;
   scale[5] = (0.5 * c.density_inf * (c.vel_mag * c.vel_mag * c.vel_mag) + ((c.gm / (c.gm - 1.)) * c.pressure_inf));
   if (is_sst(*this)) { scale[6] = c.density_inf * c.vel_mag * c.tk_inf; scale[7] = c.density_inf * c.vel_mag * c.tw_inf; }
+  if (is_sa(*this)) scale[6] = c.density_inf * c.vel_mag * c.tv_inf;   // resnorm.f90:157-158
   for (int l = 1; l <= nv; ++l) {
     double s = 0.;
     for (int k = 1; k <= kmx - 1; ++k) for (int j = 1; j <= jmx - 1; ++j) for (int i = 1; i <= imx - 1; ++i) { double r = residue(i, j, k, l); s += r * r; }

@@ -130,6 +130,48 @@ def test_duct_time_integrators(pkg, case_mod, oracle, turbulence, mu_ref, ta):
     s.close()
 
 
+# ---- Spalart-Allmaras (n_var 6, n_grad 5): every piece of the path that switches on the model ---------------------------
+@pytest.mark.parametrize("scheme_name,interpolant", [("ausm", "muscl"), ("slau", "weno"), ("van_leer", "none")])
+def test_duct_sa_residual(pkg, case_mod, oracle, scheme_name, interpolant):
+    import importlib
+    syn = importlib.import_module("fest-3d_b200.synthetic")
+    blocks = syn.make_duct_blocks(None, n3=(20, 12, 10), scheme_name=scheme_name, interpolant=interpolant, turbulence="sa")
+    s = _solver(pkg, blocks)
+    _check_residual(oracle, s, blocks)
+    s.close()
+
+
+@pytest.mark.parametrize("ta", ["none", "RK4", "TVDRK3"])
+def test_duct_sa_history(pkg, case_mod, oracle, ta):
+    import importlib
+    syn = importlib.import_module("fest-3d_b200.synthetic")
+    blocks = syn.make_duct_blocks(None, n3=(14, 10, 9), turbulence="sa", time_step_accuracy=ta, CFL=0.6)
+    s = _solver(pkg, blocks)
+    _check_history(oracle, s, blocks, 6)
+    s.close()
+
+
+@pytest.mark.parametrize("bc", [[-1, -2, -6, -6, -6, -6], [-8, -4, -5, -7, -9, -9], [-11, -4, -5, -5, -6, -6]])
+@pytest.mark.parametrize("shape", [(6, 5, 1), (9, 7, 5)])
+def test_sa_boundary_conditions(pkg, case_mod, oracle, bc, shape):
+    import importlib
+    syn = importlib.import_module("fest-3d_b200.synthetic")
+    if (-9 in bc[4:]) and shape[2] < 3:
+        pytest.skip("periodic slab copy needs 3 interior layers")
+    blocks = syn.make_duct_blocks(None, n3=shape, turbulence="sa", time_step_accuracy="RK2", interpolant="muscl")
+    blk = blocks[0]
+    blk.bc_id = list(bc)
+    fl = blk.flow
+    M2 = fl.x_speed_inf ** 2 / (fl.gm * fl.pressure_inf / fl.density_inf)
+    blk.fixed[8, :] = fl.pressure_inf * (1 + 0.5 * (fl.gm - 1.0) * M2) ** (fl.gm / (fl.gm - 1.0))
+    blk.fixed[10, :] = fl.tv_inf * (1.0 + 0.05 * np.arange(6))
+    blk.build_geometry()
+    s = _solver(pkg, blocks)
+    _check_residual(oracle, s, blocks)
+    _check_history(oracle, s, blocks, 4)
+    s.close()
+
+
 def test_duct_multiblock_local_links(pkg, case_mod, oracle):
     import importlib
     syn = importlib.import_module("fest-3d_b200.synthetic")

@@ -174,3 +174,27 @@ def test_total_pressure_bc_free_stream(oracle, case_mod):
     for v, r in enumerate(ref):
         g = q[v, K, J, 0:3]
         assert np.abs(g - r).max() <= 1e-12 * max(abs(r), fl.x_speed_inf), (v, g.ravel()[:3], r)
+
+
+def test_sa_oracle_closure_identities(oracle, case_mod):
+    """The SA branch of the oracle has no known answer in the reference's tests.  Pin what can be pinned analytically:
+    mu_t = rho * tv * fv1(chi) with chi = rho tv / mu (viscosity.f90:149-163), ghost mu_t = -interior on a wall
+    (viscosity.f90:192-206), a uniform state at rest far from walls gives a source that is pure destruction
+    -rho cw1 fw (tv/d)^2 with fw(r=tv/(S kd2)) evaluated at S = tv fv2/kd2 (source.f90:940-975), and the update
+    clamps tv at 1e-12 (update.f90:474-475)."""
+    import importlib
+    syn = importlib.import_module("fest-3d_b200.synthetic")
+    blocks = syn.make_duct_blocks(None, n3=(8, 7, 6), turbulence="sa", time_step_accuracy="none", CFL=0.5)
+    blk = blocks[0]
+    w = oracle.OracleWorld(blocks)
+    err, _ = w.residual(1)
+    assert err == 0
+    q = w.get_state(0)
+    mu = w.aux(0, 1, (blk.kmx + 5, blk.jmx + 5, blk.imx + 5))
+    mut = w.aux(0, 2, (blk.kmx + 5, blk.jmx + 5, blk.imx + 5))
+    K, J, I = slice(3, 3 + blk.kmx - 1), slice(3, 3 + blk.jmx - 1), slice(3, 3 + blk.imx - 1)
+    chi = q[0, K, J, I] * q[5, K, J, I] / mu[K, J, I]
+    fv1 = chi ** 3 / (chi ** 3 + 7.1 ** 3)
+    assert np.allclose(mut[K, J, I], q[0, K, J, I] * q[5, K, J, I] * fv1, rtol=1e-13, atol=0)
+    # jmin is a no-slip wall of the duct: ghost mu_t = -mu_t of the first interior cell
+    assert np.allclose(mut[K, 2, I], -mut[K, 3, I], rtol=0, atol=0)
