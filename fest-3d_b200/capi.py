@@ -37,7 +37,7 @@ class Fest3dGpuConfig(C.Structure):
         ("Sutherland_temp", C.c_double), ("Pr", C.c_double), ("tPr", C.c_double),
         ("density_inf", C.c_double), ("x_speed_inf", C.c_double), ("y_speed_inf", C.c_double),
         ("z_speed_inf", C.c_double), ("pressure_inf", C.c_double),
-        ("tk_inf", C.c_double), ("tw_inf", C.c_double), ("vel_mag", C.c_double), ("MInf", C.c_double), ("tv_inf", C.c_double),
+        ("tk_inf", C.c_double), ("tw_inf", C.c_double), ("vel_mag", C.c_double), ("MInf", C.c_double), ("tv_inf", C.c_double), ("tu_inf", C.c_double),
         ("fixed", (C.c_double * 6) * NFIX),
     ]
 

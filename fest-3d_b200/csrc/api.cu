@@ -61,9 +61,8 @@ extern "C" int fest3d_gpu_create(Fest3dGpuCtx** out, const Fest3dGpuConfig* cfg,
   const bool sst = cfg->turbulence == F3D_TURB_SST || cfg->turbulence == F3D_TURB_SST2003;
   const bool sa = cfg->turbulence == F3D_TURB_SA;   // 'saBC' has no case in the reference's source dispatcher (source.f90:119-153)
   if (cfg->turbulence != F3D_TURB_NONE && !sst && !sa) return F3D_ERR_UNSUPPORTED;
-  if (cfg->transition != F3D_TRANS_NONE) return F3D_ERR_UNSUPPORTED;
+  if (cfg->transition != F3D_TRANS_NONE && !(cfg->transition == F3D_TRANS_BC && (sst || sa))) return F3D_ERR_UNSUPPORTED;   // lctm2015: not built
   if (cfg->time_accuracy >= F3D_T_IMPLICIT || cfg->time_accuracy < 0) return F3D_ERR_UNSUPPORTED;
-  if (cfg->pb_switch[0] || cfg->pb_switch[1] || cfg->pb_switch[2]) return F3D_ERR_UNSUPPORTED;
   if (cfg->scheme < 0 || cfg->scheme > F3D_SLAU || cfg->interpolant < 0 || cfg->interpolant > F3D_WENO_NM) return F3D_ERR_ARGUMENT;
   if (cfg->n_var != (sst ? 7 : (sa ? 6 : 5))) return F3D_ERR_ARGUMENT;
   if ((sst || sa) && cfg->mu_ref == 0.0) return F3D_ERR_UNSUPPORTED;
@@ -83,7 +82,8 @@ extern "C" int fest3d_gpu_create(Fest3dGpuCtx** out, const Fest3dGpuConfig* cfg,
   L.fs = ((13 + L.sk * L.pk + 31) / 32) * 32;
   P.scheme = cfg->scheme; P.interpolant = cfg->interpolant; P.turbulence = cfg->turbulence;
   P.time_stepping = cfg->time_stepping; P.mu_variation = cfg->mu_variation;
-  for (int d = 0; d < 3; ++d) { P.limiter[d] = cfg->limiter[d]; P.tlimiter[d] = cfg->tlimiter[d]; }
+  const bool pb_interp = cfg->interpolant == F3D_MUSCL || cfg->interpolant == F3D_PPM;   // the only callers (muscl.f90:231, ppm.f90:220)
+  for (int d = 0; d < 3; ++d) { P.limiter[d] = cfg->limiter[d]; P.tlimiter[d] = cfg->tlimiter[d]; P.pb_switch[d] = (pb_interp && cfg->pb_switch[d] == 1) ? 1 : 0; }
   P.ppm_flag = (cfg->interpolant == F3D_PPM || cfg->interpolant == F3D_WENO || cfg->interpolant == F3D_WENO_NM) ? 1 : 0;
   for (int f = 0; f < 6; ++f) {
     int id = cfg->bc_id[f];
@@ -98,6 +98,8 @@ extern "C" int fest3d_gpu_create(Fest3dGpuCtx** out, const Fest3dGpuConfig* cfg,
   P.c2 = 1 + cfg->accur; P.c3 = 0.5 * cfg->accur; P.c1 = P.c2 - P.c3;
   P.current_iter = 1;
   P.viscous = cfg->mu_ref != 0.0; P.sst = sst ? 1 : 0; P.sa = sa ? 1 : 0;
+  P.trans_bc = cfg->transition == F3D_TRANS_BC ? 1 : 0; P.tu_inf = cfg->tu_inf;
+  P.nu_cr = cfg->mu_ref != 0.0 ? 5.0 / (cfg->density_inf * cfg->vel_mag * 1.0 / cfg->mu_ref) : 0.0;   // chi_2 / Reynolds_number (state.f90:89)
   P.CFL = cfg->CFL; P.global_time_step = cfg->global_time_step;
   P.gm = cfg->gm; P.R_gas = cfg->R_gas; P.mu_ref = cfg->mu_ref; P.T_ref = cfg->T_ref; P.Sutherland_temp = cfg->Sutherland_temp;
   P.Pr = cfg->Pr; P.tPr = cfg->tPr;
@@ -112,6 +114,8 @@ extern "C" int fest3d_gpu_create(Fest3dGpuCtx** out, const Fest3dGpuConfig* cfg,
     P.gama2 = (0.0828 / 0.09) - ((0.856 * (kappa * kappa)) / sqrt(0.09));
     P.cd_floor = 1.0e-20; P.mut_floor = 1.e-20; P.pk_limiter = 20;
   }
+  P.gama1_default = (0.075 / 0.09) - ((0.5 * (kappa * kappa)) / sqrt(0.09));
+  P.gama2_default = (0.0828 / 0.09) - ((0.856 * (kappa * kappa)) / sqrt(0.09));
   memcpy(P.fixed, cfg->fixed, sizeof(P.fixed));
   // Res_scale (resnorm.f90:136-150); slot 0 is the mass imbalance scale (1)
   double sc[9] = {1, 1, 1, 1, 1, 1, 1, 1, 1};

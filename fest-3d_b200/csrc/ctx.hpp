@@ -26,13 +26,14 @@ enum { G_VOL = 0, G_CX, G_CY, G_CZ, G_IA, G_INX, G_INY, G_INZ, G_JA, G_JNX, G_JN
 struct Params {
   Layout L;
   int scheme, interpolant, turbulence, time_stepping, mu_variation;
-  int limiter[3], tlimiter[3];
+  int limiter[3], tlimiter[3], pb_switch[3];
   int bc_id[6];
   int phys[6];            // 1 when the face is a physical boundary that gets the boundary-state override (id<0 && id!=-10)
   int farlike[6];         // 1 when id is -8 or -9 (face state = ghost value)
   int ppm_flag;           // boundary re-reconstruction active (ppm / weno / weno_NM or a pole face)
   int current_iter;
   int viscous, sst, sa;   // sa: Spalart-Allmaras (n_var 6)
+  int trans_bc;           // transition = bc: algebraic gamma_BC factor on the production term (source.f90:467-604, 985-1194)
   double zlo[3], zhi[3];  // make_{F,G,H}_flux_zero at the first / last face of each direction (bc.f90:53-66)
   double c1, c2, c3;
   double CFL, global_time_step;
@@ -40,6 +41,8 @@ struct Params {
   double inv_Pr, inv_tPr, inv_gm1;   // reciprocals of Pr, tPr, gm-1
   double density_inf, x_speed_inf, y_speed_inf, z_speed_inf, pressure_inf, tk_inf, tw_inf, tv_inf, MInf;
   double gama1, gama2, cd_floor, mut_floor, pk_limiter;
+  double gama1_default, gama2_default;   // global_sst.f90:15-16 as they stand when add_sst_source never runs (transition = bc)
+  double tu_inf, nu_cr;   // transition = bc: free-stream turbulence intensity (percent), chi_2 / Reynolds_number
   double fixed[F3D_NFIX][6];
   double res_scale[8];    // Res_scale(1:n_var) (resnorm.f90:136-150)
 };

@@ -575,7 +575,7 @@ int launch_residual(Ctx* ctx, int mode, double TF, double SF, int use_store_sum,
   }
   int rc;
   if (sweep_generation() == 3) rc = launch_sweep3(ctx, a);
-  else if (ctx->P.sa) rc = F3D_ERR_UNSUPPORTED;   // the SA model exists in generation 3 only
+  else if (ctx->P.sa || ctx->P.pb_switch[0] || ctx->P.pb_switch[1] || ctx->P.pb_switch[2]) rc = F3D_ERR_UNSUPPORTED;   // generation 3 only
   else if (ctx->P.viscous) rc = ctx->P.sst ? launch_interp<7, true>(ctx, a) : launch_interp<5, true>(ctx, a);
   else rc = launch_interp<5, false>(ctx, a);
   if (ctx->timing) cudaEventRecord(e1, ctx->stream);

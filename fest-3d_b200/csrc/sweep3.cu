@@ -350,7 +350,8 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a)
         double qm[NV], q0[NV], qp[NV];
 #pragma unroll
         for (int v = 0; v < NV; ++v) { qm[v] = q[v * fs + c - Ly.sk]; q0[v] = q[v * fs + c]; qp[v] = q[v * fs + c + Ly.sk]; }
-        recon3<NV, INTERP>(P, qm, q0, qp, kb - 1, Ly.kmx, 2, L, lo_);
+        const double p_far = (INTERP == F3D_MUSCL && P.pb_switch[2] && kb - 1 == 0) ? q[4 * fs + c + 2 * Ly.sk] : 0.0;
+        recon3<NV, INTERP>(P, qm, q0, qp, kb - 1, Ly.kmx, 2, L, lo_, p_far);
       } else {
         line_cell_values<NV, INTERP>(P, q, vol, c, Ly.sk, kb - 1, Ly.kmx, 2, L, lo_);
       }
@@ -418,7 +419,12 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a)
           double qm[NV], q0[NV], qp[NV];
 #pragma unroll
           for (int v = 0; v < NV; ++v) { qm[v] = smem[o_m + v * PSQ]; q0[v] = smem[o_0 + v * PSQ]; qp[v] = smem[o_p + v * f_p]; }
-          recon3<NV, INTERP>(P, qm, q0, qp, cpos, mx, d, hi, lo);
+          double p_far = 0.0;   // pressure-based switching at the two ghost positions reads the pressure two cells inwards
+          if (INTERP == F3D_MUSCL && P.pb_switch[d] && (cpos == 0 || cpos == mx)) {
+            const int two = (cpos == 0) ? 2 : -2;
+            p_far = krow ? q[4 * fs + cg + two * Ly.sk] : smem[o_0 + 4 * PSQ + two * nb];
+          }
+          recon3<NV, INTERP>(P, qm, q0, qp, cpos, mx, d, hi, lo, p_far);
         } else {
           line_cell_values<NV, INTERP>(P, q, vol, cg, (d == 0) ? 1 : ((d == 1) ? Ly.sj : Ly.sk), cpos, mx, d, hi, lo);
         }
@@ -469,8 +475,21 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a)
           const double divergence = g[0][0] + g[1][1] + g[2][2];
           double P_k = mut * (vort * vort) - ((2.0 / 3.0) * density * tk * divergence);
           P_k = dmin(P_k, P.pk_limiter * D_k);
-          const double P_w = (density * gama * rcp64(mut)) * P_k;
-          const double lamda = (1. - F1c) * CD;
+          double P_w = (density * gama * rcp64(mut)) * P_k;
+          double lamda = (1. - F1c) * CD;
+          if (P.trans_bc) {   // add_sst_bc_source (source.f90:467-604): no CD floor, P_k = mu_t vort^2 capped at 20 D_k, gamma_BC on P_k
+            const double CDb = 2 * density * kSigmaW2 * (g[4][0] * g[5][0] + g[4][1] * g[5][1] + g[4][2] * g[5][2]) / tw;
+            const double gam0 = P.gama1_default * F1c + P.gama2_default * (1. - F1c);
+            P_k = fmin(mut * (vort * vort), 20.0 * D_k);
+            P_w = (density * gam0 / mut) * P_k;
+            lamda = (1. - F1c) * CDb;
+            const double u_ = qA[PSQ], v_ = qA[2 * PSQ], w_ = qA[3 * PSQ];
+            const double vmag = sqrt(((u_ * u_) + (v_ * v_)) + (w_ * w_));
+            const double dist_c = a.geom[(long long)G_DIST * fs + c];
+            const double mu_c = rA[S::OFF_MU * PS];
+            const double re_v = density * dist_c * dist_c * vort / mu_c;
+            P_k = gamma_bc(P.tu_inf, P.nu_cr, mut / density, vmag, dist_c, re_v) * P_k;
+          }
           pk[NMAIN] = F1c;
           pk[2 * NMAIN] = (P_k - D_k) * volc;
           pk[3 * NMAIN] = (P_w - D_w + lamda) * volc;
@@ -513,8 +532,23 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a)
           const double D_v = density * kCw1 * fw * (td * td);
           const double P_v = density * kCb1 * scap * tv;
           const double lamda = density * CD1 / kSigmaSA - CD2 * (nu + tv) / kSigmaSA;
+          double S_v = (P_v - D_v + lamda) * volc;
+          if (P.trans_bc) {   // add_saBC_source (source.f90:985-1194); its destruction term carries no density (:1181)
+            const double u_ = qA[PSQ], v_ = qA[2 * PSQ], w_ = qA[3 * PSQ];
+            const double vmag = sqrt(u_ * u_ + v_ * v_ + w_ * w_);
+            const double dist2 = dist_c * dist_c;
+            const double inv_k2_d2 = 1.0 / ((kKappaSA * kKappaSA) * dist2);
+            const double Shat = fmax(vort + tv * fv2 * inv_k2_d2, 1.0e-10);
+            const double inv_Shat = 1.0 / Shat;
+            const double gBC = gamma_bc(P.tu_inf, P.nu_cr, tv * fv1, vmag, dist_c, dist2 * vort / nu);
+            const double Production = gBC * kCb1 * Shat * tv * volc;
+            const double fwb = sa_fw(fmin(tv * inv_Shat * inv_k2_d2, 10.0));
+            const double Destruction = (kCw1 * fwb * tv * tv / dist2) * (volc);
+            const double lam2 = (density * CD1 / kSigmaSA - CD2 * (nu + tv) / kSigmaSA) * volc;
+            S_v = (Production - Destruction + lam2);
+          }
           pk[NMAIN] = vort;
-          pk[2 * NMAIN] = (P_v - D_v + lamda) * volc;
+          pk[2 * NMAIN] = S_v;
           pk[3 * NMAIN] = mu_c;
           pk[4 * NMAIN] = dist_c;
         }

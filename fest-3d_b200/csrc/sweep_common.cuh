@@ -46,6 +46,16 @@ struct KArgs {
   double TF, SF;
 };
 
+// Pressure-based switching (muscl.f90:37-112, ppm.f90:108-170): weight of the cell at position pos along a direction with node
+// count mx.  Interior cells take it from their two neighbours; the ghost positions 0 and mx copy the value of the first / last
+// interior cell, i.e. they are built from p(2), p(0) and p(mx), p(mx-2): p_far is the pressure two cells inwards.
+__device__ __forceinline__ double pb_pdif(const Params& P, double p_m, double p_0, double p_p, double p_far, int pos, int mx) {
+  const double a = (pos == 0) ? p_far : ((pos == mx) ? p_0 : p_p);
+  const double b = (pos == 0) ? p_0 : ((pos == mx) ? p_far : p_m);
+  const double pd2 = fabs(a - b);
+  return 1 - (pd2 / (pd2 + P.pressure_inf));
+}
+
 // Values a cell contributes to its two faces along one direction, all variables.  `pos` is the cell's index along the
 // direction; the first / last interior cell next to a physical boundary is re-done with the boundary formula when
 // ppm_flag is set (boundary_state_reconstruction.f90:93-123).
@@ -73,6 +83,16 @@ __device__ __forceinline__ void line_cell_values(const Params& P, const double* 
         for (int m = 1; m <= 5; ++m) ql[m] = qv[c + (m - 3) * s];
       }
       cell_face_values<INTERP>(ql, vl, lim, to_hi[v], to_lo[v]);
+    }
+  }
+  if ((INTERP == F3D_PPM || INTERP == F3D_MUSCL) && !redo && P.pb_switch[dir]) {
+    const double* __restrict__ pv = q + 4LL * P.L.fs;
+    const double pd = pb_pdif(P, pv[c - s], pv[c], pv[c + s], (pos == 0) ? pv[c + 2 * s] : ((pos == mx) ? pv[c - 2 * s] : 0.0), pos, mx);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const double q0 = q[(long long)v * P.L.fs + c];
+      to_hi[v] = q0 + (pd * (to_hi[v] - q0));
+      to_lo[v] = q0 - (pd * (q0 - to_lo[v]));
     }
   }
 }
@@ -118,7 +138,7 @@ __device__ __forceinline__ void muscl_group(const double (&qm)[NV], const double
 // (muscl.f90:161-196; boundary_state_reconstruction.f90:93-123 for the first / last interior cell when ppm_flag is set)
 template <int NV, int INTERP>
 __device__ __forceinline__ void recon3(const Params& P, const double (&qm)[NV], const double (&q0)[NV], const double (&qp)[NV], int pos, int mx,
-                                       int dir, double (&to_hi)[NV], double (&to_lo)[NV]) {
+                                       int dir, double (&to_hi)[NV], double (&to_lo)[NV], double p_far = 0.0) {
   const bool redo = (INTERP != F3D_INTERP_NONE) && P.ppm_flag && ((pos == 1 && P.phys[2 * dir]) || (pos == mx - 1 && P.phys[2 * dir + 1]));
   if (redo) {
 #pragma unroll
@@ -133,6 +153,14 @@ __device__ __forceinline__ void recon3(const Params& P, const double (&qm)[NV], 
     } else {
       muscl_group<NV, 0, 5>(qm, q0, qp, lim, to_hi, to_lo);
       if (NV > 5) muscl_group<NV, 5, NV>(qm, q0, qp, tlim, to_hi, to_lo);
+    }
+    if (P.pb_switch[dir]) {   // pressure-based switching (muscl.f90:231-243): both face values are pulled towards the cell value
+      const double pd = pb_pdif(P, qm[4], q0[4], qp[4], p_far, pos, mx);
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        to_hi[v] = q0[v] + (pd * (to_hi[v] - q0[v]));
+        to_lo[v] = q0[v] - (pd * (q0[v] - to_lo[v]));
+      }
     }
   }
 }

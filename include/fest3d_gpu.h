@@ -80,6 +80,7 @@ typedef struct {
   double density_inf, x_speed_inf, y_speed_inf, z_speed_inf, pressure_inf;
   double tk_inf, tw_inf, vel_mag, MInf;
   double tv_inf;                       /* free-stream nu-tilde of the SA model                   state.f90:105-106 */
+  double tu_inf;                       /* free-stream turbulence intensity in percent (transition = bc)   source.f90:579,1164 */
   double fixed[F3D_NFIX][6];           /* fixed_density(6), fixed_pressure(6) ...                read_bc.f90 */
 } Fest3dGpuConfig;
 

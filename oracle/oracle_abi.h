@@ -38,7 +38,7 @@ typedef struct {
   int time_stepping;                 /* 0 = 'l' local, 1 = 'g' global */
   int limiter[3];                    /* i,j,k limiter_switch */
   int tlimiter[3];                   /* i,j,k tlimiter_switch */
-  int pb_switch[3];                  /* pressure-based switching (0 only) */
+  int pb_switch[3];                  /* i,j,k pressure-based switching (muscl, ppm) */
   int accur;                         /* higher-order BC switch */
   int mu_variation;                  /* 0 constant, 1 sutherland_law */
   int bc_id[6];                      /* imin,imax,jmin,jmax,kmin,kmax; <0 physical, >=0 neighbour block */
@@ -53,6 +53,7 @@ typedef struct {
   double density_inf, x_speed_inf, y_speed_inf, z_speed_inf, pressure_inf;
   double tk_inf, tw_inf, vel_mag, MInf;
   double tv_inf;
+  double tu_inf;                     /* percent */
   double fixed[ORC_NFIX][6];
 } OracleConfig;
 

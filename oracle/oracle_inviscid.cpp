@@ -24,6 +24,7 @@ void Block::setup(const OracleConfig& cfg) {
   yl.alloc(1, imx - 1, 0, jmx + 1, 1, kmx - 1, nv); yr = yl;
   zl.alloc(1, imx - 1, 1, jmx - 1, 0, kmx + 1, nv); zr = zl;
   delta_t.alloc(1, imx - 1, 1, jmx - 1, 1, kmx - 1);
+  pdif.alloc(0, imx, 0, jmx, 0, kmx);
   cells.alloc(imx + 2, jmx + 2, kmx + 2);
   If.alloc(imx + 3, jmx + 2, kmx + 2);
   Jf.alloc(imx + 2, jmx + 3, kmx + 2);
@@ -474,6 +475,36 @@ static void muscl_dir(const Block& B, Arr4& fl, Arr4& fr, int ii, int jj, int kk
   }
 }
 
+// muscl.f90:37-112 / ppm.f90:108-170 pressure_based_switching: pdif of every interior cell from its two neighbours along the
+// direction, the two ghost positions copy the first / last interior value, then both face states are pulled towards the cell
+// value.  pdif is a module array (0:imx,0:jmx,0:kmx) that persists between calls; everything read here is written here.
+static void pressure_based_switching(Block& B, Arr4& fl, Arr4& fr, int ii, int jj, int kk) {
+  Arr3& pdif = B.pdif;
+  const int imx = B.imx, jmx = B.jmx, kmx = B.kmx;
+  for (int k = 1; k <= kmx - 1; ++k)
+    for (int j = 1; j <= jmx - 1; ++j)
+      for (int i = 1; i <= imx - 1; ++i) {
+        double pd2 = std::fabs(B.qp(i + ii, j + jj, k + kk, 5) - B.qp(i - ii, j - jj, k - kk, 5));
+        pdif(i, j, k) = 1 - (pd2 / (pd2 + B.c.pressure_inf));
+      }
+  // ghost cells: the plane at index 0 along the direction takes the plane at 1, the plane at mx takes mx-1
+  const int mx = ii ? imx : (jj ? jmx : kmx);
+  for (int k = 1; k <= (kk ? 1 : kmx - 1); ++k)
+    for (int j = 1; j <= (jj ? 1 : jmx - 1); ++j)
+      for (int i = 1; i <= (ii ? 1 : imx - 1); ++i) {
+        pdif(i - ii, j - jj, k - kk) = pdif(i, j, k);
+        const int i2 = ii ? mx - 1 : i, j2 = jj ? mx - 1 : j, k2 = kk ? mx - 1 : k;
+        pdif(i2 + ii, j2 + jj, k2 + kk) = pdif(i2, j2, k2);
+      }
+  for (int k = 1; k <= kmx - (1 - kk); ++k)
+    for (int j = 1; j <= jmx - (1 - jj); ++j)
+      for (int i = 1; i <= imx - (1 - ii); ++i)
+        for (int l = 1; l <= B.nv; ++l) {
+          fl(i, j, k, l) = B.qp(i - ii, j - jj, k - kk, l) + (pdif(i - ii, j - jj, k - kk) * (fl(i, j, k, l) - B.qp(i - ii, j - jj, k - kk, l)));
+          fr(i, j, k, l) = B.qp(i, j, k, l) - (pdif(i, j, k) * (B.qp(i, j, k, l) - fr(i, j, k, l)));
+        }
+}
+
 // weno.f90:24-93
 static void weno_dir(const Block& B, Arr4& fl, Arr4& fr, int ii, int jj, int kk) {
   const double eps = 1e-6;
@@ -596,13 +627,19 @@ void Block::compute_face_interpolant() {
       break;
     case ORC_MUSCL:
       muscl_dir(*this, xl, xr, 1, 0, 0, c.limiter[0], c.tlimiter[0]);
+      if (c.pb_switch[0] == 1) pressure_based_switching(*this, xl, xr, 1, 0, 0);   // muscl.f90:231-243
       muscl_dir(*this, yl, yr, 0, 1, 0, c.limiter[1], c.tlimiter[1]);
+      if (c.pb_switch[1] == 1) pressure_based_switching(*this, yl, yr, 0, 1, 0);
       muscl_dir(*this, zl, zr, 0, 0, 1, c.limiter[2], c.tlimiter[2]);
+      if (c.pb_switch[2] == 1) pressure_based_switching(*this, zl, zr, 0, 0, 1);
       break;
     case ORC_PPM:
       ppm_dir(*this, xl, xr, 1, 0, 0, c.limiter[0]);
+      if (c.pb_switch[0] == 1) pressure_based_switching(*this, xl, xr, 1, 0, 0);   // ppm.f90:220-243
       ppm_dir(*this, yl, yr, 0, 1, 0, c.limiter[1]);
+      if (c.pb_switch[1] == 1) pressure_based_switching(*this, yl, yr, 0, 1, 0);
       ppm_dir(*this, zl, zr, 0, 0, 1, c.limiter[2]);
+      if (c.pb_switch[2] == 1) pressure_based_switching(*this, zl, zr, 0, 0, 1);
       break;
     case ORC_WENO:
       weno_dir(*this, xl, xr, 1, 0, 0); weno_dir(*this, yl, yr, 0, 1, 0); weno_dir(*this, zl, zr, 0, 0, 1);

@@ -423,10 +423,115 @@ static void add_sa_source(Block& B) {
       }
 }
 
-// source.f90:158-270 add_sst_source
+// gamma_BC of the algebraic Bas-Cakmakcioglu transition model (source.f90:570-585, 1156-1170)
+static double gamma_bc(const OracleConfig& c, double nu_t, double vmag, double dist_i, double re_v) {
+  const double chi_1 = 0.002, chi_2 = 5.0;
+  const double Reynolds_number = c.density_inf * c.vel_mag * 1.0 / c.mu_ref;   // state.f90:89
+  double nu_cr = chi_2 / Reynolds_number;
+  double nu_bc = nu_t / (vmag * dist_i);
+  double re_theta = re_v / 2.193;
+  double re_theta_t = (803.73 * (std::pow(c.tu_inf + 0.6067, -1.027)));
+  double term1 = std::sqrt(std::fmax(re_theta - re_theta_t, 0.) / (chi_1 * re_theta_t));
+  double term2 = std::sqrt(std::fmax(nu_bc - nu_cr, 0.0) / nu_cr);
+  double term_exponential = (term1 + term2);
+  return 1.0 - std::exp(-term_exponential);
+}
+
+// source.f90:985-1194 add_saBC_source (turbulence 'sa', transition 'bc').  KEPT DEFECTS: K-low normal (nx,nx,nx) (:1046), the
+// destruction term has no density factor (:1181).
+static void add_saBC_source(Block& B) {
+  const Rec4 &If = B.If, &Jf = B.Jf, &Kf = B.Kf;
+  for (int k = 1; k <= B.kmx - 1; ++k)
+    for (int j = 1; j <= B.jmx - 1; ++j)
+      for (int i = 1; i <= B.imx - 1; ++i) {
+        double density = B.qp(i, j, k, 1), u = B.qp(i, j, k, 2), v = B.qp(i, j, k, 3), w = B.qp(i, j, k, 4), tv = B.qp(i, j, k, 6);
+        double vmag = std::sqrt(u * u + v * v + w * w);
+        double RhoFace[6] = {B.qp(i - 1, j, k, 1) + density, B.qp(i, j - 1, k, 1) + density, B.qp(i, j, k - 1, 1) + density,
+                             B.qp(i + 1, j, k, 1) + density, B.qp(i, j + 1, k, 1) + density, B.qp(i, j, k + 1, 1) + density};
+        double Area[6] = {If.A(i, j, k), Jf.A(i, j, k), Kf.A(i, j, k), If.A(i + 1, j, k), Jf.A(i, j + 1, k), Kf.A(i, j, k + 1)};
+        double Normal[6][3] = {{If.nx(i, j, k), If.ny(i, j, k), If.nz(i, j, k)},
+                               {Jf.nx(i, j, k), Jf.ny(i, j, k), Jf.nz(i, j, k)},
+                               {Kf.nx(i, j, k), Kf.nx(i, j, k), Kf.nx(i, j, k)},
+                               {If.nx(i + 1, j, k), If.ny(i + 1, j, k), If.nz(i + 1, j, k)},
+                               {Jf.nx(i, j + 1, k), Jf.ny(i, j + 1, k), Jf.nz(i, j + 1, k)},
+                               {Kf.nx(i, j, k + 1), Kf.ny(i, j, k + 1), Kf.nz(i, j, k + 1)}};
+        double gradrho[3];
+        for (int d = 0; d < 3; ++d)
+          gradrho[d] = (-(RhoFace[0]) * Normal[0][d] * Area[0] - (RhoFace[1]) * Normal[1][d] * Area[1] - (RhoFace[2]) * Normal[2][d] * Area[2] +
+                        (RhoFace[3]) * Normal[3][d] * Area[3] + (RhoFace[4]) * Normal[4][d] * Area[4] + (RhoFace[5]) * Normal[5][d] * Area[5]) /
+                       (2 * B.cells.vol(i, j, k));
+        double a = (B.gy(i, j, k, 3) - B.gz(i, j, k, 2)), b = (B.gz(i, j, k, 1) - B.gx(i, j, k, 3)), cc = (B.gx(i, j, k, 2) - B.gy(i, j, k, 1));
+        double Omega = std::sqrt(((a * a) + (b * b) + (cc * cc)));
+        double CD1 = cb2 * ((B.gx(i, j, k, 5) * B.gx(i, j, k, 5)) + (B.gy(i, j, k, 5) * B.gy(i, j, k, 5)) + (B.gz(i, j, k, 5) * B.gz(i, j, k, 5)));
+        double CD2 = ((gradrho[0] * B.gx(i, j, k, 5)) + (gradrho[1] * B.gy(i, j, k, 5)) + (gradrho[2] * B.gz(i, j, k, 5)));
+        double dist_i = B.dist(i, j, k), dist_i_2 = dist_i * dist_i;
+        double k2 = kappa_sa * kappa_sa;
+        double nu = B.mu(i, j, k) / density;
+        double Ji = tv / nu, Ji_2 = Ji * Ji, Ji_3 = Ji_2 * Ji;
+        double fv1 = (Ji_3) / ((Ji_3) + (p3(cv1)));
+        double fv2 = 1.0 - Ji / (1.0 + (Ji * fv1));
+        double S = Omega;
+        double inv_k2_d2 = 1.0 / (k2 * dist_i_2);
+        double Shat = S + tv * fv2 * inv_k2_d2;
+        Shat = std::fmax(Shat, 1.0e-10);
+        double inv_Shat = 1.0 / Shat;
+        double nu_t = tv * fv1;
+        double re_v = dist_i_2 * Omega / nu;
+        double gBC = gamma_bc(B.c, nu_t, vmag, dist_i, re_v);
+        double Production = gBC * cb1 * Shat * tv * B.cells.vol(i, j, k);
+        double r = std::fmin(tv * inv_Shat * inv_k2_d2, 10.0);
+        double g = r + cw2 * ((p6(r)) - r);
+        double g_6 = p6(g);
+        double glim = std::pow((1.0 + p6(cw3)) / (g_6 + p6(cw3)), (1.0 / 6.0));
+        double fw = g * glim;
+        double Destruction = (cw1 * fw * tv * tv / dist_i_2) * (B.cells.vol(i, j, k));
+        double lamda = (density * CD1 / sigma_sa - CD2 * (nu + tv) / sigma_sa) * B.cells.vol(i, j, k);
+        double S_v = (Production - Destruction + lamda);
+        B.residue(i, j, k, 6) = B.residue(i, j, k, 6) - S_v;
+      }
+}
+
+// source.f90:467-604 add_sst_bc_source (sst / sst2003 with transition 'bc'): no CD floor, P_k = mu_t*vort^2 limited by 20 D_k
+// whatever the variant, module gama1 / gama2 as they stand
+static void add_sst_bc_source(Block& B) {
+  for (int k = 1; k <= B.kmx - 1; ++k)
+    for (int j = 1; j <= B.jmx - 1; ++j)
+      for (int i = 1; i <= B.imx - 1; ++i) {
+        double density = B.qp(i, j, k, 1), tk = B.qp(i, j, k, 6), tw = B.qp(i, j, k, 7);
+        double a = (B.gy(i, j, k, 3) - B.gz(i, j, k, 2)), b = (B.gz(i, j, k, 1) - B.gx(i, j, k, 3)), cc = (B.gx(i, j, k, 2) - B.gy(i, j, k, 1));
+        double vort = std::sqrt(((a * a) + (b * b) + (cc * cc)));
+        double CD = 2 * density * sigma_w2 * (B.gx(i, j, k, 5) * B.gx(i, j, k, 6) + B.gy(i, j, k, 5) * B.gy(i, j, k, 6) + B.gz(i, j, k, 5) * B.gz(i, j, k, 6)) / tw;
+        double F1c = B.F1(i, j, k);
+        double gama = B.gama1 * F1c + B.gama2 * (1. - F1c);
+        double beta = beta1 * F1c + beta2 * (1. - F1c);
+        double D_k = bstar * density * tw * tk;
+        double D_w = beta * density * (tw * tw);
+        double P_k = B.mu_t(i, j, k) * (vort * vort);
+        P_k = std::fmin(P_k, 20.0 * D_k);
+        double P_w = (density * gama / B.mu_t(i, j, k)) * P_k;
+        double lamda = (1. - F1c) * CD;
+        double u = B.qp(i, j, k, 2), v = B.qp(i, j, k, 3), w = B.qp(i, j, k, 4);
+        double vmag = std::sqrt(((u * u) + (v * v)) + (w * w));
+        double nu_t = B.mu_t(i, j, k) / density;
+        double d = B.dist(i, j, k);
+        double re_v = density * d * d * vort / B.mu(i, j, k);
+        double gBC = gamma_bc(B.c, nu_t, vmag, d, re_v);
+        P_k = gBC * P_k;
+        double S_k = P_k - D_k;
+        double S_w = P_w - D_w + lamda;
+        S_k = S_k * B.cells.vol(i, j, k);
+        S_w = S_w * B.cells.vol(i, j, k);
+        B.residue(i, j, k, 6) = B.residue(i, j, k, 6) - S_k;
+        B.residue(i, j, k, 7) = B.residue(i, j, k, 7) - S_w;
+      }
+}
+
+// source.f90:94-155 dispatch; :158-270 add_sst_source
 void Block::add_source_term_residue() {
-  if (is_sa(*this)) { add_sa_source(*this); return; }
+  const bool tbc = c.transition == 1;   // 'bc'
+  if (is_sa(*this)) { if (tbc) add_saBC_source(*this); else add_sa_source(*this); return; }
   if (!is_sst(*this)) return;
+  if (tbc) { add_sst_bc_source(*this); return; }
   int limiter;
   if (c.turbulence == ORC_TURB_SST2003) { limiter = 10; gama1 = 5.0 / 9.0; gama2 = 0.44; }
   else limiter = 20;

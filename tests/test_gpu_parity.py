@@ -172,6 +172,22 @@ def test_sa_boundary_conditions(pkg, case_mod, oracle, bc, shape):
     s.close()
 
 
+# ---- MUSCL / PPM pressure-based switching (muscl.f90:37-112, ppm.f90:108-170), every direction, quasi-2-D included -----------
+@pytest.mark.parametrize("interpolant", ["muscl", "ppm"])
+@pytest.mark.parametrize("shape,pb", [((20, 12, 10), (1, 1, 1)), ((33, 9, 1), (1, 0, 1)), ((7, 6, 5), (0, 1, 0))])
+def test_pressure_based_switching(pkg, case_mod, oracle, interpolant, shape, pb):
+    import importlib
+    syn = importlib.import_module("fest-3d_b200.synthetic")
+    blocks = syn.make_duct_blocks(None, n3=shape, scheme_name="ausm", interpolant=interpolant, turbulence="sst", time_step_accuracy="RK2")
+    blk = blocks[0]
+    blk.scheme.pb_switch = pb
+    blk.qp[4] *= 1.0 + 0.05 * np.sin(0.7 * np.arange(blk.imx + 5))[None, None, :] * np.cos(0.9 * np.arange(blk.jmx + 5))[None, :, None]
+    s = _solver(pkg, blocks)
+    _check_residual(oracle, s, blocks)
+    _check_history(oracle, s, blocks, 4)
+    s.close()
+
+
 def test_duct_multiblock_local_links(pkg, case_mod, oracle):
     import importlib
     syn = importlib.import_module("fest-3d_b200.synthetic")

@@ -40,9 +40,9 @@ def test_no_device_is_an_error_not_a_fallback():
 
 def test_config_struct_layout_matches_header():
     capi = importlib.import_module("fest-3d_b200.capi")
-    # 10 ints + 3*3 + 2 + 4*6 + 3*12 + 2 = 83 ints -> padded to 8-byte alignment, then 19 doubles + 11 x 6 fixed values
+    # 10 ints + 3*3 + 2 + 4*6 + 3*12 + 2 = 83 ints -> padded to 8-byte alignment, then 20 doubles + 11 x 6 fixed values
     n_int = 4 + 4 + 2 + 9 + 2 + 24 + 36 + 2
-    size = ((n_int * 4 + 7) // 8) * 8 + (2 + 7 + 5 + 4 + 1 + 66) * 8
+    size = ((n_int * 4 + 7) // 8) * 8 + (2 + 7 + 5 + 4 + 2 + 66) * 8
     assert C.sizeof(capi.Fest3dGpuConfig) == size
     import oracle_py
     assert C.sizeof(oracle_py.OracleConfig) == size

@@ -198,3 +198,44 @@ def test_sa_oracle_closure_identities(oracle, case_mod):
     assert np.allclose(mut[K, J, I], q[0, K, J, I] * q[5, K, J, I] * fv1, rtol=1e-13, atol=0)
     # jmin is a no-slip wall of the duct: ghost mu_t = -mu_t of the first interior cell
     assert np.allclose(mut[K, 2, I], -mut[K, 3, I], rtol=0, atol=0)
+
+
+def test_pressure_based_switching_against_numpy(oracle, case_mod):
+    """muscl.f90:37-112: x states with iPB_switch = 1 must equal the unswitched states blended towards the cell values with
+    pdif = 1 - |p(i+1) - p(i-1)| / (|p(i+1) - p(i-1)| + p_inf), ghost positions 0 / imx taking the value of cells 1 / imx-1
+    (independent numpy restatement on the ghost-filled state the oracle itself used)."""
+    import importlib
+    syn = importlib.import_module("fest-3d_b200.synthetic")
+
+    def run(pb):
+        blocks = syn.make_duct_blocks(None, n3=(9, 6, 5), turbulence="none", mu_ref=0.0, interpolant="muscl")
+        blocks[0].qp[4] *= 1.0 + 0.2 * np.sin(np.arange(blocks[0].imx + 5))[None, None, :]   # make the switch bite
+        blocks[0].scheme.pb_switch = pb
+        w = oracle.OracleWorld(blocks)
+        err, _ = w.residual(1)
+        assert err == 0
+        blk = blocks[0]
+        shp = (blk.n_var, blk.kmx - 1, blk.jmx - 1, blk.imx + 2)
+        return blk, w.get_state(0), w.aux(0, 10, shp), w.aux(0, 11, shp)
+
+    blk, q, xl0, xr0 = run((0, 0, 0))
+    _, q1, xl1, xr1 = run((1, 0, 0))
+    assert np.array_equal(q, q1)
+    K, J = slice(3, 3 + blk.kmx - 1), slice(3, 3 + blk.jmx - 1)
+    imx = blk.imx
+    p = q[4, K, J, :]                       # index i -> column i + 2
+    pdif = np.zeros(p.shape[:2] + (imx + 1,))
+    for i in range(1, imx):
+        pd2 = np.abs(p[..., i + 1 + 2] - p[..., i - 1 + 2])
+        pdif[..., i] = 1 - (pd2 / (pd2 + blk.flow.pressure_inf))
+    pdif[..., 0] = pdif[..., 1]; pdif[..., imx] = pdif[..., imx - 1]
+    # faces 2..imx-1 (face arrays start at face 0); the states of the two boundary faces are overridden afterwards by
+    # reconstruct_boundary_state (boundary_state_reconstruction.f90:124-131)
+    for i in range(2, imx):
+        for v in range(blk.n_var):
+            qm, qc = q[v, K, J, i - 1 + 2], q[v, K, J, i + 2]
+            want_l = qm + (pdif[..., i - 1] * (xl0[v, :, :, i] - qm))
+            want_r = qc - (pdif[..., i] * (qc - xr0[v, :, :, i]))
+            assert np.array_equal(xl1[v, :, :, i], want_l), (i, v)
+            assert np.array_equal(xr1[v, :, :, i], want_r), (i, v)
+    assert np.abs(xl1 - xl0).max() > 0
