@@ -59,7 +59,7 @@ __device__ __forceinline__ double pb_pdif(const Params& P, double p_m, double p_
 // Values a cell contributes to its two faces along one direction, all variables.  `pos` is the cell's index along the
 // direction; the first / last interior cell next to a physical boundary is re-done with the boundary formula when
 // ppm_flag is set (boundary_state_reconstruction.f90:93-123).
-template <int NV, int INTERP>
+template <int NV, int INTERP, bool PB = false>
 __device__ __forceinline__ void line_cell_values(const Params& P, const double* __restrict__ q, const double* __restrict__ vol,
                                                  long long c, long long s, int pos, int mx, int dir, double (&to_hi)[NV], double (&to_lo)[NV]) {
   const bool redo = (INTERP != F3D_INTERP_NONE) && P.ppm_flag && ((pos == 1 && P.phys[2 * dir]) || (pos == mx - 1 && P.phys[2 * dir + 1]));
@@ -85,7 +85,7 @@ __device__ __forceinline__ void line_cell_values(const Params& P, const double* 
       cell_face_values<INTERP>(ql, vl, lim, to_hi[v], to_lo[v]);
     }
   }
-  if ((INTERP == F3D_PPM || INTERP == F3D_MUSCL) && !redo && P.pb_switch[dir]) {
+  if (PB && (INTERP == F3D_PPM || INTERP == F3D_MUSCL) && !redo && P.pb_switch[dir]) {
     const double* __restrict__ pv = q + 4LL * P.L.fs;
     const double pd = pb_pdif(P, pv[c - s], pv[c], pv[c + s], (pos == 0) ? pv[c + 2 * s] : ((pos == mx) ? pv[c - 2 * s] : 0.0), pos, mx);
 #pragma unroll
@@ -136,7 +136,7 @@ __device__ __forceinline__ void muscl_group(const double (&qm)[NV], const double
 
 // MUSCL / first-order values of one cell along one direction from three staged values per variable
 // (muscl.f90:161-196; boundary_state_reconstruction.f90:93-123 for the first / last interior cell when ppm_flag is set)
-template <int NV, int INTERP>
+template <int NV, int INTERP, bool PB = false>
 __device__ __forceinline__ void recon3(const Params& P, const double (&qm)[NV], const double (&q0)[NV], const double (&qp)[NV], int pos, int mx,
                                        int dir, double (&to_hi)[NV], double (&to_lo)[NV], double p_far = 0.0) {
   const bool redo = (INTERP != F3D_INTERP_NONE) && P.ppm_flag && ((pos == 1 && P.phys[2 * dir]) || (pos == mx - 1 && P.phys[2 * dir + 1]));
@@ -154,7 +154,7 @@ __device__ __forceinline__ void recon3(const Params& P, const double (&qm)[NV], 
       muscl_group<NV, 0, 5>(qm, q0, qp, lim, to_hi, to_lo);
       if (NV > 5) muscl_group<NV, 5, NV>(qm, q0, qp, tlim, to_hi, to_lo);
     }
-    if (P.pb_switch[dir]) {   // pressure-based switching (muscl.f90:231-243): both face values are pulled towards the cell value
+    if (PB && P.pb_switch[dir]) {   // pressure-based switching (muscl.f90:231-243): both face values are pulled towards the cell value
       const double pd = pb_pdif(P, qm[4], q0[4], qp[4], p_far, pos, mx);
 #pragma unroll
       for (int v = 0; v < NV; ++v) {

@@ -188,6 +188,20 @@ def test_pressure_based_switching(pkg, case_mod, oracle, interpolant, shape, pb)
     s.close()
 
 
+# ---- transition = bc: algebraic gamma_BC factor on the production term (source.f90:467-604 sst, :985-1194 sa) ---------------
+@pytest.mark.parametrize("turbulence", ["sst", "sst2003", "sa"])
+def test_transition_bc_source(pkg, case_mod, oracle, turbulence):
+    import importlib
+    syn = importlib.import_module("fest-3d_b200.synthetic")
+    blocks = syn.make_duct_blocks(None, n3=(16, 12, 10), turbulence=turbulence, time_step_accuracy="RK4", CFL=0.5)
+    for b in blocks:
+        b.scheme.transition = "bc"
+    s = _solver(pkg, blocks)
+    _check_residual(oracle, s, blocks)
+    _check_history(oracle, s, blocks, 5)
+    s.close()
+
+
 def test_duct_multiblock_local_links(pkg, case_mod, oracle):
     import importlib
     syn = importlib.import_module("fest-3d_b200.synthetic")

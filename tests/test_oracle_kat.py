@@ -239,3 +239,23 @@ def test_pressure_based_switching_against_numpy(oracle, case_mod):
             assert np.array_equal(xl1[v, :, :, i], want_l), (i, v)
             assert np.array_equal(xr1[v, :, :, i], want_r), (i, v)
     assert np.abs(xl1 - xl0).max() > 0
+
+
+@pytest.mark.parametrize("turbulence", ["sst", "sa"])
+def test_transition_bc_only_touches_the_turbulence_equations(oracle, case_mod, turbulence):
+    """transition = bc multiplies the production term of the k / nu-tilde equation by gamma_BC in [0, 1]
+    (source.f90:570-586, 1156-1172): the five flow equations keep their residual bit for bit, the model equation changes."""
+    import importlib
+    syn = importlib.import_module("fest-3d_b200.synthetic")
+    res = {}
+    for tr in ("none", "bc"):
+        blocks = syn.make_duct_blocks(None, n3=(10, 8, 6), turbulence=turbulence)
+        blocks[0].scheme.transition = tr
+        assert blocks[0].n_var == (7 if turbulence == "sst" else 6)      # no extra equation (state.f90:291-320)
+        w = oracle.OracleWorld(blocks)
+        err, r = w.residual(1)
+        assert err == 0
+        res[tr] = r[0]
+    for v in range(5):
+        assert np.array_equal(res["none"][v], res["bc"][v])
+    assert np.abs(res["none"][5] - res["bc"][5]).max() > 0
