@@ -127,6 +127,9 @@ extern "C" int fest3d_gpu_create(Fest3dGpuCtx** out, const Fest3dGpuConfig* cfg,
 
   F3D_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
   ctx->stream = ctx->own_stream;
+  F3D_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+  F3D_CUDA(cudaEventCreateWithFlags(&ctx->ev_pack, cudaEventDisableTiming));
+  F3D_CUDA(cudaEventCreateWithFlags(&ctx->ev_halo, cudaEventDisableTiming));
   const size_t fb = (size_t)L.fs * sizeof(double);
   const int nv = L.nv;
   auto dalloc = [&](double** p, size_t nfields) -> cudaError_t {
@@ -196,6 +199,9 @@ extern "C" int fest3d_gpu_destroy(Fest3dGpuCtx* ctx) {
   for (auto& e : ctx->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   if (ctx->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)ctx->nccl);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
+  if (ctx->ev_pack) cudaEventDestroy(ctx->ev_pack);
+  if (ctx->ev_halo) cudaEventDestroy(ctx->ev_halo);
   delete ctx;
   return 0;
 }
@@ -475,15 +481,87 @@ int exchange(Fest3dGpuCtx** cs, int n) {
   return 0;
 }
 
+// The halo swap can run beside compute when every interface of this process goes over NCCL (one block per GPU, the
+// benchmark layout) and the run is viscous: the Green-Gauss gradients of the cells whose stencil is all-interior do not read
+// ghost cells, so they go first on the compute stream while the swap (pack -> send/recv -> unpack) runs on the context's
+// communication stream; ghost fill, the remaining gradients and the sweep wait for it.  Measured on 2 B200 (one 256^3 block
+// each, profiles/r01_g3_overlap_n2.md): the swap costs 0.02 ms of a 7.56 ms step over NVLink, the two-part gradient launch
+// costs 0.28 ms, so the overlapped schedule is OFF by default and F3D_OVERLAP=1 selects it (wide interfaces on slower links).
+bool can_overlap(Fest3dGpuCtx** cs, int n) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("F3D_OVERLAP"); on = (e && e[0] == '1') ? 1 : 0; }
+  if (!on) return false;
+  bool remote = false;
+  for (int c = 0; c < n; ++c) {
+    if (!cs[c]->P.viscous) return false;
+    for (int f = 0; f < 6; ++f) {
+      if (cs[c]->link[f].kind == 1) return false;
+      if (cs[c]->link[f].kind == 2 && cs[c]->sendbuf[f]) remote = true;
+    }
+  }
+  return remote;
+}
+
+// apply_interface on the communication streams; leaves ev_halo recorded behind the last unpack of every context
+int exchange_overlapped(Fest3dGpuCtx** cs, int n) {
+  for (int c = 0; c < n; ++c) {
+    Fest3dGpuCtx* ctx = cs[c];
+    F3D_CUDA(cudaSetDevice(ctx->device));
+    for (int f = 0; f < 6; ++f)
+      if (ctx->sendbuf[f] && ctx->link[f].kind == 2) { int rc = launch_pack(ctx, f + 1); if (rc) return rc; }
+    F3D_CUDA(cudaEventRecord(ctx->ev_pack, ctx->stream));
+    F3D_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_pack, 0));
+  }
+  std::vector<Msg> sends, recvs;
+  for (int c = 0; c < n; ++c)
+    for (int f = 0; f < 6; ++f) {
+      const Link& lk = cs[c]->link[f];
+      if (lk.kind != 2) continue;
+      sends.push_back({lk.rank, cs[c]->cfg.block_id, f + 1, cs[c], f + 1});
+      recvs.push_back({lk.rank, lk.neighbour_block, cs[c]->cfg.otherface[f], cs[c], f + 1});
+    }
+  auto key = [](const Msg& a, const Msg& b) { return std::tie(a.peer_rank, a.block, a.face) < std::tie(b.peer_rank, b.block, b.face); };
+  std::sort(sends.begin(), sends.end(), key);
+  std::sort(recvs.begin(), recvs.end(), key);
+  g_nccl.GroupStart();
+  for (const Msg& m : sends) {
+    cudaSetDevice(m.ctx->device);
+    g_nccl.Send(m.ctx->sendbuf[m.my_face - 1], m.ctx->buf_elems[m.my_face - 1], kNcclFloat64, m.peer_rank, (ncclComm_t)m.ctx->nccl, m.ctx->comm_stream);
+  }
+  for (const Msg& m : recvs) {
+    cudaSetDevice(m.ctx->device);
+    g_nccl.Recv(m.ctx->recvbuf[m.my_face - 1], m.ctx->buf_elems[m.my_face - 1], kNcclFloat64, m.peer_rank, (ncclComm_t)m.ctx->nccl, m.ctx->comm_stream);
+  }
+  if (g_nccl.GroupEnd() != 0) return F3D_ERR_CUDA;
+  for (int c = 0; c < n; ++c) {
+    Fest3dGpuCtx* ctx = cs[c];
+    F3D_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t compute = ctx->stream;
+    ctx->stream = ctx->comm_stream;   // the unpack kernels of this swap run on the communication stream
+    int rc = 0;
+    for (int f = 0; f < 6 && !rc; ++f)
+      if (ctx->link[f].kind == 2) rc = launch_unpack(ctx, f + 1, ctx->recvbuf[f]);
+    ctx->stream = compute;
+    if (rc) return rc;
+    F3D_CUDA(cudaEventRecord(ctx->ev_halo, ctx->comm_stream));
+  }
+  return 0;
+}
+
 // one get_total_conservative_Residue (+ update) on every context
 int stage(Fest3dGpuCtx** cs, int n, bool update, double TF, double SF, int use_sum, int first, int last) {
-  int rc = exchange(cs, n);
+  const bool overlap = can_overlap(cs, n);
+  int rc = overlap ? exchange_overlapped(cs, n) : exchange(cs, n);
   if (rc) return rc;
   for (int c = 0; c < n; ++c) {
     Fest3dGpuCtx* ctx = cs[c];
     F3D_CUDA(cudaSetDevice(ctx->device));
+    if (overlap) {
+      if ((rc = launch_gradients(ctx, 1))) return rc;                       // beside the swap
+      F3D_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_halo, 0));
+    }
     if ((rc = launch_bc(ctx))) return rc;
-    if (ctx->P.viscous && (rc = launch_gradients(ctx))) return rc;
+    if (ctx->P.viscous && (rc = launch_gradients(ctx, overlap ? 2 : 0))) return rc;
     if (!update) {
       if ((rc = launch_residual(ctx, MODE_RESIDUE_ONLY, 1.0, 1.0, 0, 1, 0))) return rc;
       continue;

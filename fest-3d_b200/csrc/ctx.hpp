@@ -59,6 +59,7 @@ struct Ctx {
   Params P;
   int device = 0;
   cudaStream_t stream = nullptr, own_stream = nullptr, comm_stream = nullptr;
+  cudaEvent_t ev_pack = nullptr, ev_halo = nullptr;   // compute -> comm stream hand-off and back (overlapped halo swap)
   // device memory
   double* qp = nullptr;       // nv fields (current state)
   double* qp2 = nullptr;      // nv fields (next state of the fused update; swapped with qp)
@@ -113,7 +114,7 @@ struct Ctx {
 // kernel launchers (each returns a CUDA error code through the context)
 int launch_temp(Ctx* ctx);
 int launch_bc(Ctx* ctx);
-int launch_gradients(Ctx* ctx);
+int launch_gradients(Ctx* ctx, int mode = 0);   // mode 1: cells with an all-interior stencil, 2: the others, 0: all
 int launch_residual(Ctx* ctx, int mode, double TF, double SF, int use_store_sum, int first_stage, int last_stage);
 int launch_blend(Ctx* ctx, double a, double b);
 int launch_copy_fields(Ctx* ctx, double* dst, const double* src, int nfields);

@@ -14,12 +14,19 @@ namespace f3d {
 
 template <int NG>
 __global__ void __launch_bounds__(128, 5) k_gradients(const Params P, const double* __restrict__ q, const double* __restrict__ temp,
-                                                   const double* __restrict__ geom, double* __restrict__ grad, double* __restrict__ mu3, int* err) {
+                                                   const double* __restrict__ geom, double* __restrict__ grad, double* __restrict__ mu3, int* err,
+                                                   int mode) {
   const Layout& L = P.L;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
   const int k = blockIdx.z;
   if (i > L.imx || j > L.jmx) return;
+  // mode 1: only the cells whose whole stencil is interior (no ghost cell read: they can run while the halo swap and the
+  // boundary fill are still in flight); mode 2: the rest; mode 0: all cells
+  if (mode) {
+    const bool inner = i >= 2 && i <= L.imx - 2 && j >= 2 && j <= L.jmx - 2 && k >= 2 && k <= L.kmx - 2;
+    if (inner != (mode == 1)) return;
+  }
   const long long fs = L.fs, c = L.idx(i, j, k), sj = L.sj, sk = L.sk;
   const double* gI = geom + (long long)G_IA * fs;
   const double* gJ = geom + (long long)G_JA * fs;
@@ -158,14 +165,15 @@ __global__ void k_gradient_bc(const Params P, const double* __restrict__ q, cons
   }
 }
 
-int launch_gradients(Ctx* ctx) {
+int launch_gradients(Ctx* ctx, int mode) {
   const Layout& L = ctx->P.L;
   dim3 block(32, 4, 1);
   dim3 grid((L.imx + 1 + 31) / 32, (L.jmx + 1 + 3) / 4, L.kmx + 1);
-  if (ctx->P.sa) k_gradients<5><<<grid, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->err_dev);
-  else if (ctx->P.sst) k_gradients<6><<<grid, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->err_dev);
-  else k_gradients<4><<<grid, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->err_dev);
+  if (ctx->P.sa) k_gradients<5><<<grid, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->err_dev, mode);
+  else if (ctx->P.sst) k_gradients<6><<<grid, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->err_dev, mode);
+  else k_gradients<4><<<grid, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->err_dev, mode);
   ctx->launches++;
+  if (mode == 1) { F3D_CUDA(cudaGetLastError()); return 0; }   // the ghost rules follow the second part
   const int mx[3] = {L.imx, L.jmx, L.kmx};
   int mask = 0, na = 1, nb = 1;
   for (int face = 1; face <= 6; ++face) {
