@@ -281,6 +281,14 @@ extern "C" int fest3d_gpu_set_geometry(Fest3dGpuCtx* ctx, const double* cells, c
   return 0;
 }
 
+// find_wall_dist (src/wall/wall_dist.f90:84-131) on the device; replaces the `dist` argument of fest3d_gpu_set_geometry
+extern "C" int fest3d_gpu_find_wall_dist(Fest3dGpuCtx* ctx, const double* nodes, const double* wall_xyz, long long n_wall, double* dist_out,
+                                         double* kernel_ms) {
+  if (!ctx || !nodes || n_wall < 0 || (n_wall > 0 && !wall_xyz)) return fail(ctx, F3D_ERR_ARGUMENT);
+  F3D_CUDA(cudaSetDevice(ctx->device));
+  return launch_wall_distance(ctx, nodes, wall_xyz, n_wall, dist_out, kernel_ms);
+}
+
 // Full-state transfers: one contiguous DMA between the host array (reference layout) and a device staging buffer, plus a
 // re-layout kernel (pitched per-row DMA of the padded fields reaches only about half of the PCIe rate).
 static int ensure_state_staging(Fest3dGpuCtx* ctx) {

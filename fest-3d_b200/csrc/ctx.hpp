@@ -125,6 +125,7 @@ int launch_unpack(Ctx* ctx, int face, const double* buf);
 int launch_global_dt(Ctx* ctx);
 int launch_ghost_shell_copy(Ctx* ctx, double* dst, const double* src);
 int launch_state_relayout(Ctx* ctx, double* fields, double* flat, int to_fields);
+int launch_wall_distance(Ctx* ctx, const double* nodes_host, const double* wall_host, long long n_wall, double* dist_out, double* kernel_ms);
 
 // residual modes
 enum { MODE_RESIDUE_ONLY = 0, MODE_UPDATE = 1 };

@@ -106,6 +106,17 @@ class GpuBlock:
         self._check(self.L.fest3d_gpu_get_state(self.h, _dp(q)))
         return q
 
+    def find_wall_dist(self, wall_nodes, want_time=False):
+        """find_wall_dist (wall_dist.f90:84-131) on the device from the block's node array and the global list of wall surface
+        nodes; fills the context's wall-distance field and returns dist(-2:kmx+2, -2:jmx+2, -2:imx+2)."""
+        b = self.blk
+        nodes = np.ascontiguousarray(b.nodes, dtype=np.float64)
+        wall = np.ascontiguousarray(wall_nodes, dtype=np.float64).reshape(-1, 3)
+        out = np.empty((b.kmx + 5, b.jmx + 5, b.imx + 5))
+        ms = C.c_double(0.0)
+        self._check(self.L.fest3d_gpu_find_wall_dist(self.h, _dp(nodes), _dp(wall) if len(wall) else None, len(wall), _dp(out), C.byref(ms)))
+        return (out, ms.value) if want_time else out
+
     def get_residue(self):
         b = self.blk
         r = np.empty((b.n_var, b.kmx - 1, b.jmx - 1, b.imx - 1))

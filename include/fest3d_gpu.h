@@ -105,6 +105,13 @@ int fest3d_gpu_set_geometry(Fest3dGpuCtx* ctx, const double* cells, const double
                             const double* Kfaces, const double* dist /* may be NULL without turbulence */);
 int fest3d_gpu_set_state(Fest3dGpuCtx* ctx, const double* qp);
 int fest3d_gpu_get_state(Fest3dGpuCtx* ctx, double* qp);
+/* SURVEY 8(f) rank 1 -- find_wall_dist (src/wall/wall_dist.f90:84-131) on the device: minimum distance of every node
+ * nodes(-2:imx+3,-2:jmx+3,-2:kmx+3) (nodetype records x,y,z) to the n_wall surface nodes wall_xyz[n_wall][3] (the contents of
+ * the surface-node file, wall_dist.f90:74-82), averaged over the eight nodes of each cell.  Fills the context's wall-distance
+ * field (so it replaces the `dist` argument of fest3d_gpu_set_geometry; call it after set_geometry) and, if dist_out != NULL,
+ * returns dist(-2:imx+2,-2:jmx+2,-2:kmx+2).  kernel_ms (may be NULL) receives the device time of the node kernel. */
+int fest3d_gpu_find_wall_dist(Fest3dGpuCtx* ctx, const double* nodes, const double* wall_xyz, long long n_wall, double* dist_out,
+                              double* kernel_ms);
 
 /* the hot path -------------------------------------------------------------------------------------------------- */
 /* n_iters iterations of { get_next_solution ; find_resnorm }.  current_iter is control%current_iter of the first

@@ -59,6 +59,9 @@ typedef struct {
 
 typedef struct OracleWorld OracleWorld;
 
+/* wall_dist.f90:84-131 (test infrastructure for the device wall-distance kernel) */
+void oracle_find_wall_dist(int imx, int jmx, int kmx, const double* nodes, const double* wall, long long n_wall, double* dist_out);
+
 /* A world is the set of blocks (= MPI ranks of the reference) stepped in lock step. */
 OracleWorld* oracle_create(int n_blocks, const OracleConfig* cfgs);
 void oracle_destroy(OracleWorld* w);

@@ -187,4 +187,28 @@ void oracle_kat_states(int interpolant, int n, const double* q, const double* vo
   for (int i = 0; i <= c.imx + 1; ++i) { left[i] = B.xl(i, 1, 1, 1); right[i] = B.xr(i, 1, 1, 1); }
 }
 
+// wall_dist.f90:84-131 find_wall_dist: brute-force minimum distance of every node (-2:imx+3, ...) to the wall surface nodes, then the
+// cell value as 0.125 x the sum of its eight nodes in the reference's order.  nodes: (x,y,z) records, i fastest; wall: n x 3.
+void oracle_find_wall_dist(int imx, int jmx, int kmx, const double* nodes, const double* wall, long long n_wall, double* dist_out) {
+  const long long ni = imx + 6, nj = jmx + 6, nk = kmx + 6;
+  std::vector<double> nd((size_t)(ni * nj * nk));
+  for (long long n = 0; n < ni * nj * nk; ++n) {
+    double best = 1.e+20;
+    const double x = nodes[3 * n], y = nodes[3 * n + 1], z = nodes[3 * n + 2];
+    for (long long w = 0; w < n_wall; ++w) {
+      const double a = wall[3 * w] - x, b = wall[3 * w + 1] - y, c = wall[3 * w + 2] - z;
+      const double current_dist = std::sqrt((a * a) + (b * b) + (c * c));
+      best = std::fmin(best, current_dist);
+    }
+    nd[(size_t)n] = best;
+  }
+  auto at = [&](int i, int j, int k) { return nd[(size_t)((i + 2) + ni * ((j + 2) + nj * (long long)(k + 2)))]; };
+  for (int k = -2; k <= kmx + 2; ++k)
+    for (int j = -2; j <= jmx + 2; ++j)
+      for (int i = -2; i <= imx + 2; ++i)
+        dist_out[(size_t)((i + 2) + (long long)(imx + 5) * ((j + 2) + (long long)(jmx + 5) * (k + 2)))] =
+            0.125 * (at(i, j, k) + at(i, j + 1, k) + at(i, j + 1, k + 1) + at(i, j, k + 1) + at(i + 1, j, k + 1) + at(i + 1, j, k) + at(i + 1, j + 1, k) +
+                     at(i + 1, j + 1, k + 1));
+}
+
 }  // extern "C"

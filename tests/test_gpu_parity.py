@@ -266,6 +266,32 @@ def test_boundary_conditions(pkg, case_mod, oracle, bc, shape, accur):
     s.close()
 
 
+# ---- wall distance on the device (wall_dist.f90:84-131) ---------------------------------------------------
+@pytest.mark.parametrize("shape", [(7, 6, 5), (40, 33, 9)])
+def test_wall_distance_on_device(pkg, case_mod, oracle, shape):
+    import ctypes as C
+    import importlib
+    syn = importlib.import_module("fest-3d_b200.synthetic")
+    geo = importlib.import_module("fest-3d_b200.geometry")
+    blocks = syn.make_duct_blocks(None, n3=shape, turbulence="sst")
+    blk = blocks[0]
+    wall = geo.surface_nodes(blk.nodes, blk.bc_id)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    want = np.empty((blk.kmx + 5, blk.jmx + 5, blk.imx + 5))
+    oracle.lib().oracle_find_wall_dist(blk.imx, blk.jmx, blk.kmx, dp(np.ascontiguousarray(blk.nodes)), dp(np.ascontiguousarray(wall)), len(wall), dp(want))
+    s = _solver(pkg, blocks)
+    got = s.blocks[0].find_wall_dist(wall)
+    assert np.abs(got - want).max() <= 1e-13 * np.abs(want).max()
+    # the field the kernels read is the one just computed: a residual evaluated now must match an oracle fed with the same dist
+    blk.dist = want
+    s2 = _solver(pkg, blocks)
+    r_ref = s2.residual()[0]
+    r_new = s.residual()[0]
+    assert np.abs(r_new - r_ref).max() <= 1e-12 * np.abs(r_ref).max()
+    assert np.all(s.blocks[0].find_wall_dist(np.zeros((0, 3))) == 1.e+20)
+    s.close(); s2.close()
+
+
 def test_unsupported_is_an_error_not_a_fallback(pkg, case_mod):
     import importlib
     syn = importlib.import_module("fest-3d_b200.synthetic")

@@ -259,3 +259,27 @@ def test_transition_bc_only_touches_the_turbulence_equations(oracle, case_mod, t
     for v in range(5):
         assert np.array_equal(res["none"][v], res["bc"][v])
     assert np.abs(res["none"][5] - res["bc"][5]).max() > 0
+
+
+def _wall_case(shape=(7, 6, 5)):
+    import importlib
+    syn = importlib.import_module("fest-3d_b200.synthetic")
+    geo = importlib.import_module("fest-3d_b200.geometry")
+    blk = syn.make_duct_blocks(None, n3=shape, turbulence="sst")[0]
+    wall = geo.surface_nodes(blk.nodes, blk.bc_id)          # the four no-slip walls of the duct, rounded like the text file
+    return blk, geo, wall
+
+
+def test_wall_distance_oracle_against_kdtree(oracle, case_mod):
+    """wall_dist.f90:84-131 re-stated as a brute-force loop must agree with the host harness's nearest-neighbour search, and the
+    distance of the first cell off a wall must be about half a cell."""
+    blk, geo, wall = _wall_case()
+    out = np.empty((blk.kmx + 5, blk.jmx + 5, blk.imx + 5))
+    oracle.lib().oracle_find_wall_dist(blk.imx, blk.jmx, blk.kmx, _dp(np.ascontiguousarray(blk.nodes)), _dp(np.ascontiguousarray(wall)), len(wall), _dp(out))
+    ref = geo.wall_distance(blk.nodes, wall)
+    assert np.abs(out - ref).max() <= 1e-14
+    h = 1.0 / (blk.jmx - 1)
+    assert 0.3 * h < out[5, 3, 5] < 0.8 * h                # first cell above the jmin wall
+    empty = np.empty_like(out)
+    oracle.lib().oracle_find_wall_dist(blk.imx, blk.jmx, blk.kmx, _dp(np.ascontiguousarray(blk.nodes)), None, 0, _dp(empty))
+    assert np.all(empty == 1.e+20)
