@@ -1,6 +1,10 @@
 // Generation-3 fused sweep: the instantiations that carry the code of the rare options (MUSCL / PPM pressure-based switching,
 // transition = bc); see sweep3_kernel.cuh.
+#ifdef F3D_STAGE_BULK   // experimental: planes staged by cp.async.bulk row copies + mbarrier instead of per-thread cp.async
+#include "sweep3_kernel_bulk.cuh"
+#else
 #include "sweep3_kernel.cuh"
+#endif
 
 namespace f3d {
 
