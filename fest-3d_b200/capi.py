@@ -10,7 +10,7 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfest3d_gpu.so")
+LIB_PATH = os.environ.get("F3D_LIB") or os.path.join(HERE, "libfest3d_gpu.so")   # F3D_LIB: an alternative build (A/B measurements)
 NFIX = 11
 
 SYMBOLS = [

@@ -64,22 +64,30 @@ int launch_zero_fields(Ctx* ctx, double* dst, int nfields) {
 }
 
 // every cell that is not interior: dst <- src (so that the new-state buffer is the complete array the reference
-// would hold after its in-place update)
+// would hold after its in-place update).  Only the shell is enumerated (a full-volume launch with an early exit for
+// the interior cost 83 us per stage at 256^3): blockIdx.y = plane k; ghost planes copy every cell, interior planes
+// the frame of six ghost rows (whole i extent) and six ghost columns of the interior rows.
 __global__ void k_ghost_shell(const Params P, double* __restrict__ dst, const double* __restrict__ src) {
   const Layout& L = P.L;
-  const int i = -2 + blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = -2 + blockIdx.y * blockDim.y + threadIdx.y;
-  const int k = -2 + blockIdx.z;
-  if (i > L.imx + 2 || j > L.jmx + 2) return;
-  const bool interior = i >= 1 && i <= L.imx - 1 && j >= 1 && j <= L.jmx - 1 && k >= 1 && k <= L.kmx - 1;
-  if (interior) return;
-  const long long c = L.idx(i, j, k);
-  for (int v = 0; v < L.nv; ++v) dst[v * L.fs + c] = src[v * L.fs + c];
+  const int k = -2 + blockIdx.y;
+  const int ni = L.imx + 5, nj = L.jmx + 5;
+  const bool ghost_plane = k < 1 || k > L.kmx - 1;
+  const int n_frame = 6 * ni + 6 * (L.jmx - 1);
+  const int n = ghost_plane ? ni * nj : n_frame;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    int i, j;
+    if (ghost_plane) { i = -2 + t % ni; j = -2 + t / ni; }
+    else if (t < 6 * ni) { const int r = t / ni; i = -2 + t % ni; j = (r < 3) ? -2 + r : L.jmx + (r - 3); }
+    else { const int u = t - 6 * ni, cidx = u % 6; j = 1 + u / 6; i = (cidx < 3) ? -2 + cidx : L.imx + (cidx - 3); }
+    const long long c = L.idx(i, j, k);
+    for (int v = 0; v < L.nv; ++v) dst[v * L.fs + c] = src[v * L.fs + c];
+  }
 }
 
 int launch_ghost_shell_copy(Ctx* ctx, double* dst, const double* src) {
   const Layout& L = ctx->P.L;
-  dim3 block(64, 4), grid((L.imx + 5 + 63) / 64, (L.jmx + 5 + 3) / 4, L.kmx + 5);
+  const int per_plane = 6 * (L.imx + 5) + 6 * (L.jmx - 1);
+  dim3 block(256), grid((per_plane + 255) / 256, L.kmx + 5);
   k_ghost_shell<<<grid, block, 0, ctx->stream>>>(ctx->P, dst, src);
   ctx->launches++;
   F3D_CUDA(cudaGetLastError());
