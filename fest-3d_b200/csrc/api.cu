@@ -76,7 +76,11 @@ extern "C" int fest3d_gpu_create(Fest3dGpuCtx** out, const Fest3dGpuConfig* cfg,
   memset(&P, 0, sizeof(P));
   Layout& L = P.L;
   L.imx = cfg->imx; L.jmx = cfg->jmx; L.kmx = cfg->kmx; L.nv = cfg->n_var; L.ng = sst ? 6 : (sa ? 5 : 4);
+#ifdef F3D_STAGE_BULK   // a row must hold i = -2 .. imx+2 behind its 15-element lead-in, so that a tensor map can address it as one dimension
+  L.pi = ((cfg->imx + 18 + 15) / 16) * 16; L.pj = cfg->jmx + 6; L.pk = cfg->kmx + 6;
+#else
   L.pi = ((cfg->imx + 6 + 15) / 16) * 16; L.pj = cfg->jmx + 6; L.pk = cfg->kmx + 6;
+#endif
   L.sj = L.pi; L.sk = (long long)L.pi * L.pj;
   L.base = 13 + 2 + 2 * L.sj + 2 * L.sk;
   L.fs = ((13 + L.sk * L.pk + 31) / 32) * 32;
@@ -141,7 +145,8 @@ extern "C" int fest3d_gpu_create(Fest3dGpuCtx** out, const Fest3dGpuConfig* cfg,
   F3D_CUDA(dalloc(&ctx->temp, 1)); F3D_CUDA(dalloc(&ctx->dt, 1)); F3D_CUDA(dalloc(&ctx->geom, G_NFIELDS));
   if (cfg->time_accuracy != F3D_T_NONE) F3D_CUDA(dalloc(&ctx->ustore, nv));
   if (cfg->time_accuracy == F3D_T_RK2 || cfg->time_accuracy == F3D_T_RK4) F3D_CUDA(dalloc(&ctx->rstore, nv));
-  if (P.viscous) { F3D_CUDA(dalloc(&ctx->grad, 3 * L.ng)); F3D_CUDA(dalloc(&ctx->mu, 3)); }
+  ctx->n_mu = sst ? 3 : (sa ? 2 : 1);
+  if (P.viscous) { F3D_CUDA(dalloc(&ctx->grad, 3 * L.ng)); F3D_CUDA(dalloc(&ctx->mu, ctx->n_mu + 3)); }
   // staging for the AoS records: the largest face array
   const size_t rec_max = (size_t)4 * (L.imx + 6) * (L.jmx + 6) * (L.kmx + 6) * sizeof(double);
   F3D_CUDA(cudaMalloc((void**)&ctx->staging, rec_max));
@@ -153,6 +158,31 @@ extern "C" int fest3d_gpu_create(Fest3dGpuCtx** out, const Fest3dGpuConfig* cfg,
   F3D_CUDA(cudaMalloc((void**)&ctx->err_dev, sizeof(int) * 4));
   F3D_CUDA(cudaMemsetAsync(ctx->err_dev, 0, sizeof(int) * 4, ctx->stream));
   F3D_CUDA(cudaMallocHost((void**)&ctx->err_host, sizeof(int) * 4));
+#ifdef F3D_STAGE_BULK
+  {   // 4-D tensor maps [field][k][j][i] (pitches fs, sk, sj) of the arrays the sweep stages; box = one tile plane of all fields
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return fail(ctx, F3D_ERR_CUDA);
+    auto encode = [&](CUtensorMap* tm, double* base, int nfields, int rows, int box_fields) -> bool {
+      const cuuint64_t dims[4] = {(cuuint64_t)L.sj, (cuuint64_t)L.pj, (cuuint64_t)L.pk, (cuuint64_t)nfields};
+      const cuuint64_t strides[3] = {(cuuint64_t)L.sj * 8, (cuuint64_t)L.sk * 8, (cuuint64_t)L.fs * 8};
+      const cuuint32_t box[4] = {(cuuint32_t)(kG3TX + 4), (cuuint32_t)rows, 1u, (cuuint32_t)box_fields};
+      const cuuint32_t estr[4] = {1, 1, 1, 1};
+      return ((EncodeFn)fn)(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    };
+    bool ok = encode(&ctx->tm_q[0], ctx->qp, nv, kG3TY + 4, nv) && encode(&ctx->tm_q[1], ctx->qp2, nv, kG3TY + 4, nv);
+    ctx->tm_q_ptr[0] = ctx->qp; ctx->tm_q_ptr[1] = ctx->qp2;
+    if (P.viscous) {
+      const int ngf = 3 * L.ng, naux = ctx->n_mu + 3;
+      ok = ok && encode(&ctx->tm_grad, ctx->grad, ngf, kG3TY + 2, (ngf + 1) & ~1) && encode(&ctx->tm_aux, ctx->mu, naux, kG3TY + 2, (naux + 1) & ~1);
+    }
+    if (!ok) { fprintf(stderr, "fest3d_gpu: cuTensorMapEncodeTiled failed\n"); return fail(ctx, F3D_ERR_CUDA); }
+    ctx->tmaps_ok = true;
+  }
+#endif
   // ghost-gradient face records
   if (P.viscous) {
     size_t tot = 0;
@@ -259,6 +289,8 @@ extern "C" int fest3d_gpu_set_geometry(Fest3dGpuCtx* ctx, const double* cells, c
     // record offset (i+2) + (imx+6)*((j+2) + (jmx+5)*(k+2)) of the actual array.  Reproduced here on the host, once.
     std::vector<double> mu0((size_t)fs, ctx->cfg.mu_ref);
     F3D_CUDA(cudaMemcpyAsync(ctx->mu, mu0.data(), fs * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    F3D_CUDA(cudaMemcpyAsync(ctx->mu + (long long)ctx->n_mu * fs, ctx->geom + (long long)G_CX * fs, 3 * fs * sizeof(double), cudaMemcpyDeviceToDevice,
+                             ctx->stream));   // the centre fields behind the viscosity fields: one "aux" array for the tensor-map staging
     F3D_CUDA(cudaStreamSynchronize(ctx->stream));
     const int mx[3] = {L.imx, L.jmx, L.kmx};
     const double* arrs[3] = {Ifaces, Jfaces, Kfaces};

@@ -4,6 +4,7 @@
 // already variable-major, src/vartypes.f90:21-26).  Row pitch sj is a multiple of 16 doubles and the allocation is
 // shifted by 13 doubles so that interior cell i=1 of every row starts a 128-byte line.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -11,6 +12,8 @@
 #include "../../include/fest3d_gpu.h"
 
 namespace f3d {
+
+constexpr int kG3TX = 32, kG3TY = 4;   // tile of the generation-3 sweep (sweep3_kernel*.cuh), also the box of its tensor maps
 
 struct Layout {
   int imx, jmx, kmx, nv, ng;        // ng = number of gradient components (4, 5 with sa, 6 with sst)
@@ -70,7 +73,12 @@ struct Ctx {
   double* dt = nullptr;       // 1 field
   double* geom = nullptr;     // G_NFIELDS fields
   double* grad = nullptr;     // 3*ng fields: component c, direction d -> field 3*c+d
-  double* mu = nullptr;       // mu, mu_t, F1 (3 fields)
+  double* mu = nullptr;       // "aux" fields: mu [, mu_t [, F1]] as the model has them, then a copy of the cell centre x,y,z
+  int n_mu = 0;               // 1 laminar, 2 sa, 3 sst
+  // 4-D tensor maps [field][k][j][i] of the arrays the sweep stages (only used by the -DF3D_STAGE_BULK build)
+  CUtensorMap tm_q[2], tm_grad, tm_aux;
+  double* tm_q_ptr[2] = {nullptr, nullptr};
+  bool tmaps_ok = false;
   double* gbc = nullptr;      // per-face (A,nx,ny,nz) records the ghost-gradient rule reads (mis-indexed for J/K faces)
   long long gbc_off[6];
   long long* gbc_off_dev = nullptr;   // the same offsets on the device

@@ -22,9 +22,10 @@
 // src/boundary/boundary_state_reconstruction.f90:93-131; src/face/flux/convective/*.f90, scheme.f90:111-141;
 // src/viscous.f90:144-447; src/source.f90:158-270; src/time.f90:122-246,366-531; src/resnorm.f90:171-199).
 #pragma once
-// EXPERIMENTAL variant of sweep3_kernel.cuh (build with EXTRA=-DF3D_STAGE_BULK): the staged planes are filled by the bulk-copy
-// engine (cp.async.bulk -> UBLKCP, one copy per field row, completion on an mbarrier) instead of per-thread cp.async.  Correct
-// (127 GPU parity tests, racecheck clean) but measured slower so far: see profiles/r01_g3_summary.md.
+// EXPERIMENTAL variant of sweep3_kernel.cuh (build with EXTRA=-DF3D_STAGE_BULK): the staged planes are filled by the TMA engine
+// instead of per-thread cp.async -- three 4-D tensor copies per plane (cp.async.bulk.tensor -> UTMALDG: q, gradients, aux = mu
+// fields + cell centre), completion on an mbarrier.  An earlier form with one cp.async.bulk (UBLKCP) per field row was correct but
+// no faster than cp.async (profiles/r01_g3_summary.md).
 #include "sweep_common.cuh"
 
 namespace f3d {
@@ -94,6 +95,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                "r"(smem_u32(b))
                : "memory");
 }
+__device__ __forceinline__ void tma_g2s_4d(void* dst, const CUtensorMap* tm, int x, int y, int z, int f, void* b) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(smem_u32(dst)),
+               "l"(tm), "r"(x), "r"(y), "r"(z), "r"(f), "r"(smem_u32(b))
+               : "memory");
+}
+struct TMaps { CUtensorMap q, grad, aux; };
 __device__ __forceinline__ void bar_all() { asm volatile("bar.sync 0;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const double* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void bar_group(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -258,8 +265,9 @@ __device__ __forceinline__ void cell_work(const Params& P, const KArgs& a, doubl
 
 // RARE gates the code of the seldom-used options (pressure-based switching, transition = bc): compiled into a second set of
 // instantiations (sweep3_rare.cu) because even switched off it cost the register-tight common path 4.5 % (5.82 vs 5.57 ms).
+static_assert(TX == kG3TX && TY == kG3TY, "tensor-map boxes are encoded for this tile (api.cu)");
 template <int NV, int INTERP, int SCHEME, bool VISC, bool RARE>
-__global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a) {
+__global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a, const __grid_constant__ TMaps tm) {
   using S = Sm<NV, VISC>;
   constexpr bool SST = (NV == 7), SA = (NV == 6), TURB = SST || SA;
   constexpr bool SMQ = (INTERP == F3D_MUSCL || INTERP == F3D_INTERP_NONE);   // 3-point stencils read the staged planes
@@ -336,35 +344,21 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a)
     pos = (d == 0) ? i : j; mx = (d == 0) ? Ly.imx : ((d == 1) ? Ly.jmx : Ly.kmx);
   };
 
-  // ---- staging of a plane by the bulk-copy engine (cp.async.bulk -> UBLKCP): one copy per field row, issued by the lanes of
-  // warp W_C, completion counted in bytes on the mbarrier of the buffer (plane kk -> buffer kk & 1)
+  // ---- staging of a plane by the TMA engine: one elected thread issues a tensor copy per staged array (box = 36 columns x
+  // TY+4 / TY+2 rows x 1 plane x all fields, landing as [field][row][col]); cells outside the arrays are zero-filled, so the byte
+  // count the mbarrier expects is always that of the full boxes.  Tensor coordinates: x = i + 15, y = j + 2, z = k + 2
+  // (ctx.hpp:Layout: idx = 15 + i + sj (j+2) + sk (k+2)).
   void* const mbar = smem + S::OFF_MBAR;
-  constexpr int NCOPY_Q = NV * (TY + 4), NCOPY = NCOPY_Q + S::NR * (TY + 2);
-  const int ncol = min(PW, ((Ly.imx + 2 - (i0 - 2) + 1) + 1) & ~1);            // columns that exist (cells <= imx+2), even count
-  const int nrow_q = min(TY + 4, Ly.jmx + 2 - (j0 - 2) + 1), nrow_r = min(TY + 2, Ly.jmx + 2 - (j0 - 1) + 1);   // rows with j <= jmx+2
-  const unsigned plane_bytes = (unsigned)(ncol * 8) * (unsigned)(NV * nrow_q + S::NR * nrow_r);
-  auto stage_plane = [&](int kk) {   // called by every thread: thread t issues copy t (one lane's copy at a time goes through the
-                                     // uniform datapath: spread over the warps, 200 copies leave in the time of 32)
+  constexpr unsigned plane_bytes = 8u * PW * ((TY + 4) * NV + (TY + 2) * S::NR);
+  auto stage_plane = [&](int kk) {
+    if (tid != NT - 1) return;
     double* const pl = smem + (kk & 1) * S::PLANE;
     char* const mb = (char*)mbar + 8 * (kk & 1);
-    if (tid == NT - 1) mbar_expect_tx(mb, plane_bytes);   // the one arrival of the phase; copies that finish earlier only
-                                                           // drive the byte count negative for a moment
-    for (int cidx = tid; cidx < NCOPY; cidx += NT) {
-      const double* src;
-      double* dst;
-      int jrow;
-      if (cidx < NCOPY_Q) {
-        const int f = cidx / (TY + 4), r = cidx - f * (TY + 4);
-        if (r >= nrow_q) continue;
-        jrow = j0 - 2 + r; src = q + f * fs; dst = pl + f * PSQ + r * PW;
-      } else {
-        const int c2 = cidx - NCOPY_Q;
-        const int f = c2 / (TY + 2), r = c2 - f * (TY + 2);
-        if (r >= nrow_r) continue;
-        jrow = j0 - 1 + r; dst = pl + NV * PSQ + f * PS + r * PW;
-        src = (f < S::NGF) ? a.grad + f * fs : ((f < S::NGF + S::NMU) ? a.mu + (f - S::NGF) * fs : a.geom + (long long)(G_CX + f - S::NGF - S::NMU) * fs);
-      }
-      bulk_g2s(dst, src + Ly.idx(i0 - 2, jrow, kk), (unsigned)(ncol * 8), mb);
+    mbar_expect_tx(mb, plane_bytes);
+    tma_g2s_4d(pl, &tm.q, i0 + 13, j0, kk + 2, 0, mb);
+    if (VISC) {
+      tma_g2s_4d(pl + NV * PSQ, &tm.grad, i0 + 13, j0 + 1, kk + 2, 0, mb);
+      tma_g2s_4d(pl + NV * PSQ + S::NGFS * PS, &tm.aux, i0 + 13, j0 + 1, kk + 2, 0, mb);
     }
   };
   // parity of the mbarrier phase that completes when plane kk has landed (buffer kk & 1 is used by every second plane)
@@ -650,7 +644,12 @@ static int launch_one(Ctx* ctx, KArgs& a) {
     if (e != cudaSuccess) return F3D_ERR_CUDA;
     attr_set[ctx->device & 63] = true;
   }
-  k_sweep3<NV, INTERP, SCHEME, VISC, RARE><<<grid, NT, shm, ctx->stream>>>(ctx->P, a);
+  if (!ctx->tmaps_ok) return F3D_ERR_CUDA;
+  TMaps tm;
+  tm.q = (a.q == ctx->tm_q_ptr[0]) ? ctx->tm_q[0] : ctx->tm_q[1];
+  if (a.q != ctx->tm_q_ptr[0] && a.q != ctx->tm_q_ptr[1]) return F3D_ERR_ARGUMENT;
+  tm.grad = ctx->tm_grad; tm.aux = ctx->tm_aux;
+  k_sweep3<NV, INTERP, SCHEME, VISC, RARE><<<grid, NT, shm, ctx->stream>>>(ctx->P, a, tm);
   ctx->launches++;
   return 0;
 }

@@ -14,9 +14,13 @@ struct RecF {   // fields of the non-q part of a cell record
   static constexpr bool SA = (NV == 6);                    // Spalart-Allmaras (nu-tilde)
   static constexpr int NG = SST ? 6 : (SA ? 5 : 4);        // u, v, w, T [, k, omega | nu-tilde]
   static constexpr int NGF = VISC ? 3 * NG : 0;            // gradient component c, direction d -> field 3*c+d
+  static constexpr int NGFS = (NGF + 1) & ~1;              // staged slots of the gradient fields: an even count (tensor-map boxes
+                                                           // need 128-byte aligned sub-boxes; sa has 15 fields -> one unused slot)
   static constexpr int NMU = VISC ? (SST ? 3 : (SA ? 2 : 1)) : 0;   // mu, mu_t, F1
-  static constexpr int OFF_MU = NGF, OFF_C = NGF + NMU;    // then the cell centre x,y,z
-  static constexpr int NR = VISC ? NGF + NMU + 3 : 0;
+  static constexpr int OFF_MU = NGFS, OFF_C = NGFS + NMU;  // then the cell centre x,y,z
+  static constexpr int NAUX = VISC ? NMU + 3 : 0;          // "aux" fields behind the gradients: mu [, mu_t [, F1]], centre x,y,z
+  static constexpr int NAUXS = (NAUX + 1) & ~1;
+  static constexpr int NR = VISC ? NGFS + NAUXS : 0;
 };
 
 __device__ __forceinline__ void flag_error(int* err, int cls, int i, int j, int k) {
