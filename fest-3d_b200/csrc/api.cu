@@ -76,11 +76,9 @@ extern "C" int fest3d_gpu_create(Fest3dGpuCtx** out, const Fest3dGpuConfig* cfg,
   memset(&P, 0, sizeof(P));
   Layout& L = P.L;
   L.imx = cfg->imx; L.jmx = cfg->jmx; L.kmx = cfg->kmx; L.nv = cfg->n_var; L.ng = sst ? 6 : (sa ? 5 : 4);
-#ifdef F3D_STAGE_BULK   // a row must hold i = -2 .. imx+2 behind its 15-element lead-in, so that a tensor map can address it as one dimension
+  // a row holds i = -2 .. imx+2 behind its 15-element lead-in (interior cell i = 1 starts a 128-byte line), so that the tensor maps
+  // of the sweep can address it as one dimension
   L.pi = ((cfg->imx + 18 + 15) / 16) * 16; L.pj = cfg->jmx + 6; L.pk = cfg->kmx + 6;
-#else
-  L.pi = ((cfg->imx + 6 + 15) / 16) * 16; L.pj = cfg->jmx + 6; L.pk = cfg->kmx + 6;
-#endif
   L.sj = L.pi; L.sk = (long long)L.pi * L.pj;
   L.base = 13 + 2 + 2 * L.sj + 2 * L.sk;
   L.fs = ((13 + L.sk * L.pk + 31) / 32) * 32;
@@ -158,7 +156,6 @@ extern "C" int fest3d_gpu_create(Fest3dGpuCtx** out, const Fest3dGpuConfig* cfg,
   F3D_CUDA(cudaMalloc((void**)&ctx->err_dev, sizeof(int) * 4));
   F3D_CUDA(cudaMemsetAsync(ctx->err_dev, 0, sizeof(int) * 4, ctx->stream));
   F3D_CUDA(cudaMallocHost((void**)&ctx->err_host, sizeof(int) * 4));
-#ifdef F3D_STAGE_BULK
   {   // 4-D tensor maps [field][k][j][i] (pitches fs, sk, sj) of the arrays the sweep stages; box = one tile plane of all fields
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -182,7 +179,6 @@ extern "C" int fest3d_gpu_create(Fest3dGpuCtx** out, const Fest3dGpuConfig* cfg,
     if (!ok) { fprintf(stderr, "fest3d_gpu: cuTensorMapEncodeTiled failed\n"); return fail(ctx, F3D_ERR_CUDA); }
     ctx->tmaps_ok = true;
   }
-#endif
   // ghost-gradient face records
   if (P.viscous) {
     size_t tot = 0;

@@ -75,7 +75,7 @@ struct Ctx {
   double* grad = nullptr;     // 3*ng fields: component c, direction d -> field 3*c+d
   double* mu = nullptr;       // "aux" fields: mu [, mu_t [, F1]] as the model has them, then a copy of the cell centre x,y,z
   int n_mu = 0;               // 1 laminar, 2 sa, 3 sst
-  // 4-D tensor maps [field][k][j][i] of the arrays the sweep stages (only used by the -DF3D_STAGE_BULK build)
+  // 4-D tensor maps [field][k][j][i] of the arrays the sweep stages (sweep3_kernel.cuh)
   CUtensorMap tm_q[2], tm_grad, tm_aux;
   double* tm_q_ptr[2] = {nullptr, nullptr};
   bool tmaps_ok = false;

@@ -22,6 +22,10 @@
 // src/boundary/boundary_state_reconstruction.f90:93-131; src/face/flux/convective/*.f90, scheme.f90:111-141;
 // src/viscous.f90:144-447; src/source.f90:158-270; src/time.f90:122-246,366-531; src/resnorm.f90:171-199).
 #pragma once
+// Staging: the planes are filled by the TMA engine -- three 4-D tensor copies per plane (cp.async.bulk.tensor -> UTMALDG: q,
+// gradients, aux = mu fields + cell centre), completion on an mbarrier.  Measured against per-thread cp.async in the same call:
+// 4.66 vs 5.51 ms per launch at 256^3 (sweep3_kernel_cpasync.cuh keeps that form; one cp.async.bulk per field row tied with it:
+// profiles/r01_g3_summary.md).
 #include "sweep_common.cuh"
 
 namespace f3d {
@@ -35,12 +39,14 @@ constexpr int W_IH = 3 * TY, W_JH = 3 * TY + 1, W_JL = 3 * TY + 2, W_C = 3 * TY 
 constexpr int ROWS_JL = TY / 2;   // rows whose cell work the low-j halo warp does after its (short) reconstruction; W_C does the rest
 constexpr int N_IGRP = 32 * (TY + 1), N_JGRP = 32 * (TY + 2);   // threads on named barriers 1 and 2
 
-// staged plane: (TX+2) x (TY+2) slots, slot = (ty+1)*PW + (tx+1); the q fields carry NOUT extra slots for the second
-// ring cells the halo threads' own reconstruction reads
-constexpr int PW = TX + 2;
+// Staged plane.  Rows of PW = TX+4 cells (i0-2 .. i0+TX+1: the tile, its ring and the second ring cell the halo threads'
+// reconstruction reads), because that is what the bulk-copy engine can fetch: a row of a field is contiguous in HBM, starts
+// at an even element index (16-byte aligned) at i0-2, and 36 doubles are a multiple of 16 bytes.  Record fields (gradients,
+// mu / mu_t / F1, centre) hold TY+2 rows (j0-1 .. j0+TY), q fields TY+4 rows (j0-2 .. j0+TY+1).  A "slot" is the record index
+// s = row*PW + col with row 0 = j0-1; the same cell of a q field sits at s + PW.
+constexpr int PW = TX + 4;
 constexpr int PS = PW * (TY + 2);
-constexpr int NOUT = 2 * TY + 2 * TX;
-constexpr int PSQ = PS + NOUT;
+constexpr int PSQ = PW * (TY + 4);
 // exchange area ([field][slot], slot = face): i faces TY x (TX+1), j faces (TY+1) x TX
 constexpr int SLOT_I = TY * (TX + 1);
 constexpr int SLOT_J = (TY + 1) * TX;
@@ -61,9 +67,40 @@ struct Sm : RecF<NV, VISC> {
   static constexpr int P_VOL = P_Q2 + NV;                 //   [2] volume of planes (p & 1)
   static constexpr int NPRIV = P_VOL + 2;
   static constexpr int OFF_NRM = OFF_PRIV + NPRIV * NMAIN;   // norm partials of the 64 threads that do cell work, [NV+1][64]
-  static constexpr int TOTAL = OFF_NRM + (NV + 1) * 64;
+  static constexpr int OFF_MBAR = OFF_NRM + (NV + 1) * 64;   // two mbarriers (one per staged-plane buffer)
+  static constexpr int TOTAL = OFF_MBAR + 2;
 };
 
+// cp.async.bulk (TMA engine, UBLKCP) + mbarrier: one row of one field per copy, completion counted in bytes on the mbarrier
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void* b, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* b, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, void* b) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+               "r"(smem_u32(b))
+               : "memory");
+}
+__device__ __forceinline__ void tma_g2s_4d(void* dst, const CUtensorMap* tm, int x, int y, int z, int f, void* b) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(smem_u32(dst)),
+               "l"(tm), "r"(x), "r"(y), "r"(z), "r"(f), "r"(smem_u32(b))
+               : "memory");
+}
+struct TMaps { CUtensorMap q, grad, aux; };
 __device__ __forceinline__ void bar_all() { asm volatile("bar.sync 0;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const double* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void bar_group(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -228,13 +265,14 @@ __device__ __forceinline__ void cell_work(const Params& P, const KArgs& a, doubl
 
 // RARE gates the code of the seldom-used options (pressure-based switching, transition = bc): compiled into a second set of
 // instantiations (sweep3_rare.cu) because even switched off it cost the register-tight common path 4.5 % (5.82 vs 5.57 ms).
+static_assert(TX == kG3TX && TY == kG3TY, "tensor-map boxes are encoded for this tile (api.cu)");
 template <int NV, int INTERP, int SCHEME, bool VISC, bool RARE>
-__global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a) {
+__global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a, const __grid_constant__ TMaps tm) {
   using S = Sm<NV, VISC>;
   constexpr bool SST = (NV == 7), SA = (NV == 6), TURB = SST || SA;
   constexpr bool SMQ = (INTERP == F3D_MUSCL || INTERP == F3D_INTERP_NONE);   // 3-point stencils read the staged planes
   constexpr int NF = S::NF;
-  extern __shared__ double smem[];
+  extern __shared__ __align__(128) double smem[];
   const Layout& Ly = P.L;
   const long long fs = Ly.fs;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -255,46 +293,40 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a)
   // All flux warps -- I rows, J rows, K rows, halo warps -- then run ONE instruction stream, parameterised by these values:
   // separate code copies per direction made the SM fetch-bound (24 % no_instruction stalls, profiles/r01_g3_summary.md).
   int i, j, s0, d, cell, r_lo, r_hi;
-  bool rec, fac, stg, wr_hi, irow, krow, own;
+  bool rec, fac, wr_hi, irow, krow, own;
   int om, op;                       // I/J: staged-slot offsets of the two neighbours along d
   int exw, exr;                     // I/J: exchange slots: where the hi value goes; where L is read and the flux written
-  int outer_off, outer_slot;        // halo threads: global offset of the outer neighbour they stage, and its slot
   int pos, mx;
   auto role = [&]() {
     int t_ = tid;
     asm volatile("" : "+r"(t_));
     const int ln = t_ & 31, w = t_ >> 5;
-    stg = false; wr_hi = true; irow = false; krow = false; own = false; outer_off = 0; outer_slot = 0; cell = 0; r_lo = 0; r_hi = 0;
-    rec = fac = false; d = 0; i = i0 + ln; j = j0; s0 = PW + 1; om = op = 0; exw = exr = 0;
+    wr_hi = true; irow = false; krow = false; own = false; cell = 0; r_lo = 0; r_hi = 0;
+    rec = fac = false; d = 0; i = i0 + ln; j = j0; s0 = PW + 2; om = op = 0; exw = exr = 0;
     if (w < TY) {                   // I row
       const int tx = ln, ty = w;
       d = 0; i = i0 + tx; j = j0 + ty; irow = true; cell = ty * TX + tx;
       rec = fac = (j <= Ly.jmx - 1) && (i <= Ly.imx);
-      s0 = (ty + 1) * PW + tx + 1; om = -1; op = 1;
+      s0 = (ty + 1) * PW + tx + 2; om = -1; op = 1;
       exw = ty * (TX + 1) + tx + 1; exr = ty * (TX + 1) + tx;
     } else if (w < 2 * TY) {        // J row
       const int tx = ln, ty = w - TY;
       d = 1; i = i0 + tx; j = j0 + ty;
       rec = fac = (i <= Ly.imx - 1) && (j <= Ly.jmx);
-      s0 = (ty + 1) * PW + tx + 1; om = -PW; op = PW;
+      s0 = (ty + 1) * PW + tx + 2; om = -PW; op = PW;
       exw = SLOT_I + (ty + 1) * TX + tx; exr = SLOT_I + ty * TX + tx;
     } else if (w < 3 * TY) {        // K row: the column of its cell
       const int tx = ln, ty = w - 2 * TY;
       d = 2; i = i0 + tx; j = j0 + ty; krow = true; cell = ty * TX + tx;
       own = (i <= Ly.imx - 1) && (j <= Ly.jmx - 1);
-      stg = (i <= Ly.imx + 1) && (j <= Ly.jmx + 1);   // ghost cells next to the last faces feed the i/j faces there
       rec = fac = own && k_active;
-      s0 = (ty + 1) * PW + tx + 1;
+      s0 = (ty + 1) * PW + tx + 2;
     } else if (w == W_IH) {         // the two i columns next to the tile: lanes 0..TY-1 low side, TY..2TY-1 high side
       const int r = ln % TY, side = ln / TY;
       d = 0; i = (side == 0) ? i0 - 1 : i0 + TX; j = j0 + r;
       rec = (side < 2) && (j <= Ly.jmx - 1) && (i <= Ly.imx);
-      stg = (side < 2) && (j <= Ly.jmx + 1) && (i <= Ly.imx + 1);
       fac = rec && side == 1; wr_hi = side == 0;
-      s0 = (r + 1) * PW + (side == 0 ? 0 : TX + 1);
-      outer_slot = PS + (side & 1) * TY + r;
-      outer_off = (side == 0) ? -1 : 1;
-      om = (side == 0) ? outer_slot - s0 : -1; op = (side == 0) ? 1 : outer_slot - s0;
+      s0 = (r + 1) * PW + (side == 0 ? 1 : TX + 2); om = -1; op = 1;
       exw = r * (TX + 1) + (side == 0 ? 0 : TX); exr = r * (TX + 1) + TX;
     } else if (w == W_C) {          // cell work only
       r_lo = ROWS_JL; r_hi = TY;
@@ -302,12 +334,8 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a)
       const bool high = w == W_JH;
       d = 1; i = i0 + ln; j = high ? j0 + TY : j0 - 1;
       rec = (i <= Ly.imx - 1) && (j <= Ly.jmx);
-      stg = (i <= Ly.imx + 1) && (j <= Ly.jmx + 1);
       fac = rec && high; wr_hi = !high;
-      s0 = (high ? TY + 1 : 0) * PW + ln + 1;
-      outer_slot = PS + 2 * TY + (high ? TX : 0) + ln;
-      outer_off = high ? (int)Ly.sj : -(int)Ly.sj;
-      om = high ? -PW : outer_slot - s0; op = high ? outer_slot - s0 : PW;
+      s0 = (high ? TY + 1 : 0) * PW + ln + 2; om = -PW; op = PW;
       exw = SLOT_I + (high ? TY * TX : 0) + ln; exr = SLOT_I + TY * TX + ln;
       if (!high) { r_lo = 0; r_hi = ROWS_JL; }
     }
@@ -316,36 +344,38 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a)
     pos = (d == 0) ? i : j; mx = (d == 0) ? Ly.imx : ((d == 1) ? Ly.jmx : Ly.kmx);
   };
 
-  // record of this thread's cell at plane kk -> ring buffer kk & 1 (K rows: their cell; halo threads: their ring cell and the
-  // q of the outer neighbour their reconstruction reads)
-  auto stage_cell = [&](int kk) {
-    if (!stg) return;
-    double* pl = smem + (kk & 1) * S::PLANE;
-    const long long c1 = Ly.idx(i, j, kk);
-#pragma unroll
-    for (int v = 0; v < NV; ++v) cp_async8(pl + v * PSQ + s0, q + v * fs + c1);
-    if (SMQ && rec && !krow) {
-#pragma unroll
-      for (int v = 0; v < NV; ++v) cp_async8(pl + v * PSQ + outer_slot, q + v * fs + c1 + outer_off);
-    }
+  // ---- staging of a plane by the TMA engine: one elected thread issues a tensor copy per staged array (box = 36 columns x
+  // TY+4 / TY+2 rows x 1 plane x all fields, landing as [field][row][col]); cells outside the arrays are zero-filled, so the byte
+  // count the mbarrier expects is always that of the full boxes.  Tensor coordinates: x = i + 15, y = j + 2, z = k + 2
+  // (ctx.hpp:Layout: idx = 15 + i + sj (j+2) + sk (k+2)).
+  void* const mbar = smem + S::OFF_MBAR;
+  constexpr unsigned plane_bytes = 8u * PW * ((TY + 4) * NV + (TY + 2) * S::NR);
+  auto stage_plane = [&](int kk) {
+    if (tid != NT - 1) return;
+    double* const pl = smem + (kk & 1) * S::PLANE;
+    char* const mb = (char*)mbar + 8 * (kk & 1);
+    mbar_expect_tx(mb, plane_bytes);
+    tma_g2s_4d(pl, &tm.q, i0 + 13, j0, kk + 2, 0, mb);
     if (VISC) {
-      double* pr = pl + NV * PSQ;
-#pragma unroll
-      for (int f = 0; f < S::NGF; ++f) cp_async8(pr + f * PS + s0, a.grad + f * fs + c1);
-#pragma unroll
-      for (int f = 0; f < S::NMU; ++f) cp_async8(pr + (S::OFF_MU + f) * PS + s0, a.mu + f * fs + c1);
-#pragma unroll
-      for (int f = 0; f < 3; ++f) cp_async8(pr + (S::OFF_C + f) * PS + s0, a.geom + (long long)(G_CX + f) * fs + c1);
+      tma_g2s_4d(pl + NV * PSQ, &tm.grad, i0 + 13, j0 + 1, kk + 2, 0, mb);
+      tma_g2s_4d(pl + NV * PSQ + S::NGFS * PS, &tm.aux, i0 + 13, j0 + 1, kk + 2, 0, mb);
     }
-    if (krow && own) cp_async8(smem + S::OFF_PRIV + (S::P_VOL + (kk & 1)) * NMAIN + cell, vol + c1);
   };
+  // parity of the mbarrier phase that completes when plane kk has landed (buffer kk & 1 is used by every second plane)
+  auto plane_parity = [&](int kk) { return (unsigned)(((kk - (kb - 1)) >> 1) & 1); };
+  if (tid == 0) {
+    mbar_init(mbar, 1); mbar_init((char*)mbar + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  stage_plane(kb - 1);
 
   role();
   if (krow) {   // K rows: clear the k-face ring, stage plane kb-1, prime the carried value of cell kb-1 (from global memory)
     double* const priv = smem + S::OFF_PRIV + cell;
 #pragma unroll
     for (int f = 0; f < S::P_Q2; ++f) priv[f * NMAIN] = 0.0;
-    stage_cell(kb - 1);
+    if (own) cp_async8(priv + (S::P_VOL + ((kb - 1) & 1)) * NMAIN, vol + Ly.idx(i, j, kb - 1));
     if (rec) {
       const long long c = Ly.idx(i, j, kb - 1);
       double L[NV], lo_[NV];
@@ -367,27 +397,16 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a)
   for (int k = kb - 1; k <= ke; ++k) {
     bar_all();   // plane k is staged; the fluxes and cell packets of plane k-1 are complete
     role();
-    // ---- staging of plane k+1 (nobody reads plane k-1 any more: the cell work takes what it needs from the cell packets) ----
-    if (krow) {
-      if (k <= ke - 1) {
-        stage_cell(k + 1);
-        if (rec && SMQ) {
-          const long long c2 = Ly.idx(i, j, k + 2);
+    // ---- staging of plane k+1 over plane k-1 (nobody reads plane k-1 any more: the cell work takes what it needs from the cell
+    // packets); the K rows also fetch the volume of plane k+1 and their own q of plane k+2 for the k stencil
+    if (k + 1 <= ke) stage_plane(k + 1);
+    if (krow && k <= ke - 1) {
+      if (own) cp_async8(smem + S::OFF_PRIV + (S::P_VOL + ((k + 1) & 1)) * NMAIN + cell, vol + Ly.idx(i, j, k + 1));
+      if (rec && SMQ) {
+        const long long c2 = Ly.idx(i, j, k + 2);
 #pragma unroll
-          for (int v = 0; v < NV; ++v) cp_async8(smem + S::OFF_PRIV + (S::P_Q2 + v) * NMAIN + cell, q + v * fs + c2);
-        }
-        if (VISC && stg && k + 2 <= ke) {   // pull the record of plane k+2 into L2 one plane before it is staged
-          const long long c2 = Ly.idx(i, j, k + 2);
-#pragma unroll
-          for (int f = 0; f < S::NGF; ++f) prefetch_l2(a.grad + f * fs + c2);
-#pragma unroll
-          for (int f = 0; f < S::NMU; ++f) prefetch_l2(a.mu + f * fs + c2);
-#pragma unroll
-          for (int f = 0; f < 3; ++f) prefetch_l2(a.geom + (long long)(G_CX + f) * fs + c2);
-        }
+        for (int v = 0; v < NV; ++v) cp_async8(smem + S::OFF_PRIV + (S::P_Q2 + v) * NMAIN + cell, q + v * fs + c2);
       }
-    } else if (k + 1 <= ke - 1) {
-      stage_cell(k + 1);
     }
 
     // ---- flux work: one reconstruction and one face per thread, the same code for every direction --------------------------------
@@ -396,11 +415,12 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a)
       // I/J: cell (i,j,k), face below it along d.  K: cell (i,j,k+1), face between planes k and k+1.
       const int pA = (k & 1) * S::PLANE, pB = ((k + 1) & 1) * S::PLANE;
       const int nb = (d == 0) ? 1 : PW;
-      const int o_m = krow ? pA + s0 : pA + s0 + om;                 // stencil: low neighbour, cell, high neighbour (q field 0)
-      const int o_0 = krow ? pB + s0 : pA + s0;
-      const int o_p = krow ? S::OFF_PRIV + S::P_Q2 * NMAIN + cell : pA + s0 + op;
+      const int o_m = krow ? pA + PW + s0 : pA + PW + s0 + om;       // stencil: low neighbour, cell, high neighbour (q field 0)
+      const int o_0 = krow ? pB + PW + s0 : pA + PW + s0;
+      const int o_p = krow ? S::OFF_PRIV + S::P_Q2 * NMAIN + cell : pA + PW + s0 + op;
       const int f_p = krow ? NMAIN : PSQ;                            // field stride of the high neighbour
-      const int o_ql = krow ? pA + s0 : pA + s0 - nb;                // the two cells of the face (q field 0; records follow at + NV*PSQ)
+      const int o_ql = krow ? pA + PW + s0 : pA + PW + s0 - nb;      // the two cells of the face (q field 0); their records sit at
+                                                                     // the same offset minus PW plus NV*PSQ
       const int o_qh = o_0;
       const int f_x = krow ? NMAIN : EX;                             // field stride of the hi / L / flux slots
       const int o_hw = krow ? S::OFF_PRIV + (S::P_HI + ((k + 1) & 1) * NV) * NMAIN + cell : S::OFF_X + (k & 1) * NF * EX + exw;
@@ -414,7 +434,13 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a)
         const double* __restrict__ gp = a.geom + (long long)(G_IA + 4 * d) * fs + cg;
         gA_ = gp[0]; gnx = gp[fs]; gny = gp[2 * fs]; gnz = gp[3 * fs];
       }
-      if (krow) cp_async_wait_all();   // the K rows read what they have just staged (plane k+1 of their own column)
+      if (krow) {   // the K rows read plane k+1 (and, in the first iteration, plane kb-1): wait until the bulk copies have landed
+        cp_async_wait_all();
+        mbar_wait((char*)mbar + 8 * (k & 1), plane_parity(k));
+        mbar_wait((char*)mbar + 8 * ((k + 1) & 1), plane_parity(k + 1));
+      } else {
+        mbar_wait((char*)mbar + 8 * (k & 1), plane_parity(k));
+      }
       double lo[NV];
       if (rec) {
         double hi[NV];
@@ -441,7 +467,7 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a)
         double L[NV], F[NV], lam = 0.0, vis = 0.0, tur = 0.0;
 #pragma unroll
         for (int v = 0; v < NV; ++v) L[v] = smem[o_lr + v * f_x];
-        face_eval<NV, SCHEME, VISC, PS, PSQ>(P, d, smem + o_ql, smem + o_qh, smem + o_ql + NV * PSQ, smem + o_qh + NV * PSQ, gA_, gnx, gny, gnz, cpos, mx, L, lo,
+        face_eval<NV, SCHEME, VISC, PS, PSQ>(P, d, smem + o_ql, smem + o_qh, smem + o_ql - PW + NV * PSQ, smem + o_qh - PW + NV * PSQ, gA_, gnx, gny, gnz, cpos, mx, L, lo,
                                              krow ? flux_on_k : true, need_dt, F, lam, vis, tur);
 #pragma unroll
         for (int v = 0; v < NV; ++v) smem[o_fw + v * f_x] = F[v];
@@ -452,7 +478,7 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a)
         }
       }
       if (irow && rec && i <= Ly.imx - 1) {   // I rows: the cell packet of the own cell for next iteration's cell work
-        const double* const rA = smem + o_0 + NV * PSQ;
+        const double* const rA = smem + o_0 - PW + NV * PSQ;
         const double* const qA = smem + o_0;
         double* const pk = smem + S::OFF_PK + (k & 1) * S::NPK * NMAIN + cell;
         const double volc = smem[S::OFF_PRIV + (S::P_VOL + (k & 1)) * NMAIN + cell];
@@ -618,7 +644,12 @@ static int launch_one(Ctx* ctx, KArgs& a) {
     if (e != cudaSuccess) return F3D_ERR_CUDA;
     attr_set[ctx->device & 63] = true;
   }
-  k_sweep3<NV, INTERP, SCHEME, VISC, RARE><<<grid, NT, shm, ctx->stream>>>(ctx->P, a);
+  if (!ctx->tmaps_ok) return F3D_ERR_CUDA;
+  TMaps tm;
+  tm.q = (a.q == ctx->tm_q_ptr[0]) ? ctx->tm_q[0] : ctx->tm_q[1];
+  if (a.q != ctx->tm_q_ptr[0] && a.q != ctx->tm_q_ptr[1]) return F3D_ERR_ARGUMENT;
+  tm.grad = ctx->tm_grad; tm.aux = ctx->tm_aux;
+  k_sweep3<NV, INTERP, SCHEME, VISC, RARE><<<grid, NT, shm, ctx->stream>>>(ctx->P, a, tm);
   ctx->launches++;
   return 0;
 }
