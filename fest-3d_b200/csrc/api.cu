@@ -162,7 +162,7 @@ extern "C" int fest3d_gpu_create(Fest3dGpuCtx** out, const Fest3dGpuConfig* cfg,
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return fail(ctx, F3D_ERR_CUDA);
-    auto encode = [&](CUtensorMap* tm, double* base, int nfields, int rows, int box_fields) -> bool {
+    auto encode = [&](CUtensorMap* tm, double* base, int nfields, int rows, int box_fields) -> bool {   // box: 36 x rows x 1 x box_fields
       const cuuint64_t dims[4] = {(cuuint64_t)L.sj, (cuuint64_t)L.pj, (cuuint64_t)L.pk, (cuuint64_t)nfields};
       const cuuint64_t strides[3] = {(cuuint64_t)L.sj * 8, (cuuint64_t)L.sk * 8, (cuuint64_t)L.fs * 8};
       const cuuint32_t box[4] = {(cuuint32_t)(kG3TX + 4), (cuuint32_t)rows, 1u, (cuuint32_t)box_fields};
@@ -175,6 +175,8 @@ extern "C" int fest3d_gpu_create(Fest3dGpuCtx** out, const Fest3dGpuConfig* cfg,
     if (P.viscous) {
       const int ngf = 3 * L.ng, naux = ctx->n_mu + 3;
       ok = ok && encode(&ctx->tm_grad, ctx->grad, ngf, kG3TY + 2, (ngf + 1) & ~1) && encode(&ctx->tm_aux, ctx->mu, naux, kG3TY + 2, (naux + 1) & ~1);
+      ok = ok && encode(&ctx->tm_qg[0], ctx->qp, nv, 6, (nv + 1) & ~1) && encode(&ctx->tm_qg[1], ctx->qp2, nv, 6, (nv + 1) & ~1) &&
+           encode(&ctx->tm_temp, ctx->temp, 1, 6, 1);
     }
     if (!ok) { fprintf(stderr, "fest3d_gpu: cuTensorMapEncodeTiled failed\n"); return fail(ctx, F3D_ERR_CUDA); }
     ctx->tmaps_ok = true;

@@ -77,6 +77,7 @@ struct Ctx {
   int n_mu = 0;               // 1 laminar, 2 sa, 3 sst
   // 4-D tensor maps [field][k][j][i] of the arrays the sweep stages (sweep3_kernel.cuh)
   CUtensorMap tm_q[2], tm_grad, tm_aux;
+  CUtensorMap tm_qg[2], tm_temp;   // boxes of the gradient kernel (grad.cu:k_gradients_tma): 36 x 6 x 1 x fields
   double* tm_q_ptr[2] = {nullptr, nullptr};
   bool tmaps_ok = false;
   double* gbc = nullptr;      // per-face (A,nx,ny,nz) records the ghost-gradient rule reads (mis-indexed for J/K faces)

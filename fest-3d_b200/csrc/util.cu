@@ -65,31 +65,36 @@ int launch_zero_fields(Ctx* ctx, double* dst, int nfields) {
 
 // every cell that is not interior: dst <- src (so that the new-state buffer is the complete array the reference
 // would hold after its in-place update).  Only the shell is enumerated (a full-volume launch with an early exit for
-// the interior cost 83 us per stage at 256^3): blockIdx.y = plane k; ghost planes copy every cell, interior planes
-// the frame of six ghost rows (whole i extent) and six ghost columns of the interior rows.
-__global__ void k_ghost_shell(const Params P, double* __restrict__ dst, const double* __restrict__ src) {
+// the interior cost 83 us per stage at 256^3): launch 1 copies the six ghost planes whole, launch 2 the frame of every
+// interior plane (six ghost rows over the whole i extent, six ghost columns of the interior rows).
+__global__ void k_ghost_planes(const Params P, double* __restrict__ dst, const double* __restrict__ src) {
   const Layout& L = P.L;
-  const int k = -2 + blockIdx.y;
   const int ni = L.imx + 5, nj = L.jmx + 5;
-  const bool ghost_plane = k < 1 || k > L.kmx - 1;
-  const int n_frame = 6 * ni + 6 * (L.jmx - 1);
-  const int n = ghost_plane ? ni * nj : n_frame;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
-    int i, j;
-    if (ghost_plane) { i = -2 + t % ni; j = -2 + t / ni; }
-    else if (t < 6 * ni) { const int r = t / ni; i = -2 + t % ni; j = (r < 3) ? -2 + r : L.jmx + (r - 3); }
-    else { const int u = t - 6 * ni, cidx = u % 6; j = 1 + u / 6; i = (cidx < 3) ? -2 + cidx : L.imx + (cidx - 3); }
-    const long long c = L.idx(i, j, k);
-    for (int v = 0; v < L.nv; ++v) dst[v * L.fs + c] = src[v * L.fs + c];
-  }
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ni * nj) return;
+  const int k = (blockIdx.y < 3) ? -2 + (int)blockIdx.y : L.kmx + ((int)blockIdx.y - 3);
+  const long long c = L.idx(-2 + t % ni, -2 + t / ni, k);
+  for (int v = 0; v < L.nv; ++v) dst[v * L.fs + c] = src[v * L.fs + c];
+}
+__global__ void k_ghost_frames(const Params P, double* __restrict__ dst, const double* __restrict__ src) {
+  const Layout& L = P.L;
+  const int ni = L.imx + 5;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 6 * ni + 6 * (L.jmx - 1)) return;
+  const int k = 1 + blockIdx.y;
+  int i, j;
+  if (t < 6 * ni) { const int r = t / ni; i = -2 + t % ni; j = (r < 3) ? -2 + r : L.jmx + (r - 3); }
+  else { const int u = t - 6 * ni, cidx = u % 6; j = 1 + u / 6; i = (cidx < 3) ? -2 + cidx : L.imx + (cidx - 3); }
+  const long long c = L.idx(i, j, k);
+  for (int v = 0; v < L.nv; ++v) dst[v * L.fs + c] = src[v * L.fs + c];
 }
 
 int launch_ghost_shell_copy(Ctx* ctx, double* dst, const double* src) {
   const Layout& L = ctx->P.L;
-  const int per_plane = 6 * (L.imx + 5) + 6 * (L.jmx - 1);
-  dim3 block(256), grid((per_plane + 255) / 256, L.kmx + 5);
-  k_ghost_shell<<<grid, block, 0, ctx->stream>>>(ctx->P, dst, src);
-  ctx->launches++;
+  const int plane = (L.imx + 5) * (L.jmx + 5), frame = 6 * (L.imx + 5) + 6 * (L.jmx - 1);
+  k_ghost_planes<<<dim3((plane + 255) / 256, 6), 256, 0, ctx->stream>>>(ctx->P, dst, src);
+  k_ghost_frames<<<dim3((frame + 255) / 256, L.kmx - 1), 256, 0, ctx->stream>>>(ctx->P, dst, src);
+  ctx->launches += 2;
   F3D_CUDA(cudaGetLastError());
   return 0;
 }
