@@ -18,7 +18,7 @@ SYMBOLS = [
     "fest3d_gpu_set_state", "fest3d_gpu_get_state", "fest3d_gpu_step", "fest3d_gpu_step_group", "fest3d_gpu_residual",
     "fest3d_gpu_residual_group", "fest3d_gpu_get_residue", "fest3d_gpu_get_aux", "fest3d_gpu_error",
     "fest3d_gpu_comm_unique_id", "fest3d_gpu_comm_init", "fest3d_gpu_link_local", "fest3d_gpu_launch_count",
-    "fest3d_gpu_kernel_timing", "fest3d_gpu_kernel_time_ms", "fest3d_gpu_version", "fest3d_gpu_find_wall_dist",
+    "fest3d_gpu_kernel_timing", "fest3d_gpu_kernel_time_ms", "fest3d_gpu_version", "fest3d_gpu_find_wall_dist", "fest3d_gpu_setup_geometry", "fest3d_gpu_get_geometry",
 ]
 
 
@@ -93,5 +93,7 @@ def lib():
     L.fest3d_gpu_kernel_time_ms.restype = C.c_double
     L.fest3d_gpu_version.restype = C.c_char_p
     L.fest3d_gpu_find_wall_dist.argtypes = [vp, dp, dp, C.c_longlong, dp, dp]
+    L.fest3d_gpu_setup_geometry.argtypes = [vp, dp, dp, dp]
+    L.fest3d_gpu_get_geometry.argtypes = [vp, dp, dp, dp, dp]
     _lib = L
     return L

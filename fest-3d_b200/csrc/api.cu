@@ -14,6 +14,8 @@ using namespace f3d;
 namespace f3d {
 int upload_records(Ctx* ctx, const double* host, int n0, int n1, int n2, double* field0);
 int residual_grid_ctas(const Layout& L);
+int launch_setup_geometry(Ctx* ctx, const double* grid_host, double* nodes_out);
+int download_records(Ctx* ctx, const double* field0, int n0, int n1, int n2, double* host);
 }
 
 // ---- NCCL through dlopen (the library must load on hosts without NCCL; multi-rank entry points fail loudly there) ----
@@ -266,6 +268,18 @@ static int copy_cells(Fest3dGpuCtx* ctx, double* dev_field, double* host, int nf
   return 0;
 }
 
+// mu = mu_ref everywhere (viscosity.f90:527) and the cell-centre fields behind the viscosity fields: one "aux" array for the
+// tensor-map staging of the sweep
+static int init_aux_fields(Fest3dGpuCtx* ctx) {
+  const long long fs = ctx->P.L.fs;
+  std::vector<double> mu0((size_t)fs, ctx->cfg.mu_ref);
+  F3D_CUDA(cudaMemcpyAsync(ctx->mu, mu0.data(), fs * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  F3D_CUDA(cudaMemcpyAsync(ctx->mu + (long long)ctx->n_mu * fs, ctx->geom + (long long)G_CX * fs, 3 * fs * sizeof(double), cudaMemcpyDeviceToDevice,
+                           ctx->stream));
+  F3D_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
 extern "C" int fest3d_gpu_set_geometry(Fest3dGpuCtx* ctx, const double* cells, const double* Ifaces, const double* Jfaces,
                                        const double* Kfaces, const double* dist) {
   if (!ctx || !cells || !Ifaces || !Jfaces || !Kfaces) return fail(ctx, F3D_ERR_ARGUMENT);
@@ -285,11 +299,7 @@ extern "C" int fest3d_gpu_set_geometry(Fest3dGpuCtx* ctx, const double* cells, c
     // mu = mu_ref everywhere (viscosity.f90:527); face records for the ghost-gradient rule.  The reference passes
     // Jfaces / Kfaces to a dummy declared with the Ifaces shape (gradients.f90:549-612): element (i,j,k) is then read at
     // record offset (i+2) + (imx+6)*((j+2) + (jmx+5)*(k+2)) of the actual array.  Reproduced here on the host, once.
-    std::vector<double> mu0((size_t)fs, ctx->cfg.mu_ref);
-    F3D_CUDA(cudaMemcpyAsync(ctx->mu, mu0.data(), fs * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    F3D_CUDA(cudaMemcpyAsync(ctx->mu + (long long)ctx->n_mu * fs, ctx->geom + (long long)G_CX * fs, 3 * fs * sizeof(double), cudaMemcpyDeviceToDevice,
-                             ctx->stream));   // the centre fields behind the viscosity fields: one "aux" array for the tensor-map staging
-    F3D_CUDA(cudaStreamSynchronize(ctx->stream));
+    if ((rc = init_aux_fields(ctx))) return rc;
     const int mx[3] = {L.imx, L.jmx, L.kmx};
     const double* arrs[3] = {Ifaces, Jfaces, Kfaces};
     std::vector<double> rec;
@@ -730,4 +740,33 @@ extern "C" int fest3d_gpu_step(Fest3dGpuCtx* ctx, int current_iter, int n_iters,
   if (!ctx) return F3D_ERR_ARGUMENT;
   Fest3dGpuCtx* one[1] = {ctx};
   return fest3d_gpu_step_group(one, 1, current_iter, n_iters, res_abs_out);
+}
+
+// ghost_grid + the metric set-up of geometry.f90 on the device (geometry.cu) instead of the AoS upload
+extern "C" int fest3d_gpu_setup_geometry(Fest3dGpuCtx* ctx, const double* grid_xyz, const double* dist, double* nodes_out) {
+  if (!ctx || !grid_xyz) return fail(ctx, F3D_ERR_ARGUMENT);
+  F3D_CUDA(cudaSetDevice(ctx->device));
+  const Layout& L = ctx->P.L;
+  int rc = launch_setup_geometry(ctx, grid_xyz, nodes_out);
+  if (rc) return rc;
+  if (dist) {
+    if ((rc = copy_cells(ctx, ctx->geom + (long long)G_DIST * L.fs, const_cast<double*>(dist), 1, true, -2, L.imx + 5, L.jmx + 5, L.kmx + 5))) return rc;
+  }
+  if (ctx->P.viscous && (rc = init_aux_fields(ctx))) return rc;
+  if ((rc = check_errors(ctx))) return rc;   // non-positive volume -> F3D_ERR_GEOMETRY with the cell (geometry.f90:476-494)
+  ctx->geometry_set = true;
+  return 0;
+}
+
+extern "C" int fest3d_gpu_get_geometry(Fest3dGpuCtx* ctx, double* cells, double* Ifaces, double* Jfaces, double* Kfaces) {
+  if (!ctx || !ctx->geometry_set) return fail(ctx, F3D_ERR_ARGUMENT);
+  F3D_CUDA(cudaSetDevice(ctx->device));
+  const Layout& L = ctx->P.L;
+  const long long fs = L.fs;
+  int rc = 0;
+  if (cells && (rc = download_records(ctx, ctx->geom + (long long)G_VOL * fs, L.imx + 5, L.jmx + 5, L.kmx + 5, cells))) return rc;
+  if (Ifaces && (rc = download_records(ctx, ctx->geom + (long long)G_IA * fs, L.imx + 6, L.jmx + 5, L.kmx + 5, Ifaces))) return rc;
+  if (Jfaces && (rc = download_records(ctx, ctx->geom + (long long)G_JA * fs, L.imx + 5, L.jmx + 6, L.kmx + 5, Jfaces))) return rc;
+  if (Kfaces && (rc = download_records(ctx, ctx->geom + (long long)G_KA * fs, L.imx + 5, L.jmx + 5, L.kmx + 6, Kfaces))) return rc;
+  return 0;
 }

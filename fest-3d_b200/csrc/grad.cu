@@ -309,13 +309,20 @@ __global__ void k_gradient_bc(const Params P, const double* __restrict__ q, cons
   const double sig = lo ? 1.0 : -1.0;
   const int id = P.bc_id[face - 1];
   const double ft = P.fixed[F3D_FIX_WALL_TEMP][face - 1];
+  // all loads first, then all stores: grad is read and written here, so stores between the loads would serialise the NG
+  // components into NG dependent round trips to HBM (on an i face every value is its own 32-byte sector)
+  double qI[NG], qG[NG], gI[NG][3];
 #pragma unroll
   for (int cc = 0; cc < NG; ++cc) {
     // slot cc holds variable cc+2 of qp(2:n_var): u,v,w,p,[k,omega]; slot 4 (cc == 3) is then overwritten with T
-    const double qI = (cc == 3) ? temp[ci] : q[(long long)(cc + 1) * fs + ci];
-    const double qG = (cc == 3) ? temp[cg] : q[(long long)(cc + 1) * fs + cg];
-    const double gIx = grad[(3 * cc + 0) * fs + ci], gIy = grad[(3 * cc + 1) * fs + ci], gIz = grad[(3 * cc + 2) * fs + ci];
-    double gx = sig * (qI - qG) * c_x, gy = sig * (qI - qG) * c_y, gz = sig * (qI - qG) * c_z;
+    qI[cc] = (cc == 3) ? temp[ci] : q[(long long)(cc + 1) * fs + ci];
+    qG[cc] = (cc == 3) ? temp[cg] : q[(long long)(cc + 1) * fs + cg];
+    gI[cc][0] = grad[(3 * cc + 0) * fs + ci]; gI[cc][1] = grad[(3 * cc + 1) * fs + ci]; gI[cc][2] = grad[(3 * cc + 2) * fs + ci];
+  }
+#pragma unroll
+  for (int cc = 0; cc < NG; ++cc) {
+    const double gIx = gI[cc][0], gIy = gI[cc][1], gIz = gI[cc][2];
+    double gx = sig * (qI[cc] - qG[cc]) * c_x, gy = sig * (qI[cc] - qG[cc]) * c_y, gz = sig * (qI[cc] - qG[cc]) * c_z;
     if (cc == 3 && id == -5 && (ft < 1. && ft >= 0.)) { gx = -gIx; gy = -gIy; gz = -gIz; }   // adiabatic wall
     const double dot = (gIx * nx) + (gIy * ny) + (gIz * nz);
     grad[(3 * cc + 0) * fs + cg] = gx + (gIx - dot * nx);

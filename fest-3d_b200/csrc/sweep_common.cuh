@@ -102,6 +102,28 @@ __device__ __forceinline__ void line_cell_values(const Params& P, const double* 
 }
 
 
+// Koren limiter psi(r) = max(0, min(2r, (2/3)(r-1) + 1, 2)) (muscl.f90:176-181) as ONE fused multiply-add psi = s*r+ + t whose
+// coefficients are picked by the range r falls in: r <= 0: r+ = 0 -> 0;  0 < r < 1/4: 2 r;  1/4 <= r < 5/2: (2/3) r + 1/3;
+// r >= 5/2: 2.  The break points 1/4 and 5/2 are where the reference's min() changes its argument, and both have a zero low
+// word, so a signed compare of the HIGH word of r decides the range exactly: the three FP64 compares (DSETP, on the FP64 pipe,
+// each with the NaN-propagation select sequence the compiler emits for min/max) become integer compares, and the 2r, r-1 and
+// (2/3)(.)+1 operations one DFMA: 6 -> 1 FP64 instructions per psi, 42 psi per cell and direction.  (2/3) r + 1/3 differs from
+// (2/3)(r-1) + 1 by at most one rounding (2e-16 relative on psi); F3D_KOREN_REF keeps the reference's operation sequence.
+__device__ __forceinline__ double koren_psi(double r) {
+#ifdef F3D_KOREN_REF
+  return dmax(0., dmin(dmin(2 * r, (2. / 3.) * (r - 1.0) + 1.0), 2.));
+#else
+  const int h = __double2hiint(r);
+  const bool high = h >= 0x40040000;                              // r >= 2.5 (a negative r has h < 0)
+  const bool mid = (h >= 0x3FD00000) && !high;                    // 0.25 <= r < 2.5
+  const double rp = __hiloint2double(max(h, 0), __double2loint(r));   // r <= 0 -> a value below 2^-1022*2^20: psi = 0 to 1e-300
+  const int lo = mid ? 0x55555555 : 0;
+  const int s_hi = mid ? 0x3FE55555 : (high ? 0 : 0x40000000);     // 2/3 | 0 | 2
+  const int t_hi = mid ? 0x3FD55555 : (high ? 0x40000000 : 0);     // 1/3 | 2 | 0
+  return fma(__hiloint2double(s_hi, lo), rp, __hiloint2double(t_hi, lo));
+#endif
+}
+
 // Koren-limited kappa = 1/3 MUSCL values of variables [V0, V1) of one cell (muscl.f90:161-196), branch-free inside the
 // variable loop so that the V1-V0 independent dependency chains interleave (a DFMA has 8.4 cycles of latency and the
 // pipe takes one every 2.1: profiles/r01_fp64_ops_microbench.txt)
@@ -125,10 +147,8 @@ __device__ __forceinline__ void muscl_group(const double (&qm)[NV], const double
       const double fd = qp[v] - q0[v], bd = q0[v] - qm[v];
       // x + sign(1e-14, x) written as sign(|x| + 1e-14, x): the same value bit for bit, but the constant comes from the constant
       // bank as an operand instead of being built in two registers per use (562 register moves per cell-warp, ncu)
-      double r = fd * rcp64(copysign(fabs(bd) + 1e-14, bd));
-      double psi1 = dmax(0., dmin(dmin(2 * r, (2. / 3.) * (r - 1.0) + 1.0), 2.));
-      r = bd * rcp64(copysign(fabs(fd) + 1e-14, fd));
-      double psi2 = dmax(0., dmin(dmin(2 * r, (2. / 3.) * (r - 1.0) + 1.0), 2.));
+      double psi1 = koren_psi(fd * rcp64(copysign(fabs(bd) + 1e-14, bd)));
+      double psi2 = koren_psi(bd * rcp64(copysign(fabs(fd) + 1e-14, fd)));
       if (lim != 1) {   // 1 - (1 - psi)*1 is psi to within an ulp; the general switch value keeps the reference form
         psi1 = (1 - (1 - psi1) * lim);
         psi2 = (1 - (1 - psi2) * lim);

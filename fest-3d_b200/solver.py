@@ -65,7 +65,9 @@ def fill_config(cfg, blk):
 
 
 class GpuBlock:
-    def __init__(self, blk, device=0):
+    def __init__(self, blk, device=0, device_geometry=False):
+        """device_geometry: build ghost nodes and metrics on the device from the block's grid nodes (fest3d_gpu_setup_geometry)
+        instead of uploading the host's cells / Ifaces / Jfaces / Kfaces arrays."""
         self.L = capi.lib()
         self.blk = blk
         self.device = device
@@ -75,7 +77,10 @@ class GpuBlock:
         if rc:
             raise Fest3dError(rc)
         dist = np.ascontiguousarray(blk.dist) if blk.dist is not None else None
-        self._check(self.L.fest3d_gpu_set_geometry(self.h, _dp(blk.cells), _dp(blk.Ifaces), _dp(blk.Jfaces), _dp(blk.Kfaces), _dp(dist)))
+        if device_geometry:
+            self.setup_geometry(blk.nodes[3:3 + blk.kmx, 3:3 + blk.jmx, 3:3 + blk.imx], dist)
+        else:
+            self._check(self.L.fest3d_gpu_set_geometry(self.h, _dp(blk.cells), _dp(blk.Ifaces), _dp(blk.Jfaces), _dp(blk.Kfaces), _dp(dist)))
         self.set_state(blk.qp)
 
     def _check(self, rc):
@@ -105,6 +110,27 @@ class GpuBlock:
         q = out if out is not None else np.empty((b.n_var, b.kmx + 5, b.jmx + 5, b.imx + 5))
         self._check(self.L.fest3d_gpu_get_state(self.h, _dp(q)))
         return q
+
+    def setup_geometry(self, grid_nodes, dist=None, want_nodes=False):
+        """ghost_grid (grid.f90:137-236) + the metric set-up of geometry.f90:43-545 on the device from the interior nodes
+        grid_nodes[kmx, jmx, imx, 3] (the body of the grid file); returns the ghosted node array if asked for."""
+        b = self.blk
+        g = np.ascontiguousarray(grid_nodes, dtype=np.float64)
+        assert g.shape == (b.kmx, b.jmx, b.imx, 3), g.shape
+        nodes = np.empty((b.kmx + 6, b.jmx + 6, b.imx + 6, 3)) if want_nodes else None
+        d = np.ascontiguousarray(dist, dtype=np.float64) if dist is not None else None
+        self._check(self.L.fest3d_gpu_setup_geometry(self.h, _dp(g), _dp(d), _dp(nodes)))
+        return nodes
+
+    def get_geometry(self):
+        """(cells, Ifaces, Jfaces, Kfaces) as the device holds them, in the reference's layouts."""
+        b = self.blk
+        cells = np.empty((b.kmx + 5, b.jmx + 5, b.imx + 5, 4))
+        If = np.empty((b.kmx + 5, b.jmx + 5, b.imx + 6, 4))
+        Jf = np.empty((b.kmx + 5, b.jmx + 6, b.imx + 5, 4))
+        Kf = np.empty((b.kmx + 6, b.jmx + 5, b.imx + 5, 4))
+        self._check(self.L.fest3d_gpu_get_geometry(self.h, _dp(cells), _dp(If), _dp(Jf), _dp(Kf)))
+        return cells, If, Jf, Kf
 
     def find_wall_dist(self, wall_nodes, want_time=False):
         """find_wall_dist (wall_dist.f90:84-131) on the device from the block's node array and the global list of wall surface
@@ -149,10 +175,10 @@ class GpuBlock:
 class Solver:
     """The blocks of this process, stepped in lock step (drop-in for the reference's per-iteration calls)."""
 
-    def __init__(self, blocks, devices=None):
+    def __init__(self, blocks, devices=None, device_geometry=False):
         self.L = capi.lib()
         devices = devices or [0] * len(blocks)
-        self.blocks = [GpuBlock(b, d) for b, d in zip(blocks, devices)]
+        self.blocks = [GpuBlock(b, d, device_geometry) for b, d in zip(blocks, devices)]
         for i, a in enumerate(self.blocks):
             for b in self.blocks[i + 1:]:
                 ids_a = set(a.blk.bc_id) | set(a.blk.pbc_id)

@@ -53,6 +53,7 @@ enum {
   F3D_ERR_NAN_GRADIENT = 2,  /* any(isnan(grad))         gradients.f90:478 */
   F3D_ERR_NAN_VISCOSITY = 4, /* any(isnan(mu))           viscosity.f90:542 */
   F3D_ERR_NEGATIVE_STATE = 8,/* rho<0, p<0 or NaN after update   update.f90:448-452 */
+  F3D_ERR_GEOMETRY = 16,      /* non-positive cell volume  geometry.f90:476-494 (fest3d_gpu_setup_geometry only) */
   F3D_ERR_UNSUPPORTED = 64,  /* implicit / plusgs / saBC / kkl / lctm2015 / pressure switch: not on this path */
   F3D_ERR_CUDA = 128,
   F3D_ERR_ARGUMENT = 256
@@ -112,6 +113,18 @@ int fest3d_gpu_get_state(Fest3dGpuCtx* ctx, double* qp);
  * returns dist(-2:imx+2,-2:jmx+2,-2:kmx+2).  kernel_ms (may be NULL) receives the device time of the node kernel. */
 int fest3d_gpu_find_wall_dist(Fest3dGpuCtx* ctx, const double* nodes, const double* wall_xyz, long long n_wall, double* dist_out,
                               double* kernel_ms);
+
+/* SURVEY 8(f) rank 2 -- grid ghost layers and metrics on the device instead of fest3d_gpu_set_geometry's upload of the 16 metric
+ * arrays: ghost_grid (src/grid.f90:137-236), compute_face_area_vectors / compute_face_areas / normalize_face_normals /
+ * compute_volumes / compute_cell_centre (src/geometry.f90:43-545), pole (-7) faces included; bc ids from the context's config.
+ * grid_xyz = the body of the block's grid file, nodes (1:imx,1:jmx,1:kmx) of {x,y,z}, i fastest (grid.f90:78-133).  dist as in
+ * set_geometry, or NULL when fest3d_gpu_find_wall_dist follows (it needs the ghosted nodes: pass nodes_out).  nodes_out (may be
+ * NULL) receives nodes(-2:imx+3,-2:jmx+3,-2:kmx+3).  A non-positive volume returns F3D_ERR_GEOMETRY with the cell in
+ * fest3d_gpu_error, where the reference stops with Fatal_error (geometry.f90:476-494).  Results equal the host computation bit
+ * for bit (IEEE operations, no contraction). */
+int fest3d_gpu_setup_geometry(Fest3dGpuCtx* ctx, const double* grid_xyz, const double* dist, double* nodes_out);
+/* the metric arrays back in the reference layouts (any pointer may be NULL): what the host's writers / post-processing use */
+int fest3d_gpu_get_geometry(Fest3dGpuCtx* ctx, double* cells, double* Ifaces, double* Jfaces, double* Kfaces);
 
 /* the hot path -------------------------------------------------------------------------------------------------- */
 /* n_iters iterations of { get_next_solution ; find_resnorm }.  current_iter is control%current_iter of the first

@@ -292,6 +292,49 @@ def test_wall_distance_on_device(pkg, case_mod, oracle, shape):
     s.close(); s2.close()
 
 
+# ---- ghost grid + metrics on the device (grid.f90:137-236, geometry.f90:43-545) ---------------------------
+@pytest.mark.parametrize("shape,bc", [((7, 6, 5), None), ((40, 33, 9), None), ((12, 9, 2), None),
+                                      ((9, 8, 6), [-7, -4, -5, -7, -6, -6]), ((8, 7, 6), [-3, -7, -7, -5, -7, -7])])
+def test_geometry_on_device(pkg, case_mod, oracle, shape, bc):
+    """Device metrics == the host restatement (fest-3d_b200/geometry.py, numpy, IEEE operations) bit for bit: ghost nodes, face
+    areas / unit normals (pole faces: A = 0, copied normals), volumes, centres; then a residual evaluated from device-built
+    geometry against the oracle fed with the host's arrays (that exercises the gathered ghost-gradient face records too)."""
+    import importlib
+    syn = importlib.import_module("fest-3d_b200.synthetic")
+    solver = importlib.import_module("fest-3d_b200.solver")
+    blocks = syn.make_duct_blocks(None, n3=shape, turbulence="sst")
+    blk = blocks[0]
+    if bc is not None:
+        blk.bc_id = list(bc)
+        blk.build_geometry()
+    g = solver.GpuBlock(blk, 0, device_geometry=True)
+    nodes = g.setup_geometry(blk.nodes[3:3 + blk.kmx, 3:3 + blk.jmx, 3:3 + blk.imx], blk.dist, want_nodes=True)
+    assert np.array_equal(nodes, blk.nodes)
+    cells, If, Jf, Kf = g.get_geometry()
+    for got, want, name in ((cells, blk.cells, "cells"), (If, blk.Ifaces, "Ifaces"), (Jf, blk.Jfaces, "Jfaces"), (Kf, blk.Kfaces, "Kfaces")):
+        assert np.array_equal(got, want), (name, np.abs(got - want).max())
+    g.close()
+    # the whole path from device-built geometry
+    s = solver.Solver(blocks, device_geometry=True)
+    _check_residual(oracle, s, blocks)
+    s.close()
+
+
+def test_geometry_on_device_reports_a_folded_cell(pkg, case_mod):
+    import importlib
+    syn = importlib.import_module("fest-3d_b200.synthetic")
+    solver = importlib.import_module("fest-3d_b200.solver")
+    blocks = syn.make_duct_blocks(None, n3=(7, 6, 5), turbulence="none", mu_ref=0.0)
+    blk = blocks[0]
+    g = solver.GpuBlock(blk, 0)
+    grid = blk.nodes[3:3 + blk.kmx, 3:3 + blk.jmx, 3:3 + blk.imx].copy()
+    grid[:, :, :, 0] *= -1.0   # mirrored grid: left-handed cells, every volume negative (Fatal_error in geometry.f90:476-494)
+    with pytest.raises(solver.Fest3dError) as e:
+        g.setup_geometry(grid)
+    assert e.value.rc & 16
+    g.close()
+
+
 def test_unsupported_is_an_error_not_a_fallback(pkg, case_mod):
     import importlib
     syn = importlib.import_module("fest-3d_b200.synthetic")
