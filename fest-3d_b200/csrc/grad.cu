@@ -13,15 +13,22 @@
 
 namespace f3d {
 
+#ifdef F3D_GRAD_UNALIGNED
+constexpr int G_ALIGN = 0;
+#else
+constexpr int G_ALIGN = 15;
+#endif
 template <int NG>
 __global__ void __launch_bounds__(128, 5) k_gradients(const Params P, const double* __restrict__ q, const double* __restrict__ temp,
                                                    const double* __restrict__ geom, double* __restrict__ grad, double* __restrict__ mu3, int* err,
                                                    int mode) {
   const Layout& L = P.L;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  // a warp covers cells i = 32 b - 15 .. 32 b + 16: cell 1 of a row starts a 128-byte line (ctx.hpp), so every row segment a warp
+  // loads or stores is two whole lines (starting the warps at cell 0 made it three, two of them partial)
+  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x) - G_ALIGN;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
   const int k = blockIdx.z;
-  if (i > L.imx || j > L.jmx) return;
+  if (i < 0 || i > L.imx || j > L.jmx) return;
   // mode 1: only the cells whose whole stencil is interior (no ghost cell read: they can run while the halo swap and the
   // boundary fill are still in flight); mode 2: the rest; mode 0: all cells
   if (mode) {
@@ -344,7 +351,7 @@ __global__ void k_gradient_bc(const Params P, const double* __restrict__ q, cons
 int launch_gradients(Ctx* ctx, int mode) {
   const Layout& L = ctx->P.L;
   dim3 block(32, 4, 1);
-  dim3 grid((L.imx + 1 + 31) / 32, (L.jmx + 1 + 3) / 4, L.kmx + 1);
+  dim3 grid((L.imx + 1 + G_ALIGN + 31) / 32, (L.jmx + 1 + 3) / 4, L.kmx + 1);
   static int use_tma = -1;   // F3D_GRAD_TMA=1 selects the TMA-staged kernel: measured 1.88 ms against 1.47 ms for the one-thread-per-cell
                              // kernel at 256^3 (its 69 KB ring leaves 12 warps per SM and the face metrics are still plain loads)
   if (use_tma < 0) { const char* e = getenv("F3D_GRAD_TMA"); use_tma = (e && e[0] == '1') ? 1 : 0; }

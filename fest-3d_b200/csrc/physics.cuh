@@ -213,14 +213,29 @@ __device__ __forceinline__ double inviscid_flux(int scheme, double gm, double MI
   if (scheme <= F3D_AUSM) {  // van Leer, LDFSS(0), AUSM: shared Mach / pressure splitting
     const double ic = rcp64(cbar);
     const double ML = VnL * ic, MR = VnR * ic;
-    const double aP = 0.5 * (1.0 + sgn1(ML)), bL = -subsonic(ML);
     const double Mp = 0.25 * sq(1. + ML), Dp = 0.25 * sq(1. + ML) * (2. - ML);
+    const double Mm = -0.25 * sq(1. - MR), Dm = 0.25 * sq(1. - MR) * (2. + MR);
+#ifdef F3D_SPLIT_ARITH   // the reference's arithmetic form of the switches (van_leer.f90:79-101, ausm.f90:80-100)
+    const double aP = 0.5 * (1.0 + sgn1(ML)), bL = -subsonic(ML);
     double cP = (aP * (1.0 + bL) * ML) - bL * Mp;
     const double sDp = (aP * (1. + bL)) - (bL * Dp);
     const double aM = 0.5 * (1.0 - sgn1(MR)), bR = -subsonic(MR);
-    const double Mm = -0.25 * sq(1. - MR), Dm = 0.25 * sq(1. - MR) * (2. + MR);
     double cM = (aM * (1.0 + bR) * MR) - bR * Mm;
     const double sDm = (aM * (1. + bR)) - (bR * Dm);
+#else
+    // alpha = 0.5 (1 +- sign(1, M)) is 0 or 1 and beta = -max(0, 1 - int(|M|)) is 0 or -1, so the reference's blends
+    // alpha (1 + beta) M - beta M+- and alpha (1 + beta) - beta D+- pick one of their terms.  Picked here by integer tests on the high
+    // word of M (|M| < 1 <=> high word without its sign < that of 1.0, whose low word is zero; sign(1, -0.) = -1 like the
+    // reference): the same values (a zero may differ in sign), 8 FP64 instructions fewer per side
+    const int hML = __double2hiint(ML), hMR = __double2hiint(MR);
+    const bool subL = (hML & 0x7fffffff) < 0x3ff00000, subR = (hMR & 0x7fffffff) < 0x3ff00000;
+    const bool posL = hML >= 0, negR = hMR < 0;
+    const double bL = subL ? -1.0 : 0.0, bR = subR ? -1.0 : 0.0;   // (LDFSS only)
+    double cP = subL ? Mp : (posL ? ML : 0.0);
+    const double sDp = subL ? Dp : (posL ? 1.0 : 0.0);
+    double cM = subR ? Mm : (negR ? MR : 0.0);
+    const double sDm = subR ? Dm : (negR ? 1.0 : 0.0);
+#endif
     if (scheme == F3D_AUSM) {
       const double t = cP + cM;
       cP = dmax(0., t); cM = dmin(0., t);

@@ -217,6 +217,7 @@ __device__ __forceinline__ void viscous_face(const Params& P, const double* __re
   }
   if (SST) { del[4] = qh[5] - ql[5]; del[5] = qh[6] - ql[6]; }
   if (SA) del[4] = qh[5] - ql[5];
+#ifdef F3D_VISC_HALVES   // the reference's operation sequence: every face average formed with its own multiplication by 0.5
   double G[NG][3];
 #pragma unroll
   for (int c = 0; c < NG; ++c) {
@@ -237,6 +238,34 @@ __device__ __forceinline__ void viscous_face(const Params& P, const double* __re
   const double Txy = tmu * (G[1][0] + G[0][1]), Txz = tmu * (G[2][0] + G[0][2]), Tyz = tmu * (G[2][1] + G[1][2]);
   const double Kh = (mu_f * P.inv_Pr + mut_f * P.inv_tPr) * P.gm * P.R_gas * P.inv_gm1;
   const double Qx = Kh * G[3][0], Qy = Kh * G[3][1], Qz = Kh * G[3][2];
+  const double A4 = A, mu_s = mu_f, mut_s = mut_f;
+#else
+  // Every face average 0.5*(l + h) of the reference enters the flux linearly, and scaling by a power of two commutes with
+  // rounding: the SUMS are carried instead (G2 = 2 G, mu_s = 2 mu_f, mut_s = 2 mu_t,f) and the factors collected into the few
+  // coefficients that multiply them (tmu, tmu/2, Kh/2, A/4) -- the same bits as the reference's sequence with 17 fewer
+  // multiplications per face (F3D_VISC_HALVES keeps that sequence).
+  double G[NG][3];   // 2 x the face gradient
+#pragma unroll
+  for (int c = 0; c < NG; ++c) {
+    const double ax = rl[(3 * c) * PS] + rh[(3 * c) * PS], ay = rl[(3 * c + 1) * PS] + rh[(3 * c + 1) * PS], az = rl[(3 * c + 2) * PS] + rh[(3 * c + 2) * PS];
+    const double nc = ((2. * del[c]) - (ax * dx + ay * dy + az * dz)) * inv_d;
+    G[c][0] = ax + (nc * ex);
+    G[c][1] = ay + (nc * ey);
+    G[c][2] = az + (nc * ez);
+  }
+  const double mu_hi = rh[R::OFF_MU * PS];
+  const double mu_s = rl[R::OFF_MU * PS] + mu_hi;
+  const double mut_hi = TURB ? rh[(R::OFF_MU + 1) * PS] : 0.0;
+  const double mut_s = TURB ? rl[(R::OFF_MU + 1) * PS] + mut_hi : 0.0;
+  const double tmu2 = mu_s + mut_s;
+  const double tmu = 0.5 * tmu2, tmuh = 0.25 * tmu2;
+  const double div3 = (G[0][0] + G[1][1] + G[2][2]) * (1. / 3.);
+  const double Txx = tmu * (G[0][0] - div3), Tyy = tmu * (G[1][1] - div3), Tzz = tmu * (G[2][2] - div3);
+  const double Txy = tmuh * (G[1][0] + G[0][1]), Txz = tmuh * (G[2][0] + G[0][2]), Tyz = tmuh * (G[2][1] + G[1][2]);
+  const double Kh = 0.25 * ((mu_s * P.inv_Pr + mut_s * P.inv_tPr) * P.gm * P.R_gas * P.inv_gm1);
+  const double Qx = Kh * G[3][0], Qy = Kh * G[3][1], Qz = Kh * G[3][2];
+  const double A4 = 0.25 * A;
+#endif
   const double uf = 0.5 * (ql[1] + qh[1]), vf = 0.5 * (ql[2] + qh[2]), wf = 0.5 * (ql[3] + qh[3]);
   F[1] = F[1] - ((Txx * nx + Txy * ny + Txz * nz) * A);
   F[2] = F[2] - ((Txy * nx + Tyy * ny + Tyz * nz) * A);
@@ -250,8 +279,8 @@ __device__ __forceinline__ void viscous_face(const Params& P, const double* __re
     const double rhof = 0.5 * (ql[0] + qh[0]);
     const double tkf = 0.5 * (ql[NV - 2] + qh[NV - 2]);
     const double Tk = -2.0 * rhof * tkf * (1. / 3.);
-    const double dk = (A * ((mu_f + sk * mut_f) * (G[NG - 2][0] * nx + G[NG - 2][1] * ny + G[NG - 2][2] * nz)));
-    const double dw = (A * ((mu_f + sw * mut_f) * (G[NG - 1][0] * nx + G[NG - 1][1] * ny + G[NG - 1][2] * nz)));
+    const double dk = (A4 * ((mu_s + sk * mut_s) * (G[NG - 2][0] * nx + G[NG - 2][1] * ny + G[NG - 2][2] * nz)));
+    const double dw = (A4 * ((mu_s + sw * mut_s) * (G[NG - 1][0] * nx + G[NG - 1][1] * ny + G[NG - 1][2] * nz)));
     F[1] = F[1] - (Tk * nx * A);
     F[2] = F[2] - (Tk * ny * A);
     F[3] = F[3] - (Tk * nz * A);
@@ -262,7 +291,11 @@ __device__ __forceinline__ void viscous_face(const Params& P, const double* __re
   if (SA) {   // viscous.f90:570-656: its "mut_f" is rho_face * nu-tilde_face, not the eddy viscosity; K flux also when kmx == 2
     const double rhof = 0.5 * (ql[0] + qh[0]);
     const double mut_sa = 0.5 * (ql[5] + qh[5]) * rhof;
-    F[5] = F[5] - (A * ((mu_f + mut_sa) * (G[4][0] * nx + G[4][1] * ny + G[4][2] * nz))) * (1.0 / kSigmaSA);
+#ifdef F3D_VISC_HALVES
+    F[5] = F[5] - (A * ((mu_s + mut_sa) * (G[4][0] * nx + G[4][1] * ny + G[4][2] * nz))) * (1.0 / kSigmaSA);
+#else
+    F[5] = F[5] - ((0.5 * A) * (((0.5 * mu_s) + mut_sa) * (G[4][0] * nx + G[4][1] * ny + G[4][2] * nz))) * (1.0 / kSigmaSA);
+#endif
   }
   if (need_dt) {
     const double dn = fabs(((-dx) * nx) + ((-dy) * ny) + ((-dz) * nz));
