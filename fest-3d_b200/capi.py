@@ -19,6 +19,7 @@ SYMBOLS = [
     "fest3d_gpu_residual_group", "fest3d_gpu_get_residue", "fest3d_gpu_get_aux", "fest3d_gpu_error",
     "fest3d_gpu_comm_unique_id", "fest3d_gpu_comm_init", "fest3d_gpu_link_local", "fest3d_gpu_launch_count",
     "fest3d_gpu_kernel_timing", "fest3d_gpu_kernel_time_ms", "fest3d_gpu_version", "fest3d_gpu_find_wall_dist", "fest3d_gpu_setup_geometry", "fest3d_gpu_get_geometry",
+    "fest3d_gpu_checkpoint_begin", "fest3d_gpu_checkpoint_wait", "fest3d_gpu_restart",
 ]
 
 
@@ -95,5 +96,8 @@ def lib():
     L.fest3d_gpu_find_wall_dist.argtypes = [vp, dp, dp, C.c_longlong, dp, dp]
     L.fest3d_gpu_setup_geometry.argtypes = [vp, dp, dp, dp]
     L.fest3d_gpu_get_geometry.argtypes = [vp, dp, dp, dp, dp]
+    L.fest3d_gpu_checkpoint_begin.argtypes = [vp, C.c_char_p, C.c_int]
+    L.fest3d_gpu_checkpoint_wait.argtypes = [vp]
+    L.fest3d_gpu_restart.argtypes = [vp, C.c_char_p, ip]
     _lib = L
     return L

@@ -217,6 +217,7 @@ extern "C" int fest3d_gpu_create(Fest3dGpuCtx** out, const Fest3dGpuConfig* cfg,
 extern "C" int fest3d_gpu_destroy(Fest3dGpuCtx* ctx) {
   if (!ctx) return F3D_ERR_ARGUMENT;
   cudaSetDevice(ctx->device);
+  checkpoint_free(ctx);   // joins a writer thread that may still be copying
   cudaDeviceSynchronize();
   double* bufs[] = {ctx->qp, ctx->qp2, ctx->ustore, ctx->rstore, ctx->residue, ctx->temp, ctx->dt, ctx->geom, ctx->grad, ctx->mu, ctx->gbc,
                     ctx->red, ctx->norms_dev, ctx->staging, ctx->state_staging};

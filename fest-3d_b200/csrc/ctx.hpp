@@ -95,6 +95,7 @@ struct Ctx {
   double* staging = nullptr;     // host<->device staging for AoS geometry upload
   double* state_staging = nullptr;   // contiguous copy of qp in the reference layout (set_state / get_state)
   Link link[6];
+  struct Checkpoint* ckpt = nullptr;   // asynchronous checkpoint state (checkpoint.cu), created on first use
   void* nccl = nullptr;          // ncclComm_t
   int n_ranks = 1, rank = 0;
   std::vector<int> block_to_rank;
@@ -134,6 +135,7 @@ int launch_unpack(Ctx* ctx, int face, const double* buf);
 int launch_global_dt(Ctx* ctx);
 int launch_ghost_shell_copy(Ctx* ctx, double* dst, const double* src);
 int launch_state_relayout(Ctx* ctx, double* fields, double* flat, int to_fields);
+void checkpoint_free(Ctx* ctx);
 int launch_wall_distance(Ctx* ctx, const double* nodes_host, const double* wall_host, long long n_wall, double* dist_out, double* kernel_ms);
 
 // residual modes

@@ -12,6 +12,7 @@ goes through the C ABI (capi.py); nothing here computes on the host.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -132,6 +133,19 @@ class GpuBlock:
         self._check(self.L.fest3d_gpu_get_geometry(self.h, _dp(cells), _dp(If), _dp(Jf), _dp(Kf)))
         return cells, If, Jf, Kf
 
+    def checkpoint_begin(self, path, it):
+        """Snapshot the state now (stream order) and write it to `path` in the background while the solver keeps stepping."""
+        self._check(self.L.fest3d_gpu_checkpoint_begin(self.h, os.fsencode(path), int(it)))
+
+    def checkpoint_wait(self):
+        self._check(self.L.fest3d_gpu_checkpoint_wait(self.h))
+
+    def restart(self, path):
+        """Upload the state of a checkpoint file; returns the iteration number stored in it."""
+        it = C.c_int(0)
+        self._check(self.L.fest3d_gpu_restart(self.h, os.fsencode(path), C.byref(it)))
+        return it.value
+
     def find_wall_dist(self, wall_nodes, want_time=False):
         """find_wall_dist (wall_dist.f90:84-131) on the device from the block's node array and the global list of wall surface
         nodes; fills the context's wall-distance field and returns dist(-2:kmx+2, -2:jmx+2, -2:imx+2)."""
@@ -221,6 +235,21 @@ class Solver:
                 b._check(rc)
         self.current_iter += n_iters
         return res
+
+    def checkpoint_begin(self, prefix):
+        """Asynchronous checkpoint of every block (file prefix + '_<block id>.f3dckpt'); stepping may continue at once."""
+        for b in self.blocks:
+            b.checkpoint_begin("%s_%02d.f3dckpt" % (prefix, b.blk.block_id), self.current_iter)
+
+    def checkpoint_wait(self):
+        for b in self.blocks:
+            b.checkpoint_wait()
+
+    def restart(self, prefix):
+        its = {b.restart("%s_%02d.f3dckpt" % (prefix, b.blk.block_id)) for b in self.blocks}
+        assert len(its) == 1, its
+        self.current_iter = its.pop()
+        return self.current_iter
 
     # names of the reference, for hosts written against them
     def get_next_solution(self):

@@ -54,6 +54,7 @@ enum {
   F3D_ERR_NAN_VISCOSITY = 4, /* any(isnan(mu))           viscosity.f90:542 */
   F3D_ERR_NEGATIVE_STATE = 8,/* rho<0, p<0 or NaN after update   update.f90:448-452 */
   F3D_ERR_GEOMETRY = 16,      /* non-positive cell volume  geometry.f90:476-494 (fest3d_gpu_setup_geometry only) */
+  F3D_ERR_IO = 32,            /* checkpoint file cannot be written / read (fest3d_gpu_checkpoint_*, fest3d_gpu_restart) */
   F3D_ERR_UNSUPPORTED = 64,  /* implicit / plusgs / saBC / kkl / lctm2015 / pressure switch: not on this path */
   F3D_ERR_CUDA = 128,
   F3D_ERR_ARGUMENT = 256
@@ -125,6 +126,18 @@ int fest3d_gpu_find_wall_dist(Fest3dGpuCtx* ctx, const double* nodes, const doub
 int fest3d_gpu_setup_geometry(Fest3dGpuCtx* ctx, const double* grid_xyz, const double* dist, double* nodes_out);
 /* the metric arrays back in the reference layouts (any pointer may be NULL): what the host's writers / post-processing use */
 int fest3d_gpu_get_geometry(Fest3dGpuCtx* ctx, double* cells, double* Ifaces, double* Jfaces, double* Kfaces);
+
+/* SURVEY 8(f) rank 3 -- checkpoint without stalling the solver (replaces the synchronous get_state + text dump of
+ * src/solver.f90:139,186 -> src/read_write/write/dump_solution.f90).  fest3d_gpu_checkpoint_begin snapshots qp in stream order and
+ * returns at once; the device->host copy (copy stream, pinned memory) and the file write (writer thread) overlap the following
+ * fest3d_gpu_step calls.  One checkpoint per context is in flight: a second begin, fest3d_gpu_checkpoint_wait and
+ * fest3d_gpu_destroy wait for it.  File = 64-byte header { "F3DCKPT1", int32 imx, jmx, kmx, n_var, iter, 3 x int32 0, uint64
+ * n_doubles, 16 bytes 0 } followed by qp(-2:imx+2,-2:jmx+2,-2:kmx+2,1:n_var) as float64 (ghost cells included, so that a
+ * restarted run continues bit for bit).  fest3d_gpu_restart checks the header against the context (F3D_ERR_ARGUMENT on a
+ * mismatch, F3D_ERR_IO on a short or foreign file), uploads the state and returns the stored iteration number. */
+int fest3d_gpu_checkpoint_begin(Fest3dGpuCtx* ctx, const char* path, int iter);
+int fest3d_gpu_checkpoint_wait(Fest3dGpuCtx* ctx);
+int fest3d_gpu_restart(Fest3dGpuCtx* ctx, const char* path, int* iter);
 
 /* the hot path -------------------------------------------------------------------------------------------------- */
 /* n_iters iterations of { get_next_solution ; find_resnorm }.  current_iter is control%current_iter of the first

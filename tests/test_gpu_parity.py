@@ -335,6 +335,64 @@ def test_geometry_on_device_reports_a_folded_cell(pkg, case_mod):
     g.close()
 
 
+# ---- asynchronous checkpoint + restart ---------------------------------------------------------------------
+@pytest.mark.parametrize("tsa,turb", [("RK4", "sst"), ("none", "sst"), ("TVDRK3", "none")])
+def test_async_checkpoint_and_bitwise_restart(pkg, case_mod, tmp_path, tsa, turb):
+    """A checkpoint begun after iteration 3 is written while iterations 4..6 run; its content is the state after iteration 3
+    (== get_state taken then), and a fresh solver restarted from the file reproduces iterations 4..6 BIT FOR BIT (norm history
+    and final state incl. ghost cells): everything else on the device is re-derived from qp each iteration."""
+    import importlib
+    syn = importlib.import_module("fest-3d_b200.synthetic")
+    solver = importlib.import_module("fest-3d_b200.solver")
+    kw = dict(mu_ref=0.0) if turb == "none" else {}
+    mk = lambda: syn.make_duct_blocks(None, nb=(2, 1, 1), n3=(12, 10, 8), turbulence=turb, time_step_accuracy=tsa, CFL=0.5, **kw)
+    s = solver.Solver(mk())
+    s.iterate(3)
+    snap = [b.get_state().copy() for b in s.blocks]
+    prefix = str(tmp_path / "ck")
+    s.checkpoint_begin(prefix)
+    hist = s.iterate(3)            # overlaps the copy and the file write
+    s.checkpoint_wait()
+    final = [b.get_state() for b in s.blocks]
+    for b, q in zip(s.blocks, snap):
+        raw = np.fromfile("%s_%02d.f3dckpt" % (prefix, b.blk.block_id), dtype=np.uint8)
+        assert raw[:8].tobytes() == b"F3DCKPT1"
+        hdr = raw[8:40].view(np.int32)
+        assert list(hdr[:5]) == [b.blk.imx, b.blk.jmx, b.blk.kmx, b.blk.n_var, 4]
+        assert int(raw[40:48].view(np.uint64)[0]) == q.size
+        assert np.array_equal(raw[64:].view(np.float64), q.ravel())
+    s.close()
+    r = solver.Solver(mk())
+    assert r.restart(prefix) == 4
+    hist_r = r.iterate(3)
+    assert np.array_equal(hist_r, hist)
+    for b, q in zip(r.blocks, final):
+        assert np.array_equal(b.get_state(), q)
+    r.close()
+
+
+def test_restart_rejects_a_foreign_checkpoint(pkg, case_mod, tmp_path):
+    import importlib
+    syn = importlib.import_module("fest-3d_b200.synthetic")
+    solver = importlib.import_module("fest-3d_b200.solver")
+    a = solver.Solver(syn.make_duct_blocks(None, n3=(8, 6, 5), turbulence="sst"))
+    a.checkpoint_begin(str(tmp_path / "a"))
+    a.checkpoint_wait()
+    a.close()
+    b = solver.Solver(syn.make_duct_blocks(None, n3=(8, 6, 6), turbulence="sst"))
+    with pytest.raises(solver.Fest3dError) as e:
+        b.restart(str(tmp_path / "a"))          # other block shape
+    assert e.value.rc & 256
+    (tmp_path / "junk_00.f3dckpt").write_bytes(b"not a checkpoint")
+    with pytest.raises(solver.Fest3dError) as e:
+        b.restart(str(tmp_path / "junk"))
+    assert e.value.rc & 32
+    with pytest.raises(solver.Fest3dError) as e:
+        b.restart(str(tmp_path / "missing"))
+    assert e.value.rc & 32
+    b.close()
+
+
 def test_unsupported_is_an_error_not_a_fallback(pkg, case_mod):
     import importlib
     syn = importlib.import_module("fest-3d_b200.synthetic")
