@@ -95,7 +95,7 @@ def run_reference(args, n, rank, world):
     nb = cpu_block_lattice(cores)
     nblk = nb[0] * nb[1] * nb[2]
     m = args.cpu_cells
-    blocks = syn.make_duct_blocks(m, nb=nb, scheme_name="ausm", interpolant="muscl", turbulence="sst", time_step_accuracy="none", CFL=0.5)
+    blocks = syn.make_duct_blocks(m, nb=nb, scheme_name=args.scheme, interpolant=args.interpolant, turbulence="sst", time_step_accuracy="none", CFL=0.5)
     w = oracle_py.OracleWorld(blocks, fast=True)
     it = 1
     for _ in range(args.warmup):
@@ -106,7 +106,7 @@ def run_reference(args, n, rank, world):
     dt = time.perf_counter() - t0
     cells = nblk * m ** 3
     val = cells * args.steps / dt
-    sample = "%d blocks of %d^3 cells (one thread each), %d steps; same MUSCL+AUSM+SST duct as the GPU arm at reduced size" % (nblk, m, args.steps)
+    sample = "%d blocks of %d^3 cells (one thread each), %d steps; same %s duct as the GPU arm at reduced size" % (nblk, m, args.steps, scheme_label(args))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": n, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(n, args),
@@ -115,8 +115,16 @@ def run_reference(args, n, rank, world):
     print(json.dumps(line), flush=True)
 
 
+SCHEME_LABEL = {"van_leer": "van Leer", "ldfss0": "LDFSS(0)", "ausm": "AUSM", "ausmP": "AUSM+", "ausmUP": "AUSM+-up", "slau": "SLAU"}
+INTERP_LABEL = {"none": "first order", "muscl": "MUSCL", "ppm": "PPM", "weno": "WENO", "weno_NM": "WENO-NM"}
+
+
+def scheme_label(args):
+    return "%s + %s + SST" % (INTERP_LABEL[args.interpolant], SCHEME_LABEL[args.scheme])
+
+
 def workload_config(n_gpus, args):
-    return {"workload": "synthetic duct, %d^3 cells per GPU (%s blocks), MUSCL + AUSM + SST k-omega, explicit single-stage update, local time step" % (args.cells, "x".join(map(str, block_grid(n_gpus)))),
+    return {"workload": "synthetic duct, %d^3 cells per GPU (%s blocks), %s k-omega, explicit single-stage update, local time step" % (args.cells, "x".join(map(str, block_grid(n_gpus))), scheme_label(args)),
             "cells_per_gpu": args.cells ** 3, "n_var": 7, "time_integration": "none (1 stage)",
             "l2_policy": "inputs larger than L2 (state+geometry %.1f GB per GPU vs 126 MB L2)" % (args.cells ** 3 * 8 * 31 / 1e9)}
 
@@ -129,7 +137,7 @@ def cpu_baseline_sample(args):
     nb = cpu_block_lattice(cores)
     nblk = nb[0] * nb[1] * nb[2]
     m = args.cpu_cells
-    blocks = syn.make_duct_blocks(m, nb=nb, turbulence="sst", time_step_accuracy="none", CFL=0.5)
+    blocks = syn.make_duct_blocks(m, nb=nb, scheme_name=args.scheme, interpolant=args.interpolant, turbulence="sst", time_step_accuracy="none", CFL=0.5)
     w = oracle_py.OracleWorld(blocks, fast=True)
     w.step(1)
     steps = 3
@@ -138,7 +146,7 @@ def cpu_baseline_sample(args):
         w.step(it)
     dt = time.perf_counter() - t0
     return {"value": nblk * m ** 3 * steps / dt, "unit": UNIT, "cores": min(cores, nblk), "host_cores": cores, "kind": "port",
-            "sample": "%d blocks of %d^3 cells, one thread per block, %d steps of the same MUSCL+AUSM+SST duct" % (nblk, m, steps)}
+            "sample": "%d blocks of %d^3 cells, one thread per block, %d steps of the same %s duct" % (nblk, m, steps, scheme_label(args))}
 
 
 def main():
@@ -150,6 +158,9 @@ def main():
     ap.add_argument("--cells", type=int, default=256, help="cells per block edge per GPU")
     ap.add_argument("--cpu-cells", type=int, default=48, help="cells per block edge of the CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
+    # the headline configuration is the default; BASELINE.json's other synthetic config (WENO + AUSM+ + SST) is --interpolant weno --scheme ausmP
+    ap.add_argument("--scheme", default="ausm", choices=sorted(SCHEME_LABEL))
+    ap.add_argument("--interpolant", default="muscl", choices=sorted(INTERP_LABEL))
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -173,7 +184,7 @@ def main():
     solver_mod = importlib.import_module("fest-3d_b200.solver")
 
     nb = block_grid(world)
-    blocks = syn.make_duct_blocks(args.cells, nb=nb, scheme_name="ausm", interpolant="muscl", turbulence="sst",
+    blocks = syn.make_duct_blocks(args.cells, nb=nb, scheme_name=args.scheme, interpolant=args.interpolant, turbulence="sst",
                                   time_step_accuracy="none", CFL=0.5, only_blocks=[rank])
     blk = blocks[0]
     s = solver_mod.Solver(blocks, devices=[local_rank])
@@ -264,7 +275,7 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(world, args),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "g3::k_sweep3<7,MUSCL,AUSM,viscous> (fused reconstruction + flux + source + dt + update, generation %s)" % os.environ.get("F3D_SWEEP_GEN", "3"), "kernel_ms": k_avg_ms,
+                         "kernel": "g3::k_sweep3<7,%s,%s,viscous> (fused reconstruction + flux + source + dt + update, generation %s)" % (INTERP_LABEL[args.interpolant], SCHEME_LABEL[args.scheme], os.environ.get("F3D_SWEEP_GEN", "3")), "kernel_ms": k_avg_ms,
                          "kernel_share_of_step": k_ms / ms, "algorithmic_bytes_per_cell_update": bpc, "peak_source": peak_src},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes + nvp1 * 8,
                     "steps": e2e_steps},

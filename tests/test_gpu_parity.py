@@ -354,15 +354,16 @@ def test_async_checkpoint_and_bitwise_restart(pkg, case_mod, tmp_path, tsa, turb
     hist = s.iterate(3)            # overlaps the copy and the file write
     s.checkpoint_wait()
     final = [b.get_state() for b in s.blocks]
+    ck = importlib.import_module("fest-3d_b200.checkpoint")
     for b, q in zip(s.blocks, snap):
-        raw = np.fromfile("%s_%02d.f3dckpt" % (prefix, b.blk.block_id), dtype=np.uint8)
-        assert raw[:8].tobytes() == b"F3DCKPT1"
-        hdr = raw[8:40].view(np.int32)
-        assert list(hdr[:5]) == [b.blk.imx, b.blk.jmx, b.blk.kmx, b.blk.n_var, 4]
-        assert int(raw[40:48].view(np.uint64)[0]) == q.size
-        assert np.array_equal(raw[64:].view(np.float64), q.ravel())
+        hdr, qf = ck.read_checkpoint("%s_%02d.f3dckpt" % (prefix, b.blk.block_id))
+        assert hdr == dict(imx=b.blk.imx, jmx=b.blk.jmx, kmx=b.blk.kmx, n_var=b.blk.n_var, iter=4)
+        assert np.array_equal(qf, q)
     s.close()
     r = solver.Solver(mk())
+    for b, q in zip(s.blocks, snap):   # a file written by the host from the same state is accepted alike
+        ck.write_checkpoint("%s_host_%02d.f3dckpt" % (prefix, b.blk.block_id), q, 4)
+    assert r.restart(prefix + "_host") == 4
     assert r.restart(prefix) == 4
     hist_r = r.iterate(3)
     assert np.array_equal(hist_r, hist)

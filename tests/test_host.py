@@ -152,3 +152,24 @@ def test_oracle_far_field_turbulence_rule(case_mod, oracle):
     # inflow at imin (u > 0): fixed free-stream k ; outflow at imax: flat copy of the last interior layer
     assert np.all(q[5, 3:3 + 4, 3:3 + 5, 2] == blk.flow.tk_inf)
     assert np.array_equal(q[5, 3:3 + 4, 3:3 + 5, 3 + 6], q[5, 3:3 + 4, 3:3 + 5, 3 + 5])
+
+
+def test_checkpoint_side_format_roundtrip(tmp_path):
+    """The host-side reader / writer of the binary checkpoint format (include/fest3d_gpu.h): 64-byte header, qp with ghosts."""
+    import importlib
+    ck = importlib.import_module("fest-3d_b200.checkpoint")
+    rng = np.random.default_rng(7)
+    q = rng.standard_normal((7, 4 + 5, 6 + 5, 9 + 5))
+    path = str(tmp_path / "a.f3dckpt")
+    ck.write_checkpoint(path, q, 17)
+    raw = open(path, "rb").read()
+    assert len(raw) == 64 + q.size * 8 and raw[:8] == b"F3DCKPT1"
+    assert list(np.frombuffer(raw[8:28], dtype="<i4")) == [9, 6, 4, 7, 17]
+    hdr, back = ck.read_checkpoint(path)
+    assert hdr == dict(imx=9, jmx=6, kmx=4, n_var=7, iter=17) and np.array_equal(back, q)
+    open(path, "wb").write(raw[:-8])
+    with pytest.raises(ValueError):
+        ck.read_checkpoint(path)
+    open(path, "wb").write(b"XXXXXXXX" + raw[8:])
+    with pytest.raises(ValueError):
+        ck.read_checkpoint(path)
