@@ -64,6 +64,18 @@ __device__ __forceinline__ double sqrt64(double x) {   // x > 0 only
 // min / max as compare + select (no NaN operands on these call sites)
 __device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
 __device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
+// divisions of the WENO / WENO-NM / PPM reconstructions (positive, well-scaled divisors; constant divisors 3, 6, 12)
+#ifdef F3D_WENO_IEEE
+__device__ __forceinline__ double wdiv(double a, double b) { return a / b; }
+__device__ __forceinline__ double wthird(double a) { return a / 3.0; }
+__device__ __forceinline__ double wsixth(double a) { return a / 6.0; }
+__device__ __forceinline__ double wtwelfth(double a) { return a / 12.; }
+#else
+__device__ __forceinline__ double wdiv(double a, double b) { return a * rcp64(b); }
+__device__ __forceinline__ double wthird(double a) { return a * (1.0 / 3.0); }
+__device__ __forceinline__ double wsixth(double a) { return a * (1.0 / 6.0); }
+__device__ __forceinline__ double wtwelfth(double a) { return a * (1.0 / 12.0); }
+#endif
 // max(0, 1 - floor(abs(M))) of the Mach splittings: 1 inside |M| < 1, else 0
 __device__ __forceinline__ double subsonic(double M) { return fabs(M) < 1.0 ? 1.0 : 0.0; }
 
@@ -102,26 +114,29 @@ __device__ __forceinline__ void cell_face_values(const double* q, const double* 
     const double B2 = (13.0 / 12.0) * (t * t) + (1.0 / 4.0) * (s * s);
     t = (q0 - 2.0 * qp1 + qp2); s = (3.0 * q0 - 4.0 * qp1 + qp2);
     const double B3 = (13.0 / 12.0) * (t * t) + (1.0 / 4.0) * (s * s);
-    const double i1 = 1.0 / sq(eps + B1), i2 = 1.0 / sq(eps + B2), i3 = 1.0 / sq(eps + B3);
+    // divisions: eps + B >= 1e-6 and the weight sums are positive, so the fast reciprocal applies (<= 2 ulp, like every other
+    // division of the sweep); x / 6 as x * (1/6).  The IEEE sequences cost 14.4 DFMA slots each, 11 per variable and direction:
+    // profiles/r01_fp64_ops_microbench.txt.  F3D_WENO_IEEE keeps them.
+    const double i1 = wdiv(1.0, sq(eps + B1)), i2 = wdiv(1.0, sq(eps + B2)), i3 = wdiv(1.0, sq(eps + B3));
     {
-      const double P1 = (2.0 * qm2 - 7.0 * qm1 + 11.0 * q0) / 6.0;
-      const double P2 = (-1.0 * qm1 + 5.0 * q0 + 2.0 * qp1) / 6.0;
-      const double P3 = (2.0 * q0 + 5.0 * qp1 - 1.0 * qp2) / 6.0;
+      const double P1 = wsixth(2.0 * qm2 - 7.0 * qm1 + 11.0 * q0);
+      const double P2 = wsixth(-1.0 * qm1 + 5.0 * q0 + 2.0 * qp1);
+      const double P3 = wsixth(2.0 * q0 + 5.0 * qp1 - 1.0 * qp2);
       const double w1 = 0.1 * i1, w2 = 0.6 * i2, w3 = 0.3 * i3;
-      to_hi = ((w1 * P1 + w2 * P2) + w3 * P3) / ((w1 + w2) + w3);
+      to_hi = wdiv((w1 * P1 + w2 * P2) + w3 * P3, (w1 + w2) + w3);
     }
     {  // the low-face value reuses the same smoothness indicators with mirrored linear weights (weno.f90:84-86)
-      const double P1 = (2.0 * qp2 - 7.0 * qp1 + 11.0 * q0) / 6.0;
-      const double P2 = (-1.0 * qp1 + 5.0 * q0 + 2.0 * qm1) / 6.0;
-      const double P3 = (2.0 * q0 + 5.0 * qm1 - 1.0 * qm2) / 6.0;
+      const double P1 = wsixth(2.0 * qp2 - 7.0 * qp1 + 11.0 * q0);
+      const double P2 = wsixth(-1.0 * qp1 + 5.0 * q0 + 2.0 * qm1);
+      const double P3 = wsixth(2.0 * q0 + 5.0 * qm1 - 1.0 * qm2);
       const double w1 = 0.1 * i3, w2 = 0.6 * i2, w3 = 0.3 * i1;
-      to_lo = ((w1 * P1 + w2 * P2) + w3 * P3) / ((w1 + w2) + w3);
+      to_lo = wdiv((w1 * P1 + w2 * P2) + w3 * P3, (w1 + w2) + w3);
     }
   } else if (INTERP == F3D_WENO_NM) {
     const double eps = 1e-6;
     const double vm2 = vol[1], vm1 = vol[2], v0 = vol[3], vp1 = vol[4], vp2 = vol[5];
-    const double alpha12 = vp2 / (vp1 + vp2), alpha01 = vp1 / (v0 + vp1);
-    const double alpha10 = v0 / (vm1 + v0), alpha21 = vm1 / (vm2 + vm1);
+    const double alpha12 = wdiv(vp2, vp1 + vp2), alpha01 = wdiv(vp1, v0 + vp1);   // volumes are positive (geometry.f90:476-494)
+    const double alpha10 = wdiv(v0, vm1 + v0), alpha21 = wdiv(vm1, vm2 + vm1);
     const double U01 = (1.0 - alpha01) * q0 + alpha01 * qp1;
     const double U12 = (1.0 - alpha12) * qp1 + alpha12 * qp2;
     const double U10 = (1.0 - alpha10) * qm1 + alpha10 * q0;
@@ -130,34 +145,34 @@ __device__ __forceinline__ void cell_face_values(const double* q, const double* 
     const double U11 = qp1 + alpha12 * (qp1 - qp2);
     double t, s;
     {
-      const double P1 = (6.0 * q0 - 1.0 * U10 - 2.0 * U00) / 3.0;
-      const double P2 = (-1.0 * U10 + 2.0 * q0 + 2.0 * U01) / 3.0;
-      const double P3 = (2.0 * U01 + 2.0 * qp1 - 1.0 * U12) / 3.0;
+      const double P1 = wthird(6.0 * q0 - 1.0 * U10 - 2.0 * U00);
+      const double P2 = wthird(-1.0 * U10 + 2.0 * q0 + 2.0 * U01);
+      const double P3 = wthird(2.0 * U01 + 2.0 * qp1 - 1.0 * U12);
       t = (2 * U10 - 2.0 * U00); s = (4 * q0 - 2.0 * U10 - 2.0 * U00);
       const double B1 = (13.0 / 12.0) * (t * t) + (1.0 / 4.0) * (s * s);
       t = (2 * U10 - 4.0 * q0 + 2 * U01); s = (-2 * U10 + 2.0 * U01);
       const double B2 = (13.0 / 12.0) * (t * t) + (1.0 / 4.0) * (s * s);
       t = (2 * U01 - 4.0 * qp1 + 2 * U12); s = (-6 * U01 + 8.0 * qp1 - 2.0 * U12);
       const double B3 = (13.0 / 12.0) * (t * t) + (1.0 / 4.0) * (s * s);
-      const double w1 = 0.1 / sq(eps + B1), w2 = 0.6 / sq(eps + B2), w3 = 0.3 / sq(eps + B3);
-      to_hi = ((w1 * P1 + w2 * P2) + w3 * P3) / ((w1 + w2) + w3);
+      const double w1 = wdiv(0.1, sq(eps + B1)), w2 = wdiv(0.6, sq(eps + B2)), w3 = wdiv(0.3, sq(eps + B3));
+      to_hi = wdiv((w1 * P1 + w2 * P2) + w3 * P3, (w1 + w2) + w3);
     }
     {
-      const double P1 = (6.0 * q0 - 1.0 * U01 - 2.0 * U11) / 3.0;
-      const double P2 = (-1.0 * U01 + 2.0 * q0 + 2.0 * U10) / 3.0;
-      const double P3 = (2.0 * U10 + 2.0 * qm1 - 1.0 * U21) / 3.0;
+      const double P1 = wthird(6.0 * q0 - 1.0 * U01 - 2.0 * U11);
+      const double P2 = wthird(-1.0 * U01 + 2.0 * q0 + 2.0 * U10);
+      const double P3 = wthird(2.0 * U10 + 2.0 * qm1 - 1.0 * U21);
       t = (2 * U01 - 2.0 * U11); s = (4 * q0 - 2.0 * U01 - 2.0 * U11);
       const double B1 = (13.0 / 12.0) * (t * t) + (1.0 / 4.0) * (s * s);
       t = (2 * U01 - 4.0 * q0 + 2 * U10); s = (-2 * U01 + 2.0 * U10);
       const double B2 = (13.0 / 12.0) * (t * t) + (1.0 / 4.0) * (s * s);
       t = (2 * U10 - 4.0 * qm1 + 2 * U21); s = (-6 * U10 + 8.0 * qm1 - 2.0 * U21);
       const double B3 = (13.0 / 12.0) * (t * t) + (1.0 / 4.0) * (s * s);
-      const double w1 = 0.1 / sq(eps + B1), w2 = 0.6 / sq(eps + B2), w3 = 0.3 / sq(eps + B3);
-      to_lo = ((w1 * P1 + w2 * P2) + w3 * P3) / ((w1 + w2) + w3);
+      const double w1 = wdiv(0.1, sq(eps + B1)), w2 = wdiv(0.6, sq(eps + B2)), w3 = wdiv(0.3, sq(eps + B3));
+      to_lo = wdiv((w1 * P1 + w2 * P2) + w3 * P3, (w1 + w2) + w3);
     }
   } else {  // PPM: 4-point face estimates on both faces of the cell, then the monotonicity fix of the cell
-    double R = (7. * (q0 + qm1) - (qp1 + qm2)) / 12.;         // estimate at the low face
-    double L = (7. * (qp1 + q0) - (qp2 + qm1)) / 12.;         // estimate at the high face
+    double R = wtwelfth(7. * (q0 + qm1) - (qp1 + qm2));       // estimate at the low face
+    double L = wtwelfth(7. * (qp1 + q0) - (qp2 + qm1));       // estimate at the high face
     if (limiter == 1) {
       if ((L - q0) * (q0 - R) <= 0) { L = q0; R = q0; }
       else {

@@ -662,7 +662,9 @@ static int launch_interp(Ctx* ctx, KArgs& a) {
       if (!RARE && ctx->P.scheme == F3D_AUSM) return launch_one<NV, F3D_MUSCL, F3D_AUSM, VISC, RARE>(ctx, a);   // the headline configuration
       return launch_one<NV, F3D_MUSCL, -1, VISC, RARE>(ctx, a);
     case F3D_PPM: return launch_one<NV, F3D_PPM, -1, VISC, RARE>(ctx, a);
-    case F3D_WENO: return launch_one<NV, F3D_WENO, -1, VISC, RARE>(ctx, a);
+    case F3D_WENO:
+      if (!RARE && ctx->P.scheme == F3D_AUSMP) return launch_one<NV, F3D_WENO, F3D_AUSMP, VISC, RARE>(ctx, a);   // BASELINE's second synthetic configuration
+      return launch_one<NV, F3D_WENO, -1, VISC, RARE>(ctx, a);
     case F3D_WENO_NM: return launch_one<NV, F3D_WENO_NM, -1, VISC, RARE>(ctx, a);
   }
   return F3D_ERR_UNSUPPORTED;
