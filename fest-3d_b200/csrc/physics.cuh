@@ -64,6 +64,13 @@ __device__ __forceinline__ double sqrt64(double x) {   // x > 0 only
 // min / max as compare + select (no NaN operands on these call sites)
 __device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
 __device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
+// non-linear weights of WENO-NM (weno_NM.f90:96-98): as ratios, multiplied through by the product of the three denominators
+#ifdef F3D_WENO_IEEE
+#define WENO_NM_WEIGHTS const double w1 = wdiv(0.1, sq(eps + B1)), w2 = wdiv(0.6, sq(eps + B2)), w3 = wdiv(0.3, sq(eps + B3));
+#else
+#define WENO_NM_WEIGHTS const double b1 = sq(eps + B1), b2 = sq(eps + B2), b3 = sq(eps + B3); \
+                        const double w1 = 0.1 * (b2 * b3), w2 = 0.6 * (b1 * b3), w3 = 0.3 * (b1 * b2);
+#endif
 // divisions of the WENO / WENO-NM / PPM reconstructions (positive, well-scaled divisors; constant divisors 3, 6, 12)
 #ifdef F3D_WENO_IEEE
 __device__ __forceinline__ double wdiv(double a, double b) { return a / b; }
@@ -117,7 +124,15 @@ __device__ __forceinline__ void cell_face_values(const double* q, const double* 
     // divisions: eps + B >= 1e-6 and the weight sums are positive, so the fast reciprocal applies (<= 2 ulp, like every other
     // division of the sweep); x / 6 as x * (1/6).  The IEEE sequences cost 14.4 DFMA slots each, 11 per variable and direction:
     // profiles/r01_fp64_ops_microbench.txt.  F3D_WENO_IEEE keeps them.
+#ifdef F3D_WENO_IEEE
     const double i1 = wdiv(1.0, sq(eps + B1)), i2 = wdiv(1.0, sq(eps + B2)), i3 = wdiv(1.0, sq(eps + B3));
+#else
+    // the weights g_i / (eps + B_i)^2 only enter as ratios: both sums are multiplied through by the product of the three
+    // denominators, i.e. i_1 = b_2 b_3, i_2 = b_1 b_3, i_3 = b_1 b_2 with b_i = (eps + B_i)^2 -- three products instead of three
+    // reciprocals, one normalising reciprocal per face value left (b_i between 1e-12 and ~1e20 for any physical field: no range issue)
+    const double b1 = sq(eps + B1), b2 = sq(eps + B2), b3 = sq(eps + B3);
+    const double i1 = b2 * b3, i2 = b1 * b3, i3 = b1 * b2;
+#endif
     {
       const double P1 = wsixth(2.0 * qm2 - 7.0 * qm1 + 11.0 * q0);
       const double P2 = wsixth(-1.0 * qm1 + 5.0 * q0 + 2.0 * qp1);
@@ -154,7 +169,7 @@ __device__ __forceinline__ void cell_face_values(const double* q, const double* 
       const double B2 = (13.0 / 12.0) * (t * t) + (1.0 / 4.0) * (s * s);
       t = (2 * U01 - 4.0 * qp1 + 2 * U12); s = (-6 * U01 + 8.0 * qp1 - 2.0 * U12);
       const double B3 = (13.0 / 12.0) * (t * t) + (1.0 / 4.0) * (s * s);
-      const double w1 = wdiv(0.1, sq(eps + B1)), w2 = wdiv(0.6, sq(eps + B2)), w3 = wdiv(0.3, sq(eps + B3));
+      WENO_NM_WEIGHTS
       to_hi = wdiv((w1 * P1 + w2 * P2) + w3 * P3, (w1 + w2) + w3);
     }
     {
@@ -167,7 +182,7 @@ __device__ __forceinline__ void cell_face_values(const double* q, const double* 
       const double B2 = (13.0 / 12.0) * (t * t) + (1.0 / 4.0) * (s * s);
       t = (2 * U10 - 4.0 * qm1 + 2 * U21); s = (-6 * U10 + 8.0 * qm1 - 2.0 * U21);
       const double B3 = (13.0 / 12.0) * (t * t) + (1.0 / 4.0) * (s * s);
-      const double w1 = wdiv(0.1, sq(eps + B1)), w2 = wdiv(0.6, sq(eps + B2)), w3 = wdiv(0.3, sq(eps + B3));
+      WENO_NM_WEIGHTS
       to_lo = wdiv((w1 * P1 + w2 * P2) + w3 * P3, (w1 + w2) + w3);
     }
   } else {  // PPM: 4-point face estimates on both faces of the cell, then the monotonicity fix of the cell
