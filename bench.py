@@ -4,6 +4,7 @@
 Contract (see DESIGN.md "Measurement"):
   python bench.py --gpus N --steps K --warmup W          one rank per GPU (torchrun for N>1), weak scaling
   python bench.py --impl reference ...                   the CPU arm: the oracle port on the host cores
+  python bench.py --interpolant weno --scheme ausmP      BASELINE.json's second synthetic configuration (not the headline line)
 
 A *step* is one iteration of get_next_solution + find_resnorm (src/solver.f90:184-185) on a 256^3-cell block per GPU,
 MUSCL + AUSM + SST, single-stage explicit update (time_step_accuracy 'none'): one residual evaluation + one update per
