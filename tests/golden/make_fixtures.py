@@ -6,7 +6,12 @@ verbatim from /root/reference/tests/<Case>/ (data files, not source code).  Run 
 
 Also writes tests/golden/oracle_vectors.npz: outputs of the CPU oracle on these cases, so that `-m "not gpu"`
 tests pin the oracle build against drift (the vectors are the oracle's own, NOT reference outputs -- the reference
-cannot be run here; parity with the Fortran build stays unpinned)."""
+cannot be run here; parity with the Fortran build stays unpinned).
+
+And tests/golden/smoothbump_reference_output.npz: the ONE reference output the tree ships for this path -- the flow field of the
+reference's own SmoothBump run (tests/SmoothBump/time_directories/0010/process_0{0,1}.dat: Density, u, v, w, Pressure of the
+interior cells, 16 significant digits), stored as arrays.  tests/test_oracle_kat.py uses it as a soft pin (entropy measure of
+tests/SmoothBump/pp/entropy.py against the value in tests/Report.txt, and near-stationarity under the oracle's operator)."""
 import importlib
 import os
 import shutil
@@ -70,6 +75,13 @@ def main():
         for b in range(len(blocks)):
             out["%s_res%d" % (name, b)] = res[b]
     np.savez_compressed(os.path.join(HERE, "oracle_vectors.npz"), **out)
+    # the reference's own converged SmoothBump field (a reference OUTPUT)
+    blocks = fixtures.load(case_mod, os.path.join(HERE, "smoothbump"))
+    ref_out = {}
+    for b, blk in enumerate(blocks):
+        case_mod.read_tecplot_state(os.path.join(REF, "SmoothBump/time_directories/0010/process_%02d.dat" % b), blk)
+        ref_out["q%d" % b] = blk.qp[:, 3:3 + blk.kmx - 1, 3:3 + blk.jmx - 1, 3:3 + blk.imx - 1].copy()
+    np.savez_compressed(os.path.join(HERE, "smoothbump_reference_output.npz"), **ref_out)
     print("fixtures written:", {k: v.shape for k, v in out.items()})
 
 
