@@ -266,6 +266,37 @@ def test_boundary_conditions(pkg, case_mod, oracle, bc, shape, accur):
     s.close()
 
 
+# ---- the reference's own SmoothBump output (tests/SmoothBump/time_directories/0010) under the CUDA path ------------------------
+def test_shipped_smoothbump_output_relaxes_to_the_reported_entropy(pkg, case_mod):
+    """Soft pin of the CUDA path on a reference OUTPUT (companion of test_oracle_kat.py::test_soft_pin_on_the_shipped_smoothbump_output):
+    started from the field of the reference's own run, 3000 explicit iterations (RK4, local time step, CFL 1, shipped scheme
+    muscl + ausm) damp its residual and hold the entropy measure of tests/SmoothBump/pp/entropy.py within 3 % of the figure in
+    tests/Report.txt (7.883e-07; the CPU oracle settles at 7.884e-07 +- 0.15 % over iterations 32000..39000 of the same march)."""
+    import importlib
+    solver = importlib.import_module("fest-3d_b200.solver")
+    ref = np.load(os.path.join(GOLDEN, "smoothbump_reference_output.npz"))
+    blocks = _load_fixture(case_mod, "smoothbump", scheme=dict(time_step_accuracy="RK4"), control=dict(CFL=1.0))
+    for b, blk in enumerate(blocks):
+        blk.qp[:, 3:3 + blk.kmx - 1, 3:3 + blk.jmx - 1, 3:3 + blk.imx - 1] = ref["q%d" % b]
+    s = solver.Solver(blocks)
+    first = s.iterate(1)[0]
+    s.iterate(2998, want_norms=False)
+    last = s.iterate(1)[0]
+    assert np.all(last[[1, 2, 5]] < first[[1, 2, 5]]), (first, last)
+    err2, vol = 0.0, 0.0
+    for gb, blk in zip(s.blocks, blocks):
+        q = gb.get_state()
+        nk, nj, ni = blk.kmx - 1, blk.jmx - 1, blk.imx - 1
+        rho, p = q[0, 3:3 + nk, 3:3 + nj, 3:3 + ni], q[4, 3:3 + nk, 3:3 + nj, 3:3 + ni]
+        V = blk.cells[3:3 + nk, 3:3 + nj, 3:3 + ni, 0]
+        s_inf = blk.flow.pressure_inf / blk.flow.density_inf ** 1.4
+        err2 += ((((p / rho ** 1.4) - s_inf) * V / s_inf) ** 2).sum()
+        vol += V.sum()
+    ds = float(np.sqrt(err2 / vol))
+    s.close()
+    assert abs(ds / 7.883e-07 - 1.0) < 0.03, ds
+
+
 # ---- SURVEY 8(f) rank 1: wall distance on the device (wall_dist.f90:84-131) ---------------------------------------------------
 @pytest.mark.parametrize("shape", [(7, 6, 5), (40, 33, 9)])
 def test_wall_distance_on_device(pkg, case_mod, oracle, shape):
