@@ -42,7 +42,7 @@ def algorithmic_bytes_per_cell_update(nv, viscous, sst, stages_rk):
 
 
 def block_grid(n_ranks):
-    return importlib.import_module("fest-3d_b200.parallel").block_grid(n_ranks)
+    return importlib.import_module("fest3d_b200.parallel").block_grid(n_ranks)
 
 
 def cpu_block_lattice(cores):
@@ -91,7 +91,7 @@ def run_reference(args, n, rank, world):
     if rank != 0:
         return
     import oracle_py
-    syn = importlib.import_module("fest-3d_b200.synthetic")
+    syn = importlib.import_module("fest3d_b200.synthetic")
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     nb = cpu_block_lattice(cores)
     nblk = nb[0] * nb[1] * nb[2]
@@ -133,7 +133,7 @@ def workload_config(n_gpus, args):
 def cpu_baseline_sample(args):
     """Oracle port timed on a bounded sample on this box's host cores (reported baseline, not the target)."""
     import oracle_py
-    syn = importlib.import_module("fest-3d_b200.synthetic")
+    syn = importlib.import_module("fest3d_b200.synthetic")
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     nb = cpu_block_lattice(cores)
     nblk = nb[0] * nb[1] * nb[2]
@@ -181,8 +181,8 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    syn = importlib.import_module("fest-3d_b200.synthetic")
-    solver_mod = importlib.import_module("fest-3d_b200.solver")
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    solver_mod = importlib.import_module("fest3d_b200.solver")
 
     nb = block_grid(world)
     blocks = syn.make_duct_blocks(args.cells, nb=nb, scheme_name=args.scheme, interpolant=args.interpolant, turbulence="sst",
@@ -191,7 +191,7 @@ def main():
     s = solver_mod.Solver(blocks, devices=[local_rank])
     gb = s.blocks[0]
     if world > 1:
-        par = importlib.import_module("fest-3d_b200.parallel")
+        par = importlib.import_module("fest3d_b200.parallel")
         uid = par.broadcast_unique_id(dist, solver_mod.Solver.unique_id, rank, device="cuda")
         s.init_comm(world, rank, uid, par.block_to_rank(world, world))
     stream = torch.cuda.Stream()          # a real (non-default) stream, so CUDA events bracket exactly our launches

@@ -1,10 +1,6 @@
 // Generation-3 fused sweep: the common instantiations (no pressure-based switching, no transition model) and the dispatcher.
 // The kernel template lives in sweep3_kernel.cuh; the instantiations with the rare options compile in sweep3_rare.cu.
-#ifdef F3D_STAGE_CPASYNC   // the previous staging (per-thread cp.async), kept for A/B measurements: make EXTRA=-DF3D_STAGE_CPASYNC
-#include "sweep3_kernel_cpasync.cuh"
-#else
 #include "sweep3_kernel.cuh"
-#endif
 
 namespace f3d {
 

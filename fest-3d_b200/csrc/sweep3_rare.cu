@@ -1,10 +1,6 @@
 // Generation-3 fused sweep: the instantiations that carry the code of the rare options (MUSCL / PPM pressure-based switching,
 // transition = bc); see sweep3_kernel.cuh.
-#ifdef F3D_STAGE_CPASYNC   // the previous staging (per-thread cp.async), kept for A/B measurements: make EXTRA=-DF3D_STAGE_CPASYNC
-#include "sweep3_kernel_cpasync.cuh"
-#else
 #include "sweep3_kernel.cuh"
-#endif
 
 namespace f3d {
 

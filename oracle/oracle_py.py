@@ -108,7 +108,7 @@ class OracleWorld:
 
     def __init__(self, blocks, fast=False):
         from importlib import import_module
-        case = import_module("fest-3d_b200.case")
+        case = import_module("fest3d_b200.case")
         enums = (case.SCHEMES, case.INTERPOLANTS, case.TURBULENCE, case.TRANSITION, case.TIME_ACCURACY)
         self.L = lib(fast)
         self.blocks = blocks

@@ -1,8 +1,8 @@
 import sys, os, importlib
 sys.path[:0] = ['/root/repo', '/root/repo/oracle', '/root/repo/tests']
 import numpy as np, helpers, fixtures, oracle_py
-case_mod = importlib.import_module('fest-3d_b200.case')
-solver = importlib.import_module('fest-3d_b200.solver')
+case_mod = importlib.import_module('fest3d_b200.case')
+solver = importlib.import_module('fest3d_b200.solver')
 blocks = fixtures.load(case_mod, 'tests/golden/tfp', scheme=dict(scheme_name="ausmUP", interpolant="muscl", time_step_accuracy="RK4"), control=dict(CFL=0.5))
 s = solver.Solver(blocks); w = oracle_py.OracleWorld(blocks)
 err, ro = w.residual(1); rg = s.residual()

@@ -5,7 +5,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
-case_mod = importlib.import_module("fest-3d_b200.case"); solver = importlib.import_module("fest-3d_b200.solver")
+case_mod = importlib.import_module("fest3d_b200.case"); solver = importlib.import_module("fest3d_b200.solver")
 import fixtures
 G = os.path.join(ROOT, "tests", "golden")
 blocks = fixtures.load(case_mod, os.path.join(G, "smoothbump"), scheme=dict(time_step_accuracy="RK4"), control=dict(CFL=1.0))

@@ -4,9 +4,9 @@ import importlib, json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
 import numpy as np
-syn = importlib.import_module("fest-3d_b200.synthetic")
-geo = importlib.import_module("fest-3d_b200.geometry")
-solver = importlib.import_module("fest-3d_b200.solver")
+syn = importlib.import_module("fest3d_b200.synthetic")
+geo = importlib.import_module("fest3d_b200.geometry")
+solver = importlib.import_module("fest3d_b200.solver")
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 blocks = syn.make_duct_blocks(n, turbulence="sst")
 blk = blocks[0]

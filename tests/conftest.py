@@ -17,12 +17,12 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def pkg():
     """The product package; its directory name has a hyphen, so it is imported by string."""
-    return importlib.import_module("fest-3d_b200")
+    return importlib.import_module("fest3d_b200")
 
 
 @pytest.fixture(scope="session")
 def case_mod():
-    return importlib.import_module("fest-3d_b200.case")
+    return importlib.import_module("fest3d_b200.case")
 
 
 @pytest.fixture(scope="session")

@@ -52,7 +52,7 @@ def copy_case(name, ref):
 def main():
     for name, ref in CASES.items():
         copy_case(name, ref)
-    case_mod = importlib.import_module("fest-3d_b200.case")
+    case_mod = importlib.import_module("fest3d_b200.case")
     import fixtures
     import oracle_py
     out = {}

@@ -25,7 +25,7 @@ def blank_block(case_mod, imx, jmx, kmx, bc_id=None, interpolant="muscl", scheme
 
 
 def unit_cube_geometry(blk, h=1.0):
-    geo = importlib.import_module("fest-3d_b200.geometry")
+    geo = importlib.import_module("fest3d_b200.geometry")
     k, j, i = np.meshgrid(np.arange(blk.kmx), np.arange(blk.jmx), np.arange(blk.imx), indexing="ij")
     nodes = np.stack([i * h, j * h, k * h], axis=-1).astype(np.float64)
     blk.nodes = geo.ghost_grid(nodes)

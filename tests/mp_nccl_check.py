@@ -22,9 +22,9 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    par = importlib.import_module("fest-3d_b200.parallel")
-    syn = importlib.import_module("fest-3d_b200.synthetic")
-    solver = importlib.import_module("fest-3d_b200.solver")
+    par = importlib.import_module("fest3d_b200.parallel")
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    solver = importlib.import_module("fest3d_b200.solver")
     nb = par.block_grid(world)
     kw = dict(n3=(12, 10, 8), nb=nb, turbulence="sst", time_step_accuracy="RK4", CFL=0.5)
     all_blocks = syn.make_duct_blocks(None, **kw)

@@ -20,7 +20,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 def _solver(pkg_mod, blocks):
     import importlib
-    solver = importlib.import_module("fest-3d_b200.solver")
+    solver = importlib.import_module("fest3d_b200.solver")
     return solver.Solver(blocks)
 
 
@@ -112,7 +112,7 @@ def test_tfp_sst_ausmup(pkg, case_mod, oracle):
 @pytest.mark.parametrize("interpolant", ["none", "muscl", "ppm", "weno", "weno_NM"])
 def test_duct_sst_residual(pkg, case_mod, oracle, scheme_name, interpolant):
     import importlib
-    syn = importlib.import_module("fest-3d_b200.synthetic")
+    syn = importlib.import_module("fest3d_b200.synthetic")
     blocks = syn.make_duct_blocks(None, n3=(20, 12, 10), scheme_name=scheme_name, interpolant=interpolant, turbulence="sst")
     s = _solver(pkg, blocks)
     _check_residual(oracle, s, blocks)
@@ -123,7 +123,7 @@ def test_duct_sst_residual(pkg, case_mod, oracle, scheme_name, interpolant):
 @pytest.mark.parametrize("ta", ["none", "RK2", "RK4", "TVDRK2", "TVDRK3"])
 def test_duct_time_integrators(pkg, case_mod, oracle, turbulence, mu_ref, ta):
     import importlib
-    syn = importlib.import_module("fest-3d_b200.synthetic")
+    syn = importlib.import_module("fest3d_b200.synthetic")
     blocks = syn.make_duct_blocks(None, n3=(14, 10, 9), turbulence=turbulence, mu_ref=mu_ref, time_step_accuracy=ta, CFL=0.6)
     s = _solver(pkg, blocks)
     _check_history(oracle, s, blocks, 6)
@@ -134,7 +134,7 @@ def test_duct_time_integrators(pkg, case_mod, oracle, turbulence, mu_ref, ta):
 @pytest.mark.parametrize("scheme_name,interpolant", [("ausm", "muscl"), ("slau", "weno"), ("van_leer", "none")])
 def test_duct_sa_residual(pkg, case_mod, oracle, scheme_name, interpolant):
     import importlib
-    syn = importlib.import_module("fest-3d_b200.synthetic")
+    syn = importlib.import_module("fest3d_b200.synthetic")
     blocks = syn.make_duct_blocks(None, n3=(20, 12, 10), scheme_name=scheme_name, interpolant=interpolant, turbulence="sa")
     s = _solver(pkg, blocks)
     _check_residual(oracle, s, blocks)
@@ -144,7 +144,7 @@ def test_duct_sa_residual(pkg, case_mod, oracle, scheme_name, interpolant):
 @pytest.mark.parametrize("ta", ["none", "RK4", "TVDRK3"])
 def test_duct_sa_history(pkg, case_mod, oracle, ta):
     import importlib
-    syn = importlib.import_module("fest-3d_b200.synthetic")
+    syn = importlib.import_module("fest3d_b200.synthetic")
     blocks = syn.make_duct_blocks(None, n3=(14, 10, 9), turbulence="sa", time_step_accuracy=ta, CFL=0.6)
     s = _solver(pkg, blocks)
     _check_history(oracle, s, blocks, 6)
@@ -155,7 +155,7 @@ def test_duct_sa_history(pkg, case_mod, oracle, ta):
 @pytest.mark.parametrize("shape", [(6, 5, 1), (9, 7, 5)])
 def test_sa_boundary_conditions(pkg, case_mod, oracle, bc, shape):
     import importlib
-    syn = importlib.import_module("fest-3d_b200.synthetic")
+    syn = importlib.import_module("fest3d_b200.synthetic")
     if (-9 in bc[4:]) and shape[2] < 3:
         pytest.skip("periodic slab copy needs 3 interior layers")
     blocks = syn.make_duct_blocks(None, n3=shape, turbulence="sa", time_step_accuracy="RK2", interpolant="muscl")
@@ -177,7 +177,7 @@ def test_sa_boundary_conditions(pkg, case_mod, oracle, bc, shape):
 @pytest.mark.parametrize("shape,pb", [((20, 12, 10), (1, 1, 1)), ((33, 9, 1), (1, 0, 1)), ((7, 6, 5), (0, 1, 0))])
 def test_pressure_based_switching(pkg, case_mod, oracle, interpolant, shape, pb):
     import importlib
-    syn = importlib.import_module("fest-3d_b200.synthetic")
+    syn = importlib.import_module("fest3d_b200.synthetic")
     blocks = syn.make_duct_blocks(None, n3=shape, scheme_name="ausm", interpolant=interpolant, turbulence="sst", time_step_accuracy="RK2")
     blk = blocks[0]
     blk.scheme.pb_switch = pb
@@ -192,7 +192,7 @@ def test_pressure_based_switching(pkg, case_mod, oracle, interpolant, shape, pb)
 @pytest.mark.parametrize("turbulence", ["sst", "sst2003", "sa"])
 def test_transition_bc_source(pkg, case_mod, oracle, turbulence):
     import importlib
-    syn = importlib.import_module("fest-3d_b200.synthetic")
+    syn = importlib.import_module("fest3d_b200.synthetic")
     blocks = syn.make_duct_blocks(None, n3=(16, 12, 10), turbulence=turbulence, time_step_accuracy="RK4", CFL=0.5)
     for b in blocks:
         b.scheme.transition = "bc"
@@ -204,7 +204,7 @@ def test_transition_bc_source(pkg, case_mod, oracle, turbulence):
 
 def test_duct_multiblock_local_links(pkg, case_mod, oracle):
     import importlib
-    syn = importlib.import_module("fest-3d_b200.synthetic")
+    syn = importlib.import_module("fest3d_b200.synthetic")
     blocks = syn.make_duct_blocks(None, n3=(10, 8, 6), nb=(2, 2, 2), time_step_accuracy="RK4")
     s = _solver(pkg, blocks)
     _check_residual(oracle, s, blocks)
@@ -229,7 +229,7 @@ def test_nccl_halo_exchange_multi_rank():
 
 def test_global_time_step_and_weno_history(pkg, case_mod, oracle):
     import importlib
-    syn = importlib.import_module("fest-3d_b200.synthetic")
+    syn = importlib.import_module("fest3d_b200.synthetic")
     blocks = syn.make_duct_blocks(None, n3=(12, 9, 8), interpolant="weno", scheme_name="ausmP", time_step_accuracy="TVDRK3", CFL=0.4)
     for b in blocks:
         b.scheme.time_stepping_method = "g"; b.scheme.global_time_step = -1.0   # computed: block-local minval
@@ -246,7 +246,7 @@ def test_global_time_step_and_weno_history(pkg, case_mod, oracle):
 @pytest.mark.parametrize("accur", [0, 1])
 def test_boundary_conditions(pkg, case_mod, oracle, bc, shape, accur):
     import importlib
-    syn = importlib.import_module("fest-3d_b200.synthetic")
+    syn = importlib.import_module("fest3d_b200.synthetic")
     if (-9 in bc[4:]) and shape[2] < 3:
         pytest.skip("periodic slab copy needs 3 interior layers")
     if (-9 in bc[:2]) and shape[0] < 3:
@@ -273,7 +273,7 @@ def test_shipped_smoothbump_output_relaxes_to_the_reported_entropy(pkg, case_mod
     muscl + ausm) damp its residual and hold the entropy measure of tests/SmoothBump/pp/entropy.py within 3 % of the figure in
     tests/Report.txt (7.883e-07; the CPU oracle settles at 7.884e-07 +- 0.15 % over iterations 32000..39000 of the same march)."""
     import importlib
-    solver = importlib.import_module("fest-3d_b200.solver")
+    solver = importlib.import_module("fest3d_b200.solver")
     ref = np.load(os.path.join(GOLDEN, "smoothbump_reference_output.npz"))
     blocks = _load_fixture(case_mod, "smoothbump", scheme=dict(time_step_accuracy="RK4"), control=dict(CFL=1.0))
     for b, blk in enumerate(blocks):
@@ -302,8 +302,8 @@ def test_shipped_smoothbump_output_relaxes_to_the_reported_entropy(pkg, case_mod
 def test_wall_distance_on_device(pkg, case_mod, oracle, shape):
     import ctypes as C
     import importlib
-    syn = importlib.import_module("fest-3d_b200.synthetic")
-    geo = importlib.import_module("fest-3d_b200.geometry")
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    geo = importlib.import_module("fest3d_b200.geometry")
     blocks = syn.make_duct_blocks(None, n3=shape, turbulence="sst")
     blk = blocks[0]
     wall = geo.surface_nodes(blk.nodes, blk.bc_id)
@@ -331,8 +331,8 @@ def test_geometry_on_device(pkg, case_mod, oracle, shape, bc):
     areas / unit normals (pole faces: A = 0, copied normals), volumes, centres; then a residual evaluated from device-built
     geometry against the oracle fed with the host's arrays (that exercises the gathered ghost-gradient face records too)."""
     import importlib
-    syn = importlib.import_module("fest-3d_b200.synthetic")
-    solver = importlib.import_module("fest-3d_b200.solver")
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    solver = importlib.import_module("fest3d_b200.solver")
     blocks = syn.make_duct_blocks(None, n3=shape, turbulence="sst")
     blk = blocks[0]
     if bc is not None:
@@ -353,8 +353,8 @@ def test_geometry_on_device(pkg, case_mod, oracle, shape, bc):
 
 def test_geometry_on_device_reports_a_folded_cell(pkg, case_mod):
     import importlib
-    syn = importlib.import_module("fest-3d_b200.synthetic")
-    solver = importlib.import_module("fest-3d_b200.solver")
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    solver = importlib.import_module("fest3d_b200.solver")
     blocks = syn.make_duct_blocks(None, n3=(7, 6, 5), turbulence="none", mu_ref=0.0)
     blk = blocks[0]
     g = solver.GpuBlock(blk, 0)
@@ -373,8 +373,8 @@ def test_async_checkpoint_and_bitwise_restart(pkg, case_mod, tmp_path, tsa, turb
     (== get_state taken then), and a fresh solver restarted from the file reproduces iterations 4..6 BIT FOR BIT (norm history
     and final state incl. ghost cells): everything else on the device is re-derived from qp each iteration."""
     import importlib
-    syn = importlib.import_module("fest-3d_b200.synthetic")
-    solver = importlib.import_module("fest-3d_b200.solver")
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    solver = importlib.import_module("fest3d_b200.solver")
     kw = dict(mu_ref=0.0) if turb == "none" else {}
     mk = lambda: syn.make_duct_blocks(None, nb=(2, 1, 1), n3=(12, 10, 8), turbulence=turb, time_step_accuracy=tsa, CFL=0.5, **kw)
     s = solver.Solver(mk())
@@ -385,7 +385,7 @@ def test_async_checkpoint_and_bitwise_restart(pkg, case_mod, tmp_path, tsa, turb
     hist = s.iterate(3)            # overlaps the copy and the file write
     s.checkpoint_wait()
     final = [b.get_state() for b in s.blocks]
-    ck = importlib.import_module("fest-3d_b200.checkpoint")
+    ck = importlib.import_module("fest3d_b200.checkpoint")
     for b, q in zip(s.blocks, snap):
         hdr, qf = ck.read_checkpoint("%s_%02d.f3dckpt" % (prefix, b.blk.block_id))
         assert hdr == dict(imx=b.blk.imx, jmx=b.blk.jmx, kmx=b.blk.kmx, n_var=b.blk.n_var, iter=4)
@@ -405,8 +405,8 @@ def test_async_checkpoint_and_bitwise_restart(pkg, case_mod, tmp_path, tsa, turb
 
 def test_restart_rejects_a_foreign_checkpoint(pkg, case_mod, tmp_path):
     import importlib
-    syn = importlib.import_module("fest-3d_b200.synthetic")
-    solver = importlib.import_module("fest-3d_b200.solver")
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    solver = importlib.import_module("fest3d_b200.solver")
     a = solver.Solver(syn.make_duct_blocks(None, n3=(8, 6, 5), turbulence="sst"))
     a.checkpoint_begin(str(tmp_path / "a"))
     a.checkpoint_wait()
@@ -427,8 +427,8 @@ def test_restart_rejects_a_foreign_checkpoint(pkg, case_mod, tmp_path):
 
 def test_unsupported_is_an_error_not_a_fallback(pkg, case_mod):
     import importlib
-    syn = importlib.import_module("fest-3d_b200.synthetic")
-    solver = importlib.import_module("fest-3d_b200.solver")
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    solver = importlib.import_module("fest3d_b200.solver")
     blocks = syn.make_duct_blocks(None, n3=(6, 5, 4), turbulence="none", mu_ref=0.0, time_step_accuracy="implicit")
     with pytest.raises(solver.Fest3dError):
         solver.Solver(blocks)
@@ -436,8 +436,8 @@ def test_unsupported_is_an_error_not_a_fallback(pkg, case_mod):
 
 def test_negative_pressure_is_reported(pkg, case_mod):
     import importlib
-    syn = importlib.import_module("fest-3d_b200.synthetic")
-    solver = importlib.import_module("fest-3d_b200.solver")
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    solver = importlib.import_module("fest3d_b200.solver")
     blocks = syn.make_duct_blocks(None, n3=(8, 6, 5), turbulence="none", mu_ref=0.0, CFL=50.0)
     blocks[0].qp[4, 5, 5, 5] *= 40.0   # a blast the explicit step at CFL 50 cannot survive
     s = solver.Solver(blocks)
@@ -450,7 +450,7 @@ def test_negative_pressure_is_reported(pkg, case_mod):
 # ---- full-size, size-independent properties (256^3, BASELINE config sizes; no oracle at this size) ---------------------
 def test_fullsize_freestream_preservation_and_telescoping(pkg, case_mod):
     import importlib
-    syn = importlib.import_module("fest-3d_b200.synthetic")
+    syn = importlib.import_module("fest3d_b200.synthetic")
     n = int(os.environ.get("FEST3D_FULLSIZE_N", "256"))
     blocks = syn.make_duct_blocks(n, turbulence="none", mu_ref=0.0, time_step_accuracy="none", interpolant="muscl")
     blk = blocks[0]

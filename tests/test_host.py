@@ -16,7 +16,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
 def test_abi_exports_every_declared_symbol():
-    capi = importlib.import_module("fest-3d_b200.capi")
+    capi = importlib.import_module("fest3d_b200.capi")
     hdr = open(os.path.join(ROOT, "include", "fest3d_gpu.h")).read()
     declared = sorted(set(re.findall(r"\b(fest3d_gpu_[a-z_0-9]+)\s*\(", hdr)))
     assert declared == sorted(capi.SYMBOLS)
@@ -30,7 +30,7 @@ def test_no_device_is_an_error_not_a_fallback():
     import torch
     if torch.cuda.is_available():
         pytest.skip("a GPU is present")
-    capi = importlib.import_module("fest-3d_b200.capi")
+    capi = importlib.import_module("fest3d_b200.capi")
     lib = capi.lib()
     h = C.c_void_p()
     cfg = capi.Fest3dGpuConfig()
@@ -39,7 +39,7 @@ def test_no_device_is_an_error_not_a_fallback():
 
 
 def test_config_struct_layout_matches_header():
-    capi = importlib.import_module("fest-3d_b200.capi")
+    capi = importlib.import_module("fest3d_b200.capi")
     # 10 ints + 3*3 + 2 + 4*6 + 3*12 + 2 = 83 ints -> padded to 8-byte alignment, then 20 doubles + 11 x 6 fixed values
     n_int = 4 + 4 + 2 + 9 + 2 + 24 + 36 + 2
     size = ((n_int * 4 + 7) // 8) * 8 + (2 + 7 + 5 + 4 + 2 + 66) * 8
@@ -90,7 +90,7 @@ def test_case_reader_tfp_restart_and_walls(case_mod):
 
 
 def test_geometry_invariants(case_mod):
-    syn = importlib.import_module("fest-3d_b200.synthetic")
+    syn = importlib.import_module("fest3d_b200.synthetic")
     blk = syn.make_duct_blocks(None, n3=(7, 6, 5), turbulence="none", mu_ref=0.0)[0]
     If, Jf, Kf, cells = blk.Ifaces, blk.Jfaces, blk.Kfaces, blk.cells
     for f in (If, Jf, Kf):
@@ -132,7 +132,7 @@ def test_oracle_reproduces_golden_vectors(case_mod, oracle):
 
 def test_oracle_block_split_equals_lockstep_order(case_mod, oracle):
     """Two worlds built from the same blocks give identical results (threads per block do not change arithmetic)."""
-    syn = importlib.import_module("fest-3d_b200.synthetic")
+    syn = importlib.import_module("fest3d_b200.synthetic")
     blocks = syn.make_duct_blocks(None, n3=(8, 6, 5), nb=(2, 1, 1), time_step_accuracy="RK2")
     a, b = oracle.OracleWorld(blocks), oracle.OracleWorld(blocks)
     for it in (1, 2, 3):
@@ -143,7 +143,7 @@ def test_oracle_block_split_equals_lockstep_order(case_mod, oracle):
 
 def test_oracle_far_field_turbulence_rule(case_mod, oracle):
     """bc_primitive.f90:700-757: ghost k/omega of a far-field face are decided by the LAST cell of the face loop."""
-    syn = importlib.import_module("fest-3d_b200.synthetic")
+    syn = importlib.import_module("fest3d_b200.synthetic")
     blk = syn.make_duct_blocks(None, n3=(6, 5, 4), turbulence="sst")[0]
     blk.bc_id = [-8, -8, -6, -6, -6, -6]
     w = oracle.OracleWorld([blk])
@@ -157,7 +157,7 @@ def test_oracle_far_field_turbulence_rule(case_mod, oracle):
 def test_checkpoint_side_format_roundtrip(tmp_path):
     """The host-side reader / writer of the binary checkpoint format (include/fest3d_gpu.h): 64-byte header, qp with ghosts."""
     import importlib
-    ck = importlib.import_module("fest-3d_b200.checkpoint")
+    ck = importlib.import_module("fest3d_b200.checkpoint")
     rng = np.random.default_rng(7)
     q = rng.standard_normal((7, 4 + 5, 6 + 5, 9 + 5))
     path = str(tmp_path / "a.f3dckpt")

@@ -157,7 +157,7 @@ def test_total_pressure_bc_free_stream(oracle, case_mod):
     face, the Riemann state is the free stream itself (Unb = -u_inf, Cb = c_inf, Mb = M_inf), so the ghost cells of the
     face must reproduce it."""
     import importlib
-    syn = importlib.import_module("fest-3d_b200.synthetic")
+    syn = importlib.import_module("fest3d_b200.synthetic")
     blocks = syn.make_duct_blocks(None, n3=(6, 5, 4), turbulence="sst", interpolant="muscl")
     blk = blocks[0]
     blk.bc_id = [-11, -4, -6, -6, -6, -6]
@@ -183,7 +183,7 @@ def test_sa_oracle_closure_identities(oracle, case_mod):
     -rho cw1 fw (tv/d)^2 with fw(r=tv/(S kd2)) evaluated at S = tv fv2/kd2 (source.f90:940-975), and the update
     clamps tv at 1e-12 (update.f90:474-475)."""
     import importlib
-    syn = importlib.import_module("fest-3d_b200.synthetic")
+    syn = importlib.import_module("fest3d_b200.synthetic")
     blocks = syn.make_duct_blocks(None, n3=(8, 7, 6), turbulence="sa", time_step_accuracy="none", CFL=0.5)
     blk = blocks[0]
     w = oracle.OracleWorld(blocks)
@@ -205,7 +205,7 @@ def test_pressure_based_switching_against_numpy(oracle, case_mod):
     pdif = 1 - |p(i+1) - p(i-1)| / (|p(i+1) - p(i-1)| + p_inf), ghost positions 0 / imx taking the value of cells 1 / imx-1
     (independent numpy restatement on the ghost-filled state the oracle itself used)."""
     import importlib
-    syn = importlib.import_module("fest-3d_b200.synthetic")
+    syn = importlib.import_module("fest3d_b200.synthetic")
 
     def run(pb):
         blocks = syn.make_duct_blocks(None, n3=(9, 6, 5), turbulence="none", mu_ref=0.0, interpolant="muscl")
@@ -246,7 +246,7 @@ def test_transition_bc_only_touches_the_turbulence_equations(oracle, case_mod, t
     """transition = bc multiplies the production term of the k / nu-tilde equation by gamma_BC in [0, 1]
     (source.f90:570-586, 1156-1172): the five flow equations keep their residual bit for bit, the model equation changes."""
     import importlib
-    syn = importlib.import_module("fest-3d_b200.synthetic")
+    syn = importlib.import_module("fest3d_b200.synthetic")
     res = {}
     for tr in ("none", "bc"):
         blocks = syn.make_duct_blocks(None, n3=(10, 8, 6), turbulence=turbulence)
@@ -263,8 +263,8 @@ def test_transition_bc_only_touches_the_turbulence_equations(oracle, case_mod, t
 
 def _wall_case(shape=(7, 6, 5)):
     import importlib
-    syn = importlib.import_module("fest-3d_b200.synthetic")
-    geo = importlib.import_module("fest-3d_b200.geometry")
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    geo = importlib.import_module("fest3d_b200.geometry")
     blk = syn.make_duct_blocks(None, n3=shape, turbulence="sst")[0]
     wall = geo.surface_nodes(blk.nodes, blk.bc_id)          # the four no-slip walls of the duct, rounded like the text file
     return blk, geo, wall

@@ -21,8 +21,8 @@ def _worker(rank, world, port, nb, q):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
-    par = importlib.import_module("fest-3d_b200.parallel")
-    syn = importlib.import_module("fest-3d_b200.synthetic")
+    par = importlib.import_module("fest3d_b200.parallel")
+    syn = importlib.import_module("fest3d_b200.synthetic")
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -74,7 +74,7 @@ def test_halo_plan_pairs_up_world2(nb):
 
 
 def test_block_ownership():
-    par = importlib.import_module("fest-3d_b200.parallel")
+    par = importlib.import_module("fest3d_b200.parallel")
     assert par.block_to_rank(8, 8) == list(range(8))          # the reference's rank == block
     assert par.block_to_rank(8, 2) == [0, 0, 0, 0, 1, 1, 1, 1]
     assert par.rank_blocks(8, 4, 3) == [6, 7]
