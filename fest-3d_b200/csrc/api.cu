@@ -48,8 +48,11 @@ constexpr int kNcclFloat64 = 8, kNcclSum = 0;
 }  // namespace
 
 static int fail(Fest3dGpuCtx* ctx, int cls) { if (ctx) ctx->last_error.flags |= cls; return cls; }
+#define F3D_CUDA_RC(call) do { if ((call) != cudaSuccess) return F3D_ERR_CUDA; } while (0)
 
 extern "C" const char* fest3d_gpu_version(void) { return "fest3d-b200 0.1 (sm_100a)"; }
+
+static int create_impl(Fest3dGpuCtx* ctx, const Fest3dGpuConfig* cfg, int device, bool sst, bool sa);
 
 extern "C" int fest3d_gpu_create(Fest3dGpuCtx** out, const Fest3dGpuConfig* cfg, int device) {
   if (!out || !cfg) return F3D_ERR_ARGUMENT;
@@ -73,6 +76,13 @@ extern "C" int fest3d_gpu_create(Fest3dGpuCtx** out, const Fest3dGpuConfig* cfg,
   Fest3dGpuCtx* ctx = new Fest3dGpuCtx();
   ctx->cfg = *cfg;
   ctx->device = device;
+  const int rc = create_impl(ctx, cfg, device, sst, sa);
+  if (rc) { fest3d_gpu_destroy(ctx); return rc; }   // every allocation made so far is released
+  *out = ctx;
+  return 0;
+}
+
+static int create_impl(Fest3dGpuCtx* ctx, const Fest3dGpuConfig* cfg, int device, bool sst, bool sa) {
   F3D_CUDA(cudaSetDevice(device));
   Params& P = ctx->P;
   memset(&P, 0, sizeof(P));
@@ -131,7 +141,6 @@ extern "C" int fest3d_gpu_create(Fest3dGpuCtx** out, const Fest3dGpuConfig* cfg,
 
   F3D_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
   ctx->stream = ctx->own_stream;
-  F3D_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
   F3D_CUDA(cudaEventCreateWithFlags(&ctx->ev_pack, cudaEventDisableTiming));
   F3D_CUDA(cudaEventCreateWithFlags(&ctx->ev_halo, cudaEventDisableTiming));
   const size_t fb = (size_t)L.fs * sizeof(double);
@@ -210,9 +219,10 @@ extern "C" int fest3d_gpu_create(Fest3dGpuCtx** out, const Fest3dGpuConfig* cfg,
   }
   F3D_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->last_error.block_id = cfg->block_id;
-  *out = ctx;
   return 0;
 }
+
+static void comm_release(Fest3dGpuCtx* ctx);
 
 extern "C" int fest3d_gpu_destroy(Fest3dGpuCtx* ctx) {
   if (!ctx) return F3D_ERR_ARGUMENT;
@@ -228,9 +238,8 @@ extern "C" int fest3d_gpu_destroy(Fest3dGpuCtx* ctx) {
   if (ctx->norms_host) cudaFreeHost(ctx->norms_host);
   if (ctx->err_host) cudaFreeHost(ctx->err_host);
   for (auto& e : ctx->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
-  if (ctx->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)ctx->nccl);
+  comm_release(ctx);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
-  if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
   if (ctx->ev_pack) cudaEventDestroy(ctx->ev_pack);
   if (ctx->ev_halo) cudaEventDestroy(ctx->ev_halo);
   delete ctx;
@@ -349,7 +358,10 @@ extern "C" int fest3d_gpu_set_state(Fest3dGpuCtx* ctx, const double* qp) {
   const size_t n = (size_t)L.nv * (L.imx + 5) * (L.jmx + 5) * (L.kmx + 5);
   F3D_CUDA(cudaMemcpyAsync(ctx->state_staging, qp, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   if ((rc = launch_state_relayout(ctx, ctx->qp, ctx->state_staging, 1))) return rc;
+  // a fresh state (initial field, restart from a good checkpoint) clears the sticky device error word of an earlier failure
+  F3D_CUDA(cudaMemsetAsync(ctx->err_dev, 0, sizeof(int) * 4, ctx->stream));
   F3D_CUDA(cudaStreamSynchronize(ctx->stream));
+  { const int bid = ctx->last_error.block_id; ctx->last_error = Fest3dGpuError{}; ctx->last_error.block_id = bid; }
   ctx->state_set = true;
   return 0;
 }
@@ -435,28 +447,76 @@ extern "C" int fest3d_gpu_comm_unique_id(char id_out[128]) {
   return 0;
 }
 
-extern "C" int fest3d_gpu_comm_init(Fest3dGpuCtx* ctx, int n_ranks, int rank, const char id[128], const int* block_to_rank) {
-  if (!ctx || !id || !block_to_rank) return fail(ctx, F3D_ERR_ARGUMENT);
-  if (!g_nccl.load()) { fprintf(stderr, "fest3d_gpu: libnccl.so.2 not found\n"); return fail(ctx, F3D_ERR_UNSUPPORTED); }
-  F3D_CUDA(cudaSetDevice(ctx->device));
+// One communicator per process: every context of a rank shares it (a second ncclCommInitRank with the same id and rank would
+// hang), and every NCCL call of the rank goes to ONE communication stream, so that the send / receive lists of two ranks pair
+// up whatever the number of blocks each of them owns.
+namespace {
+struct CommShared {
   ncclUniqueId uid;
-  memcpy(uid.internal, id, 128);
-  ncclComm_t comm;
-  if (g_nccl.CommInitRank(&comm, n_ranks, uid, rank) != 0) return fail(ctx, F3D_ERR_CUDA);
-  ctx->nccl = comm; ctx->n_ranks = n_ranks; ctx->rank = rank;
+  ncclComm_t comm = nullptr;
+  int n_ranks = 0, rank = -1, device = -1, refs = 0;
+  cudaStream_t stream = nullptr;     // all sends / receives / all-reduces of this process
+  cudaEvent_t ev_done = nullptr;     // recorded behind the last NCCL call of an exchange
+  int* err_word = nullptr;           // device int: OR of the error words of this rank's contexts, max-reduced over the ranks
+  int* err_host = nullptr;           // pinned
+};
+std::vector<CommShared*> g_comms;
+}  // namespace
+
+extern "C" int fest3d_gpu_comm_init(Fest3dGpuCtx* ctx, int n_ranks, int rank, const char id[128], const int* block_to_rank) {
+  if (!ctx || !id || !block_to_rank || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(ctx, F3D_ERR_ARGUMENT);
+  if (!g_nccl.load()) { fprintf(stderr, "fest3d_gpu: libnccl.so.2 not found\n"); return fail(ctx, F3D_ERR_UNSUPPORTED); }
+  if (ctx->nccl) return fail(ctx, F3D_ERR_ARGUMENT);   // already initialised
+  F3D_CUDA(cudaSetDevice(ctx->device));
+  CommShared* cs = nullptr;
+  for (CommShared* c : g_comms)
+    if (memcmp(c->uid.internal, id, 128) == 0) { cs = c; break; }
+  if (cs) {
+    // the same rank of the same communicator lives on one device: a process that drives several GPUs needs one rank per device
+    if (cs->rank != rank || cs->n_ranks != n_ranks || cs->device != ctx->device) return fail(ctx, F3D_ERR_UNSUPPORTED);
+  } else {
+    cs = new CommShared();
+    memcpy(cs->uid.internal, id, 128);
+    cs->n_ranks = n_ranks; cs->rank = rank; cs->device = ctx->device;
+    if (g_nccl.CommInitRank(&cs->comm, n_ranks, cs->uid, rank) != 0) { delete cs; return fail(ctx, F3D_ERR_CUDA); }
+    bool ok = cudaStreamCreateWithFlags(&cs->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&cs->ev_done, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&cs->err_word, sizeof(int)) == cudaSuccess && cudaMallocHost((void**)&cs->err_host, sizeof(int)) == cudaSuccess;
+    if (!ok) return fail(ctx, F3D_ERR_CUDA);
+    g_comms.push_back(cs);
+  }
+  cs->refs++;
+  ctx->nccl = cs; ctx->n_ranks = n_ranks; ctx->rank = rank;
   ctx->block_to_rank.assign(block_to_rank, block_to_rank + ctx->cfg.n_blocks);
   for (int f = 0; f < 6; ++f) {
     Link& lk = ctx->link[f];
-    if (lk.neighbour_block < 0 || lk.kind == 1) continue;
+    if (lk.neighbour_block < 0 || lk.neighbour_block >= ctx->cfg.n_blocks) continue;
+    if (ctx->block_to_rank[lk.neighbour_block] == rank) continue;   // a block of this process: fest3d_gpu_link_local
     lk.rank = ctx->block_to_rank[lk.neighbour_block];
     lk.kind = 2;
   }
   return 0;
 }
 
+static void comm_release(Fest3dGpuCtx* ctx) {
+  CommShared* cs = (CommShared*)ctx->nccl;
+  if (!cs) return;
+  ctx->nccl = nullptr;
+  if (--cs->refs > 0) return;
+  cudaSetDevice(cs->device);
+  if (cs->stream) cudaStreamSynchronize(cs->stream);
+  if (g_nccl.CommDestroy) g_nccl.CommDestroy(cs->comm);
+  if (cs->stream) cudaStreamDestroy(cs->stream);
+  if (cs->ev_done) cudaEventDestroy(cs->ev_done);
+  if (cs->err_word) cudaFree(cs->err_word);
+  if (cs->err_host) cudaFreeHost(cs->err_host);
+  g_comms.erase(std::remove(g_comms.begin(), g_comms.end(), cs), g_comms.end());
+  delete cs;
+}
+
 extern "C" int fest3d_gpu_link_local(Fest3dGpuCtx* a, Fest3dGpuCtx* b) {
   if (!a || !b) return F3D_ERR_ARGUMENT;
-  int n = 0;
+  int n = 0;   // a == b: a block that is its own neighbour (periodic with itself through PbcId)
   for (int f = 0; f < 6; ++f) {
     if (a->link[f].neighbour_block == b->cfg.block_id) { a->link[f].kind = 1; a->link[f].peer = b; ++n; }
     if (b->link[f].neighbour_block == a->cfg.block_id) { b->link[f].kind = 1; b->link[f].peer = a; ++n; }
@@ -468,149 +528,98 @@ namespace {
 
 struct Msg { int peer_rank, block, face; Fest3dGpuCtx* ctx; int my_face; };
 
-// apply_interface for every context of this process (interface1.f90:96-493)
+// apply_interface for every context of this process (interface1.f90:96-493).  No host synchronisation: every context keeps
+// its own stream, the hand-overs are events --
+//   pack (own stream) -> ev_pack -> { the process's communication stream: all ncclSend / ncclRecv of the rank in one group ;
+//   a local neighbour's stream: reads this context's send buffer } -> unpack (own stream) -> ev_halo
+// and a context re-packs a send buffer only after the local neighbour that reads it has recorded its ev_halo.
 int exchange(Fest3dGpuCtx** cs, int n) {
-  bool any = false;
-  for (int c = 0; c < n; ++c)
-    for (int f = 0; f < 6; ++f)
-      if (cs[c]->sendbuf[f] && cs[c]->link[f].kind != 0) {
-        cudaSetDevice(cs[c]->device);
-        int rc = launch_pack(cs[c], f + 1);
-        if (rc) return rc;
-        any = true;
-      }
-  if (!any) return 0;
-  // remote messages over NCCL, posted in a canonical order per peer so that sends and receives pair up
-  std::vector<Msg> sends, recvs;
+  bool any = false, remote = false;
   for (int c = 0; c < n; ++c)
     for (int f = 0; f < 6; ++f) {
-      const Link& lk = cs[c]->link[f];
-      if (lk.kind != 2) continue;
-      sends.push_back({lk.rank, cs[c]->cfg.block_id, f + 1, cs[c], f + 1});
-      recvs.push_back({lk.rank, lk.neighbour_block, cs[c]->cfg.otherface[f], cs[c], f + 1});
+      if (!cs[c]->sendbuf[f]) continue;
+      // an interface or periodic face nobody is attached to would leave its ghost layers stale: never a silent degraded path
+      if (cs[c]->link[f].kind == 0) return fail(cs[c], F3D_ERR_ARGUMENT);
+      any = true;
+      remote |= cs[c]->link[f].kind == 2;
     }
-  if (!sends.empty()) {
+  if (!any) return 0;
+  for (int c = 0; c < n; ++c) {
+    Fest3dGpuCtx* ctx = cs[c];
+    F3D_CUDA(cudaSetDevice(ctx->device));
+    for (int f = 0; f < 6; ++f)   // the readers of last stage's send buffers are done
+      if (ctx->link[f].kind == 1 && ctx->link[f].peer != ctx) F3D_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->link[f].peer->ev_halo, 0));
+    for (int f = 0; f < 6; ++f)
+      if (ctx->sendbuf[f]) { int rc = launch_pack(ctx, f + 1); if (rc) return rc; }
+    F3D_CUDA(cudaEventRecord(ctx->ev_pack, ctx->stream));
+  }
+  // remote messages over NCCL, posted in a canonical order per peer so that sends and receives pair up
+  CommShared* sh = nullptr;
+  if (remote) {
+    std::vector<Msg> sends, recvs;
+    for (int c = 0; c < n; ++c)
+      for (int f = 0; f < 6; ++f) {
+        const Link& lk = cs[c]->link[f];
+        if (lk.kind != 2) continue;
+        if (!cs[c]->nccl) return fail(cs[c], F3D_ERR_ARGUMENT);
+        if (sh && sh != (CommShared*)cs[c]->nccl) return fail(cs[c], F3D_ERR_UNSUPPORTED);   // one communicator per process
+        sh = (CommShared*)cs[c]->nccl;
+        sends.push_back({lk.rank, cs[c]->cfg.block_id, f + 1, cs[c], f + 1});
+        recvs.push_back({lk.rank, lk.neighbour_block, cs[c]->cfg.otherface[f], cs[c], f + 1});
+      }
     auto key = [](const Msg& a, const Msg& b) { return std::tie(a.peer_rank, a.block, a.face) < std::tie(b.peer_rank, b.block, b.face); };
     std::sort(sends.begin(), sends.end(), key);
     std::sort(recvs.begin(), recvs.end(), key);
+    cudaSetDevice(sh->device);
+    for (int c = 0; c < n; ++c) {
+      bool has = false;
+      for (int f = 0; f < 6; ++f) has |= cs[c]->link[f].kind == 2;
+      if (has) F3D_CUDA_RC(cudaStreamWaitEvent(sh->stream, cs[c]->ev_pack, 0));
+    }
     g_nccl.GroupStart();
-    for (const Msg& m : sends) {
-      cudaSetDevice(m.ctx->device);
-      g_nccl.Send(m.ctx->sendbuf[m.my_face - 1], m.ctx->buf_elems[m.my_face - 1], kNcclFloat64, m.peer_rank, (ncclComm_t)m.ctx->nccl, m.ctx->stream);
-    }
-    for (const Msg& m : recvs) {
-      cudaSetDevice(m.ctx->device);
-      g_nccl.Recv(m.ctx->recvbuf[m.my_face - 1], m.ctx->buf_elems[m.my_face - 1], kNcclFloat64, m.peer_rank, (ncclComm_t)m.ctx->nccl, m.ctx->stream);
-    }
+    for (const Msg& m : sends) g_nccl.Send(m.ctx->sendbuf[m.my_face - 1], m.ctx->buf_elems[m.my_face - 1], kNcclFloat64, m.peer_rank, sh->comm, sh->stream);
+    for (const Msg& m : recvs) g_nccl.Recv(m.ctx->recvbuf[m.my_face - 1], m.ctx->buf_elems[m.my_face - 1], kNcclFloat64, m.peer_rank, sh->comm, sh->stream);
     if (g_nccl.GroupEnd() != 0) return F3D_ERR_CUDA;
+    F3D_CUDA_RC(cudaEventRecord(sh->ev_done, sh->stream));
   }
-  // local links: make every packing visible, then read the peer's send buffer directly
-  bool local = false;
-  for (int c = 0; c < n; ++c) for (int f = 0; f < 6; ++f) local |= cs[c]->link[f].kind == 1;
-  if (local) for (int c = 0; c < n; ++c) { cudaSetDevice(cs[c]->device); cudaStreamSynchronize(cs[c]->stream); }
-  for (int c = 0; c < n; ++c)
+  for (int c = 0; c < n; ++c) {
+    Fest3dGpuCtx* ctx = cs[c];
+    F3D_CUDA(cudaSetDevice(ctx->device));
+    bool waited_comm = false;
     for (int f = 0; f < 6; ++f) {
-      const Link& lk = cs[c]->link[f];
+      const Link& lk = ctx->link[f];
       if (lk.kind == 0) continue;
-      cudaSetDevice(cs[c]->device);
-      const double* src = cs[c]->recvbuf[f];
+      const double* src = ctx->recvbuf[f];
       if (lk.kind == 1) {
-        const int of = cs[c]->cfg.otherface[f];
+        const int of = ctx->cfg.otherface[f];
         const double* peer_buf = lk.peer->sendbuf[of - 1];
-        if (lk.peer->device != cs[c]->device) {
-          cudaMemcpyPeerAsync(cs[c]->recvbuf[f], cs[c]->device, peer_buf, lk.peer->device, cs[c]->buf_elems[f] * sizeof(double), cs[c]->stream);
+        if (lk.peer != ctx) F3D_CUDA(cudaStreamWaitEvent(ctx->stream, lk.peer->ev_pack, 0));
+        if (lk.peer->device != ctx->device) {
+          F3D_CUDA(cudaMemcpyPeerAsync(ctx->recvbuf[f], ctx->device, peer_buf, lk.peer->device, ctx->buf_elems[f] * sizeof(double), ctx->stream));
         } else {
           src = peer_buf;
         }
+      } else if (!waited_comm) {
+        F3D_CUDA(cudaStreamWaitEvent(ctx->stream, sh->ev_done, 0));
+        waited_comm = true;
       }
-      int rc = launch_unpack(cs[c], f + 1, src);
+      int rc = launch_unpack(ctx, f + 1, src);
       if (rc) return rc;
     }
-  if (local) for (int c = 0; c < n; ++c) { cudaSetDevice(cs[c]->device); cudaStreamSynchronize(cs[c]->stream); }
-  return 0;
-}
-
-// The halo swap can run beside compute when every interface of this process goes over NCCL (one block per GPU, the
-// benchmark layout) and the run is viscous: the Green-Gauss gradients of the cells whose stencil is all-interior do not read
-// ghost cells, so they go first on the compute stream while the swap (pack -> send/recv -> unpack) runs on the context's
-// communication stream; ghost fill, the remaining gradients and the sweep wait for it.  Measured on 2 B200 (one 256^3 block
-// each, profiles/r01_g3_overlap_n2.md): the swap costs 0.02 ms of a 7.56 ms step over NVLink, the two-part gradient launch
-// costs 0.28 ms, so the overlapped schedule is OFF by default and F3D_OVERLAP=1 selects it (wide interfaces on slower links).
-bool can_overlap(Fest3dGpuCtx** cs, int n) {
-  static int on = -1;
-  if (on < 0) { const char* e = getenv("F3D_OVERLAP"); on = (e && e[0] == '1') ? 1 : 0; }
-  if (!on) return false;
-  bool remote = false;
-  for (int c = 0; c < n; ++c) {
-    if (!cs[c]->P.viscous) return false;
-    for (int f = 0; f < 6; ++f) {
-      if (cs[c]->link[f].kind == 1) return false;
-      if (cs[c]->link[f].kind == 2 && cs[c]->sendbuf[f]) remote = true;
-    }
-  }
-  return remote;
-}
-
-// apply_interface on the communication streams; leaves ev_halo recorded behind the last unpack of every context
-int exchange_overlapped(Fest3dGpuCtx** cs, int n) {
-  for (int c = 0; c < n; ++c) {
-    Fest3dGpuCtx* ctx = cs[c];
-    F3D_CUDA(cudaSetDevice(ctx->device));
-    for (int f = 0; f < 6; ++f)
-      if (ctx->sendbuf[f] && ctx->link[f].kind == 2) { int rc = launch_pack(ctx, f + 1); if (rc) return rc; }
-    F3D_CUDA(cudaEventRecord(ctx->ev_pack, ctx->stream));
-    F3D_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_pack, 0));
-  }
-  std::vector<Msg> sends, recvs;
-  for (int c = 0; c < n; ++c)
-    for (int f = 0; f < 6; ++f) {
-      const Link& lk = cs[c]->link[f];
-      if (lk.kind != 2) continue;
-      sends.push_back({lk.rank, cs[c]->cfg.block_id, f + 1, cs[c], f + 1});
-      recvs.push_back({lk.rank, lk.neighbour_block, cs[c]->cfg.otherface[f], cs[c], f + 1});
-    }
-  auto key = [](const Msg& a, const Msg& b) { return std::tie(a.peer_rank, a.block, a.face) < std::tie(b.peer_rank, b.block, b.face); };
-  std::sort(sends.begin(), sends.end(), key);
-  std::sort(recvs.begin(), recvs.end(), key);
-  g_nccl.GroupStart();
-  for (const Msg& m : sends) {
-    cudaSetDevice(m.ctx->device);
-    g_nccl.Send(m.ctx->sendbuf[m.my_face - 1], m.ctx->buf_elems[m.my_face - 1], kNcclFloat64, m.peer_rank, (ncclComm_t)m.ctx->nccl, m.ctx->comm_stream);
-  }
-  for (const Msg& m : recvs) {
-    cudaSetDevice(m.ctx->device);
-    g_nccl.Recv(m.ctx->recvbuf[m.my_face - 1], m.ctx->buf_elems[m.my_face - 1], kNcclFloat64, m.peer_rank, (ncclComm_t)m.ctx->nccl, m.ctx->comm_stream);
-  }
-  if (g_nccl.GroupEnd() != 0) return F3D_ERR_CUDA;
-  for (int c = 0; c < n; ++c) {
-    Fest3dGpuCtx* ctx = cs[c];
-    F3D_CUDA(cudaSetDevice(ctx->device));
-    cudaStream_t compute = ctx->stream;
-    ctx->stream = ctx->comm_stream;   // the unpack kernels of this swap run on the communication stream
-    int rc = 0;
-    for (int f = 0; f < 6 && !rc; ++f)
-      if (ctx->link[f].kind == 2) rc = launch_unpack(ctx, f + 1, ctx->recvbuf[f]);
-    ctx->stream = compute;
-    if (rc) return rc;
-    F3D_CUDA(cudaEventRecord(ctx->ev_halo, ctx->comm_stream));
+    F3D_CUDA(cudaEventRecord(ctx->ev_halo, ctx->stream));
   }
   return 0;
 }
 
 // one get_total_conservative_Residue (+ update) on every context
 int stage(Fest3dGpuCtx** cs, int n, bool update, double TF, double SF, int use_sum, int first, int last) {
-  const bool overlap = can_overlap(cs, n);
-  int rc = overlap ? exchange_overlapped(cs, n) : exchange(cs, n);
+  int rc = exchange(cs, n);
   if (rc) return rc;
   for (int c = 0; c < n; ++c) {
     Fest3dGpuCtx* ctx = cs[c];
     F3D_CUDA(cudaSetDevice(ctx->device));
-    if (overlap) {
-      if ((rc = launch_gradients(ctx, 1))) return rc;                       // beside the swap
-      F3D_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_halo, 0));
-    }
     if ((rc = launch_bc(ctx))) return rc;
-    if (ctx->P.viscous && (rc = launch_gradients(ctx, overlap ? 2 : 0))) return rc;
+    if (ctx->P.viscous && (rc = launch_gradients(ctx, 0))) return rc;
     if (!update) {
       if ((rc = launch_residual(ctx, MODE_RESIDUE_ONLY, 1.0, 1.0, 0, 1, 0))) return rc;
       continue;
@@ -673,7 +682,7 @@ extern "C" int fest3d_gpu_step_group(Fest3dGpuCtx** cs, int n, int current_iter,
   const int nvp1 = cs[0]->P.L.nv + 1;
   const int ta = cs[0]->cfg.time_accuracy;
   for (int c = 0; c < n; ++c) if (!cs[c]->geometry_set || !cs[c]->state_set || cs[c]->cfg.time_accuracy != ta) return fail(cs[c], F3D_ERR_ARGUMENT);
-  const int chunk = 1024 / nvp1;
+  const int chunk = 1016 / nvp1;   // norms of a chunk + the error slot fit the 1024-double norm buffers
   int rc = 0;
   for (int it0 = 0; it0 < n_iters; it0 += chunk) {
     const int nit = std::min(chunk, n_iters - it0);
@@ -713,24 +722,39 @@ extern "C" int fest3d_gpu_step_group(Fest3dGpuCtx** cs, int n, int current_iter,
       if (rc) return rc;
       for (int c = 0; c < n; ++c) { cudaSetDevice(cs[c]->device); if ((rc = launch_norms(cs[c], it))) return rc; }
     }
-    // find_resnorm: sum over all blocks (MPI_ALLGATHER + sum, resnorm.f90:201-225), then sqrt / abs
+    // find_resnorm: sum over all blocks (MPI_ALLGATHER + sum, resnorm.f90:201-225), then sqrt / abs.  The blocks of this process
+    // are added on the host; across ranks ONE ncclAllReduce per call carries the sums and, in an extra slot, the error state, so
+    // that every rank leaves with an error as soon as any rank has one (the reference's Fatal_error stops the whole job) instead
+    // of posting the next chunk's sends and receives towards a rank that has already returned.
+    CommShared* sh = nullptr;
     for (int c = 0; c < n; ++c) {
       Fest3dGpuCtx* ctx = cs[c];
       F3D_CUDA(cudaSetDevice(ctx->device));
-      if (ctx->nccl && ctx->n_ranks > 1) {
-        if (g_nccl.AllReduce(ctx->norms_dev, ctx->norms_dev, (size_t)nit * nvp1, kNcclFloat64, kNcclSum, (ncclComm_t)ctx->nccl, ctx->stream) != 0) return fail(ctx, F3D_ERR_CUDA);
-      }
-      if (res_abs_out) F3D_CUDA(cudaMemcpyAsync(ctx->norms_host, ctx->norms_dev, sizeof(double) * nit * nvp1, cudaMemcpyDeviceToHost, ctx->stream));
+      if (ctx->nccl && ctx->n_ranks > 1) sh = (CommShared*)ctx->nccl;
+      if (res_abs_out || sh) F3D_CUDA(cudaMemcpyAsync(ctx->norms_host, ctx->norms_dev, sizeof(double) * nit * nvp1, cudaMemcpyDeviceToHost, ctx->stream));
     }
     int e = 0;
     for (int c = 0; c < n; ++c) e |= check_errors(cs[c]);   // also synchronises the stream
+    double* tot = cs[0]->norms_host;
+    for (int x = 0; x < nit * nvp1; ++x) {
+      double sum = 0.0;
+      for (int c = 0; c < n; ++c) sum = sum + cs[c]->norms_host[x];
+      tot[x] = sum;
+    }
+    if (sh) {
+      Fest3dGpuCtx* ctx = cs[0];
+      const int cnt = nit * nvp1 + 1;
+      tot[cnt - 1] = e ? 1.0 : 0.0;
+      F3D_CUDA(cudaSetDevice(sh->device));
+      F3D_CUDA(cudaMemcpyAsync(ctx->norms_dev, tot, sizeof(double) * cnt, cudaMemcpyHostToDevice, sh->stream));
+      if (g_nccl.AllReduce(ctx->norms_dev, ctx->norms_dev, (size_t)cnt, kNcclFloat64, kNcclSum, sh->comm, sh->stream) != 0) return fail(ctx, F3D_ERR_CUDA);
+      F3D_CUDA(cudaMemcpyAsync(tot, ctx->norms_dev, sizeof(double) * cnt, cudaMemcpyDeviceToHost, sh->stream));
+      F3D_CUDA(cudaStreamSynchronize(sh->stream));
+      if (tot[cnt - 1] != 0.0 && !e) { e = F3D_ERR_PEER; for (int c = 0; c < n; ++c) cs[c]->last_error.flags |= F3D_ERR_PEER; }
+    }
     if (res_abs_out) {
       for (int it = 0; it < nit; ++it)
-        for (int l = 0; l < nvp1; ++l) {
-          double s = 0.0;
-          for (int c = 0; c < n; ++c) s = s + cs[c]->norms_host[it * nvp1 + l];
-          res_abs_out[(size_t)(it0 + it) * nvp1 + l] = (l == 0) ? fabs(s) : sqrt(s);
-        }
+        for (int l = 0; l < nvp1; ++l) res_abs_out[(size_t)(it0 + it) * nvp1 + l] = (l == 0) ? fabs(tot[it * nvp1 + l]) : sqrt(tot[it * nvp1 + l]);
     }
     if (e) return e;
   }

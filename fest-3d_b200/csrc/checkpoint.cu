@@ -8,6 +8,7 @@
 // fest3d_gpu_restart reads it back (header checked against the context) and uploads it: since every other device field is
 // re-derived from qp each iteration (Temp, delta_t, gradients, mu / mu_t / F1, RK stores), a restarted run continues bit for bit.
 #include "ctx.hpp"
+#include <unistd.h>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -67,11 +68,15 @@ static int checkpoint_begin(Ctx* ctx, const char* path, int iter) {
     Checkpoint* ck = new Checkpoint;
     ctx->ckpt = ck;
     ck->n = state_doubles(L);
-    F3D_CUDA(cudaMalloc((void**)&ck->dev, ck->n * sizeof(double)));
-    F3D_CUDA(cudaMallocHost((void**)&ck->host, ck->n * sizeof(double)));
-    F3D_CUDA(cudaStreamCreateWithFlags(&ck->copy_stream, cudaStreamNonBlocking));
-    F3D_CUDA(cudaEventCreateWithFlags(&ck->ev_snap, cudaEventDisableTiming));
-    F3D_CUDA(cudaEventCreateWithFlags(&ck->ev_done, cudaEventDisableTiming));
+    cudaError_t e = cudaMalloc((void**)&ck->dev, ck->n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&ck->host, ck->n * sizeof(double));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ck->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ck->ev_snap, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ck->ev_done, cudaEventDisableTiming);
+    if (e != cudaSuccess) {   // never leave a half-built checkpoint state behind: the next begin starts from scratch
+      checkpoint_free(ctx);
+      F3D_CUDA(e);
+    }
   }
   Checkpoint* ck = ctx->ckpt;
   if ((rc = launch_state_relayout(ctx, ctx->qp, ck->dev, 0))) return rc;   // the snapshot: stream order, later iterations do not touch it
@@ -90,10 +95,15 @@ static int checkpoint_begin(Ctx* ctx, const char* path, int iter) {
   ck->writer = std::thread([ck, h, file, device]() {
     cudaSetDevice(device);
     if (cudaEventSynchronize(ck->ev_done) != cudaSuccess) { ck->write_rc = 1; return; }
-    FILE* f = fopen(file.c_str(), "wb");
+    // write beside the target, flush to the device, then rename: a crash, kill or full disk mid-write leaves the previous good
+    // checkpoint of the same name untouched (the reference purges old time directories only after the new one is complete)
+    const std::string tmp = file + ".tmp";
+    FILE* f = fopen(tmp.c_str(), "wb");
     if (!f) { ck->write_rc = 2; return; }
-    const bool ok = fwrite(&h, sizeof(h), 1, f) == 1 && fwrite(ck->host, sizeof(double), ck->n, f) == ck->n;
-    if (fclose(f) != 0 || !ok) ck->write_rc = 3;
+    bool ok = fwrite(&h, sizeof(h), 1, f) == 1 && fwrite(ck->host, sizeof(double), ck->n, f) == ck->n;
+    ok = ok && fflush(f) == 0 && fsync(fileno(f)) == 0;
+    if (fclose(f) != 0 || !ok) { ck->write_rc = 3; remove(tmp.c_str()); return; }
+    if (rename(tmp.c_str(), file.c_str()) != 0) { ck->write_rc = 4; remove(tmp.c_str()); }
   });
   return 0;
 }

@@ -61,8 +61,8 @@ struct Ctx {
   Fest3dGpuConfig cfg;
   Params P;
   int device = 0;
-  cudaStream_t stream = nullptr, own_stream = nullptr, comm_stream = nullptr;
-  cudaEvent_t ev_pack = nullptr, ev_halo = nullptr;   // compute -> comm stream hand-off and back (overlapped halo swap)
+  cudaStream_t stream = nullptr, own_stream = nullptr;
+  cudaEvent_t ev_pack = nullptr, ev_halo = nullptr;   // halo swap hand-overs: send buffers packed / ghost layers unpacked (api.cu:exchange)
   // device memory
   double* qp = nullptr;       // nv fields (current state)
   double* qp2 = nullptr;      // nv fields (next state of the fused update; swapped with qp)
@@ -96,7 +96,7 @@ struct Ctx {
   double* state_staging = nullptr;   // contiguous copy of qp in the reference layout (set_state / get_state)
   Link link[6];
   struct Checkpoint* ckpt = nullptr;   // asynchronous checkpoint state (checkpoint.cu), created on first use
-  void* nccl = nullptr;          // ncclComm_t
+  void* nccl = nullptr;          // the process-wide communicator record (api.cu:CommShared)
   int n_ranks = 1, rank = 0;
   std::vector<int> block_to_rank;
   // instrumentation

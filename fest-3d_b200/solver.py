@@ -27,7 +27,8 @@ class Fest3dError(RuntimeError):
         self.rc = rc
         self.info = info
         names = {1: "NaN in flux", 2: "NaN in gradient", 4: "NaN in viscosity", 8: "negative density/pressure or NaN after update",
-                 64: "configuration not supported by the device path", 128: "CUDA error", 256: "bad argument"}
+                 16: "non-positive cell volume", 32: "checkpoint I/O", 64: "configuration not supported by the device path", 128: "CUDA error",
+                 256: "bad argument (or an interface face nobody is attached to)", 512: "another rank reported an error"}
         msg = ", ".join(v for k, v in names.items() if rc & k) or "error %d" % rc
         if info is not None and (info.i or info.j or info.k):
             msg += " at block %d cell (%d,%d,%d)" % (info.block_id, info.i, info.j, info.k)
@@ -194,7 +195,7 @@ class Solver:
         devices = devices or [0] * len(blocks)
         self.blocks = [GpuBlock(b, d, device_geometry) for b, d in zip(blocks, devices)]
         for i, a in enumerate(self.blocks):
-            for b in self.blocks[i + 1:]:
+            for b in self.blocks[i:]:      # b is a: a block that is its own (periodic) neighbour
                 ids_a = set(a.blk.bc_id) | set(a.blk.pbc_id)
                 if b.blk.block_id in ids_a:
                     self.L.fest3d_gpu_link_local(a.h, b.h)

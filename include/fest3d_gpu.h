@@ -55,9 +55,10 @@ enum {
   F3D_ERR_NEGATIVE_STATE = 8,/* rho<0, p<0 or NaN after update   update.f90:448-452 */
   F3D_ERR_GEOMETRY = 16,      /* non-positive cell volume  geometry.f90:476-494 (fest3d_gpu_setup_geometry only) */
   F3D_ERR_IO = 32,            /* checkpoint file cannot be written / read (fest3d_gpu_checkpoint_*, fest3d_gpu_restart) */
-  F3D_ERR_UNSUPPORTED = 64,  /* implicit / plusgs / saBC / kkl / lctm2015 / pressure switch: not on this path */
+  F3D_ERR_UNSUPPORTED = 64,  /* implicit / plusgs / saBC / kkl / lctm2015: not on this path */
   F3D_ERR_CUDA = 128,
-  F3D_ERR_ARGUMENT = 256
+  F3D_ERR_ARGUMENT = 256,    /* also: an interface / periodic face that was neither linked locally nor given a communicator */
+  F3D_ERR_PEER = 512         /* another rank reported an error in this call: every rank returns (Fatal_error stops the whole job) */
 };
 
 typedef struct {
@@ -67,7 +68,8 @@ typedef struct {
   int time_stepping;                   /* 0 = 'l' local, 1 = 'g' global                          time.f90:323-326 */
   int limiter[3];                      /* i,j,k limiter_switch                                   vartypes.f90:206-211 */
   int tlimiter[3];                     /* i,j,k turbulent limiter switch */
-  int pb_switch[3];                    /* pressure-based switching; must be 0 */
+  int pb_switch[3];                    /* i,j,k pressure-based switching of muscl / ppm (ignored by the other interpolants)
+                                                                                                 muscl.f90:37-112, ppm.f90:108-170 */
   int accur;                           /* higher-order boundary switch -> c1,c2,c3               bc.f90:48-50 */
   int mu_variation;                    /* 0 constant, 1 sutherland_law                           viscosity.f90:109-138 */
   int bc_id[6];                        /* imin,imax,jmin,jmax,kmin,kmax: <0 physical BC id, >=0 neighbour block */
@@ -160,6 +162,9 @@ int fest3d_gpu_error(Fest3dGpuCtx* ctx, Fest3dGpuError* info);
 
 /* multi-process (one rank per GPU) halo exchange + norm all-reduce over NCCL ------------------------------------ */
 int fest3d_gpu_comm_unique_id(char id_out[128]);                    /* rank 0 calls, host broadcasts the 128 bytes */
+/* Call once per context.  All contexts of a process share ONE communicator (the first call creates it, the others attach to
+ * it), so a rank may own several blocks; blocks of the same rank are linked with fest3d_gpu_link_local.  An error on any rank
+ * makes fest3d_gpu_step_group return on every rank (F3D_ERR_PEER where the error is not local). */
 int fest3d_gpu_comm_init(Fest3dGpuCtx* ctx, int n_ranks, int rank, const char id[128],
                          const int* block_to_rank /* [n_blocks] owner rank of every block */);
 /* link two contexts of the same process so that their shared interface is exchanged device-to-device */

@@ -94,6 +94,9 @@ void oracle_kat_flux(int scheme, int n_var, double gm, double MInf, const double
                      const double* face /*A,nx,ny,nz*/, int mask, double* flux);
 void oracle_kat_states(int interpolant, int n, const double* q /*cells -2..n-3*/, const double* vol,
                        int limiter, double* left, double* right);
+/* compute_residue (scheme.f90:111-141) + the mass imbalance of get_absolute_resnorm (resnorm.f90:190-198) on given F, G, H */
+void oracle_kat_residue(int imx, int jmx, int kmx, int n_var, const double* F, const double* G, const double* H,
+                        double* residue, double* merror);
 
 #ifdef __cplusplus
 }

@@ -187,6 +187,25 @@ void oracle_kat_states(int interpolant, int n, const double* q, const double* vo
   for (int i = 0; i <= c.imx + 1; ++i) { left[i] = B.xl(i, 1, 1, 1); right[i] = B.xr(i, 1, 1, 1); }
 }
 
+// test_residue.f90:19-30: compute_residue (scheme.f90:111-141) on hand-set flux arrays.  F is (1:imx,1:jmx-1,1:kmx-1,nv), G and H
+// alike (Fortran order, i fastest); residue is (1:imx-1,1:jmx-1,1:kmx-1,nv).  Also returns the boundary mass-flux imbalance of
+// get_absolute_resnorm (resnorm.f90:190-198) in *merror.
+void oracle_kat_residue(int imx, int jmx, int kmx, int n_var, const double* F, const double* G, const double* H, double* residue, double* merror) {
+  OracleConfig c;
+  std::memset(&c, 0, sizeof(c));
+  c.imx = imx; c.jmx = jmx; c.kmx = kmx; c.n_var = n_var; c.scheme = ORC_AUSM; c.interpolant = ORC_NONE;
+  c.density_inf = 1.0; c.vel_mag = 1.0; c.pressure_inf = 1.0; c.gm = 1.4;
+  for (int f = 0; f < 6; ++f) { c.bc_id[f] = 0; c.pbc_id[f] = -1; }
+  Block B; B.setup(c);
+  std::memcpy(B.F.d.data(), F, B.F.d.size() * sizeof(double));
+  std::memcpy(B.G.d.data(), G, B.G.d.size() * sizeof(double));
+  std::memcpy(B.H.d.data(), H, B.H.d.size() * sizeof(double));
+  B.compute_residue();
+  std::memcpy(residue, B.residue.d.data(), B.residue.d.size() * sizeof(double));
+  B.absolute_resnorm();
+  if (merror) *merror = B.res_abs_local[0];
+}
+
 // wall_dist.f90:84-131 find_wall_dist: brute-force minimum distance of every node (-2:imx+3, ...) to the wall surface nodes, then the
 // cell value as 0.125 x the sum of its eight nodes in the reference's order.  nodes: (x,y,z) records, i fastest; wall: n x 3.
 void oracle_find_wall_dist(int imx, int jmx, int kmx, const double* nodes, const double* wall, long long n_wall, double* dist_out) {

@@ -93,6 +93,8 @@ def lib(fast=False):
     L.oracle_get_aux.argtypes = [C.c_void_p, C.c_int, C.c_int, dp]
     L.oracle_kat_flux.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, dp, dp, dp, C.c_int, dp]
     L.oracle_kat_states.argtypes = [C.c_int, C.c_int, dp, dp, C.c_int, dp, dp]
+    L.oracle_kat_residue.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, dp]
+    L.oracle_kat_residue.restype = None
     L.oracle_find_wall_dist.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, C.c_longlong, dp]
     L.oracle_find_wall_dist.restype = None
     _libs[fast] = L

@@ -85,3 +85,17 @@ def state_rel_diff(a, b):
         den = max(np.abs(b[v]).max(), 1e-300)
         out.append(float(np.abs(a[v] - b[v]).max() / den))
     return out
+
+
+def boundary_mass_flux_scale(world, blocks):
+    """sum over all blocks and all six block faces of |mass flux| of the fluxes the oracle holds (F, G, H of the last stage):
+    the scale the round-off of Res_abs(0) = |sum of signed boundary mass fluxes| (resnorm.f90:190-198) lives on."""
+    tot = 0.0
+    for b, blk in enumerate(blocks):
+        nv = blk.n_var
+        F = world.aux(b, 20, (nv, blk.kmx - 1, blk.jmx - 1, blk.imx))
+        G = world.aux(b, 21, (nv, blk.kmx - 1, blk.jmx, blk.imx - 1))
+        H = world.aux(b, 22, (nv, blk.kmx, blk.jmx - 1, blk.imx - 1))
+        tot += (np.abs(F[0, :, :, 0]).sum() + np.abs(F[0, :, :, -1]).sum() + np.abs(G[0, :, 0, :]).sum() + np.abs(G[0, :, -1, :]).sum()
+                + np.abs(H[0, 0]).sum() + np.abs(H[0, -1]).sum())
+    return float(tot)

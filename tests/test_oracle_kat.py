@@ -84,12 +84,54 @@ def _unit_block(case_mod, imx, jmx, kmx, **kw):
 
 
 def test_residue_and_mass_kat(oracle, case_mod):
-    # test_residue.f90: residue = dF + dG + dH with F=(1,2,3,4,5)->(2,2,9,0,5.1), G=H=1.  Driven through the
-    # block path: uniform state on unit cube gives zero residual; the association (dF)+(dG)+(dH) is checked on
-    # literal numbers here.
-    F1 = np.array([1.0, 2.0, 3.0, 4.0, 5.0]); F2 = np.array([2.0, 2.0, 9.0, 0.0, 5.1])
-    res = (F2 - F1) + (1.0 - 1.0) + (1.0 - 1.0)
-    assert res[0] == 1.0 and res[1] == 0.0 and res[2] == 6.0 and 0.09 < res[4] < 1.1
+    """test_residue.f90:19-30 through the oracle's compute_residue (scheme.f90:111-141): imx = jmx = kmx = 2, n_var = 5,
+    F(1) = (1,2,3,4,5), F(2) = (2,2,9,0,5.1), G = H = 1; the reference accepts residue(1) == 1, (2) == 0, (3) == 6,
+    0.09 < (5) < 1.1.  The same arrays give the boundary mass imbalance of resnorm.f90:190-198: F(1,1) - F(2,1) + 1 - 1 + 1 - 1."""
+    import ctypes as C
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    F = np.array([[1.0, 2.0], [2.0, 2.0], [3.0, 9.0], [4.0, 0.0], [5.0, 5.1]])     # [l][i]
+    G = np.ones((5, 2)); H = np.ones((5, 2))
+    res = np.full(5, np.nan); merr = np.full(1, np.nan)
+    oracle.lib().oracle_kat_residue(2, 2, 2, 5, dp(F), dp(G), dp(H), dp(res), dp(merr))
+    assert res[0] == 1.0 and res[1] == 0.0 and res[2] == 6.0 and res[3] == -4.0 and 0.09 < res[4] < 1.1
+    assert merr[0] == -1.0
+    # the association (dF) + (dG) + (dH): a case where it differs from any other order in the last bit
+    F = np.array([[0.1, 0.7]] * 5); G = np.array([[1e16, 1e16 + 2.0]] * 5); H = np.array([[3.0, 3.5]] * 5)
+    oracle.lib().oracle_kat_residue(2, 2, 2, 5, dp(F), dp(G), dp(H), dp(res), dp(merr))
+    want = ((0.7 - 0.1) + ((1e16 + 2.0) - 1e16)) + (3.5 - 3.0)
+    assert np.all(res == want)
+
+
+def test_oracle_interface_maps_are_orientation_consistent(oracle, case_mod):
+    """Unpack maps with reversed ranges (PjDir = PkDir = -1) and swapped transverse axes (dir_switch = 1), interface1.f90:144-168:
+    a two-block duct whose second block is stored through rotated (j, k) axes must give the residual of the plainly stored duct,
+    cell for cell, to round-off (the face sums run in another order).  Also pins tests/block_ops.py, which the GPU tests use."""
+    import importlib
+    import block_ops
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    mk = lambda: syn.make_duct_blocks(None, n3=(8, 6, 5), nb=(2, 1, 1), turbulence="none", mu_ref=0.0)   # inviscid: the viscous wall rules carry
+    # orientation-dependent reference defects (mis-indexed ghost-gradient faces, unfilled j edges) that a rotation legitimately changes
+    plain = mk()
+    w0 = oracle.OracleWorld(plain)
+    err, r0 = w0.residual(1)
+    assert err == 0
+    for op in ("rot180", "rot90"):
+        blocks = block_ops.two_block_duct_with_rotated_neighbour(mk(), op)
+        w = oracle.OracleWorld(blocks)
+        err, r = w.residual(1)
+        assert err == 0
+        back = block_ops.unrotate_cells(r[1], op)
+        sc = np.abs(r0[1]).max(axis=(1, 2, 3), keepdims=True)
+        assert np.abs(r[0] - r0[0]).max() <= 1e-11 * np.abs(r0[0]).max(), op
+        assert (np.abs(back - r0[1]) / sc).max() < 1e-11, op
+        # the permutation matters: with the identity maps the ghost layers of both blocks are filled wrongly
+        bad = block_ops.two_block_duct_with_rotated_neighbour(mk(), op)
+        for b in bad:
+            b.default_maps(); b.dir_switch = [0] * 6
+        if op == "rot90":
+            continue   # identity maps do not even have the right extents there
+        err, rb = oracle.OracleWorld(bad).residual(1)
+        assert np.abs(rb[0] - r0[0]).max() > 1e-6 * np.abs(r0[0]).max()
 
 
 def test_gradient_kat(oracle, case_mod):
