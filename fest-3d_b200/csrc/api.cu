@@ -155,7 +155,6 @@ static int create_impl(Fest3dGpuCtx* ctx, const Fest3dGpuConfig* cfg, int device
   if (cfg->time_accuracy != F3D_T_NONE) F3D_CUDA(dalloc(&ctx->ustore, nv));
   if (cfg->time_accuracy == F3D_T_RK2 || cfg->time_accuracy == F3D_T_RK4) F3D_CUDA(dalloc(&ctx->rstore, nv));
   ctx->n_mu = sst ? 3 : (sa ? 2 : 1);
-  if (P.viscous) { F3D_CUDA(dalloc(&ctx->grad, 3 * L.ng)); F3D_CUDA(dalloc(&ctx->mu, ctx->n_mu + 3)); }
   // staging for the AoS records: the largest face array
   const size_t rec_max = (size_t)4 * (L.imx + 6) * (L.jmx + 6) * (L.kmx + 6) * sizeof(double);
   F3D_CUDA(cudaMalloc((void**)&ctx->staging, rec_max));
@@ -183,12 +182,8 @@ static int create_impl(Fest3dGpuCtx* ctx, const Fest3dGpuConfig* cfg, int device
     };
     bool ok = encode(&ctx->tm_q[0], ctx->qp, nv, kG3TY + 4, nv) && encode(&ctx->tm_q[1], ctx->qp2, nv, kG3TY + 4, nv);
     ctx->tm_q_ptr[0] = ctx->qp; ctx->tm_q_ptr[1] = ctx->qp2;
-    if (P.viscous) {
-      const int ngf = 3 * L.ng, naux = ctx->n_mu + 3;
-      ok = ok && encode(&ctx->tm_grad, ctx->grad, ngf, kG3TY + 2, (ngf + 1) & ~1) && encode(&ctx->tm_aux, ctx->mu, naux, kG3TY + 2, (naux + 1) & ~1);
-      ok = ok && encode(&ctx->tm_qg[0], ctx->qp, nv, 6, (nv + 1) & ~1) && encode(&ctx->tm_qg[1], ctx->qp2, nv, 6, (nv + 1) & ~1) &&
-           encode(&ctx->tm_temp, ctx->temp, 1, 6, 1);
-    }
+    ok = ok && encode(&ctx->tm_temp, ctx->temp, 1, kG3TY + 4, 1);
+    ok = ok && encode(&ctx->tm_geo, ctx->geom, G_NFIELDS, kG3TY + 2, 4);   // volume + centre x, y, z = geometry fields 0..3
     if (!ok) { fprintf(stderr, "fest3d_gpu: cuTensorMapEncodeTiled failed\n"); return fail(ctx, F3D_ERR_CUDA); }
     ctx->tmaps_ok = true;
   }
@@ -278,18 +273,6 @@ static int copy_cells(Fest3dGpuCtx* ctx, double* dev_field, double* host, int nf
   return 0;
 }
 
-// mu = mu_ref everywhere (viscosity.f90:527) and the cell-centre fields behind the viscosity fields: one "aux" array for the
-// tensor-map staging of the sweep
-static int init_aux_fields(Fest3dGpuCtx* ctx) {
-  const long long fs = ctx->P.L.fs;
-  std::vector<double> mu0((size_t)fs, ctx->cfg.mu_ref);
-  F3D_CUDA(cudaMemcpyAsync(ctx->mu, mu0.data(), fs * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  F3D_CUDA(cudaMemcpyAsync(ctx->mu + (long long)ctx->n_mu * fs, ctx->geom + (long long)G_CX * fs, 3 * fs * sizeof(double), cudaMemcpyDeviceToDevice,
-                           ctx->stream));
-  F3D_CUDA(cudaStreamSynchronize(ctx->stream));
-  return 0;
-}
-
 extern "C" int fest3d_gpu_set_geometry(Fest3dGpuCtx* ctx, const double* cells, const double* Ifaces, const double* Jfaces,
                                        const double* Kfaces, const double* dist) {
   if (!ctx || !cells || !Ifaces || !Jfaces || !Kfaces) return fail(ctx, F3D_ERR_ARGUMENT);
@@ -306,10 +289,9 @@ extern "C" int fest3d_gpu_set_geometry(Fest3dGpuCtx* ctx, const double* cells, c
     if ((rc = copy_cells(ctx, ctx->geom + (long long)G_DIST * fs, const_cast<double*>(dist), 1, true, -2, L.imx + 5, L.jmx + 5, L.kmx + 5))) return rc;
   }
   if (ctx->P.viscous) {
-    // mu = mu_ref everywhere (viscosity.f90:527); face records for the ghost-gradient rule.  The reference passes
-    // Jfaces / Kfaces to a dummy declared with the Ifaces shape (gradients.f90:549-612): element (i,j,k) is then read at
-    // record offset (i+2) + (imx+6)*((j+2) + (jmx+5)*(k+2)) of the actual array.  Reproduced here on the host, once.
-    if ((rc = init_aux_fields(ctx))) return rc;
+    // face records for the ghost-gradient rule.  The reference passes Jfaces / Kfaces to a dummy declared with the Ifaces
+    // shape (gradients.f90:549-612): element (i,j,k) is then read at record offset (i+2) + (imx+6)*((j+2) + (jmx+5)*(k+2)) of
+    // the actual array.  Reproduced here on the host, once.
     const int mx[3] = {L.imx, L.jmx, L.kmx};
     const double* arrs[3] = {Ifaces, Jfaces, Kfaces};
     std::vector<double> rec;
@@ -394,8 +376,22 @@ extern "C" int fest3d_gpu_get_aux(Fest3dGpuCtx* ctx, int which, double* out) {
   F3D_CUDA(cudaSetDevice(ctx->device));
   const Layout& L = ctx->P.L;
   int rc = F3D_ERR_ARGUMENT;
+  const bool view = (which >= 1 && which <= 3) || (which >= 30 && which <= 32);
+  if (view && ctx->P.viscous) {
+    // mu / mu_t / F1 / gradients never reach HBM on the hot path (the fused sweep keeps them in shared memory): for these views the
+    // stand-alone kernels of grad.cu recompute them from the current qp / Temp (ghost cells as the last stage left them)
+    const size_t fb = (size_t)L.fs * sizeof(double);
+    if (!ctx->grad) {
+      F3D_CUDA(cudaMalloc((void**)&ctx->grad, (size_t)3 * L.ng * fb));
+      F3D_CUDA(cudaMalloc((void**)&ctx->mu, (size_t)ctx->n_mu * fb));
+    }
+    F3D_CUDA(cudaMemsetAsync(ctx->grad, 0, (size_t)3 * L.ng * fb, ctx->stream));
+    F3D_CUDA(cudaMemsetAsync(ctx->mu, 0, (size_t)ctx->n_mu * fb, ctx->stream));
+    if ((rc = launch_gradients(ctx))) return fail(ctx, rc);
+    rc = F3D_ERR_ARGUMENT;
+  }
   if (which == 0) rc = copy_cells(ctx, ctx->dt, out, 1, false, 1, L.imx - 1, L.jmx - 1, L.kmx - 1);
-  else if (which >= 1 && which <= 3 && ctx->mu) rc = copy_cells(ctx, ctx->mu + (long long)(which - 1) * L.fs, out, 1, false, -2, L.imx + 5, L.jmx + 5, L.kmx + 5);
+  else if (which >= 1 && which <= 3 && ctx->mu && which <= ctx->n_mu) rc = copy_cells(ctx, ctx->mu + (long long)(which - 1) * L.fs, out, 1, false, -2, L.imx + 5, L.jmx + 5, L.kmx + 5);
   else if (which == 4) rc = copy_cells(ctx, ctx->temp, out, 1, false, -2, L.imx + 5, L.jmx + 5, L.kmx + 5);
   else if (which >= 30 && which <= 32 && ctx->grad) {
     // gradqp_d(0:imx,0:jmx,0:kmx,1:n_grad): component c of direction d lives in field 3*c+d
@@ -619,7 +615,6 @@ int stage(Fest3dGpuCtx** cs, int n, bool update, double TF, double SF, int use_s
     Fest3dGpuCtx* ctx = cs[c];
     F3D_CUDA(cudaSetDevice(ctx->device));
     if ((rc = launch_bc(ctx))) return rc;
-    if (ctx->P.viscous && (rc = launch_gradients(ctx, 0))) return rc;
     if (!update) {
       if ((rc = launch_residual(ctx, MODE_RESIDUE_ONLY, 1.0, 1.0, 0, 1, 0))) return rc;
       continue;
@@ -777,7 +772,6 @@ extern "C" int fest3d_gpu_setup_geometry(Fest3dGpuCtx* ctx, const double* grid_x
   if (dist) {
     if ((rc = copy_cells(ctx, ctx->geom + (long long)G_DIST * L.fs, const_cast<double*>(dist), 1, true, -2, L.imx + 5, L.jmx + 5, L.kmx + 5))) return rc;
   }
-  if (ctx->P.viscous && (rc = init_aux_fields(ctx))) return rc;
   if ((rc = check_errors(ctx))) return rc;   // non-positive volume -> F3D_ERR_GEOMETRY with the cell (geometry.f90:476-494)
   ctx->geometry_set = true;
   return 0;

@@ -13,7 +13,7 @@
 
 namespace f3d {
 
-constexpr int kG3TX = 32, kG3TY = 4;   // tile of the generation-3 sweep (sweep3_kernel*.cuh), also the box of its tensor maps
+constexpr int kG3TX = 32, kG3TY = 4;   // tile of the fused sweep (fused_kernel.cuh), also the box of its tensor maps
 
 struct Layout {
   int imx, jmx, kmx, nv, ng;        // ng = number of gradient components (4, 5 with sa, 6 with sst)
@@ -72,12 +72,14 @@ struct Ctx {
   double* temp = nullptr;     // 1 field
   double* dt = nullptr;       // 1 field
   double* geom = nullptr;     // G_NFIELDS fields
+  // Gradients and viscosities live only inside the fused sweep (shared memory).  These two arrays exist for the debugging /
+  // parity views of fest3d_gpu_get_aux alone and are allocated on its first call (grad.cu fills them then):
   double* grad = nullptr;     // 3*ng fields: component c, direction d -> field 3*c+d
-  double* mu = nullptr;       // "aux" fields: mu [, mu_t [, F1]] as the model has them, then a copy of the cell centre x,y,z
+  double* mu = nullptr;       // mu [, mu_t [, F1]] as the model has them
   int n_mu = 0;               // 1 laminar, 2 sa, 3 sst
-  // 4-D tensor maps [field][k][j][i] of the arrays the sweep stages (sweep3_kernel.cuh)
-  CUtensorMap tm_q[2], tm_grad, tm_aux;
-  CUtensorMap tm_qg[2], tm_temp;   // boxes of the gradient kernel (grad.cu:k_gradients_tma): 36 x 6 x 1 x fields
+  // 4-D tensor maps [field][k][j][i] of the arrays the sweep stages (fused_kernel.cuh): q (36 x 8 cells x nv fields), Temp
+  // (36 x 8 x 1), geometry fields volume + centre (36 x 6 x 4)
+  CUtensorMap tm_q[2], tm_temp, tm_geo;
   double* tm_q_ptr[2] = {nullptr, nullptr};
   bool tmaps_ok = false;
   double* gbc = nullptr;      // per-face (A,nx,ny,nz) records the ghost-gradient rule reads (mis-indexed for J/K faces)
@@ -124,7 +126,7 @@ struct Ctx {
 // kernel launchers (each returns a CUDA error code through the context)
 int launch_temp(Ctx* ctx);
 int launch_bc(Ctx* ctx);
-int launch_gradients(Ctx* ctx, int mode = 0);   // mode 1: cells with an all-interior stencil, 2: the others, 0: all
+int launch_gradients(Ctx* ctx);   // debugging views only (fest3d_gpu_get_aux): the sweep computes its own gradients in shared memory
 int launch_residual(Ctx* ctx, int mode, double TF, double SF, int use_store_sum, int first_stage, int last_stage);
 int launch_blend(Ctx* ctx, double a, double b);
 int launch_copy_fields(Ctx* ctx, double* dst, const double* src, int nfields);

@@ -1,6 +1,6 @@
 // Launch side of the fused residual / time-step / update sweep: kernel arguments, CUDA-event timing of the sweep launch,
-// per-CTA norm partials -> Res_abs (resnorm.f90:171-199).  The kernel itself lives in sweep3_kernel.cuh (instantiated in
-// sweep3.cu / sweep3_rare.cu).
+// per-CTA norm partials -> Res_abs (resnorm.f90:171-199).  The kernel itself lives in fused_kernel.cuh (instantiated in
+// fused.cu / fused_rare.cu).
 #include "sweep_common.cuh"
 #include <cstdlib>
 #include <cstring>
@@ -24,10 +24,10 @@ __global__ void k_norm_final(const double* __restrict__ red, int n_cta, int nvp1
   }
 }
 
-int sweep3_grid_ctas(const Layout& L);
-int launch_sweep3(Ctx* ctx, KArgs& a);
+int fused_grid_ctas(const Layout& L);
+int launch_fused(Ctx* ctx, KArgs& a);
 
-int residual_grid_ctas(const Layout& L) { return sweep3_grid_ctas(L); }   // one norm partial per CTA of the sweep
+int residual_grid_ctas(const Layout& L) { return fused_grid_ctas(L); }   // one norm partial per CTA of the sweep
 
 int launch_residual(Ctx* ctx, int mode, double TF, double SF, int use_store_sum, int first_stage, int want_norms) {
   KArgs a{};
@@ -39,8 +39,8 @@ int launch_residual(Ctx* ctx, int mode, double TF, double SF, int use_store_sum,
   a.rstore = (mode == MODE_UPDATE && have_store) ? ctx->rstore : nullptr;
   a.dt = ctx->dt;
   a.geom = ctx->geom;
-  a.grad = ctx->grad;
-  a.mu = ctx->mu;
+  a.gbc = ctx->gbc;
+  for (int f = 0; f < 6; ++f) a.gbc_off[f] = ctx->gbc_off[f];
   a.red = ctx->red;
   a.err = ctx->err_dev;
   a.mode = mode; a.first_stage = first_stage; a.want_norms = want_norms;
@@ -56,7 +56,7 @@ int launch_residual(Ctx* ctx, int mode, double TF, double SF, int use_store_sum,
     e0 = ctx->ev_pool[ctx->ev_used].first; e1 = ctx->ev_pool[ctx->ev_used].second; ctx->ev_used++;
     cudaEventRecord(e0, ctx->stream);
   }
-  const int rc = launch_sweep3(ctx, a);
+  const int rc = launch_fused(ctx, a);
   if (ctx->timing) cudaEventRecord(e1, ctx->stream);
   if (rc) return rc;
   F3D_CUDA(cudaGetLastError());

@@ -42,8 +42,8 @@ struct KArgs {
   double* __restrict__ rstore;        // nv fields or nullptr
   double* __restrict__ dt;            // 1 field
   const double* __restrict__ geom;
-  const double* __restrict__ grad;
-  const double* __restrict__ mu;      // mu, mu_t, F1
+  const double* __restrict__ gbc;     // face records (A, nx, ny, nz) of the ghost-gradient rule, six faces back to back
+  long long gbc_off[6];               // offset of every face's records inside gbc
   double* __restrict__ red;           // per-CTA partials [(nv+1) * n_cta]
   int* err;
   int mode, first_stage, want_norms, have_store, use_store_sum, kchunk;
