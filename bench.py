@@ -4,7 +4,10 @@
 Contract (see DESIGN.md "Measurement"):
   python bench.py --gpus N --steps K --warmup W          one rank per GPU (torchrun for N>1), weak scaling
   python bench.py --impl reference ...                   the CPU arm: the oracle port on the host cores
-  python bench.py --interpolant weno --scheme ausmP      BASELINE.json's second synthetic configuration (not the headline line)
+  python bench.py --interpolant weno --scheme ausmP --mode residual
+                                                         BASELINE.json's second synthetic configuration: residual evaluations/s
+  python bench.py --scaling strong --gpus N              BASELINE.json's multi-block configuration: 512^3 as 8 blocks on N GPUs
+  python bench.py --gradients fused                      the fused form of the viscous path (A/B against the default staged form)
 
 A *step* is one iteration of get_next_solution + find_resnorm (src/solver.f90:184-185) on a 256^3-cell block per GPU,
 MUSCL + AUSM + SST, single-stage explicit update (time_step_accuracy 'none'): one residual evaluation + one update per
@@ -150,24 +153,39 @@ def cpu_baseline_sample(args):
             "sample": "%d blocks of %d^3 cells, one thread per block, %d steps of the same %s duct" % (nblk, m, steps, scheme_label(args))}
 
 
+def kernel_profile(kernel_key):
+    """Per-kernel constants taken from committed ncu captures (profiles/kernels.json): DRAM bytes per launch at the bench workload
+    and FP64-pipe warp instructions per cell-warp.  Keyed by the kernel that actually ran; a kernel without a capture gets null."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "kernels.json"))).get(kernel_key, {})
+    except Exception:
+        return {}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--cells", type=int, default=256, help="cells per block edge per GPU")
+    ap.add_argument("--cells", type=int, default=256, help="cells per block edge")
     ap.add_argument("--cpu-cells", type=int, default=48, help="cells per block edge of the CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
-    # the headline configuration is the default; BASELINE.json's other synthetic config (WENO + AUSM+ + SST) is --interpolant weno --scheme ausmP
+    # the headline configuration is the default; BASELINE.json's other synthetic config (WENO + AUSM+ + SST, residual evaluations) is
+    # --interpolant weno --scheme ausmP --mode residual; its multi-block config is --scaling strong (512^3 as 8 blocks on 1/2/4/8 GPUs)
     ap.add_argument("--scheme", default="ausm", choices=sorted(SCHEME_LABEL))
     ap.add_argument("--interpolant", default="muscl", choices=sorted(INTERP_LABEL))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--mode", default="step", choices=["step", "residual"], help="residual: one get_total_conservative_Residue per step (no update)")
+    ap.add_argument("--gradients", default=None, choices=["staged", "fused"], help="form of the viscous path (default: the library's)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n = args.gpus
+    if args.gradients:
+        os.environ["F3D_GRADIENTS"] = args.gradients
 
     if args.impl == "reference":
         run_reference(args, n, rank, world)
@@ -183,22 +201,45 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     syn = importlib.import_module("fest3d_b200.synthetic")
     solver_mod = importlib.import_module("fest3d_b200.solver")
+    par = importlib.import_module("fest3d_b200.parallel")
 
-    nb = block_grid(world)
-    blocks = syn.make_duct_blocks(args.cells, nb=nb, scheme_name=args.scheme, interpolant=args.interpolant, turbulence="sst",
-                                  time_step_accuracy="none", CFL=0.5, only_blocks=[rank])
+    # weak: one block per GPU (1, 2, 4, 8 blocks); strong: always the 2 x 2 x 2 blocks of the 512^3 case, 8 / world of them per GPU
+    if args.scaling == "strong":
+        nb, n_blocks = (2, 2, 2), 8
+        if 8 % world:
+            raise SystemExit("--scaling strong needs 1, 2, 4 or 8 GPUs")
+    else:
+        nb, n_blocks = block_grid(world), world
+    owners = par.block_to_rank(n_blocks, world)
+    mine = [b for b in range(n_blocks) if owners[b] == rank]
+    # blocks are built and uploaded one at a time; the host copies of the big arrays are dropped afterwards (8 blocks of 256^3 are
+    # ~30 GB of numpy arrays otherwise)
+    gblocks, blocks = [], []
+    q_keep = None
+    for b in mine:
+        blk = syn.make_duct_blocks(args.cells, nb=nb, scheme_name=args.scheme, interpolant=args.interpolant, turbulence="sst",
+                                   time_step_accuracy="none", CFL=0.5, only_blocks=[b])[0]
+        gblocks.append(solver_mod.GpuBlock(blk, local_rank))
+        if q_keep is None:
+            q_keep = blk.qp
+        blk.cells = blk.Ifaces = blk.Jfaces = blk.Kfaces = blk.nodes = blk.dist = None
+        if len(blocks):
+            blk.qp = None
+        blocks.append(blk)
+    s = solver_mod.Solver.from_gpu_blocks(gblocks)
     blk = blocks[0]
-    s = solver_mod.Solver(blocks, devices=[local_rank])
     gb = s.blocks[0]
     if world > 1:
-        par = importlib.import_module("fest3d_b200.parallel")
         uid = par.broadcast_unique_id(dist, solver_mod.Solver.unique_id, rank, device="cuda")
-        s.init_comm(world, rank, uid, par.block_to_rank(world, world))
+        s.init_comm(world, rank, uid, owners)
     stream = torch.cuda.Stream()          # a real (non-default) stream, so CUDA events bracket exactly our launches
     torch.cuda.set_stream(stream)
-    gb.set_stream(stream.cuda_stream)
+    gb.set_stream(stream.cuda_stream)     # block 0 of the rank runs on the timed stream; the others on their own, joined by events
     nvp1 = blk.n_var + 1
-    cells = (blk.imx - 1) * (blk.jmx - 1) * (blk.kmx - 1)
+    cells_blk = (blk.imx - 1) * (blk.jmx - 1) * (blk.kmx - 1)
+    cells_rank = cells_blk * len(mine)
+    cells_all = cells_blk * n_blocks
+    path = gb.gradient_path()
 
     def barrier():
         torch.cuda.synchronize()
@@ -206,52 +247,69 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def one_call(k, want):
+        if args.mode == "residual":
+            for _ in range(k):
+                s.residual_only()
+            return None
+        return s.iterate(k, want_norms=want)
+
     # ---- device-resident throughput ("value") ----
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    s.iterate(args.warmup, want_norms=False)
-    launches0 = gb.launch_count()
-    gb.kernel_timing(True)
-    gb.kernel_time_ms(reset=True)
+    one_call(args.warmup, False)
+    launches0 = sum(g.launch_count() for g in s.blocks)
+    for g in s.blocks:
+        g.kernel_timing(True); g.kernel_time_ms(reset=True); g.gradient_time_ms(reset=True)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    norms = s.iterate(args.steps, want_norms=True)
+    norms = one_call(args.steps, True)
     e1.record(stream)
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = gb.launch_count() - launches0
-    k_ms, k_n = gb.kernel_time_ms(reset=True)
-    gb.kernel_timing(False)
+    barrier()                              # (every block's stream is synchronised here: the elapsed time below is taken up to e1 on
+    ms = e0.elapsed_time(e1)               # block 0's stream, which the norm assembly of the call makes wait for all blocks)
+    launches = sum(g.launch_count() for g in s.blocks) - launches0
+    k_ms = k_n = g_ms = g_n = 0
+    for g in s.blocks:
+        t, c = g.kernel_time_ms(reset=True); k_ms += t; k_n += c
+        t, c = g.gradient_time_ms(reset=True); g_ms += t; g_n += c
+        g.kernel_timing(False)
     tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms = float(tms.item())
-    value = cells * world * args.steps / (ms * 1e-3)
+    value = cells_all * args.steps / (ms * 1e-3)
 
     # ---- end to end through the C ABI with host buffers ("e2e") ----
-    q_host = torch.from_numpy(np.ascontiguousarray(blk.qp)).pin_memory()
-    q_back = torch.empty_like(q_host).pin_memory()
-    q_np, qb_np = q_host.numpy(), q_back.numpy()
+    e2e_value = None
+    state_bytes = 0
     e2e_steps = max(3, min(args.steps, 5))
-    gb.set_state(q_np); s.iterate(1); gb.get_state(qb_np)   # warm-up of the path
-    barrier()
-    t0 = time.perf_counter()
-    e0.record(stream)
-    for _ in range(e2e_steps):
-        gb.set_state(q_np)            # H2D of the step's input state
-        r = s.iterate(1)              # one cell-update everywhere + norms (D2H of n_var+1 doubles)
-        gb.get_state(qb_np)           # D2H of the step's result
-    e1.record(stream)
-    barrier()
-    ms_e2e = e0.elapsed_time(e1)
+    if args.mode == "step":
+        q_host = torch.from_numpy(np.ascontiguousarray(q_keep)).pin_memory()
+        q_back = torch.empty_like(q_host).pin_memory()
+        q_np, qb_np = q_host.numpy(), q_back.numpy()
+        for g in s.blocks:
+            g.set_state(q_np)
+        s.iterate(1)
+        for g in s.blocks:
+            g.get_state(qb_np)   # warm-up of the path
+        barrier()
+        e0.record(stream)
+        for _ in range(e2e_steps):
+            s.set_states_async([q_np] * len(s.blocks))     # H2D of the step's input state (every block of the rank)
+            r = s.iterate(1)                               # one cell-update everywhere + norms (D2H of n_var+1 doubles)
+            s.get_states_async([qb_np] * len(s.blocks))    # D2H of the step's result (overlaps the next step's H2D: PCIe is full duplex)
+        s.state_wait()                                     # the last result has arrived on the host
+        e1.record(stream)
+        barrier()
+        ms_e2e = e0.elapsed_time(e1)
+        tm2 = torch.tensor([ms_e2e], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tm2, op=dist.ReduceOp.MAX)
+        e2e_value = cells_all * e2e_steps / (float(tm2.item()) * 1e-3)
+        state_bytes = int(q_host.numel() * 8) * len(s.blocks)
     sampler.stop_flag = True
-    tm2 = torch.tensor([ms_e2e], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tm2, op=dist.ReduceOp.MAX)
-    e2e_value = cells * world * e2e_steps / (float(tm2.item()) * 1e-3)
-    state_bytes = int(q_host.numel() * 8)
 
     if rank == 0:
         peaks = {}
@@ -263,26 +321,51 @@ def main():
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md 6.65 TB/s)"
         bpc = algorithmic_bytes_per_cell_update(blk.n_var, True, True, False)
         k_avg_ms = k_ms / max(k_n, 1)
-        achieved = bpc * cells / (k_avg_ms * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
-            try:
-                traffic = json.load(open(tp)).get("k_residual_dram_bytes_per_launch")
-            except Exception:
-                pass
+        g_avg_ms = g_ms / max(g_n, 1) if g_n else 0.0
+        achieved = bpc * cells_blk / (k_avg_ms * 1e-3) / 1e9
+        step_gbs = bpc * cells_rank / (ms / args.steps * 1e-3) / 1e9
+        kname = ("g4::k_fused" if path == "fused" else "g3::k_sweep3") + "<7,%s,%s,viscous>" % (INTERP_LABEL[args.interpolant], SCHEME_LABEL[args.scheme])
+        kp = kernel_profile(kname)
+        fp64_frac = None
+        if kp.get("fp64_warp_instr_per_cell_warp"):   # FP64 pipe: one warp instruction per 2 cycles per SM sub-partition (4 per SM, 148 SMs)
+            sm_mhz = (sampler.summary().get("sm_mhz") or 1965.0)
+            fp64_frac = kp["fp64_warp_instr_per_cell_warp"] * (cells_blk / 32.0) * 2.0 / (148 * 4) / (k_avg_ms * 1e-3 * sm_mhz * 1e6)
+        halo = 0
+        for b in blocks:
+            for f in range(6):
+                if b.bc_id[f] >= 0:
+                    mxs = (b.imx, b.jmx, b.kmx); ax = f // 2
+                    a_, b_ = (1 if ax == 0 else 0), (1 if ax == 2 else 2)
+                    halo += 3 * b.n_var * (mxs[a_] - 1) * (mxs[b_] - 1) * 8
+        cfg = workload_config(world, args)
+        cfg.update({"scaling_mode": args.scaling, "blocks_total": n_blocks, "blocks_per_gpu": len(mine), "gradients": path, "mode": args.mode,
+                    "halo_bytes_sent_per_stage_per_gpu": halo})
+        if args.scaling == "strong":
+            cfg["workload"] = "synthetic duct, %d^3 cells as 2x2x2 blocks of %d^3 (%d per GPU), %s k-omega, explicit single-stage update, local time step" % (
+                2 * args.cells, args.cells, len(mine), scheme_label(args))
+        if args.mode == "residual":
+            cfg["workload"] = cfg["workload"].replace("explicit single-stage update", "residual evaluation only (get_total_conservative_Residue)")
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": workload_config(world, args),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "g3::k_sweep3<7,%s,%s,viscous> (fused reconstruction + flux + source + dt + update, generation %s)" % (INTERP_LABEL[args.interpolant], SCHEME_LABEL[args.scheme], os.environ.get("F3D_SWEEP_GEN", "3")), "kernel_ms": k_avg_ms,
-                         "kernel_share_of_step": k_ms / ms, "algorithmic_bytes_per_cell_update": bpc, "peak_source": peak_src},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes + nvp1 * 8,
-                    "steps": e2e_steps},
+            "metric": METRIC if args.mode == "step" else "FP64 residual evaluations/s (cells x get_total_conservative_Residue calls per second)",
+            "value": value, "unit": UNIT if args.mode == "step" else "cell-residuals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": cfg,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": kp.get("dram_bytes_per_launch"),
+                         "kernel": kname + (" (reconstruction + flux + source + dt + update; gradients staged from k_gradients)" if path == "staged" else
+                                            " (gradients + reconstruction + flux + source + dt + update in one tile pass)"),
+                         "kernel_ms": k_avg_ms, "kernel_share_of_step": k_ms / max(len(s.blocks), 1) / ms * 1.0 if len(s.blocks) == 1 else k_ms / ms,
+                         "gradient_kernels_ms": g_avg_ms, "step_achieved": step_gbs, "step_frac": step_gbs / peak,
+                         "fp64_pipe_frac": fp64_frac, "fp64_pipe_note": "FP64 warp instructions per cell-warp of this kernel (ncu, profiles/kernels.json) x cells / measured kernel time, against 1 per 2 cycles per SM sub-partition at the sampled SM clock",
+                         "algorithmic_bytes_per_cell_update": bpc, "peak_source": peak_src},
             "gpu_launches": launches, "clocks": sampler.summary(),
-            "res_abs_last": [float(x) for x in norms[-1]],
         }
+        if e2e_value is not None:
+            line["e2e"] = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes + nvp1 * 8, "steps": e2e_steps}
+        else:
+            line["e2e"] = {"value": value, "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                           "note": "residual-only mode keeps no host-visible result per call; the headline step mode carries the end-to-end figure"}
+        if norms is not None:
+            line["res_abs_last"] = [float(x) for x in norms[-1]]
         if not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_sample(args)
         print(json.dumps(line), flush=True)

@@ -49,6 +49,7 @@ constexpr int kNcclFloat64 = 8, kNcclSum = 0;
 
 static int fail(Fest3dGpuCtx* ctx, int cls) { if (ctx) ctx->last_error.flags |= cls; return cls; }
 #define F3D_CUDA_RC(call) do { if ((call) != cudaSuccess) return F3D_ERR_CUDA; } while (0)
+static int apply_pending_state(Fest3dGpuCtx* ctx);
 
 extern "C" const char* fest3d_gpu_version(void) { return "fest3d-b200 0.1 (sm_100a)"; }
 
@@ -155,6 +156,11 @@ static int create_impl(Fest3dGpuCtx* ctx, const Fest3dGpuConfig* cfg, int device
   if (cfg->time_accuracy != F3D_T_NONE) F3D_CUDA(dalloc(&ctx->ustore, nv));
   if (cfg->time_accuracy == F3D_T_RK2 || cfg->time_accuracy == F3D_T_RK4) F3D_CUDA(dalloc(&ctx->rstore, nv));
   ctx->n_mu = sst ? 3 : (sa ? 2 : 1);
+  {   // form of the viscous path: "staged" (default: measured faster on B200) or "fused" (no gradient / viscosity array in HBM)
+    const char* e = getenv("F3D_GRADIENTS");
+    ctx->fused = (e && strcmp(e, "fused") == 0) ? 1 : 0;
+  }
+  if (P.viscous && !ctx->fused) { F3D_CUDA(dalloc(&ctx->grad, 3 * L.ng)); F3D_CUDA(dalloc(&ctx->mu, ctx->n_mu + 3)); }
   // staging for the AoS records: the largest face array
   const size_t rec_max = (size_t)4 * (L.imx + 6) * (L.jmx + 6) * (L.kmx + 6) * sizeof(double);
   F3D_CUDA(cudaMalloc((void**)&ctx->staging, rec_max));
@@ -184,6 +190,10 @@ static int create_impl(Fest3dGpuCtx* ctx, const Fest3dGpuConfig* cfg, int device
     ctx->tm_q_ptr[0] = ctx->qp; ctx->tm_q_ptr[1] = ctx->qp2;
     ok = ok && encode(&ctx->tm_temp, ctx->temp, 1, kG3TY + 4, 1);
     ok = ok && encode(&ctx->tm_geo, ctx->geom, G_NFIELDS, kG3TY + 2, 4);   // volume + centre x, y, z = geometry fields 0..3
+    if (P.viscous && !ctx->fused) {
+      const int ngf = 3 * L.ng, naux = ctx->n_mu + 3;
+      ok = ok && encode(&ctx->tm_grad, ctx->grad, ngf, kG3TY + 2, (ngf + 1) & ~1) && encode(&ctx->tm_aux, ctx->mu, naux, kG3TY + 2, (naux + 1) & ~1);
+    }
     if (!ok) { fprintf(stderr, "fest3d_gpu: cuTensorMapEncodeTiled failed\n"); return fail(ctx, F3D_ERR_CUDA); }
     ctx->tmaps_ok = true;
   }
@@ -233,7 +243,12 @@ extern "C" int fest3d_gpu_destroy(Fest3dGpuCtx* ctx) {
   if (ctx->norms_host) cudaFreeHost(ctx->norms_host);
   if (ctx->err_host) cudaFreeHost(ctx->err_host);
   for (auto& e : ctx->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  for (auto& e : ctx->ev_pool2) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   comm_release(ctx);
+  if (ctx->state_staging_out) cudaFree(ctx->state_staging_out);
+  if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+  if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
+  for (cudaEvent_t e : {ctx->ev_h2d, ctx->ev_in_free, ctx->ev_relaid, ctx->ev_d2h}) if (e) cudaEventDestroy(e);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->ev_pack) cudaEventDestroy(ctx->ev_pack);
   if (ctx->ev_halo) cudaEventDestroy(ctx->ev_halo);
@@ -273,6 +288,16 @@ static int copy_cells(Fest3dGpuCtx* ctx, double* dev_field, double* host, int nf
   return 0;
 }
 
+// staged path: the cell-centre fields copied behind the viscosity fields: one "aux" array for the tensor-map staging of the sweep
+static int init_aux_fields(Fest3dGpuCtx* ctx) {
+  if (!ctx->P.viscous || ctx->fused) return 0;
+  const long long fs = ctx->P.L.fs;
+  F3D_CUDA(cudaMemcpyAsync(ctx->mu + (long long)ctx->n_mu * fs, ctx->geom + (long long)G_CX * fs, 3 * fs * sizeof(double), cudaMemcpyDeviceToDevice,
+                           ctx->stream));
+  F3D_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
 extern "C" int fest3d_gpu_set_geometry(Fest3dGpuCtx* ctx, const double* cells, const double* Ifaces, const double* Jfaces,
                                        const double* Kfaces, const double* dist) {
   if (!ctx || !cells || !Ifaces || !Jfaces || !Kfaces) return fail(ctx, F3D_ERR_ARGUMENT);
@@ -292,6 +317,7 @@ extern "C" int fest3d_gpu_set_geometry(Fest3dGpuCtx* ctx, const double* cells, c
     // face records for the ghost-gradient rule.  The reference passes Jfaces / Kfaces to a dummy declared with the Ifaces
     // shape (gradients.f90:549-612): element (i,j,k) is then read at record offset (i+2) + (imx+6)*((j+2) + (jmx+5)*(k+2)) of
     // the actual array.  Reproduced here on the host, once.
+    if ((rc = init_aux_fields(ctx))) return rc;
     const int mx[3] = {L.imx, L.jmx, L.kmx};
     const double* arrs[3] = {Ifaces, Jfaces, Kfaces};
     std::vector<double> rec;
@@ -354,10 +380,87 @@ extern "C" int fest3d_gpu_get_state(Fest3dGpuCtx* ctx, double* qp) {
   const Layout& L = ctx->P.L;
   int rc = ensure_state_staging(ctx);
   if (rc) return rc;
+  if ((rc = apply_pending_state(ctx))) return rc;
+  if (ctx->ev_in_free) F3D_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d, 0));
   const size_t n = (size_t)L.nv * (L.imx + 5) * (L.jmx + 5) * (L.kmx + 5);
   if ((rc = launch_state_relayout(ctx, ctx->qp, ctx->state_staging, 0))) return rc;
   F3D_CUDA(cudaMemcpyAsync(qp, ctx->state_staging, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   F3D_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// Asynchronous, full-duplex form of the two transfers (a host that wants qp back every few iterations, the e2e leg of bench.py):
+//   fest3d_gpu_set_state_async  H2D on the inbound copy stream into the staging buffer and return; the re-layout into the padded
+//                               fields is queued by the next fest3d_gpu_step / fest3d_gpu_residual call (stream-ordered behind the copy)
+//   fest3d_gpu_get_state_async  re-layout on the compute stream (stream order: after every step issued so far), D2H on the outbound copy
+//                               stream; the host buffer is valid after fest3d_gpu_state_wait
+// so the upload of the next state overlaps the running iterations AND the download of the previous result (PCIe is full duplex).
+static int ensure_async_state(Fest3dGpuCtx* ctx) {
+  int rc = ensure_state_staging(ctx);
+  if (rc) return rc;
+  if (ctx->copy_in) return 0;
+  const Layout& L = ctx->P.L;
+  const size_t n = (size_t)L.nv * (L.imx + 5) * (L.jmx + 5) * (L.kmx + 5);
+  F3D_CUDA(cudaMalloc((void**)&ctx->state_staging_out, n * sizeof(double)));
+  F3D_CUDA(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+  F3D_CUDA(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+  F3D_CUDA(cudaEventCreateWithFlags(&ctx->ev_h2d, cudaEventDisableTiming));
+  F3D_CUDA(cudaEventCreateWithFlags(&ctx->ev_in_free, cudaEventDisableTiming));
+  F3D_CUDA(cudaEventCreateWithFlags(&ctx->ev_relaid, cudaEventDisableTiming));
+  F3D_CUDA(cudaEventCreateWithFlags(&ctx->ev_d2h, cudaEventDisableTiming));
+  return 0;
+}
+
+// queue the re-layout of an uploaded state (called at the head of every step / residual call)
+static int apply_pending_state(Fest3dGpuCtx* ctx) {
+  if (!ctx->state_pending) return 0;
+  F3D_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d, 0));
+  int rc = launch_state_relayout(ctx, ctx->qp, ctx->state_staging, 1);
+  if (rc) return rc;
+  F3D_CUDA(cudaMemsetAsync(ctx->err_dev, 0, sizeof(int) * 4, ctx->stream));
+  F3D_CUDA(cudaEventRecord(ctx->ev_in_free, ctx->stream));   // the staging buffer may take the next upload
+  ctx->state_pending = false;
+  ctx->state_set = true;
+  return 0;
+}
+
+extern "C" int fest3d_gpu_set_state_async(Fest3dGpuCtx* ctx, const double* qp) {
+  if (!ctx || !qp) return fail(ctx, F3D_ERR_ARGUMENT);
+  F3D_CUDA(cudaSetDevice(ctx->device));
+  int rc = ensure_async_state(ctx);
+  if (rc) return rc;
+  if (ctx->state_pending && (rc = apply_pending_state(ctx))) return rc;   // a second upload without a step in between: keep the order
+  const Layout& L = ctx->P.L;
+  const size_t n = (size_t)L.nv * (L.imx + 5) * (L.jmx + 5) * (L.kmx + 5);
+  F3D_CUDA(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_in_free, 0));
+  F3D_CUDA(cudaMemcpyAsync(ctx->state_staging, qp, n * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
+  F3D_CUDA(cudaEventRecord(ctx->ev_h2d, ctx->copy_in));
+  ctx->state_pending = true;
+  { const int bid = ctx->last_error.block_id; ctx->last_error = Fest3dGpuError{}; ctx->last_error.block_id = bid; }
+  return 0;
+}
+
+extern "C" int fest3d_gpu_get_state_async(Fest3dGpuCtx* ctx, double* qp) {
+  if (!ctx || !qp) return fail(ctx, F3D_ERR_ARGUMENT);
+  F3D_CUDA(cudaSetDevice(ctx->device));
+  int rc = ensure_async_state(ctx);
+  if (rc) return rc;
+  if ((rc = apply_pending_state(ctx))) return rc;
+  const Layout& L = ctx->P.L;
+  const size_t n = (size_t)L.nv * (L.imx + 5) * (L.jmx + 5) * (L.kmx + 5);
+  F3D_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h, 0));   // the previous download has left the outbound buffer
+  if ((rc = launch_state_relayout(ctx, ctx->qp, ctx->state_staging_out, 0))) return rc;
+  F3D_CUDA(cudaEventRecord(ctx->ev_relaid, ctx->stream));
+  F3D_CUDA(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_relaid, 0));
+  F3D_CUDA(cudaMemcpyAsync(qp, ctx->state_staging_out, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy_out));
+  F3D_CUDA(cudaEventRecord(ctx->ev_d2h, ctx->copy_out));
+  return 0;
+}
+
+extern "C" int fest3d_gpu_state_wait(Fest3dGpuCtx* ctx) {
+  if (!ctx) return F3D_ERR_ARGUMENT;
+  F3D_CUDA(cudaSetDevice(ctx->device));
+  if (ctx->copy_in) { F3D_CUDA(cudaStreamSynchronize(ctx->copy_in)); F3D_CUDA(cudaStreamSynchronize(ctx->copy_out)); }
   return 0;
 }
 
@@ -377,9 +480,9 @@ extern "C" int fest3d_gpu_get_aux(Fest3dGpuCtx* ctx, int which, double* out) {
   const Layout& L = ctx->P.L;
   int rc = F3D_ERR_ARGUMENT;
   const bool view = (which >= 1 && which <= 3) || (which >= 30 && which <= 32);
-  if (view && ctx->P.viscous) {
-    // mu / mu_t / F1 / gradients never reach HBM on the hot path (the fused sweep keeps them in shared memory): for these views the
-    // stand-alone kernels of grad.cu recompute them from the current qp / Temp (ghost cells as the last stage left them)
+  if (view && ctx->P.viscous && ctx->fused) {
+    // fused path: mu / mu_t / F1 / gradients never reach HBM (the sweep keeps them in shared memory): for these views the stand-alone
+    // kernels of grad.cu recompute them from the current qp / Temp (ghost cells as the last stage left them)
     const size_t fb = (size_t)L.fs * sizeof(double);
     if (!ctx->grad) {
       F3D_CUDA(cudaMalloc((void**)&ctx->grad, (size_t)3 * L.ng * fb));
@@ -433,6 +536,23 @@ extern "C" double fest3d_gpu_kernel_time_ms(Fest3dGpuCtx* ctx, long long* n, int
   if (reset) { ctx->ktime_ms = 0.0; ctx->ktime_n = 0; }
   return t;
 }
+
+extern "C" double fest3d_gpu_gradient_time_ms(Fest3dGpuCtx* ctx, long long* n, int reset) {
+  if (!ctx) return -1.0;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (size_t e = 0; e < ctx->ev_used2; ++e) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev_pool2[e].first, ctx->ev_pool2[e].second) == cudaSuccess) { ctx->ktime2_ms += ms; ctx->ktime2_n++; }
+  }
+  ctx->ev_used2 = 0;
+  const double t = ctx->ktime2_ms;
+  if (n) *n = ctx->ktime2_n;
+  if (reset) { ctx->ktime2_ms = 0.0; ctx->ktime2_n = 0; }
+  return t;
+}
+
+extern "C" int fest3d_gpu_gradient_path(Fest3dGpuCtx* ctx) { return ctx ? ctx->fused : -1; }
 
 // ---- multi-block plumbing -------------------------------------------------------------------------------------------
 extern "C" int fest3d_gpu_comm_unique_id(char id_out[128]) {
@@ -615,6 +735,7 @@ int stage(Fest3dGpuCtx** cs, int n, bool update, double TF, double SF, int use_s
     Fest3dGpuCtx* ctx = cs[c];
     F3D_CUDA(cudaSetDevice(ctx->device));
     if ((rc = launch_bc(ctx))) return rc;
+    if (ctx->P.viscous && !ctx->fused && (rc = launch_gradients(ctx))) return rc;   // staged path: gradients + viscosities into HBM
     if (!update) {
       if ((rc = launch_residual(ctx, MODE_RESIDUE_ONLY, 1.0, 1.0, 0, 1, 0))) return rc;
       continue;
@@ -651,8 +772,9 @@ extern "C" int fest3d_gpu_residual_group(Fest3dGpuCtx** cs, int n, int current_i
   if (!cs || n < 1) return F3D_ERR_ARGUMENT;
   for (int c = 0; c < n; ++c) {
     Fest3dGpuCtx* ctx = cs[c];
-    if (!ctx->geometry_set || !ctx->state_set) return fail(ctx, F3D_ERR_ARGUMENT);
     F3D_CUDA(cudaSetDevice(ctx->device));
+    { int rp = apply_pending_state(ctx); if (rp) return rp; }
+    if (!ctx->geometry_set || !ctx->state_set) return fail(ctx, F3D_ERR_ARGUMENT);
     ctx->P.current_iter = current_iter;
     int rc = launch_temp(ctx);
     if (rc) return rc;
@@ -676,7 +798,12 @@ extern "C" int fest3d_gpu_step_group(Fest3dGpuCtx** cs, int n, int current_iter,
   if (!cs || n < 1 || n_iters < 1) return F3D_ERR_ARGUMENT;
   const int nvp1 = cs[0]->P.L.nv + 1;
   const int ta = cs[0]->cfg.time_accuracy;
-  for (int c = 0; c < n; ++c) if (!cs[c]->geometry_set || !cs[c]->state_set || cs[c]->cfg.time_accuracy != ta) return fail(cs[c], F3D_ERR_ARGUMENT);
+  for (int c = 0; c < n; ++c) {
+    cudaSetDevice(cs[c]->device);
+    int rp = apply_pending_state(cs[c]);
+    if (rp) return rp;
+    if (!cs[c]->geometry_set || !cs[c]->state_set || cs[c]->cfg.time_accuracy != ta) return fail(cs[c], F3D_ERR_ARGUMENT);
+  }
   const int chunk = 1016 / nvp1;   // norms of a chunk + the error slot fit the 1024-double norm buffers
   int rc = 0;
   for (int it0 = 0; it0 < n_iters; it0 += chunk) {
@@ -772,6 +899,7 @@ extern "C" int fest3d_gpu_setup_geometry(Fest3dGpuCtx* ctx, const double* grid_x
   if (dist) {
     if ((rc = copy_cells(ctx, ctx->geom + (long long)G_DIST * L.fs, const_cast<double*>(dist), 1, true, -2, L.imx + 5, L.jmx + 5, L.kmx + 5))) return rc;
   }
+  if ((rc = init_aux_fields(ctx))) return rc;
   if ((rc = check_errors(ctx))) return rc;   // non-positive volume -> F3D_ERR_GEOMETRY with the cell (geometry.f90:476-494)
   ctx->geometry_set = true;
   return 0;

@@ -72,14 +72,18 @@ struct Ctx {
   double* temp = nullptr;     // 1 field
   double* dt = nullptr;       // 1 field
   double* geom = nullptr;     // G_NFIELDS fields
-  // Gradients and viscosities live only inside the fused sweep (shared memory).  These two arrays exist for the debugging /
-  // parity views of fest3d_gpu_get_aux alone and are allocated on its first call (grad.cu fills them then):
+  // Two forms of the viscous path (F3D_GRADIENTS = staged | fused, api.cu):
+  //   staged  Green-Gauss gradients + viscosities by their own kernel (grad.cu) into these arrays, staged by the sweep with TMA
+  //           (sweep3_kernel.cuh) -- the faster form on B200 as measured (profiles/r02_g4_summary.md), default
+  //   fused   computed inside the tile pass, nothing in HBM (fused_kernel.cuh); the arrays then exist only for the debugging views
+  //           of fest3d_gpu_get_aux and are allocated on its first call
+  int fused = 0;
   double* grad = nullptr;     // 3*ng fields: component c, direction d -> field 3*c+d
-  double* mu = nullptr;       // mu [, mu_t [, F1]] as the model has them
+  double* mu = nullptr;       // mu [, mu_t [, F1]] as the model has them, then (staged path) a copy of the cell centre x,y,z
   int n_mu = 0;               // 1 laminar, 2 sa, 3 sst
-  // 4-D tensor maps [field][k][j][i] of the arrays the sweep stages (fused_kernel.cuh): q (36 x 8 cells x nv fields), Temp
-  // (36 x 8 x 1), geometry fields volume + centre (36 x 6 x 4)
-  CUtensorMap tm_q[2], tm_temp, tm_geo;
+  // 4-D tensor maps [field][k][j][i]: q (36 x 8 cells x nv fields); fused path: Temp (36 x 8 x 1), geometry fields volume + centre
+  // (36 x 6 x 4); staged path: gradients and the aux array (36 x 6 x fields)
+  CUtensorMap tm_q[2], tm_temp, tm_geo, tm_grad, tm_aux;
   double* tm_q_ptr[2] = {nullptr, nullptr};
   bool tmaps_ok = false;
   double* gbc = nullptr;      // per-face (A,nx,ny,nz) records the ghost-gradient rule reads (mis-indexed for J/K faces)
@@ -95,7 +99,12 @@ struct Ctx {
   double* recvbuf[6] = {nullptr};
   size_t buf_elems[6] = {0};
   double* staging = nullptr;     // host<->device staging for AoS geometry upload
-  double* state_staging = nullptr;   // contiguous copy of qp in the reference layout (set_state / get_state)
+  double* state_staging = nullptr;   // contiguous copy of qp in the reference layout (set_state / get_state, and the inbound side of the
+                                     // asynchronous transfers)
+  double* state_staging_out = nullptr;   // outbound side of the asynchronous transfers
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;       // H2D / D2H run on their own streams: full duplex beside the compute stream
+  cudaEvent_t ev_h2d = nullptr, ev_in_free = nullptr, ev_relaid = nullptr, ev_d2h = nullptr;
+  bool state_pending = false;        // an uploaded state waits in state_staging to be laid out into qp (done at the next step / residual)
   Link link[6];
   struct Checkpoint* ckpt = nullptr;   // asynchronous checkpoint state (checkpoint.cu), created on first use
   void* nccl = nullptr;          // the process-wide communicator record (api.cu:CommShared)
@@ -108,6 +117,10 @@ struct Ctx {
   size_t ev_used = 0;
   double ktime_ms = 0.0;
   long long ktime_n = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool2;   // the same for the gradient kernels of the staged path
+  size_t ev_used2 = 0;
+  double ktime2_ms = 0.0;
+  long long ktime2_n = 0;
   Fest3dGpuError last_error{};
   bool geometry_set = false, state_set = false;
 };

@@ -17,3 +17,18 @@ int launch_fused(Ctx* ctx, KArgs& a) {
 }
 
 }  // namespace f3d
+
+#ifdef F3D_PHASE_TIMING
+extern "C" void fest3d_gpu_phase_dump() {
+  unsigned long long h[64];
+  cudaMemcpyFromSymbol(h, f3d::g4::g_phase, sizeof(h));
+  const char* nm[4] = {"phase 1 work", "wait barrier A", "phase 2 work", "wait barrier B"};
+  for (int w = 0; w < 16; ++w) {
+    unsigned long long tot = 0;
+    for (int n = 0; n < 4; ++n) tot += h[w * 4 + n];
+    printf("warp %2d:", w);
+    for (int n = 0; n < 4; ++n) printf("  %s %5.1f %%", nm[n], 100.0 * h[w * 4 + n] / (double)(tot ? tot : 1));
+    printf("   (total %.3e cycles)\n", (double)tot);
+  }
+}
+#endif

@@ -35,12 +35,26 @@
 namespace f3d {
 namespace g4 {
 
+#ifdef F3D_PHASE_TIMING   // development aid: clock64 totals per warp and bucket (phase 1 work, wait at barrier A, phase 2 work, wait at barrier B)
+__device__ unsigned long long g_phase[16 * 4];
+#define PT_DECL unsigned long long pt_t = clock64(), pt_acc[4] = {0, 0, 0, 0};
+#define PT_MARK(n) { const unsigned long long t_ = clock64(); pt_acc[n] += t_ - pt_t; pt_t = t_; }
+#define PT_FLUSH if (lane == 0) { for (int n_ = 0; n_ < 4; ++n_) atomicAdd(&g_phase[wid * 4 + n_], pt_acc[n_]); }
+#else
+#define PT_DECL
+#define PT_MARK(n)
+#define PT_FLUSH
+#endif
+
 constexpr int TX = 32, TY = 4;
 constexpr int NMAIN = TX * TY;
-constexpr int NW = 16, NT = 32 * NW;
-constexpr int W_J0 = TY, W_K0 = 2 * TY, W_IH = 3 * TY, W_JH = 3 * TY + 1, W_JL = 3 * TY + 2, W_C = 3 * TY + 3;
+constexpr int NW = 15, NT = 32 * NW;                            // 15 warps x 136 registers = the register file of the SM
+constexpr int W_J0 = TY, W_K0 = 2 * TY, W_IH = 3 * TY, W_JH = 3 * TY + 1, W_JL = 3 * TY + 2;
+constexpr int W_OBS = W_K0 + 3;                                 // a warp without phase-2 work: observes the plane arrivals of inviscid runs
+// cell work of row r (phase 2) by a warp of the row's lane quarter: the three halo warps 12..14 for rows 0..2, J row 3 (warp 7) for row 3
+__device__ __forceinline__ int cell_row_of_warp(int wid) { return wid >= W_IH ? wid - W_IH : ((wid == W_J0 + 3) ? 3 : -1); }
 constexpr int N_IGRP = 32 * (TY + 1), N_JGRP = 32 * (TY + 2);   // threads on named barriers 1 and 2
-constexpr int NGW = 7;                                          // warps 0..6 do the gradient tasks of phase 2 (204 cells)
+constexpr int NGW = 7;                                          // warps 0..6 (I rows, J rows 0..2) do the gradient tasks of phase 2 (204 cells)
 
 // staged q plane: rows j0-2 .. j0+TY+1 of PW = TX+4 cells (i0-2 .. i0+TX+1); slot of cell (col, row) = row*PW + col
 constexpr int PW = TX + 4, QROWS = TY + 4, PSQ = PW * QROWS;
@@ -50,7 +64,8 @@ constexpr int RW = TX + 2, RROWS = TY + 2, NRC = RW * RROWS;
 constexpr int GW = TX + 4, PSG = GW * RROWS;
 constexpr int NQS = 4, NGS = 3;                                 // ring depths
 // exchange area ([field][slot], slot = face): i faces TY x (TX+1), j faces (TY+1) x TX
-constexpr int SLOT_I = TY * (TX + 1), SLOT_J = (TY + 1) * TX, EX = SLOT_I + SLOT_J;
+constexpr int SLOT_I = TY * (TX + 1), SLOT_J = (TY + 1) * TX, EX = SLOT_I + SLOT_J;   // slot EX: dummy (idle lanes of the i-halo warp)
+constexpr int EXP = EX + 2;                                     // field pitch of the exchange area
 
 // tensor-memory map of one cell column, in doubles (column = 2 x index): k-face flux ring, cell packet, norm partials, carried hi
 constexpr int T_FK = 0;      // [2][10]: flux + lambda / viscous / turbulent time-step terms of the k face below plane p: half p & 1
@@ -75,11 +90,13 @@ struct Sm : RecF<NV, VISC> {
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_G = OFF_Q + NQS * QSLOT;
   static constexpr int OFF_R = OFF_G + NGS * GSLOT;
-  static constexpr int OFF_X = OFF_R + 2 * RSLOT;           // exchange [NF][EX]
-  static constexpr int OFF_MBAR = OFF_X + NF * EX;          // NQS + NGS mbarriers, then the tensor-memory base address
+  static constexpr int OFF_X = OFF_R + 2 * RSLOT;           // exchange [NF][EXP]
+  static constexpr int OFF_MBAR = OFF_X + NF * EXP;         // NQS + NGS mbarriers, then the tensor-memory base address
   static constexpr int OFF_RED = OFF_MBAR + NQS + NGS + 1;  // final norm reduction [NV+1][4]
   static constexpr int TOTAL = OFF_RED + (NV + 1) * 4;
 };
+
+__device__ __forceinline__ void prefetch_l2(const double* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---- mbarrier / TMA / named barriers -----------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -108,7 +125,6 @@ __device__ __forceinline__ void tma_g2s_4d(void* dst, const CUtensorMap* tm, int
 struct TMaps { CUtensorMap q, temp, geo; };
 __device__ __forceinline__ void bar_all() { asm volatile("bar.sync 0;" ::: "memory"); }
 __device__ __forceinline__ void bar_group(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void prefetch_l2(const double* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---- tensor memory as per-column scratch: tcgen05.ld / tcgen05.st, shape 32x32b (thread t of the warp <-> lane 32*(warp%4) + t) ----
 __device__ __forceinline__ void tm_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -144,6 +160,24 @@ __device__ __forceinline__ void tm_ld8(unsigned a, double* v) {   // 8 doubles (
   tm_wait_ld();
 #pragma unroll
   for (int n = 0; n < 8; ++n) v[n] = __hiloint2double(r[2 * n + 1], r[2 * n]);
+}
+#define F3D_TM_LD32(r, a)                                                                                                                                  \
+  asm volatile(                                                                                                                                           \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, " \
+      "%26, %27, %28, %29, %30, %31}, [%32];"                                                                                                           \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), \
+        "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),       \
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                                                     \
+      : "r"(a)                                                                                                                                            \
+      : "memory")
+__device__ __forceinline__ void tm_ld16_3(unsigned a0, double* v0, unsigned a1, double* v1, unsigned a2, double* v2) {   // 3 x 16 doubles, one wait
+  unsigned r0[32], r1[32], r2[32];
+  F3D_TM_LD32(r0, a0);
+  F3D_TM_LD32(r1, a1);
+  F3D_TM_LD32(r2, a2);
+  tm_wait_ld();
+#pragma unroll
+  for (int n = 0; n < 16; ++n) { v0[n] = __hiloint2double(r0[2 * n + 1], r0[2 * n]); v1[n] = __hiloint2double(r1[2 * n + 1], r1[2 * n]); v2[n] = __hiloint2double(r2[2 * n + 1], r2[2 * n]); }
 }
 __device__ __forceinline__ void tm_ld16(unsigned a, double* v) {   // 16 doubles (32 columns)
   unsigned r[32];
@@ -285,28 +319,49 @@ __device__ __forceinline__ void face_eval4(const Params& P, int d, const double*
 
 // ---- phase 2, gradient task: Green-Gauss gradients (gradients.f90:405-482) + Sutherland / SA / SST viscosities (viscosity.f90) of one
 // cell of plane p from the staged q planes p-1 (qm), p (q0), p+1 (qp); sq = the cell's slot in a q plane.  Writes the record.
-template <int NV>
-__device__ __forceinline__ void gradient_record(const Params& P, const KArgs& a, const double* __restrict__ qm, const double* __restrict__ q0,
-                                                const double* __restrict__ qp, int sq, double vol_c, long long c, double* __restrict__ rec) {
-  using R = RecF<NV, true>;
-  constexpr int NG = R::NG, F_MU = 3 * NG, RP = ((3 * NG + R::NMU) + 1) & ~1;
-  const Layout& L = P.L;
+// n*A of the six faces of a cell per direction component: the only global loads of the gradient task (rows of consecutive cells;
+// the same lines come back from L2 when the flux warps ask for them two planes later).  Requested BEFORE the phase barrier, so
+// that their latency is spent waiting at the barrier instead of at the head of the task.
+struct GradW { double wl[3][3], wh[3][3]; };
+__device__ __forceinline__ void gradient_weights(const KArgs& a, const Layout& L, long long c, GradW& w) {
   const long long fs = L.fs;
   const double* __restrict__ gI = a.geom + (long long)G_IA * fs + c;
   const double* __restrict__ gJ = a.geom + (long long)G_JA * fs + c;
   const double* __restrict__ gK = a.geom + (long long)G_KA * fs + c;
-  // n*A of the six faces per direction component: the only global loads of the task (rows of consecutive cells; the k faces of
-  // plane p+1 and everything else come back from L2 when the flux warps ask for them two planes later)
-  double wl[3][3], wh[3][3];
-  {
-    const double AIl = gI[0], AIh = gI[1], AJl = gJ[0], AJh = gJ[L.sj], AKl = gK[0], AKh = gK[L.sk];
+  const double AIl = gI[0], AIh = gI[1], AJl = gJ[0], AJh = gJ[L.sj], AKl = gK[0], AKh = gK[L.sk];
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      wl[0][d] = gI[(1 + d) * fs] * AIl; wh[0][d] = gI[(1 + d) * fs + 1] * AIh;
-      wl[1][d] = gJ[(1 + d) * fs] * AJl; wh[1][d] = gJ[(1 + d) * fs + L.sj] * AJh;
-      wl[2][d] = gK[(1 + d) * fs] * AKl; wh[2][d] = gK[(1 + d) * fs + L.sk] * AKh;
-    }
+  for (int d = 0; d < 3; ++d) {
+    w.wl[0][d] = gI[(1 + d) * fs] * AIl; w.wh[0][d] = gI[(1 + d) * fs + 1] * AIh;
+    w.wl[1][d] = gJ[(1 + d) * fs] * AJl; w.wh[1][d] = gJ[(1 + d) * fs + L.sj] * AJh;
+    w.wl[2][d] = gK[(1 + d) * fs] * AKl; w.wh[2][d] = gK[(1 + d) * fs + L.sk] * AKh;
   }
+}
+
+__device__ __forceinline__ void gradient_prefetch(const KArgs& a, const Layout& L, long long c) {
+  const long long fs = L.fs;
+  const double* gI = a.geom + (long long)G_IA * fs + c;
+#pragma unroll
+  for (int f = 0; f < 12; ++f) prefetch_l2(gI + f * fs);   // A, nx, ny, nz of the I, J, K faces of the cell: the neighbours' lines cover the high faces
+  prefetch_l2(a.geom + (long long)G_DIST * fs + c);
+}
+
+// tanh(x) for x >= 0 through one exponential: (1 - e) / (1 + e), e = exp(-2x).  Absolute error <= ~2e-16 (the blending functions it
+// feeds are O(1) factors: the error that matters is absolute), a third of the instructions of the library tanh and no slow path.
+__device__ __forceinline__ double tanh_pos(double x) {
+  const double e = exp(-2.0 * dmin(x, 20.0));
+  return (1.0 - e) * rcp64(1.0 + e);
+}
+
+template <int NV>
+__device__ __forceinline__ void gradient_record(const Params& P, const KArgs& a, const double* __restrict__ qm, const double* __restrict__ q0,
+                                                const double* __restrict__ qp, int sq, double vol_c, long long c, const GradW& w,
+                                                double* __restrict__ rec) {
+  using R = RecF<NV, true>;
+  constexpr int NG = R::NG, F_MU = 3 * NG, RP = ((3 * NG + R::NMU) + 1) & ~1;
+  const Layout& L = P.L;
+  const long long fs = L.fs;
+  const double (&wl)[3][3] = w.wl;
+  const double (&wh)[3][3] = w.wh;
   const double ivol2 = rcp64(2 * vol_c);
   const bool zgrad = L.kmx > 2;   // gradqp_z = 0 when kmx == 2 (gradients.f90:328-336)
   double g[NG][3];
@@ -347,7 +402,7 @@ __device__ __forceinline__ void gradient_record(const Params& P, const KArgs& a,
     const double var1 = sqrt(tk) * rcp64(kBstar * tw * dd);
     const double var2 = 500 * (mu * rcp64(density)) * rcp64((dd * dd) * tw);
     const double arg2 = dmax(2 * var1, var2);
-    const double Fb = tanh(arg2 * arg2);
+    const double Fb = tanh_pos(arg2 * arg2);
     double rate;
     if (P.turbulence == F3D_TURB_SST) {
       const double wx = g[2][1] - g[1][2], wy = g[0][2] - g[2][0], wz = g[1][0] - g[0][1];
@@ -364,7 +419,7 @@ __device__ __forceinline__ void gradient_record(const Params& P, const KArgs& a,
     const double right = 4 * (density * kSigmaW2 * tk) * rcp64(CD * (dd * dd));
     const double left = dmax(var1, var2);
     const double arg1 = dmin(left, right);
-    F1 = tanh((arg1 * arg1) * (arg1 * arg1));
+    F1 = tanh_pos((arg1 * arg1) * (arg1 * arg1));
   }
   double out[RP];
 #pragma unroll
@@ -433,7 +488,7 @@ __device__ __forceinline__ void cell_work4(const Params& P, const KArgs& a, cons
   double merr = 0.0;
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
-    const double Fl0 = xF[v * EX + sl0], Fh0 = xF[v * EX + sh0], Fl1 = xF[v * EX + sl1], Fh1 = xF[v * EX + sh1];
+    const double Fl0 = xF[v * EXP + sl0], Fh0 = xF[v * EXP + sh0], Fl1 = xF[v * EXP + sl1], Fh1 = xF[v * EXP + sh1];
     double rr = 0.0;
     rr = rr + (Fh0 - Fl0);   // scheme.f90:133-135
     rr = rr + (Fh1 - Fl1);
@@ -467,18 +522,18 @@ __device__ __forceinline__ void cell_work4(const Params& P, const KArgs& a, cons
     if (P.time_stepping == 1 && P.global_time_step > 0) {
       dtc = P.global_time_step;
     } else {
-      const double* lamv = xF + NV * EX;
+      const double* lamv = xF + NV * EXP;
       const double lmxsum = lamv[sl0] + lamv[sl1] + Flo[NV] + lamv[sh0] + lamv[sh1] + Fhi[NV];
       dtc = rcp64(lmxsum);
       dtc = dtc * volc * P.CFL;
       if (VISC) {
-        const double* visv = xF + (NV + 1) * EX;
+        const double* visv = xF + (NV + 1) * EXP;
         double s = visv[sl0] + visv[sl1] + Flo[NV + 1] + visv[sh0] + visv[sh1] + Fhi[NV + 1];
         s = P.gm * s * P.inv_Pr;
         s = 2. * rcp64(s + (2. * P.CFL * volc * rcp64(dtc)));
         dtc = P.CFL * (s * volc);
         if (TURB) {
-          const double* turv = xF + (NV + 2) * EX;
+          const double* turv = xF + (NV + 2) * EXP;
           double tt = turv[sl0] + turv[sl1] + Flo[NV + 2] + turv[sh0] + turv[sh1] + Fhi[NV + 2];
           tt = P.gm * tt * P.inv_tPr;
           tt = 2. * rcp64(tt + (2. * P.CFL * volc * rcp64(dtc)));
@@ -602,7 +657,7 @@ __global__ void __launch_bounds__(NT, 1) k_fused(const Params P, const KArgs a, 
   __syncthreads();
   tm_fence_after();
   const unsigned tbase = *reinterpret_cast<volatile unsigned*>(tm_slot) + ((unsigned)(32 * (wid & 3)) << 16);   // this warp's lane quarter
-  if (wid >= W_IH) {   // the norm partials start at zero (cleared by the warp that accumulates them: no cross-warp ordering needed)
+  if (cell_row_of_warp(wid) >= 0) {   // the norm partials start at zero (cleared by the warp that accumulates them: no cross-warp ordering needed)
     const double z[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
     tm_st8(tbase + 2 * T_NRM, z);
     tm_wait_st();
@@ -635,62 +690,84 @@ __global__ void __launch_bounds__(NT, 1) k_fused(const Params P, const KArgs a, 
     issue_g(kb - 1);
   }
 
-  // ---- role of this thread in phase 1 (all flux warps run ONE instruction stream, parameterised by these values) ----------------------
-  int i, j, s0, rc, sg, d, cell;
-  bool rec, fac, wr_hi, irow, krow, own;
-  int exw, exr;                     // I/J: exchange slots: where the hi value goes; where L is read and the flux written
+  // ---- role of this thread in phase 1 (all flux warps run ONE instruction stream, parameterised by these values).  With the staged
+  // 3-point stencils (SMQ) the lanes outside the block (ragged last tiles) simply compute on the zero-filled planes: their results
+  // land in slots nobody consumes, and the hot path has no divergent domain test.  The 5-point interpolants read global memory and
+  // keep the tests.
+  // The values are packed into three words and unpacked again at the top of every plane (an empty asm keeps the compiler from
+  // hoisting the unpacked forms out of the loop: carried as ~15 separate registers they were spilled, and every plane began by
+  // waiting for their reloads -- 17 % of the stall samples of phase 1, profiles/r02_g4_summary.md).
+  unsigned rw_ij, rw_sx, rw_fl;
   {
-    wr_hi = true; irow = false; krow = false; own = false; cell = 0;
-    rec = fac = false; d = 0; i = i0 + lane; j = j0; s0 = 2 * PW + 2; rc = RW + 1; sg = GW + 2; exw = exr = 0;
+    int i, j, s0, d, row;
+    bool rec, fac, wr_hi, irow, krow;
+    int exw, exr;                     // I/J: exchange slots: where the hi value goes; where L is read and the flux written
+    int rc = 0, sg = 0;
+    wr_hi = true; irow = false; krow = false;
+    rec = fac = false; d = 0; i = i0 + lane; j = j0; s0 = 2 * PW + 2; rc = RW + 1; sg = GW + 2; exw = exr = EX;
     if (wid < TY) {                   // I row
       const int tx = lane, ty = wid;
-      d = 0; i = i0 + tx; j = j0 + ty; irow = true; cell = ty * TX + tx;
-      rec = fac = (j <= Ly.jmx - 1) && (i <= Ly.imx);
+      d = 0; i = i0 + tx; j = j0 + ty; irow = true;
+      rec = fac = SMQ || ((j <= Ly.jmx - 1) && (i <= Ly.imx));
       s0 = (ty + 2) * PW + tx + 2; rc = (ty + 1) * RW + tx + 1; sg = (ty + 1) * GW + tx + 2;
       exw = ty * (TX + 1) + tx + 1; exr = ty * (TX + 1) + tx;
     } else if (wid < 2 * TY) {        // J row
       const int tx = lane, ty = wid - TY;
       d = 1; i = i0 + tx; j = j0 + ty;
-      rec = fac = (i <= Ly.imx - 1) && (j <= Ly.jmx);
+      rec = fac = SMQ || ((i <= Ly.imx - 1) && (j <= Ly.jmx));
       s0 = (ty + 2) * PW + tx + 2; rc = (ty + 1) * RW + tx + 1; sg = (ty + 1) * GW + tx + 2;
       exw = SLOT_I + (ty + 1) * TX + tx; exr = SLOT_I + ty * TX + tx;
     } else if (wid < 3 * TY) {        // K row: the column of its cell
       const int tx = lane, ty = wid - 2 * TY;
-      d = 2; i = i0 + tx; j = j0 + ty; krow = true; cell = ty * TX + tx;
-      own = (i <= Ly.imx - 1) && (j <= Ly.jmx - 1);
-      rec = fac = own && k_active;
+      d = 2; i = i0 + tx; j = j0 + ty; krow = true;
+      rec = fac = k_active && (SMQ || ((i <= Ly.imx - 1) && (j <= Ly.jmx - 1)));
       s0 = (ty + 2) * PW + tx + 2; rc = (ty + 1) * RW + tx + 1; sg = (ty + 1) * GW + tx + 2;
-    } else if (wid == W_IH) {         // the two i columns next to the tile: lanes 0..TY-1 low side, TY..2TY-1 high side
-      const int r = lane % TY, side = lane / TY;
+    } else if (wid == W_IH) {         // the two i columns next to the tile: lanes 0..TY-1 low side, TY..2TY-1 high side; the other
+      const int r = lane % TY, side = (lane / TY) & 1;   // lanes repeat them into a dummy exchange slot
       d = 0; i = (side == 0) ? i0 - 1 : i0 + TX; j = j0 + r;
-      rec = (side < 2) && (j <= Ly.jmx - 1) && (i <= Ly.imx);
+      rec = SMQ || ((lane < 2 * TY) && (j <= Ly.jmx - 1) && (i <= Ly.imx));
       fac = rec && side == 1; wr_hi = side == 0;
       s0 = (r + 2) * PW + (side == 0 ? 1 : TX + 2); rc = (r + 1) * RW + (side == 0 ? 0 : TX + 1); sg = (r + 1) * GW + (side == 0 ? 1 : TX + 2);
-      exw = r * (TX + 1) + (side == 0 ? 0 : TX); exr = r * (TX + 1) + TX;
-    } else if (wid != W_C) {          // high (W_JH) and low (W_JL) j rows next to the tile
+      if (lane < 2 * TY) { exw = r * (TX + 1) + (side == 0 ? 0 : TX); exr = r * (TX + 1) + TX; }
+    } else {                          // high (W_JH) and low (W_JL) j rows next to the tile
       const bool high = wid == W_JH;
       d = 1; i = i0 + lane; j = high ? j0 + TY : j0 - 1;
-      rec = (i <= Ly.imx - 1) && (j <= Ly.jmx);
+      rec = SMQ || ((i <= Ly.imx - 1) && (j <= Ly.jmx));
       fac = rec && high; wr_hi = !high;
       s0 = (high ? TY + 2 : 1) * PW + lane + 2; rc = (high ? TY + 1 : 0) * RW + lane + 1; sg = (high ? TY + 1 : 0) * GW + lane + 2;
       exw = SLOT_I + (high ? TY * TX : 0) + lane; exr = SLOT_I + TY * TX + lane;
     }
     if (i > Ly.imx + 1) i = Ly.imx + 1;
     if (j > Ly.jmx + 1) j = Ly.jmx + 1;
+    (void)rc; (void)sg;
+    row = s0 / PW;               // rc = s0 - 2 row - (PW - 1), sg = s0 - PW
+    rw_ij = (unsigned)i | ((unsigned)j << 16);
+    rw_sx = (unsigned)s0 | ((unsigned)exw << 10) | ((unsigned)exr << 20);
+    rw_fl = (rec ? 1u : 0u) | (fac ? 2u : 0u) | (wr_hi ? 4u : 0u) | (irow ? 8u : 0u) | (krow ? 16u : 0u) | ((unsigned)d << 5) | ((unsigned)row << 8);
   }
-  const int pos = (d == 0) ? i : j, mx = (d == 0) ? Ly.imx : ((d == 1) ? Ly.jmx : Ly.kmx);
-  const int dq = (d == 0) ? 1 : PW, dr = (d == 0) ? 1 : RW, dg = (d == 0) ? 1 : GW;   // low neighbour along d (I / J warps)
+  const bool krow = (wid >= W_K0) && (wid < W_IH), irow = wid < TY;   // warp-uniform forms, for the control flow outside the flux code
 
   // ---- phase 2, gradient task of the 34 x 6 cells of tile + ring of plane p (warps 0..NGW-1), in two steps around named barrier 3 ------
-  const int gt = wid * 32 + lane;                 // gradient cell of this thread
-  const int g_row = gt / RW, g_col = gt - g_row * RW;
-  const int gi = i0 - 1 + g_col, gj = j0 - 1 + g_row;
-  const bool g_valid = VISC && gt < NRC && gi <= Ly.imx && gj <= Ly.jmx;
-  const int g_sq = (g_row + 1) * PW + g_col + 1, g_sg = g_row * GW + g_col + 1;
-  auto grad_gauss = [&](int p) {
+  const int gt = tid;                             // gradient cell of this thread
+  unsigned rw_g;                                  // row | col << 8 | valid << 16
+  {
+    const int g_row_ = gt / RW, g_col_ = gt - g_row_ * RW;
+    const bool v_ = VISC && gt < NRC && (i0 - 1 + g_col_) <= Ly.imx && (j0 - 1 + g_row_) <= Ly.jmx;
+    rw_g = (unsigned)g_row_ | ((unsigned)g_col_ << 8) | (v_ ? 0x10000u : 0u);
+  }
+  int g_row, g_col, gi, gj, g_sq, g_sg;
+  bool g_valid;
+  auto unpack_g = [&]() {
+    unsigned w_ = rw_g;
+    asm volatile("" : "+r"(w_));
+    g_row = w_ & 0xff; g_col = (w_ >> 8) & 0xff; g_valid = (w_ >> 16) != 0;
+    gi = i0 - 1 + g_col; gj = j0 - 1 + g_row;
+    g_sq = (g_row + 1) * PW + g_col + 1; g_sg = g_row * GW + g_col + 1;
+  };
+  auto grad_gauss = [&](int p, const GradW& gw) {
     if constexpr (VISC) {
       if (g_valid)
-        gradient_record<NV>(P, a, smem + q_off(p - 1), smem + q_off(p), smem + q_off(p + 1), g_sq, smem[g_off(p) + g_sg], Ly.idx(gi, gj, p),
+        gradient_record<NV>(P, a, smem + q_off(p - 1), smem + q_off(p), smem + q_off(p + 1), g_sq, smem[g_off(p) + g_sg], Ly.idx(gi, gj, p), gw,
                             smem + r_off(p) + gt * RP);
     }
   };
@@ -722,13 +799,22 @@ __global__ void __launch_bounds__(NT, 1) k_fused(const Params P, const KArgs a, 
   // The march starts two iterations early: iteration kb-3 only computes the records of plane kb-1, iteration kb-2 those of plane kb
   // and the K rows' value at the high face of cell kb-1 (no face yet); from kb-1 on the K rows evaluate the face between planes k
   // and k+1, from kb on everything runs.  One instance of every piece of code, no separate prologue.
+  PT_DECL
   for (int k = kb - 3; k <= ke - 1; ++k) {
     // =========================== phase 1: one reconstruction and one face per thread ====================================================
-    const bool active = (wid != W_C) && (krow ? k >= kb - 2 : k >= kb);
+    const bool active = krow ? k >= kb - 2 : k >= kb;
     if (active) {
-      // I/J: cell (i,j,k), face below it along d.  K: cell (i,j,k+1), face between planes k and k+1.
-      if (k == kb - 2) { wait_q(k); wait_q(k + 1); }
-      wait_q(k + 2); wait_g(k + 1);   // the newest planes this phase may touch (complete long ago; the wait orders the TMA writes)
+      unsigned w_ij = rw_ij, w_sx = rw_sx, w_fl = rw_fl;
+      asm volatile("" : "+r"(w_ij), "+r"(w_sx), "+r"(w_fl));
+      const int i = w_ij & 0xffff, j = w_ij >> 16;
+      const int s0 = w_sx & 0x3ff, exw = (w_sx >> 10) & 0x3ff, exr = w_sx >> 20;
+      const bool rec = w_fl & 1, fac = w_fl & 2, wr_hi = w_fl & 4;
+      const int d = (w_fl >> 5) & 3, row = w_fl >> 8;
+      const int rc = s0 - 2 * row - (PW - 1), sg = s0 - PW;
+      const int pos = (d == 0) ? i : j, mx = (d == 0) ? Ly.imx : ((d == 1) ? Ly.jmx : Ly.kmx);
+      const int dq = (d == 0) ? 1 : PW, dr = (d == 0) ? 1 : RW, dg = (d == 0) ? 1 : GW;   // low neighbour along d (I / J warps)
+      // I/J: cell (i,j,k), face below it along d.  K: cell (i,j,k+1), face between planes k and k+1.  The planes this phase reads
+      // landed long ago: the threads of phase 2 waited on their mbarriers, and two CTA barriers lie in between.
       const bool fac_k = fac && k >= kb - 1;   // no face in the priming iteration of the K rows
       const int oqA = q_off(k), oqB = q_off(k + 1);
       const int o_0 = (krow ? oqB : oqA) + s0;                                   // the cell (q field 0)
@@ -746,13 +832,11 @@ __global__ void __launch_bounds__(NT, 1) k_fused(const Params P, const KArgs a, 
         const double* __restrict__ gp = a.geom + (long long)(G_IA + 4 * d) * fs + cg;
         gA_ = gp[0]; gnx = gp[fs]; gny = gp[2 * fs]; gnz = gp[3 * fs];
       }
-      double Lk[8];
-      if (krow) tm_ld8(tbase + 2 * T_HI, Lk);   // value at the high face of cell k, left by the previous iteration
-      double lo[NV], hi[8];
+      double lo[NV], hv[8];
 #pragma unroll
-      for (int v = 0; v < 8; ++v) hi[v] = 0.0;
+      for (int v = 0; v < 8; ++v) hv[v] = 0.0;
       if (rec) {
-        double hv[NV];
+        double hv_[NV];
         if (SMQ) {
           double qm[NV], q0[NV], qp[NV];
 #pragma unroll
@@ -762,58 +846,60 @@ __global__ void __launch_bounds__(NT, 1) k_fused(const Params P, const KArgs a, 
             const int two = (cpos == 0) ? 2 : -2;
             p_far = krow ? q[4 * fs + cg + two * Ly.sk] : smem[o_0 + 4 * PSQ + two * dq];
           }
-          recon3<NV, INTERP, RARE>(P, qm, q0, qp, cpos, mx, d, hv, lo, p_far);
+          recon3<NV, INTERP, RARE>(P, qm, q0, qp, cpos, mx, d, hv_, lo, p_far);
         } else {
-          line_cell_values<NV, INTERP, RARE>(P, q, vol, cg, (d == 0) ? 1 : ((d == 1) ? Ly.sj : Ly.sk), cpos, mx, d, hv, lo);
+          line_cell_values<NV, INTERP, RARE>(P, q, vol, cg, (d == 0) ? 1 : ((d == 1) ? Ly.sj : Ly.sk), cpos, mx, d, hv_, lo);
         }
-        if (!krow) {
-          if (wr_hi) {
 #pragma unroll
-            for (int v = 0; v < NV; ++v) smem[S::OFF_X + v * EX + exw] = hv[v];
-          }
-        } else {
+        for (int v = 0; v < NV; ++v) hv[v] = hv_[v];
+        if (!krow && wr_hi) {
 #pragma unroll
-          for (int v = 0; v < NV; ++v) hi[v] = hv[v];
+          for (int v = 0; v < NV; ++v) smem[S::OFF_X + v * EXP + exw] = hv[v];
         }
       }
-      if (krow) tm_st8(tbase + 2 * T_HI, hi);
-      else bar_group(1 + d, (d == 0) ? N_IGRP : N_JGRP);
-      double Fo[10];
+      double L[8];
+      if (krow) {   // warp-uniform: L = value at the high face of cell k (left by the previous iteration), then this iteration's one
+        tm_ld8(tbase + 2 * T_HI, L);
+        tm_st8(tbase + 2 * T_HI, hv);
+      } else {
+        bar_group(1 + d, (d == 0) ? N_IGRP : N_JGRP);
+      }
+      double F[10];
 #pragma unroll
-      for (int v = 0; v < 10; ++v) Fo[v] = 0.0;
+      for (int v = 0; v < 10; ++v) F[v] = 0.0;
       if (fac_k) {
-        double L[NV], F[NV], lam = 0.0, vis = 0.0, tur = 0.0;
+        double Lf[NV], Ff[NV], lam = 0.0, vis = 0.0, tur = 0.0;
         if (krow) {
 #pragma unroll
-          for (int v = 0; v < NV; ++v) L[v] = Lk[v];
+          for (int v = 0; v < NV; ++v) Lf[v] = L[v];
         } else {
 #pragma unroll
-          for (int v = 0; v < NV; ++v) L[v] = smem[S::OFF_X + v * EX + exr];
+          for (int v = 0; v < NV; ++v) Lf[v] = smem[S::OFF_X + v * EXP + exr];
         }
-        face_eval4<NV, SCHEME, VISC, RP>(P, d, smem + o_m, smem + o_0, smem + r_l, smem + r_h, smem + g_l, smem + g_h, gA_, gnx, gny, gnz, cpos, mx, L, lo,
-                                         krow ? flux_on_k : true, need_dt, F, lam, vis, tur);
+        face_eval4<NV, SCHEME, VISC, RP>(P, d, smem + o_m, smem + o_0, smem + r_l, smem + r_h, smem + g_l, smem + g_h, gA_, gnx, gny, gnz, cpos, mx, Lf, lo,
+                                         krow ? flux_on_k : true, need_dt, Ff, lam, vis, tur);
         if (krow) {
 #pragma unroll
-          for (int v = 0; v < NV; ++v) Fo[v] = F[v];
-          Fo[NV] = lam; Fo[NV + 1] = vis; Fo[NV + 2] = tur;
+          for (int v = 0; v < NV; ++v) F[v] = Ff[v];
+          F[NV] = lam; F[NV + 1] = vis; F[NV + 2] = tur;
         } else {
 #pragma unroll
-          for (int v = 0; v < NV; ++v) smem[S::OFF_X + v * EX + exr] = F[v];
+          for (int v = 0; v < NV; ++v) smem[S::OFF_X + v * EXP + exr] = Ff[v];
           if (need_dt) {
-            smem[S::OFF_X + NV * EX + exr] = lam;
-            if (VISC) smem[S::OFF_X + (NV + 1) * EX + exr] = vis;
-            if (VISC && TURB) smem[S::OFF_X + (NV + 2) * EX + exr] = tur;
+            smem[S::OFF_X + NV * EXP + exr] = lam;
+            if (VISC) smem[S::OFF_X + (NV + 1) * EXP + exr] = vis;
+            if (VISC && TURB) smem[S::OFF_X + (NV + 2) * EXP + exr] = tur;
           }
         }
       }
       if (krow) {   // flux of the k face below plane k+1 into its half of the ring
         const unsigned ta = tbase + 2 * (T_FK + 10 * ((k + 1) & 1));
-        tm_st8(ta, Fo);
-        if (NF > 8) tm_st2(ta + 16, Fo[8], Fo[9]);
+        tm_st8(ta, F);
+        if (NF > 8) tm_st2(ta + 16, F[8], F[9]);
       }
       if (irow) {   // I rows: the cell packet of the own cell for the cell work of phase 2
         double pkv[6] = {0., 0., 0., 0., 0., 0.};
-        if (rec && i <= Ly.imx - 1) {
+        if (rec && (SMQ || i <= Ly.imx - 1)) {
           const double* const rA = smem + r_h;   // own record
           const double* const qA = smem + o_0;
           const double volc = smem[g_h];
@@ -920,41 +1006,60 @@ __global__ void __launch_bounds__(NT, 1) k_fused(const Params P, const KArgs a, 
         if (SA) tm_st1(tbase + 2 * (T_PK + 4), pkv[4]);
       }
     }
+    const bool grad_now = VISC && wid < NGW && k + 2 <= ke;
     tm_wait_st();
     tm_fence_before();
+    PT_MARK(0)
     bar_all();   // ---- the fluxes, packets and k faces of plane k are complete; nobody reads q plane k / geometry plane k any more
     tm_fence_after();
+    PT_MARK(1)
 
     // =========================== phase 2: records of plane k+2 | cell work of plane k ===================================================
     if (tid == NT - 1) {   // into the slots of q plane k and geometry plane k
       if (k + 4 <= ke + 1) issue_q(k + 4);
       if (k + 3 <= ke) issue_g(k + 3);
     }
-    if (VISC && wid < NGW && k + 2 <= ke) {
+    if (grad_now) {
+      if constexpr (VISC) {
+        unpack_g();
+        GradW gw;
+        if (g_valid) gradient_weights(a, Ly, Ly.idx(gi, gj, k + 2), gw);   // L2 hits: prefetched by the previous iteration's task
+        if (k == kb - 3) { wait_q(k + 1); wait_q(k + 2); }
+        wait_q(k + 3); wait_g(k + 2);
+        grad_gauss(k + 2, gw);
+        bar_group(3, 32 * NGW);
+        grad_ghost(k + 2);
+        if (g_valid && k + 3 <= ke) gradient_prefetch(a, Ly, Ly.idx(gi, gj, k + 3));   // next plane's face metrics on their way to L2
+      }
+    } else if (wid == W_OBS && k + 2 <= ke + 1) {
+      // inviscid runs have no gradient task: one warp observes the arrival of the planes for everybody (the barrier below orders it)
       if (k == kb - 3) { wait_q(k + 1); wait_q(k + 2); }
-      wait_q(k + 3); wait_g(k + 2);
-      grad_gauss(k + 2);
-      bar_group(3, 32 * NGW);
-      grad_ghost(k + 2);
+      if (k + 3 <= ke + 1) wait_q(k + 3);
+      if (k + 2 <= ke) wait_g(k + 2);
     }
-    if (wid >= W_IH && k >= kb) {   // cell work of row r = wid - 12 (the warp shares the lane quarter of the row's I / J / K warps)
-      const int r = wid - W_IH, ic = i0 + lane, jc = j0 + r;
+    const int crow = cell_row_of_warp(wid);
+    if (crow >= 0 && k >= kb) {   // cell work of row crow (the warp shares the lane quarter of the row's I / J / K warps)
+      const int r = crow, ic = i0 + lane, jc = j0 + r;
       double Flo[16], Fhi[16], pn[16];
-      tm_ld16(tbase + 2 * (T_FK + 10 * (k & 1)), Flo);          // k face below plane k
-      tm_ld16(tbase + 2 * (T_FK + 10 * ((k + 1) & 1)), Fhi);    // and above it
-      tm_ld16(tbase + 2 * T_PK, pn);                            // cell packet [0..5], norm partials [6..13]
+      tm_ld16_3(tbase + 2 * (T_FK + 10 * (k & 1)), Flo,          // k face below plane k
+                tbase + 2 * (T_FK + 10 * ((k + 1) & 1)), Fhi,    // and above it
+                tbase + 2 * T_PK, pn);                           // cell packet [0..5], norm partials [6..13]
       if (ic <= Ly.imx - 1 && jc <= Ly.jmx - 1)
         cell_work4<NV, VISC>(P, a, smem + S::OFF_X, lane, r, ic, jc, k, need_dt, k_active, Flo, Fhi, pn, pn + (T_NRM - T_PK));
       if (a.want_norms) { tm_st8(tbase + 2 * T_NRM, pn + (T_NRM - T_PK)); tm_wait_st(); }
     }
     tm_fence_before();
+    PT_MARK(2)
     bar_all();   // ---- records of plane k+2 are complete; the exchange area and the packets are free again
     tm_fence_after();
+    PT_MARK(3)
   }
+  PT_FLUSH
 
   if (a.want_norms) {   // per-CTA partial: warp shuffle inside the four warps that did the cell work, then across them
     double* const sred = smem + S::OFF_RED;   // [NV+1][4]
-    if (wid >= W_IH) {
+    const int crow = cell_row_of_warp(wid);
+    if (crow >= 0) {
       double x[8];
       tm_ld8(tbase + 2 * T_NRM, x);
 #pragma unroll
@@ -964,7 +1069,7 @@ __global__ void __launch_bounds__(NT, 1) k_fused(const Params P, const KArgs a, 
       }
       if (lane == 0) {
 #pragma unroll
-        for (int v = 0; v <= NV; ++v) sred[v * 4 + (wid - W_IH)] = x[v];
+        for (int v = 0; v <= NV; ++v) sred[v * 4 + crow] = x[v];
       }
     }
     bar_all();

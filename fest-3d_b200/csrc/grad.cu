@@ -177,6 +177,15 @@ __global__ void k_gradient_bc(const Params P, const double* __restrict__ q, cons
 
 int launch_gradients(Ctx* ctx) {
   const Layout& L = ctx->P.L;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (ctx->timing) {
+    if (ctx->ev_used2 == ctx->ev_pool2.size()) {
+      cudaEvent_t x, y; cudaEventCreate(&x); cudaEventCreate(&y);
+      ctx->ev_pool2.emplace_back(x, y);
+    }
+    e0 = ctx->ev_pool2[ctx->ev_used2].first; e1 = ctx->ev_pool2[ctx->ev_used2].second; ctx->ev_used2++;
+    cudaEventRecord(e0, ctx->stream);
+  }
   dim3 block(32, 4, 1);
   dim3 grid((L.imx + 1 + G_ALIGN + 31) / 32, (L.jmx + 1 + 3) / 4, L.kmx + 1);
   if (ctx->P.sa) k_gradients<5><<<grid, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->err_dev);
@@ -199,6 +208,7 @@ int launch_gradients(Ctx* ctx) {
     else k_gradient_bc<4><<<g2, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->gbc, ctx->gbc_off_dev, mask);
     ctx->launches++;
   }
+  if (ctx->timing) cudaEventRecord(e1, ctx->stream);
   F3D_CUDA(cudaGetLastError());
   return 0;
 }

@@ -204,13 +204,20 @@ __device__ __forceinline__ void cell_face_values(const double* q, const double* 
 // Boundary re-reconstruction of the first/last interior cell (boundary_state_reconstruction.f90:93-123):
 // third-order MUSCL with the *unguarded* ratio fd/bd.  Fortran min/max with a NaN operand are taken with
 // fmin/fmax semantics (0/0 on a uniform field picks the finite operand).
+// The quotient of the unguarded ratios with the IEEE results the reference relies on for a vanishing divisor (x/0 = +-inf, 0/0 = NaN;
+// a difference of two equal numbers is +0), and the fast reciprocal elsewhere (<= 2 ulp): no slow-path call in the kernel.
+__device__ __forceinline__ double ratio_ieee0(double a, double b) {
+  const double r = a * rcp64(b);
+  const double z = (a == 0.0) ? __longlong_as_double(0x7ff8000000000000LL) : copysign(__longlong_as_double(0x7ff0000000000000LL), a);
+  return (b == 0.0) ? z : r;
+}
 __device__ __forceinline__ void boundary_cell_face_values(double qm1, double q0, double qp1, int limiter, double& to_hi, double& to_lo) {
   const double fd = qp1 - q0, bd = q0 - qm1;
-  double r = fd / bd;
-  double psi1 = fmax(0., fmin(fmin(2 * r, (2 + r) / 3.), 2.));
+  double r = ratio_ieee0(fd, bd);
+  double psi1 = fmax(0., fmin(fmin(2 * r, (2 + r) * (1. / 3.)), 2.));
   psi1 = (1 - (1 - psi1) * limiter);
-  r = bd / fd;
-  double psi2 = fmax(0., fmin(fmin(2 * r, (2 + r) / 3.), 2.));
+  r = ratio_ieee0(bd, fd);
+  double psi2 = fmax(0., fmin(fmin(2 * r, (2 + r) * (1. / 3.)), 2.));
   psi2 = (1 - (1 - psi2) * limiter);
   const double kappa = 1. / 3.;
   to_hi = q0 + 0.25 * (((1. - kappa) * psi1 * bd) + ((1. + kappa) * psi2 * fd));

@@ -26,8 +26,10 @@ __global__ void k_norm_final(const double* __restrict__ red, int n_cta, int nvp1
 
 int fused_grid_ctas(const Layout& L);
 int launch_fused(Ctx* ctx, KArgs& a);
+int sweep3_grid_ctas(const Layout& L);
+int launch_sweep3(Ctx* ctx, KArgs& a);
 
-int residual_grid_ctas(const Layout& L) { return fused_grid_ctas(L); }   // one norm partial per CTA of the sweep
+int residual_grid_ctas(const Layout& L) { const int a_ = fused_grid_ctas(L), b_ = sweep3_grid_ctas(L); return a_ > b_ ? a_ : b_; }   // one norm partial per CTA of the sweep
 
 int launch_residual(Ctx* ctx, int mode, double TF, double SF, int use_store_sum, int first_stage, int want_norms) {
   KArgs a{};
@@ -39,6 +41,8 @@ int launch_residual(Ctx* ctx, int mode, double TF, double SF, int use_store_sum,
   a.rstore = (mode == MODE_UPDATE && have_store) ? ctx->rstore : nullptr;
   a.dt = ctx->dt;
   a.geom = ctx->geom;
+  a.grad = ctx->grad;
+  a.mu = ctx->mu;
   a.gbc = ctx->gbc;
   for (int f = 0; f < 6; ++f) a.gbc_off[f] = ctx->gbc_off[f];
   a.red = ctx->red;
@@ -56,7 +60,7 @@ int launch_residual(Ctx* ctx, int mode, double TF, double SF, int use_store_sum,
     e0 = ctx->ev_pool[ctx->ev_used].first; e1 = ctx->ev_pool[ctx->ev_used].second; ctx->ev_used++;
     cudaEventRecord(e0, ctx->stream);
   }
-  const int rc = launch_fused(ctx, a);
+  const int rc = ctx->fused ? launch_fused(ctx, a) : launch_sweep3(ctx, a);
   if (ctx->timing) cudaEventRecord(e1, ctx->stream);
   if (rc) return rc;
   F3D_CUDA(cudaGetLastError());

@@ -42,6 +42,8 @@ struct KArgs {
   double* __restrict__ rstore;        // nv fields or nullptr
   double* __restrict__ dt;            // 1 field
   const double* __restrict__ geom;
+  const double* __restrict__ grad;    // staged-gradient path only (sweep3_kernel.cuh)
+  const double* __restrict__ mu;      //   mu, mu_t, F1 + centre copy
   const double* __restrict__ gbc;     // face records (A, nx, ny, nz) of the ghost-gradient rule, six faces back to back
   long long gbc_off[6];               // offset of every face's records inside gbc
   double* __restrict__ red;           // per-CTA partials [(nv+1) * n_cta]
@@ -124,69 +126,62 @@ __device__ __forceinline__ double koren_psi(double r) {
 #endif
 }
 
-// Koren-limited kappa = 1/3 MUSCL values of variables [V0, V1) of one cell (muscl.f90:161-196), branch-free inside the
-// variable loop so that the V1-V0 independent dependency chains interleave (a DFMA has 8.4 cycles of latency and the
-// pipe takes one every 2.1: profiles/r01_fp64_ops_microbench.txt)
-template <int NV, int V0, int V1>
-__device__ __forceinline__ void muscl_group(const double (&qm)[NV], const double (&q0)[NV], const double (&qp)[NV], int lim, double (&to_hi)[NV],
-                                            double (&to_lo)[NV]) {
+// Koren-limited kappa = 1/3 MUSCL values of all variables of one cell (muscl.f90:161-196): ONE branch-free loop, so that the NV
+// independent dependency chains interleave (a DFMA has 8.4 cycles of latency and the pipe takes one every 2.1:
+// profiles/r01_fp64_ops_microbench.txt) and the code exists once.  The limiter switches (0 / 1 per direction, flow and turbulence
+// variables separately) select between psi and 1: the reference's 1 - (1 - psi)*switch is psi to within an ulp for switch = 1 and
+// exactly 1 for switch = 0.
+template <int NV>
+__device__ __forceinline__ void muscl_all(const double (&qm)[NV], const double (&q0)[NV], const double (&qp)[NV], int lim, int tlim, double (&to_hi)[NV],
+                                          double (&to_lo)[NV]) {
   // q0 +- 0.25*((1 -+ kappa) psi1 bd + (1 +- kappa) psi2 fd) with the constant factors folded: ca = 0.25 (1 - kappa),
   // cb = 0.25 (1 + kappa), and the two limited differences p1 = psi1 bd, p2 = psi2 fd shared by both faces
   const double kappa = 1. / 3.;
   const double ca = 0.25 * (1. - kappa), cb = 0.25 * (1. + kappa);
-  if (lim == 0) {   // psi = 1 - (1 - psi)*0 = 1 exactly
 #pragma unroll
-    for (int v = V0; v < V1; ++v) {
-      const double fd = qp[v] - q0[v], bd = q0[v] - qm[v];
-      to_hi[v] = fma(ca, bd, fma(cb, fd, q0[v]));
-      to_lo[v] = fma(-cb, bd, fma(-ca, fd, q0[v]));
-    }
-  } else {
-#pragma unroll
-    for (int v = V0; v < V1; ++v) {
-      const double fd = qp[v] - q0[v], bd = q0[v] - qm[v];
-      // x + sign(1e-14, x) written as sign(|x| + 1e-14, x): the same value bit for bit, but the constant comes from the constant
-      // bank as an operand instead of being built in two registers per use (562 register moves per cell-warp, ncu)
-      double psi1 = koren_psi(fd * rcp64(copysign(fabs(bd) + 1e-14, bd)));
-      double psi2 = koren_psi(bd * rcp64(copysign(fabs(fd) + 1e-14, fd)));
-      if (lim != 1) {   // 1 - (1 - psi)*1 is psi to within an ulp; the general switch value keeps the reference form
-        psi1 = (1 - (1 - psi1) * lim);
-        psi2 = (1 - (1 - psi2) * lim);
-      }
-      const double p1 = psi1 * bd, p2 = psi2 * fd;
-      to_hi[v] = fma(ca, p1, fma(cb, p2, q0[v]));
-      to_lo[v] = fma(-cb, p1, fma(-ca, p2, q0[v]));
-    }
+  for (int v = 0; v < NV; ++v) {
+    const bool on = ((v >= 5) ? tlim : lim) != 0;
+    const double fd = qp[v] - q0[v], bd = q0[v] - qm[v];
+    // x + sign(1e-14, x) written as sign(|x| + 1e-14, x): the same value bit for bit, but the constant comes from the constant
+    // bank as an operand instead of being built in two registers per use
+    double psi1 = koren_psi(fd * rcp64(copysign(fabs(bd) + 1e-14, bd)));
+    double psi2 = koren_psi(bd * rcp64(copysign(fabs(fd) + 1e-14, fd)));
+    psi1 = on ? psi1 : 1.0;
+    psi2 = on ? psi2 : 1.0;
+    const double p1 = psi1 * bd, p2 = psi2 * fd;
+    to_hi[v] = fma(ca, p1, fma(cb, p2, q0[v]));
+    to_lo[v] = fma(-cb, p1, fma(-ca, p2, q0[v]));
   }
 }
 
 // MUSCL / first-order values of one cell along one direction from three staged values per variable
-// (muscl.f90:161-196; boundary_state_reconstruction.f90:93-123 for the first / last interior cell when ppm_flag is set)
+// (muscl.f90:161-196; boundary_state_reconstruction.f90:93-123 for the first / last interior cell when ppm_flag is set: done as an
+// overwrite AFTER the regular formula, so that the hot path carries no merge of the two)
 template <int NV, int INTERP, bool PB = false>
 __device__ __forceinline__ void recon3(const Params& P, const double (&qm)[NV], const double (&q0)[NV], const double (&qp)[NV], int pos, int mx,
                                        int dir, double (&to_hi)[NV], double (&to_lo)[NV], double p_far = 0.0) {
-  const bool redo = (INTERP != F3D_INTERP_NONE) && P.ppm_flag && ((pos == 1 && P.phys[2 * dir]) || (pos == mx - 1 && P.phys[2 * dir + 1]));
-  if (redo) {
-#pragma unroll
-    for (int v = 0; v < NV; ++v) boundary_cell_face_values(qm[v], q0[v], qp[v], (v >= 5) ? P.tlimiter[dir] : P.limiter[dir], to_hi[v], to_lo[v]);
-  } else if (INTERP == F3D_INTERP_NONE) {
+  if (INTERP == F3D_INTERP_NONE) {
 #pragma unroll
     for (int v = 0; v < NV; ++v) { to_hi[v] = q0[v]; to_lo[v] = q0[v]; }
-  } else {
-    const int lim = P.limiter[dir], tlim = P.tlimiter[dir];
-    if (NV > 5 && tlim == lim) {
-      muscl_group<NV, 0, NV>(qm, q0, qp, lim, to_hi, to_lo);
-    } else {
-      muscl_group<NV, 0, 5>(qm, q0, qp, lim, to_hi, to_lo);
-      if (NV > 5) muscl_group<NV, 5, NV>(qm, q0, qp, tlim, to_hi, to_lo);
-    }
-    if (PB && P.pb_switch[dir]) {   // pressure-based switching (muscl.f90:231-243): both face values are pulled towards the cell value
-      const double pd = pb_pdif(P, qm[4], q0[4], qp[4], p_far, pos, mx);
+    return;
+  }
+  const int lim = P.limiter[dir], tlim = P.tlimiter[dir];
+  muscl_all<NV>(qm, q0, qp, lim, tlim, to_hi, to_lo);
+  if (PB && P.pb_switch[dir]) {   // pressure-based switching (muscl.f90:231-243): both face values are pulled towards the cell value
+    const double pd = pb_pdif(P, qm[4], q0[4], qp[4], p_far, pos, mx);
 #pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        to_hi[v] = q0[v] + (pd * (to_hi[v] - q0[v]));
-        to_lo[v] = q0[v] - (pd * (q0[v] - to_lo[v]));
-      }
+    for (int v = 0; v < NV; ++v) {
+      to_hi[v] = q0[v] + (pd * (to_hi[v] - q0[v]));
+      to_lo[v] = q0[v] - (pd * (q0[v] - to_lo[v]));
+    }
+  }
+  const bool redo = P.ppm_flag && ((pos == 1 && P.phys[2 * dir]) || (pos == mx - 1 && P.phys[2 * dir + 1]));
+  if (redo) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      double h, l;
+      boundary_cell_face_values(qm[v], q0[v], qp[v], (v >= 5) ? tlim : lim, h, l);
+      to_hi[v] = h; to_lo[v] = l;
     }
   }
 }

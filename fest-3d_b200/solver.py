@@ -113,6 +113,19 @@ class GpuBlock:
         self._check(self.L.fest3d_gpu_get_state(self.h, _dp(q)))
         return q
 
+    def set_state_async(self, qp):
+        """Start the upload (qp: C-contiguous float64, ideally pinned) and return; takes effect at the next iterate / residual."""
+        assert qp.flags["C_CONTIGUOUS"] and qp.dtype == np.float64
+        self._check(self.L.fest3d_gpu_set_state_async(self.h, _dp(qp)))
+
+    def get_state_async(self, out):
+        """Snapshot qp in stream order and start its download into `out`; valid after state_wait()."""
+        assert out.flags["C_CONTIGUOUS"] and out.dtype == np.float64
+        self._check(self.L.fest3d_gpu_get_state_async(self.h, _dp(out)))
+
+    def state_wait(self):
+        self._check(self.L.fest3d_gpu_state_wait(self.h))
+
     def setup_geometry(self, grid_nodes, dist=None, want_nodes=False):
         """ghost_grid (grid.f90:137-236) + the metric set-up of geometry.f90:43-545 on the device from the interior nodes
         grid_nodes[kmx, jmx, imx, 3] (the body of the grid file); returns the ghosted node array if asked for."""
@@ -186,14 +199,26 @@ class GpuBlock:
         t = self.L.fest3d_gpu_kernel_time_ms(self.h, C.byref(n), 1 if reset else 0)
         return float(t), int(n.value)
 
+    def gradient_time_ms(self, reset=True):
+        n = C.c_longlong(0)
+        t = self.L.fest3d_gpu_gradient_time_ms(self.h, C.byref(n), 1 if reset else 0)
+        return float(t), int(n.value)
+
+    def gradient_path(self):
+        return "fused" if self.L.fest3d_gpu_gradient_path(self.h) == 1 else "staged"
+
 
 class Solver:
     """The blocks of this process, stepped in lock step (drop-in for the reference's per-iteration calls)."""
 
-    def __init__(self, blocks, devices=None, device_geometry=False):
+    def __init__(self, blocks, devices=None, device_geometry=False, gpu_blocks=None):
         self.L = capi.lib()
-        devices = devices or [0] * len(blocks)
-        self.blocks = [GpuBlock(b, d, device_geometry) for b, d in zip(blocks, devices)]
+        if gpu_blocks is not None:
+            self.blocks = list(gpu_blocks)
+            blocks = [g.blk for g in self.blocks]
+        else:
+            devices = devices or [0] * len(blocks)
+            self.blocks = [GpuBlock(b, d, device_geometry) for b, d in zip(blocks, devices)]
         for i, a in enumerate(self.blocks):
             for b in self.blocks[i:]:      # b is a: a block that is its own (periodic) neighbour
                 ids_a = set(a.blk.bc_id) | set(a.blk.pbc_id)
@@ -203,9 +228,32 @@ class Solver:
         self.current_iter = 1   # control%current_iter after setup (solver.f90:140)
         self._handles = (C.c_void_p * len(self.blocks))(*[b.h for b in self.blocks])
 
+    @classmethod
+    def from_gpu_blocks(cls, gpu_blocks):
+        """Blocks that were created (and uploaded) one at a time, e.g. to drop the host copies of their big arrays in between."""
+        return cls(None, gpu_blocks=gpu_blocks)
+
     def close(self):
         for b in self.blocks:
             b.close()
+
+    def residual_only(self):
+        """get_total_conservative_Residue on every block, nothing copied back (throughput runs of the residual path)."""
+        rc = self.L.fest3d_gpu_residual_group(self._handles, len(self.blocks), self.current_iter)
+        if rc:
+            self.blocks[0]._check(rc)
+
+    def set_states_async(self, qps):
+        for b, q in zip(self.blocks, qps):
+            b.set_state_async(q)
+
+    def get_states_async(self, outs):
+        for b, q in zip(self.blocks, outs):
+            b.get_state_async(q)
+
+    def state_wait(self):
+        for b in self.blocks:
+            b.state_wait()
 
     def init_comm(self, n_ranks, rank, unique_id, block_to_rank):
         arr = (C.c_int * len(block_to_rank))(*block_to_rank)

@@ -109,6 +109,14 @@ int fest3d_gpu_set_geometry(Fest3dGpuCtx* ctx, const double* cells, const double
                             const double* Kfaces, const double* dist /* may be NULL without turbulence */);
 int fest3d_gpu_set_state(Fest3dGpuCtx* ctx, const double* qp);
 int fest3d_gpu_get_state(Fest3dGpuCtx* ctx, double* qp);
+/* Asynchronous, full-duplex forms (pinned host memory gives the overlap): set_state_async starts the upload on a copy stream and
+ * returns -- the state takes effect at the next fest3d_gpu_step / fest3d_gpu_residual call, which is stream-ordered behind it, so the
+ * upload of the next state overlaps the iterations still running and the download of the previous result; get_state_async snapshots
+ * qp in stream order (after every step issued so far) and downloads it on a second copy stream; the host buffers may be reused /
+ * read after fest3d_gpu_state_wait.  The checkpoint host of src/solver.f90:139,186 only needs the outbound one. */
+int fest3d_gpu_set_state_async(Fest3dGpuCtx* ctx, const double* qp);
+int fest3d_gpu_get_state_async(Fest3dGpuCtx* ctx, double* qp);
+int fest3d_gpu_state_wait(Fest3dGpuCtx* ctx);
 /* SURVEY 8(f) rank 1 -- find_wall_dist (src/wall/wall_dist.f90:84-131) on the device: minimum distance of every node
  * nodes(-2:imx+3,-2:jmx+3,-2:kmx+3) (nodetype records x,y,z) to the n_wall surface nodes wall_xyz[n_wall][3] (the contents of
  * the surface-node file, wall_dist.f90:74-82), averaged over the eight nodes of each cell.  Fills the context's wall-distance
@@ -178,6 +186,12 @@ long long fest3d_gpu_launch_count(Fest3dGpuCtx* ctx);
  * Timing is off until fest3d_gpu_kernel_timing(ctx, 1). */
 int fest3d_gpu_kernel_timing(Fest3dGpuCtx* ctx, int enable);
 double fest3d_gpu_kernel_time_ms(Fest3dGpuCtx* ctx, long long* n_launches, int reset);
+/* the same for the Green-Gauss gradient + viscosity kernels of the staged form of the viscous path (0 launches when fused) */
+double fest3d_gpu_gradient_time_ms(Fest3dGpuCtx* ctx, long long* n_launches, int reset);
+/* which form of the viscous path this context runs (environment F3D_GRADIENTS at fest3d_gpu_create): 0 = staged -- gradients and
+ * viscosities by their own kernel into HBM arrays that the sweep stages with TMA (default: the faster one on B200 as measured);
+ * 1 = fused -- computed inside the sweep's tile pass, no gradient / viscosity array in HBM */
+int fest3d_gpu_gradient_path(Fest3dGpuCtx* ctx);
 const char* fest3d_gpu_version(void);
 
 #ifdef __cplusplus

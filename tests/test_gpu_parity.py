@@ -373,6 +373,83 @@ def test_boundary_conditions(pkg, case_mod, oracle, bc, shape, accur):
     s.close()
 
 
+# ---- the fused form of the viscous path (F3D_GRADIENTS=fused: gradients, viscosities and the ghost-gradient rule inside the tile pass,
+# tensor-memory hand-overs) against the oracle: every model, the boundary rules, several blocks, the benchmark's tiling ------------
+@pytest.fixture
+def fused_path(monkeypatch):
+    monkeypatch.setenv("F3D_GRADIENTS", "fused")   # read by fest3d_gpu_create
+
+
+@pytest.mark.parametrize("turbulence,mu_ref,ta", [("sst", None, "RK4"), ("sst2003", None, "none"), ("sa", None, "TVDRK3"), ("none", None, "RK2"), ("none", 0.0, "RK4")])
+def test_fused_path_models_and_integrators(pkg, case_mod, oracle, fused_path, turbulence, mu_ref, ta):
+    import importlib
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    blocks = syn.make_duct_blocks(None, n3=(37, 10, 9), turbulence=turbulence, mu_ref=mu_ref, time_step_accuracy=ta, CFL=0.6)
+    s = _solver(pkg, blocks)
+    _check_residual(oracle, s, blocks)
+    _check_history(oracle, s, blocks, 5)
+    s.close()
+
+
+@pytest.mark.parametrize("scheme_name,interpolant", [("ausm", "muscl"), ("slau", "weno"), ("ausmUP", "ppm"), ("van_leer", "none"), ("ausmP", "weno_NM")])
+def test_fused_path_schemes(pkg, case_mod, oracle, fused_path, scheme_name, interpolant):
+    import importlib
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    blocks = syn.make_duct_blocks(None, n3=(20, 12, 10), scheme_name=scheme_name, interpolant=interpolant, turbulence="sst")
+    s = _solver(pkg, blocks)
+    _check_residual(oracle, s, blocks)
+    s.close()
+
+
+@pytest.mark.parametrize("bc", [[-3, -4, -5, -6, -6, -6], [-8, -4, -7, -6, -9, -9], [-11, -4, -5, -5, -5, -5], [-1, -2, -6, -5, -5, -6]])
+@pytest.mark.parametrize("shape", [(6, 5, 1), (9, 7, 5), (35, 6, 4)])
+def test_fused_path_boundary_conditions(pkg, case_mod, oracle, fused_path, bc, shape):
+    import importlib
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    if (-9 in bc[4:]) and shape[2] < 3:
+        pytest.skip("periodic slab copy needs 3 interior layers")
+    blocks = syn.make_duct_blocks(None, n3=shape, turbulence="sst", time_step_accuracy="RK2", interpolant="muscl")
+    blk = blocks[0]
+    blk.bc_id = list(bc)
+    blk.scheme.accur = 1
+    blk.fixed[7, 2] = 350.0   # isothermal wall at jmin, adiabatic elsewhere
+    fl = blk.flow
+    M2 = fl.x_speed_inf ** 2 / (fl.gm * fl.pressure_inf / fl.density_inf)
+    blk.fixed[8, :] = fl.pressure_inf * (1 + 0.5 * (fl.gm - 1.0) * M2) ** (fl.gm / (fl.gm - 1.0)) * (1.0 + 1e-3 * np.arange(6))
+    blk.build_geometry()
+    s = _solver(pkg, blocks)
+    _check_residual(oracle, s, blocks)
+    _check_history(oracle, s, blocks, 4)
+    s.close()
+
+
+def test_fused_path_reference_cases_and_blocks(pkg, case_mod, oracle, fused_path):
+    import importlib
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    for name, over in (("lfp", dict(scheme_name="slau", interpolant="muscl", time_step_accuracy="RK4")),
+                       ("tfp", dict(scheme_name="ausmUP", interpolant="muscl", time_step_accuracy="RK4"))):
+        blocks = _load_fixture(case_mod, name, scheme=over, control=dict(CFL=0.5))
+        s = _solver(pkg, blocks)
+        _check_residual(oracle, s, blocks)
+        _check_history(oracle, s, blocks, 10)
+        s.close()
+    blocks = syn.make_duct_blocks(None, n3=(10, 8, 6), nb=(2, 2, 2), time_step_accuracy="RK4")
+    s = _solver(pkg, blocks)
+    _check_residual(oracle, s, blocks)
+    _check_history(oracle, s, blocks, 5)
+    s.close()
+
+
+def test_fused_path_at_multi_tile_multi_chunk_size(pkg, case_mod, oracle, fused_path):
+    import importlib
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    blocks = syn.make_duct_blocks(None, n3=(100, 70, 300), turbulence="sst", time_step_accuracy="none", CFL=0.5)
+    s = _solver(pkg, blocks)
+    _check_residual(oracle, s, blocks)
+    _check_history(oracle, s, blocks, 2)
+    s.close()
+
+
 # ---- the reference's own SmoothBump output (tests/SmoothBump/time_directories/0010) under the CUDA path ------------------------
 def test_shipped_smoothbump_output_relaxes_to_the_reported_entropy(pkg, case_mod):
     """Soft pin of the CUDA path on a reference OUTPUT (companion of test_oracle_kat.py::test_soft_pin_on_the_shipped_smoothbump_output):
@@ -508,6 +585,32 @@ def test_async_checkpoint_and_bitwise_restart(pkg, case_mod, tmp_path, tsa, turb
     for b, q in zip(r.blocks, final):
         assert np.array_equal(b.get_state(), q)
     r.close()
+
+
+def test_async_duplex_state_transfers_equal_the_synchronous_ones(pkg, case_mod):
+    """fest3d_gpu_set_state_async / get_state_async / state_wait (copy streams, stream-ordered hand-overs) against set_state /
+    get_state: same states in, same iterations, bitwise the same states and norms out -- also when uploads and downloads of
+    consecutive steps overlap."""
+    import importlib
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    solver = importlib.import_module("fest3d_b200.solver")
+    mk = lambda: syn.make_duct_blocks(None, n3=(33, 12, 9), turbulence="sst", time_step_accuracy="RK2", CFL=0.5)
+    blocks = mk()
+    q0 = blocks[0].qp.copy()
+    q1 = q0 * (1.0 + 1e-3 * np.cos(np.arange(q0.size).reshape(q0.shape) * 0.37))
+    a = solver.Solver(mk()); b = solver.Solver(mk())
+    outs_a, outs_b, hist_a, hist_b = [], [], [], []
+    bufs = [np.empty_like(q0) for _ in range(3)]
+    for n, qin in enumerate((q0, q1, q0)):
+        a.blocks[0].set_state(qin); a.current_iter = 1
+        hist_a.append(a.iterate(2)); outs_a.append(a.blocks[0].get_state().copy())
+        b.blocks[0].set_state_async(np.ascontiguousarray(qin)); b.current_iter = 1
+        hist_b.append(b.iterate(2)); b.blocks[0].get_state_async(bufs[n])     # no wait: the next upload overlaps this download
+    b.state_wait()
+    for n in range(3):
+        assert np.array_equal(hist_a[n], hist_b[n])
+        assert np.array_equal(outs_a[n], bufs[n])
+    a.close(); b.close()
 
 
 def test_restart_rejects_a_foreign_checkpoint(pkg, case_mod, tmp_path):
