@@ -169,8 +169,8 @@ static int create_impl(Fest3dGpuCtx* ctx, const Fest3dGpuConfig* cfg, int device
   F3D_CUDA(cudaMalloc((void**)&ctx->norms_dev, sizeof(double) * (1024 + 64)));
   F3D_CUDA(cudaMemcpyAsync(ctx->norms_dev + 1024, sc, sizeof(double) * 9, cudaMemcpyHostToDevice, ctx->stream));
   F3D_CUDA(cudaMallocHost((void**)&ctx->norms_host, sizeof(double) * 1024));
-  F3D_CUDA(cudaMalloc((void**)&ctx->err_dev, sizeof(int) * 4));
-  F3D_CUDA(cudaMemsetAsync(ctx->err_dev, 0, sizeof(int) * 4, ctx->stream));
+  F3D_CUDA(cudaMalloc((void**)&ctx->err_dev, sizeof(int) * 8));
+  F3D_CUDA(cudaMemsetAsync(ctx->err_dev, 0, sizeof(int) * 8, ctx->stream));
   F3D_CUDA(cudaMallocHost((void**)&ctx->err_host, sizeof(int) * 4));
   {   // 4-D tensor maps [field][k][j][i] (pitches fs, sk, sj) of the arrays the sweep stages; box = one tile plane of all fields
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -239,6 +239,7 @@ extern "C" int fest3d_gpu_destroy(Fest3dGpuCtx* ctx) {
   for (double* b : bufs) if (b) cudaFree(b);
   for (int f = 0; f < 6; ++f) { if (ctx->sendbuf[f]) cudaFree(ctx->sendbuf[f]); if (ctx->recvbuf[f]) cudaFree(ctx->recvbuf[f]); }
   if (ctx->err_dev) cudaFree(ctx->err_dev);
+  for (auto& g : ctx->graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
   if (ctx->gbc_off_dev) cudaFree(ctx->gbc_off_dev);
   if (ctx->norms_host) cudaFreeHost(ctx->norms_host);
   if (ctx->err_host) cudaFreeHost(ctx->err_host);
@@ -794,6 +795,152 @@ extern "C" int fest3d_gpu_residual(Fest3dGpuCtx* ctx, int current_iter, double* 
   return rc;
 }
 
+namespace {
+
+// one iteration of get_next_solution on every context (update.f90:129-226) + the norm assembly launch of find_resnorm
+int issue_iteration(Fest3dGpuCtx** cs, int n, int ta, int iter) {
+  int rc = 0;
+  for (int c = 0; c < n; ++c) {
+    Fest3dGpuCtx* ctx = cs[c];
+    F3D_CUDA(cudaSetDevice(ctx->device));
+    ctx->P.current_iter = iter;
+    if ((rc = launch_temp(ctx))) return rc;   // update.f90:170
+    if (ta != F3D_T_NONE && (rc = launch_copy_fields(ctx, ctx->ustore, ctx->qp, ctx->P.L.nv))) return rc;       // U_store = qp
+    if ((ta == F3D_T_RK2 || ta == F3D_T_RK4) && (rc = launch_zero_fields(ctx, ctx->rstore, ctx->P.L.nv))) return rc;  // R_store = 0
+  }
+  auto blend_all = [&](double a, double b) { for (int c = 0; c < n && !rc; ++c) { cudaSetDevice(cs[c]->device); rc = launch_blend(cs[c], a, b); } return rc; };
+  switch (ta) {   // update.f90:171-215
+    case F3D_T_NONE:
+      rc = stage(cs, n, true, 1., 1., 0, 1, 1); break;
+    case F3D_T_RK4:
+      if ((rc = stage(cs, n, true, 0.5, 1., 0, 1, 0))) break;
+      if ((rc = stage(cs, n, true, 0.5, 2., 0, 0, 0))) break;
+      if ((rc = stage(cs, n, true, 1.0, 2., 0, 0, 0))) break;
+      rc = stage(cs, n, true, 1. / 6., 1., 1, 0, 1); break;
+    case F3D_T_RK2:
+      if ((rc = stage(cs, n, true, 0.5, 1., 0, 1, 0))) break;
+      rc = stage(cs, n, true, 0.5, 1., 1, 0, 1); break;
+    case F3D_T_TVDRK3:
+      if ((rc = stage(cs, n, true, 1.0, 1., 0, 1, 0))) break;
+      if ((rc = stage(cs, n, true, 1.0, 1., 0, 0, 0))) break;
+      if ((rc = blend_all(0.75, 0.25))) break;
+      if ((rc = stage(cs, n, true, 1.0, 1., 0, 0, 1))) break;
+      rc = blend_all((1. / 3.), (2. / 3.)); break;
+    case F3D_T_TVDRK2:
+      if ((rc = stage(cs, n, true, 1.0, 1., 0, 1, 0))) break;
+      if ((rc = stage(cs, n, true, 1.0, 1., 0, 0, 1))) break;
+      rc = blend_all(0.5, 0.5); break;
+    default: rc = F3D_ERR_UNSUPPORTED;
+  }
+  if (rc) return rc;
+  for (int c = 0; c < n; ++c) { cudaSetDevice(cs[c]->device); if ((rc = launch_norms(cs[c]))) return rc; }
+  return 0;
+}
+
+// CUDA graph of one iteration.  Small blocks are launch-bound (the SmoothBump case: ~45 launches of a few microseconds of work per
+// RK4 iteration), so from the third iteration on (the fixed-value boundary conditions stop changing with current_iter then,
+// bc_primitive.f90:236) the whole iteration -- every stage of every context, their streams forked from and joined to the first
+// context's stream -- is captured once per buffer parity and replayed.  Not used with NCCL links (their host-side grouping),
+// with kernel timing, or across devices; F3D_GRAPHS=0 turns it off.
+bool graphs_allowed(Fest3dGpuCtx** cs, int n) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("F3D_GRAPHS"); on = (e && e[0] == '0') ? 0 : 1; }
+  if (!on) return false;
+  for (int c = 0; c < n; ++c) {
+    if (cs[c]->timing || cs[c]->device != cs[0]->device) return false;
+    for (int f = 0; f < 6; ++f) {
+      const Link& lk = cs[c]->link[f];
+      if (lk.kind == 2) return false;
+      if (lk.kind == 1) {   // every local neighbour must be part of this group (its stream is forked into the capture)
+        bool in = false;
+        for (int d = 0; d < n; ++d) in |= cs[d] == lk.peer;
+        if (!in) return false;
+      }
+    }
+  }
+  return true;
+}
+
+// the graph runs on the first context's stream: everything queued on the other contexts' streams goes before it ...
+int graph_join_before(Fest3dGpuCtx** cs, int n) {
+  for (int c = 1; c < n; ++c) {
+    F3D_CUDA_RC(cudaEventRecord(cs[c]->ev_halo, cs[c]->stream));
+    F3D_CUDA_RC(cudaStreamWaitEvent(cs[0]->stream, cs[c]->ev_halo, 0));
+  }
+  return 0;
+}
+// ... and whatever is queued on them afterwards (norm download, the next direct iteration) comes after it
+int graph_fork_after(Fest3dGpuCtx** cs, int n) {
+  if (n > 1) F3D_CUDA_RC(cudaEventRecord(cs[0]->ev_pack, cs[0]->stream));
+  for (int c = 1; c < n; ++c) F3D_CUDA_RC(cudaStreamWaitEvent(cs[c]->stream, cs[0]->ev_pack, 0));
+  return 0;
+}
+
+int run_iteration_graph(Fest3dGpuCtx** cs, int n, int ta, int iter, bool* used) {
+  *used = false;
+  Fest3dGpuCtx* c0 = cs[0];
+  unsigned long long key = 1469598103934665603ULL;
+  auto mix = [&](unsigned long long v) { key = (key ^ v) * 1099511628211ULL; };
+  mix((unsigned long long)n); mix((unsigned long long)ta);
+  for (int c = 0; c < n; ++c) { mix((unsigned long long)(uintptr_t)cs[c]); mix((unsigned long long)(uintptr_t)cs[c]->qp); mix((unsigned long long)(uintptr_t)cs[c]->stream); }
+  auto it = c0->graphs.find(key);
+  if (it == c0->graphs.end()) {
+    // capture.  Host-side state the issue path advances (buffer swaps, launch counters) is advanced by the capture pass itself.
+    std::vector<double*> q0(n), q1(n);
+    std::vector<long long> l0(n);
+    for (int c = 0; c < n; ++c) { q0[c] = cs[c]->qp; q1[c] = cs[c]->qp2; l0[c] = cs[c]->launches; }
+    cudaSetDevice(c0->device);
+    if (cudaStreamBeginCapture(c0->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); return 0; }
+    bool ok = true;
+    for (int c = 1; c < n && ok; ++c) {
+      ok = cudaEventRecord(c0->ev_pack, c0->stream) == cudaSuccess && cudaStreamWaitEvent(cs[c]->stream, c0->ev_pack, 0) == cudaSuccess;
+    }
+    // every event the exchange waits on must have been recorded inside the capture (the first stage would otherwise wait on the
+    // previous iteration's, across the capture boundary)
+    for (int c = 0; c < n && ok; ++c)
+      ok = cudaEventRecord(cs[c]->ev_halo, cs[c]->stream) == cudaSuccess && (c == 0 || cudaEventRecord(cs[c]->ev_pack, cs[c]->stream) == cudaSuccess);
+    int rc = ok ? issue_iteration(cs, n, ta, iter) : F3D_ERR_CUDA;
+    for (int c = 1; c < n; ++c) {
+      if (cudaEventRecord(cs[c]->ev_halo, cs[c]->stream) != cudaSuccess || cudaStreamWaitEvent(c0->stream, cs[c]->ev_halo, 0) != cudaSuccess) ok = false;
+    }
+    cudaGraph_t g = nullptr;
+    const cudaError_t ee = cudaStreamEndCapture(c0->stream, &g);
+    Ctx::IterGraph ig;
+    if (rc == 0 && ok && ee == cudaSuccess && g && cudaGraphInstantiate(&ig.exec, g, 0) == cudaSuccess) {
+      ig.launches = c0->launches - l0[0];
+      ig.swaps = c0->qp != q0[0];
+      cudaGraphDestroy(g);
+      it = c0->graphs.emplace(key, ig).first;
+      // the capture pass has advanced the host-side state of this iteration; now run it
+      if (graph_join_before(cs, n)) return F3D_ERR_CUDA;
+      if (cudaGraphLaunch(it->second.exec, c0->stream) != cudaSuccess) return F3D_ERR_CUDA;
+      if (graph_fork_after(cs, n)) return F3D_ERR_CUDA;
+      *used = true;
+      return 0;
+    }
+    // not capturable here: undo the host-side state, remember not to try again for this key, issue directly
+    if (g) cudaGraphDestroy(g);
+    cudaGetLastError();
+    for (int c = 0; c < n; ++c) { cs[c]->qp = q0[c]; cs[c]->qp2 = q1[c]; cs[c]->launches = l0[c]; }
+    c0->graphs.emplace(key, Ctx::IterGraph{});
+    return 0;
+  }
+  if (!it->second.exec) return 0;
+  cudaSetDevice(c0->device);
+  if (graph_join_before(cs, n)) return F3D_ERR_CUDA;
+  if (cudaGraphLaunch(it->second.exec, c0->stream) != cudaSuccess) return F3D_ERR_CUDA;
+  if (graph_fork_after(cs, n)) return F3D_ERR_CUDA;
+  for (int c = 0; c < n; ++c) {
+    cs[c]->launches += it->second.launches;
+    cs[c]->P.current_iter = iter;
+    if (it->second.swaps) std::swap(cs[c]->qp, cs[c]->qp2);
+  }
+  *used = true;
+  return 0;
+}
+
+}  // namespace
+
 extern "C" int fest3d_gpu_step_group(Fest3dGpuCtx** cs, int n, int current_iter, int n_iters, double* res_abs_out) {
   if (!cs || n < 1 || n_iters < 1) return F3D_ERR_ARGUMENT;
   const int nvp1 = cs[0]->P.L.nv + 1;
@@ -805,44 +952,19 @@ extern "C" int fest3d_gpu_step_group(Fest3dGpuCtx** cs, int n, int current_iter,
     if (!cs[c]->geometry_set || !cs[c]->state_set || cs[c]->cfg.time_accuracy != ta) return fail(cs[c], F3D_ERR_ARGUMENT);
   }
   const int chunk = 1016 / nvp1;   // norms of a chunk + the error slot fit the 1024-double norm buffers
+  const bool graphs = graphs_allowed(cs, n);
   int rc = 0;
   for (int it0 = 0; it0 < n_iters; it0 += chunk) {
     const int nit = std::min(chunk, n_iters - it0);
+    for (int c = 0; c < n; ++c) {   // the norm slot counter of the chunk starts at 0
+      F3D_CUDA_RC(cudaSetDevice(cs[c]->device));
+      F3D_CUDA_RC(cudaMemsetAsync(cs[c]->err_dev + 4, 0, sizeof(int), cs[c]->stream));
+    }
     for (int it = 0; it < nit; ++it) {
-      for (int c = 0; c < n; ++c) {
-        Fest3dGpuCtx* ctx = cs[c];
-        F3D_CUDA(cudaSetDevice(ctx->device));
-        ctx->P.current_iter = current_iter + it0 + it;
-        if ((rc = launch_temp(ctx))) return rc;   // update.f90:170
-        if (ta != F3D_T_NONE && (rc = launch_copy_fields(ctx, ctx->ustore, ctx->qp, ctx->P.L.nv))) return rc;       // U_store = qp
-        if ((ta == F3D_T_RK2 || ta == F3D_T_RK4) && (rc = launch_zero_fields(ctx, ctx->rstore, ctx->P.L.nv))) return rc;  // R_store = 0
-      }
-      auto blend_all = [&](double a, double b) { for (int c = 0; c < n && !rc; ++c) { cudaSetDevice(cs[c]->device); rc = launch_blend(cs[c], a, b); } return rc; };
-      switch (ta) {   // update.f90:171-215
-        case F3D_T_NONE:
-          rc = stage(cs, n, true, 1., 1., 0, 1, 1); break;
-        case F3D_T_RK4:
-          if ((rc = stage(cs, n, true, 0.5, 1., 0, 1, 0))) break;
-          if ((rc = stage(cs, n, true, 0.5, 2., 0, 0, 0))) break;
-          if ((rc = stage(cs, n, true, 1.0, 2., 0, 0, 0))) break;
-          rc = stage(cs, n, true, 1. / 6., 1., 1, 0, 1); break;
-        case F3D_T_RK2:
-          if ((rc = stage(cs, n, true, 0.5, 1., 0, 1, 0))) break;
-          rc = stage(cs, n, true, 0.5, 1., 1, 0, 1); break;
-        case F3D_T_TVDRK3:
-          if ((rc = stage(cs, n, true, 1.0, 1., 0, 1, 0))) break;
-          if ((rc = stage(cs, n, true, 1.0, 1., 0, 0, 0))) break;
-          if ((rc = blend_all(0.75, 0.25))) break;
-          if ((rc = stage(cs, n, true, 1.0, 1., 0, 0, 1))) break;
-          rc = blend_all((1. / 3.), (2. / 3.)); break;
-        case F3D_T_TVDRK2:
-          if ((rc = stage(cs, n, true, 1.0, 1., 0, 1, 0))) break;
-          if ((rc = stage(cs, n, true, 1.0, 1., 0, 0, 1))) break;
-          rc = blend_all(0.5, 0.5); break;
-        default: rc = F3D_ERR_UNSUPPORTED;
-      }
-      if (rc) return rc;
-      for (int c = 0; c < n; ++c) { cudaSetDevice(cs[c]->device); if ((rc = launch_norms(cs[c], it))) return rc; }
+      const int iter = current_iter + it0 + it;
+      bool used = false;
+      if (graphs && iter > 2 && (rc = run_iteration_graph(cs, n, ta, iter, &used))) return rc;
+      if (!used && (rc = issue_iteration(cs, n, ta, iter))) return rc;
     }
     // find_resnorm: sum over all blocks (MPI_ALLGATHER + sum, resnorm.f90:201-225), then sqrt / abs.  The blocks of this process
     // are added on the host; across ranks ONE ncclAllReduce per call carries the sums and, in an extra slot, the error state, so

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <map>
 #include <vector>
 #include "../../include/fest3d_gpu.h"
 
@@ -93,7 +94,7 @@ struct Ctx {
   int red_blocks = 0;
   double* norms_dev = nullptr;   // (nv+1) per iteration slot
   double* norms_host = nullptr;  // pinned
-  int* err_dev = nullptr;        // sticky error word + first offending cell
+  int* err_dev = nullptr;        // [0..3] sticky error word + first offending cell; [4] iteration slot of the norm buffer (launch_norms)
   int* err_host = nullptr;
   double* sendbuf[6] = {nullptr};
   double* recvbuf[6] = {nullptr};
@@ -121,6 +122,10 @@ struct Ctx {
   size_t ev_used2 = 0;
   double ktime2_ms = 0.0;
   long long ktime2_n = 0;
+  // CUDA graphs of one whole iteration (every stage of every context of a step group), keyed by the group and the buffer parity;
+  // kept by the first context of the group (api.cu:step_group)
+  struct IterGraph { cudaGraphExec_t exec = nullptr; long long launches = 0; bool swaps = false; };
+  std::map<unsigned long long, IterGraph> graphs;
   Fest3dGpuError last_error{};
   bool geometry_set = false, state_set = false;
 };
@@ -144,7 +149,7 @@ int launch_residual(Ctx* ctx, int mode, double TF, double SF, int use_store_sum,
 int launch_blend(Ctx* ctx, double a, double b);
 int launch_copy_fields(Ctx* ctx, double* dst, const double* src, int nfields);
 int launch_zero_fields(Ctx* ctx, double* dst, int nfields);
-int launch_norms(Ctx* ctx, int slot);
+int launch_norms(Ctx* ctx);   // into the slot counted by the device word err_dev[4], which it advances
 int launch_pack(Ctx* ctx, int face);
 int launch_unpack(Ctx* ctx, int face, const double* buf);
 int launch_global_dt(Ctx* ctx);

@@ -8,20 +8,25 @@
 namespace f3d {
 
 
-// final reduction of the per-CTA partials in a fixed order (deterministic), scaled like get_absolute_resnorm
-__global__ void k_norm_final(const double* __restrict__ red, int n_cta, int nvp1, const double* scale /* nvp1 */, double* out) {
+// final reduction of the per-CTA partials in a fixed order (deterministic), scaled like get_absolute_resnorm.  The iteration slot the
+// norms go to is a device-side counter (advanced here), so that the launch is the same every iteration and can sit in a CUDA graph.
+__global__ void k_norm_final(const double* __restrict__ red, int n_cta, int nvp1, const double* scale /* nvp1 */, double* norms, int* slot_ctr) {
   __shared__ double sm[32];
-  const int v = blockIdx.x;
-  double x = 0.0;
-  for (int b = threadIdx.x; b < n_cta; b += blockDim.x) x += red[(long long)b * nvp1 + v];
-  for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = x;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = 0.0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sm[w];
-    out[v] = (v == 0) ? (t / scale[0]) : (t / (scale[v] * scale[v]));
+  const int slot = *slot_ctr;
+  for (int v = 0; v < nvp1; ++v) {
+    double x = 0.0;
+    for (int b = threadIdx.x; b < n_cta; b += blockDim.x) x += red[(long long)b * nvp1 + v];
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sm[w];
+      norms[(long long)slot * nvp1 + v] = (v == 0) ? (t / scale[0]) : (t / (scale[v] * scale[v]));
+    }
+    __syncthreads();
   }
+  if (threadIdx.x == 0) *slot_ctr = slot + 1;
 }
 
 int fused_grid_ctas(const Layout& L);
@@ -68,9 +73,9 @@ int launch_residual(Ctx* ctx, int mode, double TF, double SF, int use_store_sum,
 }
 
 
-int launch_norms(Ctx* ctx, int slot) {
+int launch_norms(Ctx* ctx) {
   const int nvp1 = ctx->P.L.nv + 1;
-  k_norm_final<<<nvp1, 256, 0, ctx->stream>>>(ctx->red, ctx->red_blocks, nvp1, ctx->norms_dev + 1024, ctx->norms_dev + (long long)slot * nvp1);
+  k_norm_final<<<1, 256, 0, ctx->stream>>>(ctx->red, ctx->red_blocks, nvp1, ctx->norms_dev + 1024, ctx->norms_dev, ctx->err_dev + 4);
   ctx->launches++;
   F3D_CUDA(cudaGetLastError());
   return 0;

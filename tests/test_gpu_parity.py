@@ -481,6 +481,30 @@ def test_shipped_smoothbump_output_relaxes_to_the_reported_entropy(pkg, case_mod
     assert abs(ds / 7.883e-07 - 1.0) < 0.03, ds
 
 
+# ---- the reference's own physics gates for the viscous and SST paths (tests/Report.txt:20-23, 33-36; tests/*/pp/Surface.py:87-153) ------
+@pytest.mark.parametrize("case,n_iter,tol", [("lfp", 40000, 0.01), ("tfp", 70000, 0.02)])
+def test_flat_plate_drag_coefficient_meets_the_reference_gate(pkg, case_mod, case, n_iter, tol):
+    """The only reference-held pins of the viscous flux, the ghost-gradient rule, the SST source and the wall omega: the flat-plate
+    drag coefficients.  The reference's cases (its grids, boundary files and flow files; Tfp from its shipped restart) are marched
+    on the device with the reference's scheme (ausm + muscl) by explicit RK4 with local time steps, and C_d is evaluated as the
+    reference's post-processing does (tests/surface_drag.py).  Gate = the reference's own: within 1 % of 1.33e-3 (laminar), within
+    2 % of 2.90e-3 (SST).  Converged values of the full marches (profiles/r02_lfp_drag_march.txt, r02_tfp_drag_march.txt):
+    1.31943e-3 at a residual of 2e-16 (the reference's run reports 1.329e-3) and 2.877e-3 (the reference's run: 2.872e-3)."""
+    import importlib
+    import fixtures
+    import surface_drag
+    solver = importlib.import_module("fest3d_b200.solver")
+    blocks = fixtures.load(case_mod, os.path.join(GOLDEN, case), scheme=dict(scheme_name="ausm", interpolant="muscl", time_step_accuracy="RK4"),
+                           control=dict(CFL=1.5 if case == "lfp" else 1.0))
+    s = solver.Solver(blocks)
+    s.iterate(n_iter - 1, want_norms=False)
+    s.iterate(1)
+    cd = surface_drag.device_wall_drag(s, blocks, case)
+    s.close()
+    assert abs(cd / surface_drag.CD_EXPECTED[case] - 1.0) < tol, cd
+    assert abs(cd / surface_drag.CD_REPORT[case] - 1.0) < tol, cd
+
+
 # ---- SURVEY 8(f) rank 1: wall distance on the device (wall_dist.f90:84-131) ---------------------------------------------------
 @pytest.mark.parametrize("shape", [(7, 6, 5), (40, 33, 9)])
 def test_wall_distance_on_device(pkg, case_mod, oracle, shape):
