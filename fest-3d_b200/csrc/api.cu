@@ -650,7 +650,11 @@ struct Msg { int peer_rank, block, face; Fest3dGpuCtx* ctx; int my_face; };
 //   pack (own stream) -> ev_pack -> { the process's communication stream: all ncclSend / ncclRecv of the rank in one group ;
 //   a local neighbour's stream: reads this context's send buffer } -> unpack (own stream) -> ev_halo
 // and a context re-packs a send buffer only after the local neighbour that reads it has recorded its ev_halo.
-int exchange(Fest3dGpuCtx** cs, int n) {
+// The swap comes in two halves so that it can be POSTED AHEAD: exchange_post (packs + the NCCL group on the communication stream)
+// right behind the sweep that produced the layers, exchange_finish (waits + unpacks) at the head of the next stage -- the
+// carry-over of the ghost shell and the Temp refresh of the next iteration then run on the compute stream while the messages are
+// in flight (they read or write ghost cells only before the unpack).
+int exchange_post(Fest3dGpuCtx** cs, int n) {
   bool any = false, remote = false;
   for (int c = 0; c < n; ++c)
     for (int f = 0; f < 6; ++f) {
@@ -699,9 +703,20 @@ int exchange(Fest3dGpuCtx** cs, int n) {
     if (g_nccl.GroupEnd() != 0) return F3D_ERR_CUDA;
     F3D_CUDA_RC(cudaEventRecord(sh->ev_done, sh->stream));
   }
+  for (int c = 0; c < n; ++c) cs[c]->halo_posted = true;
+  return 0;
+}
+
+int exchange_finish(Fest3dGpuCtx** cs, int n) {
+  CommShared* sh = nullptr;
+  for (int c = 0; c < n; ++c) {
+    if (!cs[c]->halo_posted) return 0;   // nothing was posted (no interface at all)
+    for (int f = 0; f < 6; ++f) if (cs[c]->link[f].kind == 2) sh = (CommShared*)cs[c]->nccl;
+  }
   for (int c = 0; c < n; ++c) {
     Fest3dGpuCtx* ctx = cs[c];
     F3D_CUDA(cudaSetDevice(ctx->device));
+    ctx->halo_posted = false;
     bool waited_comm = false;
     for (int f = 0; f < 6; ++f) {
       const Link& lk = ctx->link[f];
@@ -728,8 +743,15 @@ int exchange(Fest3dGpuCtx** cs, int n) {
   return 0;
 }
 
+int exchange(Fest3dGpuCtx** cs, int n) {
+  bool posted = true;
+  for (int c = 0; c < n; ++c) posted &= cs[c]->halo_posted;
+  if (!posted) { int rc = exchange_post(cs, n); if (rc) return rc; }
+  return exchange_finish(cs, n);
+}
+
 // one get_total_conservative_Residue (+ update) on every context
-int stage(Fest3dGpuCtx** cs, int n, bool update, double TF, double SF, int use_sum, int first, int last) {
+int stage(Fest3dGpuCtx** cs, int n, bool update, double TF, double SF, int use_sum, int first, int last, bool post_ahead = false) {
   int rc = exchange(cs, n);
   if (rc) return rc;
   for (int c = 0; c < n; ++c) {
@@ -749,8 +771,14 @@ int stage(Fest3dGpuCtx** cs, int n, bool update, double TF, double SF, int use_s
       fst = 0;
     }
     if ((rc = launch_residual(ctx, MODE_UPDATE, TF, SF, use_sum, fst, last))) return rc;
-    if ((rc = launch_ghost_shell_copy(ctx, ctx->qp2, ctx->qp))) return rc;
     std::swap(ctx->qp, ctx->qp2);
+  }
+  if (!update) return 0;
+  // the interior layers of the new state exist: the next stage's swap can leave now, beside the ghost-shell carry-over
+  if (post_ahead && (rc = exchange_post(cs, n))) return rc;
+  for (int c = 0; c < n; ++c) {
+    F3D_CUDA_RC(cudaSetDevice(cs[c]->device));
+    if ((rc = launch_ghost_shell_copy(cs[c], cs[c]->qp, cs[c]->qp2))) return rc;
   }
   return 0;
 }
@@ -798,7 +826,10 @@ extern "C" int fest3d_gpu_residual(Fest3dGpuCtx* ctx, int current_iter, double* 
 namespace {
 
 // one iteration of get_next_solution on every context (update.f90:129-226) + the norm assembly launch of find_resnorm
-int issue_iteration(Fest3dGpuCtx** cs, int n, int ta, int iter) {
+int issue_iteration(Fest3dGpuCtx** cs, int n, int ta, int iter, bool more_follow = false) {
+  // post_ahead: the stage is followed, inside this call, by another stage with nothing in between that changes the interior state
+  // (the whole-array blends of the TVD schemes do): A = after an inner stage, Z = after the last stage of the iteration
+  const bool A = true, Z = more_follow;
   int rc = 0;
   for (int c = 0; c < n; ++c) {
     Fest3dGpuCtx* ctx = cs[c];
@@ -811,23 +842,23 @@ int issue_iteration(Fest3dGpuCtx** cs, int n, int ta, int iter) {
   auto blend_all = [&](double a, double b) { for (int c = 0; c < n && !rc; ++c) { cudaSetDevice(cs[c]->device); rc = launch_blend(cs[c], a, b); } return rc; };
   switch (ta) {   // update.f90:171-215
     case F3D_T_NONE:
-      rc = stage(cs, n, true, 1., 1., 0, 1, 1); break;
+      rc = stage(cs, n, true, 1., 1., 0, 1, 1, Z); break;
     case F3D_T_RK4:
-      if ((rc = stage(cs, n, true, 0.5, 1., 0, 1, 0))) break;
-      if ((rc = stage(cs, n, true, 0.5, 2., 0, 0, 0))) break;
-      if ((rc = stage(cs, n, true, 1.0, 2., 0, 0, 0))) break;
-      rc = stage(cs, n, true, 1. / 6., 1., 1, 0, 1); break;
+      if ((rc = stage(cs, n, true, 0.5, 1., 0, 1, 0, A))) break;
+      if ((rc = stage(cs, n, true, 0.5, 2., 0, 0, 0, A))) break;
+      if ((rc = stage(cs, n, true, 1.0, 2., 0, 0, 0, A))) break;
+      rc = stage(cs, n, true, 1. / 6., 1., 1, 0, 1, Z); break;
     case F3D_T_RK2:
-      if ((rc = stage(cs, n, true, 0.5, 1., 0, 1, 0))) break;
-      rc = stage(cs, n, true, 0.5, 1., 1, 0, 1); break;
+      if ((rc = stage(cs, n, true, 0.5, 1., 0, 1, 0, A))) break;
+      rc = stage(cs, n, true, 0.5, 1., 1, 0, 1, Z); break;
     case F3D_T_TVDRK3:
-      if ((rc = stage(cs, n, true, 1.0, 1., 0, 1, 0))) break;
+      if ((rc = stage(cs, n, true, 1.0, 1., 0, 1, 0, A))) break;
       if ((rc = stage(cs, n, true, 1.0, 1., 0, 0, 0))) break;
       if ((rc = blend_all(0.75, 0.25))) break;
       if ((rc = stage(cs, n, true, 1.0, 1., 0, 0, 1))) break;
       rc = blend_all((1. / 3.), (2. / 3.)); break;
     case F3D_T_TVDRK2:
-      if ((rc = stage(cs, n, true, 1.0, 1., 0, 1, 0))) break;
+      if ((rc = stage(cs, n, true, 1.0, 1., 0, 1, 0, A))) break;
       if ((rc = stage(cs, n, true, 1.0, 1., 0, 0, 1))) break;
       rc = blend_all(0.5, 0.5); break;
     default: rc = F3D_ERR_UNSUPPORTED;
@@ -964,7 +995,8 @@ extern "C" int fest3d_gpu_step_group(Fest3dGpuCtx** cs, int n, int current_iter,
       const int iter = current_iter + it0 + it;
       bool used = false;
       if (graphs && iter > 2 && (rc = run_iteration_graph(cs, n, ta, iter, &used))) return rc;
-      if (!used && (rc = issue_iteration(cs, n, ta, iter))) return rc;
+      // outside a graph the last stage may post the next iteration's swap ahead, as long as that iteration belongs to this call
+      if (!used && (rc = issue_iteration(cs, n, ta, iter, !graphs && (it0 + it + 1 < n_iters)))) return rc;
     }
     // find_resnorm: sum over all blocks (MPI_ALLGATHER + sum, resnorm.f90:201-225), then sqrt / abs.  The blocks of this process
     // are added on the host; across ranks ONE ncclAllReduce per call carries the sums and, in an extra slot, the error state, so
