@@ -33,6 +33,17 @@
 namespace f3d {
 namespace g3 {
 
+#ifdef F3D_PHASE_TIMING   // development aid: clock64 totals per warp: work of a plane, wait at the plane barrier
+__device__ unsigned long long g_phase3[16 * 2];
+#define PT3_DECL unsigned long long pt_t = clock64(), pt_acc[2] = {0, 0};
+#define PT3_MARK(n) { const unsigned long long t_ = clock64(); pt_acc[n] += t_ - pt_t; pt_t = t_; }
+#define PT3_FLUSH if (lane == 0) { atomicAdd(&g_phase3[wid * 2], pt_acc[0]); atomicAdd(&g_phase3[wid * 2 + 1], pt_acc[1]); }
+#else
+#define PT3_DECL
+#define PT3_MARK(n)
+#define PT3_FLUSH
+#endif
+
 constexpr int TX = 32, TY = 4;
 constexpr int NMAIN = TX * TY;
 constexpr int NW = 3 * TY + 4;
@@ -396,8 +407,11 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a,
     cp_async_wait_all();
   }
 
+  PT3_DECL
   for (int k = kb - 1; k <= ke; ++k) {
+    PT3_MARK(0)
     bar_all();   // plane k is staged; the fluxes and cell packets of plane k-1 are complete
+    PT3_MARK(1)
     role();
     // ---- staging of plane k+1 over plane k-1 (nobody reads plane k-1 any more: the cell work takes what it needs from the cell
     // packets); the K rows also fetch the volume of plane k+1 and their own q of plane k+2 for the k stencil
@@ -456,7 +470,8 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a,
             p_far = krow ? q[4 * fs + cg + two * Ly.sk] : smem[o_0 + 4 * PSQ + two * nb];
           }
           recon3<NV, INTERP, RARE>(P, qm, q0, qp, cpos, mx, d, hi, lo, p_far);
-        } else {
+        } else {   // five-point stencils from global memory / L2.  Measured (profiles/r02_summary.md): taking them from the staged plane
+                   // for the I / J row warps, whose stencils lie inside it, changes nothing (9.81 vs 9.63 ms): the WENO weights bind
           line_cell_values<NV, INTERP, RARE>(P, q, vol, cg, (d == 0) ? 1 : ((d == 1) ? Ly.sj : Ly.sk), cpos, mx, d, hi, lo);
         }
         if (wr_hi) {
@@ -597,6 +612,7 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a,
     }
     cp_async_wait_all();
   }
+  PT3_FLUSH
 
   if (a.want_norms) {   // per-CTA partial: warp shuffle inside the two warps that did the cell work, then across them
     bar_all();

@@ -20,4 +20,6 @@ r = s.iterate(args.steps)
 print("res_abs last:", r[-1])
 if hasattr(L, "fest3d_gpu_phase_dump"):
     L.fest3d_gpu_phase_dump()
+if hasattr(L, "fest3d_gpu_phase_dump3"):
+    L.fest3d_gpu_phase_dump3()
 s.close()
