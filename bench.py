@@ -144,7 +144,7 @@ def cpu_baseline_sample(args):
     blocks = syn.make_duct_blocks(m, nb=nb, scheme_name=args.scheme, interpolant=args.interpolant, turbulence="sst", time_step_accuracy="none", CFL=0.5)
     w = oracle_py.OracleWorld(blocks, fast=True)
     w.step(1)
-    steps = 3
+    steps = 8
     t0 = time.perf_counter()
     for it in range(2, 2 + steps):
         w.step(it)
@@ -169,7 +169,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cells", type=int, default=256, help="cells per block edge")
-    ap.add_argument("--cpu-cells", type=int, default=48, help="cells per block edge of the CPU sample")
+    ap.add_argument("--cpu-cells", type=int, default=96, help="cells per block edge of the CPU sample (96^3 x ~60 arrays per block: far beyond the host caches)")
     ap.add_argument("--no-cpu", action="store_true")
     # the headline configuration is the default; BASELINE.json's other synthetic config (WENO + AUSM+ + SST, residual evaluations) is
     # --interpolant weno --scheme ausmP --mode residual; its multi-block config is --scaling strong (512^3 as 8 blocks on 1/2/4/8 GPUs)
@@ -296,11 +296,14 @@ def main():
             g.get_state(qb_np)   # warm-up of the path
         barrier()
         e0.record(stream)
-        for _ in range(e2e_steps):
-            s.set_states_async([q_np] * len(s.blocks))     # H2D of the step's input state (every block of the rank)
-            r = s.iterate(1)                               # one cell-update everywhere + norms (D2H of n_var+1 doubles)
-            s.get_states_async([qb_np] * len(s.blocks))    # D2H of the step's result (overlaps the next step's H2D: PCIe is full duplex)
-        s.state_wait()                                     # the last result has arrived on the host
+        s.set_states_async([q_np] * len(s.blocks))             # H2D of step 0's input state (every block of the rank)
+        for step in range(e2e_steps):
+            s.iterate_begin(1)                                 # takes the uploaded state, one cell-update everywhere (queued, returns)
+            if step + 1 < e2e_steps:
+                s.set_states_async([q_np] * len(s.blocks))     # H2D of the NEXT step's input: overlaps this step and the previous D2H
+            r = s.iterate_end()                                # this step's norms (D2H of n_var+1 doubles)
+            s.get_states_async([qb_np] * len(s.blocks))        # D2H of this step's result (PCIe is full duplex)
+        s.state_wait()                                         # the last result has arrived on the host
         e1.record(stream)
         barrier()
         ms_e2e = e0.elapsed_time(e1)

@@ -20,7 +20,7 @@ SYMBOLS = [
     "fest3d_gpu_comm_unique_id", "fest3d_gpu_comm_init", "fest3d_gpu_link_local", "fest3d_gpu_launch_count",
     "fest3d_gpu_kernel_timing", "fest3d_gpu_kernel_time_ms", "fest3d_gpu_version", "fest3d_gpu_find_wall_dist", "fest3d_gpu_setup_geometry", "fest3d_gpu_get_geometry",
     "fest3d_gpu_checkpoint_begin", "fest3d_gpu_checkpoint_wait", "fest3d_gpu_restart", "fest3d_gpu_gradient_time_ms", "fest3d_gpu_gradient_path",
-    "fest3d_gpu_set_state_async", "fest3d_gpu_get_state_async", "fest3d_gpu_state_wait",
+    "fest3d_gpu_set_state_async", "fest3d_gpu_get_state_async", "fest3d_gpu_state_wait", "fest3d_gpu_step_group_begin", "fest3d_gpu_step_group_end",
 ]
 
 
@@ -99,6 +99,8 @@ def lib():
     L.fest3d_gpu_set_state_async.argtypes = [vp, dp]
     L.fest3d_gpu_get_state_async.argtypes = [vp, dp]
     L.fest3d_gpu_state_wait.argtypes = [vp]
+    L.fest3d_gpu_step_group_begin.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int]
+    L.fest3d_gpu_step_group_end.argtypes = [C.POINTER(vp), C.c_int, dp]
     L.fest3d_gpu_version.restype = C.c_char_p
     L.fest3d_gpu_find_wall_dist.argtypes = [vp, dp, dp, C.c_longlong, dp, dp]
     L.fest3d_gpu_setup_geometry.argtypes = [vp, dp, dp, dp]

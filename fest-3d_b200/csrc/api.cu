@@ -972,9 +972,10 @@ int run_iteration_graph(Fest3dGpuCtx** cs, int n, int ta, int iter, bool* used) 
 
 }  // namespace
 
-extern "C" int fest3d_gpu_step_group(Fest3dGpuCtx** cs, int n, int current_iter, int n_iters, double* res_abs_out) {
+namespace {
+
+int step_prepare(Fest3dGpuCtx** cs, int n, int n_iters, int* ta_out) {
   if (!cs || n < 1 || n_iters < 1) return F3D_ERR_ARGUMENT;
-  const int nvp1 = cs[0]->P.L.nv + 1;
   const int ta = cs[0]->cfg.time_accuracy;
   for (int c = 0; c < n; ++c) {
     cudaSetDevice(cs[c]->device);
@@ -982,59 +983,110 @@ extern "C" int fest3d_gpu_step_group(Fest3dGpuCtx** cs, int n, int current_iter,
     if (rp) return rp;
     if (!cs[c]->geometry_set || !cs[c]->state_set || cs[c]->cfg.time_accuracy != ta) return fail(cs[c], F3D_ERR_ARGUMENT);
   }
-  const int chunk = 1016 / nvp1;   // norms of a chunk + the error slot fit the 1024-double norm buffers
-  const bool graphs = graphs_allowed(cs, n);
+  *ta_out = ta;
+  return 0;
+}
+
+// queue the iterations it0 .. it0+nit-1 of a call and the download of their norms and of the error word; no host synchronisation
+int chunk_issue(Fest3dGpuCtx** cs, int n, int ta, int current_iter, int it0, int nit, int n_iters, bool graphs) {
+  const int nvp1 = cs[0]->P.L.nv + 1;
   int rc = 0;
-  for (int it0 = 0; it0 < n_iters; it0 += chunk) {
-    const int nit = std::min(chunk, n_iters - it0);
-    for (int c = 0; c < n; ++c) {   // the norm slot counter of the chunk starts at 0
-      F3D_CUDA_RC(cudaSetDevice(cs[c]->device));
-      F3D_CUDA_RC(cudaMemsetAsync(cs[c]->err_dev + 4, 0, sizeof(int), cs[c]->stream));
-    }
-    for (int it = 0; it < nit; ++it) {
-      const int iter = current_iter + it0 + it;
-      bool used = false;
-      if (graphs && iter > 2 && (rc = run_iteration_graph(cs, n, ta, iter, &used))) return rc;
-      // outside a graph the last stage may post the next iteration's swap ahead, as long as that iteration belongs to this call
-      if (!used && (rc = issue_iteration(cs, n, ta, iter, !graphs && (it0 + it + 1 < n_iters)))) return rc;
-    }
-    // find_resnorm: sum over all blocks (MPI_ALLGATHER + sum, resnorm.f90:201-225), then sqrt / abs.  The blocks of this process
-    // are added on the host; across ranks ONE ncclAllReduce per call carries the sums and, in an extra slot, the error state, so
-    // that every rank leaves with an error as soon as any rank has one (the reference's Fatal_error stops the whole job) instead
-    // of posting the next chunk's sends and receives towards a rank that has already returned.
-    CommShared* sh = nullptr;
-    for (int c = 0; c < n; ++c) {
-      Fest3dGpuCtx* ctx = cs[c];
-      F3D_CUDA(cudaSetDevice(ctx->device));
-      if (ctx->nccl && ctx->n_ranks > 1) sh = (CommShared*)ctx->nccl;
-      if (res_abs_out || sh) F3D_CUDA(cudaMemcpyAsync(ctx->norms_host, ctx->norms_dev, sizeof(double) * nit * nvp1, cudaMemcpyDeviceToHost, ctx->stream));
-    }
-    int e = 0;
-    for (int c = 0; c < n; ++c) e |= check_errors(cs[c]);   // also synchronises the stream
-    double* tot = cs[0]->norms_host;
-    for (int x = 0; x < nit * nvp1; ++x) {
-      double sum = 0.0;
-      for (int c = 0; c < n; ++c) sum = sum + cs[c]->norms_host[x];
-      tot[x] = sum;
-    }
-    if (sh) {
-      Fest3dGpuCtx* ctx = cs[0];
-      const int cnt = nit * nvp1 + 1;
-      tot[cnt - 1] = e ? 1.0 : 0.0;
-      F3D_CUDA(cudaSetDevice(sh->device));
-      F3D_CUDA(cudaMemcpyAsync(ctx->norms_dev, tot, sizeof(double) * cnt, cudaMemcpyHostToDevice, sh->stream));
-      if (g_nccl.AllReduce(ctx->norms_dev, ctx->norms_dev, (size_t)cnt, kNcclFloat64, kNcclSum, sh->comm, sh->stream) != 0) return fail(ctx, F3D_ERR_CUDA);
-      F3D_CUDA(cudaMemcpyAsync(tot, ctx->norms_dev, sizeof(double) * cnt, cudaMemcpyDeviceToHost, sh->stream));
-      F3D_CUDA(cudaStreamSynchronize(sh->stream));
-      if (tot[cnt - 1] != 0.0 && !e) { e = F3D_ERR_PEER; for (int c = 0; c < n; ++c) cs[c]->last_error.flags |= F3D_ERR_PEER; }
-    }
-    if (res_abs_out) {
-      for (int it = 0; it < nit; ++it)
-        for (int l = 0; l < nvp1; ++l) res_abs_out[(size_t)(it0 + it) * nvp1 + l] = (l == 0) ? fabs(tot[it * nvp1 + l]) : sqrt(tot[it * nvp1 + l]);
-    }
-    if (e) return e;
+  for (int c = 0; c < n; ++c) {   // the norm slot counter of the chunk starts at 0
+    F3D_CUDA_RC(cudaSetDevice(cs[c]->device));
+    F3D_CUDA_RC(cudaMemsetAsync(cs[c]->err_dev + 4, 0, sizeof(int), cs[c]->stream));
+  }
+  for (int it = 0; it < nit; ++it) {
+    const int iter = current_iter + it0 + it;
+    bool used = false;
+    if (graphs && iter > 2 && (rc = run_iteration_graph(cs, n, ta, iter, &used))) return rc;
+    // outside a graph the last stage may post the next iteration's swap ahead, as long as that iteration belongs to this call
+    if (!used && (rc = issue_iteration(cs, n, ta, iter, !graphs && (it0 + it + 1 < n_iters)))) return rc;
+  }
+  for (int c = 0; c < n; ++c) {
+    Fest3dGpuCtx* ctx = cs[c];
+    F3D_CUDA(cudaSetDevice(ctx->device));
+    F3D_CUDA(cudaMemcpyAsync(ctx->norms_host, ctx->norms_dev, sizeof(double) * nit * nvp1, cudaMemcpyDeviceToHost, ctx->stream));
+    F3D_CUDA(cudaMemcpyAsync(ctx->err_host, ctx->err_dev, sizeof(int) * 4, cudaMemcpyDeviceToHost, ctx->stream));
   }
   return 0;
+}
+
+// find_resnorm: sum over all blocks (MPI_ALLGATHER + sum, resnorm.f90:201-225), then sqrt / abs.  The blocks of this process are added
+// on the host; across ranks ONE ncclAllReduce per chunk carries the sums and, in an extra slot, the error state, so that every rank
+// leaves with an error as soon as any rank has one (the reference's Fatal_error stops the whole job) instead of posting the next
+// chunk's sends and receives towards a rank that has already returned.
+int chunk_collect(Fest3dGpuCtx** cs, int n, int it0, int nit, double* res_abs_out) {
+  const int nvp1 = cs[0]->P.L.nv + 1;
+  CommShared* sh = nullptr;
+  int e = 0;
+  for (int c = 0; c < n; ++c) {
+    Fest3dGpuCtx* ctx = cs[c];
+    F3D_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->nccl && ctx->n_ranks > 1) sh = (CommShared*)ctx->nccl;
+    F3D_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->err_host[0]) {
+      ctx->last_error.flags |= ctx->err_host[0];
+      ctx->last_error.i = ctx->err_host[1]; ctx->last_error.j = ctx->err_host[2]; ctx->last_error.k = ctx->err_host[3];
+      e |= ctx->err_host[0];
+    }
+  }
+  double* tot = cs[0]->norms_host;
+  for (int x = 0; x < nit * nvp1; ++x) {
+    double sum = 0.0;
+    for (int c = 0; c < n; ++c) sum = sum + cs[c]->norms_host[x];
+    tot[x] = sum;
+  }
+  if (sh) {
+    Fest3dGpuCtx* ctx = cs[0];
+    const int cnt = nit * nvp1 + 1;
+    tot[cnt - 1] = e ? 1.0 : 0.0;
+    F3D_CUDA(cudaSetDevice(sh->device));
+    F3D_CUDA(cudaMemcpyAsync(ctx->norms_dev, tot, sizeof(double) * cnt, cudaMemcpyHostToDevice, sh->stream));
+    if (g_nccl.AllReduce(ctx->norms_dev, ctx->norms_dev, (size_t)cnt, kNcclFloat64, kNcclSum, sh->comm, sh->stream) != 0) return fail(ctx, F3D_ERR_CUDA);
+    F3D_CUDA(cudaMemcpyAsync(tot, ctx->norms_dev, sizeof(double) * cnt, cudaMemcpyDeviceToHost, sh->stream));
+    F3D_CUDA(cudaStreamSynchronize(sh->stream));
+    if (tot[cnt - 1] != 0.0 && !e) { e = F3D_ERR_PEER; for (int c = 0; c < n; ++c) cs[c]->last_error.flags |= F3D_ERR_PEER; }
+  }
+  if (res_abs_out) {
+    for (int it = 0; it < nit; ++it)
+      for (int l = 0; l < nvp1; ++l) res_abs_out[(size_t)(it0 + it) * nvp1 + l] = (l == 0) ? fabs(tot[it * nvp1 + l]) : sqrt(tot[it * nvp1 + l]);
+  }
+  return e;
+}
+
+}  // namespace
+
+extern "C" int fest3d_gpu_step_group(Fest3dGpuCtx** cs, int n, int current_iter, int n_iters, double* res_abs_out) {
+  int ta = 0;
+  int rc = step_prepare(cs, n, n_iters, &ta);
+  if (rc) return rc;
+  const int chunk = 1016 / (cs[0]->P.L.nv + 1);   // norms of a chunk + the error slot fit the 1024-double norm buffers
+  const bool graphs = graphs_allowed(cs, n);
+  for (int it0 = 0; it0 < n_iters; it0 += chunk) {
+    const int nit = std::min(chunk, n_iters - it0);
+    if ((rc = chunk_issue(cs, n, ta, current_iter, it0, nit, n_iters, graphs))) return rc;
+    if ((rc = chunk_collect(cs, n, it0, nit, res_abs_out))) return rc;
+  }
+  return 0;
+}
+
+// The same in two halves: _begin queues the iterations and returns, _end waits for them and delivers the norms.  Between the two the
+// host is free -- e.g. to start the upload of the next state (fest3d_gpu_set_state_async) while these iterations run.
+extern "C" int fest3d_gpu_step_group_begin(Fest3dGpuCtx** cs, int n, int current_iter, int n_iters) {
+  int ta = 0;
+  int rc = step_prepare(cs, n, n_iters, &ta);
+  if (rc) return rc;
+  if (n_iters > 1016 / (cs[0]->P.L.nv + 1) || cs[0]->steps_in_flight) return fail(cs[0], F3D_ERR_ARGUMENT);
+  if ((rc = chunk_issue(cs, n, ta, current_iter, 0, n_iters, n_iters, graphs_allowed(cs, n)))) return rc;
+  cs[0]->steps_in_flight = n_iters;
+  return 0;
+}
+
+extern "C" int fest3d_gpu_step_group_end(Fest3dGpuCtx** cs, int n, double* res_abs_out) {
+  if (!cs || n < 1 || !cs[0]->steps_in_flight) return F3D_ERR_ARGUMENT;
+  const int nit = cs[0]->steps_in_flight;
+  cs[0]->steps_in_flight = 0;
+  return chunk_collect(cs, n, 0, nit, res_abs_out);
 }
 
 extern "C" int fest3d_gpu_step(Fest3dGpuCtx* ctx, int current_iter, int n_iters, double* res_abs_out) {

@@ -107,6 +107,7 @@ struct Ctx {
   cudaEvent_t ev_h2d = nullptr, ev_in_free = nullptr, ev_relaid = nullptr, ev_d2h = nullptr;
   bool state_pending = false;        // an uploaded state waits in state_staging to be laid out into qp (done at the next step / residual)
   Link link[6];
+  int steps_in_flight = 0;       // iterations queued by fest3d_gpu_step_group_begin and not yet collected (kept by the group's first context)
   bool halo_posted = false;      // the send buffers are packed and the messages of the coming stage are on their way (api.cu:exchange_post)
   struct Checkpoint* ckpt = nullptr;   // asynchronous checkpoint state (checkpoint.cu), created on first use
   void* nccl = nullptr;          // the process-wide communicator record (api.cu:CommShared)

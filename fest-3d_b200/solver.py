@@ -285,6 +285,24 @@ class Solver:
         self.current_iter += n_iters
         return res
 
+    def iterate_begin(self, n_iters=1):
+        """Queue n iterations and return; iterate_end() waits for them and returns Res_abs[n_iters, n_var+1]."""
+        rc = self.L.fest3d_gpu_step_group_begin(self._handles, len(self.blocks), self.current_iter, n_iters)
+        if rc:
+            for b in self.blocks:
+                b._check(rc)
+        self._in_flight = n_iters
+
+    def iterate_end(self, want_norms=True):
+        n_iters = self._in_flight
+        res = np.zeros((n_iters, self.n_var + 1)) if want_norms else None
+        rc = self.L.fest3d_gpu_step_group_end(self._handles, len(self.blocks), _dp(res))
+        if rc:
+            for b in self.blocks:
+                b._check(rc)
+        self.current_iter += n_iters
+        return res
+
     def checkpoint_begin(self, prefix):
         """Asynchronous checkpoint of every block (file prefix + '_<block id>.f3dckpt'); stepping may continue at once."""
         for b in self.blocks:

@@ -158,6 +158,11 @@ int fest3d_gpu_step(Fest3dGpuCtx* ctx, int current_iter, int n_iters, double* re
 /* several blocks that live in this process (any devices) stepped in lock step; interfaces between them are
  * exchanged device-to-device, interfaces to blocks of other processes through the communicator. */
 int fest3d_gpu_step_group(Fest3dGpuCtx** ctxs, int n_ctx, int current_iter, int n_iters, double* res_abs_out);
+/* The same in two halves (n_iters <= 127): _begin queues the iterations and returns at once, _end waits for them and delivers the
+ * norms / the error state.  In between the host is free, e.g. to start the upload of the next state with fest3d_gpu_set_state_async
+ * while these iterations run (one begin in flight per group). */
+int fest3d_gpu_step_group_begin(Fest3dGpuCtx** ctxs, int n_ctx, int current_iter, int n_iters);
+int fest3d_gpu_step_group_end(Fest3dGpuCtx** ctxs, int n_ctx, double* res_abs_out);
 /* one residual evaluation (Temp refresh, halo exchange, ghost fill, ... , source); residue_out may be NULL */
 int fest3d_gpu_residual(Fest3dGpuCtx* ctx, int current_iter, double* residue_out);
 int fest3d_gpu_residual_group(Fest3dGpuCtx** ctxs, int n_ctx, int current_iter);

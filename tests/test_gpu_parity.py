@@ -634,6 +634,21 @@ def test_async_duplex_state_transfers_equal_the_synchronous_ones(pkg, case_mod):
     for n in range(3):
         assert np.array_equal(hist_a[n], hist_b[n])
         assert np.array_equal(outs_a[n], bufs[n])
+    # the pipelined form of bench.py's e2e leg: the next upload is started while the iterations of the current state are in flight
+    outs_c, hist_c = [np.empty_like(q0) for _ in range(3)], []
+    ins = [np.ascontiguousarray(x) for x in (q0, q1, q0)]
+    b.blocks[0].set_state_async(ins[0])
+    for n in range(3):
+        b.current_iter = 1
+        b.iterate_begin(2)
+        if n + 1 < 3:
+            b.blocks[0].set_state_async(ins[n + 1])
+        hist_c.append(b.iterate_end())
+        b.blocks[0].get_state_async(outs_c[n])
+    b.state_wait()
+    for n in range(3):
+        assert np.array_equal(hist_a[n], hist_c[n])
+        assert np.array_equal(outs_a[n], outs_c[n])
     a.close(); b.close()
 
 
