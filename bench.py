@@ -284,7 +284,7 @@ def main():
     # ---- end to end through the C ABI with host buffers ("e2e") ----
     e2e_value = None
     state_bytes = 0
-    e2e_steps = max(3, min(args.steps, 5))
+    e2e_steps = max(3, min(args.steps, 12))   # the pipeline needs a few periods to reach its steady rate (one upload / download of 1 GB each per step)
     if args.mode == "step":
         q_host = torch.from_numpy(np.ascontiguousarray(q_keep)).pin_memory()
         q_back = torch.empty_like(q_host).pin_memory()

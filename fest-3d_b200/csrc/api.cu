@@ -446,7 +446,8 @@ extern "C" int fest3d_gpu_get_state_async(Fest3dGpuCtx* ctx, double* qp) {
   F3D_CUDA(cudaSetDevice(ctx->device));
   int rc = ensure_async_state(ctx);
   if (rc) return rc;
-  if ((rc = apply_pending_state(ctx))) return rc;
+  // (an upload that is still pending -- fest3d_gpu_set_state_async of the NEXT state -- is not applied here: it takes effect at the
+  // next step call; what is downloaded is the state behind the steps issued so far)
   const Layout& L = ctx->P.L;
   const size_t n = (size_t)L.nv * (L.imx + 5) * (L.jmx + 5) * (L.kmx + 5);
   F3D_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h, 0));   // the previous download has left the outbound buffer

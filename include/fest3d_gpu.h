@@ -112,7 +112,8 @@ int fest3d_gpu_get_state(Fest3dGpuCtx* ctx, double* qp);
 /* Asynchronous, full-duplex forms (pinned host memory gives the overlap): set_state_async starts the upload on a copy stream and
  * returns -- the state takes effect at the next fest3d_gpu_step / fest3d_gpu_residual call, which is stream-ordered behind it, so the
  * upload of the next state overlaps the iterations still running and the download of the previous result; get_state_async snapshots
- * qp in stream order (after every step issued so far) and downloads it on a second copy stream; the host buffers may be reused /
+ * qp in stream order (after every step issued so far; an upload still pending for the next step is NOT applied by it) and downloads
+ * it on a second copy stream; the host buffers may be reused /
  * read after fest3d_gpu_state_wait.  The checkpoint host of src/solver.f90:139,186 only needs the outbound one. */
 int fest3d_gpu_set_state_async(Fest3dGpuCtx* ctx, const double* qp);
 int fest3d_gpu_get_state_async(Fest3dGpuCtx* ctx, double* qp);
