@@ -29,9 +29,9 @@ INTERPOLANTS = {"none": 0, "muscl": 1, "ppm": 2, "weno": 3, "weno_NM": 4}
 TURBULENCE = {"none": 0, "sa": 1, "saBC": 2, "sst": 3, "sst2003": 4, "kkl": 5}
 TRANSITION = {"none": 0, "bc": 1, "lctm2015": 2}
 TIME_ACCURACY = {"none": 0, "RK2": 1, "RK4": 2, "TVDRK2": 3, "TVDRK3": 4, "implicit": 5, "plusgs": 6}
-FIX_SLOTS = ["density", "pressure", "x_speed", "y_speed", "z_speed", "tk", "tw", "wall_temperature", "Tpressure", "Ttemperature", "tv"]
+FIX_SLOTS = ["density", "pressure", "x_speed", "y_speed", "z_speed", "tk", "tw", "wall_temperature", "Tpressure", "Ttemperature", "tv", "tkl"]
 FIX_KEYS = {"FIX_DENSITY": 0, "FIX_PRESSURE": 1, "FIX_X_SPEED": 2, "FIX_Y_SPEED": 3, "FIX_Z_SPEED": 4,
-            "FIX_tk": 5, "FIX_tw": 6, "WALL_TEMPERATURE": 7, "TOTAL_PRESSURE": 8, "TOTAL_TEMPERATURE": 9, "FIX_tv": 10}
+            "FIX_tk": 5, "FIX_tw": 6, "WALL_TEMPERATURE": 7, "TOTAL_PRESSURE": 8, "TOTAL_TEMPERATURE": 9, "FIX_tv": 10, "FIX_tkl": 11}
 
 
 def _tokens(path):
@@ -80,6 +80,7 @@ class Flow:
     tk_inf: float = 0.0
     tw_inf: float = 0.0
     tv_inf: float = 0.0
+    tkl_inf: float = 0.0
 
     def derive(self, turbulence):
         self.vel_mag = math.sqrt(self.x_speed_inf ** 2 + self.y_speed_inf ** 2 + self.z_speed_inf ** 2)
@@ -90,6 +91,10 @@ class Flow:
             self.tw_inf = self.density_inf * self.tk_inf / (self.mu_ref * self.mu_ratio_inf)
         if turbulence == "sa":      # state.f90:105-106
             self.tv_inf = self.mu_ratio_inf * self.mu_ref / self.density_inf
+        if turbulence == "kkl":     # state.f90:101-103
+            c_inf = math.sqrt(self.gm * self.pressure_inf / self.density_inf)
+            self.tk_inf = 9 * (1e-9) * (c_inf ** 2)
+            self.tkl_inf = 1.5589 * (1e-6) * (self.mu_ref * c_inf) / self.density_inf
         return self
 
 
@@ -203,7 +208,7 @@ class BlockSetup:
         self.fixed = np.zeros((len(FIX_SLOTS), 6))
         self.fixed[0, :] = f.density_inf; self.fixed[1, :] = f.pressure_inf
         self.fixed[2, :] = f.x_speed_inf; self.fixed[3, :] = f.y_speed_inf; self.fixed[4, :] = f.z_speed_inf
-        self.fixed[5, :] = f.tk_inf; self.fixed[6, :] = f.tw_inf; self.fixed[10, :] = f.tv_inf
+        self.fixed[5, :] = f.tk_inf; self.fixed[6, :] = f.tw_inf; self.fixed[10, :] = f.tv_inf; self.fixed[11, :] = f.tkl_inf
 
     def init_state(self):
         """state.f90:193-247 init_state_with_infinity_values (ghosts included)."""
@@ -212,7 +217,7 @@ class BlockSetup:
         q = np.empty((nv, self.kmx + 5, self.jmx + 5, self.imx + 5))
         q[0] = f.density_inf; q[1] = f.x_speed_inf; q[2] = f.y_speed_inf; q[3] = f.z_speed_inf; q[4] = f.pressure_inf
         if nv >= 7:
-            q[5] = f.tk_inf; q[6] = f.tw_inf
+            q[5] = f.tk_inf; q[6] = f.tkl_inf if self.scheme.turbulence == "kkl" else f.tw_inf     # state.f90:228-238
         elif nv == 6:               # state.f90:240-242
             q[5] = f.tv_inf
         self.qp = q

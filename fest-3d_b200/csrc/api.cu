@@ -64,10 +64,12 @@ extern "C" int fest3d_gpu_create(Fest3dGpuCtx** out, const Fest3dGpuConfig* cfg,
     return F3D_ERR_CUDA;
   }
   // scope check: only what this path implements; everything else is an explicit error, never a silent fallback
-  const bool sst = cfg->turbulence == F3D_TURB_SST || cfg->turbulence == F3D_TURB_SST2003;
+  const bool kkl = cfg->turbulence == F3D_TURB_KKL;
+  const bool sst = cfg->turbulence == F3D_TURB_SST || cfg->turbulence == F3D_TURB_SST2003 || kkl;   // the two-equation layout (n_var 7, n_grad 6)
   const bool sa = cfg->turbulence == F3D_TURB_SA;   // 'saBC' has no case in the reference's source dispatcher (source.f90:119-153)
   if (cfg->turbulence != F3D_TURB_NONE && !sst && !sa) return F3D_ERR_UNSUPPORTED;
-  if (cfg->transition != F3D_TRANS_NONE && !(cfg->transition == F3D_TRANS_BC && (sst || sa))) return F3D_ERR_UNSUPPORTED;   // lctm2015: not built
+  if (cfg->transition != F3D_TRANS_NONE && !(cfg->transition == F3D_TRANS_BC && (sst || sa) && !kkl)) return F3D_ERR_UNSUPPORTED;   // lctm2015: not built
+  if (kkl) { const char* e = getenv("F3D_GRADIENTS"); if (e && strcmp(e, "fused") == 0) return F3D_ERR_UNSUPPORTED; }   // k-kL: staged form only
   if (cfg->time_accuracy >= F3D_T_IMPLICIT || cfg->time_accuracy < 0) return F3D_ERR_UNSUPPORTED;
   if (cfg->scheme < 0 || cfg->scheme > F3D_SLAU || cfg->interpolant < 0 || cfg->interpolant > F3D_WENO_NM) return F3D_ERR_ARGUMENT;
   if (cfg->n_var != (sst ? 7 : (sa ? 6 : 5))) return F3D_ERR_ARGUMENT;
@@ -112,7 +114,8 @@ static int create_impl(Fest3dGpuCtx* ctx, const Fest3dGpuConfig* cfg, int device
   for (int d = 0; d < 3; ++d) { P.zlo[d] = wallish(P.bc_id[2 * d]) ? 0.0 : 1.0; P.zhi[d] = wallish(P.bc_id[2 * d + 1]) ? 0.0 : 1.0; }
   P.c2 = 1 + cfg->accur; P.c3 = 0.5 * cfg->accur; P.c1 = P.c2 - P.c3;
   P.current_iter = 1;
-  P.viscous = cfg->mu_ref != 0.0; P.sst = sst ? 1 : 0; P.sa = sa ? 1 : 0;
+  P.viscous = cfg->mu_ref != 0.0; P.sst = sst ? 1 : 0; P.sa = sa ? 1 : 0; P.kkl = cfg->turbulence == F3D_TURB_KKL ? 1 : 0;
+  P.tkl_inf = cfg->tkl_inf;
   P.trans_bc = cfg->transition == F3D_TRANS_BC ? 1 : 0; P.tu_inf = cfg->tu_inf;
   P.nu_cr = cfg->mu_ref != 0.0 ? 5.0 / (cfg->density_inf * cfg->vel_mag * 1.0 / cfg->mu_ref) : 0.0;   // chi_2 / Reynolds_number (state.f90:89)
   P.CFL = cfg->CFL; P.global_time_step = cfg->global_time_step;
@@ -137,7 +140,7 @@ static int create_impl(Fest3dGpuCtx* ctx, const Fest3dGpuConfig* cfg, int device
   sc[1] = cfg->density_inf * cfg->vel_mag;
   sc[2] = sc[3] = sc[4] = cfg->density_inf * cfg->vel_mag * cfg->vel_mag;
   sc[5] = (0.5 * cfg->density_inf * (cfg->vel_mag * cfg->vel_mag * cfg->vel_mag) + ((cfg->gm / (cfg->gm - 1.)) * cfg->pressure_inf));
-  if (sst) { sc[6] = cfg->density_inf * cfg->vel_mag * cfg->tk_inf; sc[7] = cfg->density_inf * cfg->vel_mag * cfg->tw_inf; }
+  if (sst) { sc[6] = cfg->density_inf * cfg->vel_mag * cfg->tk_inf; sc[7] = cfg->density_inf * cfg->vel_mag * (P.kkl ? cfg->tkl_inf : cfg->tw_inf); }   // resnorm.f90:148-153
   if (sa) sc[6] = cfg->density_inf * cfg->vel_mag * cfg->tv_inf;   // resnorm.f90:157-158
 
   F3D_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));

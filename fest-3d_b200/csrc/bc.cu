@@ -95,8 +95,12 @@ __global__ void k_bc_face(const Params P, double* __restrict__ q, const double* 
   const long long o = (long long)a * fr.sa + (long long)b * fr.sb;
   const long long fs = P.L.fs;
   const int id = P.bc_id[face - 1];
-  const bool sst = P.sst != 0;
+  const bool sst = P.sst != 0;   // two-equation layout (sst, sst2003, kkl)
   const bool sa = P.sa != 0;   // the SA variable (field 5) follows the pattern of tk on every face (bc_primitive.f90:246 ... 543)
+  // k-kL: kL (field 6) follows the pattern of omega with its own fixed value (fixed_tkl) -- except at the subsonic inlet, which fixes it
+  // to fixed_tw (bc_primitive.f90:333-336, reproduced), and at the wall, which takes the anti copy instead of the wall-omega rule (:548-550)
+  const bool kkl = P.kkl != 0;
+  const int FIX_7 = kkl ? F3D_FIX_TKL : F3D_FIX_TW;
   double* rho = q; double* u = q + fs; double* v = q + 2 * fs; double* w = q + 3 * fs; double* p = q + 4 * fs;
   double* tk = q + 5 * fs; double* tw = q + 6 * fs;
   const double(*fx)[6] = P.fixed;
@@ -107,7 +111,7 @@ __global__ void k_bc_face(const Params P, double* __restrict__ q, const double* 
       if (P.current_iter <= 2) {
         fix3(rho, fr, o, fx[F3D_FIX_DENSITY][fi]); fix3(u, fr, o, fx[F3D_FIX_X_SPEED][fi]); fix3(v, fr, o, fx[F3D_FIX_Y_SPEED][fi]);
         fix3(w, fr, o, fx[F3D_FIX_Z_SPEED][fi]); fix3(p, fr, o, fx[F3D_FIX_PRESSURE][fi]);
-        if (sst) { fix3(tk, fr, o, fx[F3D_FIX_TK][fi]); fix3(tw, fr, o, fx[F3D_FIX_TW][fi]); }
+        if (sst) { fix3(tk, fr, o, fx[F3D_FIX_TK][fi]); fix3(tw, fr, o, fx[FIX_7][fi]); }
         if (sa) fix3(tk, fr, o, fx[F3D_FIX_TV][fi]);
       }
       break;
@@ -147,7 +151,8 @@ __global__ void k_bc_face(const Params P, double* __restrict__ q, const double* 
       }
       copy3_anti(u, fr, o); copy3_anti(v, fr, o); copy3_anti(w, fr, o);
       if (sa) copy3_anti(tk, fr, o);
-      if (sst) {
+      if (kkl) { copy3_anti(tk, fr, o); copy3_anti(tw, fr, o); }
+      if (sst && !kkl) {
         copy3_anti(tk, fr, o);
         const double* dist = geom + (long long)G_DIST * fs;
         const long long g1 = GHO_(1), c = INT_(1);
@@ -205,7 +210,7 @@ __global__ void k_bc_face(const Params P, double* __restrict__ q, const double* 
         double Ub2, Cb2, a2, b2, x2, y2, z2;
         far_field_state(P, q, gn, fr, olast, Ub2, Cb2, a2, b2, x2, y2, z2);
         if (Ub2 > 0.) { copy3_flat(tk, fr, o); if (sst) copy3_flat(tw, fr, o); }
-        else if (sst) { fix3(tk, fr, o, fx[F3D_FIX_TK][fi]); fix3(tw, fr, o, fx[F3D_FIX_TW][fi]); }
+        else if (sst) { fix3(tk, fr, o, fx[F3D_FIX_TK][fi]); fix3(tw, fr, o, fx[FIX_7][fi]); }
         else fix3(tk, fr, o, fx[F3D_FIX_TV][fi]);
       }
       break;
@@ -231,7 +236,7 @@ __global__ void k_bc_face(const Params P, double* __restrict__ q, const double* 
         double Ub2, Cb2, a2, b2, x2, y2, z2;
         far_field_state(P, q, gn, fr, olast, Ub2, Cb2, a2, b2, x2, y2, z2);
         if (Ub2 > 0.) { copy3_flat(tk, fr, o); if (sst) copy3_flat(tw, fr, o); }
-        else if (sst) { fix3(tk, fr, o, fx[F3D_FIX_TK][fi]); fix3(tw, fr, o, fx[F3D_FIX_TW][fi]); }
+        else if (sst) { fix3(tk, fr, o, fx[F3D_FIX_TK][fi]); fix3(tw, fr, o, fx[FIX_7][fi]); }
         else fix3(tk, fr, o, fx[F3D_FIX_TV][fi]);
       }
       break;

@@ -36,14 +36,15 @@ struct Params {
   int farlike[6];         // 1 when id is -8 or -9 (face state = ghost value)
   int ppm_flag;           // boundary re-reconstruction active (ppm / weno / weno_NM or a pole face)
   int current_iter;
-  int viscous, sst, sa;   // sa: Spalart-Allmaras (n_var 6)
+  int viscous, sst, sa;   // sst: a two-equation model with n_var 7 (sst, sst2003, kkl: same field layout); sa: Spalart-Allmaras (n_var 6)
+  int kkl;                // k-kL model: variable 7 is kL; its own mu_t, viscous-flux constants, source and point-implicit terms
   int trans_bc;           // transition = bc: algebraic gamma_BC factor on the production term (source.f90:467-604, 985-1194)
   double zlo[3], zhi[3];  // make_{F,G,H}_flux_zero at the first / last face of each direction (bc.f90:53-66)
   double c1, c2, c3;
   double CFL, global_time_step;
   double gm, R_gas, mu_ref, T_ref, Sutherland_temp, Pr, tPr;
   double inv_Pr, inv_tPr, inv_gm1;   // reciprocals of Pr, tPr, gm-1
-  double density_inf, x_speed_inf, y_speed_inf, z_speed_inf, pressure_inf, tk_inf, tw_inf, tv_inf, MInf;
+  double density_inf, x_speed_inf, y_speed_inf, z_speed_inf, pressure_inf, tk_inf, tw_inf, tv_inf, tkl_inf, MInf;
   double gama1, gama2, cd_floor, mut_floor, pk_limiter;
   double gama1_default, gama2_default;   // global_sst.f90:15-16 as they stand when add_sst_source never runs (transition = bc)
   double tu_inf, nu_cr;   // transition = bc: free-stream turbulence intensity (percent), chi_2 / Reynolds_number

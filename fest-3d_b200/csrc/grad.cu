@@ -87,7 +87,13 @@ __global__ void __launch_bounds__(128, 5) k_gradients(const Params P, const doub
     const double fv1 = (pow3(xi)) / ((pow3(xi)) + (pow3(kCv1)));
     mu3[fs + c] = density * tv * fv1;
   }
-  if (NG == 6) {
+  if (NG == 6 && P.kkl) {   // k-kL: mu_t = cmu^(1/4) rho kL / max(sqrt(k), 1e-20), 0 below 1e-14 (viscosity.f90:469-484); no F1
+    const double density = q[c], tk = q[5 * fs + c], tkl = q[6 * fs + c];
+    double m = kKklCmu25 * density * tkl / (fmax(sqrt(tk), 1.e-20));
+    if (tkl < 1.e-14 || tk < 1.e-14) m = 0.0;
+    mu3[fs + c] = m;
+    mu3[2 * fs + c] = 0.0;
+  } else if (NG == 6) {
     const double density = q[c], tk = q[5 * fs + c], tw = q[6 * fs + c];
     const double d = geom[(long long)G_DIST * fs + c];
     const double var1 = sqrt(tk) * rcp64(kBstar * tw * d);
@@ -167,7 +173,10 @@ __global__ void k_gradient_bc(const Params P, const double* __restrict__ q, cons
     if (id == -5) mu3[fs + cg] = -mu3[fs + ci];
     else if (id == -1 || id == -2 || id == -3 || id == -4 || id == -6 || id == -7 || id == -8 || id == -9) mu3[fs + cg] = mu3[fs + ci];
   }
-  if (NG == 6) {
+  if (NG == 6 && P.kkl) {   // viscosity.f90:488-531: copy on -4..-1, -6, -8, -9 (no -7), anti on the wall
+    if (id == -5) mu3[fs + cg] = -mu3[fs + ci];
+    else if (id == -1 || id == -2 || id == -3 || id == -4 || id == -6 || id == -8 || id == -9) mu3[fs + cg] = mu3[fs + ci];
+  } else if (NG == 6) {
     if (id == -5) { mu3[fs + cg] = -mu3[fs + ci]; mu3[2 * fs + cg] = mu3[2 * fs + ci]; }
     else if (id == -1 || id == -2 || id == -3 || id == -4 || id == -6 || id == -7 || id == -8 || id == -9) {
       mu3[fs + cg] = mu3[fs + ci]; mu3[2 * fs + cg] = mu3[2 * fs + ci];

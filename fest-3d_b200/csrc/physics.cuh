@@ -10,6 +10,10 @@ namespace f3d {
 // SST closure constants (src/global/global_sst.f90:6-16)
 __device__ constexpr double kSigmaK1 = 0.85, kSigmaK2 = 1.0, kSigmaW1 = 0.5, kSigmaW2 = 0.856;
 __device__ constexpr double kBeta1 = 0.075, kBeta2 = 0.0828, kBstar = 0.09, kA1 = 0.31;
+// k-kL closure constants (src/global/global_kkl.f90:6-15); sigma_k = sigma_phi = 1
+__device__ constexpr double kKklZeta1 = 1.2, kKklZeta2 = 0.97, kKklZeta3 = 0.13, kKklCmu = 0.09, kKklKappa = 0.41, kKklC11 = 10.0, kKklC12 = 1.3, kKklCd1 = 4.7;
+__device__ constexpr double kKklCmu25 = 0.54772255750516607;   // cmu**0.25
+__device__ constexpr double kKklCmu75 = 0.16431676725154984;   // cmu**0.75
 // SA closure constants (src/global/global_sa.f90:6-19)
 __device__ constexpr double kCb1 = 0.1355, kCb2 = 0.6220, kCw2 = 0.3, kCw3 = 2.0, kCv1 = 7.1, kSigmaSA = 2. / 3., kKappaSA = 0.41;
 __device__ constexpr double kCw1 = (kCb1 / (kKappaSA * kKappaSA)) + ((1 + kCb2) / kSigmaSA);

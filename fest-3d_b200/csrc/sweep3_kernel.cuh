@@ -124,7 +124,7 @@ __device__ __forceinline__ void bar_group(int id, int count) { asm volatile("bar
 // the K threads' ring), and the cell packet of the I rows (q, volume, F1, source terms).
 template <int NV, bool VISC>
 __device__ __forceinline__ void cell_work(const Params& P, const KArgs& a, double* __restrict__ smem, int tx, int r, int i, int j, int kc,
-                                          bool need_dt, bool k_active, double* __restrict__ nrm /* [NV+1], stride 64 */) {
+                                          bool need_dt, bool k_active, double* __restrict__ nrm /* [NV+1], stride 64 */, bool kkl = false) {
   using S = Sm<NV, VISC>;
   constexpr bool SST = (NV == 7), SA = (NV == 6), TURB = SST || SA;
   constexpr int NF = S::NF;
@@ -220,7 +220,13 @@ __device__ __forceinline__ void cell_work(const Params& P, const KArgs& a, doubl
       for (int v = 1; v < NV; ++v) u1[v] = qc[v] * u1[0];
     }
     u1[4] = (u1[4] * P.inv_gm1 + 0.5 * (u1[1] * u1[1] + u1[2] * u1[2] + u1[3] * u1[3])) * rcp64(u1[0]) + 0.;
-    if (SST) {
+    if (SST && kkl) {   // update.f90:399-404: u1(6), u1(7) are rho*k, rho*kL here, used where the model has k, kL -- reproduced
+      const double mu_c = pk[NMAIN], dist_c = a.geom[(long long)G_DIST * fs + cc];
+      const double eta = u1[0] * dist_c * (sqrt(0.3 * u1[5]) / (20 * mu_c));
+      const double fphi = (1 + kKklCd1 * eta) / (1 + (eta * eta) * (eta * eta));
+      R[5] = R[5] / (1. + ((2.5 * (kKklCmu75 * sqrt(u1[0]) * (u1[5] * sqrt(u1[5])) / fmax(u1[6], 1.e-20)) + (2 * mu_c / (dist_c * dist_c))) * dtc));
+      R[6] = R[6] / (1. + (6 * mu_c * fphi / (dist_c * dist_c)) * dtc);
+    } else if (SST) {
       const double F1 = VISC ? pk[NMAIN] : 0.0;
       const double beta = kBeta1 * F1 + (1. - F1) * kBeta2;
       R[5] = R[5] * rcp64(1 + (beta * qc[6] * dtc));
@@ -485,7 +491,7 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a,
 #pragma unroll
         for (int v = 0; v < NV; ++v) L[v] = smem[o_lr + v * f_x];
         face_eval<NV, SCHEME, VISC, PS, PSQ>(P, d, smem + o_ql, smem + o_qh, smem + o_ql - PW + NV * PSQ, smem + o_qh - PW + NV * PSQ, gA_, gnx, gny, gnz, cpos, mx, L, lo,
-                                             krow ? flux_on_k : true, need_dt, F, lam, vis, tur);
+                                             krow ? flux_on_k : true, need_dt, F, lam, vis, tur, RARE && P.kkl);
 #pragma unroll
         for (int v = 0; v < NV; ++v) smem[o_fw + v * f_x] = F[v];
         if (need_dt || krow) {
@@ -500,7 +506,65 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a,
         double* const pk = smem + S::OFF_PK + (k & 1) * S::NPK * NMAIN + cell;
         const double volc = smem[S::OFF_PRIV + (S::P_VOL + (k & 1)) * NMAIN + cell];
         pk[0] = volc;
-        if (SST && VISC) {   // SST source terms (source.f90:214-268)
+        if (SST && VISC && RARE && P.kkl) {   // k-kL source terms (source.f90:607-832)
+          const double* const rB = rA - pA + pB;   // the same cell's record in plane k+1 ...
+          mbar_wait((char*)mbar + 8 * ((k + 1) & 1), plane_parity(k + 1));   // ... which only the K rows have waited for so far
+          const long long cI = c;
+          const double density = qA[0], tk = qA[5 * PSQ], tkl = qA[6 * PSQ];
+          double gv[3][3];   // velocity gradients of the cell: gv[component][direction]
+#pragma unroll
+          for (int cc = 0; cc < 3; ++cc) { gv[cc][0] = rA[(3 * cc + 0) * PS]; gv[cc][1] = rA[(3 * cc + 1) * PS]; gv[cc][2] = rA[(3 * cc + 2) * PS]; }
+          const double mut = rA[(S::OFF_MU + 1) * PS], mu_c = rA[S::OFF_MU * PS];
+          const double S11 = 0.5 * (gv[0][0] + gv[0][0]), S12 = 0.5 * (gv[0][1] + gv[1][0]), S13 = 0.5 * (gv[0][2] + gv[2][0]);
+          const double S22 = 0.5 * (gv[1][1] + gv[1][1]), S23 = 0.5 * (gv[1][2] + gv[2][1]), S33 = 0.5 * (gv[2][2] + gv[2][2]);
+          const double delv = gv[0][0] + gv[1][1] + gv[2][2];
+          const double tkk = (2.0 / 3.0) * density * tk;
+          const double T11 = mut * (2 * S11 - (2.0 / 3.0) * delv) - tkk, T22 = mut * (2 * S22 - (2.0 / 3.0) * delv) - tkk, T33 = mut * (2 * S33 - (2.0 / 3.0) * delv) - tkk;
+          const double T12 = mut * (2 * S12), T13 = mut * (2 * S13), T23 = mut * (2 * S23);
+          double P_k = 0.;
+          P_k = P_k + T11 * gv[0][0] + T12 * gv[0][1] + T13 * gv[0][2];
+          P_k = P_k + T12 * gv[1][0] + T22 * gv[1][1] + T23 * gv[1][2];
+          P_k = P_k + T13 * gv[2][0] + T23 * gv[2][1] + T33 * gv[2][2];
+          const double D_k = kKklCmu75 * density * ((tk * tk) * sqrt(tk)) / fmax(tkl, 1.e-20);
+          P_k = fmin(P_k, 20 * D_k);
+          // Green-Gauss sums of the cell gradients over the six faces (the k-1 neighbour is no longer staged: global memory / L2)
+          const double* __restrict__ gI = a.geom + (long long)G_IA * fs;
+          const double* __restrict__ gJ = a.geom + (long long)G_JA * fs;
+          const double* __restrict__ gK = a.geom + (long long)G_KA * fs;
+          double lap[3] = {0., 0., 0.};
+#pragma unroll
+          for (int dd = 0; dd < 3; ++dd) {
+            const double wIl = gI[(1 + dd) * fs + cI] * gI[cI], wIh = gI[(1 + dd) * fs + cI + 1] * gI[cI + 1];
+            const double wJl = gJ[(1 + dd) * fs + cI] * gJ[cI], wJh = gJ[(1 + dd) * fs + cI + Ly.sj] * gJ[cI + Ly.sj];
+            const double wKl = gK[(1 + dd) * fs + cI] * gK[cI], wKh = gK[(1 + dd) * fs + cI + Ly.sk] * gK[cI + Ly.sk];
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) {
+              const int f = 3 * cc + dd;
+              const double g0 = gv[cc][dd];
+              const double s2 = (-(rA[f * PS - 1] + g0) * wIl - (rA[f * PS - PW] + g0) * wJl - (a.grad[(long long)f * fs + cI - Ly.sk] + g0) * wKl +
+                                 (rA[f * PS + 1] + g0) * wIh + (rA[f * PS + PW] + g0) * wJh + (rB[f * PS] + g0) * wKh) / (2 * volc);
+              lap[cc] += s2;
+            }
+          }
+          const double udd = sqrt(lap[0] * lap[0] + lap[1] * lap[1] + lap[2] * lap[2]);
+          const double ud = sqrt(2 * (S11 * S11 + S12 * S12 + S13 * S13 + S12 * S12 + S22 * S22 + S23 * S23 + S13 * S13 + S23 * S23 + S33 * S33));
+          const double dist_c = a.geom[(long long)G_DIST * fs + cI];
+          double Lvk = kKklKappa * fabs(ud / fmax(udd, 1.e-20));
+          const double fp = fmin(fmax(P_k / D_k, 0.5), 1.0);
+          Lvk = fmax(Lvk, tkl / fmax((tk * kKklC11), 1.e-20));
+          Lvk = fmin(Lvk, kKklC12 * kKklKappa * dist_c * fp);
+          const double eta = density * dist_c * sqrt(0.3 * tk) / (20 * mu_c);
+          const double fphi = (1 + kKklCd1 * eta) / (1 + (eta * eta) * (eta * eta));
+          const double rr = (tkl / fmax(tk * Lvk, 1.e-20));
+          const double cphi1 = (kKklZeta1 - kKklZeta2 * (rr * rr));
+          const double P_kl = cphi1 * tkl * P_k / fmax(tk, 1.e-20);
+          const double D_kl = kKklZeta3 * density * (tk * sqrt(tk));
+          const double S_k = P_k - D_k - 2 * mu_c * tk / (dist_c * dist_c);
+          const double S_kl = P_kl - D_kl - 6 * mu_c * tkl * fphi / (dist_c * dist_c);
+          pk[NMAIN] = mu_c;
+          pk[2 * NMAIN] = S_k * volc;
+          pk[3 * NMAIN] = S_kl * volc;
+        } else if (SST && VISC) {   // SST source terms (source.f90:214-268)
           double g[6][3];
 #pragma unroll
           for (int cc = 0; cc < 6; ++cc) {
@@ -607,7 +671,7 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a,
       for (int r = r_lo; r < r_hi; ++r) {
         const int jc = j0 + r;
         if (ic <= Ly.imx - 1 && jc <= Ly.jmx - 1)
-          cell_work<NV, VISC>(P, a, smem, lane, r, ic, jc, k - 1, need_dt, k_active, smem + S::OFF_NRM + (wid == W_C ? 32 : 0) + lane);
+          cell_work<NV, VISC>(P, a, smem, lane, r, ic, jc, k - 1, need_dt, k_active, smem + S::OFF_NRM + (wid == W_C ? 32 : 0) + lane, RARE && P.kkl);
       }
     }
     cp_async_wait_all();

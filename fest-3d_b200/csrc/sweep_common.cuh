@@ -193,7 +193,7 @@ __device__ __forceinline__ void recon3(const Params& P, const double (&qm)[NV], 
 template <int NV, int PS, int PSQ>
 __device__ __forceinline__ void viscous_face(const Params& P, const double* __restrict__ ql_, const double* __restrict__ qh_,
                                              const double* __restrict__ rl, const double* __restrict__ rh, double A, double nx, double ny,
-                                             double nz, bool sst_on, bool need_dt, double (&F)[NV], double& vis, double& tur) {
+                                             double nz, bool sst_on, bool need_dt, double (&F)[NV], double& vis, double& tur, bool kkl = false) {
   using R = RecF<NV, true>;
   constexpr bool SST = (NV == 7), SA = (NV == 6), TURB = SST || SA;
   constexpr int NG = R::NG;
@@ -267,10 +267,10 @@ __device__ __forceinline__ void viscous_face(const Params& P, const double* __re
   F[3] = F[3] - ((Txz * nx + Tyz * ny + Tzz * nz) * A);
   F[4] = F[4] - (A * (((Txx * uf + Txy * vf + Txz * wf + Qx) * nx) + ((Txy * uf + Tyy * vf + Tyz * wf + Qy) * ny) +
                       ((Txz * uf + Tyz * vf + Tzz * wf + Qz) * nz)));
-  if (SST && sst_on) {
+  if (SST && (sst_on || kkl)) {   // k-kL (viscous.f90:450-567): the same form with sigma_k = sigma_phi = 1, in all three directions whatever kmx
     const double F1 = 0.5 * (rl[(R::OFF_MU + 2) * PS] + rh[(R::OFF_MU + 2) * PS]);
-    const double sk = kSigmaK1 * F1 + kSigmaK2 * (1.0 - F1);
-    const double sw = kSigmaW1 * F1 + kSigmaW2 * (1.0 - F1);
+    const double sk = kkl ? 1.0 : kSigmaK1 * F1 + kSigmaK2 * (1.0 - F1);
+    const double sw = kkl ? 1.0 : kSigmaW1 * F1 + kSigmaW2 * (1.0 - F1);
     const double rhof = 0.5 * (ql[0] + qh[0]);
     const double tkf = 0.5 * (ql[NV - 2] + qh[NV - 2]);
     const double Tk = -2.0 * rhof * tkf * (1. / 3.);
@@ -307,7 +307,7 @@ template <int NV, int SCHEME, bool VISC, int PS, int PSQ>
 __device__ __forceinline__ void face_eval(const Params& P, int d, const double* __restrict__ ql, const double* __restrict__ qh,
                                           const double* __restrict__ rl, const double* __restrict__ rh, double A, double nx, double ny,
                                           double nz, int f, int m, double (&L)[NV], double (&R)[NV], bool flux_on, bool need_dt,
-                                          double (&F)[NV], double& lam, double& vis, double& tur) {
+                                          double (&F)[NV], double& lam, double& vis, double& tur, bool kkl = false) {
   if (P.interpolant != F3D_INTERP_NONE) {
     if (f == 1 && P.phys[2 * d]) {
       const bool far = P.farlike[2 * d] != 0;
@@ -332,7 +332,7 @@ __device__ __forceinline__ void face_eval(const Params& P, int d, const double* 
     const double vn = fabs((qh[1 * PSQ] * nx) + (qh[2 * PSQ] * ny) + (qh[3 * PSQ] * nz));
     lam = A * (vn + cbar);
   }
-  if (VISC) viscous_face<NV, PS, PSQ>(P, ql, qh, rl, rh, A, nx, ny, nz, (NV == 7) && flux_on, need_dt, F, vis, tur);
+  if (VISC) viscous_face<NV, PS, PSQ>(P, ql, qh, rl, rh, A, nx, ny, nz, (NV == 7) && flux_on, need_dt, F, vis, tur, kkl);
 }
 
 }  // namespace f3d

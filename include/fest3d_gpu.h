@@ -43,7 +43,7 @@ enum { F3D_T_NONE = 0, F3D_T_RK2 = 1, F3D_T_RK4 = 2, F3D_T_TVDRK2 = 3, F3D_T_TVD
 /* slots of the per-face fixed values (src/vartypes.f90:307-334, src/boundary/read_bc.f90:28-147) */
 enum {
   F3D_FIX_DENSITY = 0, F3D_FIX_PRESSURE, F3D_FIX_X_SPEED, F3D_FIX_Y_SPEED, F3D_FIX_Z_SPEED,
-  F3D_FIX_TK, F3D_FIX_TW, F3D_FIX_WALL_TEMP, F3D_FIX_TPRESSURE, F3D_FIX_TTEMPERATURE, F3D_FIX_TV,
+  F3D_FIX_TK, F3D_FIX_TW, F3D_FIX_WALL_TEMP, F3D_FIX_TPRESSURE, F3D_FIX_TTEMPERATURE, F3D_FIX_TV, F3D_FIX_TKL,
   F3D_NFIX
 };
 
@@ -55,14 +55,14 @@ enum {
   F3D_ERR_NEGATIVE_STATE = 8,/* rho<0, p<0 or NaN after update   update.f90:448-452 */
   F3D_ERR_GEOMETRY = 16,      /* non-positive cell volume  geometry.f90:476-494 (fest3d_gpu_setup_geometry only) */
   F3D_ERR_IO = 32,            /* checkpoint file cannot be written / read (fest3d_gpu_checkpoint_*, fest3d_gpu_restart) */
-  F3D_ERR_UNSUPPORTED = 64,  /* implicit / plusgs / saBC / kkl / lctm2015: not on this path */
+  F3D_ERR_UNSUPPORTED = 64,  /* implicit / plusgs / saBC / lctm2015 (and kkl with F3D_GRADIENTS=fused): not on this path */
   F3D_ERR_CUDA = 128,
   F3D_ERR_ARGUMENT = 256,    /* also: an interface / periodic face that was neither linked locally nor given a communicator */
   F3D_ERR_PEER = 512         /* another rank reported an error in this call: every rank returns (Fatal_error stops the whole job) */
 };
 
 typedef struct {
-  int imx, jmx, kmx, n_var;            /* node counts of the block; n_var 5 (none), 6 (sa) or 7 (sst)    vartypes.f90:21-26 */
+  int imx, jmx, kmx, n_var;            /* node counts of the block; n_var 5 (none), 6 (sa) or 7 (sst, sst2003, kkl)   vartypes.f90:21-26 */
   int scheme, interpolant, turbulence, transition;
   int time_accuracy;                   /* F3D_T_*                                                update.f90:171 */
   int time_stepping;                   /* 0 = 'l' local, 1 = 'g' global                          time.f90:323-326 */
@@ -85,6 +85,7 @@ typedef struct {
   double tk_inf, tw_inf, vel_mag, MInf;
   double tv_inf;                       /* free-stream nu-tilde of the SA model                   state.f90:105-106 */
   double tu_inf;                       /* free-stream turbulence intensity in percent (transition = bc)   source.f90:579,1164 */
+  double tkl_inf;                      /* free-stream kL of the k-kL model                       state.f90:101-103 */
   double fixed[F3D_NFIX][6];           /* fixed_density(6), fixed_pressure(6) ...                read_bc.f90 */
 } Fest3dGpuConfig;
 

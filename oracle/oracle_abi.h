@@ -21,13 +21,13 @@ extern "C" {
  * update.f90:171-225, time.f90:323-326) */
 enum { ORC_VAN_LEER = 0, ORC_LDFSS0 = 1, ORC_AUSM = 2, ORC_AUSMP = 3, ORC_AUSMUP = 4, ORC_SLAU = 5 };
 enum { ORC_NONE = 0, ORC_MUSCL = 1, ORC_PPM = 2, ORC_WENO = 3, ORC_WENO_NM = 4 };
-enum { ORC_TURB_NONE = 0, ORC_TURB_SA = 1, ORC_TURB_SST = 3, ORC_TURB_SST2003 = 4 };
+enum { ORC_TURB_NONE = 0, ORC_TURB_SA = 1, ORC_TURB_SST = 3, ORC_TURB_SST2003 = 4, ORC_TURB_KKL = 5 };
 enum { ORC_T_NONE = 0, ORC_T_RK2 = 1, ORC_T_RK4 = 2, ORC_T_TVDRK2 = 3, ORC_T_TVDRK3 = 4 };
 
 /* fixed-value slots (reference: vartypes.f90:307-334) */
 enum {
   ORC_FIX_DENSITY = 0, ORC_FIX_PRESSURE, ORC_FIX_X_SPEED, ORC_FIX_Y_SPEED, ORC_FIX_Z_SPEED,
-  ORC_FIX_TK, ORC_FIX_TW, ORC_FIX_WALL_TEMP, ORC_FIX_TPRESSURE, ORC_FIX_TTEMPERATURE, ORC_FIX_TV,
+  ORC_FIX_TK, ORC_FIX_TW, ORC_FIX_WALL_TEMP, ORC_FIX_TPRESSURE, ORC_FIX_TTEMPERATURE, ORC_FIX_TV, ORC_FIX_TKL,
   ORC_NFIX
 };
 
@@ -54,6 +54,7 @@ typedef struct {
   double tk_inf, tw_inf, vel_mag, MInf;
   double tv_inf;
   double tu_inf;                     /* percent */
+  double tkl_inf;                    /* free-stream kL of the k-kL model (state.f90:101-103) */
   double fixed[ORC_NFIX][6];
 } OracleConfig;
 

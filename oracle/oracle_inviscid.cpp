@@ -13,7 +13,7 @@ static inline double fmin3(double a, double b, double c) { return std::fmin(std:
 void Block::setup(const OracleConfig& cfg) {
   c = cfg;
   imx = c.imx; jmx = c.jmx; kmx = c.kmx; nv = c.n_var;
-  n_grad = (c.turbulence == ORC_TURB_SST || c.turbulence == ORC_TURB_SST2003) ? 6 : (c.turbulence == ORC_TURB_SA ? 5 : 4);   // gradients.f90:160-175
+  n_grad = (c.turbulence == ORC_TURB_SST || c.turbulence == ORC_TURB_SST2003 || c.turbulence == ORC_TURB_KKL) ? 6 : (c.turbulence == ORC_TURB_SA ? 5 : 4);   // gradients.f90:160-175
   qp.alloc(-2, imx + 2, -2, jmx + 2, -2, kmx + 2, nv);
   Temp.alloc(-2, imx + 2, -2, jmx + 2, -2, kmx + 2);
   residue.alloc(1, imx - 1, 1, jmx - 1, 1, kmx - 1, nv);
@@ -135,6 +135,7 @@ static void fix(Block& B, int var, int slot, int face) {
 
 static inline bool is_sst(const Block& B) { return B.c.turbulence == ORC_TURB_SST || B.c.turbulence == ORC_TURB_SST2003; }
 static inline bool is_sa(const Block& B) { return B.c.turbulence == ORC_TURB_SA; }
+static inline bool is_kkl(const Block& B) { return B.c.turbulence == ORC_TURB_KKL; }
 
 // FT_bc.f90:15-107  flow_tangency.  NOTE (kept defect): for J and K faces the dot product uses the
 // Jfaces/Kfaces normal but the reflection subtracts 2*dot*Ifaces(i,1,k)%n etc. (FT_bc.f90:66-69,...)
@@ -248,7 +249,7 @@ static void far_field(Block& B, int face) {
         double s = B.qp(i, j, k, 5) / std::pow(B.qp(i, j, k, 1), c.gm);
         B.qp(ig, jg, kg, 1) = std::pow(Cb * Cb / (c.gm * s), 1. / (c.gm - 1.));
         B.qp(ig, jg, kg, 5) = (B.qp(ig, jg, kg, 1) * Cb * Cb / c.gm);
-        if (is_sst(B)) { copy3(B, 6, FLAT, face); copy3(B, 7, FLAT, face); }
+        if (is_sst(B) || is_kkl(B)) { copy3(B, 6, FLAT, face); copy3(B, 7, FLAT, face); }
         if (is_sa(B)) copy3(B, 6, FLAT, face);
         already_fixed = 0;
       } else {
@@ -261,6 +262,7 @@ static void far_field(Block& B, int face) {
         B.qp(ig, jg, kg, 5) = (B.qp(ig, jg, kg, 1) * Cb * Cb / c.gm);
         if (already_fixed == 0) {
           if (is_sst(B)) { fix(B, 6, ORC_FIX_TK, face); fix(B, 7, ORC_FIX_TW, face); }
+          if (is_kkl(B)) { fix(B, 6, ORC_FIX_TK, face); fix(B, 7, ORC_FIX_TKL, face); }
           if (is_sa(B)) fix(B, 6, ORC_FIX_TV, face);
         }
         already_fixed = 1;
@@ -318,7 +320,7 @@ static void total_pressure(Block& B, int face) {
         B.qp(ig, jg, kg, 2) = B.qp(i, j, k, 2) + vel_diff * nx;
         B.qp(ig, jg, kg, 3) = B.qp(i, j, k, 3) + vel_diff * ny;
         B.qp(ig, jg, kg, 4) = B.qp(i, j, k, 4) + vel_diff * nz;
-        if (is_sst(B)) { copy3(B, 6, FLAT, face); copy3(B, 7, FLAT, face); }
+        if (is_sst(B) || is_kkl(B)) { copy3(B, 6, FLAT, face); copy3(B, 7, FLAT, face); }
         if (is_sa(B)) copy3(B, 6, FLAT, face);
       } else {
         double vel_diff = Unb - Uninf;
@@ -326,6 +328,7 @@ static void total_pressure(Block& B, int face) {
         B.qp(ig, jg, kg, 3) = c.y_speed_inf + vel_diff * ny;
         B.qp(ig, jg, kg, 4) = c.z_speed_inf + vel_diff * nz;
         if (is_sst(B)) { fix(B, 6, ORC_FIX_TK, face); fix(B, 7, ORC_FIX_TW, face); }
+        if (is_kkl(B)) { fix(B, 6, ORC_FIX_TK, face); fix(B, 7, ORC_FIX_TKL, face); }
         if (is_sa(B)) fix(B, 6, ORC_FIX_TV, face);
       }
       int im = ig, jm = jg, km = kg;
@@ -366,6 +369,9 @@ void Block::populate_ghost_primitive() {
   Block& B = *this;
   const bool sst = is_sst(B);
   const bool sa = is_sa(B);   // the SA variable follows the pattern of tk on every face (bc_primitive.f90:246,288,327,373,425,463,543)
+  // k-kL: kL (variable 7) follows the pattern of omega, except that the wall takes the anti copy instead of the wall-omega rule (:548-550)
+  // and the subsonic inlet fixes it to fixed_tw, not fixed_tkl (:333-336, reproduced)
+  const bool kkl = is_kkl(B);
   for (int face = 1; face <= 6; ++face) {
     switch (c.bc_id[face - 1]) {
       case -1:  // supersonic_inlet :229
@@ -373,19 +379,20 @@ void Block::populate_ghost_primitive() {
           fix(B, 1, ORC_FIX_DENSITY, face); fix(B, 2, ORC_FIX_X_SPEED, face); fix(B, 3, ORC_FIX_Y_SPEED, face);
           fix(B, 4, ORC_FIX_Z_SPEED, face); fix(B, 5, ORC_FIX_PRESSURE, face);
           if (sst) { fix(B, 6, ORC_FIX_TK, face); fix(B, 7, ORC_FIX_TW, face); }
+          if (kkl) { fix(B, 6, ORC_FIX_TK, face); fix(B, 7, ORC_FIX_TKL, face); }
           if (sa) fix(B, 6, ORC_FIX_TV, face);
         }
         break;
       case -2:  // supersonic_outlet :270
         for (int v = 1; v <= 5; ++v) copy3(B, v, FLAT, face);
-        if (sst) { copy3(B, 6, FLAT, face); copy3(B, 7, FLAT, face); }
+        if (sst || kkl) { copy3(B, 6, FLAT, face); copy3(B, 7, FLAT, face); }
         if (sa) copy3(B, 6, FLAT, face);
         break;
       case -3:  // subsonic_inlet :308
         if (current_iter <= 2) {
           fix(B, 1, ORC_FIX_DENSITY, face); fix(B, 2, ORC_FIX_X_SPEED, face); fix(B, 3, ORC_FIX_Y_SPEED, face);
           fix(B, 4, ORC_FIX_Z_SPEED, face);
-          if (sst) { fix(B, 6, ORC_FIX_TK, face); fix(B, 7, ORC_FIX_TW, face); }
+          if (sst || kkl) { fix(B, 6, ORC_FIX_TK, face); fix(B, 7, ORC_FIX_TW, face); }
           if (sa) fix(B, 6, ORC_FIX_TV, face);
         }
         copy3(B, 5, FLAT, face);
@@ -393,7 +400,7 @@ void Block::populate_ghost_primitive() {
       case -4:  // subsonic_outlet :352
         for (int v = 1; v <= 4; ++v) copy3(B, v, FLAT, face);
         if (current_iter <= 2) fix(B, 5, ORC_FIX_PRESSURE, face);
-        if (sst) { copy3(B, 6, FLAT, face); copy3(B, 7, FLAT, face); }
+        if (sst || kkl) { copy3(B, 6, FLAT, face); copy3(B, 7, FLAT, face); }
         if (sa) copy3(B, 6, FLAT, face);
         break;
       case -5:  // wall :392 -> pressure symm, temp_based_density, no_slip :528
@@ -401,17 +408,18 @@ void Block::populate_ghost_primitive() {
         temp_based_density(B, face);
         copy3(B, 2, ANTI, face); copy3(B, 3, ANTI, face); copy3(B, 4, ANTI, face);
         if (sst) { copy3(B, 6, ANTI, face); set_omega_at_wall(B, face); }
+        if (kkl) { copy3(B, 6, ANTI, face); copy3(B, 7, ANTI, face); }
         if (sa) copy3(B, 6, ANTI, face);
         break;
       case -6:  // slip_wall :405
         copy3(B, 1, SYMM, face); copy3(B, 5, SYMM, face);
-        if (sst) { copy3(B, 6, SYMM, face); copy3(B, 7, SYMM, face); }
+        if (sst || kkl) { copy3(B, 6, SYMM, face); copy3(B, 7, SYMM, face); }
         if (sa) copy3(B, 6, SYMM, face);
         flow_tangency(B, face);
         break;
       case -7:  // pole :446
         for (int v = 1; v <= 5; ++v) copy3(B, v, FLAT, face);
-        if (sst) { copy3(B, 6, FLAT, face); copy3(B, 7, FLAT, face); }
+        if (sst || kkl) { copy3(B, 6, FLAT, face); copy3(B, 7, FLAT, face); }
         if (sa) copy3(B, 6, FLAT, face);
         break;
       case -8: far_field(B, face); break;

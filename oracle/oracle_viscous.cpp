@@ -7,6 +7,10 @@ namespace orc {
 
 static inline bool is_sst(const Block& B) { return B.c.turbulence == ORC_TURB_SST || B.c.turbulence == ORC_TURB_SST2003; }
 static inline bool is_sa(const Block& B) { return B.c.turbulence == ORC_TURB_SA; }
+static inline bool is_kkl(const Block& B) { return B.c.turbulence == ORC_TURB_KKL; }
+// k-kL closure constants (global_kkl.f90:6-15)
+static const double kkl_zeta1 = 1.2, kkl_zeta2 = 0.97, kkl_zeta3 = 0.13, kkl_sigma_k = 1.0, kkl_sigma_phi = 1.0, kkl_cmu = 0.09, kkl_kappa = 0.41,
+                    kkl_c11 = 10.0, kkl_c12 = 1.3, kkl_cd1 = 4.7;
 
 // global_sa.f90:6-19
 constexpr double cb1 = 0.1355, cb2 = 0.6220, cw2 = 0.3, cw3 = 2.0, cv1 = 7.1, sigma_sa = 2. / 3., kappa_sa = 0.41;
@@ -91,7 +95,7 @@ void Block::evaluate_all_gradients() {
   } else {
     std::fill(gz.d.begin(), gz.d.end(), 0.0);   // gradqp_z = 0.0 (:336)
   }
-  if (is_sst(B)) {
+  if (is_sst(B) || is_kkl(B)) {   // k-kL: the same with kL in place of omega (gradients.f90:364-374)
     QpVar tk{qp, 6}, tw{qp, 7};
     gradient_G(B, gx, 5, tk, 0); gradient_G(B, gx, 6, tw, 0);
     gradient_G(B, gy, 5, tk, 1); gradient_G(B, gy, 6, tw, 1);
@@ -180,6 +184,37 @@ void Block::calculate_viscosity() {
           }
           mu_t(ig, jg, kg) = sgn * mu_t(i, j, k);
           F1(ig, jg, kg) = F1(i, j, k);
+        }
+    }
+  }
+  if (is_kkl(B)) {   // viscosity.f90:469-533: mu_t = cmu^(1/4) rho kL / max(sqrt(k), 1e-20), 0 below 1e-14; ghost copies per BC id
+    const double cq = std::pow(kkl_cmu, 0.25);
+    for (int k = 0; k <= kmx; ++k)
+      for (int j = 0; j <= jmx; ++j)
+        for (int i = 0; i <= imx; ++i) {
+          double density = qp(i, j, k, 1), tk = qp(i, j, k, 6), tkl = qp(i, j, k, 7);
+          mu_t(i, j, k) = cq * density * tkl / (std::fmax(std::sqrt(tk), 1.e-20));
+          if (tkl < 1.e-14 || tk < 1.e-14) mu_t(i, j, k) = 0.0;
+        }
+    for (int face = 1; face <= 6; ++face) {
+      int id = c.bc_id[face - 1];
+      double sgn;
+      if (id == -5) sgn = -1.0;
+      else if (id == -1 || id == -2 || id == -3 || id == -4 || id == -6 || id == -8 || id == -9) sgn = 1.0;   // (:492: no -7 here)
+      else continue;
+      int na = face <= 2 ? jmx - 1 : imx - 1, nb = face <= 4 ? kmx - 1 : jmx - 1;
+      for (int b = 1; b <= nb; ++b)
+        for (int a = 1; a <= na; ++a) {
+          int i, j, k, ig, jg, kg;
+          switch (face) {
+            case 1: i = 1; j = a; k = b; ig = 0; jg = a; kg = b; break;
+            case 2: i = imx - 1; j = a; k = b; ig = imx; jg = a; kg = b; break;
+            case 3: i = a; j = 1; k = b; ig = a; jg = 0; kg = b; break;
+            case 4: i = a; j = jmx - 1; k = b; ig = a; jg = jmx; kg = b; break;
+            case 5: i = a; j = b; k = 1; ig = a; jg = b; kg = 0; break;
+            default: i = a; j = b; k = kmx - 1; ig = a; jg = b; kg = kmx; break;
+          }
+          mu_t(ig, jg, kg) = sgn * mu_t(i, j, k);
         }
     }
   }
@@ -334,6 +369,48 @@ static void viscous_sst(Block& B, Arr4& F, const Rec4& faces, int ii, int jj, in
       }
 }
 
+// viscous.f90:450-567 compute_viscous_fluxes_kkl: the SST form with constant sigma_k = sigma_phi = 1 (no F1)
+static void viscous_kkl(Block& B, Arr4& F, const Rec4& faces, int ii, int jj, int kk) {
+  for (int k = 1; k <= B.kmx - 1 + kk; ++k)
+    for (int j = 1; j <= B.jmx - 1 + jj; ++j)
+      for (int i = 1; i <= B.imx - 1 + ii; ++i) {
+        const int im = i - ii, jm = j - jj, km = k - kk;
+        double dtkdx = 0.5 * (B.gx(im, jm, km, 5) + B.gx(i, j, k, 5));
+        double dtkdy = 0.5 * (B.gy(im, jm, km, 5) + B.gy(i, j, k, 5));
+        double dtkdz = 0.5 * (B.gz(im, jm, km, 5) + B.gz(i, j, k, 5));
+        double dtkldx = 0.5 * (B.gx(im, jm, km, 6) + B.gx(i, j, k, 6));
+        double dtkldy = 0.5 * (B.gy(im, jm, km, 6) + B.gy(i, j, k, 6));
+        double dtkldz = 0.5 * (B.gz(im, jm, km, 6) + B.gz(i, j, k, 6));
+        double delx = B.cells.cx(i, j, k) - B.cells.cx(im, jm, km);
+        double dely = B.cells.cy(i, j, k) - B.cells.cy(im, jm, km);
+        double delz = B.cells.cz(i, j, k) - B.cells.cz(im, jm, km);
+        double d_LR = std::sqrt(delx * delx + dely * dely + delz * delz);
+        double deltk = B.qp(i, j, k, 6) - B.qp(im, jm, km, 6);
+        double deltkl = B.qp(i, j, k, 7) - B.qp(im, jm, km, 7);
+        double normal_comp = (deltk - (dtkdx * delx + dtkdy * dely + dtkdz * delz)) / d_LR;
+        dtkdx = dtkdx + (normal_comp * delx / d_LR);
+        dtkdy = dtkdy + (normal_comp * dely / d_LR);
+        dtkdz = dtkdz + (normal_comp * delz / d_LR);
+        normal_comp = (deltkl - (dtkldx * delx + dtkldy * dely + dtkldz * delz)) / d_LR;
+        dtkldx = dtkldx + (normal_comp * delx / d_LR);
+        dtkldy = dtkldy + (normal_comp * dely / d_LR);
+        dtkldz = dtkldz + (normal_comp * delz / d_LR);
+        double mu_f = 0.5 * (B.mu(im, jm, km) + B.mu(i, j, k));
+        double mut_f = 0.5 * (B.mu_t(im, jm, km) + B.mu_t(i, j, k));
+        double rhoface = 0.5 * (B.qp(im, jm, km, 1) + B.qp(i, j, k, 1));
+        double tkface = 0.5 * (B.qp(im, jm, km, 6) + B.qp(i, j, k, 6));
+        double Tau_xx = -2.0 * rhoface * tkface / 3.0;
+        double Tau_yy = Tau_xx, Tau_zz = Tau_xx;
+        double nx = faces.nx(i, j, k), ny = faces.ny(i, j, k), nz = faces.nz(i, j, k), area = faces.A(i, j, k);
+        F(i, j, k, 2) = F(i, j, k, 2) - (Tau_xx * nx * area);
+        F(i, j, k, 3) = F(i, j, k, 3) - (Tau_yy * ny * area);
+        F(i, j, k, 4) = F(i, j, k, 4) - (Tau_zz * nz * area);
+        F(i, j, k, 5) = F(i, j, k, 5) - (area * ((mu_f + kkl_sigma_k * mut_f) * (dtkdx * nx + dtkdy * ny + dtkdz * nz)));
+        F(i, j, k, 6) = F(i, j, k, 6) - (area * ((mu_f + kkl_sigma_k * mut_f) * (dtkdx * nx + dtkdy * ny + dtkdz * nz)));
+        F(i, j, k, 7) = F(i, j, k, 7) - (area * ((mu_f + kkl_sigma_phi * mut_f) * (dtkldx * nx + dtkldy * ny + dtkldz * nz)));
+      }
+}
+
 // viscous.f90:570-656 compute_viscous_fluxes_sa: "mut_f" here is rho_face * tv_face, not the eddy viscosity
 static void viscous_sa(Block& B, Arr4& F, const Rec4& faces, int ii, int jj, int kk) {
   for (int k = 1; k <= B.kmx - 1 + kk; ++k)
@@ -369,6 +446,11 @@ void Block::compute_viscous_fluxes() {
     viscous_sst(*this, F, If, 1, 0, 0);
     viscous_sst(*this, G, Jf, 0, 1, 0);
     if (kmx != 2) viscous_sst(*this, H, Kf, 0, 0, 1);
+  }
+  if (is_kkl(*this)) {   // all three directions whatever kmx (:101-105)
+    viscous_kkl(*this, F, If, 1, 0, 0);
+    viscous_kkl(*this, G, Jf, 0, 1, 0);
+    viscous_kkl(*this, H, Kf, 0, 0, 1);
   }
   if (is_sa(*this)) {   // the K flux too when kmx == 2 (:94-97)
     viscous_sa(*this, F, If, 1, 0, 0);
@@ -526,9 +608,75 @@ static void add_sst_bc_source(Block& B) {
       }
 }
 
+// source.f90:607-832 add_kkl_source.  The "second derivatives" are Green-Gauss sums of the cell gradients over the six faces, one
+// per velocity component and direction; the von Karman length uses the three Laplacian-like sums.
+static void add_kkl_source(Block& B) {
+  const Rec4 &If = B.If, &Jf = B.Jf, &Kf = B.Kf;
+  const double cmu = kkl_cmu, kappa = kkl_kappa;
+  for (int k = 1; k <= B.kmx - 1; ++k)
+    for (int j = 1; j <= B.jmx - 1; ++j)
+      for (int i = 1; i <= B.imx - 1; ++i) {
+        const double density = B.qp(i, j, k, 1), tk = B.qp(i, j, k, 6), tkl = B.qp(i, j, k, 7);
+        const double ux = B.gx(i, j, k, 1), uy = B.gy(i, j, k, 1), uz = B.gz(i, j, k, 1);
+        const double vx = B.gx(i, j, k, 2), vy = B.gy(i, j, k, 2), vz = B.gz(i, j, k, 2);
+        const double wx = B.gx(i, j, k, 3), wy = B.gy(i, j, k, 3), wz = B.gz(i, j, k, 3);
+        const double S11 = 0.5 * (ux + ux), S12 = 0.5 * (uy + vx), S13 = 0.5 * (uz + wx);
+        const double S21 = 0.5 * (vx + uy), S22 = 0.5 * (vy + vy), S23 = 0.5 * (vz + wy);
+        const double S31 = 0.5 * (wx + uz), S32 = 0.5 * (wy + vz), S33 = 0.5 * (wz + wz);
+        const double delv = ux + vy + wz;
+        const double mut = B.mu_t(i, j, k);
+        const double Tau11 = mut * (2 * S11 - (2.0 / 3.0) * delv) - (2.0 / 3.0) * density * tk;
+        const double Tau12 = mut * (2 * S12), Tau13 = mut * (2 * S13), Tau21 = mut * (2 * S21);
+        const double Tau22 = mut * (2 * S22 - (2.0 / 3.0) * delv) - (2.0 / 3.0) * density * tk;
+        const double Tau23 = mut * (2 * S23), Tau31 = mut * (2 * S31), Tau32 = mut * (2 * S32);
+        const double Tau33 = mut * (2 * S33 - (2.0 / 3.0) * delv) - (2.0 / 3.0) * density * tk;
+        double P_k = 0.;
+        P_k = P_k + Tau11 * ux + Tau12 * uy + Tau13 * uz;
+        P_k = P_k + Tau21 * vx + Tau22 * vy + Tau23 * vz;
+        P_k = P_k + Tau31 * wx + Tau32 * wy + Tau33 * wz;
+        const double D_k = (std::pow(cmu, 0.75)) * density * (std::pow(tk, 2.5)) / std::fmax(tkl, 1.e-20);
+        P_k = std::fmin(P_k, 20 * D_k);
+        // Green-Gauss of gradient component g (1 = u, 2 = v, 3 = w) in direction dd (0 x, 1 y, 2 z)
+        auto second = [&](const Arr4& G, int g, int dd) {
+          auto n = [&](const Rec4& Fc, int a, int b, int cc) { return dd == 0 ? Fc.nx(a, b, cc) : (dd == 1 ? Fc.ny(a, b, cc) : Fc.nz(a, b, cc)); };
+          const double g0 = G(i, j, k, g);
+          return (-(G(i - 1, j, k, g) + g0) * n(If, i, j, k) * If.A(i, j, k)
+                  - (G(i, j - 1, k, g) + g0) * n(Jf, i, j, k) * Jf.A(i, j, k)
+                  - (G(i, j, k - 1, g) + g0) * n(Kf, i, j, k) * Kf.A(i, j, k)
+                  + (G(i + 1, j, k, g) + g0) * n(If, i + 1, j, k) * If.A(i + 1, j, k)
+                  + (G(i, j + 1, k, g) + g0) * n(Jf, i, j + 1, k) * Jf.A(i, j + 1, k)
+                  + (G(i, j, k + 1, g) + g0) * n(Kf, i, j, k + 1) * Kf.A(i, j, k + 1)) / (2 * B.cells.vol(i, j, k));
+        };
+        const double d2udx2 = second(B.gx, 1, 0), d2udy2 = second(B.gy, 1, 1), d2udz2 = second(B.gz, 1, 2);
+        const double d2vdx2 = second(B.gx, 2, 0), d2vdy2 = second(B.gy, 2, 1), d2vdz2 = second(B.gz, 2, 2);
+        const double d2wdx2 = second(B.gx, 3, 0), d2wdy2 = second(B.gy, 3, 1), d2wdz2 = second(B.gz, 3, 2);
+        const double a1 = (d2udx2 + d2udy2 + d2udz2), a2 = (d2vdx2 + d2vdy2 + d2vdz2), a3 = (d2wdx2 + d2wdy2 + d2wdz2);
+        const double udd = std::sqrt(a1 * a1 + a2 * a2 + a3 * a3);
+        const double ud = std::sqrt(2 * (S11 * S11 + S12 * S12 + S13 * S13 + S21 * S21 + S22 * S22 + S23 * S23 + S31 * S31 + S32 * S32 + S33 * S33));
+        double Lvk = kappa * std::fabs(ud / std::fmax(udd, 1.e-20));
+        const double fp = std::fmin(std::fmax(P_k / D_k, 0.5), 1.0);
+        Lvk = std::fmax(Lvk, tkl / std::fmax((tk * kkl_c11), 1.e-20));
+        Lvk = std::fmin(Lvk, kkl_c12 * kappa * B.dist(i, j, k) * fp);
+        const double eta = density * B.dist(i, j, k) * std::sqrt(0.3 * tk) / (20 * B.mu(i, j, k));
+        const double fphi = (1 + kkl_cd1 * eta) / (1 + (eta * eta) * (eta * eta));
+        const double cphi2 = kkl_zeta3;
+        const double rr = (tkl / std::fmax(tk * Lvk, 1.e-20));
+        const double cphi1 = (kkl_zeta1 - kkl_zeta2 * (rr * rr));
+        const double P_kl = cphi1 * tkl * P_k / std::fmax(tk, 1.e-20);
+        const double D_kl = cphi2 * density * (std::pow(tk, 1.5));
+        double S_k = P_k - D_k - 2 * B.mu(i, j, k) * tk / (B.dist(i, j, k) * B.dist(i, j, k));
+        double S_kl = P_kl - D_kl - 6 * B.mu(i, j, k) * tkl * fphi / (B.dist(i, j, k) * B.dist(i, j, k));
+        S_k = S_k * B.cells.vol(i, j, k);
+        S_kl = S_kl * B.cells.vol(i, j, k);
+        B.residue(i, j, k, 6) = B.residue(i, j, k, 6) - S_k;
+        B.residue(i, j, k, 7) = B.residue(i, j, k, 7) - S_kl;
+      }
+}
+
 // source.f90:94-155 dispatch; :158-270 add_sst_source
 void Block::add_source_term_residue() {
   const bool tbc = c.transition == 1;   // 'bc'
+  if (is_kkl(*this)) { add_kkl_source(*this); return; }
   if (is_sa(*this)) { if (tbc) add_saBC_source(*this); else add_sa_source(*this); return; }
   if (!is_sst(*this)) return;
   if (tbc) { add_sst_bc_source(*this); return; }
@@ -657,6 +805,13 @@ void Block::update_with(double TF, double SF, bool TU, bool have_store) {
           R[5] = R[5] / (1 + (beta * qp(i, j, k, 7) * delta_t(i, j, k)));
           R[6] = R[6] / (1 + (2 * beta * qp(i, j, k, 7) * delta_t(i, j, k)));
         }
+        if (is_kkl(*this)) {   // update.f90:399-404: u1(6), u1(7) are rho*k, rho*kL here, used where the model has k, kL -- reproduced
+          double eta = u1[0] * dist(i, j, k) * (std::sqrt(0.3 * u1[5]) / (20 * mu(i, j, k)));
+          double fphi = (1 + kkl_cd1 * eta) / (1 + (eta * eta) * (eta * eta));
+          R[5] = R[5] / (1. + ((2.5 * ((std::pow(kkl_cmu, 0.75)) * std::sqrt(u1[0]) * (std::pow(u1[5], 1.5)) / std::fmax(u1[6], 1.e-20)) +
+                                (2 * mu(i, j, k) / (dist(i, j, k) * dist(i, j, k)))) * delta_t(i, j, k)));
+          R[6] = R[6] / (1. + (6 * mu(i, j, k) * fphi / (dist(i, j, k) * dist(i, j, k))) * delta_t(i, j, k));
+        }
         if (is_sa(*this)) {   // update.f90:405-420: u1(6) is rho*tv here, used where the model has tv -- reproduced
           double a = (gy(i, j, k, 3) - gz(i, j, k, 2)), b = (gz(i, j, k, 1) - gx(i, j, k, 3)), cc = (gx(i, j, k, 2) - gy(i, j, k, 1));
           double vort = std::sqrt(((a * a) + (b * b) + (cc * cc)));
@@ -683,7 +838,7 @@ void Block::update_with(double TF, double SF, bool TU, bool have_store) {
         for (int l = 0; l < nv; ++l) if (std::isnan(u2[l])) bad = true;
         if (bad) { error |= 8; continue; }   // reference: Fatal_error (STOP)
         for (int l = 1; l <= 5; ++l) qp(i, j, k, l) = u2[l - 1];
-        if (is_sst(*this)) {
+        if (is_sst(*this) || is_kkl(*this)) {
           if (u2[5] >= 0.) qp(i, j, k, 6) = u2[5];
           if (u2[6] >= 0.) qp(i, j, k, 7) = u2[6];
         }
@@ -699,6 +854,7 @@ void Block::absolute_resnorm() {
   scale[2] = scale[3] = scale[4] = c.density_inf * c.vel_mag * c.vel_mag;
   scale[5] = (0.5 * c.density_inf * (c.vel_mag * c.vel_mag * c.vel_mag) + ((c.gm / (c.gm - 1.)) * c.pressure_inf));
   if (is_sst(*this)) { scale[6] = c.density_inf * c.vel_mag * c.tk_inf; scale[7] = c.density_inf * c.vel_mag * c.tw_inf; }
+  if (is_kkl(*this)) { scale[6] = c.density_inf * c.vel_mag * c.tk_inf; scale[7] = c.density_inf * c.vel_mag * c.tkl_inf; }   // resnorm.f90:151-153
   if (is_sa(*this)) scale[6] = c.density_inf * c.vel_mag * c.tv_inf;   // resnorm.f90:157-158
   for (int l = 1; l <= nv; ++l) {
     double s = 0.;

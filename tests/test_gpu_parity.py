@@ -176,6 +176,68 @@ def test_sa_boundary_conditions(pkg, case_mod, oracle, bc, shape):
     s.close()
 
 
+# ---- k-kL model (n_var 7: k, kL; viscosity.f90:469-533, viscous.f90:450-567, source.f90:607-832, update.f90:399-404) --------------------
+@pytest.mark.parametrize("scheme_name,interpolant,ta", [("ausm", "muscl", "RK4"), ("slau", "weno", "none"), ("ausmUP", "ppm", "TVDRK3"), ("van_leer", "none", "RK2")])
+def test_duct_kkl(pkg, case_mod, oracle, scheme_name, interpolant, ta):
+    import importlib
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    blocks = syn.make_duct_blocks(None, n3=(37, 11, 9), scheme_name=scheme_name, interpolant=interpolant, turbulence="kkl", time_step_accuracy=ta, CFL=0.5)
+    s = _solver(pkg, blocks)
+    _check_residual(oracle, s, blocks)
+    _check_history(oracle, s, blocks, 5)
+    s.close()
+
+
+@pytest.mark.parametrize("bc", [[-3, -4, -5, -6, -6, -6], [-8, -4, -7, -6, -9, -9], [-11, -4, -5, -5, -5, -5], [-1, -2, -6, -5, -5, -6]])
+@pytest.mark.parametrize("shape", [(6, 5, 1), (9, 7, 5)])
+def test_kkl_boundary_conditions(pkg, case_mod, oracle, bc, shape):
+    import importlib
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    if (-9 in bc[4:]) and shape[2] < 3:
+        pytest.skip("periodic slab copy needs 3 interior layers")
+    blocks = syn.make_duct_blocks(None, n3=shape, turbulence="kkl", time_step_accuracy="RK2", interpolant="muscl")
+    blk = blocks[0]
+    blk.bc_id = list(bc)
+    fl = blk.flow
+    M2 = fl.x_speed_inf ** 2 / (fl.gm * fl.pressure_inf / fl.density_inf)
+    blk.fixed[8, :] = fl.pressure_inf * (1 + 0.5 * (fl.gm - 1.0) * M2) ** (fl.gm / (fl.gm - 1.0)) * (1.0 + 1e-3 * np.arange(6))
+    blk.fixed[11, :] = fl.tkl_inf * (1.0 + 0.05 * np.arange(6))     # fixed_tkl; the subsonic inlet takes fixed_tw instead (reproduced)
+    blk.fixed[6, :] = fl.tkl_inf * (1.0 - 0.03 * np.arange(6))
+    blk.build_geometry()
+    s = _solver(pkg, blocks)
+    _check_residual(oracle, s, blocks)
+    _check_history(oracle, s, blocks, 4)
+    s.close()
+
+
+@pytest.mark.parametrize("kscale,klscale", [(1e3, 1e6), (1e4, 1e8)])
+@pytest.mark.parametrize("interpolant,ta", [("muscl", "RK4"), ("weno_NM", "none")])
+def test_duct_kkl_strong_turbulence(pkg, case_mod, oracle, kscale, klscale, interpolant, ta):
+    """The free-stream k and kL leave mu_t/mu ~ 1e-2 and the sources below the flux round-off; scaled up (mu_t/mu ~ 3e2 and 9e3) the
+    production, destruction and second-derivative terms of source.f90:607-832 and the point-implicit update carry O(1e-2) of the
+    residual (measured on the oracle by perturbing the wall distance), so this is where their parity is actually tested."""
+    import importlib
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    blocks = syn.make_duct_blocks(None, n3=(17, 11, 9), scheme_name="ausm", interpolant=interpolant, turbulence="kkl", time_step_accuracy=ta, CFL=0.5)
+    for blk in blocks:
+        blk.qp[5] *= kscale
+        blk.qp[6] *= klscale
+    s = _solver(pkg, blocks)
+    _check_residual(oracle, s, blocks)
+    _check_history(oracle, s, blocks, 5)
+    s.close()
+
+
+def test_kkl_multiblock(pkg, case_mod, oracle):
+    import importlib
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    blocks = syn.make_duct_blocks(None, n3=(10, 8, 6), nb=(2, 2, 2), turbulence="kkl", time_step_accuracy="RK4")
+    s = _solver(pkg, blocks)
+    _check_residual(oracle, s, blocks)
+    _check_history(oracle, s, blocks, 4)
+    s.close()
+
+
 # ---- MUSCL / PPM pressure-based switching (muscl.f90:37-112, ppm.f90:108-170), every direction, quasi-2-D included -----------
 @pytest.mark.parametrize("interpolant", ["muscl", "ppm"])
 @pytest.mark.parametrize("shape,pb", [((20, 12, 10), (1, 1, 1)), ((33, 9, 1), (1, 0, 1)), ((7, 6, 5), (0, 1, 0))])
@@ -681,6 +743,17 @@ def test_unsupported_is_an_error_not_a_fallback(pkg, case_mod):
     blocks = syn.make_duct_blocks(None, n3=(6, 5, 4), turbulence="none", mu_ref=0.0, time_step_accuracy="implicit")
     with pytest.raises(solver.Fest3dError):
         solver.Solver(blocks)
+
+
+def test_kkl_on_the_fused_form_is_refused(pkg, case_mod, fused_path):
+    """The one-kernel form has no k-kL source (it needs the gradients of plane k+1): asking for both is an error, not a silent
+    switch to the staged form."""
+    import importlib
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    solver = importlib.import_module("fest3d_b200.solver")
+    with pytest.raises(solver.Fest3dError) as e:
+        solver.Solver(syn.make_duct_blocks(None, n3=(6, 5, 4), turbulence="kkl"))
+    assert e.value.rc & 64
 
 
 def test_negative_pressure_is_reported(pkg, case_mod):

@@ -38,14 +38,24 @@ def test_no_device_is_an_error_not_a_fallback():
     assert not h.value
 
 
-def test_config_struct_layout_matches_header():
+def test_config_struct_layout_matches_header(tmp_path):
+    """The ctypes mirrors (product binding and oracle binding) against the C compiler's view of include/fest3d_gpu.h: size, the number
+    of fixed-value slots, and the offsets of the first and last double fields."""
+    import subprocess
     capi = importlib.import_module("fest3d_b200.capi")
-    # 10 ints + 3*3 + 2 + 4*6 + 3*12 + 2 = 83 ints -> padded to 8-byte alignment, then 20 doubles + 11 x 6 fixed values
-    n_int = 4 + 4 + 2 + 9 + 2 + 24 + 36 + 2
-    size = ((n_int * 4 + 7) // 8) * 8 + (2 + 7 + 5 + 4 + 2 + 66) * 8
-    assert C.sizeof(capi.Fest3dGpuConfig) == size
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "fest3d_gpu.h"\n'
+                   'int main(void) { printf("%zu %d %zu %zu %zu\\n", sizeof(Fest3dGpuConfig), F3D_NFIX, offsetof(Fest3dGpuConfig, gm),'
+                   ' offsetof(Fest3dGpuConfig, tkl_inf), offsetof(Fest3dGpuConfig, fixed)); return 0; }\n')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    size, nfix, off_gm, off_tkl, off_fixed = (int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split())
+    cfg = capi.Fest3dGpuConfig
+    assert C.sizeof(cfg) == size and capi.NFIX == nfix == 12
+    assert cfg.gm.offset == off_gm and cfg.tkl_inf.offset == off_tkl and cfg.fixed.offset == off_fixed
     import oracle_py
-    assert C.sizeof(oracle_py.OracleConfig) == size
+    ocfg = oracle_py.OracleConfig
+    assert C.sizeof(ocfg) == size and ocfg.gm.offset == off_gm and ocfg.tkl_inf.offset == off_tkl and ocfg.fixed.offset == off_fixed
 
 
 def test_product_does_not_import_the_oracle():

@@ -383,3 +383,35 @@ def test_soft_pin_on_the_shipped_smoothbump_output(oracle, case_mod):
     assert np.all(hist[-1, 1:] <= 1.05 * hist[0, 1:] + 1e-300), (hist[0], hist[-1])
     ds = _entropy_measure(blocks, [w.get_state(b) for b in range(len(blocks))])
     assert abs(ds / REPORT_ENTROPY - 1.0) < 0.04, ds
+
+
+def test_kkl_model_pins(oracle, case_mod):
+    """k-kL pieces the reference's unit tests hold no answer for, pinned analytically on the oracle: free-stream values
+    (state.f90:101-103), mu_t = cmu^(1/4) rho kL / sqrt(k) with its 1e-14 cut-off (viscosity.f90:469-484), the wall ghost rule
+    (anti copies of k and kL, bc_primitive.f90:548-550; mu_t(ghost) = -mu_t(interior), viscosity.f90:512-531) and the fixed value of
+    the subsonic inlet (fixed_tw on kL: bc_primitive.f90:333-336, a reference quirk that is kept)."""
+    import importlib
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    blocks = syn.make_duct_blocks(None, n3=(6, 5, 4), turbulence="kkl")
+    blk = blocks[0]
+    fl = blk.flow
+    c_inf = np.sqrt(fl.gm * fl.pressure_inf / fl.density_inf)
+    assert fl.tk_inf == 9 * (1e-9) * (c_inf ** 2) and fl.tkl_inf == 1.5589 * (1e-6) * (fl.mu_ref * c_inf) / fl.density_inf
+    assert blk.n_var == 7
+    blk.fixed[6, :] = 3.0e-9          # fixed_tw, used by the subsonic inlet for kL
+    blk.fixed[11, :] = 5.0e-9         # fixed_tkl
+    blk.qp[5, 3 + 2, 3 + 2, 3 + 2] = 1.0e-15     # below the cut-off: mu_t = 0 there
+    w = oracle.OracleWorld(blocks)
+    err, _ = w.residual(1)
+    assert err == 0
+    q = w.get_state(0)
+    mut = w.aux(0, 2, (blk.kmx + 5, blk.jmx + 5, blk.imx + 5))
+    K, J, I = slice(3, 3 + blk.kmx - 1), slice(3, 3 + blk.jmx - 1), slice(3, 3 + blk.imx - 1)
+    want = 0.09 ** 0.25 * q[0, K, J, I] * q[6, K, J, I] / np.sqrt(q[5, K, J, I])
+    want[2, 2, 2] = 0.0
+    assert np.allclose(mut[K, J, I], want, rtol=1e-14, atol=0)
+    # wall at jmin (bc -5): ghost k, kL = -interior; ghost mu_t = -interior mu_t
+    assert np.array_equal(q[5, K, 2, I], -q[5, K, 3, I]) and np.array_equal(q[6, K, 2, I], -q[6, K, 3, I])
+    assert np.array_equal(mut[K, 2, I], -mut[K, 3, I])
+    # subsonic inlet at imin (bc -3): kL ghost layers = fixed_tw
+    assert np.all(q[6, K, J, 0:3] == 3.0e-9) and np.all(q[5, K, J, 0:3] == fl.tk_inf)
