@@ -11,7 +11,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("F3D_LIB") or os.path.join(HERE, "libfest3d_gpu.so")   # F3D_LIB: an alternative build (A/B measurements)
-NFIX = 12
+NFIX = 13
 
 SYMBOLS = [
     "fest3d_gpu_create", "fest3d_gpu_destroy", "fest3d_gpu_set_stream", "fest3d_gpu_sync", "fest3d_gpu_set_geometry",
@@ -39,7 +39,7 @@ class Fest3dGpuConfig(C.Structure):
         ("Sutherland_temp", C.c_double), ("Pr", C.c_double), ("tPr", C.c_double),
         ("density_inf", C.c_double), ("x_speed_inf", C.c_double), ("y_speed_inf", C.c_double),
         ("z_speed_inf", C.c_double), ("pressure_inf", C.c_double),
-        ("tk_inf", C.c_double), ("tw_inf", C.c_double), ("vel_mag", C.c_double), ("MInf", C.c_double), ("tv_inf", C.c_double), ("tu_inf", C.c_double), ("tkl_inf", C.c_double),
+        ("tk_inf", C.c_double), ("tw_inf", C.c_double), ("vel_mag", C.c_double), ("MInf", C.c_double), ("tv_inf", C.c_double), ("tu_inf", C.c_double), ("tkl_inf", C.c_double), ("tgm_inf", C.c_double),
         ("fixed", (C.c_double * 6) * NFIX),
     ]
 

@@ -29,9 +29,9 @@ INTERPOLANTS = {"none": 0, "muscl": 1, "ppm": 2, "weno": 3, "weno_NM": 4}
 TURBULENCE = {"none": 0, "sa": 1, "saBC": 2, "sst": 3, "sst2003": 4, "kkl": 5}
 TRANSITION = {"none": 0, "bc": 1, "lctm2015": 2}
 TIME_ACCURACY = {"none": 0, "RK2": 1, "RK4": 2, "TVDRK2": 3, "TVDRK3": 4, "implicit": 5, "plusgs": 6}
-FIX_SLOTS = ["density", "pressure", "x_speed", "y_speed", "z_speed", "tk", "tw", "wall_temperature", "Tpressure", "Ttemperature", "tv", "tkl"]
+FIX_SLOTS = ["density", "pressure", "x_speed", "y_speed", "z_speed", "tk", "tw", "wall_temperature", "Tpressure", "Ttemperature", "tv", "tkl", "tgm"]
 FIX_KEYS = {"FIX_DENSITY": 0, "FIX_PRESSURE": 1, "FIX_X_SPEED": 2, "FIX_Y_SPEED": 3, "FIX_Z_SPEED": 4,
-            "FIX_tk": 5, "FIX_tw": 6, "WALL_TEMPERATURE": 7, "TOTAL_PRESSURE": 8, "TOTAL_TEMPERATURE": 9, "FIX_tv": 10, "FIX_tkl": 11}
+            "FIX_tk": 5, "FIX_tw": 6, "WALL_TEMPERATURE": 7, "TOTAL_PRESSURE": 8, "TOTAL_TEMPERATURE": 9, "FIX_tv": 10, "FIX_tkl": 11, "FIX_tgm": 12}
 
 
 def _tokens(path):
@@ -208,7 +208,7 @@ class BlockSetup:
         self.fixed = np.zeros((len(FIX_SLOTS), 6))
         self.fixed[0, :] = f.density_inf; self.fixed[1, :] = f.pressure_inf
         self.fixed[2, :] = f.x_speed_inf; self.fixed[3, :] = f.y_speed_inf; self.fixed[4, :] = f.z_speed_inf
-        self.fixed[5, :] = f.tk_inf; self.fixed[6, :] = f.tw_inf; self.fixed[10, :] = f.tv_inf; self.fixed[11, :] = f.tkl_inf
+        self.fixed[5, :] = f.tk_inf; self.fixed[6, :] = f.tw_inf; self.fixed[10, :] = f.tv_inf; self.fixed[11, :] = f.tkl_inf; self.fixed[12, :] = f.tgm_inf
 
     def init_state(self):
         """state.f90:193-247 init_state_with_infinity_values (ghosts included)."""
@@ -220,6 +220,8 @@ class BlockSetup:
             q[5] = f.tk_inf; q[6] = f.tkl_inf if self.scheme.turbulence == "kkl" else f.tw_inf     # state.f90:228-238
         elif nv == 6:               # state.f90:240-242
             q[5] = f.tv_inf
+        if self.scheme.transition == "lctm2015":    # state.f90:260-266: the intermittency is the last variable
+            q[nv - 1] = f.tgm_inf
         self.qp = q
 
     def build_geometry(self):

@@ -68,11 +68,15 @@ extern "C" int fest3d_gpu_create(Fest3dGpuCtx** out, const Fest3dGpuConfig* cfg,
   const bool sst = cfg->turbulence == F3D_TURB_SST || cfg->turbulence == F3D_TURB_SST2003 || kkl;   // the two-equation layout (n_var 7, n_grad 6)
   const bool sa = cfg->turbulence == F3D_TURB_SA;   // 'saBC' has no case in the reference's source dispatcher (source.f90:119-153)
   if (cfg->turbulence != F3D_TURB_NONE && !sst && !sa) return F3D_ERR_UNSUPPORTED;
-  if (cfg->transition != F3D_TRANS_NONE && !(cfg->transition == F3D_TRANS_BC && (sst || sa) && !kkl)) return F3D_ERR_UNSUPPORTED;   // lctm2015: not built
-  if (kkl) { const char* e = getenv("F3D_GRADIENTS"); if (e && strcmp(e, "fused") == 0) return F3D_ERR_UNSUPPORTED; }   // k-kL: staged form only
+  // transition = bc with sa / sst / sst2003; lctm2015 with sst / sst2003 (the only cases of the reference's source dispatcher, source.f90:119-153)
+  const bool lctm = cfg->transition == F3D_TRANS_LCTM2015;
+  if (cfg->transition == F3D_TRANS_BC && !((sst || sa) && !kkl)) return F3D_ERR_UNSUPPORTED;
+  if (lctm && !(sst && !kkl)) return F3D_ERR_UNSUPPORTED;
+  if (cfg->transition != F3D_TRANS_NONE && cfg->transition != F3D_TRANS_BC && !lctm) return F3D_ERR_ARGUMENT;
+  if (kkl || lctm) { const char* e = getenv("F3D_GRADIENTS"); if (e && strcmp(e, "fused") == 0) return F3D_ERR_UNSUPPORTED; }   // staged form only
   if (cfg->time_accuracy >= F3D_T_IMPLICIT || cfg->time_accuracy < 0) return F3D_ERR_UNSUPPORTED;
   if (cfg->scheme < 0 || cfg->scheme > F3D_SLAU || cfg->interpolant < 0 || cfg->interpolant > F3D_WENO_NM) return F3D_ERR_ARGUMENT;
-  if (cfg->n_var != (sst ? 7 : (sa ? 6 : 5))) return F3D_ERR_ARGUMENT;
+  if (cfg->n_var != (sst ? 7 : (sa ? 6 : 5)) + (lctm ? 1 : 0)) return F3D_ERR_ARGUMENT;   // state.f90:291-320
   if ((sst || sa) && cfg->mu_ref == 0.0) return F3D_ERR_UNSUPPORTED;
   if (cfg->imx < 2 || cfg->jmx < 2 || cfg->kmx < 2) return F3D_ERR_ARGUMENT;
 
@@ -91,6 +95,7 @@ static int create_impl(Fest3dGpuCtx* ctx, const Fest3dGpuConfig* cfg, int device
   memset(&P, 0, sizeof(P));
   Layout& L = P.L;
   L.imx = cfg->imx; L.jmx = cfg->jmx; L.kmx = cfg->kmx; L.nv = cfg->n_var; L.ng = sst ? 6 : (sa ? 5 : 4);
+  if (cfg->transition == F3D_TRANS_LCTM2015) L.ng += 1;   // gradients.f90:259-264
   // a row holds i = -2 .. imx+2 behind its 15-element lead-in (interior cell i = 1 starts a 128-byte line), so that the tensor maps
   // of the sweep can address it as one dimension
   L.pi = ((cfg->imx + 18 + 15) / 16) * 16; L.pj = cfg->jmx + 6; L.pk = cfg->kmx + 6;
@@ -116,6 +121,7 @@ static int create_impl(Fest3dGpuCtx* ctx, const Fest3dGpuConfig* cfg, int device
   P.current_iter = 1;
   P.viscous = cfg->mu_ref != 0.0; P.sst = sst ? 1 : 0; P.sa = sa ? 1 : 0; P.kkl = cfg->turbulence == F3D_TURB_KKL ? 1 : 0;
   P.tkl_inf = cfg->tkl_inf;
+  P.lctm = cfg->transition == F3D_TRANS_LCTM2015 ? 1 : 0; P.tgm_inf = cfg->tgm_inf;
   P.trans_bc = cfg->transition == F3D_TRANS_BC ? 1 : 0; P.tu_inf = cfg->tu_inf;
   P.nu_cr = cfg->mu_ref != 0.0 ? 5.0 / (cfg->density_inf * cfg->vel_mag * 1.0 / cfg->mu_ref) : 0.0;   // chi_2 / Reynolds_number (state.f90:89)
   P.CFL = cfg->CFL; P.global_time_step = cfg->global_time_step;
@@ -142,6 +148,8 @@ static int create_impl(Fest3dGpuCtx* ctx, const Fest3dGpuConfig* cfg, int device
   sc[5] = (0.5 * cfg->density_inf * (cfg->vel_mag * cfg->vel_mag * cfg->vel_mag) + ((cfg->gm / (cfg->gm - 1.)) * cfg->pressure_inf));
   if (sst) { sc[6] = cfg->density_inf * cfg->vel_mag * cfg->tk_inf; sc[7] = cfg->density_inf * cfg->vel_mag * (P.kkl ? cfg->tkl_inf : cfg->tw_inf); }   // resnorm.f90:148-153
   if (sa) sc[6] = cfg->density_inf * cfg->vel_mag * cfg->tv_inf;   // resnorm.f90:157-158
+  // lctm2015: setup_scale never assigns Res_scale(8) (resnorm.f90:136-167), the reference divides by whatever its allocation holds: no
+  // reference value exists for that norm; it is reported here with scale 1 (sc[8] above)
 
   F3D_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
   ctx->stream = ctx->own_stream;
@@ -194,8 +202,10 @@ static int create_impl(Fest3dGpuCtx* ctx, const Fest3dGpuConfig* cfg, int device
     ok = ok && encode(&ctx->tm_temp, ctx->temp, 1, kG3TY + 4, 1);
     ok = ok && encode(&ctx->tm_geo, ctx->geom, G_NFIELDS, kG3TY + 2, 4);   // volume + centre x, y, z = geometry fields 0..3
     if (P.viscous && !ctx->fused) {
-      const int ngf = 3 * L.ng, naux = ctx->n_mu + 3;
-      ok = ok && encode(&ctx->tm_grad, ctx->grad, ngf, kG3TY + 2, (ngf + 1) & ~1) && encode(&ctx->tm_aux, ctx->mu, naux, kG3TY + 2, (naux + 1) & ~1);
+      // lctm2015 (eight variables): the sweep stages the first 18 gradient fields and mu, mu_t, F1 + the CC.f90 field; the intermittency
+      // gradient and the cell centres stay in global memory (sweep_common.cuh:RecF)
+      const int ngf = 3 * L.ng, naux = P.lctm ? ctx->n_mu + 1 : ctx->n_mu + 3;
+      ok = ok && encode(&ctx->tm_grad, ctx->grad, ngf, kG3TY + 2, P.lctm ? 18 : ((ngf + 1) & ~1)) && encode(&ctx->tm_aux, ctx->mu, naux, kG3TY + 2, (naux + 1) & ~1);
     }
     if (!ok) { fprintf(stderr, "fest3d_gpu: cuTensorMapEncodeTiled failed\n"); return fail(ctx, F3D_ERR_CUDA); }
     ctx->tmaps_ok = true;
@@ -293,9 +303,16 @@ static int copy_cells(Fest3dGpuCtx* ctx, double* dev_field, double* host, int nf
 }
 
 // staged path: the cell-centre fields copied behind the viscosity fields: one "aux" array for the tensor-map staging of the sweep
+// (lctm2015: the static CC.f90 field instead, which depends on the wall distance)
 static int init_aux_fields(Fest3dGpuCtx* ctx) {
   if (!ctx->P.viscous || ctx->fused) return 0;
   const long long fs = ctx->P.L.fs;
+  if (ctx->P.lctm) {
+    const int rc = launch_dvdy(ctx);
+    if (rc) return rc;
+    F3D_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+  }
   F3D_CUDA(cudaMemcpyAsync(ctx->mu + (long long)ctx->n_mu * fs, ctx->geom + (long long)G_CX * fs, 3 * fs * sizeof(double), cudaMemcpyDeviceToDevice,
                            ctx->stream));
   F3D_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -501,6 +518,7 @@ extern "C" int fest3d_gpu_get_aux(Fest3dGpuCtx* ctx, int which, double* out) {
   if (which == 0) rc = copy_cells(ctx, ctx->dt, out, 1, false, 1, L.imx - 1, L.jmx - 1, L.kmx - 1);
   else if (which >= 1 && which <= 3 && ctx->mu && which <= ctx->n_mu) rc = copy_cells(ctx, ctx->mu + (long long)(which - 1) * L.fs, out, 1, false, -2, L.imx + 5, L.jmx + 5, L.kmx + 5);
   else if (which == 4) rc = copy_cells(ctx, ctx->temp, out, 1, false, -2, L.imx + 5, L.jmx + 5, L.kmx + 5);
+  else if (which == 5 && ctx->P.lctm && ctx->mu) rc = copy_cells(ctx, ctx->mu + 3 * L.fs, out, 1, false, -2, L.imx + 5, L.jmx + 5, L.kmx + 5);
   else if (which >= 30 && which <= 32 && ctx->grad) {
     // gradqp_d(0:imx,0:jmx,0:kmx,1:n_grad): component c of direction d lives in field 3*c+d
     const int d = which - 30;

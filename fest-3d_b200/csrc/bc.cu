@@ -103,6 +103,10 @@ __global__ void k_bc_face(const Params P, double* __restrict__ q, const double* 
   const int FIX_7 = kkl ? F3D_FIX_TKL : F3D_FIX_TW;
   double* rho = q; double* u = q + fs; double* v = q + 2 * fs; double* w = q + 3 * fs; double* p = q + 4 * fs;
   double* tk = q + 5 * fs; double* tw = q + 6 * fs;
+  // transition = lctm2015: the intermittency (field 7) is fixed at the two inlets and copied flat on every other face, the wall included
+  // (bc_primitive.f90:259-265, 299-304, 340-346, 384-389, 436-441, 474-479, 554-559); far-field / total pressure: as k (last cell decides)
+  const bool lctm = P.lctm != 0;
+  double* tgm = q + 7 * fs;
   const double(*fx)[6] = P.fixed;
   const int fi = face - 1;
   const int ax = (face - 1) / 2;
@@ -113,12 +117,14 @@ __global__ void k_bc_face(const Params P, double* __restrict__ q, const double* 
         fix3(w, fr, o, fx[F3D_FIX_Z_SPEED][fi]); fix3(p, fr, o, fx[F3D_FIX_PRESSURE][fi]);
         if (sst) { fix3(tk, fr, o, fx[F3D_FIX_TK][fi]); fix3(tw, fr, o, fx[FIX_7][fi]); }
         if (sa) fix3(tk, fr, o, fx[F3D_FIX_TV][fi]);
+        if (lctm) fix3(tgm, fr, o, fx[F3D_FIX_TGM][fi]);
       }
       break;
     case -2: case -7:   // supersonic_outlet, pole: everything flat
       copy3_flat(rho, fr, o); copy3_flat(u, fr, o); copy3_flat(v, fr, o); copy3_flat(w, fr, o); copy3_flat(p, fr, o);
       if (sst) { copy3_flat(tk, fr, o); copy3_flat(tw, fr, o); }
       if (sa) copy3_flat(tk, fr, o);
+      if (lctm) copy3_flat(tgm, fr, o);
       break;
     case -3:   // subsonic_inlet
       if (P.current_iter <= 2) {
@@ -126,6 +132,7 @@ __global__ void k_bc_face(const Params P, double* __restrict__ q, const double* 
         fix3(w, fr, o, fx[F3D_FIX_Z_SPEED][fi]);
         if (sst) { fix3(tk, fr, o, fx[F3D_FIX_TK][fi]); fix3(tw, fr, o, fx[F3D_FIX_TW][fi]); }
         if (sa) fix3(tk, fr, o, fx[F3D_FIX_TV][fi]);
+        if (lctm) fix3(tgm, fr, o, fx[F3D_FIX_TGM][fi]);
       }
       copy3_flat(p, fr, o);
       break;
@@ -134,6 +141,7 @@ __global__ void k_bc_face(const Params P, double* __restrict__ q, const double* 
       if (P.current_iter <= 2) fix3(p, fr, o, fx[F3D_FIX_PRESSURE][fi]);
       if (sst) { copy3_flat(tk, fr, o); copy3_flat(tw, fr, o); }
       if (sa) copy3_flat(tk, fr, o);
+      if (lctm) copy3_flat(tgm, fr, o);
       break;
     case -5: {  // wall: pressure symm, temp_based_density, no_slip (+ omega at wall)
       copy3_symm(p, fr, o, P.c1, P.c2, P.c3);
@@ -163,12 +171,14 @@ __global__ void k_bc_face(const Params P, double* __restrict__ q, const double* 
 #pragma unroll
         for (int l = 1; l <= 3; ++l) tw[GHO_(l)] = 120 * mu / (rh * kBeta1 * (d2 * d2)) - tw[INT_(l)];
       }
+      if (lctm) copy3_flat(tgm, fr, o);
       break;
     }
     case -6: {  // slip_wall
       copy3_symm(rho, fr, o, P.c1, P.c2, P.c3); copy3_symm(p, fr, o, P.c1, P.c2, P.c3);
       if (sst) { copy3_symm(tk, fr, o, P.c1, P.c2, P.c3); copy3_symm(tw, fr, o, P.c1, P.c2, P.c3); }
       if (sa) copy3_symm(tk, fr, o, P.c1, P.c2, P.c3);
+      if (lctm) copy3_flat(tgm, fr, o);
       // flow_tangency: dot with this direction's face normal, reflection with the I-face normal at the same index
       const double* gd = geom + (long long)(G_IA + 4 * ax) * fs;
       const double* gi = geom + (long long)G_IA * fs;
@@ -209,8 +219,8 @@ __global__ void k_bc_face(const Params P, double* __restrict__ q, const double* 
         const long long olast = (long long)(fr.na - 1) * fr.sa + (long long)(fr.nb - 1) * fr.sb;
         double Ub2, Cb2, a2, b2, x2, y2, z2;
         far_field_state(P, q, gn, fr, olast, Ub2, Cb2, a2, b2, x2, y2, z2);
-        if (Ub2 > 0.) { copy3_flat(tk, fr, o); if (sst) copy3_flat(tw, fr, o); }
-        else if (sst) { fix3(tk, fr, o, fx[F3D_FIX_TK][fi]); fix3(tw, fr, o, fx[FIX_7][fi]); }
+        if (Ub2 > 0.) { copy3_flat(tk, fr, o); if (sst) copy3_flat(tw, fr, o); if (lctm) copy3_flat(tgm, fr, o); }
+        else if (sst) { fix3(tk, fr, o, fx[F3D_FIX_TK][fi]); fix3(tw, fr, o, fx[FIX_7][fi]); if (lctm) fix3(tgm, fr, o, fx[F3D_FIX_TGM][fi]); }
         else fix3(tk, fr, o, fx[F3D_FIX_TV][fi]);
       }
       break;
@@ -235,8 +245,8 @@ __global__ void k_bc_face(const Params P, double* __restrict__ q, const double* 
         const long long olast = (long long)(fr.na - 1) * fr.sa + (long long)(fr.nb - 1) * fr.sb;
         double Ub2, Cb2, a2, b2, x2, y2, z2;
         far_field_state(P, q, gn, fr, olast, Ub2, Cb2, a2, b2, x2, y2, z2);
-        if (Ub2 > 0.) { copy3_flat(tk, fr, o); if (sst) copy3_flat(tw, fr, o); }
-        else if (sst) { fix3(tk, fr, o, fx[F3D_FIX_TK][fi]); fix3(tw, fr, o, fx[FIX_7][fi]); }
+        if (Ub2 > 0.) { copy3_flat(tk, fr, o); if (sst) copy3_flat(tw, fr, o); if (lctm) copy3_flat(tgm, fr, o); }
+        else if (sst) { fix3(tk, fr, o, fx[F3D_FIX_TK][fi]); fix3(tw, fr, o, fx[FIX_7][fi]); if (lctm) fix3(tgm, fr, o, fx[F3D_FIX_TGM][fi]); }
         else fix3(tk, fr, o, fx[F3D_FIX_TV][fi]);
       }
       break;

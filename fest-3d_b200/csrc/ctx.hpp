@@ -17,7 +17,7 @@ namespace f3d {
 constexpr int kG3TX = 32, kG3TY = 4;   // tile of the fused sweep (fused_kernel.cuh), also the box of its tensor maps
 
 struct Layout {
-  int imx, jmx, kmx, nv, ng;        // ng = number of gradient components (4, 5 with sa, 6 with sst)
+  int imx, jmx, kmx, nv, ng;        // ng = number of gradient components (4, 5 with sa, 6 with sst, 7 with sst + lctm2015)
   int pi, pj, pk;                   // padded extents
   long long sj, sk, base, fs;       // strides, index of cell (0,0,0), doubles per field
   __host__ __device__ inline long long idx(int i, int j, int k) const { return base + i + sj * j + sk * (long long)k; }
@@ -38,18 +38,19 @@ struct Params {
   int current_iter;
   int viscous, sst, sa;   // sst: a two-equation model with n_var 7 (sst, sst2003, kkl: same field layout); sa: Spalart-Allmaras (n_var 6)
   int kkl;                // k-kL model: variable 7 is kL; its own mu_t, viscous-flux constants, source and point-implicit terms
+  int lctm;               // transition = lctm2015: n_var 8 (intermittency), n_grad 7; modified F1, its own SST source, gamma diffusion flux
   int trans_bc;           // transition = bc: algebraic gamma_BC factor on the production term (source.f90:467-604, 985-1194)
   double zlo[3], zhi[3];  // make_{F,G,H}_flux_zero at the first / last face of each direction (bc.f90:53-66)
   double c1, c2, c3;
   double CFL, global_time_step;
   double gm, R_gas, mu_ref, T_ref, Sutherland_temp, Pr, tPr;
   double inv_Pr, inv_tPr, inv_gm1;   // reciprocals of Pr, tPr, gm-1
-  double density_inf, x_speed_inf, y_speed_inf, z_speed_inf, pressure_inf, tk_inf, tw_inf, tv_inf, tkl_inf, MInf;
+  double density_inf, x_speed_inf, y_speed_inf, z_speed_inf, pressure_inf, tk_inf, tw_inf, tv_inf, tkl_inf, tgm_inf, MInf;
   double gama1, gama2, cd_floor, mut_floor, pk_limiter;
   double gama1_default, gama2_default;   // global_sst.f90:15-16 as they stand when add_sst_source never runs (transition = bc)
   double tu_inf, nu_cr;   // transition = bc: free-stream turbulence intensity (percent), chi_2 / Reynolds_number
   double fixed[F3D_NFIX][6];
-  double res_scale[8];    // Res_scale(1:n_var) (resnorm.f90:136-150)
+  double res_scale[9];    // Res_scale(1:n_var) (resnorm.f90:136-150)
 };
 
 struct Link {             // what sits behind an interface face
@@ -147,7 +148,8 @@ struct Ctx {
 // kernel launchers (each returns a CUDA error code through the context)
 int launch_temp(Ctx* ctx);
 int launch_bc(Ctx* ctx);
-int launch_gradients(Ctx* ctx);   // debugging views only (fest3d_gpu_get_aux): the sweep computes its own gradients in shared memory
+int launch_gradients(Ctx* ctx);   // staged form: gradients, viscosities, F1 into ctx->grad / ctx->mu (grad.cu)
+int launch_dvdy(Ctx* ctx);        // lctm2015: the CC.f90 field into aux field 3 (grad.cu)
 int launch_residual(Ctx* ctx, int mode, double TF, double SF, int use_store_sum, int first_stage, int last_stage);
 int launch_blend(Ctx* ctx, double a, double b);
 int launch_copy_fields(Ctx* ctx, double* dst, const double* src, int nfields);

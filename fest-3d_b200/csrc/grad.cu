@@ -1,13 +1,13 @@
-// DEBUGGING / PARITY VIEWS ONLY (fest3d_gpu_get_aux which = 1..3, 30..32).  On the hot path the gradients and viscosities are
-// computed inside the fused sweep and never reach HBM (fused_kernel.cuh: gradient_record, ghost_record); these two stand-alone
-// kernels write the same quantities to arrays so that a host can look at them: Green-Gauss cell gradients of
-// (u,v,w,T[,k,omega]) on cells 0..imx x 0..jmx x 0..kmx with the molecular (Sutherland) and eddy viscosity / SST blending function
-// F1 of the same cell, then the ghost-gradient rule and the ghost mu_t / F1 copies on physical faces.
+// Gradient / viscosity kernels of the STAGED form of the viscous path (the default, F3D_GRADIENTS=staged): Green-Gauss cell gradients of
+// (u,v,w,T[,k,omega | nu-tilde][,gamma]) on cells 0..imx x 0..jmx x 0..kmx with the molecular (Sutherland) and eddy viscosity / SST
+// blending function F1 of the same cell, then the ghost-gradient rule and the ghost mu_t / F1 copies on physical faces.  The sweep
+// (sweep3_kernel.cuh) stages these arrays with TMA.  With F3D_GRADIENTS=fused the sweep computes the same quantities in shared memory
+// (fused_kernel.cuh) and these kernels only serve the views of fest3d_gpu_get_aux (which = 1..3, 30..32).
 //
 // Reference: src/gradients.f90:276-402 (evaluate_all_gradients), :405-482 (compute_gradient_G), :486-676
 // (apply_gradient_bc, incl. the Ifaces-shaped dummy that mis-indexes Jfaces/Kfaces -- those records are gathered on the
 // host into ctx->gbc with the reference's linear offset); src/viscosity.f90:109-138 (Sutherland), :343-388 (sst),
-// :215-263 (sst2003), :408-465 (ghost mu_t / F1).
+// :215-263 (sst2003), :265-279 / :390-404 (lctm2015 F1), :408-465 (ghost mu_t / F1), :469-533 (kkl); src/CC.f90:73-200 (lctm2015 fields).
 #include "ctx.hpp"
 #include "physics.cuh"
 #include <algorithm>
@@ -87,13 +87,14 @@ __global__ void __launch_bounds__(128, 5) k_gradients(const Params P, const doub
     const double fv1 = (pow3(xi)) / ((pow3(xi)) + (pow3(kCv1)));
     mu3[fs + c] = density * tv * fv1;
   }
-  if (NG == 6 && P.kkl) {   // k-kL: mu_t = cmu^(1/4) rho kL / max(sqrt(k), 1e-20), 0 below 1e-14 (viscosity.f90:469-484); no F1
+  constexpr bool TWO_EQ = (NG >= 6);   // sst, sst2003, kkl (6); sst / sst2003 with the intermittency of lctm2015 (7)
+  if (TWO_EQ && P.kkl) {   // k-kL: mu_t = cmu^(1/4) rho kL / max(sqrt(k), 1e-20), 0 below 1e-14 (viscosity.f90:469-484); no F1
     const double density = q[c], tk = q[5 * fs + c], tkl = q[6 * fs + c];
     double m = kKklCmu25 * density * tkl / (fmax(sqrt(tk), 1.e-20));
     if (tkl < 1.e-14 || tk < 1.e-14) m = 0.0;
     mu3[fs + c] = m;
     mu3[2 * fs + c] = 0.0;
-  } else if (NG == 6) {
+  } else if (TWO_EQ) {
     const double density = q[c], tk = q[5 * fs + c], tw = q[6 * fs + c];
     const double d = geom[(long long)G_DIST * fs + c];
     const double var1 = sqrt(tk) * rcp64(kBstar * tw * d);
@@ -116,8 +117,52 @@ __global__ void __launch_bounds__(128, 5) k_gradients(const Params P, const doub
     const double right = 4 * (density * kSigmaW2 * tk) * rcp64(CD * (d * d));
     const double left = dmax(var1, var2);
     const double arg1 = dmin(left, right);
-    mu3[2 * fs + c] = tanh((arg1 * arg1) * (arg1 * arg1));
+    double F1 = tanh((arg1 * arg1) * (arg1 * arg1));
+    if (NG == 7) {
+      // viscosity.f90:265-279 / :390-404 "modified blending function (Menter 2015)".  KEPT DEFECT: its loop reuses the scalars `density`
+      // and `tk` the loop above left behind -- those of its last cell (imx, jmx, kmx), a corner ghost cell -- for every cell.
+      const long long cl = L.idx(L.imx, L.jmx, L.kmx);
+      const double x = (q[cl] * d * sqrt(q[5 * fs + cl]) / mu) / 120;
+      const double x2 = x * x, x4 = x2 * x2;
+      F1 = fmax(F1, exp(-(x4 * x4)));
+    }
+    mu3[2 * fs + c] = F1;
   }
+}
+
+// lctm2015, CC.f90:73-122: find_CCnormal = Green-Gauss gradient g of the wall distance on cells 0..imx (compute_gradient :125-200),
+// normalised with |g| + 1e-12; find_DCCVn then -- KEPT DEFECT -- differentiates `dist` once more instead of CCVn = CCnormal . velocity,
+// so the "wall-normal velocity gradient" of add_sst_source_lctm2015 is DCCVn . CCnormal = |g|^2 / (|g| + 1e-12): a field fixed by the
+// grid.  Computed once per geometry / wall distance (api.cu:init_aux_fields) into aux field 3, where the sweep stages it.
+__global__ void k_dvdy(const Params P, const double* __restrict__ geom, double* __restrict__ out) {
+  const Layout& L = P.L;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y, k = blockIdx.z;
+  if (i > L.imx || j > L.jmx) return;
+  const long long fs = L.fs, c = L.idx(i, j, k), sj = L.sj, sk = L.sk;
+  const double* gI = geom + (long long)G_IA * fs;
+  const double* gJ = geom + (long long)G_JA * fs;
+  const double* gK = geom + (long long)G_KA * fs;
+  const double* var = geom + (long long)G_DIST * fs;
+  const double v0 = var[c];
+  double g[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    g[d] = (-(var[c - 1] + v0) * gI[(1 + d) * fs + c] * gI[c] - (var[c - sj] + v0) * gJ[(1 + d) * fs + c] * gJ[c] - (var[c - sk] + v0) * gK[(1 + d) * fs + c] * gK[c] +
+            (var[c + 1] + v0) * gI[(1 + d) * fs + c + 1] * gI[c + 1] + (var[c + sj] + v0) * gJ[(1 + d) * fs + c + sj] * gJ[c + sj] +
+            (var[c + sk] + v0) * gK[(1 + d) * fs + c + sk] * gK[c + sk]) /
+           (2 * geom[(long long)G_VOL * fs + c]);
+  }
+  const double mag = sqrt(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+  const double nx = g[0] / (mag + 1e-12), ny = g[1] / (mag + 1e-12), nz = g[2] / (mag + 1e-12);
+  out[c] = g[0] * nx + g[1] * ny + g[2] * nz;
+}
+
+int launch_dvdy(Ctx* ctx) {
+  const Layout& L = ctx->P.L;
+  dim3 block(32, 4, 1), grid((L.imx + 1 + 31) / 32, (L.jmx + 1 + 3) / 4, L.kmx + 1);
+  k_dvdy<<<grid, block, 0, ctx->stream>>>(ctx->P, ctx->geom, ctx->mu + 3 * L.fs);
+  F3D_CUDA(cudaGetLastError());
+  return 0;
 }
 
 // ghost-gradient rule + ghost mu_t/F1 on one physical face (gradients.f90:638-674, viscosity.f90:408-465)
@@ -173,10 +218,10 @@ __global__ void k_gradient_bc(const Params P, const double* __restrict__ q, cons
     if (id == -5) mu3[fs + cg] = -mu3[fs + ci];
     else if (id == -1 || id == -2 || id == -3 || id == -4 || id == -6 || id == -7 || id == -8 || id == -9) mu3[fs + cg] = mu3[fs + ci];
   }
-  if (NG == 6 && P.kkl) {   // viscosity.f90:488-531: copy on -4..-1, -6, -8, -9 (no -7), anti on the wall
+  if (NG >= 6 && P.kkl) {   // viscosity.f90:488-531: copy on -4..-1, -6, -8, -9 (no -7), anti on the wall
     if (id == -5) mu3[fs + cg] = -mu3[fs + ci];
     else if (id == -1 || id == -2 || id == -3 || id == -4 || id == -6 || id == -8 || id == -9) mu3[fs + cg] = mu3[fs + ci];
-  } else if (NG == 6) {
+  } else if (NG >= 6) {
     if (id == -5) { mu3[fs + cg] = -mu3[fs + ci]; mu3[2 * fs + cg] = mu3[2 * fs + ci]; }
     else if (id == -1 || id == -2 || id == -3 || id == -4 || id == -6 || id == -7 || id == -8 || id == -9) {
       mu3[fs + cg] = mu3[fs + ci]; mu3[2 * fs + cg] = mu3[2 * fs + ci];
@@ -198,6 +243,7 @@ int launch_gradients(Ctx* ctx) {
   dim3 block(32, 4, 1);
   dim3 grid((L.imx + 1 + G_ALIGN + 31) / 32, (L.jmx + 1 + 3) / 4, L.kmx + 1);
   if (ctx->P.sa) k_gradients<5><<<grid, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->err_dev);
+  else if (ctx->P.lctm) k_gradients<7><<<grid, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->err_dev);
   else if (ctx->P.sst) k_gradients<6><<<grid, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->err_dev);
   else k_gradients<4><<<grid, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->err_dev);
   ctx->launches++;
@@ -213,6 +259,7 @@ int launch_gradients(Ctx* ctx) {
   if (mask) {
     dim3 g2((na + 31) / 32, (nb + 3) / 4, 6);
     if (ctx->P.sa) k_gradient_bc<5><<<g2, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->gbc, ctx->gbc_off_dev, mask);
+    else if (ctx->P.lctm) k_gradient_bc<7><<<g2, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->gbc, ctx->gbc_off_dev, mask);
     else if (ctx->P.sst) k_gradient_bc<6><<<g2, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->gbc, ctx->gbc_off_dev, mask);
     else k_gradient_bc<4><<<g2, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->gbc, ctx->gbc_off_dev, mask);
     ctx->launches++;

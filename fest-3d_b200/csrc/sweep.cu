@@ -1,6 +1,6 @@
 // Launch side of the fused residual / time-step / update sweep: kernel arguments, CUDA-event timing of the sweep launch,
-// per-CTA norm partials -> Res_abs (resnorm.f90:171-199).  The kernel itself lives in fused_kernel.cuh (instantiated in
-// fused.cu / fused_rare.cu).
+// per-CTA norm partials -> Res_abs (resnorm.f90:171-199).  The kernels live in sweep3_kernel.cuh (staged form, the default:
+// sweep3.cu / sweep3_rare.cu) and fused_kernel.cuh (F3D_GRADIENTS=fused: fused.cu / fused_rare.cu).
 #include "sweep_common.cuh"
 #include <cstdlib>
 #include <cstring>

@@ -12,7 +12,7 @@ int sweep3_grid_ctas(const Layout& L) {
 }
 
 int launch_sweep3(Ctx* ctx, KArgs& a) {
-  const bool rare = ctx->P.trans_bc || ctx->P.pb_switch[0] || ctx->P.pb_switch[1] || ctx->P.pb_switch[2] || ctx->P.kkl;
+  const bool rare = ctx->P.trans_bc || ctx->P.pb_switch[0] || ctx->P.pb_switch[1] || ctx->P.pb_switch[2] || ctx->P.kkl || ctx->P.lctm;
   return rare ? launch_sweep3_rare(ctx, a) : g3::launch_sweep3_set<false>(ctx, a);
 }
 

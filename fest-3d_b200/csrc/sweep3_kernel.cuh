@@ -71,13 +71,13 @@ struct Sm : RecF<NV, VISC> {
   static constexpr int NF = NV + 3;                       // flux + the lambda / viscous / turbulent face terms of the time step
   static constexpr int PLANE = NV * PSQ + NR * PS;        // doubles per staged plane
   static constexpr int OFF_X = 2 * PLANE;                 // exchange area [2][NF][EX]: hi values, then fluxes (same slot)
-  static constexpr int NPK = (NV == 6) ? 5 : 4;           // cell packet: volume; sst: F1, S_k, S_w; sa: vorticity, S_v, mu, dist
+  static constexpr int NPK = (NV == 6 || NV == 8) ? 5 : 4;   // cell packet: volume; sst: F1, S_k, S_w [, S_gamma]; sa: vorticity, S_v, mu, dist
   static constexpr int OFF_PK = OFF_X + 2 * NF * EX;      // cell packets [2][NPK][NMAIN], written by the I rows
   static constexpr int OFF_PRIV = OFF_PK + 2 * NPK * NMAIN;   // private slots of the K threads, [field][NMAIN]:
   static constexpr int P_FK = 0;                          //   [3][NF] k-face flux; the face below plane p sits in third p % 3
   static constexpr int P_HI = 3 * NF;                     //   [2][NV] value at the high k face of the cell of plane p: half p & 1
-  static constexpr int P_Q2 = P_HI + 2 * NV;              //   [NV] q of plane k+2
-  static constexpr int P_VOL = P_Q2 + NV;                 //   [2] volume of planes (p & 1)
+  static constexpr int P_Q2 = P_HI + 2 * NV;              //   [NV] q of plane k+2 (not with eight variables: no room, read from global memory)
+  static constexpr int P_VOL = P_Q2 + (NV == 8 ? 0 : NV); //   [2] volume of planes (p & 1)
   static constexpr int NPRIV = P_VOL + 2;
   static constexpr int OFF_NRM = OFF_PRIV + NPRIV * NMAIN;   // norm partials of the 64 threads that do cell work, [NV+1][64]
   static constexpr int OFF_MBAR = OFF_NRM + (NV + 1) * 64;   // two mbarriers (one per staged-plane buffer)
@@ -126,7 +126,7 @@ template <int NV, bool VISC>
 __device__ __forceinline__ void cell_work(const Params& P, const KArgs& a, double* __restrict__ smem, int tx, int r, int i, int j, int kc,
                                           bool need_dt, bool k_active, double* __restrict__ nrm /* [NV+1], stride 64 */, bool kkl = false) {
   using S = Sm<NV, VISC>;
-  constexpr bool SST = (NV == 7), SA = (NV == 6), TURB = SST || SA;
+  constexpr bool SST = (NV >= 7), LCTM = (NV == 8), SA = (NV == 6), TURB = SST || SA;
   constexpr int NF = S::NF;
   const Layout& Ly = P.L;
   const long long fs = Ly.fs;
@@ -171,6 +171,7 @@ __device__ __forceinline__ void cell_work(const Params& P, const KArgs& a, doubl
   if (SST && VISC) {
     res[5] = res[5] - pk[2 * NMAIN];
     res[6] = res[6] - pk[3 * NMAIN];
+    if (LCTM) res[7] = res[7] - pk[4 * NMAIN];
   }
   if (SA && VISC) res[5] = res[5] - pk[2 * NMAIN];
 
@@ -271,6 +272,9 @@ __device__ __forceinline__ void cell_work(const Params& P, const KArgs& a, doubl
       if (SST) {
         a.qnew[5 * fs + cc] = (u2[5] >= 0.) ? u2[5] : qc[5];
         a.qnew[6 * fs + cc] = (u2[6] >= 0.) ? u2[6] : qc[6];
+        // lctm2015: update_with (update.f90:349-362, 462-484) writes qp(1:5), qp(6) and qp(7) back and nothing else -- the explicit
+        // integrators never advance the intermittency (only plusgs.f90:2129 does); its residual still enters R_store and the norms
+        if (LCTM) a.qnew[7 * fs + cc] = qc[7];
       }
       if (SA) a.qnew[5 * fs + cc] = fmax(u2[5], 1.e-12);   // update.f90:474-475
     }
@@ -288,7 +292,7 @@ static_assert(TX == kG3TX && TY == kG3TY, "tensor-map boxes are encoded for this
 template <int NV, int INTERP, int SCHEME, bool VISC, bool RARE>
 __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a, const __grid_constant__ TMaps tm) {
   using S = Sm<NV, VISC>;
-  constexpr bool SST = (NV == 7), SA = (NV == 6), TURB = SST || SA;
+  constexpr bool SST = (NV >= 7), LCTM = (NV == 8), SA = (NV == 6), TURB = SST || SA;
   constexpr bool SMQ = (INTERP == F3D_MUSCL || INTERP == F3D_INTERP_NONE);   // 3-point stencils read the staged planes
   constexpr int NF = S::NF;
   extern __shared__ __align__(128) double smem[];
@@ -424,7 +428,7 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a,
     if (k + 1 <= ke) stage_plane(k + 1);
     if (krow && k <= ke - 1) {
       if (own) cp_async8(smem + S::OFF_PRIV + (S::P_VOL + ((k + 1) & 1)) * NMAIN + cell, vol + Ly.idx(i, j, k + 1));
-      if (rec && SMQ) {
+      if (rec && SMQ && !LCTM) {
         const long long c2 = Ly.idx(i, j, k + 2);
 #pragma unroll
         for (int v = 0; v < NV; ++v) cp_async8(smem + S::OFF_PRIV + (S::P_Q2 + v) * NMAIN + cell, q + v * fs + c2);
@@ -469,7 +473,10 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a,
         if (SMQ) {
           double qm[NV], q0[NV], qp[NV];
 #pragma unroll
-          for (int v = 0; v < NV; ++v) { qm[v] = smem[o_m + v * PSQ]; q0[v] = smem[o_0 + v * PSQ]; qp[v] = smem[o_p + v * f_p]; }
+          for (int v = 0; v < NV; ++v) {
+            qm[v] = smem[o_m + v * PSQ]; q0[v] = smem[o_0 + v * PSQ];
+            qp[v] = (LCTM && krow) ? q[v * fs + cg + Ly.sk] : smem[o_p + v * f_p];   // plane k+2: no private slot with eight variables (Sm)
+          }
           double p_far = 0.0;   // pressure-based switching at the two ghost positions reads the pressure two cells inwards
           if (RARE && INTERP == F3D_MUSCL && P.pb_switch[d] && (cpos == 0 || cpos == mx)) {
             const int two = (cpos == 0) ? 2 : -2;
@@ -491,7 +498,8 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a,
 #pragma unroll
         for (int v = 0; v < NV; ++v) L[v] = smem[o_lr + v * f_x];
         face_eval<NV, SCHEME, VISC, PS, PSQ>(P, d, smem + o_ql, smem + o_qh, smem + o_ql - PW + NV * PSQ, smem + o_qh - PW + NV * PSQ, gA_, gnx, gny, gnz, cpos, mx, L, lo,
-                                             krow ? flux_on_k : true, need_dt, F, lam, vis, tur, RARE && P.kkl);
+                                             krow ? flux_on_k : true, need_dt, F, lam, vis, tur, RARE && P.kkl, &a,
+                                             cg - ((d == 0) ? 1 : ((d == 1) ? Ly.sj : Ly.sk)), cg);
 #pragma unroll
         for (int v = 0; v < NV; ++v) smem[o_fw + v * f_x] = F[v];
         if (need_dt || krow) {
@@ -564,6 +572,54 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a,
           pk[NMAIN] = mu_c;
           pk[2 * NMAIN] = S_k * volc;
           pk[3 * NMAIN] = S_kl * volc;
+        } else if (LCTM && VISC) {   // SST source terms with the gamma transition model (source.f90:273-463)
+          double g[6][3];
+#pragma unroll
+          for (int cc = 0; cc < 6; ++cc) {
+            if (cc == 3) continue;
+            g[cc][0] = rA[(3 * cc + 0) * PS]; g[cc][1] = rA[(3 * cc + 1) * PS]; g[cc][2] = rA[(3 * cc + 2) * PS];
+          }
+          const double mu_c = rA[S::OFF_MU * PS], mut = rA[(S::OFF_MU + 1) * PS], F1c = rA[(S::OFF_MU + 2) * PS], dvdy = rA[(S::OFF_MU + 3) * PS];
+          const double density = qA[0], tk = qA[5 * PSQ], tw = qA[6 * PSQ], gm_ = qA[7 * PSQ];
+          const double wx = g[2][1] - g[1][2], wy = g[0][2] - g[2][0], wz = g[1][0] - g[0][1];
+          const double vort = sqrt(wx * wx + wy * wy + wz * wz);
+          const double syz = g[2][1] + g[1][2], szx = g[0][2] + g[2][0], sxy = g[1][0] + g[0][1];
+          const double strain = sqrt(((syz * syz) + (szx * szx) + (sxy * sxy) + 2 * (g[0][0] * g[0][0]) + 2 * (g[1][1] * g[1][1]) + 2 * (g[2][2] * g[2][2])));
+          double CD = 2 * density * kSigmaW2 * (g[4][0] * g[5][0] + g[4][1] * g[5][1] + g[4][2] * g[5][2]) / tw;
+          CD = fmax(CD, P.cd_floor);
+          const double gama = P.gama1 * F1c + P.gama2 * (1. - F1c);
+          const double beta = kBeta1 * F1c + kBeta2 * (1. - F1c);
+          const double D_k = kBstar * density * tw * tk;
+          const double D_w = beta * density * (tw * tw);
+          const double divergence = g[0][0] + g[1][1] + g[2][2];
+          double P_k = mut * (vort * strain) - ((2.0 / 3.0) * density * tk * divergence);
+          P_k = fmin(P_k, P.pk_limiter * D_k);
+          const double P_w = (density * gama / mut) * P_k;
+          const double lamda = (1. - F1c) * CD;
+          const double dist_c = a.geom[(long long)G_DIST * fs + c];
+          double lamd = (-7.57e-3) * (dvdy * dist_c * dist_c * density / mu_c) + 0.0128;
+          lamd = fmin(fmax(lamd, -1.0), 1.0);
+          double Fpg = (lamd >= 0.0) ? fmin(1.0 + 14.68 * lamd, 1.5) : fmin(1.0 - 7.34 * lamd, 3.0);
+          Fpg = fmax(Fpg, 0.0);
+          const double TuL = fmin(100.0 * sqrt(2.0 * tk / 3.0) / (tw * dist_c), 100.0);
+          const double Re_theta = 100.0 + 1000.0 * exp(-TuL * Fpg);
+          const double Rev = density * dist_c * dist_c * strain / mu_c;
+          const double RT = density * tk / (mu_c * tw);
+          const double hr = 0.5 * RT;
+          const double Fturb = exp(-((hr * hr) * (hr * hr)));
+          const double Fonset1 = Rev / (2.2 * Re_theta);
+          const double Fonset2 = fmin(Fonset1, 2.0);
+          const double r35 = RT / 3.5;
+          const double Fonset3 = fmax(1.0 - (r35 * r35 * r35), 0.0);
+          const double Fonset = fmax(Fonset2 - Fonset3, 0.0);
+          const double P_gm = 100 * density * strain * gm_ * (1.0 - gm_) * Fonset;
+          const double D_gm = 0.06 * density * vort * gm_ * Fturb * ((50.0 * gm_) - 1.0);
+          const double Fon_lim = fmin(fmax((Rev / (2.2 * 1100.0)) - 1.0, 0.0), 3.0);
+          const double Pk_lim = 5 * fmax(gm_ - 0.2, 0.0) * (1.0 - gm_) * Fon_lim * fmax(3 * mu_c - mut, 0.0) * strain * vort;
+          pk[NMAIN] = F1c;
+          pk[2 * NMAIN] = (gm_ * P_k - fmax(gm_, 0.1) * D_k + Pk_lim) * volc;
+          pk[3 * NMAIN] = (P_w - D_w + lamda) * volc;
+          pk[4 * NMAIN] = (P_gm - D_gm) * volc;
         } else if (SST && VISC) {   // SST source terms (source.f90:214-268)
           double g[6][3];
 #pragma unroll
@@ -755,6 +811,10 @@ static int launch_interp(Ctx* ctx, KArgs& a) {
 template <bool RARE>
 static int launch_sweep3_set(Ctx* ctx, KArgs& a) {
   if (ctx->P.sa) return ctx->P.viscous ? launch_interp<6, true, RARE>(ctx, a) : F3D_ERR_UNSUPPORTED;   // sa needs mu_ref /= 0
+  if (ctx->P.lctm) {   // eight variables: compiled into the second set only (sweep3_rare.cu)
+    if constexpr (RARE) return ctx->P.viscous ? launch_interp<8, true, true>(ctx, a) : F3D_ERR_UNSUPPORTED;
+    else return F3D_ERR_UNSUPPORTED;
+  }
   if (ctx->P.viscous) return ctx->P.sst ? launch_interp<7, true, RARE>(ctx, a) : launch_interp<5, true, RARE>(ctx, a);
   return launch_interp<5, false, RARE>(ctx, a);
 }

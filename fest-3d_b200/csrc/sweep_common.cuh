@@ -10,15 +10,18 @@ namespace f3d {
 
 template <int NV, bool VISC>
 struct RecF {   // fields of the non-q part of a cell record
-  static constexpr bool SST = (NV == 7);                  // sst / sst2003 (k, omega)
+  static constexpr bool SST = (NV >= 7);                  // sst / sst2003 (k, omega), k-kL (k, kL)
+  static constexpr bool LCTM = (NV == 8);                  // sst / sst2003 + the intermittency of transition = lctm2015 (variable 8)
   static constexpr bool SA = (NV == 6);                    // Spalart-Allmaras (nu-tilde)
-  static constexpr int NG = SST ? 6 : (SA ? 5 : 4);        // u, v, w, T [, k, omega | nu-tilde]
+  // staged gradient components: u, v, w, T [, k, omega | nu-tilde].  The intermittency gradient (component 6 of lctm2015) is NOT staged:
+  // with eight variables the shared memory of an SM is full, so its diffusion flux reads it -- and the cell centres -- from global memory
+  static constexpr int NG = SST ? 6 : (SA ? 5 : 4);
   static constexpr int NGF = VISC ? 3 * NG : 0;            // gradient component c, direction d -> field 3*c+d
   static constexpr int NGFS = (NGF + 1) & ~1;              // staged slots of the gradient fields: an even count (tensor-map boxes
                                                            // need 128-byte aligned sub-boxes; sa has 15 fields -> one unused slot)
   static constexpr int NMU = VISC ? (SST ? 3 : (SA ? 2 : 1)) : 0;   // mu, mu_t, F1
-  static constexpr int OFF_MU = NGFS, OFF_C = NGFS + NMU;  // then the cell centre x,y,z
-  static constexpr int NAUX = VISC ? NMU + 3 : 0;          // "aux" fields behind the gradients: mu [, mu_t [, F1]], centre x,y,z
+  static constexpr int OFF_MU = NGFS, OFF_C = NGFS + NMU;  // then the cell centre x,y,z (lctm2015: the CC.f90 field instead, grad.cu:k_dvdy)
+  static constexpr int NAUX = VISC ? (LCTM ? NMU + 1 : NMU + 3) : 0;   // "aux" fields behind the gradients: mu [, mu_t [, F1]], centre x,y,z
   static constexpr int NAUXS = (NAUX + 1) & ~1;
   static constexpr int NR = VISC ? NGFS + NAUXS : 0;
 };
@@ -193,12 +196,19 @@ __device__ __forceinline__ void recon3(const Params& P, const double (&qm)[NV], 
 template <int NV, int PS, int PSQ>
 __device__ __forceinline__ void viscous_face(const Params& P, const double* __restrict__ ql_, const double* __restrict__ qh_,
                                              const double* __restrict__ rl, const double* __restrict__ rh, double A, double nx, double ny,
-                                             double nz, bool sst_on, bool need_dt, double (&F)[NV], double& vis, double& tur, bool kkl = false) {
+                                             double nz, bool sst_on, bool need_dt, double (&F)[NV], double& vis, double& tur, bool kkl = false,
+                                             const KArgs* a = nullptr, long long fs = 0, long long cgl = 0, long long cgh = 0) {
   using R = RecF<NV, true>;
-  constexpr bool SST = (NV == 7), SA = (NV == 6), TURB = SST || SA;
+  constexpr bool SST = R::SST, SA = R::SA, LCTM = R::LCTM, TURB = SST || SA;
   constexpr int NG = R::NG;
-  const double dx = rh[(R::OFF_C + 0) * PS] - rl[(R::OFF_C + 0) * PS], dy = rh[(R::OFF_C + 1) * PS] - rl[(R::OFF_C + 1) * PS],
-               dz = rh[(R::OFF_C + 2) * PS] - rl[(R::OFF_C + 2) * PS];
+  double dx, dy, dz;
+  if (LCTM) {   // the centres are not staged (RecF): cells cgl / cgh of the global arrays
+    const double* __restrict__ cx = a->geom + (long long)G_CX * fs;
+    dx = cx[cgh] - cx[cgl]; dy = cx[fs + cgh] - cx[fs + cgl]; dz = cx[2 * fs + cgh] - cx[2 * fs + cgl];
+  } else {
+    dx = rh[(R::OFF_C + 0) * PS] - rl[(R::OFF_C + 0) * PS]; dy = rh[(R::OFF_C + 1) * PS] - rl[(R::OFF_C + 1) * PS];
+    dz = rh[(R::OFF_C + 2) * PS] - rl[(R::OFF_C + 2) * PS];
+  }
   const double inv_d = rsqrt64(dx * dx + dy * dy + dz * dz);   // 1 / d_LR
   const double ex = dx * inv_d, ey = dy * inv_d, ez = dz * inv_d;
   double ql[NV], qh[NV];
@@ -272,7 +282,7 @@ __device__ __forceinline__ void viscous_face(const Params& P, const double* __re
     const double sk = kkl ? 1.0 : kSigmaK1 * F1 + kSigmaK2 * (1.0 - F1);
     const double sw = kkl ? 1.0 : kSigmaW1 * F1 + kSigmaW2 * (1.0 - F1);
     const double rhof = 0.5 * (ql[0] + qh[0]);
-    const double tkf = 0.5 * (ql[NV - 2] + qh[NV - 2]);
+    const double tkf = 0.5 * (ql[5] + qh[5]);
     const double Tk = -2.0 * rhof * tkf * (1. / 3.);
     const double dk = (A4 * ((mu_s + sk * mut_s) * (G[NG - 2][0] * nx + G[NG - 2][1] * ny + G[NG - 2][2] * nz)));
     const double dw = (A4 * ((mu_s + sw * mut_s) * (G[NG - 1][0] * nx + G[NG - 1][1] * ny + G[NG - 1][2] * nz)));
@@ -280,8 +290,19 @@ __device__ __forceinline__ void viscous_face(const Params& P, const double* __re
     F[2] = F[2] - (Tk * ny * A);
     F[3] = F[3] - (Tk * nz * A);
     F[4] = F[4] - dk;
-    F[NV - 2] = F[NV - 2] - dk;
-    F[NV - 1] = F[NV - 1] - dw;
+    F[5] = F[5] - dk;
+    F[6] = F[6] - dw;
+  }
+  if (LCTM && sst_on) {   // viscous.f90:659-746: diffusion of the intermittency with mu + mu_t; like the k / omega fluxes skipped on K faces when kmx == 2
+    const double* __restrict__ gg = a->grad + 18 * fs;   // gradient component 6, directions x, y, z
+    const double ax = gg[cgl] + gg[cgh], ay = gg[fs + cgl] + gg[fs + cgh], az = gg[2 * fs + cgl] + gg[2 * fs + cgh];
+    const double nc = ((2. * (qh[7] - ql[7])) - (ax * dx + ay * dy + az * dz)) * inv_d;
+    const double gx = ax + (nc * ex), gy = ay + (nc * ey), gz = az + (nc * ez);   // 2 x the face gradient
+#ifdef F3D_VISC_HALVES
+    F[7] = F[7] - (A * ((mu_s + mut_s) * ((0.5 * gx) * nx + (0.5 * gy) * ny + (0.5 * gz) * nz)));
+#else
+    F[7] = F[7] - (A4 * ((mu_s + mut_s) * (gx * nx + gy * ny + gz * nz)));
+#endif
   }
   if (SA) {   // viscous.f90:570-656: its "mut_f" is rho_face * nu-tilde_face, not the eddy viscosity; K flux also when kmx == 2
     const double rhof = 0.5 * (ql[0] + qh[0]);
@@ -307,7 +328,8 @@ template <int NV, int SCHEME, bool VISC, int PS, int PSQ>
 __device__ __forceinline__ void face_eval(const Params& P, int d, const double* __restrict__ ql, const double* __restrict__ qh,
                                           const double* __restrict__ rl, const double* __restrict__ rh, double A, double nx, double ny,
                                           double nz, int f, int m, double (&L)[NV], double (&R)[NV], bool flux_on, bool need_dt,
-                                          double (&F)[NV], double& lam, double& vis, double& tur, bool kkl = false) {
+                                          double (&F)[NV], double& lam, double& vis, double& tur, bool kkl = false, const KArgs* a = nullptr,
+                                          long long cgl = 0, long long cgh = 0) {
   if (P.interpolant != F3D_INTERP_NONE) {
     if (f == 1 && P.phys[2 * d]) {
       const bool far = P.farlike[2 * d] != 0;
@@ -332,7 +354,7 @@ __device__ __forceinline__ void face_eval(const Params& P, int d, const double* 
     const double vn = fabs((qh[1 * PSQ] * nx) + (qh[2 * PSQ] * ny) + (qh[3 * PSQ] * nz));
     lam = A * (vn + cbar);
   }
-  if (VISC) viscous_face<NV, PS, PSQ>(P, ql, qh, rl, rh, A, nx, ny, nz, (NV == 7) && flux_on, need_dt, F, vis, tur, kkl);
+  if (VISC) viscous_face<NV, PS, PSQ>(P, ql, qh, rl, rh, A, nx, ny, nz, (NV >= 7) && flux_on, need_dt, F, vis, tur, kkl, a, P.L.fs, cgl, cgh);
 }
 
 }  // namespace f3d

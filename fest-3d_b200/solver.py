@@ -58,7 +58,7 @@ def fill_config(cfg, blk):
     cfg.block_id, cfg.n_blocks = blk.block_id, blk.n_blocks
     cfg.CFL = c.CFL; cfg.global_time_step = s.global_time_step
     for k in ("gm", "R_gas", "mu_ref", "T_ref", "Sutherland_temp", "Pr", "tPr", "density_inf", "x_speed_inf",
-              "y_speed_inf", "z_speed_inf", "pressure_inf", "tk_inf", "tw_inf", "vel_mag", "MInf", "tv_inf", "tu_inf", "tkl_inf"):
+              "y_speed_inf", "z_speed_inf", "pressure_inf", "tk_inf", "tw_inf", "vel_mag", "MInf", "tv_inf", "tu_inf", "tkl_inf", "tgm_inf"):
         setattr(cfg, k, getattr(f, k))
     for sl in range(capi.NFIX):
         for i in range(6):

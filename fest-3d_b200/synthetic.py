@@ -23,7 +23,7 @@ TFP_FLOW = dict(density_inf=1.17659, x_speed_inf=69.445, y_speed_inf=0.0, z_spee
 
 
 def make_duct_blocks(n, nb=(1, 1, 1), scheme_name="ausm", interpolant="muscl", turbulence="sst", time_step_accuracy="none",
-                     CFL=0.5, limiter=(1, 1, 1), tlimiter=(1, 1, 1), only_blocks=None, mu_ref=None, n3=None):
+                     CFL=0.5, limiter=(1, 1, 1), tlimiter=(1, 1, 1), only_blocks=None, mu_ref=None, n3=None, transition="none"):
     """Return the list of BlockSetup for the duct.  ``n`` = cells per block edge (or n3 = (ni,nj,nk)).
     ``only_blocks``: build just these block ids (a rank builds only what it owns)."""
     ni, nj, nk = n3 if n3 is not None else (n, n, n)
@@ -35,7 +35,7 @@ def make_duct_blocks(n, nb=(1, 1, 1), scheme_name="ausm", interpolant="muscl", t
     if mu_ref is not None:
         flow_kw["mu_ref"] = mu_ref
     sch = case_mod.Scheme(scheme_name=scheme_name, interpolant=interpolant, limiter=tuple(limiter), tlimiter=tuple(tlimiter),
-                          turbulence=turbulence, time_step_accuracy=time_step_accuracy, time_stepping_method="l", accur=0)
+                          turbulence=turbulence, transition=transition, time_step_accuracy=time_step_accuracy, time_stepping_method="l", accur=0)
     fl = case_mod.Flow(**flow_kw).derive(turbulence)
     ctl = case_mod.Control(CFL=CFL)
     Nx, Ny, Nz = nbx * ni, nby * nj, nbz * nk     # global cell counts
@@ -83,9 +83,11 @@ def make_duct_blocks(n, nb=(1, 1, 1), scheme_name="ausm", interpolant="muscl", t
                 q[2] = fl.x_speed_inf * 1e-3 * s3
                 q[3] = fl.x_speed_inf * 1e-3 * s1 * s2
                 q[4] *= 1 + 1e-3 * s3
-                if blk.n_var == 7:
+                if blk.n_var >= 7:
                     q[5] *= 1 + 1e-3 * s2
                     q[6] *= 1 + 1e-3 * s1
+                    if blk.n_var == 8:      # intermittency in (0, 1): the explicit update never rewrites it (update.f90:349-362)
+                        q[7] = 0.55 + 0.4 * s3
                 elif blk.n_var == 6:
                     q[5] *= 1 + 1e-3 * s2
                 blocks.append(blk)

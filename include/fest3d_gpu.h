@@ -43,7 +43,7 @@ enum { F3D_T_NONE = 0, F3D_T_RK2 = 1, F3D_T_RK4 = 2, F3D_T_TVDRK2 = 3, F3D_T_TVD
 /* slots of the per-face fixed values (src/vartypes.f90:307-334, src/boundary/read_bc.f90:28-147) */
 enum {
   F3D_FIX_DENSITY = 0, F3D_FIX_PRESSURE, F3D_FIX_X_SPEED, F3D_FIX_Y_SPEED, F3D_FIX_Z_SPEED,
-  F3D_FIX_TK, F3D_FIX_TW, F3D_FIX_WALL_TEMP, F3D_FIX_TPRESSURE, F3D_FIX_TTEMPERATURE, F3D_FIX_TV, F3D_FIX_TKL,
+  F3D_FIX_TK, F3D_FIX_TW, F3D_FIX_WALL_TEMP, F3D_FIX_TPRESSURE, F3D_FIX_TTEMPERATURE, F3D_FIX_TV, F3D_FIX_TKL, F3D_FIX_TGM,
   F3D_NFIX
 };
 
@@ -55,14 +55,15 @@ enum {
   F3D_ERR_NEGATIVE_STATE = 8,/* rho<0, p<0 or NaN after update   update.f90:448-452 */
   F3D_ERR_GEOMETRY = 16,      /* non-positive cell volume  geometry.f90:476-494 (fest3d_gpu_setup_geometry only) */
   F3D_ERR_IO = 32,            /* checkpoint file cannot be written / read (fest3d_gpu_checkpoint_*, fest3d_gpu_restart) */
-  F3D_ERR_UNSUPPORTED = 64,  /* implicit / plusgs / saBC / lctm2015 (and kkl with F3D_GRADIENTS=fused): not on this path */
+  F3D_ERR_UNSUPPORTED = 64,  /* implicit / plusgs / saBC (and kkl or lctm2015 with F3D_GRADIENTS=fused): not on this path */
   F3D_ERR_CUDA = 128,
   F3D_ERR_ARGUMENT = 256,    /* also: an interface / periodic face that was neither linked locally nor given a communicator */
   F3D_ERR_PEER = 512         /* another rank reported an error in this call: every rank returns (Fatal_error stops the whole job) */
 };
 
 typedef struct {
-  int imx, jmx, kmx, n_var;            /* node counts of the block; n_var 5 (none), 6 (sa) or 7 (sst, sst2003, kkl)   vartypes.f90:21-26 */
+  int imx, jmx, kmx, n_var;            /* node counts of the block; n_var 5 (none), 6 (sa) or 7 (sst, sst2003, kkl); 8 = sst/sst2003 with
+                                          transition = lctm2015                                   state.f90:291-320 */
   int scheme, interpolant, turbulence, transition;
   int time_accuracy;                   /* F3D_T_*                                                update.f90:171 */
   int time_stepping;                   /* 0 = 'l' local, 1 = 'g' global                          time.f90:323-326 */
@@ -86,6 +87,7 @@ typedef struct {
   double tv_inf;                       /* free-stream nu-tilde of the SA model                   state.f90:105-106 */
   double tu_inf;                       /* free-stream turbulence intensity in percent (transition = bc)   source.f90:579,1164 */
   double tkl_inf;                      /* free-stream kL of the k-kL model                       state.f90:101-103 */
+  double tgm_inf;                      /* free-stream intermittency (transition = lctm2015)       vartypes.f90:258, state.f90:265 */
   double fixed[F3D_NFIX][6];           /* fixed_density(6), fixed_pressure(6) ...                read_bc.f90 */
 } Fest3dGpuConfig;
 
@@ -170,7 +172,8 @@ int fest3d_gpu_residual(Fest3dGpuCtx* ctx, int current_iter, double* residue_out
 int fest3d_gpu_residual_group(Fest3dGpuCtx** ctxs, int n_ctx, int current_iter);
 int fest3d_gpu_get_residue(Fest3dGpuCtx* ctx, double* residue_out);
 
-/* debugging / parity views: which = 0 delta_t(1:imx-1,..) ; 1 mu ; 2 mu_t ; 3 sst_F1 ; 4 Temp (all -2:imx+2,..) ;
+/* debugging / parity views: which = 0 delta_t(1:imx-1,..) ; 1 mu ; 2 mu_t ; 3 sst_F1 ; 4 Temp ; 5 the CC.f90 field of
+ * transition = lctm2015, DCCVn . CCnormal (all -2:imx+2,..) ;
  * 30,31,32 gradqp_x,y,z (0:imx,0:jmx,0:kmx,n_grad) */
 int fest3d_gpu_get_aux(Fest3dGpuCtx* ctx, int which, double* out);
 int fest3d_gpu_error(Fest3dGpuCtx* ctx, Fest3dGpuError* info);

@@ -27,12 +27,12 @@ enum { ORC_T_NONE = 0, ORC_T_RK2 = 1, ORC_T_RK4 = 2, ORC_T_TVDRK2 = 3, ORC_T_TVD
 /* fixed-value slots (reference: vartypes.f90:307-334) */
 enum {
   ORC_FIX_DENSITY = 0, ORC_FIX_PRESSURE, ORC_FIX_X_SPEED, ORC_FIX_Y_SPEED, ORC_FIX_Z_SPEED,
-  ORC_FIX_TK, ORC_FIX_TW, ORC_FIX_WALL_TEMP, ORC_FIX_TPRESSURE, ORC_FIX_TTEMPERATURE, ORC_FIX_TV, ORC_FIX_TKL,
+  ORC_FIX_TK, ORC_FIX_TW, ORC_FIX_WALL_TEMP, ORC_FIX_TPRESSURE, ORC_FIX_TTEMPERATURE, ORC_FIX_TV, ORC_FIX_TKL, ORC_FIX_TGM,
   ORC_NFIX
 };
 
 typedef struct {
-  int imx, jmx, kmx, n_var;          /* node counts; n_var 5, 6 (sa) or 7 */
+  int imx, jmx, kmx, n_var;          /* node counts; n_var 5, 6 (sa) or 7, +1 with transition = lctm2015 */
   int scheme, interpolant, turbulence, transition;
   int time_accuracy;                 /* ORC_T_* */
   int time_stepping;                 /* 0 = 'l' local, 1 = 'g' global */
@@ -55,6 +55,7 @@ typedef struct {
   double tv_inf;
   double tu_inf;                     /* percent */
   double tkl_inf;                    /* free-stream kL of the k-kL model (state.f90:101-103) */
+  double tgm_inf;                    /* free-stream intermittency of transition = lctm2015 (vartypes.f90:258, default 1) */
   double fixed[ORC_NFIX][6];
 } OracleConfig;
 

@@ -153,6 +153,7 @@ int oracle_get_aux(OracleWorld* w, int b, int which, double* out) {
     case 2: src = &B.mu_t.d; break;
     case 3: src = &B.F1.d; break;
     case 4: src = &B.Temp.d; break;
+    case 5: src = &B.dvdy.d; break;   // lctm2015 only
     case 10: src = &B.xl.d; break; case 11: src = &B.xr.d; break;
     case 12: src = &B.yl.d; break; case 13: src = &B.yr.d; break;
     case 14: src = &B.zl.d; break; case 15: src = &B.zr.d; break;

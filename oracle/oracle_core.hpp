@@ -76,6 +76,8 @@ struct Block {
   Arr4 xl, xr, yl, yr, zl, zr;        // x_qp_left ... (face_interpolant.f90:43-55)
   Arr4 gx, gy, gz;                    // gradqp_x/y/z (0:imx,0:jmx,0:kmx,n_grad)
   Arr3 Temp, delta_t, mu, mu_t, F1, dist, pdif;
+  Arr3 dvdy;                          // lctm2015: DCCVn . CCnormal of CC.f90 (a function of the wall distance only, see add_sst_source_lctm2015)
+  bool dvdy_ready = false;
   Rec4 cells, If, Jf, Kf;
   std::vector<int> zF, zG, zH;        // make_{F,G,H}_flux_zero, 1-based (bc.f90:53-66)
   double c1, c2, c3;                  // bc.f90:48-50

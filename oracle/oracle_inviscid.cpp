@@ -14,6 +14,7 @@ void Block::setup(const OracleConfig& cfg) {
   c = cfg;
   imx = c.imx; jmx = c.jmx; kmx = c.kmx; nv = c.n_var;
   n_grad = (c.turbulence == ORC_TURB_SST || c.turbulence == ORC_TURB_SST2003 || c.turbulence == ORC_TURB_KKL) ? 6 : (c.turbulence == ORC_TURB_SA ? 5 : 4);   // gradients.f90:160-175
+  if (c.transition == 2) n_grad += 1;   // lctm2015: the intermittency gradient is the last one (gradients.f90:259-264, :207-211)
   qp.alloc(-2, imx + 2, -2, jmx + 2, -2, kmx + 2, nv);
   Temp.alloc(-2, imx + 2, -2, jmx + 2, -2, kmx + 2);
   residue.alloc(1, imx - 1, 1, jmx - 1, 1, kmx - 1, nv);
@@ -38,6 +39,7 @@ void Block::setup(const OracleConfig& cfg) {
     F1.alloc(-2, imx + 2, -2, jmx + 2, -2, kmx + 2);
     dist.alloc(-2, imx + 2, -2, jmx + 2, -2, kmx + 2);
   }
+  if (c.transition == 2) dvdy.alloc(-2, imx + 2, -2, jmx + 2, -2, kmx + 2);   // CC.f90:59-66
   if (c.time_accuracy != ORC_T_NONE) U_store.alloc(-2, imx + 2, -2, jmx + 2, -2, kmx + 2, nv);
   if (c.time_accuracy == ORC_T_RK2 || c.time_accuracy == ORC_T_RK4)
     R_store.alloc(1, imx - 1, 1, jmx - 1, 1, kmx - 1, nv);
@@ -136,6 +138,7 @@ static void fix(Block& B, int var, int slot, int face) {
 static inline bool is_sst(const Block& B) { return B.c.turbulence == ORC_TURB_SST || B.c.turbulence == ORC_TURB_SST2003; }
 static inline bool is_sa(const Block& B) { return B.c.turbulence == ORC_TURB_SA; }
 static inline bool is_kkl(const Block& B) { return B.c.turbulence == ORC_TURB_KKL; }
+static inline bool is_lctm(const Block& B) { return B.c.transition == 2; }   // intermittency = variable 8 (bc_primitive.f90:143)
 
 // FT_bc.f90:15-107  flow_tangency.  NOTE (kept defect): for J and K faces the dot product uses the
 // Jfaces/Kfaces normal but the reflection subtracts 2*dot*Ifaces(i,1,k)%n etc. (FT_bc.f90:66-69,...)
@@ -251,6 +254,7 @@ static void far_field(Block& B, int face) {
         B.qp(ig, jg, kg, 5) = (B.qp(ig, jg, kg, 1) * Cb * Cb / c.gm);
         if (is_sst(B) || is_kkl(B)) { copy3(B, 6, FLAT, face); copy3(B, 7, FLAT, face); }
         if (is_sa(B)) copy3(B, 6, FLAT, face);
+        if (is_lctm(B)) copy3(B, 8, FLAT, face);
         already_fixed = 0;
       } else {
         double vel_diff = Unb - Uninf;
@@ -264,6 +268,7 @@ static void far_field(Block& B, int face) {
           if (is_sst(B)) { fix(B, 6, ORC_FIX_TK, face); fix(B, 7, ORC_FIX_TW, face); }
           if (is_kkl(B)) { fix(B, 6, ORC_FIX_TK, face); fix(B, 7, ORC_FIX_TKL, face); }
           if (is_sa(B)) fix(B, 6, ORC_FIX_TV, face);
+          if (is_lctm(B)) fix(B, 8, ORC_FIX_TGM, face);
         }
         already_fixed = 1;
       }
@@ -322,6 +327,7 @@ static void total_pressure(Block& B, int face) {
         B.qp(ig, jg, kg, 4) = B.qp(i, j, k, 4) + vel_diff * nz;
         if (is_sst(B) || is_kkl(B)) { copy3(B, 6, FLAT, face); copy3(B, 7, FLAT, face); }
         if (is_sa(B)) copy3(B, 6, FLAT, face);
+        if (is_lctm(B)) copy3(B, 8, FLAT, face);
       } else {
         double vel_diff = Unb - Uninf;
         B.qp(ig, jg, kg, 2) = c.x_speed_inf + vel_diff * nx;
@@ -330,6 +336,7 @@ static void total_pressure(Block& B, int face) {
         if (is_sst(B)) { fix(B, 6, ORC_FIX_TK, face); fix(B, 7, ORC_FIX_TW, face); }
         if (is_kkl(B)) { fix(B, 6, ORC_FIX_TK, face); fix(B, 7, ORC_FIX_TKL, face); }
         if (is_sa(B)) fix(B, 6, ORC_FIX_TV, face);
+        if (is_lctm(B)) fix(B, 8, ORC_FIX_TGM, face);
       }
       int im = ig, jm = jg, km = kg;
       if (face == 5) { im = i; jm = j; km = k; }
@@ -372,6 +379,8 @@ void Block::populate_ghost_primitive() {
   // k-kL: kL (variable 7) follows the pattern of omega, except that the wall takes the anti copy instead of the wall-omega rule (:548-550)
   // and the subsonic inlet fixes it to fixed_tw, not fixed_tkl (:333-336, reproduced)
   const bool kkl = is_kkl(B);
+  // lctm2015: the intermittency is fixed at the two inlets (:259-265, :340-346) and copied flat everywhere else (:299-304 ... :554-559)
+  const bool lctm = is_lctm(B);
   for (int face = 1; face <= 6; ++face) {
     switch (c.bc_id[face - 1]) {
       case -1:  // supersonic_inlet :229
@@ -381,12 +390,14 @@ void Block::populate_ghost_primitive() {
           if (sst) { fix(B, 6, ORC_FIX_TK, face); fix(B, 7, ORC_FIX_TW, face); }
           if (kkl) { fix(B, 6, ORC_FIX_TK, face); fix(B, 7, ORC_FIX_TKL, face); }
           if (sa) fix(B, 6, ORC_FIX_TV, face);
+          if (lctm) fix(B, 8, ORC_FIX_TGM, face);
         }
         break;
       case -2:  // supersonic_outlet :270
         for (int v = 1; v <= 5; ++v) copy3(B, v, FLAT, face);
         if (sst || kkl) { copy3(B, 6, FLAT, face); copy3(B, 7, FLAT, face); }
         if (sa) copy3(B, 6, FLAT, face);
+        if (lctm) copy3(B, 8, FLAT, face);
         break;
       case -3:  // subsonic_inlet :308
         if (current_iter <= 2) {
@@ -394,6 +405,7 @@ void Block::populate_ghost_primitive() {
           fix(B, 4, ORC_FIX_Z_SPEED, face);
           if (sst || kkl) { fix(B, 6, ORC_FIX_TK, face); fix(B, 7, ORC_FIX_TW, face); }
           if (sa) fix(B, 6, ORC_FIX_TV, face);
+          if (lctm) fix(B, 8, ORC_FIX_TGM, face);
         }
         copy3(B, 5, FLAT, face);
         break;
@@ -402,6 +414,7 @@ void Block::populate_ghost_primitive() {
         if (current_iter <= 2) fix(B, 5, ORC_FIX_PRESSURE, face);
         if (sst || kkl) { copy3(B, 6, FLAT, face); copy3(B, 7, FLAT, face); }
         if (sa) copy3(B, 6, FLAT, face);
+        if (lctm) copy3(B, 8, FLAT, face);
         break;
       case -5:  // wall :392 -> pressure symm, temp_based_density, no_slip :528
         copy3(B, 5, SYMM, face);
@@ -410,17 +423,20 @@ void Block::populate_ghost_primitive() {
         if (sst) { copy3(B, 6, ANTI, face); set_omega_at_wall(B, face); }
         if (kkl) { copy3(B, 6, ANTI, face); copy3(B, 7, ANTI, face); }
         if (sa) copy3(B, 6, ANTI, face);
+        if (lctm) copy3(B, 8, FLAT, face);
         break;
       case -6:  // slip_wall :405
         copy3(B, 1, SYMM, face); copy3(B, 5, SYMM, face);
         if (sst || kkl) { copy3(B, 6, SYMM, face); copy3(B, 7, SYMM, face); }
         if (sa) copy3(B, 6, SYMM, face);
+        if (lctm) copy3(B, 8, FLAT, face);
         flow_tangency(B, face);
         break;
       case -7:  // pole :446
         for (int v = 1; v <= 5; ++v) copy3(B, v, FLAT, face);
         if (sst || kkl) { copy3(B, 6, FLAT, face); copy3(B, 7, FLAT, face); }
         if (sa) copy3(B, 6, FLAT, face);
+        if (lctm) copy3(B, 8, FLAT, face);
         break;
       case -8: far_field(B, face); break;
       case -9: periodic_bc(B, face); break;

@@ -12,7 +12,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-NFIX = 12
+NFIX = 13
 
 
 class OracleConfig(C.Structure):
@@ -30,7 +30,7 @@ class OracleConfig(C.Structure):
         ("Sutherland_temp", C.c_double), ("Pr", C.c_double), ("tPr", C.c_double),
         ("density_inf", C.c_double), ("x_speed_inf", C.c_double), ("y_speed_inf", C.c_double),
         ("z_speed_inf", C.c_double), ("pressure_inf", C.c_double),
-        ("tk_inf", C.c_double), ("tw_inf", C.c_double), ("vel_mag", C.c_double), ("MInf", C.c_double), ("tv_inf", C.c_double), ("tu_inf", C.c_double), ("tkl_inf", C.c_double),
+        ("tk_inf", C.c_double), ("tw_inf", C.c_double), ("vel_mag", C.c_double), ("MInf", C.c_double), ("tv_inf", C.c_double), ("tu_inf", C.c_double), ("tkl_inf", C.c_double), ("tgm_inf", C.c_double),
         ("fixed", (C.c_double * 6) * NFIX),
     ]
 
@@ -56,7 +56,7 @@ def fill_config(cfg, blk, enums):
     cfg.block_id, cfg.n_blocks = blk.block_id, blk.n_blocks
     cfg.CFL = c.CFL; cfg.global_time_step = s.global_time_step
     for k in ("gm", "R_gas", "mu_ref", "T_ref", "Sutherland_temp", "Pr", "tPr", "density_inf", "x_speed_inf",
-              "y_speed_inf", "z_speed_inf", "pressure_inf", "tk_inf", "tw_inf", "vel_mag", "MInf", "tv_inf", "tu_inf", "tkl_inf"):
+              "y_speed_inf", "z_speed_inf", "pressure_inf", "tk_inf", "tw_inf", "vel_mag", "MInf", "tv_inf", "tu_inf", "tkl_inf", "tgm_inf"):
         setattr(cfg, k, getattr(f, k))
     for sl in range(NFIX):
         for i in range(6):

@@ -238,6 +238,78 @@ def test_kkl_multiblock(pkg, case_mod, oracle):
     s.close()
 
 
+# ---- gamma transition model lctm2015 (n_var 8: k, omega, intermittency; source.f90:273-463, viscous.f90:659-746, viscosity.f90:265-279,
+# CC.f90, gradients.f90:382-389) ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("turbulence", ["sst", "sst2003"])
+@pytest.mark.parametrize("scheme_name,interpolant,ta", [("ausm", "muscl", "RK4"), ("slau", "weno", "none"), ("ausmUP", "ppm", "TVDRK3"), ("ldfss0", "none", "RK2")])
+def test_duct_lctm2015(pkg, case_mod, oracle, turbulence, scheme_name, interpolant, ta):
+    import importlib
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    blocks = syn.make_duct_blocks(None, n3=(37, 11, 9), scheme_name=scheme_name, interpolant=interpolant, turbulence=turbulence, transition="lctm2015",
+                                  time_step_accuracy=ta, CFL=0.5)
+    if turbulence == "sst2003":
+        blocks[0].qp[5] *= 0.25       # rho d sqrt(k) / mu = 75 .. 500 around the 120 of the modified blending function: both of its branches
+    gamma0 = blocks[0].qp[7].copy()
+    s = _solver(pkg, blocks)
+    _, w = _check_residual(oracle, s, blocks)
+    blk = blocks[0]
+    full = (blk.kmx + 5, blk.jmx + 5, blk.imx + 5)
+    K, J, I = slice(2, blk.kmx + 3), slice(2, blk.jmx + 3), slice(2, blk.imx + 3)      # cells 0..imx: where CC.f90 / viscosity.f90 compute
+    dv_o, dv_g = w.aux(0, 5, full)[K, J, I], s.blocks[0].aux(5, full)[K, J, I]
+    assert np.abs(dv_g - dv_o).max() <= 1e-13 * np.abs(dv_o).max()
+    F1_o, F1_g = w.aux(0, 3, full)[K, J, I], s.blocks[0].aux(3, full)[K, J, I]          # Menter-2015 F1 with the stale-scalar quirk
+    assert np.abs(F1_g - F1_o).max() <= 1e-12
+    _check_history(oracle, s, blocks, 5)
+    # the explicit integrators never advance the intermittency (update.f90:349-362): interior untouched, on both sides
+    q_g = s.blocks[0].get_state()
+    Ki, Ji, Ii = slice(3, blk.kmx + 2), slice(3, blk.jmx + 2), slice(3, blk.imx + 2)
+    if ta.startswith("TVD"):      # the TVD blends a*U_store + b*qp (update.f90:197-215) re-round the unchanged value
+        assert np.allclose(q_g[7][Ki, Ji, Ii], gamma0[Ki, Ji, Ii], rtol=1e-14, atol=0)
+    else:
+        assert np.array_equal(q_g[7][Ki, Ji, Ii], gamma0[Ki, Ji, Ii])
+    s.close()
+
+
+@pytest.mark.parametrize("bc", [[-3, -4, -5, -6, -6, -6], [-8, -4, -7, -6, -9, -9], [-11, -4, -5, -5, -5, -5], [-1, -2, -6, -5, -5, -6]])
+@pytest.mark.parametrize("shape", [(6, 5, 1), (9, 7, 5)])
+def test_lctm2015_boundary_conditions(pkg, case_mod, oracle, bc, shape):
+    import importlib
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    if (-9 in bc[4:]) and shape[2] < 3:
+        pytest.skip("periodic slab copy needs 3 interior layers")
+    blocks = syn.make_duct_blocks(None, n3=shape, turbulence="sst", transition="lctm2015", time_step_accuracy="RK2", interpolant="muscl")
+    blk = blocks[0]
+    blk.bc_id = list(bc)
+    fl = blk.flow
+    M2 = fl.x_speed_inf ** 2 / (fl.gm * fl.pressure_inf / fl.density_inf)
+    blk.fixed[8, :] = fl.pressure_inf * (1 + 0.5 * (fl.gm - 1.0) * M2) ** (fl.gm / (fl.gm - 1.0)) * (1.0 + 1e-3 * np.arange(6))
+    blk.fixed[12, :] = 0.9 - 0.05 * np.arange(6)     # fixed_tgm
+    blk.build_geometry()
+    s = _solver(pkg, blocks)
+    _check_residual(oracle, s, blocks)
+    _check_history(oracle, s, blocks, 4)
+    s.close()
+
+
+def test_lctm2015_multiblock(pkg, case_mod, oracle):
+    import importlib
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    blocks = syn.make_duct_blocks(None, n3=(10, 8, 6), nb=(2, 2, 2), turbulence="sst2003", transition="lctm2015", time_step_accuracy="RK4")
+    s = _solver(pkg, blocks)
+    _check_residual(oracle, s, blocks)
+    _check_history(oracle, s, blocks, 4)
+    s.close()
+
+
+def test_lctm2015_on_the_fused_form_is_refused(pkg, case_mod, fused_path):
+    import importlib
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    solver = importlib.import_module("fest3d_b200.solver")
+    with pytest.raises(solver.Fest3dError) as e:
+        solver.Solver(syn.make_duct_blocks(None, n3=(6, 5, 4), turbulence="sst", transition="lctm2015"))
+    assert e.value.rc & 64
+
+
 # ---- MUSCL / PPM pressure-based switching (muscl.f90:37-112, ppm.f90:108-170), every direction, quasi-2-D included -----------
 @pytest.mark.parametrize("interpolant", ["muscl", "ppm"])
 @pytest.mark.parametrize("shape,pb", [((20, 12, 10), (1, 1, 1)), ((33, 9, 1), (1, 0, 1)), ((7, 6, 5), (0, 1, 0))])

@@ -51,7 +51,7 @@ def test_config_struct_layout_matches_header(tmp_path):
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     size, nfix, off_gm, off_tkl, off_fixed = (int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split())
     cfg = capi.Fest3dGpuConfig
-    assert C.sizeof(cfg) == size and capi.NFIX == nfix == 12
+    assert C.sizeof(cfg) == size and capi.NFIX == nfix == 13
     assert cfg.gm.offset == off_gm and cfg.tkl_inf.offset == off_tkl and cfg.fixed.offset == off_fixed
     import oracle_py
     ocfg = oracle_py.OracleConfig

@@ -415,3 +415,97 @@ def test_kkl_model_pins(oracle, case_mod):
     assert np.array_equal(mut[K, 2, I], -mut[K, 3, I])
     # subsonic inlet at imin (bc -3): kL ghost layers = fixed_tw
     assert np.all(q[6, K, J, 0:3] == 3.0e-9) and np.all(q[5, K, J, 0:3] == fl.tk_inf)
+
+
+def _lctm_world(oracle, turbulence="sst", kscale=40.0):
+    import importlib
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    blocks = syn.make_duct_blocks(None, n3=(9, 7, 6), turbulence=turbulence, transition="lctm2015")
+    blk = blocks[0]
+    blk.qp[5] *= kscale        # 40: a turbulence level at which every term of the gamma model is active
+    w = oracle.OracleWorld(blocks)
+    err, r = w.residual(1)
+    assert err == 0
+    return blocks, blk, w, r[0]
+
+
+def test_lctm2015_blending_function_and_frozen_intermittency(oracle, case_mod):
+    """Two reference quirks of transition = lctm2015, pinned on the oracle: (1) the 'modified blending function' loop (viscosity.f90:390-404)
+    reuses the scalars density / tk left by the previous loop, i.e. those of cell (imx, jmx, kmx); (2) the explicit update never writes
+    variable 8 back (update.f90:349-362, 462-484)."""
+    import importlib
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    blocks, blk, w, _ = _lctm_world(oracle, kscale=0.25)      # rho d sqrt(k) / mu = 75 .. 500 around the model's 120
+    assert blk.n_var == 8 and blk.qp.shape[0] == 8
+    full = (blk.kmx + 5, blk.jmx + 5, blk.imx + 5)
+    q = w.get_state(0)
+    F1, mu = w.aux(0, 3, full), w.aux(0, 1, full)
+    # the same first seven variables without the transition model: the plain SST F1
+    plain = syn.make_duct_blocks(None, n3=(9, 7, 6), turbulence="sst")
+    plain[0].qp[:] = blocks[0].qp[:7]
+    wp = oracle.OracleWorld(plain)
+    assert wp.residual(1)[0] == 0
+    F1p = wp.aux(0, 3, full)
+    K, J, I = slice(2, blk.kmx + 3), slice(2, blk.jmx + 3), slice(2, blk.imx + 3)
+    rho_c, tk_c = q[0, blk.kmx + 2, blk.jmx + 2, blk.imx + 2], q[5, blk.kmx + 2, blk.jmx + 2, blk.imx + 2]
+    var2 = np.exp(-((rho_c * blk.dist[K, J, I] * np.sqrt(tk_c) / mu[K, J, I]) / 120) ** 8)
+    want = np.maximum(F1p[K, J, I], var2)
+    inner = (slice(1, -1),) * 3          # the boundary ring of F1 is then overwritten by the ghost rule
+    assert np.allclose(F1[K, J, I][inner], want[inner], rtol=1e-13, atol=0)
+    assert (var2[inner] > F1p[K, J, I][inner]).any() and (var2[inner] < F1p[K, J, I][inner]).any()
+    g0 = q[7].copy()
+    for it in range(1, 4):
+        assert w.step(it)[0] == 0
+    q1 = w.get_state(0)
+    Ki, Ji, Ii = slice(3, blk.kmx + 2), slice(3, blk.jmx + 2), slice(3, blk.imx + 2)
+    assert np.array_equal(q1[7][Ki, Ji, Ii], g0[Ki, Ji, Ii]) and not np.array_equal(q1[5][Ki, Ji, Ii], q[5][Ki, Ji, Ii])
+
+
+@pytest.mark.parametrize("turbulence", ["sst", "sst2003"])
+def test_lctm2015_source_against_numpy(oracle, case_mod, turbulence):
+    """add_sst_source_lctm2015 (source.f90:273-463) restated in numpy from the oracle's own gradients / viscosities, against what the
+    oracle subtracted from the flux balance (residue = sum of face fluxes - S * volume)."""
+    blocks, blk, w, res = _lctm_world(oracle, turbulence)
+    nv = 8
+    full = (blk.kmx + 5, blk.jmx + 5, blk.imx + 5)
+    F = w.aux(0, 20, (nv, blk.kmx - 1, blk.jmx - 1, blk.imx))
+    G = w.aux(0, 21, (nv, blk.kmx - 1, blk.jmx, blk.imx - 1))
+    H = w.aux(0, 22, (nv, blk.kmx, blk.jmx - 1, blk.imx - 1))
+    balance = (F[..., 1:] - F[..., :-1]) + (G[:, :, 1:, :] - G[:, :, :-1, :]) + (H[:, 1:] - H[:, :-1])
+    S_vol = balance - res                                  # what the source routine subtracted
+    gshape = (7, blk.kmx + 1, blk.jmx + 1, blk.imx + 1)
+    gx, gy, gz = (w.aux(0, 30 + d, gshape)[:, 1:-1, 1:-1, 1:-1] for d in range(3))
+    Ki, Ji, Ii = slice(3, blk.kmx + 2), slice(3, blk.jmx + 2), slice(3, blk.imx + 2)
+    q = w.get_state(0)[:, Ki, Ji, Ii]
+    mu, mut, F1, dvdy = (w.aux(0, n, full)[Ki, Ji, Ii] for n in (1, 2, 3, 5))
+    d, vol = blk.dist[Ki, Ji, Ii], blk.cells[Ki, Ji, Ii, 0]
+    rho, tk, tw, gam = q[0], q[5], q[6], q[7]
+    ux, uy, uz, vx, vy, vz, wx, wy, wz = gx[0], gy[0], gz[0], gx[1], gy[1], gz[1], gx[2], gy[2], gz[2]
+    vort = np.sqrt((wy - vz) ** 2 + (uz - wx) ** 2 + (vx - uy) ** 2)
+    strain = np.sqrt((wy + vz) ** 2 + (uz + wx) ** 2 + (vx + uy) ** 2 + 2 * ux ** 2 + 2 * vy ** 2 + 2 * wz ** 2)
+    s2003 = turbulence == "sst2003"
+    limiter = 10 if s2003 else 20
+    beta1, beta2, bstar, sigma_w2, kappa = 0.075, 0.0828, 0.09, 0.856, 0.41
+    gama1 = 5.0 / 9.0 if s2003 else beta1 / bstar - 0.5 * kappa ** 2 / np.sqrt(bstar)
+    gama2 = 0.44 if s2003 else beta2 / bstar - sigma_w2 * kappa ** 2 / np.sqrt(bstar)
+    CD = np.maximum(2 * rho * sigma_w2 * (gx[4] * gx[5] + gy[4] * gy[5] + gz[4] * gz[5]) / tw, 10.0 ** (-limiter))
+    gama, beta = gama1 * F1 + gama2 * (1 - F1), beta1 * F1 + beta2 * (1 - F1)
+    D_k, D_w = bstar * rho * tw * tk, beta * rho * tw ** 2
+    P_k = np.minimum(mut * vort * strain - (2.0 / 3.0) * rho * tk * (ux + vy + wz), limiter * D_k)
+    P_w = rho * gama / mut * P_k
+    lamd = np.clip(-7.57e-3 * (dvdy * d * d * rho / mu) + 0.0128, -1.0, 1.0)
+    Fpg = np.maximum(np.where(lamd >= 0, np.minimum(1 + 14.68 * lamd, 1.5), np.minimum(1 - 7.34 * lamd, 3.0)), 0.0)
+    TuL = np.minimum(100 * np.sqrt(2 * tk / 3) / (tw * d), 100.0)
+    Re_theta = 100 + 1000 * np.exp(-TuL * Fpg)
+    Rev, RT = rho * d * d * strain / mu, rho * tk / (mu * tw)
+    Fonset = np.maximum(np.minimum(Rev / (2.2 * Re_theta), 2.0) - np.maximum(1 - (RT / 3.5) ** 3, 0.0), 0.0)
+    P_gm = 100 * rho * strain * gam * (1 - gam) * Fonset
+    D_gm = 0.06 * rho * vort * gam * np.exp(-(0.5 * RT) ** 4) * (50 * gam - 1)
+    Fon_lim = np.clip(Rev / (2.2 * 1100.0) - 1.0, 0.0, 3.0)
+    Pk_lim = 5 * np.maximum(gam - 0.2, 0) * (1 - gam) * Fon_lim * np.maximum(3 * mu - mut, 0) * strain * vort
+    want = {5: (gam * P_k - np.maximum(gam, 0.1) * D_k + Pk_lim) * vol, 6: (P_w - D_w + (1 - F1) * CD) * vol, 7: (P_gm - D_gm) * vol}
+    for v, wv in want.items():
+        scale = np.abs(balance[v]) + np.abs(res[v]) + np.abs(wv)
+        assert np.abs(S_vol[v] - wv).max() <= 2e-12 * scale.max(), v
+        assert np.abs(wv).max() > 1e-3 * np.abs(res[v]).max(), v          # the term is not negligible in this state
+    assert np.count_nonzero(Fonset) > 0 and np.count_nonzero(Fon_lim) >= 0
