@@ -74,7 +74,14 @@ extern "C" int fest3d_gpu_create(Fest3dGpuCtx** out, const Fest3dGpuConfig* cfg,
   if (lctm && !(sst && !kkl)) return F3D_ERR_UNSUPPORTED;
   if (cfg->transition != F3D_TRANS_NONE && cfg->transition != F3D_TRANS_BC && !lctm) return F3D_ERR_ARGUMENT;
   if (kkl || lctm) { const char* e = getenv("F3D_GRADIENTS"); if (e && strcmp(e, "fused") == 0) return F3D_ERR_UNSUPPORTED; }   // staged form only
-  if (cfg->time_accuracy >= F3D_T_IMPLICIT || cfg->time_accuracy < 0) return F3D_ERR_UNSUPPORTED;
+  if (cfg->time_accuracy > F3D_T_IMPLICIT || cfg->time_accuracy < 0) return F3D_ERR_UNSUPPORTED;   // plusgs
+  if (cfg->time_accuracy == F3D_T_IMPLICIT) {
+    // LU-SGS: the laminar / inviscid and the SST routines of lusgs.f90 (:186, :686); its sa, kkl and lctm2015 routines are not built.  The sweeps
+    // read mu / mu_t / F1 as arrays, which only the staged form of the viscous path keeps.
+    if (sa || kkl || lctm) return F3D_ERR_UNSUPPORTED;
+    const char* e = getenv("F3D_GRADIENTS");
+    if (cfg->mu_ref != 0.0 && e && strcmp(e, "fused") == 0) return F3D_ERR_UNSUPPORTED;
+  }
   if (cfg->scheme < 0 || cfg->scheme > F3D_SLAU || cfg->interpolant < 0 || cfg->interpolant > F3D_WENO_NM) return F3D_ERR_ARGUMENT;
   if (cfg->n_var != (sst ? 7 : (sa ? 6 : 5)) + (lctm ? 1 : 0)) return F3D_ERR_ARGUMENT;   // state.f90:291-320
   if ((sst || sa) && cfg->mu_ref == 0.0) return F3D_ERR_UNSUPPORTED;
@@ -164,8 +171,9 @@ static int create_impl(Fest3dGpuCtx* ctx, const Fest3dGpuConfig* cfg, int device
   };
   F3D_CUDA(dalloc(&ctx->qp, nv)); F3D_CUDA(dalloc(&ctx->qp2, nv)); F3D_CUDA(dalloc(&ctx->residue, nv));
   F3D_CUDA(dalloc(&ctx->temp, 1)); F3D_CUDA(dalloc(&ctx->dt, 1)); F3D_CUDA(dalloc(&ctx->geom, G_NFIELDS));
-  if (cfg->time_accuracy != F3D_T_NONE) F3D_CUDA(dalloc(&ctx->ustore, nv));
+  if (cfg->time_accuracy != F3D_T_NONE && cfg->time_accuracy != F3D_T_IMPLICIT) F3D_CUDA(dalloc(&ctx->ustore, nv));
   if (cfg->time_accuracy == F3D_T_RK2 || cfg->time_accuracy == F3D_T_RK4) F3D_CUDA(dalloc(&ctx->rstore, nv));
+  if (cfg->time_accuracy == F3D_T_IMPLICIT) { F3D_CUDA(dalloc(&ctx->lusgs_dqs, nv)); F3D_CUDA(dalloc(&ctx->lusgs_dq, nv)); F3D_CUDA(dalloc(&ctx->lusgs_lam, 3)); }
   ctx->n_mu = sst ? 3 : (sa ? 2 : 1);
   {   // form of the viscous path: "staged" (default: measured faster on B200) or "fused" (no gradient / viscosity array in HBM)
     const char* e = getenv("F3D_GRADIENTS");
@@ -248,7 +256,7 @@ extern "C" int fest3d_gpu_destroy(Fest3dGpuCtx* ctx) {
   checkpoint_free(ctx);   // joins a writer thread that may still be copying
   cudaDeviceSynchronize();
   double* bufs[] = {ctx->qp, ctx->qp2, ctx->ustore, ctx->rstore, ctx->residue, ctx->temp, ctx->dt, ctx->geom, ctx->grad, ctx->mu, ctx->gbc,
-                    ctx->red, ctx->norms_dev, ctx->staging, ctx->state_staging};
+                    ctx->red, ctx->norms_dev, ctx->staging, ctx->state_staging, ctx->lusgs_dqs, ctx->lusgs_dq, ctx->lusgs_lam};
   for (double* b : bufs) if (b) cudaFree(b);
   for (int f = 0; f < 6; ++f) { if (ctx->sendbuf[f]) cudaFree(ctx->sendbuf[f]); if (ctx->recvbuf[f]) cudaFree(ctx->recvbuf[f]); }
   if (ctx->err_dev) cudaFree(ctx->err_dev);
@@ -773,7 +781,7 @@ int exchange(Fest3dGpuCtx** cs, int n) {
 }
 
 // one get_total_conservative_Residue (+ update) on every context
-int stage(Fest3dGpuCtx** cs, int n, bool update, double TF, double SF, int use_sum, int first, int last, bool post_ahead = false) {
+int stage(Fest3dGpuCtx** cs, int n, bool update, double TF, double SF, int use_sum, int first, int last, bool post_ahead = false, bool implicit = false) {
   int rc = exchange(cs, n);
   if (rc) return rc;
   for (int c = 0; c < n; ++c) {
@@ -781,6 +789,12 @@ int stage(Fest3dGpuCtx** cs, int n, bool update, double TF, double SF, int use_s
     F3D_CUDA(cudaSetDevice(ctx->device));
     if ((rc = launch_bc(ctx))) return rc;
     if (ctx->P.viscous && !ctx->fused && (rc = launch_gradients(ctx))) return rc;   // staged path: gradients + viscosities into HBM
+    if (implicit) {   // update.f90:216-219: residual, time step, then the LU-SGS sweeps update qp in place (ghost layers stay as filled)
+      if ((rc = launch_residual(ctx, MODE_RESIDUE_ONLY, 1.0, 1.0, 0, 1, 1))) return rc;
+      if (ctx->P.time_stepping == 1 && !(ctx->P.global_time_step > 0) && (rc = launch_global_dt(ctx))) return rc;
+      if ((rc = launch_lusgs(ctx))) return rc;
+      continue;
+    }
     if (!update) {
       if ((rc = launch_residual(ctx, MODE_RESIDUE_ONLY, 1.0, 1.0, 0, 1, 0))) return rc;
       continue;
@@ -795,6 +809,7 @@ int stage(Fest3dGpuCtx** cs, int n, bool update, double TF, double SF, int use_s
     if ((rc = launch_residual(ctx, MODE_UPDATE, TF, SF, use_sum, fst, last))) return rc;
     std::swap(ctx->qp, ctx->qp2);
   }
+  if (implicit) return post_ahead ? exchange_post(cs, n) : 0;
   if (!update) return 0;
   // the interior layers of the new state exist: the next stage's swap can leave now, beside the ghost-shell carry-over
   if (post_ahead && (rc = exchange_post(cs, n))) return rc;
@@ -858,7 +873,7 @@ int issue_iteration(Fest3dGpuCtx** cs, int n, int ta, int iter, bool more_follow
     F3D_CUDA(cudaSetDevice(ctx->device));
     ctx->P.current_iter = iter;
     if ((rc = launch_temp(ctx))) return rc;   // update.f90:170
-    if (ta != F3D_T_NONE && (rc = launch_copy_fields(ctx, ctx->ustore, ctx->qp, ctx->P.L.nv))) return rc;       // U_store = qp
+    if (ta != F3D_T_NONE && ta != F3D_T_IMPLICIT && (rc = launch_copy_fields(ctx, ctx->ustore, ctx->qp, ctx->P.L.nv))) return rc;       // U_store = qp
     if ((ta == F3D_T_RK2 || ta == F3D_T_RK4) && (rc = launch_zero_fields(ctx, ctx->rstore, ctx->P.L.nv))) return rc;  // R_store = 0
   }
   auto blend_all = [&](double a, double b) { for (int c = 0; c < n && !rc; ++c) { cudaSetDevice(cs[c]->device); rc = launch_blend(cs[c], a, b); } return rc; };
@@ -883,6 +898,8 @@ int issue_iteration(Fest3dGpuCtx** cs, int n, int ta, int iter, bool more_follow
       if ((rc = stage(cs, n, true, 1.0, 1., 0, 1, 0, A))) break;
       if ((rc = stage(cs, n, true, 1.0, 1., 0, 0, 1))) break;
       rc = blend_all(0.5, 0.5); break;
+    case F3D_T_IMPLICIT:
+      rc = stage(cs, n, false, 1., 1., 0, 1, 1, Z, true); break;
     default: rc = F3D_ERR_UNSUPPORTED;
   }
   if (rc) return rc;

@@ -92,6 +92,11 @@ struct Ctx {
   double* gbc = nullptr;      // per-face (A,nx,ny,nz) records the ghost-gradient rule reads (mis-indexed for J/K faces)
   long long gbc_off[6];
   long long* gbc_off_dev = nullptr;   // the same offsets on the device
+  // implicit LU-SGS (time_accuracy = implicit, lusgs.cu): delQstar and delQ (nv fields each; ghost cells stay zero) and the three face
+  // fields of spectral radius x area
+  double* lusgs_dqs = nullptr;
+  double* lusgs_dq = nullptr;
+  double* lusgs_lam = nullptr;
   double* red = nullptr;      // reduction partials
   int red_blocks = 0;
   double* norms_dev = nullptr;   // (nv+1) per iteration slot
@@ -149,6 +154,7 @@ struct Ctx {
 int launch_temp(Ctx* ctx);
 int launch_bc(Ctx* ctx);
 int launch_gradients(Ctx* ctx);   // staged form: gradients, viscosities, F1 into ctx->grad / ctx->mu (grad.cu)
+int launch_lusgs(Ctx* ctx);       // implicit update of qp in place from residue and dt (lusgs.cu)
 int launch_dvdy(Ctx* ctx);        // lctm2015: the CC.f90 field into aux field 3 (grad.cu)
 int launch_residual(Ctx* ctx, int mode, double TF, double SF, int use_store_sum, int first_stage, int last_stage);
 int launch_blend(Ctx* ctx, double a, double b);

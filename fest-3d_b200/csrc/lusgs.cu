@@ -1,0 +1,268 @@
+// Implicit LU-SGS update (time_step_accuracy = implicit) for laminar / inviscid flow and the SST models: SURVEY.md 8(f) rank 4.
+//
+// Reference: src/lusgs.f90:134-183 (update_with_lusgs), :186-488 (update_laminar_variables), :491-630 (Flux), :633-683
+// (SpectralRadius), :686-1024 (update_SST_variables), :1027-1196 (SSTFlux); called from update.f90:216-219 after one residual
+// evaluation and the time-step computation.
+//
+// The reference sweeps the block lexicographically (forward k,j,i ascending; backward descending): cell (i,j,k) reads the correction of
+// (i-1,j,k), (i,j-1,k), (i,j,k-1) in the forward sweep and of the three high neighbours in the backward one.  Cells on a hyperplane
+// i+j+k = h do not depend on each other, and every cell reads only finished values whichever order the hyperplanes' cells are taken in,
+// so marching the hyperplanes h = 3 .. imx+jmx+kmx-3 (one launch each, ascending then descending) reproduces the reference bit for bit up
+// to FMA contraction -- there is no reduction whose order could change.  Corrections outside the block are zero (delQ / delQstar are
+// allocated 0:imx and never written there, lusgs.f90:114-115): the blocks of a multi-block case are not coupled inside the sweeps.
+//
+// Work shared by both sweeps is done once, in a data-parallel pre-pass: the spectral radius times area of every face (SpectralRadius is
+// symmetric in its two cells bit for bit: sums commute, |x| = |-x|), three face fields.
+//
+// Kernels: k_lusgs_lambda (pre-pass), k_lusgs_sweep<NV, FWD> (one hyperplane), k_lusgs_apply<NV> (conservative update, in place).
+// Access along a hyperplane is strided (each thread of a warp touches its own row): this path is latency- / sector-bound, not the
+// benchmark path; DESIGN.md section 3.6 has the measured cost.
+#include "ctx.hpp"
+#include "physics.cuh"
+#include <algorithm>
+
+namespace f3d {
+
+namespace {
+
+struct LFace { double A, nx, ny, nz, vol, mmu, tmu, F1; };
+
+// lusgs.f90:491-630 / :1027-1196
+template <int NV>
+__device__ __forceinline__ void lusgs_flux(const Params& P, const double (&ql)[NV], const double (&qr)[NV], const double (&du)[NV], const LFace& f,
+                                           double (&Flux)[NV]) {
+  const double gm = P.gm, R_gas = P.R_gas;
+  double U[NV], W[NV];
+  U[0] = ql[0];
+  U[1] = ql[0] * ql[1];
+  U[2] = ql[0] * ql[2];
+  U[3] = ql[0] * ql[3];
+  U[4] = (ql[4] / (gm - 1.0)) + (0.5 * ql[0] * (((ql[1] * ql[1]) + (ql[2] * ql[2])) + (ql[3] * ql[3])));
+  if (NV == 7) { U[5] = ql[0] * ql[5]; U[6] = ql[0] * ql[6]; }
+#pragma unroll
+  for (int l = 0; l < NV; ++l) U[l] = U[l] + du[l];
+  W[0] = U[0];
+  W[1] = U[1] / U[0];
+  W[2] = U[2] / U[0];
+  W[3] = U[3] / U[0];
+  W[4] = (gm - 1.0) * (U[4] - (0.5 * (((U[1] * U[1]) + (U[2] * U[2])) + (U[3] * U[3])) / U[0]));
+  if (NV == 7) {
+    W[5] = U[5] / U[0];
+    W[6] = U[6] / U[0];
+    W[5] = W[5] + 0.5 * (1. - copysign(1.0, W[5])) * (ql[5] - W[5]);
+    W[6] = W[6] + 0.5 * (1. - copysign(1.0, W[6])) * (ql[6] - W[6]);
+  }
+  const double nx = f.nx, ny = f.ny, nz = f.nz, Area = f.A, Volume = f.vol, mmu = f.mmu, tmu = f.tmu;
+  const double FaceNormalVelocity = (W[1] * nx) + (W[2] * ny) + (W[3] * nz);
+  const double uface = 0.5 * (W[1] + qr[1]), vface = 0.5 * (W[2] + qr[2]), wface = 0.5 * (W[3] + qr[3]);
+  Flux[0] = W[0] * FaceNormalVelocity;
+  Flux[1] = (W[1] * Flux[0]) + (W[4] * nx);
+  Flux[2] = (W[2] * Flux[0]) + (W[4] * ny);
+  Flux[3] = (W[3] * Flux[0]) + (W[4] * nz);
+  const double HalfRhoUsquare = 0.5 * W[0] * (W[1] * W[1] + W[2] * W[2] + W[3] * W[3]);
+  const double RhoHt = ((gm / (gm - 1.0)) * W[4]) + HalfRhoUsquare;
+  Flux[4] = RhoHt * FaceNormalVelocity;
+  if (NV == 7) { Flux[5] = (W[5] * Flux[0]); Flux[6] = (W[6] * Flux[0]); }
+  const double mu = mmu + tmu;
+  const double T1 = W[4] / (W[0] * R_gas), T2 = qr[4] / (qr[0] * R_gas);
+  const double dTdx = (T2 - T1) * nx * Area / Volume, dTdy = (T2 - T1) * ny * Area / Volume, dTdz = (T2 - T1) * nz * Area / Volume;
+  const double dudx = (qr[1] - W[1]) * nx * Area / Volume, dudy = (qr[1] - W[1]) * ny * Area / Volume, dudz = (qr[1] - W[1]) * nz * Area / Volume;
+  const double dvdx = (qr[2] - W[2]) * nx * Area / Volume, dvdy = (qr[2] - W[2]) * ny * Area / Volume, dvdz = (qr[2] - W[2]) * nz * Area / Volume;
+  const double dwdx = (qr[3] - W[3]) * nx * Area / Volume, dwdy = (qr[3] - W[3]) * ny * Area / Volume, dwdz = (qr[3] - W[3]) * nz * Area / Volume;
+  const double trace = dudx + dvdy + dwdz;
+  const double Tauxx = 2. * mu * (dudx - trace / 3.0), Tauyy = 2. * mu * (dvdy - trace / 3.0), Tauzz = 2. * mu * (dwdz - trace / 3.0);
+  const double Tauxy = mu * (dvdx + dudy), Tauxz = mu * (dwdx + dudz), Tauyz = mu * (dwdy + dvdz);
+  const double K_heat = (mmu / P.Pr + tmu / P.tPr) * gm * R_gas / (gm - 1.0);
+  const double Qx = K_heat * dTdx, Qy = K_heat * dTdy, Qz = K_heat * dTdz;
+  Flux[1] = Flux[1] - (Tauxx * nx + Tauxy * ny + Tauxz * nz);
+  Flux[2] = Flux[2] - (Tauxy * nx + Tauyy * ny + Tauyz * nz);
+  Flux[3] = Flux[3] - (Tauxz * nx + Tauyz * ny + Tauzz * nz);
+  Flux[4] = Flux[4] - (Tauxx * uface + Tauxy * vface + Tauxz * wface + Qx) * nx;
+  Flux[4] = Flux[4] - (Tauxy * uface + Tauyy * vface + Tauyz * wface + Qy) * ny;
+  Flux[4] = Flux[4] - (Tauxz * uface + Tauyz * vface + Tauzz * wface + Qz) * nz;
+  if (NV == 7) {
+    const double dtkdx = (qr[5] - W[5]) * nx * Area / Volume, dtkdy = (qr[5] - W[5]) * ny * Area / Volume, dtkdz = (qr[5] - W[5]) * nz * Area / Volume;
+    const double dtwdx = (qr[6] - W[6]) * nx * Area / Volume, dtwdy = (qr[6] - W[6]) * ny * Area / Volume, dtwdz = (qr[6] - W[6]) * nz * Area / Volume;
+    const double sigma_k = kSigmaK1 * f.F1 + kSigmaK2 * (1.0 - f.F1);
+    const double sigma_w = kSigmaW1 * f.F1 + kSigmaW2 * (1.0 - f.F1);
+    Flux[5] = Flux[5] + (mmu + sigma_k * tmu) * (dtkdx * nx + dtkdy * ny + dtkdz * nz);
+    Flux[6] = Flux[6] + (mmu + sigma_w * tmu) * (dtwdx * nx + dtwdy * ny + dtwdz * nz);
+  }
+#pragma unroll
+  for (int l = 0; l < NV; ++l) Flux[l] = Flux[l] * Area;
+}
+
+// SpectralRadius (lusgs.f90:633-683) of the low face of cell (i,j,k) in each direction, into lam[d] at the cell's index (= the face's)
+template <int NV>
+__global__ void __launch_bounds__(128) k_lusgs_lambda(const Params P, const double* __restrict__ q, const double* __restrict__ geom,
+                                                      const double* __restrict__ mu3 /* mu [, mu_t, F1] or nullptr */, double* __restrict__ lam) {
+  const Layout& L = P.L;
+  const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y * blockDim.y + threadIdx.y, k = 1 + blockIdx.z;
+  if (i > L.imx || j > L.jmx) return;
+  const long long fs = L.fs, c = L.idx(i, j, k);
+  const long long st[3] = {1, L.sj, L.sk};
+  const int pos[3] = {i, j, k}, mx[3] = {L.imx, L.jmx, L.kmx};
+  const double cx = geom[(long long)G_CX * fs + c], cy = geom[(long long)G_CY * fs + c], cz = geom[(long long)G_CZ * fs + c];
+  const double r0 = q[c], u0 = q[fs + c], v0 = q[2 * fs + c], w0 = q[3 * fs + c], p0 = q[4 * fs + c];
+  const double m0 = mu3 ? mu3[c] : 0.0, t0 = (mu3 && NV == 7) ? mu3[fs + c] : 0.0;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    // the face exists when the cell index is interior in the two other directions
+    bool ok = true;
+#pragma unroll
+    for (int e = 0; e < 3; ++e) if (e != d && pos[e] > mx[e] - 1) ok = false;
+    if (!ok) continue;
+    const long long n = c - st[d];
+    const double* gf = geom + (long long)(G_IA + 4 * d) * fs;
+    const double A = gf[c], nx = gf[fs + c], ny = gf[2 * fs + c], nz = gf[3 * fs + c];
+    const double r1 = q[n], u1 = q[fs + n], v1 = q[2 * fs + n], w1 = q[3 * fs + n], p1 = q[4 * fs + n];
+    double NormalSpeed = 0.5 * (((u1 + u0) * nx) + ((v1 + v0) * ny) + ((w1 + w0) * nz));
+    NormalSpeed = fabs(NormalSpeed);
+    const double SpeedOfSound = 0.5 * (sqrt(P.gm * p1 / r1) + sqrt(P.gm * p0 / r0));
+    const double rho = 0.5 * (r1 + r0);
+    const double dx = geom[(long long)G_CX * fs + n] - cx, dy = geom[(long long)G_CY * fs + n] - cy, dz = geom[(long long)G_CZ * fs + n] - cz;
+    const double distance = sqrt(((dx * dx) + (dy * dy)) + (dz * dz));
+    const double mm = mu3 ? 0.5 * (mu3[n] + m0) : 0.0, tm = (mu3 && NV == 7) ? 0.5 * (mu3[fs + n] + t0) : 0.0;
+    const double vis = P.gm * (mm / P.Pr + tm / P.tPr) / (rho * distance);
+    lam[d * fs + c] = (NormalSpeed + SpeedOfSound + vis) * A;
+  }
+}
+
+// one hyperplane i + j + k = h of a sweep.  FWD: delQstar from the low neighbours (lusgs.f90:296-312, 802-838); else delQ from the high
+// neighbours (:426-447, 920-959).  Grid: x over i, y over the k planes the hyperplane crosses (k = k0 + blockIdx.y).
+template <int NV, bool FWD>
+__global__ void __launch_bounds__(128) k_lusgs_sweep(const Params P, const double* __restrict__ q, const double* __restrict__ geom,
+                                                     const double* __restrict__ mu3, const double* __restrict__ lam, const double* __restrict__ dt,
+                                                     const double* __restrict__ residue, double* __restrict__ dqs, double* __restrict__ dq, int h, int k0) {
+  const Layout& L = P.L;
+  const int k = k0 + blockIdx.y;
+  const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = h - i - k;
+  if (i > L.imx - 1 || j < 1 || j > L.jmx - 1) return;
+  const long long fs = L.fs, c = L.idx(i, j, k);
+  const long long st[3] = {1, L.sj, L.sk};
+  double Q0[NV];
+#pragma unroll
+  for (int l = 0; l < NV; ++l) Q0[l] = q[l * fs + c];
+  const double vol0 = geom[(long long)G_VOL * fs + c];
+  const double m0 = mu3 ? mu3[c] : 0.0, t0 = (mu3 && NV == 7) ? mu3[fs + c] : 0.0, f0 = (mu3 && NV == 7) ? mu3[2 * fs + c] : 0.0;
+  // LambdaTimesArea(1..6): low I, J, K faces, then high I, J, K faces; SUM in that order
+  double Lm[6];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) { Lm[d] = lam[d * fs + c]; Lm[3 + d] = lam[d * fs + c + st[d]]; }
+  double s = 0.0;
+#pragma unroll
+  for (int n = 0; n < 6; ++n) s = s + Lm[n];
+  double D[NV];
+  {
+    const double D0 = (vol0 / dt[c]) + 0.5 * s;
+#pragma unroll
+    for (int l = 0; l < NV; ++l) D[l] = D0;
+    if (NV == 7) {   // lusgs.f90:830-832
+      const double beta = f0 * kBeta1 + (1.0 - f0) * kBeta2;
+      D[5] = (D[5] + (kBstar * Q0[6]) * vol0);
+      D[6] = (D[6] + 2.0 * beta * Q0[6] * vol0);
+    }
+  }
+  const double* __restrict__ src = FWD ? dqs : dq;
+  double acc[NV];   // ((I) + (J)) + (K)
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const long long n = FWD ? c - st[d] : c + st[d];
+    const long long fc = FWD ? c : c + st[d];          // index of the face record
+    const double sg = FWD ? -1.0 : 1.0;
+    const double* gf = geom + (long long)(G_IA + 4 * d) * fs;
+    LFace f;
+    f.A = gf[fc]; f.nx = sg * gf[fs + fc]; f.ny = sg * gf[2 * fs + fc]; f.nz = sg * gf[3 * fs + fc];
+    f.vol = 0.5 * (geom[(long long)G_VOL * fs + n] + vol0);
+    f.mmu = mu3 ? 0.5 * (mu3[n] + m0) : 0.0;
+    f.tmu = (mu3 && NV == 7) ? 0.5 * (mu3[fs + n] + t0) : 0.0;
+    f.F1 = (mu3 && NV == 7) ? 0.5 * (mu3[2 * fs + n] + f0) : 0.0;
+    double Qn[NV], DQ[NV], zero[NV], Fn[NV], Fo[NV];
+#pragma unroll
+    for (int l = 0; l < NV; ++l) { Qn[l] = q[l * fs + n]; DQ[l] = src[l * fs + n]; zero[l] = 0.0; }
+    lusgs_flux<NV>(P, Qn, Q0, DQ, f, Fn);
+    lusgs_flux<NV>(P, Qn, Q0, zero, f, Fo);
+    const double lm = Lm[FWD ? d : 3 + d];
+#pragma unroll
+    for (int l = 0; l < NV; ++l) {
+      const double term = ((Fn[l] - Fo[l]) - lm * DQ[l]);
+      acc[l] = (d == 0) ? term : acc[l] + term;
+    }
+  }
+#pragma unroll
+  for (int l = 0; l < NV; ++l) {
+    if (FWD) dqs[l * fs + c] = (-residue[l * fs + c] - 0.5 * acc[l]) / D[l];
+    else dq[l * fs + c] = dqs[l * fs + c] - 0.5 * acc[l] / D[l];
+  }
+}
+
+// conservative update with delQ, back to primitive variables, in place (lusgs.f90:452-486, 964-1021)
+template <int NV>
+__global__ void __launch_bounds__(128) k_lusgs_apply(const Params P, double* __restrict__ q, const double* __restrict__ dq) {
+  const Layout& L = P.L;
+  const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y * blockDim.y + threadIdx.y, k = 1 + blockIdx.z;
+  if (i > L.imx - 1 || j > L.jmx - 1) return;
+  const long long fs = L.fs, c = L.idx(i, j, k);
+  double qq[NV], cq[NV];
+#pragma unroll
+  for (int l = 0; l < NV; ++l) qq[l] = q[l * fs + c];
+  cq[0] = qq[0];
+  cq[1] = qq[0] * qq[1];
+  cq[2] = qq[0] * qq[2];
+  cq[3] = qq[0] * qq[3];
+  cq[4] = (qq[4] / (P.gm - 1.0)) + (0.5 * qq[0] * (((qq[1] * qq[1]) + (qq[2] * qq[2])) + (qq[3] * qq[3])));
+  if (NV == 7) { cq[5] = qq[0] * qq[5]; cq[6] = qq[0] * qq[6]; }
+#pragma unroll
+  for (int l = 0; l < NV; ++l) cq[l] = cq[l] + dq[l * fs + c];
+  q[c] = cq[0];
+  q[fs + c] = cq[1] / cq[0];
+  q[2 * fs + c] = cq[2] / cq[0];
+  q[3 * fs + c] = cq[3] / cq[0];
+  q[4 * fs + c] = (P.gm - 1.0) * (cq[4] - (0.5 * (((cq[1] * cq[1]) + (cq[2] * cq[2])) + (cq[3] * cq[3])) / cq[0]));
+  if (NV == 7) {
+    if (cq[5] > 0) q[5 * fs + c] = cq[5] / cq[0];
+    if (cq[6] > 0) q[6 * fs + c] = cq[6] / cq[0];
+  }
+}
+
+template <int NV>
+int lusgs_run(Ctx* ctx) {
+  const Layout& L = ctx->P.L;
+  const int ni = L.imx - 1, nj = L.jmx - 1, nk = L.kmx - 1;
+  const double* mu3 = ctx->P.viscous ? ctx->mu : nullptr;
+  cudaStream_t st = ctx->stream;
+  dim3 block(32, 4, 1);
+  k_lusgs_lambda<NV><<<dim3((L.imx + 31) / 32, (L.jmx + 3) / 4, L.kmx), block, 0, st>>>(ctx->P, ctx->qp, ctx->geom, mu3, ctx->lusgs_lam);
+  ctx->launches++;
+  const dim3 sb(128, 1, 1);
+  const int gx = (ni + 127) / 128;
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int hh = 3; hh <= ni + nj + nk; ++hh) {
+      const int h = pass == 0 ? hh : (ni + nj + nk + 3 - hh);
+      const int klo = std::max(1, h - ni - nj), khi = std::min(nk, h - 2);
+      if (khi < klo) continue;
+      const dim3 grid(gx, khi - klo + 1, 1);
+      if (pass == 0)
+        k_lusgs_sweep<NV, true><<<grid, sb, 0, st>>>(ctx->P, ctx->qp, ctx->geom, mu3, ctx->lusgs_lam, ctx->dt, ctx->residue, ctx->lusgs_dqs, ctx->lusgs_dq, h, klo);
+      else
+        k_lusgs_sweep<NV, false><<<grid, sb, 0, st>>>(ctx->P, ctx->qp, ctx->geom, mu3, ctx->lusgs_lam, ctx->dt, ctx->residue, ctx->lusgs_dqs, ctx->lusgs_dq, h, klo);
+      ctx->launches++;
+    }
+  }
+  k_lusgs_apply<NV><<<dim3((ni + 31) / 32, (nj + 3) / 4, nk), block, 0, st>>>(ctx->P, ctx->qp, ctx->lusgs_dq);
+  ctx->launches++;
+  F3D_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+int launch_lusgs(Ctx* ctx) {
+  if (!ctx->lusgs_dqs || !ctx->lusgs_dq || !ctx->lusgs_lam) return F3D_ERR_ARGUMENT;
+  if (ctx->P.L.nv == 5) return lusgs_run<5>(ctx);
+  if (ctx->P.L.nv == 7 && ctx->P.sst && !ctx->P.kkl) return lusgs_run<7>(ctx);
+  return F3D_ERR_UNSUPPORTED;
+}
+
+}  // namespace f3d

@@ -22,7 +22,7 @@ extern "C" {
 enum { ORC_VAN_LEER = 0, ORC_LDFSS0 = 1, ORC_AUSM = 2, ORC_AUSMP = 3, ORC_AUSMUP = 4, ORC_SLAU = 5 };
 enum { ORC_NONE = 0, ORC_MUSCL = 1, ORC_PPM = 2, ORC_WENO = 3, ORC_WENO_NM = 4 };
 enum { ORC_TURB_NONE = 0, ORC_TURB_SA = 1, ORC_TURB_SST = 3, ORC_TURB_SST2003 = 4, ORC_TURB_KKL = 5 };
-enum { ORC_T_NONE = 0, ORC_T_RK2 = 1, ORC_T_RK4 = 2, ORC_T_TVDRK2 = 3, ORC_T_TVDRK3 = 4 };
+enum { ORC_T_NONE = 0, ORC_T_RK2 = 1, ORC_T_RK4 = 2, ORC_T_TVDRK2 = 3, ORC_T_TVDRK3 = 4, ORC_T_IMPLICIT = 5 };
 
 /* fixed-value slots (reference: vartypes.f90:307-334) */
 enum {

@@ -128,8 +128,15 @@ int oracle_step(OracleWorld* w, int current_iter, double* res_abs) {
       residual_all(w); upd(1.0, 1., false, false);
       for (Block& B : w->blocks) blend(B, 0.5, 0.5);
       break;
+    case ORC_T_IMPLICIT: {   // update.f90:216-219
+      residual_all(w); dt();
+      int rc = 0;
+      for (Block& B : w->blocks) rc |= B.update_with_lusgs();
+      if (rc) return rc;
+      break;
+    }
     default:
-      return 64;  // implicit / plusgs: not on this path
+      return 64;  // plusgs: not on this path
   }
   // find_resnorm: per-block sums, "allgather", sum over blocks, sqrt / abs (resnorm.f90:171-225)
   const int nv = w->blocks[0].nv;

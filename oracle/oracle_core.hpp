@@ -94,6 +94,7 @@ struct Block {
   void total_residue();               // everything after apply_interface
   void compute_time_step();
   void update_with(double TF, double SF, bool TU, bool have_store);
+  int update_with_lusgs();            // lusgs.f90:134-183 (oracle_lusgs.cpp); 64 = a model whose LU-SGS routine is not restated
   void absolute_resnorm();
   // pieces
   void populate_ghost_primitive();

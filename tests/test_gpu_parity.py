@@ -310,6 +310,90 @@ def test_lctm2015_on_the_fused_form_is_refused(pkg, case_mod, fused_path):
     assert e.value.rc & 64
 
 
+# ---- implicit LU-SGS (time_step_accuracy = implicit; lusgs.f90:186-488 laminar, :686-1024 SST; update.f90:216-219): the method every
+# shipped case of the reference runs -------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("turbulence,mu_ref,transition", [("none", 0.0, "none"), ("none", None, "none"), ("sst", None, "none"), ("sst2003", None, "bc")])
+@pytest.mark.parametrize("scheme_name,interpolant,CFL", [("ausm", "muscl", 20.0), ("slau", "weno", 5.0), ("van_leer", "none", 100.0)])
+def test_duct_lusgs(pkg, case_mod, oracle, turbulence, mu_ref, transition, scheme_name, interpolant, CFL):
+    import importlib
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    blocks = syn.make_duct_blocks(None, n3=(37, 11, 9), scheme_name=scheme_name, interpolant=interpolant, turbulence=turbulence, mu_ref=mu_ref,
+                                  transition=transition, time_step_accuracy="implicit", CFL=CFL)
+    s = _solver(pkg, blocks)
+    _check_history(oracle, s, blocks, 8)          # norms, Res_abs(0) and the final fields incl. ghost layers; iterations 3.. replay a CUDA graph
+    s.close()
+
+
+@pytest.mark.parametrize("bc", [[-3, -4, -5, -6, -6, -6], [-8, -4, -7, -6, -9, -9], [-11, -4, -5, -5, -5, -5], [-1, -2, -6, -5, -5, -6]])
+@pytest.mark.parametrize("shape,turbulence", [((6, 5, 1), "none"), ((9, 7, 5), "sst"), ((2, 3, 2), "none")])
+def test_lusgs_boundary_conditions(pkg, case_mod, oracle, bc, shape, turbulence):
+    import importlib
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    if (-9 in bc[4:]) and shape[2] < 3:
+        pytest.skip("periodic slab copy needs 3 interior layers")
+    blocks = syn.make_duct_blocks(None, n3=shape, turbulence=turbulence, time_step_accuracy="implicit", interpolant="muscl", CFL=10.0)
+    blk = blocks[0]
+    blk.bc_id = list(bc)
+    fl = blk.flow
+    M2 = fl.x_speed_inf ** 2 / (fl.gm * fl.pressure_inf / fl.density_inf)
+    blk.fixed[8, :] = fl.pressure_inf * (1 + 0.5 * (fl.gm - 1.0) * M2) ** (fl.gm / (fl.gm - 1.0)) * (1.0 + 1e-3 * np.arange(6))
+    blk.build_geometry()
+    s = _solver(pkg, blocks)
+    _check_history(oracle, s, blocks, 5)
+    s.close()
+
+
+@pytest.mark.parametrize("turbulence", ["none", "sst"])
+def test_lusgs_multiblock_and_global_time_step(pkg, case_mod, oracle, turbulence):
+    import importlib
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    blocks = syn.make_duct_blocks(None, n3=(10, 8, 6), nb=(2, 2, 2), turbulence=turbulence, time_step_accuracy="implicit", CFL=15.0)
+    if turbulence == "none":
+        for blk in blocks:
+            blk.scheme.time_stepping_method = "g"          # delta_t = minval over the block (time.f90:286)
+    s = _solver(pkg, blocks)
+    _check_history(oracle, s, blocks, 6)
+    s.close()
+
+
+def test_lusgs_models_without_a_routine_are_refused(pkg, case_mod):
+    import importlib
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    solver = importlib.import_module("fest3d_b200.solver")
+    for kw in (dict(turbulence="sa"), dict(turbulence="kkl"), dict(turbulence="sst", transition="lctm2015")):
+        with pytest.raises(solver.Fest3dError) as e:
+            solver.Solver(syn.make_duct_blocks(None, n3=(6, 5, 4), time_step_accuracy="implicit", **kw))
+        assert e.value.rc & 64
+
+
+def test_smoothbump_in_the_reference_configuration(pkg, case_mod):
+    """The reference's own SmoothBump run, unmodified: system/control.md and fvscheme.md as shipped (ausm + muscl, implicit LU-SGS, local time
+    step, CFL 1000, 3000 iterations from the free stream).  tests/Report.txt holds its entropy measure, 7.883e-07
+    (tests/SmoothBump/pp/entropy.py); the device run must land on it."""
+    import importlib
+    solver = importlib.import_module("fest3d_b200.solver")
+    blocks = _load_fixture(case_mod, "smoothbump")
+    assert blocks[0].scheme.time_step_accuracy == "implicit" and blocks[0].control.CFL == 1000.0
+    s = solver.Solver(blocks)
+    first = s.iterate(1)[0]
+    s.iterate(2998, want_norms=False)
+    last = s.iterate(1)[0]
+    err2, vol = 0.0, 0.0
+    for gb, blk in zip(s.blocks, blocks):
+        q = gb.get_state()
+        nk, nj, ni = blk.kmx - 1, blk.jmx - 1, blk.imx - 1
+        rho, p = q[0, 3:3 + nk, 3:3 + nj, 3:3 + ni], q[4, 3:3 + nk, 3:3 + nj, 3:3 + ni]
+        V = blk.cells[3:3 + nk, 3:3 + nj, 3:3 + ni, 0]
+        s_inf = blk.flow.pressure_inf / blk.flow.density_inf ** 1.4
+        err2 += ((((p / rho ** 1.4) - s_inf) * V / s_inf) ** 2).sum()
+        vol += V.sum()
+    ds = float(np.sqrt(err2 / vol))
+    s.close()
+    print("SmoothBump, reference configuration: entropy measure %.6e (tests/Report.txt: 7.883e-07), continuity residual %.3e -> %.3e" % (ds, first[1], last[1]))
+    assert last[1] < 1e-5 * first[1], (first, last)          # continuity residual: the run converges
+    assert abs(ds / 7.883e-07 - 1.0) < 0.005, ds
+
+
 # ---- MUSCL / PPM pressure-based switching (muscl.f90:37-112, ppm.f90:108-170), every direction, quasi-2-D included -----------
 @pytest.mark.parametrize("interpolant", ["muscl", "ppm"])
 @pytest.mark.parametrize("shape,pb", [((20, 12, 10), (1, 1, 1)), ((33, 9, 1), (1, 0, 1)), ((7, 6, 5), (0, 1, 0))])
@@ -812,7 +896,7 @@ def test_unsupported_is_an_error_not_a_fallback(pkg, case_mod):
     import importlib
     syn = importlib.import_module("fest3d_b200.synthetic")
     solver = importlib.import_module("fest3d_b200.solver")
-    blocks = syn.make_duct_blocks(None, n3=(6, 5, 4), turbulence="none", mu_ref=0.0, time_step_accuracy="implicit")
+    blocks = syn.make_duct_blocks(None, n3=(6, 5, 4), turbulence="none", mu_ref=0.0, time_step_accuracy="plusgs")
     with pytest.raises(solver.Fest3dError):
         solver.Solver(blocks)
 

@@ -509,3 +509,57 @@ def test_lctm2015_source_against_numpy(oracle, case_mod, turbulence):
         assert np.abs(S_vol[v] - wv).max() <= 2e-12 * scale.max(), v
         assert np.abs(wv).max() > 1e-3 * np.abs(res[v]).max(), v          # the term is not negligible in this state
     assert np.count_nonzero(Fonset) > 0 and np.count_nonzero(Fon_lim) >= 0
+
+
+def test_lusgs_single_cell_and_zero_residual(oracle, case_mod):
+    """LU-SGS pins on the oracle that need no reference run (lusgs.f90:186-488, 633-683).  (1) A block of ONE cell has no neighbour
+    corrections: Del*Flux = 0, so delQ = -R / (V/dt + 0.5 sum(lambda A)) with the six spectral radii written out here in numpy.
+    (2) A uniform free stream in a periodic box has zero residual: the update must leave it untouched."""
+    import importlib
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    blocks = syn.make_duct_blocks(None, n3=(1, 1, 1), turbulence="none", mu_ref=None, time_step_accuracy="implicit", CFL=7.0)
+    blk = blocks[0]
+    fl = blk.flow
+    w = oracle.OracleWorld(blocks)
+    err, res = w.residual(1)
+    assert err == 0
+    w2 = oracle.OracleWorld(blocks)
+    err, _ = w2.step(1)
+    assert err == 0
+    q0, q1 = w.get_state(0), w2.get_state(0)      # q0: ghost cells filled, the state the sweeps see; q1: after the update
+    dt = w2.aux(0, 0, (1, 1, 1))[0, 0, 0]
+    mu = w2.aux(0, 1, (blk.kmx + 5, blk.jmx + 5, blk.imx + 5))
+    c = (3, 3, 3)
+    gm, Pr = fl.gm, fl.Pr
+    lamA = 0.0
+    faces = [(blk.Ifaces, (3, 3, 3), (3, 3, 2)), (blk.Jfaces, (3, 3, 3), (3, 2, 3)), (blk.Kfaces, (3, 3, 3), (2, 3, 3)),
+             (blk.Ifaces, (3, 3, 4), (3, 3, 4)), (blk.Jfaces, (3, 4, 3), (3, 4, 3)), (blk.Kfaces, (4, 3, 3), (4, 3, 3))]
+    for arr, fidx, nidx in faces:
+        A, n = arr[fidx][0], arr[fidx][1:4]
+        ql, qr = q0[(slice(None),) + nidx], q0[(slice(None),) + c]
+        un = abs(0.5 * np.dot(ql[1:4] + qr[1:4], n))
+        a = 0.5 * (np.sqrt(gm * ql[4] / ql[0]) + np.sqrt(gm * qr[4] / qr[0]))
+        dist = np.linalg.norm(blk.cells[nidx][1:4] - blk.cells[c][1:4])
+        vis = gm * (0.5 * (mu[nidx] + mu[c]) / Pr) / (0.5 * (ql[0] + qr[0]) * dist)
+        lamA += (un + a + vis) * A
+    D = blk.cells[c][0] / dt + 0.5 * lamA
+    rho, u, p = q0[0][c], q0[1:4, 3, 3, 3], q0[4][c]
+    U0 = np.array([rho, *(rho * u), p / (gm - 1) + 0.5 * rho * np.dot(u, u)])
+    U1 = U0 - res[0][:, 0, 0, 0] / D
+    want = np.array([U1[0], *(U1[1:4] / U1[0]), (gm - 1) * (U1[4] - 0.5 * np.dot(U1[1:4], U1[1:4]) / U1[0])])
+    got = q1[:, 3, 3, 3]
+    assert np.allclose(got, want, rtol=1e-13, atol=1e-13 * np.abs(want).max()), (got, want)
+    assert not np.allclose(got, q0[:, 3, 3, 3], rtol=1e-6)          # ... and the update did something
+    # (2) uniform state, periodic in all three directions
+    blocks = syn.make_duct_blocks(None, n3=(5, 4, 4), turbulence="none", mu_ref=None, time_step_accuracy="implicit", CFL=50.0)
+    blk = blocks[0]
+    blk.bc_id = [-9] * 6
+    blk.init_state()
+    blk.build_geometry()
+    w = oracle.OracleWorld(blocks)
+    err, norms = w.step(1)
+    assert err == 0
+    q = w.get_state(0)
+    scale = np.abs(blk.qp).reshape(5, -1).max(axis=1)[:, None, None, None]
+    # the metric of the wavy grid closes to round-off only: the residual, and with it the update, is ~1e-16 of the flux scale
+    assert np.abs(q - blk.qp)[:, 3:-3, 3:-3, 3:-3].max() <= 1e-10 * 1.0 and np.abs((q - blk.qp) / np.maximum(scale, 1.0))[:, 3:-3, 3:-3, 3:-3].max() < 1e-9
