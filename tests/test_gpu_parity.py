@@ -723,6 +723,30 @@ def test_flat_plate_drag_coefficient_meets_the_reference_gate(pkg, case_mod, cas
     assert abs(cd / surface_drag.CD_REPORT[case] - 1.0) < tol, cd
 
 
+@pytest.mark.parametrize("case,tol", [("lfp", 0.002), ("tfp", 0.002)])
+def test_flat_plate_in_the_reference_configuration(pkg, case_mod, case, tol):
+    """The two flat-plate cases exactly as the reference ships and runs them (system/control.md, fvscheme.md untouched): ausm + muscl, implicit
+    LU-SGS with local time steps, CFL 2000 for 5000 iterations from the free stream (Lfp), CFL 3000 for 10000 iterations from the shipped
+    restart (Tfp).  tests/Report.txt holds the drag coefficients of the reference's own runs: 1.329e-3 and 2.872e-3; the device run is compared
+    with THOSE (not only with the looser gates of the reference's test script, 1 % / 2 % of 1.33e-3 / 2.90e-3)."""
+    import importlib
+    import fixtures
+    import surface_drag
+    solver = importlib.import_module("fest3d_b200.solver")
+    blocks = fixtures.load(case_mod, os.path.join(GOLDEN, case))
+    assert blocks[0].scheme.time_step_accuracy == "implicit" and blocks[0].scheme.scheme_name == "ausm" and blocks[0].scheme.interpolant == "muscl"
+    n_iter = {"lfp": 5000, "tfp": 10000}[case]
+    assert blocks[0].control.CFL == {"lfp": 2000.0, "tfp": 3000.0}[case]
+    s = solver.Solver(blocks)
+    first = s.iterate(1)[0]
+    s.iterate(n_iter - 2, want_norms=False)
+    last = s.iterate(1)[0]
+    cd = surface_drag.device_wall_drag(s, blocks, case)
+    s.close()
+    print("%s, reference configuration: C_d = %.6e (tests/Report.txt: %.3e), continuity residual %.3e -> %.3e" % (case, cd, surface_drag.CD_REPORT[case], first[1], last[1]))
+    assert abs(cd / surface_drag.CD_REPORT[case] - 1.0) < tol, cd
+
+
 # ---- SURVEY 8(f) rank 1: wall distance on the device (wall_dist.f90:84-131) ---------------------------------------------------
 @pytest.mark.parametrize("shape", [(7, 6, 5), (40, 33, 9)])
 def test_wall_distance_on_device(pkg, case_mod, oracle, shape):
