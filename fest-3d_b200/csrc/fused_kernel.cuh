@@ -352,6 +352,32 @@ __device__ __forceinline__ double tanh_pos(double x) {
   return (1.0 - e) * rcp64(1.0 + e);
 }
 
+// SST eddy viscosity and F1 of a cell from its gradients (viscosity.f90:215-263, 343-388)
+__device__ __forceinline__ void sst_eddy4(const Params& P, double density, double tk, double tw, double mu, double dd, const double (&g)[6][3], double& mut,
+                                          double& F1) {
+  const double var1 = sqrt(tk) * rcp64(kBstar * tw * dd);
+  const double var2 = 500 * (mu * rcp64(density)) * rcp64((dd * dd) * tw);
+  const double arg2 = dmax(2 * var1, var2);
+  const double Fb = tanh_pos(arg2 * arg2);
+  double rate;
+  if (P.turbulence == F3D_TURB_SST) {
+    const double wx = g[2][1] - g[1][2], wy = g[0][2] - g[2][0], wz = g[1][0] - g[0][1];
+    rate = sqrt(wx * wx + wy * wy + wz * wz);
+  } else {
+    const double sxx = g[0][0], syy = g[1][1], szz = g[2][2];
+    const double syz = g[2][1] + g[1][2], szx = g[0][2] + g[2][0], sxy = g[1][0] + g[0][1];
+    rate = sqrt((2.0 * (sxx * sxx)) + (2.0 * (syy * syy)) + (2.0 * (szz * szz)) + syz * syz + szx * szx + sxy * sxy);
+  }
+  const double NUM = density * kA1 * tk;
+  const double DENOM = dmax(dmax((kA1 * tw), rate * Fb), P.mut_floor);
+  mut = NUM * rcp64(DENOM);
+  const double CD = dmax(2 * density * kSigmaW2 * (g[4][0] * g[5][0] + g[4][1] * g[5][1] + g[4][2] * g[5][2]) * rcp64(tw), P.mut_floor);
+  const double right = 4 * (density * kSigmaW2 * tk) * rcp64(CD * (dd * dd));
+  const double left = dmax(var1, var2);
+  const double arg1 = dmin(left, right);
+  F1 = tanh_pos((arg1 * arg1) * (arg1 * arg1));
+}
+
 template <int NV>
 __device__ __forceinline__ void gradient_record(const Params& P, const KArgs& a, const double* __restrict__ qm, const double* __restrict__ q0,
                                                 const double* __restrict__ qp, int sq, double vol_c, long long c, const GradW& w,
@@ -396,31 +422,7 @@ __device__ __forceinline__ void gradient_record(const Params& P, const KArgs& a,
     const double fv1 = (pow3(xi)) / ((pow3(xi)) + (pow3(kCv1)));
     mut = density * tv * fv1;
   }
-  if (NG == 6) {
-    const double tk = q0[5 * PSQ + sq], tw = q0[6 * PSQ + sq];
-    const double dd = a.geom[(long long)G_DIST * fs + c];
-    const double var1 = sqrt(tk) * rcp64(kBstar * tw * dd);
-    const double var2 = 500 * (mu * rcp64(density)) * rcp64((dd * dd) * tw);
-    const double arg2 = dmax(2 * var1, var2);
-    const double Fb = tanh_pos(arg2 * arg2);
-    double rate;
-    if (P.turbulence == F3D_TURB_SST) {
-      const double wx = g[2][1] - g[1][2], wy = g[0][2] - g[2][0], wz = g[1][0] - g[0][1];
-      rate = sqrt(wx * wx + wy * wy + wz * wz);
-    } else {
-      const double sxx = g[0][0], syy = g[1][1], szz = g[2][2];
-      const double syz = g[2][1] + g[1][2], szx = g[0][2] + g[2][0], sxy = g[1][0] + g[0][1];
-      rate = sqrt((2.0 * (sxx * sxx)) + (2.0 * (syy * syy)) + (2.0 * (szz * szz)) + syz * syz + szx * szx + sxy * sxy);
-    }
-    const double NUM = density * kA1 * tk;
-    const double DENOM = dmax(dmax((kA1 * tw), rate * Fb), P.mut_floor);
-    mut = NUM * rcp64(DENOM);
-    const double CD = dmax(2 * density * kSigmaW2 * (g[4][0] * g[5][0] + g[4][1] * g[5][1] + g[4][2] * g[5][2]) * rcp64(tw), P.mut_floor);
-    const double right = 4 * (density * kSigmaW2 * tk) * rcp64(CD * (dd * dd));
-    const double left = dmax(var1, var2);
-    const double arg1 = dmin(left, right);
-    F1 = tanh_pos((arg1 * arg1) * (arg1 * arg1));
-  }
+  if constexpr (NG == 6) sst_eddy4(P, density, q0[5 * PSQ + sq], q0[6 * PSQ + sq], mu, a.geom[(long long)G_DIST * fs + c], g, mut, F1);
   double out[RP];
 #pragma unroll
   for (int cc = 0; cc < NG; ++cc) { out[3 * cc] = g[cc][0]; out[3 * cc + 1] = g[cc][1]; out[3 * cc + 2] = g[cc][2]; }
@@ -437,7 +439,7 @@ __device__ __forceinline__ void gradient_record(const Params& P, const KArgs& a,
 // density of the interior / ghost cell in their staged q planes; fr = the (mis-indexed) face record A, nx, ny, nz; face = 1..6.
 template <int NV>
 __device__ __forceinline__ void ghost_record(const Params& P, const double* __restrict__ recI, double* __restrict__ rec, const double* __restrict__ qI,
-                                             const double* __restrict__ qG, const double* __restrict__ fr, double vol_i, int face) {
+                                             const double* __restrict__ qG, const double* __restrict__ fr, double vol_i, int face, double dist_g) {
   using R = RecF<NV, true>;
   constexpr int NG = R::NG, F_MU = 3 * NG;
   const bool lo = (face % 2) == 1;
@@ -466,6 +468,18 @@ __device__ __forceinline__ void ghost_record(const Params& P, const double* __re
   }
   if (R::NMU >= 3) {
     if (id == -5 || copyish) rec[F_MU + 2] = recI[F_MU + 2];
+  }
+  if constexpr (NG == 6) {
+    // Where the reference does not copy (periodic interfaces -10, total pressure -11) the ghost mu_t / F1 follow from the ghost cell's own
+    // state and its rule-made gradients: apply_gradient_bc runs before calculate_viscosity (update.f90:534-541)
+    if (id != -5 && !copyish) {
+      double g[6][3];
+#pragma unroll
+      for (int cc = 0; cc < 6; ++cc) { g[cc][0] = rec[3 * cc]; g[cc][1] = rec[3 * cc + 1]; g[cc][2] = rec[3 * cc + 2]; }
+      double mut, F1;
+      sst_eddy4(P, qG[0], qG[5 * PSQ], qG[6 * PSQ], rec[F_MU], dist_g, g, mut, F1);
+      rec[F_MU + 1] = mut; rec[F_MU + 2] = F1;
+    }
   }
 }
 
@@ -792,7 +806,9 @@ __global__ void __launch_bounds__(NT, 1) k_fused(const Params P, const KArgs a, 
       const double* qG = smem + q_off(pg) + g_sq;
       const double* qI = smem + q_off(pi) + g_sq + dsq;
       const double vol_i = smem[g_off(pi) + g_sg + dsg];
-      ghost_record<NV>(P, smem + r_off(pi) + (gt + dt_) * RP, smem + r_off(pg) + gt * RP, qI, qG, fr, vol_i, face);
+      const int id_ = P.bc_id[face - 1];
+      const double dist_g = (NV == 7 && (id_ == -10 || id_ == -11)) ? a.geom[(long long)G_DIST * Ly.fs + Ly.idx(gi, gj, pg)] : 0.0;
+      ghost_record<NV>(P, smem + r_off(pi) + (gt + dt_) * RP, smem + r_off(pg) + gt * RP, qI, qG, fr, vol_i, face, dist_g);
     }
   };
 

@@ -20,44 +20,29 @@ constexpr int G_ALIGN = 0;
 #else
 constexpr int G_ALIGN = 15;
 #endif
+// Green-Gauss gradient of (u, v, w, T [, k, omega | nu-tilde] [, gamma]) at cell c (gradients.f90:405-482)
 template <int NG>
-__global__ void __launch_bounds__(128, 5) k_gradients(const Params P, const double* __restrict__ q, const double* __restrict__ temp,
-                                                   const double* __restrict__ geom, double* __restrict__ grad, double* __restrict__ mu3, int* err) {
+__device__ __forceinline__ void green_gauss(const Params& P, const double* __restrict__ q, const double* __restrict__ temp, const double* __restrict__ geom,
+                                            long long c, double (&g)[NG][3], double& nan_probe) {
   const Layout& L = P.L;
-  // a warp covers cells i = 32 b - 15 .. 32 b + 16: cell 1 of a row starts a 128-byte line (ctx.hpp), so every row segment a warp
-  // loads or stores is two whole lines (starting the warps at cell 0 made it three, two of them partial)
-  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x) - G_ALIGN;
-  const int j = blockIdx.y * blockDim.y + threadIdx.y;
-  const int k = blockIdx.z;
-  if (i < 0 || i > L.imx || j > L.jmx) return;
-  const long long fs = L.fs, c = L.idx(i, j, k), sj = L.sj, sk = L.sk;
+  const long long fs = L.fs, sj = L.sj, sk = L.sk;
   const double* gI = geom + (long long)G_IA * fs;
   const double* gJ = geom + (long long)G_JA * fs;
   const double* gK = geom + (long long)G_KA * fs;
-  // face area vectors n*A of the six faces, per direction component
-  double wlo[3][3], whi[3][3];   // [face dir][component]
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    wlo[0][d] = gI[(1 + d) * fs + c]; whi[0][d] = gI[(1 + d) * fs + c + 1];
-    wlo[1][d] = gJ[(1 + d) * fs + c]; whi[1][d] = gJ[(1 + d) * fs + c + sj];
-    wlo[2][d] = gK[(1 + d) * fs + c]; whi[2][d] = gK[(1 + d) * fs + c + sk];
-  }
   const double AIl = gI[c], AIh = gI[c + 1], AJl = gJ[c], AJh = gJ[c + sj], AKl = gK[c], AKh = gK[c + sk];
   const double ivol2 = rcp64(2 * geom[(long long)G_VOL * fs + c]);
   const bool zgrad = L.kmx > 2;   // gradqp_z = 0 when kmx == 2 (gradients.f90:328-336)
-  double g[NG][3];
   // face weights n*A once per face and direction (18 products), then 6 FMAs per gradient component: branch-free so the
   // NG*3 independent chains interleave
   double wl[3][3], wh[3][3];
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
-    wl[0][d] = wlo[0][d] * AIl; wl[1][d] = wlo[1][d] * AJl; wl[2][d] = wlo[2][d] * AKl;
-    wh[0][d] = whi[0][d] * AIh; wh[1][d] = whi[1][d] * AJh; wh[2][d] = whi[2][d] * AKh;
+    wl[0][d] = gI[(1 + d) * fs + c] * AIl; wl[1][d] = gJ[(1 + d) * fs + c] * AJl; wl[2][d] = gK[(1 + d) * fs + c] * AKl;
+    wh[0][d] = gI[(1 + d) * fs + c + 1] * AIh; wh[1][d] = gJ[(1 + d) * fs + c + sj] * AJh; wh[2][d] = gK[(1 + d) * fs + c + sk] * AKh;
   }
-  double nan_probe = 0.0;
 #pragma unroll
   for (int cc = 0; cc < NG; ++cc) {
-    const double* __restrict__ var = (cc < 3) ? (q + (long long)(cc + 1) * fs) : (cc == 3 ? temp : (q + (long long)(cc + 1) * fs));
+    const double* __restrict__ var = (cc == 3) ? temp : (q + (long long)(cc + 1) * fs);
     const double v0 = var[c];
     const double sIl = var[c - 1] + v0, sJl = var[c - sj] + v0, sKl = var[c - sk] + v0;
     const double sIh = var[c + 1] + v0, sJh = var[c + sj] + v0, sKh = var[c + sk] + v0;
@@ -67,33 +52,42 @@ __global__ void __launch_bounds__(128, 5) k_gradients(const Params P, const doub
       if (d == 2) r = zgrad ? r : 0.0;
       nan_probe += r;
       g[cc][d] = r;
-      grad[(3 * cc + d) * fs + c] = r;
     }
   }
-  const bool bad = isnan(nan_probe);
-  if (bad) { atomicOr(err, F3D_ERR_NAN_GRADIENT); }
-  // molecular viscosity on 0..imx (mu_ref when constant, viscosity.f90:527)
+}
+
+// molecular viscosity (mu_ref when constant, viscosity.f90:527; Sutherland :109-138)
+__device__ __forceinline__ double molecular_viscosity(const Params& P, const double* __restrict__ q, long long c, int* err) {
   double mu = P.mu_ref;
   if (P.mu_variation == 1) {
-    const double T = q[4 * fs + c] * rcp64(q[c] * P.R_gas);
+    const double T = q[4 * P.L.fs + c] * rcp64(q[c] * P.R_gas);
     const double tr = T / P.T_ref;   // (T/T_ref)**1.5 = tr*sqrt(tr): <= 1 ulp from pow, 8x cheaper
     mu = P.mu_ref * (tr * sqrt(tr)) * ((P.T_ref + P.Sutherland_temp) * rcp64(T + P.Sutherland_temp));
     if (isnan(mu)) atomicOr(err, F3D_ERR_NAN_VISCOSITY);
   }
-  mu3[c] = mu;
-  if (NG == 5) {   // Spalart-Allmaras: mu_t = rho*tv*fv1 (viscosity.f90:149-163)
+  return mu;
+}
+
+// eddy viscosity and blending function of cell c from its gradients g and molecular viscosity mu
+// (viscosity.f90:149-163 sa, :215-263 sst2003, :343-388 sst, :265-279 / :390-404 lctm2015, :469-484 kkl)
+template <int NG>
+__device__ __forceinline__ void eddy_viscosity(const Params& P, const double* __restrict__ q, const double* __restrict__ geom, long long c,
+                                               const double (&g)[NG][3], double mu, double& mut, double& F1) {
+  const Layout& L = P.L;
+  const long long fs = L.fs;
+  constexpr bool TWO_EQ = (NG >= 6);   // sst, sst2003, kkl (6); sst / sst2003 with the intermittency of lctm2015 (7)
+  mut = 0.0; F1 = 0.0;
+  if (NG == 5) {   // Spalart-Allmaras: mu_t = rho*tv*fv1
     const double tv = q[5 * fs + c], density = q[c];
     const double xi = tv * density / mu;
     const double fv1 = (pow3(xi)) / ((pow3(xi)) + (pow3(kCv1)));
-    mu3[fs + c] = density * tv * fv1;
+    mut = density * tv * fv1;
   }
-  constexpr bool TWO_EQ = (NG >= 6);   // sst, sst2003, kkl (6); sst / sst2003 with the intermittency of lctm2015 (7)
-  if (TWO_EQ && P.kkl) {   // k-kL: mu_t = cmu^(1/4) rho kL / max(sqrt(k), 1e-20), 0 below 1e-14 (viscosity.f90:469-484); no F1
+  if (TWO_EQ && P.kkl) {   // k-kL: mu_t = cmu^(1/4) rho kL / max(sqrt(k), 1e-20), 0 below 1e-14; no F1
     const double density = q[c], tk = q[5 * fs + c], tkl = q[6 * fs + c];
     double m = kKklCmu25 * density * tkl / (fmax(sqrt(tk), 1.e-20));
     if (tkl < 1.e-14 || tk < 1.e-14) m = 0.0;
-    mu3[fs + c] = m;
-    mu3[2 * fs + c] = 0.0;
+    mut = m;
   } else if (TWO_EQ) {
     const double density = q[c], tk = q[5 * fs + c], tw = q[6 * fs + c];
     const double d = geom[(long long)G_DIST * fs + c];
@@ -112,12 +106,12 @@ __global__ void __launch_bounds__(128, 5) k_gradients(const Params P, const doub
     }
     const double NUM = density * kA1 * tk;
     const double DENOM = dmax(dmax((kA1 * tw), rate * Fb), P.mut_floor);
-    mu3[fs + c] = NUM * rcp64(DENOM);
+    mut = NUM * rcp64(DENOM);
     const double CD = dmax(2 * density * kSigmaW2 * (g[4][0] * g[5][0] + g[4][1] * g[5][1] + g[4][2] * g[5][2]) * rcp64(tw), P.mut_floor);
     const double right = 4 * (density * kSigmaW2 * tk) * rcp64(CD * (d * d));
     const double left = dmax(var1, var2);
     const double arg1 = dmin(left, right);
-    double F1 = tanh((arg1 * arg1) * (arg1 * arg1));
+    F1 = tanh((arg1 * arg1) * (arg1 * arg1));
     if (NG == 7) {
       // viscosity.f90:265-279 / :390-404 "modified blending function (Menter 2015)".  KEPT DEFECT: its loop reuses the scalars `density`
       // and `tk` the loop above left behind -- those of its last cell (imx, jmx, kmx), a corner ghost cell -- for every cell.
@@ -126,7 +120,109 @@ __global__ void __launch_bounds__(128, 5) k_gradients(const Params P, const doub
       const double x2 = x * x, x4 = x2 * x2;
       F1 = fmax(F1, exp(-(x4 * x4)));
     }
-    mu3[2 * fs + c] = F1;
+  }
+}
+
+// One thread per cell of 0..imx x 0..jmx x 0..kmx: gradient, molecular and eddy viscosity, F1 of the cell itself
+template <int NG>
+__global__ void __launch_bounds__(128, 5) k_gradients(const Params P, const double* __restrict__ q, const double* __restrict__ temp,
+                                                   const double* __restrict__ geom, double* __restrict__ grad, double* __restrict__ mu3, int* err) {
+  const Layout& L = P.L;
+  // a warp covers cells i = 32 b - 15 .. 32 b + 16: cell 1 of a row starts a 128-byte line (ctx.hpp), so every row segment a warp
+  // loads or stores is two whole lines (starting the warps at cell 0 made it three, two of them partial)
+  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x) - G_ALIGN;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int k = blockIdx.z;
+  if (i < 0 || i > L.imx || j > L.jmx) return;
+  const long long fs = L.fs, c = L.idx(i, j, k);
+  double nan_probe = 0.0;
+  double g[NG][3];
+  green_gauss<NG>(P, q, temp, geom, c, g, nan_probe);
+#pragma unroll
+  for (int cc = 0; cc < NG; ++cc) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) grad[(3 * cc + d) * fs + c] = g[cc][d];
+  }
+  if (isnan(nan_probe)) atomicOr(err, F3D_ERR_NAN_GRADIENT);
+  const double mu = molecular_viscosity(P, q, c, err);
+  mu3[c] = mu;
+  if (NG >= 5) {
+    double mut, F1;
+    eddy_viscosity<NG>(P, q, geom, c, g, mu, mut, F1);
+    mu3[fs + c] = mut;
+    if (NG >= 6) mu3[2 * fs + c] = F1;
+  }
+}
+
+// Ghost-gradient rule + ghost mu_t / F1 on the physical faces (gradients.f90:486-676, viscosity.f90:165-212, 408-465, 488-531).  The
+// reference applies the rule BEFORE it computes the viscosities and then copies mu_t / F1 from the interior cell on most boundary types;
+// where it does not copy (periodic interfaces -10, total pressure -11) the ghost values follow from the ghost cell's own state and its
+// rule-made gradients, recomputed here.  A separate kernel on purpose: folded into k_gradients (the ghost thread evaluating the interior
+// cell itself) the pair measured 1.88-2.05 ms against 1.43 + 0.23 ms at 256^3 (divergent boundary warps, 26 more registers:
+// profiles/r02_summary.md).
+template <int NG>
+__global__ void k_gradient_bc(const Params P, const double* __restrict__ q, const double* __restrict__ temp, const double* __restrict__ geom,
+                              double* __restrict__ grad, double* __restrict__ mu3, const double* __restrict__ rec_all, const long long* rec_off,
+                              int face_mask) {
+  // one launch for all physical faces (blockIdx.z = face-1): each face reads interior gradients and writes its own ghost cells
+  const int face = blockIdx.z + 1;
+  if (!(face_mask >> (face - 1) & 1)) return;
+  const double* __restrict__ rec = rec_all + rec_off[face - 1];
+  const Layout& L = P.L;
+  const int ax = (face - 1) / 2;
+  const bool lo = (face % 2) == 1;
+  const int a_ax = (ax == 0) ? 1 : 0, b_ax = (ax == 2) ? 1 : 2;
+  const int mx[3] = {L.imx, L.jmx, L.kmx};
+  const long long st[3] = {1, L.sj, L.sk};
+  const int a = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y * blockDim.y + threadIdx.y;
+  const int na = mx[a_ax] - 1, nb = mx[b_ax] - 1;
+  if (a >= na || b >= nb) return;
+  int idx[3]; idx[a_ax] = a + 1; idx[b_ax] = b + 1; idx[ax] = lo ? 1 : mx[ax] - 1;
+  const long long ci = L.idx(idx[0], idx[1], idx[2]);       // interior cell
+  const long long cg = lo ? ci - st[ax] : ci + st[ax];       // ghost cell
+  const long long fs = L.fs;
+  const double* r = rec + 4 * ((long long)b * na + a);
+  const double A = r[0], nx = r[1], ny = r[2], nz = r[3];
+  const double vol = geom[(long long)G_VOL * fs + ci];
+  const double c_x = A * nx / vol, c_y = A * ny / vol, c_z = A * nz / vol;
+  const double sig = lo ? 1.0 : -1.0;
+  const int id = P.bc_id[face - 1];
+  const double ft = P.fixed[F3D_FIX_WALL_TEMP][face - 1];
+  // all loads first, then all stores: grad is read and written here, so stores between the loads would serialise the NG
+  // components into NG dependent round trips to HBM (on an i face every value is its own 32-byte sector)
+  double qI[NG], qG[NG], gI[NG][3], gG[NG][3];
+#pragma unroll
+  for (int cc = 0; cc < NG; ++cc) {
+    // slot cc holds variable cc+2 of qp(2:n_var): u,v,w,p,[k,omega]; slot 4 (cc == 3) is then overwritten with T
+    qI[cc] = (cc == 3) ? temp[ci] : q[(long long)(cc + 1) * fs + ci];
+    qG[cc] = (cc == 3) ? temp[cg] : q[(long long)(cc + 1) * fs + cg];
+    gI[cc][0] = grad[(3 * cc + 0) * fs + ci]; gI[cc][1] = grad[(3 * cc + 1) * fs + ci]; gI[cc][2] = grad[(3 * cc + 2) * fs + ci];
+  }
+#pragma unroll
+  for (int cc = 0; cc < NG; ++cc) {
+    const double gIx = gI[cc][0], gIy = gI[cc][1], gIz = gI[cc][2];
+    double gx = sig * (qI[cc] - qG[cc]) * c_x, gy = sig * (qI[cc] - qG[cc]) * c_y, gz = sig * (qI[cc] - qG[cc]) * c_z;
+    if (cc == 3 && id == -5 && (ft < 1. && ft >= 0.)) { gx = -gIx; gy = -gIy; gz = -gIz; }   // adiabatic wall
+    const double dot = (gIx * nx) + (gIy * ny) + (gIz * nz);
+    gG[cc][0] = gx + (gIx - dot * nx);
+    gG[cc][1] = gy + (gIy - dot * ny);
+    gG[cc][2] = gz + (gIz - dot * nz);
+    grad[(3 * cc + 0) * fs + cg] = gG[cc][0];
+    grad[(3 * cc + 1) * fs + cg] = gG[cc][1];
+    grad[(3 * cc + 2) * fs + cg] = gG[cc][2];
+  }
+  if (NG >= 5) {
+    // boundary types that copy the interior mu_t (and F1): sa and sst -4..-1, -6..-9; kkl the same without the pole -7; the wall takes -mu_t
+    const bool listed = id == -1 || id == -2 || id == -3 || id == -4 || id == -6 || id == -8 || id == -9 || (id == -7 && !(NG >= 6 && P.kkl));
+    if (id == -5 || listed) {
+      mu3[fs + cg] = (id == -5) ? -mu3[fs + ci] : mu3[fs + ci];
+      if (NG >= 6 && !P.kkl) mu3[2 * fs + cg] = mu3[2 * fs + ci];
+    } else {
+      double mut, F1;
+      eddy_viscosity<NG>(P, q, geom, cg, gG, mu3[cg], mut, F1);
+      mu3[fs + cg] = mut;
+      if (NG >= 6) mu3[2 * fs + cg] = F1;
+    }
   }
 }
 
@@ -165,70 +261,6 @@ int launch_dvdy(Ctx* ctx) {
   return 0;
 }
 
-// ghost-gradient rule + ghost mu_t/F1 on one physical face (gradients.f90:638-674, viscosity.f90:408-465)
-template <int NG>
-__global__ void k_gradient_bc(const Params P, const double* __restrict__ q, const double* __restrict__ temp, const double* __restrict__ geom,
-                              double* __restrict__ grad, double* __restrict__ mu3, const double* __restrict__ rec_all, const long long* rec_off,
-                              int face_mask) {
-  // one launch for all physical faces (blockIdx.z = face-1): each face reads interior gradients and writes its own ghost cells
-  const int face = blockIdx.z + 1;
-  if (!(face_mask >> (face - 1) & 1)) return;
-  const double* __restrict__ rec = rec_all + rec_off[face - 1];
-  const Layout& L = P.L;
-  const int ax = (face - 1) / 2;
-  const bool lo = (face % 2) == 1;
-  const int a_ax = (ax == 0) ? 1 : 0, b_ax = (ax == 2) ? 1 : 2;
-  const int mx[3] = {L.imx, L.jmx, L.kmx};
-  const long long st[3] = {1, L.sj, L.sk};
-  const int a = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y * blockDim.y + threadIdx.y;
-  const int na = mx[a_ax] - 1, nb = mx[b_ax] - 1;
-  if (a >= na || b >= nb) return;
-  int idx[3]; idx[a_ax] = a + 1; idx[b_ax] = b + 1; idx[ax] = lo ? 1 : mx[ax] - 1;
-  const long long ci = L.idx(idx[0], idx[1], idx[2]);       // interior cell
-  const long long cg = lo ? ci - st[ax] : ci + st[ax];       // ghost cell
-  const long long fs = L.fs;
-  const double* r = rec + 4 * ((long long)b * na + a);
-  const double A = r[0], nx = r[1], ny = r[2], nz = r[3];
-  const double vol = geom[(long long)G_VOL * fs + ci];
-  const double c_x = A * nx / vol, c_y = A * ny / vol, c_z = A * nz / vol;
-  const double sig = lo ? 1.0 : -1.0;
-  const int id = P.bc_id[face - 1];
-  const double ft = P.fixed[F3D_FIX_WALL_TEMP][face - 1];
-  // all loads first, then all stores: grad is read and written here, so stores between the loads would serialise the NG
-  // components into NG dependent round trips to HBM (on an i face every value is its own 32-byte sector)
-  double qI[NG], qG[NG], gI[NG][3];
-#pragma unroll
-  for (int cc = 0; cc < NG; ++cc) {
-    // slot cc holds variable cc+2 of qp(2:n_var): u,v,w,p,[k,omega]; slot 4 (cc == 3) is then overwritten with T
-    qI[cc] = (cc == 3) ? temp[ci] : q[(long long)(cc + 1) * fs + ci];
-    qG[cc] = (cc == 3) ? temp[cg] : q[(long long)(cc + 1) * fs + cg];
-    gI[cc][0] = grad[(3 * cc + 0) * fs + ci]; gI[cc][1] = grad[(3 * cc + 1) * fs + ci]; gI[cc][2] = grad[(3 * cc + 2) * fs + ci];
-  }
-#pragma unroll
-  for (int cc = 0; cc < NG; ++cc) {
-    const double gIx = gI[cc][0], gIy = gI[cc][1], gIz = gI[cc][2];
-    double gx = sig * (qI[cc] - qG[cc]) * c_x, gy = sig * (qI[cc] - qG[cc]) * c_y, gz = sig * (qI[cc] - qG[cc]) * c_z;
-    if (cc == 3 && id == -5 && (ft < 1. && ft >= 0.)) { gx = -gIx; gy = -gIy; gz = -gIz; }   // adiabatic wall
-    const double dot = (gIx * nx) + (gIy * ny) + (gIz * nz);
-    grad[(3 * cc + 0) * fs + cg] = gx + (gIx - dot * nx);
-    grad[(3 * cc + 1) * fs + cg] = gy + (gIy - dot * ny);
-    grad[(3 * cc + 2) * fs + cg] = gz + (gIz - dot * nz);
-  }
-  if (NG == 5) {   // viscosity.f90:165-212
-    if (id == -5) mu3[fs + cg] = -mu3[fs + ci];
-    else if (id == -1 || id == -2 || id == -3 || id == -4 || id == -6 || id == -7 || id == -8 || id == -9) mu3[fs + cg] = mu3[fs + ci];
-  }
-  if (NG >= 6 && P.kkl) {   // viscosity.f90:488-531: copy on -4..-1, -6, -8, -9 (no -7), anti on the wall
-    if (id == -5) mu3[fs + cg] = -mu3[fs + ci];
-    else if (id == -1 || id == -2 || id == -3 || id == -4 || id == -6 || id == -8 || id == -9) mu3[fs + cg] = mu3[fs + ci];
-  } else if (NG >= 6) {
-    if (id == -5) { mu3[fs + cg] = -mu3[fs + ci]; mu3[2 * fs + cg] = mu3[2 * fs + ci]; }
-    else if (id == -1 || id == -2 || id == -3 || id == -4 || id == -6 || id == -7 || id == -8 || id == -9) {
-      mu3[fs + cg] = mu3[fs + ci]; mu3[2 * fs + cg] = mu3[2 * fs + ci];
-    }
-  }
-}
-
 int launch_gradients(Ctx* ctx) {
   const Layout& L = ctx->P.L;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -242,10 +274,12 @@ int launch_gradients(Ctx* ctx) {
   }
   dim3 block(32, 4, 1);
   dim3 grid((L.imx + 1 + G_ALIGN + 31) / 32, (L.jmx + 1 + 3) / 4, L.kmx + 1);
-  if (ctx->P.sa) k_gradients<5><<<grid, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->err_dev);
-  else if (ctx->P.lctm) k_gradients<7><<<grid, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->err_dev);
-  else if (ctx->P.sst) k_gradients<6><<<grid, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->err_dev);
-  else k_gradients<4><<<grid, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->err_dev);
+#define F3D_GRAD_LAUNCH(NG_) k_gradients<NG_><<<grid, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->err_dev)
+  if (ctx->P.sa) F3D_GRAD_LAUNCH(5);
+  else if (ctx->P.lctm) F3D_GRAD_LAUNCH(7);
+  else if (ctx->P.sst) F3D_GRAD_LAUNCH(6);
+  else F3D_GRAD_LAUNCH(4);
+#undef F3D_GRAD_LAUNCH
   ctx->launches++;
   const int mx[3] = {L.imx, L.jmx, L.kmx};
   int mask = 0, na = 1, nb = 1;
@@ -258,10 +292,12 @@ int launch_gradients(Ctx* ctx) {
   }
   if (mask) {
     dim3 g2((na + 31) / 32, (nb + 3) / 4, 6);
-    if (ctx->P.sa) k_gradient_bc<5><<<g2, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->gbc, ctx->gbc_off_dev, mask);
-    else if (ctx->P.lctm) k_gradient_bc<7><<<g2, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->gbc, ctx->gbc_off_dev, mask);
-    else if (ctx->P.sst) k_gradient_bc<6><<<g2, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->gbc, ctx->gbc_off_dev, mask);
-    else k_gradient_bc<4><<<g2, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->gbc, ctx->gbc_off_dev, mask);
+#define F3D_GBC_LAUNCH(NG_) k_gradient_bc<NG_><<<g2, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->gbc, ctx->gbc_off_dev, mask)
+    if (ctx->P.sa) F3D_GBC_LAUNCH(5);
+    else if (ctx->P.lctm) F3D_GBC_LAUNCH(7);
+    else if (ctx->P.sst) F3D_GBC_LAUNCH(6);
+    else F3D_GBC_LAUNCH(4);
+#undef F3D_GBC_LAUNCH
     ctx->launches++;
   }
   if (ctx->timing) cudaEventRecord(e1, ctx->stream);

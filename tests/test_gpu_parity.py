@@ -394,6 +394,33 @@ def test_smoothbump_in_the_reference_configuration(pkg, case_mod):
     assert abs(ds / 7.883e-07 - 1.0) < 0.005, ds
 
 
+@pytest.mark.parametrize("turbulence", ["sst", "sst2003"])
+@pytest.mark.parametrize("bc", [[-11, -4, -5, -6, -11, -6], [-8, -11, -7, -5, -6, -11]])
+def test_ghost_eddy_viscosity_where_it_is_not_copied(pkg, case_mod, oracle, fused_or_staged, turbulence, bc):
+    """On a total-pressure face (-11) the reference does not copy mu_t / F1 into the ghost cell (viscosity.f90:408-465 lists -4..-1, -6..-9 and
+    the wall): they come out of the ghost cell's own state and its rule-made gradients (apply_gradient_bc runs before calculate_viscosity).
+    With omega lowered 1000-fold the strain term of mu_t = rho a1 k / max(a1 omega, S F2) binds, so those gradients matter."""
+    import importlib
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    blocks = syn.make_duct_blocks(None, n3=(9, 7, 5), turbulence=turbulence, time_step_accuracy="RK2", interpolant="muscl")
+    blk = blocks[0]
+    blk.bc_id = list(bc)
+    blk.qp[6] *= 1e-3
+    fl = blk.flow
+    M2 = fl.x_speed_inf ** 2 / (fl.gm * fl.pressure_inf / fl.density_inf)
+    blk.fixed[8, :] = fl.pressure_inf * (1 + 0.5 * (fl.gm - 1.0) * M2) ** (fl.gm / (fl.gm - 1.0)) * (1.0 + 1e-3 * np.arange(6))
+    blk.build_geometry()
+    s = _solver(pkg, blocks)
+    _, w = _check_residual(oracle, s, blocks)
+    full = (blk.kmx + 5, blk.jmx + 5, blk.imx + 5)
+    for which in (2, 3):      # mu_t, F1 incl. the first ghost layer
+        o, g = w.aux(0, which, full), s.blocks[0].aux(which, full)
+        K, J, I = slice(2, blk.kmx + 3), slice(2, blk.jmx + 3), slice(2, blk.imx + 3)
+        assert np.abs(g[K, J, I] - o[K, J, I]).max() <= 1e-12 * np.abs(o[K, J, I]).max(), which
+    _check_history(oracle, s, blocks, 4)
+    s.close()
+
+
 # ---- MUSCL / PPM pressure-based switching (muscl.f90:37-112, ppm.f90:108-170), every direction, quasi-2-D included -----------
 @pytest.mark.parametrize("interpolant", ["muscl", "ppm"])
 @pytest.mark.parametrize("shape,pb", [((20, 12, 10), (1, 1, 1)), ((33, 9, 1), (1, 0, 1)), ((7, 6, 5), (0, 1, 0))])
@@ -593,6 +620,13 @@ def test_boundary_conditions(pkg, case_mod, oracle, bc, shape, accur):
 
 # ---- the fused form of the viscous path (F3D_GRADIENTS=fused: gradients, viscosities and the ghost-gradient rule inside the tile pass,
 # tensor-memory hand-overs) against the oracle: every model, the boundary rules, several blocks, the benchmark's tiling ------------
+@pytest.fixture(params=["staged", "fused"])
+def fused_or_staged(request, monkeypatch):
+    if request.param == "fused":
+        monkeypatch.setenv("F3D_GRADIENTS", "fused")
+    return request.param
+
+
 @pytest.fixture
 def fused_path(monkeypatch):
     monkeypatch.setenv("F3D_GRADIENTS", "fused")   # read by fest3d_gpu_create
