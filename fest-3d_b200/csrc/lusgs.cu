@@ -41,18 +41,22 @@ __device__ __forceinline__ void lusgs_flux(const Params& P, const double (&ql)[N
   if (NV == 7) { U[5] = ql[0] * ql[5]; U[6] = ql[0] * ql[6]; }
 #pragma unroll
   for (int l = 0; l < NV; ++l) U[l] = U[l] + du[l];
+  // Divisions by one and the same denominator are taken as multiplications with its reciprocal (U(1), Volume: 6 + 21 IEEE divisions per
+  // flux in the reference's text, 12 fluxes per cell and iteration; each is a ~40-instruction sequence on this machine and the sweeps are
+  // bound by the length of one thread's instruction stream).  <= 1 ulp per quotient, inside the 1e-10 history tolerance like rcp64 in the sweep.
+  const double iU0 = 1.0 / U[0];
   W[0] = U[0];
-  W[1] = U[1] / U[0];
-  W[2] = U[2] / U[0];
-  W[3] = U[3] / U[0];
-  W[4] = (gm - 1.0) * (U[4] - (0.5 * (((U[1] * U[1]) + (U[2] * U[2])) + (U[3] * U[3])) / U[0]));
+  W[1] = U[1] * iU0;
+  W[2] = U[2] * iU0;
+  W[3] = U[3] * iU0;
+  W[4] = (gm - 1.0) * (U[4] - (0.5 * (((U[1] * U[1]) + (U[2] * U[2])) + (U[3] * U[3])) * iU0));
   if (NV == 7) {
-    W[5] = U[5] / U[0];
-    W[6] = U[6] / U[0];
+    W[5] = U[5] * iU0;
+    W[6] = U[6] * iU0;
     W[5] = W[5] + 0.5 * (1. - copysign(1.0, W[5])) * (ql[5] - W[5]);
     W[6] = W[6] + 0.5 * (1. - copysign(1.0, W[6])) * (ql[6] - W[6]);
   }
-  const double nx = f.nx, ny = f.ny, nz = f.nz, Area = f.A, Volume = f.vol, mmu = f.mmu, tmu = f.tmu;
+  const double nx = f.nx, ny = f.ny, nz = f.nz, Area = f.A, mmu = f.mmu, tmu = f.tmu;
   const double FaceNormalVelocity = (W[1] * nx) + (W[2] * ny) + (W[3] * nz);
   const double uface = 0.5 * (W[1] + qr[1]), vface = 0.5 * (W[2] + qr[2]), wface = 0.5 * (W[3] + qr[3]);
   Flux[0] = W[0] * FaceNormalVelocity;
@@ -65,14 +69,17 @@ __device__ __forceinline__ void lusgs_flux(const Params& P, const double (&ql)[N
   if (NV == 7) { Flux[5] = (W[5] * Flux[0]); Flux[6] = (W[6] * Flux[0]); }
   const double mu = mmu + tmu;
   const double T1 = W[4] / (W[0] * R_gas), T2 = qr[4] / (qr[0] * R_gas);
-  const double dTdx = (T2 - T1) * nx * Area / Volume, dTdy = (T2 - T1) * ny * Area / Volume, dTdz = (T2 - T1) * nz * Area / Volume;
-  const double dudx = (qr[1] - W[1]) * nx * Area / Volume, dudy = (qr[1] - W[1]) * ny * Area / Volume, dudz = (qr[1] - W[1]) * nz * Area / Volume;
-  const double dvdx = (qr[2] - W[2]) * nx * Area / Volume, dvdy = (qr[2] - W[2]) * ny * Area / Volume, dvdz = (qr[2] - W[2]) * nz * Area / Volume;
-  const double dwdx = (qr[3] - W[3]) * nx * Area / Volume, dwdy = (qr[3] - W[3]) * ny * Area / Volume, dwdz = (qr[3] - W[3]) * nz * Area / Volume;
+  const double iV = 1.0 / f.vol;
+  const double ax = nx * Area * iV, ay = ny * Area * iV, az = nz * Area * iV;   // n A / V of the one-sided differences
+  const double dTdx = (T2 - T1) * ax, dTdy = (T2 - T1) * ay, dTdz = (T2 - T1) * az;
+  const double dudx = (qr[1] - W[1]) * ax, dudy = (qr[1] - W[1]) * ay, dudz = (qr[1] - W[1]) * az;
+  const double dvdx = (qr[2] - W[2]) * ax, dvdy = (qr[2] - W[2]) * ay, dvdz = (qr[2] - W[2]) * az;
+  const double dwdx = (qr[3] - W[3]) * ax, dwdy = (qr[3] - W[3]) * ay, dwdz = (qr[3] - W[3]) * az;
   const double trace = dudx + dvdy + dwdz;
-  const double Tauxx = 2. * mu * (dudx - trace / 3.0), Tauyy = 2. * mu * (dvdy - trace / 3.0), Tauzz = 2. * mu * (dwdz - trace / 3.0);
+  const double tr3 = trace * (1.0 / 3.0);
+  const double Tauxx = 2. * mu * (dudx - tr3), Tauyy = 2. * mu * (dvdy - tr3), Tauzz = 2. * mu * (dwdz - tr3);
   const double Tauxy = mu * (dvdx + dudy), Tauxz = mu * (dwdx + dudz), Tauyz = mu * (dwdy + dvdz);
-  const double K_heat = (mmu / P.Pr + tmu / P.tPr) * gm * R_gas / (gm - 1.0);
+  const double K_heat = (mmu * P.inv_Pr + tmu * P.inv_tPr) * gm * R_gas * P.inv_gm1;
   const double Qx = K_heat * dTdx, Qy = K_heat * dTdy, Qz = K_heat * dTdz;
   Flux[1] = Flux[1] - (Tauxx * nx + Tauxy * ny + Tauxz * nz);
   Flux[2] = Flux[2] - (Tauxy * nx + Tauyy * ny + Tauyz * nz);
@@ -81,8 +88,8 @@ __device__ __forceinline__ void lusgs_flux(const Params& P, const double (&ql)[N
   Flux[4] = Flux[4] - (Tauxy * uface + Tauyy * vface + Tauyz * wface + Qy) * ny;
   Flux[4] = Flux[4] - (Tauxz * uface + Tauyz * vface + Tauzz * wface + Qz) * nz;
   if (NV == 7) {
-    const double dtkdx = (qr[5] - W[5]) * nx * Area / Volume, dtkdy = (qr[5] - W[5]) * ny * Area / Volume, dtkdz = (qr[5] - W[5]) * nz * Area / Volume;
-    const double dtwdx = (qr[6] - W[6]) * nx * Area / Volume, dtwdy = (qr[6] - W[6]) * ny * Area / Volume, dtwdz = (qr[6] - W[6]) * nz * Area / Volume;
+    const double dtkdx = (qr[5] - W[5]) * ax, dtkdy = (qr[5] - W[5]) * ay, dtkdz = (qr[5] - W[5]) * az;
+    const double dtwdx = (qr[6] - W[6]) * ax, dtwdy = (qr[6] - W[6]) * ay, dtwdz = (qr[6] - W[6]) * az;
     const double sigma_k = kSigmaK1 * f.F1 + kSigmaK2 * (1.0 - f.F1);
     const double sigma_w = kSigmaW1 * f.F1 + kSigmaW2 * (1.0 - f.F1);
     Flux[5] = Flux[5] + (mmu + sigma_k * tmu) * (dtkdx * nx + dtkdy * ny + dtkdz * nz);

@@ -29,7 +29,13 @@ def main():
     per = int(os.environ.get("F3D_BLOCKS_PER_RANK", "1"))
     n_blocks = world * per
     nb = par.block_grid(n_blocks)
-    kw = dict(n3=(12, 10, 8), nb=nb, turbulence="sst", time_step_accuracy="RK4", CFL=0.5)
+    # F3D_MP_CASE: the model / integrator the ranks run (the halo messages carry n_var = 7, 8, 7, 7 fields per cell)
+    case = os.environ.get("F3D_MP_CASE", "sst_rk4")
+    extra = {"sst_rk4": dict(turbulence="sst", time_step_accuracy="RK4", CFL=0.5),
+             "lctm_rk2": dict(turbulence="sst", transition="lctm2015", time_step_accuracy="RK2", CFL=0.5),
+             "kkl_none": dict(turbulence="kkl", time_step_accuracy="none", CFL=0.5),
+             "sst_implicit": dict(turbulence="sst", time_step_accuracy="implicit", CFL=20.0)}[case]
+    kw = dict(n3=(12, 10, 8), nb=nb, **extra)
     all_blocks = syn.make_duct_blocks(None, **kw)
     owners = par.block_to_rank(n_blocks, world)
     mine = [b for b in all_blocks if owners[b.block_id] == rank]
@@ -48,7 +54,7 @@ def main():
     rel = max(rel, (np.abs(hist[:, 0] - ho[:, 0]) / np.array(ms)).max())   # Res_abs(0) on the scale of sum |boundary mass flux|
     d = max(max(helpers.state_rel_diff(gb.get_state(), w.get_state(gb.blk.block_id))) for gb in s.blocks)
     ok = rel < 1e-10 and d < 1e-10
-    print("rank %d (%d blocks): history %.2e state %.2e %s" % (rank, len(mine), rel, d, "ok" if ok else "FAIL"), flush=True)
+    print("%s rank %d (%d blocks): history %.2e state %.2e %s" % (case, rank, len(mine), rel, d, "ok" if ok else "FAIL"), flush=True)
     t = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(t)
     s.close()

@@ -511,8 +511,8 @@ def test_headline_scheme_at_multi_tile_multi_chunk_sizes(pkg, case_mod, oracle, 
     s.close()
 
 
-@pytest.mark.parametrize("blocks_per_rank", [1, 2])
-def test_nccl_halo_exchange_multi_rank(blocks_per_rank):
+@pytest.mark.parametrize("blocks_per_rank,mp_case", [(1, "sst_rk4"), (2, "sst_rk4"), (1, "lctm_rk2"), (2, "sst_implicit"), (1, "kkl_none")])
+def test_nccl_halo_exchange_multi_rank(blocks_per_rank, mp_case):
     """One rank per GPU, one or two blocks per rank: halos over ncclSend/ncclRecv between ranks and device-to-device inside a
     rank, norms over ncclAllReduce, all contexts of a rank on ONE communicator (needs >= 2 GPUs)."""
     import subprocess
@@ -525,9 +525,10 @@ def test_nccl_halo_exchange_multi_rank(blocks_per_rank):
     if blocks_per_rank == 2:
         n = min(n, 4)
     script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "mp_nccl_check.py")
-    env = dict(os.environ, F3D_BLOCKS_PER_RANK=str(blocks_per_rank))
+    env = dict(os.environ, F3D_BLOCKS_PER_RANK=str(blocks_per_rank), F3D_MP_CASE=mp_case)
+    port = 29631 + blocks_per_rank + 10 * ["sst_rk4", "lctm_rk2", "sst_implicit", "kkl_none"].index(mp_case)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
-                        "--master-port", str(29631 + blocks_per_rank), script], capture_output=True, text=True, timeout=600, env=env)
+                        "--master-port", str(port), script], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
