@@ -421,6 +421,22 @@ def test_ghost_eddy_viscosity_where_it_is_not_copied(pkg, case_mod, oracle, fuse
     s.close()
 
 
+@pytest.mark.parametrize("kw", [dict(turbulence="sst", transition="lctm2015"), dict(turbulence="kkl"), dict(turbulence="sst", time_step_accuracy="implicit", CFL=30.0)],
+                         ids=["lctm2015", "kkl", "lusgs"])
+def test_second_wave_models_on_several_tiles_and_chunks(pkg, case_mod, oracle, kw):
+    """70 x 21 x 40 cells: three i tiles with a ragged last one, six j tiles with a ragged last one, four k chunks -- the seams the kernels'
+    global-memory side reads (plane k-1 / k+1 gradients of k-kL, intermittency gradient and cell centres of lctm2015, hyperplanes of LU-SGS)
+    must get right."""
+    import importlib
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    kw = dict(dict(time_step_accuracy="RK2", CFL=0.5), **kw)
+    blocks = syn.make_duct_blocks(None, n3=(70, 21, 40), **kw)
+    s = _solver(pkg, blocks)
+    _check_residual(oracle, s, blocks)
+    _check_history(oracle, s, blocks, 3)
+    s.close()
+
+
 # ---- MUSCL / PPM pressure-based switching (muscl.f90:37-112, ppm.f90:108-170), every direction, quasi-2-D included -----------
 @pytest.mark.parametrize("interpolant", ["muscl", "ppm"])
 @pytest.mark.parametrize("shape,pb", [((20, 12, 10), (1, 1, 1)), ((33, 9, 1), (1, 0, 1)), ((7, 6, 5), (0, 1, 0))])
