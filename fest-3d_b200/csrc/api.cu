@@ -130,6 +130,7 @@ static int create_impl(Fest3dGpuCtx* ctx, const Fest3dGpuConfig* cfg, int device
   P.tkl_inf = cfg->tkl_inf;
   P.lctm = cfg->transition == F3D_TRANS_LCTM2015 ? 1 : 0; P.tgm_inf = cfg->tgm_inf;
   P.trans_bc = cfg->transition == F3D_TRANS_BC ? 1 : 0; P.tu_inf = cfg->tu_inf;
+  P.re_theta_t = (803.73 * (pow(cfg->tu_inf + 0.6067, -1.027)));   // source.f90:579, 1164
   P.nu_cr = cfg->mu_ref != 0.0 ? 5.0 / (cfg->density_inf * cfg->vel_mag * 1.0 / cfg->mu_ref) : 0.0;   // chi_2 / Reynolds_number (state.f90:89)
   P.CFL = cfg->CFL; P.global_time_step = cfg->global_time_step;
   P.gm = cfg->gm; P.R_gas = cfg->R_gas; P.mu_ref = cfg->mu_ref; P.T_ref = cfg->T_ref; P.Sutherland_temp = cfg->Sutherland_temp;

@@ -48,7 +48,7 @@ struct Params {
   double density_inf, x_speed_inf, y_speed_inf, z_speed_inf, pressure_inf, tk_inf, tw_inf, tv_inf, tkl_inf, tgm_inf, MInf;
   double gama1, gama2, cd_floor, mut_floor, pk_limiter;
   double gama1_default, gama2_default;   // global_sst.f90:15-16 as they stand when add_sst_source never runs (transition = bc)
-  double tu_inf, nu_cr;   // transition = bc: free-stream turbulence intensity (percent), chi_2 / Reynolds_number
+  double tu_inf, nu_cr, re_theta_t;   // transition = bc: free-stream turbulence intensity (percent), chi_2 / Reynolds_number, 803.73 (Tu + 0.6067)^-1.027
   double fixed[F3D_NFIX][6];
   double res_scale[9];    // Res_scale(1:n_var) (resnorm.f90:136-150)
 };

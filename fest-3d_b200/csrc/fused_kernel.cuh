@@ -954,7 +954,7 @@ __global__ void __launch_bounds__(NT, 1) k_fused(const Params P, const KArgs a, 
               const double dist_c = a.geom[(long long)G_DIST * fs + c];
               const double mu_c = rA[F_MU];
               const double re_v = density * dist_c * dist_c * vort / mu_c;
-              P_k = gamma_bc(P.tu_inf, P.nu_cr, mut / density, vmag, dist_c, re_v) * P_k;
+              P_k = gamma_bc(P.re_theta_t, P.nu_cr, mut / density, vmag, dist_c, re_v) * P_k;
             }
             pkv[1] = F1c;
             pkv[2] = (P_k - D_k) * volc;
@@ -1005,7 +1005,7 @@ __global__ void __launch_bounds__(NT, 1) k_fused(const Params P, const KArgs a, 
               const double inv_k2_d2 = 1.0 / ((kKappaSA * kKappaSA) * dist2);
               const double Shat = fmax(vort + tv * fv2 * inv_k2_d2, 1.0e-10);
               const double inv_Shat = 1.0 / Shat;
-              const double gBC = gamma_bc(P.tu_inf, P.nu_cr, tv * fv1, vmag, dist_c, dist2 * vort / nu);
+              const double gBC = gamma_bc(P.re_theta_t, P.nu_cr, tv * fv1, vmag, dist_c, dist2 * vort / nu);
               const double Production = gBC * kCb1 * Shat * tv * volc;
               const double fwb = sa_fw(fmin(tv * inv_Shat * inv_k2_d2, 10.0));
               const double Destruction = (kCw1 * fwb * tv * tv / dist2) * (volc);
