@@ -268,10 +268,10 @@ extern "C" int fest3d_gpu_destroy(Fest3dGpuCtx* ctx) {
   for (auto& e : ctx->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   for (auto& e : ctx->ev_pool2) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   comm_release(ctx);
-  if (ctx->state_staging_out) cudaFree(ctx->state_staging_out);
+  for (double* b : {ctx->state_staging_out, ctx->state_staging_out2, ctx->state_staging_in2}) if (b) cudaFree(b);
   if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
   if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
-  for (cudaEvent_t e : {ctx->ev_h2d, ctx->ev_in_free, ctx->ev_relaid, ctx->ev_d2h}) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : {ctx->ev_h2d[0], ctx->ev_h2d[1], ctx->ev_in_free[0], ctx->ev_in_free[1], ctx->ev_relaid, ctx->ev_d2h[0], ctx->ev_d2h[1]}) if (e) cudaEventDestroy(e);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->ev_pack) cudaEventDestroy(ctx->ev_pack);
   if (ctx->ev_halo) cudaEventDestroy(ctx->ev_halo);
@@ -393,6 +393,7 @@ extern "C" int fest3d_gpu_set_state(Fest3dGpuCtx* ctx, const double* qp) {
   const Layout& L = ctx->P.L;
   int rc = ensure_state_staging(ctx);
   if (rc) return rc;
+  if ((rc = apply_pending_state(ctx))) return rc;   // an asynchronous upload still waiting: lay it out first, this state then replaces it
   const size_t n = (size_t)L.nv * (L.imx + 5) * (L.jmx + 5) * (L.kmx + 5);
   F3D_CUDA(cudaMemcpyAsync(ctx->state_staging, qp, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   if ((rc = launch_state_relayout(ctx, ctx->qp, ctx->state_staging, 1))) return rc;
@@ -411,7 +412,7 @@ extern "C" int fest3d_gpu_get_state(Fest3dGpuCtx* ctx, double* qp) {
   int rc = ensure_state_staging(ctx);
   if (rc) return rc;
   if ((rc = apply_pending_state(ctx))) return rc;
-  if (ctx->ev_in_free) F3D_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d, 0));
+  if (ctx->ev_h2d[0]) F3D_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[0], 0));   // (buffer 0 is the one the synchronous calls share)
   const size_t n = (size_t)L.nv * (L.imx + 5) * (L.jmx + 5) * (L.kmx + 5);
   if ((rc = launch_state_relayout(ctx, ctx->qp, ctx->state_staging, 0))) return rc;
   F3D_CUDA(cudaMemcpyAsync(qp, ctx->state_staging, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -432,23 +433,28 @@ static int ensure_async_state(Fest3dGpuCtx* ctx) {
   const Layout& L = ctx->P.L;
   const size_t n = (size_t)L.nv * (L.imx + 5) * (L.jmx + 5) * (L.kmx + 5);
   F3D_CUDA(cudaMalloc((void**)&ctx->state_staging_out, n * sizeof(double)));
+  F3D_CUDA(cudaMalloc((void**)&ctx->state_staging_out2, n * sizeof(double)));
+  F3D_CUDA(cudaMalloc((void**)&ctx->state_staging_in2, n * sizeof(double)));
   F3D_CUDA(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
   F3D_CUDA(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
-  F3D_CUDA(cudaEventCreateWithFlags(&ctx->ev_h2d, cudaEventDisableTiming));
-  F3D_CUDA(cudaEventCreateWithFlags(&ctx->ev_in_free, cudaEventDisableTiming));
+  for (int b = 0; b < 2; ++b) {
+    F3D_CUDA(cudaEventCreateWithFlags(&ctx->ev_h2d[b], cudaEventDisableTiming));
+    F3D_CUDA(cudaEventCreateWithFlags(&ctx->ev_in_free[b], cudaEventDisableTiming));
+    F3D_CUDA(cudaEventCreateWithFlags(&ctx->ev_d2h[b], cudaEventDisableTiming));
+  }
   F3D_CUDA(cudaEventCreateWithFlags(&ctx->ev_relaid, cudaEventDisableTiming));
-  F3D_CUDA(cudaEventCreateWithFlags(&ctx->ev_d2h, cudaEventDisableTiming));
   return 0;
 }
 
 // queue the re-layout of an uploaded state (called at the head of every step / residual call)
 static int apply_pending_state(Fest3dGpuCtx* ctx) {
   if (!ctx->state_pending) return 0;
-  F3D_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d, 0));
-  int rc = launch_state_relayout(ctx, ctx->qp, ctx->state_staging, 1);
+  const int b = ctx->in_pending;
+  F3D_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[b], 0));
+  int rc = launch_state_relayout(ctx, ctx->qp, b ? ctx->state_staging_in2 : ctx->state_staging, 1);
   if (rc) return rc;
   F3D_CUDA(cudaMemsetAsync(ctx->err_dev, 0, sizeof(int) * 4, ctx->stream));
-  F3D_CUDA(cudaEventRecord(ctx->ev_in_free, ctx->stream));   // the staging buffer may take the next upload
+  F3D_CUDA(cudaEventRecord(ctx->ev_in_free[b], ctx->stream));   // this staging buffer may take the upload after the next
   ctx->state_pending = false;
   ctx->state_set = true;
   return 0;
@@ -462,9 +468,11 @@ extern "C" int fest3d_gpu_set_state_async(Fest3dGpuCtx* ctx, const double* qp) {
   if (ctx->state_pending && (rc = apply_pending_state(ctx))) return rc;   // a second upload without a step in between: keep the order
   const Layout& L = ctx->P.L;
   const size_t n = (size_t)L.nv * (L.imx + 5) * (L.jmx + 5) * (L.kmx + 5);
-  F3D_CUDA(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_in_free, 0));
-  F3D_CUDA(cudaMemcpyAsync(ctx->state_staging, qp, n * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
-  F3D_CUDA(cudaEventRecord(ctx->ev_h2d, ctx->copy_in));
+  const int b = ctx->in_next;
+  F3D_CUDA(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_in_free[b], 0));   // the re-layout that last read this buffer (two uploads ago) is done
+  F3D_CUDA(cudaMemcpyAsync(b ? ctx->state_staging_in2 : ctx->state_staging, qp, n * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
+  F3D_CUDA(cudaEventRecord(ctx->ev_h2d[b], ctx->copy_in));
+  ctx->in_pending = b; ctx->in_next = b ^ 1;
   ctx->state_pending = true;
   { const int bid = ctx->last_error.block_id; ctx->last_error = Fest3dGpuError{}; ctx->last_error.block_id = bid; }
   return 0;
@@ -479,12 +487,15 @@ extern "C" int fest3d_gpu_get_state_async(Fest3dGpuCtx* ctx, double* qp) {
   // next step call; what is downloaded is the state behind the steps issued so far)
   const Layout& L = ctx->P.L;
   const size_t n = (size_t)L.nv * (L.imx + 5) * (L.jmx + 5) * (L.kmx + 5);
-  F3D_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h, 0));   // the previous download has left the outbound buffer
-  if ((rc = launch_state_relayout(ctx, ctx->qp, ctx->state_staging_out, 0))) return rc;
+  const int b = ctx->out_next;
+  double* const out = b ? ctx->state_staging_out2 : ctx->state_staging_out;
+  F3D_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[b], 0));   // the download before the previous one has left this outbound buffer
+  if ((rc = launch_state_relayout(ctx, ctx->qp, out, 0))) return rc;
   F3D_CUDA(cudaEventRecord(ctx->ev_relaid, ctx->stream));
   F3D_CUDA(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_relaid, 0));
-  F3D_CUDA(cudaMemcpyAsync(qp, ctx->state_staging_out, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy_out));
-  F3D_CUDA(cudaEventRecord(ctx->ev_d2h, ctx->copy_out));
+  F3D_CUDA(cudaMemcpyAsync(qp, out, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy_out));
+  F3D_CUDA(cudaEventRecord(ctx->ev_d2h[b], ctx->copy_out));
+  ctx->out_next = b ^ 1;
   return 0;
 }
 

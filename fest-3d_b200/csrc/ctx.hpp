@@ -109,9 +109,14 @@ struct Ctx {
   double* staging = nullptr;     // host<->device staging for AoS geometry upload
   double* state_staging = nullptr;   // contiguous copy of qp in the reference layout (set_state / get_state, and the inbound side of the
                                      // asynchronous transfers)
-  double* state_staging_out = nullptr;   // outbound side of the asynchronous transfers
+  // asynchronous transfers: TWO inbound and TWO outbound staging buffers, used alternately, so that the next upload does not wait for the
+  // re-layout of the previous one (nor a download for the previous download): the PCIe streams then run back to back (api.cu)
+  double* state_staging_in2 = nullptr;   // inbound buffer 1 (buffer 0 is state_staging)
+  double* state_staging_out = nullptr;   // outbound buffers 0, 1
+  double* state_staging_out2 = nullptr;
+  int in_next = 0, in_pending = 0, out_next = 0;
   cudaStream_t copy_in = nullptr, copy_out = nullptr;       // H2D / D2H run on their own streams: full duplex beside the compute stream
-  cudaEvent_t ev_h2d = nullptr, ev_in_free = nullptr, ev_relaid = nullptr, ev_d2h = nullptr;
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_in_free[2] = {nullptr, nullptr}, ev_relaid = nullptr, ev_d2h[2] = {nullptr, nullptr};
   bool state_pending = false;        // an uploaded state waits in state_staging to be laid out into qp (done at the next step / residual)
   Link link[6];
   int steps_in_flight = 0;       // iterations queued by fest3d_gpu_step_group_begin and not yet collected (kept by the group's first context)
