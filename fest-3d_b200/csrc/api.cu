@@ -180,7 +180,9 @@ static int create_impl(Fest3dGpuCtx* ctx, const Fest3dGpuConfig* cfg, int device
     const char* e = getenv("F3D_GRADIENTS");
     ctx->fused = (e && strcmp(e, "fused") == 0) ? 1 : 0;
   }
-  if (P.viscous && !ctx->fused) { F3D_CUDA(dalloc(&ctx->grad, 3 * L.ng)); F3D_CUDA(dalloc(&ctx->mu, ctx->n_mu + 3)); }
+  // (sa: the 15 gradient fields are followed by one more, the cross-diffusion scalar grad(rho) . grad(nu-tilde) of its source term -- the
+  // slot the tensor-map box of the sweep would otherwise pad: grad.cu:k_gradients)
+  if (P.viscous && !ctx->fused) { F3D_CUDA(dalloc(&ctx->grad, sa ? 16 : 3 * L.ng)); F3D_CUDA(dalloc(&ctx->mu, ctx->n_mu + 3)); }
   // staging for the AoS records: the largest face array
   const size_t rec_max = (size_t)4 * (L.imx + 6) * (L.jmx + 6) * (L.kmx + 6) * sizeof(double);
   F3D_CUDA(cudaMalloc((void**)&ctx->staging, rec_max));
@@ -213,7 +215,7 @@ static int create_impl(Fest3dGpuCtx* ctx, const Fest3dGpuConfig* cfg, int device
     if (P.viscous && !ctx->fused) {
       // lctm2015 (eight variables): the sweep stages the first 18 gradient fields and mu, mu_t, F1 + the CC.f90 field; the intermittency
       // gradient and the cell centres stay in global memory (sweep_common.cuh:RecF)
-      const int ngf = 3 * L.ng, naux = P.lctm ? ctx->n_mu + 1 : ctx->n_mu + 3;
+      const int ngf = P.sa ? 16 : 3 * L.ng, naux = P.lctm ? ctx->n_mu + 1 : ctx->n_mu + 3;
       ok = ok && encode(&ctx->tm_grad, ctx->grad, ngf, kG3TY + 2, P.lctm ? 18 : ((ngf + 1) & ~1)) && encode(&ctx->tm_aux, ctx->mu, naux, kG3TY + 2, (naux + 1) & ~1);
     }
     if (!ok) { fprintf(stderr, "fest3d_gpu: cuTensorMapEncodeTiled failed\n"); return fail(ctx, F3D_ERR_CUDA); }
@@ -527,10 +529,10 @@ extern "C" int fest3d_gpu_get_aux(Fest3dGpuCtx* ctx, int which, double* out) {
     // kernels of grad.cu recompute them from the current qp / Temp (ghost cells as the last stage left them)
     const size_t fb = (size_t)L.fs * sizeof(double);
     if (!ctx->grad) {
-      F3D_CUDA(cudaMalloc((void**)&ctx->grad, (size_t)3 * L.ng * fb));
+      F3D_CUDA(cudaMalloc((void**)&ctx->grad, (size_t)(ctx->P.sa ? 16 : 3 * L.ng) * fb));
       F3D_CUDA(cudaMalloc((void**)&ctx->mu, (size_t)ctx->n_mu * fb));
     }
-    F3D_CUDA(cudaMemsetAsync(ctx->grad, 0, (size_t)3 * L.ng * fb, ctx->stream));
+    F3D_CUDA(cudaMemsetAsync(ctx->grad, 0, (size_t)(ctx->P.sa ? 16 : 3 * L.ng) * fb, ctx->stream));
     F3D_CUDA(cudaMemsetAsync(ctx->mu, 0, (size_t)ctx->n_mu * fb, ctx->stream));
     if ((rc = launch_gradients(ctx))) return fail(ctx, rc);
     rc = F3D_ERR_ARGUMENT;

@@ -152,6 +152,28 @@ __global__ void __launch_bounds__(128, 5) k_gradients(const Params P, const doub
     mu3[fs + c] = mut;
     if (NG >= 6) mu3[2 * fs + c] = F1;
   }
+  if (NG == 5) {
+    // Spalart-Allmaras: the cross-diffusion scalar CD2 = grad(rho) . grad(nu-tilde) of add_sa_source (source.f90:883-952), whose density
+    // gradient is a Green-Gauss sum over the six neighbours.  Made here, where the gradient of nu-tilde is in registers, and carried to the
+    // sweep in the 16th gradient field: in the sweep it sat on the I-row warps alone, which the other warps then waited for.
+    // KEPT DEFECT: the normal of the low K face is (nx, nx, nx) (source.f90:901).
+    const long long sj = L.sj, sk = L.sk;
+    const double* __restrict__ gI = geom + (long long)G_IA * fs;
+    const double* __restrict__ gJ = geom + (long long)G_JA * fs;
+    const double* __restrict__ gK = geom + (long long)G_KA * fs;
+    const double density = q[c];
+    const double RhoFace[6] = {q[c - 1] + density, q[c - sj] + density, q[c - sk] + density, q[c + 1] + density, q[c + sj] + density, q[c + sk] + density};
+    const double volc = geom[(long long)G_VOL * fs + c];
+    double gradrho[3];
+#pragma unroll
+    for (int dd = 0; dd < 3; ++dd) {
+      const double n0 = gI[(1 + dd) * fs + c], n1 = gJ[(1 + dd) * fs + c], n2 = gK[fs + c];
+      const double n3 = gI[(1 + dd) * fs + c + 1], n4 = gJ[(1 + dd) * fs + c + sj], n5 = gK[(1 + dd) * fs + c + sk];
+      gradrho[dd] = (-(RhoFace[0]) * n0 * gI[c] - (RhoFace[1]) * n1 * gJ[c] - (RhoFace[2]) * n2 * gK[c] + (RhoFace[3]) * n3 * gI[c + 1] +
+                     (RhoFace[4]) * n4 * gJ[c + sj] + (RhoFace[5]) * n5 * gK[c + sk]) / (2.0 * volc);
+    }
+    grad[15 * fs + c] = ((gradrho[0] * g[4][0]) + (gradrho[1] * g[4][1]) + (gradrho[2] * g[4][2]));
+  }
 }
 
 // Ghost-gradient rule + ghost mu_t / F1 on the physical faces (gradients.f90:486-676, viscosity.f90:165-212, 408-465, 488-531).  The

@@ -660,30 +660,15 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a,
           pk[2 * NMAIN] = (P_k - D_k) * volc;
           pk[3 * NMAIN] = (P_w - D_w + lamda) * volc;
         }
-        if (SA && VISC) {   // SA source term (source.f90:835-983); the density gradient is built in place from the six neighbours
+        if (SA && VISC) {   // SA source term (source.f90:835-983)
           const double density = qA[0], tv = qA[5 * PSQ];
           const long long cI = c;   // global index of the cell
-          const double rho_km = q[cI - Ly.sk], rho_kp = q[cI + Ly.sk];   // the k neighbours are not staged: global memory (L2)
-          const double RhoFace[6] = {qA[-1] + density, qA[-PW] + density, rho_km + density, qA[1] + density, qA[PW] + density, rho_kp + density};
-          const double* __restrict__ gI = a.geom + (long long)G_IA * fs;
-          const double* __restrict__ gJ = a.geom + (long long)G_JA * fs;
-          const double* __restrict__ gK = a.geom + (long long)G_KA * fs;
-          const long long cf[6] = {cI, cI, cI, cI + 1, cI + Ly.sj, cI + Ly.sk};
-          double gradrho[3];
-#pragma unroll
-          for (int dd = 0; dd < 3; ++dd) {
-            // KEPT DEFECT: the normal of the low K face is (nx,nx,nx) (source.f90:901)
-            const double n0 = gI[(1 + dd) * fs + cf[0]], n1 = gJ[(1 + dd) * fs + cf[1]], n2 = gK[fs + cf[2]];
-            const double n3 = gI[(1 + dd) * fs + cf[3]], n4 = gJ[(1 + dd) * fs + cf[4]], n5 = gK[(1 + dd) * fs + cf[5]];
-            gradrho[dd] = (-(RhoFace[0]) * n0 * gI[cf[0]] - (RhoFace[1]) * n1 * gJ[cf[1]] - (RhoFace[2]) * n2 * gK[cf[2]] +
-                           (RhoFace[3]) * n3 * gI[cf[3]] + (RhoFace[4]) * n4 * gJ[cf[4]] + (RhoFace[5]) * n5 * gK[cf[5]]) / (2.0 * volc);
-          }
           const double wx = rA[(3 * 2 + 1) * PS] - rA[(3 * 1 + 2) * PS], wy = rA[(3 * 0 + 2) * PS] - rA[(3 * 2 + 0) * PS],
                        wz = rA[(3 * 1 + 0) * PS] - rA[(3 * 0 + 1) * PS];
           const double vort = sqrt(((wx * wx) + (wy * wy) + (wz * wz)));
           const double tvx = rA[(3 * 4 + 0) * PS], tvy = rA[(3 * 4 + 1) * PS], tvz = rA[(3 * 4 + 2) * PS];
           const double CD1 = kCb2 * ((tvx * tvx) + (tvy * tvy) + (tvz * tvz));
-          const double CD2 = ((gradrho[0] * tvx) + (gradrho[1] * tvy) + (gradrho[2] * tvz));
+          const double CD2 = rA[15 * PS];   // grad(rho) . grad(nu-tilde), made by k_gradients (16th staged gradient field)
           const double mu_c = rA[S::OFF_MU * PS];
           const double dist_c = a.geom[(long long)G_DIST * fs + cI];
           const double kd = kKappaSA * dist_c, kd2 = kd * kd;
