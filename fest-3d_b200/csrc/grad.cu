@@ -248,6 +248,36 @@ __global__ void k_gradient_bc(const Params P, const double* __restrict__ q, cons
   }
 }
 
+// k-kL: magnitude of the second velocity derivatives the von Karman length scale needs (source.f90:700-760): for each velocity component the
+// sum over the three directions of the Green-Gauss derivative of its first derivative, from the finished gradient arrays (ghost rule applied).
+// Written into aux field 2 (the F1 slot, unused by k-kL) of the interior cells, where the sweep stages it.
+__global__ void __launch_bounds__(128) k_kkl_udd(const Params P, const double* __restrict__ geom, const double* __restrict__ grad, double* __restrict__ mu3) {
+  const Layout& L = P.L;
+  const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y * blockDim.y + threadIdx.y, k = 1 + blockIdx.z;
+  if (i > L.imx - 1 || j > L.jmx - 1) return;
+  const long long fs = L.fs, c = L.idx(i, j, k), sj = L.sj, sk = L.sk;
+  const double* __restrict__ gI = geom + (long long)G_IA * fs;
+  const double* __restrict__ gJ = geom + (long long)G_JA * fs;
+  const double* __restrict__ gK = geom + (long long)G_KA * fs;
+  const double volc = geom[(long long)G_VOL * fs + c];
+  double lap[3] = {0., 0., 0.};
+#pragma unroll
+  for (int dd = 0; dd < 3; ++dd) {
+    const double wIl = gI[(1 + dd) * fs + c] * gI[c], wIh = gI[(1 + dd) * fs + c + 1] * gI[c + 1];
+    const double wJl = gJ[(1 + dd) * fs + c] * gJ[c], wJh = gJ[(1 + dd) * fs + c + sj] * gJ[c + sj];
+    const double wKl = gK[(1 + dd) * fs + c] * gK[c], wKh = gK[(1 + dd) * fs + c + sk] * gK[c + sk];
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc) {
+      const double* __restrict__ gf = grad + (long long)(3 * cc + dd) * fs;
+      const double g0 = gf[c];
+      const double s2 = (-(gf[c - 1] + g0) * wIl - (gf[c - sj] + g0) * wJl - (gf[c - sk] + g0) * wKl + (gf[c + 1] + g0) * wIh + (gf[c + sj] + g0) * wJh +
+                         (gf[c + sk] + g0) * wKh) / (2 * volc);
+      lap[cc] += s2;
+    }
+  }
+  mu3[2 * fs + c] = sqrt(lap[0] * lap[0] + lap[1] * lap[1] + lap[2] * lap[2]);
+}
+
 // lctm2015, CC.f90:73-122: find_CCnormal = Green-Gauss gradient g of the wall distance on cells 0..imx (compute_gradient :125-200),
 // normalised with |g| + 1e-12; find_DCCVn then -- KEPT DEFECT -- differentiates `dist` once more instead of CCVn = CCnormal . velocity,
 // so the "wall-normal velocity gradient" of add_sst_source_lctm2015 is DCCVn . CCnormal = |g|^2 / (|g| + 1e-12): a field fixed by the
@@ -320,6 +350,10 @@ int launch_gradients(Ctx* ctx) {
     else if (ctx->P.sst) F3D_GBC_LAUNCH(6);
     else F3D_GBC_LAUNCH(4);
 #undef F3D_GBC_LAUNCH
+    ctx->launches++;
+  }
+  if (ctx->P.kkl) {
+    k_kkl_udd<<<dim3((L.imx - 1 + 31) / 32, (L.jmx - 1 + 3) / 4, L.kmx - 1), block, 0, ctx->stream>>>(ctx->P, ctx->geom, ctx->grad, ctx->mu);
     ctx->launches++;
   }
   if (ctx->timing) cudaEventRecord(e1, ctx->stream);

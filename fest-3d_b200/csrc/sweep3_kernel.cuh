@@ -515,8 +515,6 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a,
         const double volc = smem[S::OFF_PRIV + (S::P_VOL + (k & 1)) * NMAIN + cell];
         pk[0] = volc;
         if (SST && VISC && RARE && P.kkl) {   // k-kL source terms (source.f90:607-832)
-          const double* const rB = rA - pA + pB;   // the same cell's record in plane k+1 ...
-          mbar_wait((char*)mbar + 8 * ((k + 1) & 1), plane_parity(k + 1));   // ... which only the K rows have waited for so far
           const long long cI = c;
           const double density = qA[0], tk = qA[5 * PSQ], tkl = qA[6 * PSQ];
           double gv[3][3];   // velocity gradients of the cell: gv[component][direction]
@@ -535,26 +533,10 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a,
           P_k = P_k + T13 * gv[2][0] + T23 * gv[2][1] + T33 * gv[2][2];
           const double D_k = kKklCmu75 * density * ((tk * tk) * sqrt(tk)) / fmax(tkl, 1.e-20);
           P_k = fmin(P_k, 20 * D_k);
-          // Green-Gauss sums of the cell gradients over the six faces (the k-1 neighbour is no longer staged: global memory / L2)
-          const double* __restrict__ gI = a.geom + (long long)G_IA * fs;
-          const double* __restrict__ gJ = a.geom + (long long)G_JA * fs;
-          const double* __restrict__ gK = a.geom + (long long)G_KA * fs;
-          double lap[3] = {0., 0., 0.};
-#pragma unroll
-          for (int dd = 0; dd < 3; ++dd) {
-            const double wIl = gI[(1 + dd) * fs + cI] * gI[cI], wIh = gI[(1 + dd) * fs + cI + 1] * gI[cI + 1];
-            const double wJl = gJ[(1 + dd) * fs + cI] * gJ[cI], wJh = gJ[(1 + dd) * fs + cI + Ly.sj] * gJ[cI + Ly.sj];
-            const double wKl = gK[(1 + dd) * fs + cI] * gK[cI], wKh = gK[(1 + dd) * fs + cI + Ly.sk] * gK[cI + Ly.sk];
-#pragma unroll
-            for (int cc = 0; cc < 3; ++cc) {
-              const int f = 3 * cc + dd;
-              const double g0 = gv[cc][dd];
-              const double s2 = (-(rA[f * PS - 1] + g0) * wIl - (rA[f * PS - PW] + g0) * wJl - (a.grad[(long long)f * fs + cI - Ly.sk] + g0) * wKl +
-                                 (rA[f * PS + 1] + g0) * wIh + (rA[f * PS + PW] + g0) * wJh + (rB[f * PS] + g0) * wKh) / (2 * volc);
-              lap[cc] += s2;
-            }
-          }
-          const double udd = sqrt(lap[0] * lap[0] + lap[1] * lap[1] + lap[2] * lap[2]);
+          // |d2u| of the von Karman length scale: made by k_kkl_udd (grad.cu) from the finished gradient arrays and staged in the aux slot
+          // the SST models use for F1 (k-kL has no blending function).  In this packet it cost the I-row warps 27 neighbour reads of plane
+          // k-1 / k+1 and 18 face metrics from global memory while the other warps waited.
+          const double udd = rA[(S::OFF_MU + 2) * PS];
           const double ud = sqrt(2 * (S11 * S11 + S12 * S12 + S13 * S13 + S12 * S12 + S22 * S22 + S23 * S23 + S13 * S13 + S23 * S23 + S33 * S33));
           const double dist_c = a.geom[(long long)G_DIST * fs + cI];
           double Lvk = kKklKappa * fabs(ud / fmax(udd, 1.e-20));
