@@ -563,3 +563,41 @@ def test_lusgs_single_cell_and_zero_residual(oracle, case_mod):
     scale = np.abs(blk.qp).reshape(5, -1).max(axis=1)[:, None, None, None]
     # the metric of the wavy grid closes to round-off only: the residual, and with it the update, is ~1e-16 of the flux scale
     assert np.abs(q - blk.qp)[:, 3:-3, 3:-3, 3:-3].max() <= 1e-10 * 1.0 and np.abs((q - blk.qp) / np.maximum(scale, 1.0))[:, 3:-3, 3:-3, 3:-3].max() < 1e-9
+
+
+def test_lusgs_single_cell_sst_source_jacobian(oracle, case_mod):
+    """The SST routine of LU-SGS (lusgs.f90:686-1024) on a block of one cell: no neighbour corrections, so delQ(l) = -R(l) / D(l) with
+    D(6) = D + bstar omega V and D(7) = D + 2 beta omega V (:830-832); k and omega only move where their conservative value stays positive
+    (:1010-1019).  D itself is taken from the mean-flow variables (same closed form as the laminar pin)."""
+    import importlib
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    blocks = syn.make_duct_blocks(None, n3=(1, 1, 1), turbulence="sst", time_step_accuracy="implicit", CFL=7.0)
+    blk = blocks[0]
+    fl = blk.flow
+    w = oracle.OracleWorld(blocks)
+    err, res = w.residual(1)
+    assert err == 0
+    w2 = oracle.OracleWorld(blocks)
+    assert w2.step(1)[0] == 0
+    q0, q1 = w.get_state(0), w2.get_state(0)
+    full = (blk.kmx + 5, blk.jmx + 5, blk.imx + 5)
+    F1 = w2.aux(0, 3, full)[3, 3, 3]
+    gm = fl.gm
+    rho, u, p, tk, tw = q0[0, 3, 3, 3], q0[1:4, 3, 3, 3], q0[4, 3, 3, 3], q0[5, 3, 3, 3], q0[6, 3, 3, 3]
+    U0 = np.array([rho, *(rho * u), p / (gm - 1) + 0.5 * rho * np.dot(u, u), rho * tk, rho * tw])
+    r1 = q1[0, 3, 3, 3]
+    R = res[0][:, 0, 0, 0]
+    D = -R[0] / (r1 - rho)                       # density: delQ(1) = -R(1) / D
+    V = blk.cells[3, 3, 3, 0]
+    beta = F1 * 0.075 + (1.0 - F1) * 0.0828
+    D6, D7 = D + 0.09 * tw * V, D + 2.0 * beta * tw * V
+    assert D6 > D * (1 + 1e-6) and D7 > D6            # the source Jacobian is not negligible in this state
+    U1 = U0 - R / np.array([D, D, D, D, D, D6, D7])
+    want_k, want_w = U1[5] / U1[0], U1[6] / U1[0]
+    assert U1[5] > 0 and U1[6] > 0
+    # (D comes out of a small density difference here: 1e-9, not round-off, is the resolution of this check)
+    assert abs(q1[5, 3, 3, 3] - want_k) <= 1e-9 * abs(want_k) and abs(q1[6, 3, 3, 3] - want_w) <= 1e-9 * abs(want_w)
+    want_u = U1[1:4] / U1[0]
+    assert np.allclose(q1[1:4, 3, 3, 3], want_u, rtol=1e-9, atol=1e-9 * np.abs(want_u).max())
+    # and the Jacobian matters at that resolution: without it k would land somewhere else
+    assert abs((U0[5] - R[5] / D) / U1[0] - want_k) > 1e-6 * abs(want_k)
