@@ -14,9 +14,9 @@
 // Work shared by both sweeps is done once, in a data-parallel pre-pass: the spectral radius times area of every face (SpectralRadius is
 // symmetric in its two cells bit for bit: sums commute, |x| = |-x|), three face fields.
 //
-// Kernels: k_lusgs_lambda (pre-pass), k_lusgs_sweep<NV, FWD> (one hyperplane), k_lusgs_apply<NV> (conservative update, in place).
-// Access along a hyperplane is strided (each thread of a warp touches its own row): this path is latency- / sector-bound, not the
-// benchmark path; DESIGN.md section 3.6 has the measured cost.
+// Kernels: k_lusgs_lambda (pre-pass), k_lusgs_sweep<NV, FWD> (one hyperplane, four lanes per cell), k_lusgs_apply<NV> (conservative update,
+// in place).  Access along a hyperplane is strided (every cell of a warp sits in its own row): this path is latency- / sector-bound, not
+// the benchmark path; DESIGN.md section 3.6 has the measured cost.
 #include "ctx.hpp"
 #include "physics.cuh"
 #include <algorithm>
@@ -135,46 +135,35 @@ __global__ void __launch_bounds__(128) k_lusgs_lambda(const Params P, const doub
   }
 }
 
-// one hyperplane i + j + k = h of a sweep.  FWD: delQstar from the low neighbours (lusgs.f90:296-312, 802-838); else delQ from the high
-// neighbours (:426-447, 920-959).  Grid: x over i, y over the k planes the hyperplane crosses (k = k0 + blockIdx.y).
+// One hyperplane i + j + k = h of a sweep.  FWD: delQstar from the low neighbours (lusgs.f90:296-312, 802-838); else delQ from the high
+// neighbours (:426-447, 920-959).  Grid: x over i (32 cells per CTA), y over the k planes the hyperplane crosses (k = k0 + blockIdx.y).
+// FOUR lanes per cell: lanes 0..2 evaluate the flux pair of the I, J, K face, lane 3 the diagonal D; the three face terms meet in lane 0
+// by shuffles and are added in the reference's order ((I) + (J)) + (K).  A sweep is bound by the length of one thread's instruction stream
+// times the number of hyperplanes (a hyperplane of a 128^3 block holds <= 12 k cells, one of SmoothBump 48): splitting the cell's work
+// across lanes shortens that stream.  Measured against one thread per cell: the reference's three shipped cases 80 -> 15 s, 128^3 9.0 -> 8.6 ms,
+// 256^3 SST 63.5 -> 54.4 ms per iteration (profiles/r02_lusgs_timing.txt).
 template <int NV, bool FWD>
 __global__ void __launch_bounds__(128) k_lusgs_sweep(const Params P, const double* __restrict__ q, const double* __restrict__ geom,
-                                                     const double* __restrict__ mu3, const double* __restrict__ lam, const double* __restrict__ dt,
-                                                     const double* __restrict__ residue, double* __restrict__ dqs, double* __restrict__ dq, int h, int k0) {
+                                                      const double* __restrict__ mu3, const double* __restrict__ lam, const double* __restrict__ dt,
+                                                      const double* __restrict__ residue, double* __restrict__ dqs, double* __restrict__ dq, int h, int k0) {
   const Layout& L = P.L;
   const int k = k0 + blockIdx.y;
-  const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane4 = threadIdx.x & 3;
+  const int i = 1 + blockIdx.x * (blockDim.x >> 2) + (threadIdx.x >> 2);
   const int j = h - i - k;
-  if (i > L.imx - 1 || j < 1 || j > L.jmx - 1) return;
-  const long long fs = L.fs, c = L.idx(i, j, k);
+  const bool valid = !(i > L.imx - 1 || j < 1 || j > L.jmx - 1);   // no early return: every lane of the warp takes part in the shuffles
+  const long long fs = L.fs, c = valid ? L.idx(i, j, k) : L.idx(1, 1, 1);
   const long long st[3] = {1, L.sj, L.sk};
-  double Q0[NV];
+  double term[NV], D[NV];
 #pragma unroll
-  for (int l = 0; l < NV; ++l) Q0[l] = q[l * fs + c];
-  const double vol0 = geom[(long long)G_VOL * fs + c];
-  const double m0 = mu3 ? mu3[c] : 0.0, t0 = (mu3 && NV == 7) ? mu3[fs + c] : 0.0, f0 = (mu3 && NV == 7) ? mu3[2 * fs + c] : 0.0;
-  // LambdaTimesArea(1..6): low I, J, K faces, then high I, J, K faces; SUM in that order
-  double Lm[6];
+  for (int l = 0; l < NV; ++l) { term[l] = 0.0; D[l] = 1.0; }
+  if (valid && lane4 < 3) {
+    const int d = lane4;
+    double Q0[NV];
 #pragma unroll
-  for (int d = 0; d < 3; ++d) { Lm[d] = lam[d * fs + c]; Lm[3 + d] = lam[d * fs + c + st[d]]; }
-  double s = 0.0;
-#pragma unroll
-  for (int n = 0; n < 6; ++n) s = s + Lm[n];
-  double D[NV];
-  {
-    const double D0 = (vol0 / dt[c]) + 0.5 * s;
-#pragma unroll
-    for (int l = 0; l < NV; ++l) D[l] = D0;
-    if (NV == 7) {   // lusgs.f90:830-832
-      const double beta = f0 * kBeta1 + (1.0 - f0) * kBeta2;
-      D[5] = (D[5] + (kBstar * Q0[6]) * vol0);
-      D[6] = (D[6] + 2.0 * beta * Q0[6] * vol0);
-    }
-  }
-  const double* __restrict__ src = FWD ? dqs : dq;
-  double acc[NV];   // ((I) + (J)) + (K)
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
+    for (int l = 0; l < NV; ++l) Q0[l] = q[l * fs + c];
+    const double vol0 = geom[(long long)G_VOL * fs + c];
+    const double m0 = mu3 ? mu3[c] : 0.0, t0 = (mu3 && NV == 7) ? mu3[fs + c] : 0.0, f0 = (mu3 && NV == 7) ? mu3[2 * fs + c] : 0.0;
     const long long n = FWD ? c - st[d] : c + st[d];
     const long long fc = FWD ? c : c + st[d];          // index of the face record
     const double sg = FWD ? -1.0 : 1.0;
@@ -185,22 +174,41 @@ __global__ void __launch_bounds__(128) k_lusgs_sweep(const Params P, const doubl
     f.mmu = mu3 ? 0.5 * (mu3[n] + m0) : 0.0;
     f.tmu = (mu3 && NV == 7) ? 0.5 * (mu3[fs + n] + t0) : 0.0;
     f.F1 = (mu3 && NV == 7) ? 0.5 * (mu3[2 * fs + n] + f0) : 0.0;
+    const double* __restrict__ src = FWD ? dqs : dq;
     double Qn[NV], DQ[NV], zero[NV], Fn[NV], Fo[NV];
 #pragma unroll
     for (int l = 0; l < NV; ++l) { Qn[l] = q[l * fs + n]; DQ[l] = src[l * fs + n]; zero[l] = 0.0; }
     lusgs_flux<NV>(P, Qn, Q0, DQ, f, Fn);
     lusgs_flux<NV>(P, Qn, Q0, zero, f, Fo);
-    const double lm = Lm[FWD ? d : 3 + d];
+    const double lm = lam[d * fs + fc];
 #pragma unroll
-    for (int l = 0; l < NV; ++l) {
-      const double term = ((Fn[l] - Fo[l]) - lm * DQ[l]);
-      acc[l] = (d == 0) ? term : acc[l] + term;
+    for (int l = 0; l < NV; ++l) term[l] = ((Fn[l] - Fo[l]) - lm * DQ[l]);
+  } else if (valid) {   // lane 3: D = V / dt + sum(lambda A) / 2 (+ the SST source Jacobian)
+    double s = 0.0;   // LambdaTimesArea(1..6): low I, J, K faces, then high I, J, K faces; SUM in that order
+#pragma unroll
+    for (int d = 0; d < 3; ++d) s = s + lam[d * fs + c];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) s = s + lam[d * fs + c + st[d]];
+    const double vol0 = geom[(long long)G_VOL * fs + c];
+    const double D0 = (vol0 / dt[c]) + 0.5 * s;
+#pragma unroll
+    for (int l = 0; l < NV; ++l) D[l] = D0;
+    if (NV == 7) {   // lusgs.f90:830-832
+      const double f0 = mu3 ? mu3[2 * fs + c] : 0.0, tw = q[6 * fs + c];
+      const double beta = f0 * kBeta1 + (1.0 - f0) * kBeta2;
+      D[5] = (D[5] + (kBstar * tw) * vol0);
+      D[6] = (D[6] + 2.0 * beta * tw * vol0);
     }
   }
 #pragma unroll
   for (int l = 0; l < NV; ++l) {
-    if (FWD) dqs[l * fs + c] = (-residue[l * fs + c] - 0.5 * acc[l]) / D[l];
-    else dq[l * fs + c] = dqs[l * fs + c] - 0.5 * acc[l] / D[l];
+    const double tJ = __shfl_down_sync(0xffffffffu, term[l], 1, 4), tK = __shfl_down_sync(0xffffffffu, term[l], 2, 4);
+    const double Dl = __shfl_down_sync(0xffffffffu, D[l], 3, 4);
+    if (valid && lane4 == 0) {
+      const double acc = (term[l] + tJ) + tK;   // ((I) + (J)) + (K)
+      if (FWD) dqs[l * fs + c] = (-residue[l * fs + c] - 0.5 * acc) / Dl;
+      else dq[l * fs + c] = dqs[l * fs + c] - 0.5 * acc / Dl;
+    }
   }
 }
 
@@ -243,7 +251,7 @@ int lusgs_run(Ctx* ctx) {
   k_lusgs_lambda<NV><<<dim3((L.imx + 31) / 32, (L.jmx + 3) / 4, L.kmx), block, 0, st>>>(ctx->P, ctx->qp, ctx->geom, mu3, ctx->lusgs_lam);
   ctx->launches++;
   const dim3 sb(128, 1, 1);
-  const int gx = (ni + 127) / 128;
+  const int gx = (ni + 31) / 32;   // four lanes per cell
   for (int pass = 0; pass < 2; ++pass) {
     for (int hh = 3; hh <= ni + nj + nk; ++hh) {
       const int h = pass == 0 ? hh : (ni + nj + nk + 3 - hh);
