@@ -183,6 +183,7 @@ static int create_impl(Fest3dGpuCtx* ctx, const Fest3dGpuConfig* cfg, int device
   // (sa: the 15 gradient fields are followed by one more, the cross-diffusion scalar grad(rho) . grad(nu-tilde) of its source term -- the
   // slot the tensor-map box of the sweep would otherwise pad: grad.cu:k_gradients)
   if (P.viscous && !ctx->fused) { F3D_CUDA(dalloc(&ctx->grad, sa ? 16 : 3 * L.ng)); F3D_CUDA(dalloc(&ctx->mu, ctx->n_mu + 3)); }
+  if (P.lctm) F3D_CUDA(dalloc(&ctx->src, 3));
   // staging for the AoS records: the largest face array
   const size_t rec_max = (size_t)4 * (L.imx + 6) * (L.jmx + 6) * (L.kmx + 6) * sizeof(double);
   F3D_CUDA(cudaMalloc((void**)&ctx->staging, rec_max));
@@ -259,7 +260,7 @@ extern "C" int fest3d_gpu_destroy(Fest3dGpuCtx* ctx) {
   checkpoint_free(ctx);   // joins a writer thread that may still be copying
   cudaDeviceSynchronize();
   double* bufs[] = {ctx->qp, ctx->qp2, ctx->ustore, ctx->rstore, ctx->residue, ctx->temp, ctx->dt, ctx->geom, ctx->grad, ctx->mu, ctx->gbc,
-                    ctx->red, ctx->norms_dev, ctx->staging, ctx->state_staging, ctx->lusgs_dqs, ctx->lusgs_dq, ctx->lusgs_lam};
+                    ctx->red, ctx->norms_dev, ctx->staging, ctx->state_staging, ctx->lusgs_dqs, ctx->lusgs_dq, ctx->lusgs_lam, ctx->src};
   for (double* b : bufs) if (b) cudaFree(b);
   for (int f = 0; f < 6; ++f) { if (ctx->sendbuf[f]) cudaFree(ctx->sendbuf[f]); if (ctx->recvbuf[f]) cudaFree(ctx->recvbuf[f]); }
   if (ctx->err_dev) cudaFree(ctx->err_dev);

@@ -84,6 +84,7 @@ struct Ctx {
   double* grad = nullptr;     // 3*ng fields: component c, direction d -> field 3*c+d
   double* mu = nullptr;       // mu [, mu_t [, F1]] as the model has them, then (staged path) a copy of the cell centre x,y,z
   int n_mu = 0;               // 1 laminar, 2 sa, 3 sst
+  double* src = nullptr;      // lctm2015: the three source terms x volume, made by k_gradients<7>
   // 4-D tensor maps [field][k][j][i]: q (36 x 8 cells x nv fields); fused path: Temp (36 x 8 x 1), geometry fields volume + centre
   // (36 x 6 x 4); staged path: gradients and the aux array (36 x 6 x fields)
   CUtensorMap tm_q[2], tm_temp, tm_geo, tm_grad, tm_aux;

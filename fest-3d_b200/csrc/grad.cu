@@ -123,10 +123,53 @@ __device__ __forceinline__ void eddy_viscosity(const Params& P, const double* __
   }
 }
 
+// add_sst_source_lctm2015 (source.f90:273-463) of one interior cell: S_k V, S_omega V, S_gamma V.  dvdy is the CC.f90 field (k_dvdy).
+__device__ __forceinline__ void lctm_sources(const Params& P, const double (&g)[7][3], double density, double tk, double tw, double gm_, double mu_c,
+                                             double mut, double F1c, double dvdy, double dist_c, double volc, double& Sk, double& Sw, double& Sg) {
+  const double wx = g[2][1] - g[1][2], wy = g[0][2] - g[2][0], wz = g[1][0] - g[0][1];
+  const double vort = sqrt(wx * wx + wy * wy + wz * wz);
+  const double syz = g[2][1] + g[1][2], szx = g[0][2] + g[2][0], sxy = g[1][0] + g[0][1];
+  const double strain = sqrt(((syz * syz) + (szx * szx) + (sxy * sxy) + 2 * (g[0][0] * g[0][0]) + 2 * (g[1][1] * g[1][1]) + 2 * (g[2][2] * g[2][2])));
+  double CD = 2 * density * kSigmaW2 * (g[4][0] * g[5][0] + g[4][1] * g[5][1] + g[4][2] * g[5][2]) / tw;
+  CD = fmax(CD, P.cd_floor);
+  const double gama = P.gama1 * F1c + P.gama2 * (1. - F1c);
+  const double beta = kBeta1 * F1c + kBeta2 * (1. - F1c);
+  const double D_k = kBstar * density * tw * tk;
+  const double D_w = beta * density * (tw * tw);
+  const double divergence = g[0][0] + g[1][1] + g[2][2];
+  double P_k = mut * (vort * strain) - ((2.0 / 3.0) * density * tk * divergence);
+  P_k = fmin(P_k, P.pk_limiter * D_k);
+  const double P_w = (density * gama / mut) * P_k;
+  const double lamda = (1. - F1c) * CD;
+  double lamd = (-7.57e-3) * (dvdy * dist_c * dist_c * density / mu_c) + 0.0128;
+  lamd = fmin(fmax(lamd, -1.0), 1.0);
+  double Fpg = (lamd >= 0.0) ? fmin(1.0 + 14.68 * lamd, 1.5) : fmin(1.0 - 7.34 * lamd, 3.0);
+  Fpg = fmax(Fpg, 0.0);
+  const double TuL = fmin(100.0 * sqrt(2.0 * tk / 3.0) / (tw * dist_c), 100.0);
+  const double Re_theta = 100.0 + 1000.0 * exp(-TuL * Fpg);
+  const double Rev = density * dist_c * dist_c * strain / mu_c;
+  const double RT = density * tk / (mu_c * tw);
+  const double hr = 0.5 * RT;
+  const double Fturb = exp(-((hr * hr) * (hr * hr)));
+  const double Fonset1 = Rev / (2.2 * Re_theta);
+  const double Fonset2 = fmin(Fonset1, 2.0);
+  const double r35 = RT / 3.5;
+  const double Fonset3 = fmax(1.0 - (r35 * r35 * r35), 0.0);
+  const double Fonset = fmax(Fonset2 - Fonset3, 0.0);
+  const double P_gm = 100 * density * strain * gm_ * (1.0 - gm_) * Fonset;
+  const double D_gm = 0.06 * density * vort * gm_ * Fturb * ((50.0 * gm_) - 1.0);
+  const double Fon_lim = fmin(fmax((Rev / (2.2 * 1100.0)) - 1.0, 0.0), 3.0);
+  const double Pk_lim = 5 * fmax(gm_ - 0.2, 0.0) * (1.0 - gm_) * Fon_lim * fmax(3 * mu_c - mut, 0.0) * strain * vort;
+  Sk = (gm_ * P_k - fmax(gm_, 0.1) * D_k + Pk_lim) * volc;
+  Sw = (P_w - D_w + lamda) * volc;
+  Sg = (P_gm - D_gm) * volc;
+}
+
 // One thread per cell of 0..imx x 0..jmx x 0..kmx: gradient, molecular and eddy viscosity, F1 of the cell itself
 template <int NG>
 __global__ void __launch_bounds__(128, 5) k_gradients(const Params P, const double* __restrict__ q, const double* __restrict__ temp,
-                                                   const double* __restrict__ geom, double* __restrict__ grad, double* __restrict__ mu3, int* err) {
+                                                   const double* __restrict__ geom, double* __restrict__ grad, double* __restrict__ mu3, int* err,
+                                                   double* __restrict__ src /* lctm2015 only */) {
   const Layout& L = P.L;
   // a warp covers cells i = 32 b - 15 .. 32 b + 16: cell 1 of a row starts a 128-byte line (ctx.hpp), so every row segment a warp
   // loads or stores is two whole lines (starting the warps at cell 0 made it three, two of them partial)
@@ -151,6 +194,14 @@ __global__ void __launch_bounds__(128, 5) k_gradients(const Params P, const doub
     eddy_viscosity<NG>(P, q, geom, c, g, mu, mut, F1);
     mu3[fs + c] = mut;
     if (NG >= 6) mu3[2 * fs + c] = F1;
+    if constexpr (NG == 7) {
+      if (src && i >= 1 && i <= L.imx - 1 && j >= 1 && j <= L.jmx - 1 && k >= 1 && k <= L.kmx - 1) {
+        double Sk, Sw, Sg;
+        lctm_sources(P, g, q[c], q[5 * fs + c], q[6 * fs + c], q[7 * fs + c], mu, mut, F1, mu3[3 * fs + c], geom[(long long)G_DIST * fs + c],
+                     geom[(long long)G_VOL * fs + c], Sk, Sw, Sg);
+        src[c] = Sk; src[fs + c] = Sw; src[2 * fs + c] = Sg;
+      }
+    }
   }
   if (NG == 5) {
     // Spalart-Allmaras: the cross-diffusion scalar CD2 = grad(rho) . grad(nu-tilde) of add_sa_source (source.f90:883-952), whose density
@@ -326,7 +377,7 @@ int launch_gradients(Ctx* ctx) {
   }
   dim3 block(32, 4, 1);
   dim3 grid((L.imx + 1 + G_ALIGN + 31) / 32, (L.jmx + 1 + 3) / 4, L.kmx + 1);
-#define F3D_GRAD_LAUNCH(NG_) k_gradients<NG_><<<grid, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->err_dev)
+#define F3D_GRAD_LAUNCH(NG_) k_gradients<NG_><<<grid, block, 0, ctx->stream>>>(ctx->P, ctx->qp, ctx->temp, ctx->geom, ctx->grad, ctx->mu, ctx->err_dev, ctx->src)
   if (ctx->P.sa) F3D_GRAD_LAUNCH(5);
   else if (ctx->P.lctm) F3D_GRAD_LAUNCH(7);
   else if (ctx->P.sst) F3D_GRAD_LAUNCH(6);

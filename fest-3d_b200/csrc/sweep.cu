@@ -48,6 +48,7 @@ int launch_residual(Ctx* ctx, int mode, double TF, double SF, int use_store_sum,
   a.geom = ctx->geom;
   a.grad = ctx->grad;
   a.mu = ctx->mu;
+  a.src = ctx->src;
   a.gbc = ctx->gbc;
   for (int f = 0; f < 6; ++f) a.gbc_off[f] = ctx->gbc_off[f];
   a.red = ctx->red;

@@ -554,54 +554,14 @@ __global__ void __launch_bounds__(NT, 1) k_sweep3(const Params P, const KArgs a,
           pk[NMAIN] = mu_c;
           pk[2 * NMAIN] = S_k * volc;
           pk[3 * NMAIN] = S_kl * volc;
-        } else if (LCTM && VISC) {   // SST source terms with the gamma transition model (source.f90:273-463)
-          double g[6][3];
-#pragma unroll
-          for (int cc = 0; cc < 6; ++cc) {
-            if (cc == 3) continue;
-            g[cc][0] = rA[(3 * cc + 0) * PS]; g[cc][1] = rA[(3 * cc + 1) * PS]; g[cc][2] = rA[(3 * cc + 2) * PS];
-          }
-          const double mu_c = rA[S::OFF_MU * PS], mut = rA[(S::OFF_MU + 1) * PS], F1c = rA[(S::OFF_MU + 2) * PS], dvdy = rA[(S::OFF_MU + 3) * PS];
-          const double density = qA[0], tk = qA[5 * PSQ], tw = qA[6 * PSQ], gm_ = qA[7 * PSQ];
-          const double wx = g[2][1] - g[1][2], wy = g[0][2] - g[2][0], wz = g[1][0] - g[0][1];
-          const double vort = sqrt(wx * wx + wy * wy + wz * wz);
-          const double syz = g[2][1] + g[1][2], szx = g[0][2] + g[2][0], sxy = g[1][0] + g[0][1];
-          const double strain = sqrt(((syz * syz) + (szx * szx) + (sxy * sxy) + 2 * (g[0][0] * g[0][0]) + 2 * (g[1][1] * g[1][1]) + 2 * (g[2][2] * g[2][2])));
-          double CD = 2 * density * kSigmaW2 * (g[4][0] * g[5][0] + g[4][1] * g[5][1] + g[4][2] * g[5][2]) / tw;
-          CD = fmax(CD, P.cd_floor);
-          const double gama = P.gama1 * F1c + P.gama2 * (1. - F1c);
-          const double beta = kBeta1 * F1c + kBeta2 * (1. - F1c);
-          const double D_k = kBstar * density * tw * tk;
-          const double D_w = beta * density * (tw * tw);
-          const double divergence = g[0][0] + g[1][1] + g[2][2];
-          double P_k = mut * (vort * strain) - ((2.0 / 3.0) * density * tk * divergence);
-          P_k = fmin(P_k, P.pk_limiter * D_k);
-          const double P_w = (density * gama / mut) * P_k;
-          const double lamda = (1. - F1c) * CD;
-          const double dist_c = a.geom[(long long)G_DIST * fs + c];
-          double lamd = (-7.57e-3) * (dvdy * dist_c * dist_c * density / mu_c) + 0.0128;
-          lamd = fmin(fmax(lamd, -1.0), 1.0);
-          double Fpg = (lamd >= 0.0) ? fmin(1.0 + 14.68 * lamd, 1.5) : fmin(1.0 - 7.34 * lamd, 3.0);
-          Fpg = fmax(Fpg, 0.0);
-          const double TuL = fmin(100.0 * sqrt(2.0 * tk / 3.0) / (tw * dist_c), 100.0);
-          const double Re_theta = 100.0 + 1000.0 * exp(-TuL * Fpg);
-          const double Rev = density * dist_c * dist_c * strain / mu_c;
-          const double RT = density * tk / (mu_c * tw);
-          const double hr = 0.5 * RT;
-          const double Fturb = exp(-((hr * hr) * (hr * hr)));
-          const double Fonset1 = Rev / (2.2 * Re_theta);
-          const double Fonset2 = fmin(Fonset1, 2.0);
-          const double r35 = RT / 3.5;
-          const double Fonset3 = fmax(1.0 - (r35 * r35 * r35), 0.0);
-          const double Fonset = fmax(Fonset2 - Fonset3, 0.0);
-          const double P_gm = 100 * density * strain * gm_ * (1.0 - gm_) * Fonset;
-          const double D_gm = 0.06 * density * vort * gm_ * Fturb * ((50.0 * gm_) - 1.0);
-          const double Fon_lim = fmin(fmax((Rev / (2.2 * 1100.0)) - 1.0, 0.0), 3.0);
-          const double Pk_lim = 5 * fmax(gm_ - 0.2, 0.0) * (1.0 - gm_) * Fon_lim * fmax(3 * mu_c - mut, 0.0) * strain * vort;
-          pk[NMAIN] = F1c;
-          pk[2 * NMAIN] = (gm_ * P_k - fmax(gm_, 0.1) * D_k + Pk_lim) * volc;
-          pk[3 * NMAIN] = (P_w - D_w + lamda) * volc;
-          pk[4 * NMAIN] = (P_gm - D_gm) * volc;
+        } else if (LCTM && VISC) {
+          // SST + gamma-transition source terms (source.f90:273-463): made by k_gradients<7> (grad.cu:lctm_sources), where the gradients, mu_t and
+          // F1 of the cell are in registers, and read here from global memory -- the packet (three exponentials, a dozen divisions) sat on the
+          // I-row warps alone while the other warps waited
+          pk[NMAIN] = rA[(S::OFF_MU + 2) * PS];
+          pk[2 * NMAIN] = a.src[c];
+          pk[3 * NMAIN] = a.src[fs + c];
+          pk[4 * NMAIN] = a.src[2 * fs + c];
         } else if (SST && VISC) {   // SST source terms (source.f90:214-268)
           double g[6][3];
 #pragma unroll

@@ -47,6 +47,7 @@ struct KArgs {
   const double* __restrict__ geom;
   const double* __restrict__ grad;    // staged-gradient path only (sweep3_kernel.cuh)
   const double* __restrict__ mu;      //   mu, mu_t, F1 + centre copy
+  const double* __restrict__ src;     //   lctm2015: S_k V, S_omega V, S_gamma V of every interior cell (grad.cu:lctm_sources)
   const double* __restrict__ gbc;     // face records (A, nx, ny, nz) of the ghost-gradient rule, six faces back to back
   long long gbc_off[6];               // offset of every face's records inside gbc
   double* __restrict__ red;           // per-CTA partials [(nv+1) * n_cta]

@@ -4,9 +4,13 @@ sys.path.insert(0, ".")
 import torch
 syn = importlib.import_module("fest3d_b200.synthetic")
 solver = importlib.import_module("fest3d_b200.solver")
+import os
 n = 256
+only = os.environ.get("MODELS")
 for name, kw in (("none (laminar)", dict(turbulence="none")), ("sa", dict(turbulence="sa")), ("sst", dict(turbulence="sst")), ("sst + bc", dict(turbulence="sst", transition="bc")),
                  ("kkl", dict(turbulence="kkl")), ("sst + lctm2015", dict(turbulence="sst", transition="lctm2015"))):
+    if only and name not in only.split(","):
+        continue
     blocks = syn.make_duct_blocks(n, time_step_accuracy="none", CFL=0.5, **kw)
     s = solver.Solver(blocks)
     s.iterate(3)
