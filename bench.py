@@ -153,6 +153,28 @@ def cpu_baseline_sample(args):
             "sample": "%d blocks of %d^3 cells, one thread per block, %d steps of the same %s duct" % (nblk, m, steps, scheme_label(args))}
 
 
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Host side of the e2e leg: run (and first-touch the pinned buffers) on the CPUs of the NUMA node the GPU hangs off, as a deployment
+    with numactl would.  Returns (description, previous affinity) -- the CPU baseline leg gets its full affinity back afterwards."""
+    prev = os.sched_getaffinity(0)
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return {"gpu_numa_node": None}, prev
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        use = cpus & prev
+        if use:
+            os.sched_setaffinity(0, use)
+        return {"gpu_numa_node": node, "cpus_allowed": len(prev), "cpus_on_node": len(use), "bound": bool(use)}, prev
+    except Exception as e:          # no sysfs / no permission: run where we are
+        return {"gpu_numa_node": "unknown (%s)" % type(e).__name__}, prev
+
+
 def kernel_profile(kernel_key):
     """Per-kernel constants taken from committed ncu captures (profiles/kernels.json): DRAM bytes per launch at the bench workload
     and FP64-pipe warp instructions per cell-warp.  Keyed by the kernel that actually ran; a kernel without a capture gets null."""
@@ -285,7 +307,9 @@ def main():
     e2e_value = None
     state_bytes = 0
     e2e_steps = max(3, min(args.steps, 12))   # the pipeline needs a few periods to reach its steady rate (one upload / download of 1 GB each per step)
+    numa_info, prev_affinity = {}, None
     if args.mode == "step":
+        numa_info, prev_affinity = bind_to_gpu_numa_node(torch, local_rank)
         q_host = torch.from_numpy(np.ascontiguousarray(q_keep)).pin_memory()
         q_back = torch.empty_like(q_host).pin_memory()
         q_np, qb_np = q_host.numpy(), q_back.numpy()
@@ -294,6 +318,15 @@ def main():
         s.iterate(1)
         for g in s.blocks:
             g.get_state(qb_np)   # warm-up of the path
+        # ... and of the asynchronous one: its staging buffers (3 GB of cudaMalloc per block), copy streams and events are created by the
+        # first asynchronous call -- tens to hundreds of milliseconds on a fresh box, which read as 0.44 - 0.75 G cell-updates/s from run to
+        # run while they sat inside the timed region
+        for _ in range(max(2, min(args.warmup, 3))):
+            s.set_states_async([q_np] * len(s.blocks))
+            s.iterate_begin(1)
+            s.iterate_end()
+            s.get_states_async([qb_np] * len(s.blocks))
+        s.state_wait()
         barrier()
         e0.record(stream)
         s.set_states_async([q_np] * len(s.blocks))             # H2D of step 0's input state (every block of the rank)
@@ -312,6 +345,8 @@ def main():
             dist.all_reduce(tm2, op=dist.ReduceOp.MAX)
         e2e_value = cells_all * e2e_steps / (float(tm2.item()) * 1e-3)
         state_bytes = int(q_host.numel() * 8) * len(s.blocks)
+        if prev_affinity:
+            os.sched_setaffinity(0, prev_affinity)
     sampler.stop_flag = True
 
     if rank == 0:
@@ -363,7 +398,7 @@ def main():
             "gpu_launches": launches, "clocks": sampler.summary(),
         }
         if e2e_value is not None:
-            line["e2e"] = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes + nvp1 * 8, "steps": e2e_steps}
+            line["e2e"] = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes + nvp1 * 8, "steps": e2e_steps, "host_numa": numa_info}
         else:
             line["e2e"] = {"value": value, "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                            "note": "residual-only mode keeps no host-visible result per call; the headline step mode carries the end-to-end figure"}
