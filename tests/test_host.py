@@ -183,3 +183,26 @@ def test_checkpoint_side_format_roundtrip(tmp_path):
     open(path, "wb").write(b"XXXXXXXX" + raw[8:])
     with pytest.raises(ValueError):
         ck.read_checkpoint(path)
+
+
+def test_bc_file_fixed_values_of_the_second_wave_models(case_mod, tmp_path):
+    """read_bc.f90:28-160: '- FIX_tkl v' / '- FIX_tgm v' lines land in their slots of the face they stand under; faces without a line keep the
+    free-stream defaults (fill_fixed_values: tkl_inf, tgm_inf)."""
+    import importlib
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    blk = syn.make_duct_blocks(None, n3=(4, 3, 2), turbulence="sst", transition="lctm2015")[0]
+    blk.flow.tkl_inf = 3.5e-7
+    f = tmp_path / "bc_00.md"
+    f.write_text("BOUNDARY CONDITIONS CONFIGURATION\n=================================\n\n# imn\n- FIX_DENSITY 1.3\n- FIX_tgm 0.25\n- FIX_tkl 1e-6\n\n"
+                 "# imx\n- COPY_DENSITY\n\n# jmn\n- WALL_TEMPERATURE 300.0\n\n# jmx\n- FIX_tgm 0.75\n\n# kmn\n\n# kmx\n- TOTAL_PRESSURE 123456.0\n\nFIN\n")
+    case_mod.read_bc_file(str(f), blk)
+    k = case_mod.FIX_KEYS
+    assert blk.fixed.shape == (13, 6) and k["FIX_tkl"] == 11 and k["FIX_tgm"] == 12
+    assert blk.fixed[k["FIX_DENSITY"], 0] == 1.3 and blk.fixed[k["FIX_DENSITY"], 1] == blk.flow.density_inf
+    assert list(blk.fixed[k["FIX_tgm"]]) == [0.25, 1.0, 1.0, 0.75, 1.0, 1.0]           # tgm_inf = 1 (vartypes.f90:258)
+    assert blk.fixed[k["FIX_tkl"], 0] == 1e-6 and blk.fixed[k["FIX_tkl"], 3] == 3.5e-7
+    assert blk.fixed[k["WALL_TEMPERATURE"], 2] == 300.0 and blk.fixed[k["TOTAL_PRESSURE"], 5] == 123456.0
+    # n_var and the initial intermittency (state.f90:260-266, 307-310)
+    assert blk.n_var == 8 and case_mod.n_var_of("sa", "lctm2015") == 7 and case_mod.n_var_of("kkl") == 7
+    blk.init_state()
+    assert blk.qp.shape[0] == 8 and np.all(blk.qp[7] == 1.0)
