@@ -601,3 +601,74 @@ def test_lusgs_single_cell_sst_source_jacobian(oracle, case_mod):
     assert np.allclose(q1[1:4, 3, 3, 3], want_u, rtol=1e-9, atol=1e-9 * np.abs(want_u).max())
     # and the Jacobian matters at that resolution: without it k would land somewhere else
     assert abs((U0[5] - R[5] / D) / U1[0] - want_k) > 1e-6 * abs(want_k)
+
+
+def test_kkl_source_against_numpy(oracle, case_mod):
+    """add_kkl_source (source.f90:607-832) restated in numpy from the oracle's own gradient arrays (cells 0..imx, ghost rule applied), against
+    what the oracle subtracted from the flux balance.  The second derivatives are Green-Gauss sums of the first ones over the six faces."""
+    import importlib
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    blocks = syn.make_duct_blocks(None, n3=(9, 7, 6), turbulence="kkl")
+    blk = blocks[0]
+    blk.qp[5] *= 1e3
+    blk.qp[6] *= 1e6          # mu_t / mu ~ 3e2: every term of the model is active
+    w = oracle.OracleWorld(blocks)
+    err, res = w.residual(1)
+    assert err == 0
+    res = res[0]
+    nv = 7
+    full = (blk.kmx + 5, blk.jmx + 5, blk.imx + 5)
+    F = w.aux(0, 20, (nv, blk.kmx - 1, blk.jmx - 1, blk.imx))
+    G = w.aux(0, 21, (nv, blk.kmx - 1, blk.jmx, blk.imx - 1))
+    H = w.aux(0, 22, (nv, blk.kmx, blk.jmx - 1, blk.imx - 1))
+    balance = (F[..., 1:] - F[..., :-1]) + (G[:, :, 1:, :] - G[:, :, :-1, :]) + (H[:, 1:] - H[:, :-1])
+    S_vol = balance - res
+    gshape = (6, blk.kmx + 1, blk.jmx + 1, blk.imx + 1)
+    g = [w.aux(0, 30 + d, gshape) for d in range(3)]            # g[d][component, k, j, i] on cells 0..imx
+    C = (slice(1, -1),) * 3                                        # interior cells inside the 0..imx arrays
+    Ki, Ji, Ii = slice(3, blk.kmx + 2), slice(3, blk.jmx + 2), slice(3, blk.imx + 2)
+    q = w.get_state(0)[:, Ki, Ji, Ii]
+    mu, mut = (w.aux(0, n, full)[Ki, Ji, Ii] for n in (1, 2))
+    d, vol = blk.dist[Ki, Ji, Ii], blk.cells[Ki, Ji, Ii, 0]
+    rho, tk, tkl = q[0], q[5], q[6]
+    dv = [[g[dd][c][C] for dd in range(3)] for c in range(3)]      # dv[c][dd] = d u_c / d x_dd
+    S = [[0.5 * (dv[a][b] + dv[b][a]) for b in range(3)] for a in range(3)]
+    delv = dv[0][0] + dv[1][1] + dv[2][2]
+    P_k = 0.0
+    for a in range(3):
+        for b in range(3):
+            tau = mut * (2 * S[a][b] - ((2.0 / 3.0) * delv if a == b else 0.0)) - ((2.0 / 3.0) * rho * tk if a == b else 0.0)
+            P_k = P_k + tau * dv[a][b]
+    cmu, kappa, c11, c12, cd1, z1, z2, z3 = 0.09, 0.41, 10.0, 1.3, 4.7, 1.2, 0.97, 0.13
+    D_k = cmu ** 0.75 * rho * tk ** 2.5 / np.maximum(tkl, 1e-20)
+    P_k = np.minimum(P_k, 20 * D_k)
+    # Green-Gauss second derivatives: face arrays at the cell's low faces (index c) and high faces (index c + 1 along the direction)
+    K1, J1, I1 = slice(4, blk.kmx + 3), slice(4, blk.jmx + 3), slice(4, blk.imx + 3)
+    lap = []
+    for c in range(3):
+        acc = 0.0
+        for dd in range(3):
+            G_ = g[dd][c]
+            g0 = G_[C]
+            nI_lo, nI_hi = blk.Ifaces[Ki, Ji, Ii, 1 + dd] * blk.Ifaces[Ki, Ji, Ii, 0], blk.Ifaces[Ki, Ji, I1, 1 + dd] * blk.Ifaces[Ki, Ji, I1, 0]
+            nJ_lo, nJ_hi = blk.Jfaces[Ki, Ji, Ii, 1 + dd] * blk.Jfaces[Ki, Ji, Ii, 0], blk.Jfaces[Ki, J1, Ii, 1 + dd] * blk.Jfaces[Ki, J1, Ii, 0]
+            nK_lo, nK_hi = blk.Kfaces[Ki, Ji, Ii, 1 + dd] * blk.Kfaces[Ki, Ji, Ii, 0], blk.Kfaces[K1, Ji, Ii, 1 + dd] * blk.Kfaces[K1, Ji, Ii, 0]
+            acc = acc + (-(G_[1:-1, 1:-1, :-2] + g0) * nI_lo - (G_[1:-1, :-2, 1:-1] + g0) * nJ_lo - (G_[:-2, 1:-1, 1:-1] + g0) * nK_lo
+                         + (G_[1:-1, 1:-1, 2:] + g0) * nI_hi + (G_[1:-1, 2:, 1:-1] + g0) * nJ_hi + (G_[2:, 1:-1, 1:-1] + g0) * nK_hi) / (2 * vol)
+        lap.append(acc)
+    udd = np.sqrt(lap[0] ** 2 + lap[1] ** 2 + lap[2] ** 2)
+    ud = np.sqrt(2 * sum(S[a][b] ** 2 for a in range(3) for b in range(3)))
+    Lvk = kappa * np.abs(ud / np.maximum(udd, 1e-20))
+    fp = np.clip(P_k / D_k, 0.5, 1.0)
+    Lvk = np.maximum(Lvk, tkl / np.maximum(tk * c11, 1e-20))
+    Lvk = np.minimum(Lvk, c12 * kappa * d * fp)
+    eta = rho * d * np.sqrt(0.3 * tk) / (20 * mu)
+    fphi = (1 + cd1 * eta) / (1 + eta ** 4)
+    cphi1 = z1 - z2 * (tkl / np.maximum(tk * Lvk, 1e-20)) ** 2
+    P_kl = cphi1 * tkl * P_k / np.maximum(tk, 1e-20)
+    D_kl = z3 * rho * tk ** 1.5
+    want = {5: (P_k - D_k - 2 * mu * tk / d ** 2) * vol, 6: (P_kl - D_kl - 6 * mu * tkl * fphi / d ** 2) * vol}
+    for v, wv in want.items():
+        scale = np.abs(balance[v]) + np.abs(res[v]) + np.abs(wv)
+        assert np.abs(S_vol[v] - wv).max() <= 5e-12 * scale.max(), v
+        assert np.abs(wv).max() > 1e-4 * np.abs(res[v]).max(), v
