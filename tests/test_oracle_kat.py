@@ -672,3 +672,48 @@ def test_kkl_source_against_numpy(oracle, case_mod):
         scale = np.abs(balance[v]) + np.abs(res[v]) + np.abs(wv)
         assert np.abs(S_vol[v] - wv).max() <= 5e-12 * scale.max(), v
         assert np.abs(wv).max() > 1e-4 * np.abs(res[v]).max(), v
+
+
+@pytest.mark.parametrize("turbulence", ["sst", "sst2003"])
+def test_sst_source_against_numpy(oracle, case_mod, turbulence):
+    """add_sst_source (source.f90:158-270) -- the source term of the benchmark configuration -- restated in numpy from the oracle's own
+    gradients, mu_t and F1, against what the oracle subtracted from the flux balance."""
+    import importlib
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    blocks = syn.make_duct_blocks(None, n3=(9, 7, 6), turbulence=turbulence)
+    blk = blocks[0]
+    blk.qp[5] *= 40.0
+    w = oracle.OracleWorld(blocks)
+    err, res = w.residual(1)
+    assert err == 0
+    res = res[0]
+    nv = 7
+    full = (blk.kmx + 5, blk.jmx + 5, blk.imx + 5)
+    F = w.aux(0, 20, (nv, blk.kmx - 1, blk.jmx - 1, blk.imx))
+    G = w.aux(0, 21, (nv, blk.kmx - 1, blk.jmx, blk.imx - 1))
+    H = w.aux(0, 22, (nv, blk.kmx, blk.jmx - 1, blk.imx - 1))
+    balance = (F[..., 1:] - F[..., :-1]) + (G[:, :, 1:, :] - G[:, :, :-1, :]) + (H[:, 1:] - H[:, :-1])
+    S_vol = balance - res
+    gshape = (6, blk.kmx + 1, blk.jmx + 1, blk.imx + 1)
+    gx, gy, gz = (w.aux(0, 30 + d, gshape)[:, 1:-1, 1:-1, 1:-1] for d in range(3))
+    Ki, Ji, Ii = slice(3, blk.kmx + 2), slice(3, blk.jmx + 2), slice(3, blk.imx + 2)
+    q = w.get_state(0)[:, Ki, Ji, Ii]
+    mut, F1 = (w.aux(0, n, full)[Ki, Ji, Ii] for n in (2, 3))
+    vol = blk.cells[Ki, Ji, Ii, 0]
+    rho, tk, tw = q[0], q[5], q[6]
+    vort = np.sqrt((gy[2] - gz[1]) ** 2 + (gz[0] - gx[2]) ** 2 + (gx[1] - gy[0]) ** 2)
+    s2003 = turbulence == "sst2003"
+    limiter = 10 if s2003 else 20
+    beta1, beta2, bstar, sigma_w2, kappa = 0.075, 0.0828, 0.09, 0.856, 0.41
+    gama1 = 5.0 / 9.0 if s2003 else beta1 / bstar - 0.5 * kappa ** 2 / np.sqrt(bstar)
+    gama2 = 0.44 if s2003 else beta2 / bstar - sigma_w2 * kappa ** 2 / np.sqrt(bstar)
+    CD = np.maximum(2 * rho * sigma_w2 * (gx[4] * gx[5] + gy[4] * gy[5] + gz[4] * gz[5]) / tw, 10.0 ** (-limiter))
+    gama, beta = gama1 * F1 + gama2 * (1 - F1), beta1 * F1 + beta2 * (1 - F1)
+    D_k, D_w = bstar * rho * tw * tk, beta * rho * tw ** 2
+    P_k = np.minimum(mut * vort ** 2 - (2.0 / 3.0) * rho * tk * (gx[0] + gy[1] + gz[2]), limiter * D_k)
+    P_w = rho * gama / mut * P_k
+    want = {5: (P_k - D_k) * vol, 6: (P_w - D_w + (1 - F1) * CD) * vol}
+    for v, wv in want.items():
+        scale = np.abs(balance[v]) + np.abs(res[v]) + np.abs(wv)
+        assert np.abs(S_vol[v] - wv).max() <= 2e-12 * scale.max(), v
+        assert np.abs(wv).max() > 1e-3 * np.abs(res[v]).max(), v
