@@ -206,3 +206,31 @@ def test_bc_file_fixed_values_of_the_second_wave_models(case_mod, tmp_path):
     assert blk.n_var == 8 and case_mod.n_var_of("sa", "lctm2015") == 7 and case_mod.n_var_of("kkl") == 7
     blk.init_state()
     assert blk.qp.shape[0] == 8 and np.all(blk.qp[7] == 1.0)
+
+
+def test_relative_resnorm_named_norms_and_convergence():
+    """resnorm.f90:227-239 (Res_save frozen after iteration 3), :259-360 (named norms), convergence.f90 (tolerance only after iteration 10,
+    with its swapped Y / Z momentum entries)."""
+    rn = importlib.import_module("fest3d_b200.resnorm")
+    h = rn.ResnormHistory("sst")
+    base = np.array([1e-3, 2.0, 3.0, 4.0, 5.0, 6.0, 7.0, 8.0])
+    for it in range(1, 13):
+        rel = h.update(it, base * 0.5 ** it)
+        if it <= 3:
+            assert np.all(rel == 1.0)
+        else:
+            assert np.allclose(rel, 0.5 ** (it - 3), rtol=1e-15)
+    a = base * 0.5 ** 12
+    assert h.named("Mass_abs") == a[0] and h.named("Continuity_abs") == a[1] and h.named("Omega_abs") == a[7] and h.named("Kl_abs") is None
+    assert h.named("Resnorm_abs") == float(np.sqrt((a[1:] ** 2).sum())) and h.named("Viscous_abs") == float(np.sqrt((a[1:6] ** 2).sum()))
+    assert h.named("Turbulent_rel") == float(np.sqrt(2.0)) * 0.5 ** 9
+    assert h.line(["Mass_abs", "Kl_abs", "TKE_abs"], last_iter=100) == [112, a[0], a[6]]
+    assert h.converged(a[1] * 1.01, "Continuity_abs") and not h.converged(a[1] * 0.99, "Continuity_abs")
+    assert h.converged(a[3] * 1.01, "Z-mom_abs") and not h.converged(a[3] * 1.01, "Y-mom_abs")          # convergence.f90:31-34 as written
+    assert h.converged(1.0, "no such norm") == (h.named("Resnorm_abs") < 1.0)
+    early = rn.ResnormHistory("none")
+    early.update(10, [0.0] * 6)
+    assert not early.converged(1.0, "Resnorm_abs")                                                       # current_iter > 10 only
+    # restart: Res_save comes from the restart record and is never overwritten
+    r = rn.ResnormHistory("none", previous_res=[1, 2, 2, 2, 2, 2])
+    assert np.allclose(r.update(1, [1, 1, 1, 1, 1, 1]), [1, .5, .5, .5, .5, .5])
