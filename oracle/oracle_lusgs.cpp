@@ -1,8 +1,9 @@
 // TEST INFRASTRUCTURE ONLY -- CPU oracle, part 3: the implicit LU-SGS update (time_step_accuracy = implicit) for laminar / inviscid
-// flow and the SST models.  PARITY UNPINNED (see oracle_abi.h).
+// flow, the SST models, Spalart-Allmaras and k-kL.  PARITY UNPINNED (see oracle_abi.h).
 //
 // Reference: src/lusgs.f90:86-131 (setup: delQ / delQstar on 0:imx, mmu / tmu aliases), :134-183 (dispatch), :186-488
-// (update_laminar_variables), :491-630 (Flux), :633-683 (SpectralRadius), :686-1024 (update_SST_variables), :1027-1196 (SSTFlux).
+// (update_laminar_variables), :491-630 (Flux), :633-683 (SpectralRadius), :686-1024 (update_SST_variables), :1027-1196 (SSTFlux),
+// :1198-1512 (update_KKL_variables), :1515-1677 (KKLFlux), :1680-2101 (update_SA_variables), :2104-2259 (SAFlux).
 // The sweeps are written in the reference's loop order (forward k,j,i ascending; backward i,j,k descending with k innermost); every cell
 // only reads neighbours the same sweep has already passed, so any order that respects that gives the same bits.
 #include "oracle_core.hpp"
@@ -20,9 +21,15 @@ struct LusgsCtx {
 };
 
 static inline double fsign1(double b) { return std::copysign(1.0, b); }   // sign(1., b)
+enum { M_LAM = 0, M_SST = 1, M_SA = 2, M_KKL = 3 };
+// global_sa.f90:6-19, global_kkl.f90:6-15
+constexpr double sa_cb1 = 0.1355, sa_cb2 = 0.6220, sa_cw2 = 0.3, sa_cw3 = 2.0, sa_cv1 = 7.1, sa_sigma = 2. / 3., sa_kappa = 0.41;
+static const double sa_cw1 = (sa_cb1 / (sa_kappa * sa_kappa)) + ((1 + sa_cb2) / sa_sigma);
+static const double sa_cv1_3 = sa_cv1 * sa_cv1 * sa_cv1, sa_cw3_6 = (sa_cw3 * sa_cw3 * sa_cw3) * (sa_cw3 * sa_cw3 * sa_cw3);
+constexpr double kkl_cmu_l = 0.09, kkl_sigma_k_l = 1.0, kkl_sigma_phi_l = 1.0;
 
 // lusgs.f90:491-630 (n_var 5) and :1027-1196 (n_var 7): flux through the face of the neighbour state ql advanced by du, against the cell qr
-template <int NV>
+template <int NV, int MODEL>
 static void lusgs_flux(const LusgsCtx& X, const double* ql, const double* qr, const double* du, const Face& f, double* Flux) {
   const double gm = X.gm, R_gas = X.R_gas;
   double U[NV], W[NV];
@@ -32,18 +39,29 @@ static void lusgs_flux(const LusgsCtx& X, const double* ql, const double* qr, co
   U[2] = ql[0] * ql[2];
   U[3] = ql[0] * ql[3];
   U[4] = (ql[4] / (gm - 1.0)) + (0.5 * ql[0] * (((ql[1] * ql[1]) + (ql[2] * ql[2])) + (ql[3] * ql[3])));
-  if (NV == 7) { U[5] = ql[0] * ql[5]; U[6] = ql[0] * ql[6]; }
+  if (NV >= 6) U[5] = ql[0] * ql[5];
+  if (NV == 7) U[6] = ql[0] * ql[6];
   for (int l = 0; l < NV; ++l) U[l] = U[l] + du[l];
   W[0] = U[0];
   W[1] = U[1] / U[0];
   W[2] = U[2] / U[0];
   W[3] = U[3] / U[0];
   W[4] = (gm - 1.0) * (U[4] - (0.5 * (((U[1] * U[1]) + (U[2] * U[2])) + (U[3] * U[3])) / U[0]));
-  if (NV == 7) {
+  if (MODEL == M_SST) {
     W[5] = U[5] / U[0];
     W[6] = U[6] / U[0];
     W[5] = W[5] + 0.5 * (1. - fsign1(W[5])) * (ql[5] - W[5]);
     W[6] = W[6] + 0.5 * (1. - fsign1(W[6])) * (ql[6] - W[6]);
+  }
+  if (MODEL == M_KKL) {   // lusgs.f90:1551-1554
+    W[5] = U[5] / U[0];
+    W[6] = U[6] / U[0];
+    W[5] = std::fmax(W[5], 1e-8);
+    W[6] = std::fmax(W[6], 1e-8);
+  }
+  if (MODEL == M_SA) {    // lusgs.f90:2140-2141
+    W[5] = U[5] / U[0];
+    W[5] = std::fmax(W[5], 1e-8);
   }
   const double nx = f.nx, ny = f.ny, nz = f.nz, Area = f.A, Volume = f.vol, mmu = f.mmu, tmu = f.tmu;
   const double FaceNormalVelocity = (W[1] * nx) + (W[2] * ny) + (W[3] * nz);
@@ -57,7 +75,9 @@ static void lusgs_flux(const LusgsCtx& X, const double* ql, const double* qr, co
   const double HalfRhoUsquare = 0.5 * W[0] * (W[1] * W[1] + W[2] * W[2] + W[3] * W[3]);
   const double RhoHt = ((gm / (gm - 1.0)) * W[4]) + HalfRhoUsquare;
   Flux[4] = RhoHt * FaceNormalVelocity;
-  if (NV == 7) { Flux[5] = (W[5] * Flux[0]); Flux[6] = (W[6] * Flux[0]); }
+  if (NV >= 6) Flux[5] = (W[5] * Flux[0]);
+  if (NV == 7) Flux[6] = (W[6] * Flux[0]);
+  const double muCap = (MODEL == M_SA) ? 0.25 * (P[0] + W[0]) * (P[5] + W[5]) : 0.0;   // lusgs.f90:2155
   const double mu = mmu + tmu;
   const double T1 = W[4] / (W[0] * R_gas);
   const double T2 = P[4] / (P[0] * R_gas);
@@ -80,11 +100,15 @@ static void lusgs_flux(const LusgsCtx& X, const double* ql, const double* qr, co
   Flux[4] = Flux[4] - (Tauxx * uface + Tauxy * vface + Tauxz * wface + Qx) * nx;
   Flux[4] = Flux[4] - (Tauxy * uface + Tauyy * vface + Tauyz * wface + Qy) * ny;
   Flux[4] = Flux[4] - (Tauxz * uface + Tauyz * vface + Tauzz * wface + Qz) * nz;
+  if (MODEL == M_SA) {   // lusgs.f90:2171-2173, 2192
+    const double dtvdx = (P[5] - W[5]) * nx * Area / Volume, dtvdy = (P[5] - W[5]) * ny * Area / Volume, dtvdz = (P[5] - W[5]) * nz * Area / Volume;
+    Flux[5] = Flux[5] + (mmu + muCap) * (dtvdx * nx + dtvdy * ny + dtvdz * nz) / sa_sigma;
+  }
   if (NV == 7) {
     const double dtkdx = (P[5] - W[5]) * nx * Area / Volume, dtkdy = (P[5] - W[5]) * ny * Area / Volume, dtkdz = (P[5] - W[5]) * nz * Area / Volume;
     const double dtwdx = (P[6] - W[6]) * nx * Area / Volume, dtwdy = (P[6] - W[6]) * ny * Area / Volume, dtwdz = (P[6] - W[6]) * nz * Area / Volume;
-    const double sigma_k = sigma_k1 * f.F1 + sigma_k2 * (1.0 - f.F1);
-    const double sigma_w = sigma_w1 * f.F1 + sigma_w2 * (1.0 - f.F1);
+    const double sigma_k = (MODEL == M_KKL) ? kkl_sigma_k_l : sigma_k1 * f.F1 + sigma_k2 * (1.0 - f.F1);
+    const double sigma_w = (MODEL == M_KKL) ? kkl_sigma_phi_l : sigma_w1 * f.F1 + sigma_w2 * (1.0 - f.F1);
     Flux[5] = Flux[5] + (mmu + sigma_k * tmu) * (dtkdx * nx + dtkdy * ny + dtkdz * nz);
     Flux[6] = Flux[6] + (mmu + sigma_w * tmu) * (dtwdx * nx + dtwdy * ny + dtwdz * nz);
   }
@@ -102,12 +126,12 @@ static double spectral_radius(const LusgsCtx& X, const double* ql, const double*
   return (NormalSpeed + SpeedOfSound + vis) * f.A;
 }
 
-template <int NV>
+template <int NV, int MODEL>
 static void lusgs_update(Block& B) {
   const int imx = B.imx, jmx = B.jmx, kmx = B.kmx;
   const OracleConfig& c = B.c;
   const LusgsCtx X{c.gm, c.R_gas, c.Pr, c.tPr};
-  const bool have_mu = c.mu_ref != 0.0, have_mut = (NV == 7);   // lusgs.f90:117-130: mmu / tmu point at a zero array otherwise
+  const bool have_mu = c.mu_ref != 0.0, have_mut = (MODEL != M_LAM);   // lusgs.f90:117-130: mmu / tmu point at a zero array otherwise
   Arr4 delQstar, delQ;
   delQstar.alloc(0, imx, 0, jmx, 0, kmx, NV);
   delQ.alloc(0, imx, 0, jmx, 0, kmx, NV);
@@ -128,7 +152,7 @@ static void lusgs_update(Block& B) {
       F[n].vol = 0.5 * (B.cells.vol(a, b, cc) + B.cells.vol(i, j, k));
       F[n].mmu = 0.5 * (mmu(a, b, cc) + mmu(i, j, k));
       F[n].tmu = 0.5 * (tmu(a, b, cc) + tmu(i, j, k));
-      F[n].F1 = (NV == 7) ? 0.5 * (B.F1(a, b, cc) + B.F1(i, j, k)) : 0.0;
+      F[n].F1 = (MODEL == M_SST) ? 0.5 * (B.F1(a, b, cc) + B.F1(i, j, k)) : 0.0;
       double C1[3] = {B.cells.cx(a, b, cc), B.cells.cy(a, b, cc), B.cells.cz(a, b, cc)};
       L[n] = spectral_radius(X, Q[n + 1], Q[0], F[n], C1, C0);
     }
@@ -136,10 +160,49 @@ static void lusgs_update(Block& B) {
     for (int n = 0; n < 6; ++n) s = s + L[n];   // SUM(LambdaTimesArea)
     const double D0 = (B.cells.vol(i, j, k) / B.delta_t(i, j, k)) + 0.5 * s;
     for (int l = 0; l < NV; ++l) D[l] = D0;
-    if (NV == 7) {   // lusgs.f90:830-832
+    if (MODEL == M_SST) {   // lusgs.f90:830-832
       const double beta = B.F1(i, j, k) * beta1 + (1.0 - B.F1(i, j, k)) * beta2;
       D[5] = (D[5] + (bstar * B.qp(i, j, k, 7)) * B.cells.vol(i, j, k));
       D[6] = (D[6] + 2.0 * beta * B.qp(i, j, k, 7) * B.cells.vol(i, j, k));
+    }
+    if (MODEL == M_KKL) {   // lusgs.f90:1339-1341
+      const double vol = B.cells.vol(i, j, k), d = B.dist(i, j, k);
+      D[5] = D[5] + (2.5 * (std::pow(kkl_cmu_l, (0.75))) * Q[0][0] * (std::pow(Q[0][5], (1.5))) * vol / Q[0][6]);
+      D[5] = D[5] + (2 * mmu(i, j, k) * vol / (d * d));
+      D[6] = D[6] + (6 * mmu(i, j, k) * vol / (d * d));
+    }
+    if (MODEL == M_SA) {   // lusgs.f90:1868-1913: the source-term derivatives go into EVERY component of D (array assignment) -- reproduced
+      const double vol = B.cells.vol(i, j, k);
+      const double density = B.qp(i, j, k, 1);
+      const double a = (B.gy(i, j, k, 3) - B.gz(i, j, k, 2)), b = (B.gz(i, j, k, 1) - B.gx(i, j, k, 3)), cc = (B.gx(i, j, k, 2) - B.gy(i, j, k, 1));
+      const double Omega = std::sqrt(((a * a) + (b * b) + (cc * cc)));
+      const double dist_i = B.dist(i, j, k), dist_i_2 = dist_i * dist_i, k2 = sa_kappa * sa_kappa;
+      const double nu = B.mu(i, j, k) / density;
+      const double Ji = Q[0][5] / nu, Ji_2 = Ji * Ji, Ji_3 = Ji_2 * Ji;
+      const double fv1 = (Ji_3) / ((Ji_3) + (sa_cv1_3));
+      const double fv2 = 1.0 - Ji / (1.0 + (Ji * fv1));
+      const double inv_k2_d2 = 1.0 / (k2 * dist_i_2);
+      double Shat = Omega + Q[0][5] * fv2 * inv_k2_d2;
+      Shat = std::fmax(Shat, 1.0e-10);
+      const double inv_Shat = 1.0 / Shat;
+      const double den1 = (Ji_3 + sa_cv1_3);
+      const double dfv1 = 3.0 * Ji_2 * sa_cv1_3 / (nu * (den1 * den1));
+      const double den2 = (1.0 + Ji * fv1);
+      const double dfv2 = -((1.0 / nu) - Ji_2 * dfv1) / (den2 * den2);
+      const double dShat = (fv2 + Q[0][5] * dfv2) * inv_k2_d2;
+      const double r = std::fmin(Q[0][5] * inv_Shat * inv_k2_d2, 10.0);
+      const double r2 = r * r, r6 = r2 * r2 * r2;
+      const double g = r + sa_cw2 * ((r6) - r);
+      const double g2 = g * g, g_6 = g2 * g2 * g2;
+      const double glim = std::pow((1.0 + sa_cw3_6) / (g_6 + sa_cw3_6), (1.0 / 6.0));
+      const double fw = g * glim;
+      const double dr = (Shat - Q[0][5] * dShat) * inv_Shat * inv_Shat * inv_k2_d2;
+      const double dg = dr * (1.0 + sa_cw2 * (6.0 * (r2 * r2 * r) - 1.0));
+      const double dfw = dg * glim * (1.0 - g_6 / (g_6 + sa_cw3_6));
+      for (int l = 0; l < NV; ++l) {
+        D[l] = D[l] - sa_cb1 * (Q[0][5] * dShat + Shat) * vol;
+        D[l] = D[l] + sa_cw1 * (dfw * Q[0][5] + 2 * fw) * Q[0][5] / dist_i_2 * vol;
+      }
     }
   };
   const double zero[NV] = {0};
@@ -153,8 +216,8 @@ static void lusgs_update(Block& B) {
         for (int n = 0; n < 3; ++n) {
           for (int l = 0; l < NV; ++l) DQ[n][l] = delQstar(i + di[n], j + dj[n], k + dk[n], l + 1);
           double Fn[NV], Fo[NV];
-          lusgs_flux<NV>(X, Q[n + 1], Q[0], DQ[n], F[n], Fn);
-          lusgs_flux<NV>(X, Q[n + 1], Q[0], zero, F[n], Fo);
+          lusgs_flux<NV, MODEL>(X, Q[n + 1], Q[0], DQ[n], F[n], Fn);
+          lusgs_flux<NV, MODEL>(X, Q[n + 1], Q[0], zero, F[n], Fo);
           for (int l = 0; l < NV; ++l) Del[n][l] = Fn[l] - Fo[l];
         }
         for (int l = 0; l < NV; ++l) {
@@ -173,8 +236,8 @@ static void lusgs_update(Block& B) {
         for (int n = 0; n < 3; ++n) {
           for (int l = 0; l < NV; ++l) DQ[n][l] = delQ(i + di[n + 3], j + dj[n + 3], k + dk[n + 3], l + 1);
           double Fn[NV], Fo[NV];
-          lusgs_flux<NV>(X, Q[n + 4], Q[0], DQ[n], F[n + 3], Fn);
-          lusgs_flux<NV>(X, Q[n + 4], Q[0], zero, F[n + 3], Fo);
+          lusgs_flux<NV, MODEL>(X, Q[n + 4], Q[0], DQ[n], F[n + 3], Fn);
+          lusgs_flux<NV, MODEL>(X, Q[n + 4], Q[0], zero, F[n + 3], Fo);
           for (int l = 0; l < NV; ++l) Del[n][l] = Fn[l] - Fo[l];
         }
         for (int l = 0; l < NV; ++l)
@@ -192,27 +255,35 @@ static void lusgs_update(Block& B) {
         cq[3] = B.qp(i, j, k, 1) * B.qp(i, j, k, 4);
         cq[4] = (B.qp(i, j, k, 5) / (c.gm - 1.0)) +
                 (0.5 * B.qp(i, j, k, 1) * (((B.qp(i, j, k, 2) * B.qp(i, j, k, 2)) + (B.qp(i, j, k, 3) * B.qp(i, j, k, 3))) + (B.qp(i, j, k, 4) * B.qp(i, j, k, 4))));
-        if (NV == 7) { cq[5] = B.qp(i, j, k, 1) * B.qp(i, j, k, 6); cq[6] = B.qp(i, j, k, 1) * B.qp(i, j, k, 7); }
+        if (NV >= 6) cq[5] = B.qp(i, j, k, 1) * B.qp(i, j, k, 6);
+        if (NV == 7) cq[6] = B.qp(i, j, k, 1) * B.qp(i, j, k, 7);
         for (int l = 0; l < NV; ++l) cq[l] = cq[l] + delQ(i, j, k, l + 1);
         B.qp(i, j, k, 1) = cq[0];
         B.qp(i, j, k, 2) = cq[1] / cq[0];
         B.qp(i, j, k, 3) = cq[2] / cq[0];
         B.qp(i, j, k, 4) = cq[3] / cq[0];
         B.qp(i, j, k, 5) = (c.gm - 1.0) * (cq[4] - (0.5 * (((cq[1] * cq[1]) + (cq[2] * cq[2])) + (cq[3] * cq[3])) / cq[0]));
-        if (NV == 7) {
+        if (MODEL == M_SST) {
           if (cq[5] > 0) B.qp(i, j, k, 6) = cq[5] / cq[0];
           if (cq[6] > 0) B.qp(i, j, k, 7) = cq[6] / cq[0];
         }
+        if (MODEL == M_KKL) {   // lusgs.f90:1505-1508
+          B.qp(i, j, k, 6) = std::fmax(cq[5] / cq[0], 1.e-8);
+          B.qp(i, j, k, 7) = std::fmax(cq[6] / cq[0], 1.e-8);
+        }
+        if (MODEL == M_SA) B.qp(i, j, k, 6) = std::fmax(cq[5] / cq[0], 1.e-8);   // lusgs.f90:2095-2096
       }
 }
 
 }  // namespace
 
-// lusgs.f90:134-183: laminar / inviscid and sst / sst2003 (transition none | bc); kkl, sa and lctm2015 have their own routines there
-// (:1198, :1680, :2262) that are not restated
+// lusgs.f90:134-183: laminar / inviscid, sst / sst2003 (transition none | bc), kkl, sa (the dispatcher ignores transition = bc for sa);
+// the lctm2015 routine (:2262) is not restated
 int Block::update_with_lusgs() {
-  if (c.turbulence == ORC_TURB_NONE) { lusgs_update<5>(*this); return 0; }
-  if ((c.turbulence == ORC_TURB_SST || c.turbulence == ORC_TURB_SST2003) && c.transition != 2) { lusgs_update<7>(*this); return 0; }
+  if (c.turbulence == ORC_TURB_NONE) { lusgs_update<5, M_LAM>(*this); return 0; }
+  if ((c.turbulence == ORC_TURB_SST || c.turbulence == ORC_TURB_SST2003) && c.transition != 2) { lusgs_update<7, M_SST>(*this); return 0; }
+  if (c.turbulence == ORC_TURB_KKL) { lusgs_update<7, M_KKL>(*this); return 0; }
+  if (c.turbulence == ORC_TURB_SA) { lusgs_update<6, M_SA>(*this); return 0; }
   return 64;
 }
 
