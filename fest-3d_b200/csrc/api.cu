@@ -76,9 +76,8 @@ extern "C" int fest3d_gpu_create(Fest3dGpuCtx** out, const Fest3dGpuConfig* cfg,
   if (kkl || lctm) { const char* e = getenv("F3D_GRADIENTS"); if (e && strcmp(e, "fused") == 0) return F3D_ERR_UNSUPPORTED; }   // staged form only
   if (cfg->time_accuracy > F3D_T_IMPLICIT || cfg->time_accuracy < 0) return F3D_ERR_UNSUPPORTED;   // plusgs
   if (cfg->time_accuracy == F3D_T_IMPLICIT) {
-    // LU-SGS: the laminar / inviscid, SST, k-kL and SA routines of lusgs.f90 (:186, :686, :1198, :1680); its lctm2015 routine (:2262) is not
-    // built.  The sweeps read mu / mu_t / F1 (and, for sa, the velocity gradients) as arrays, which only the staged form of the viscous path keeps.
-    if (lctm) return F3D_ERR_UNSUPPORTED;
+    // LU-SGS: every routine of lusgs.f90's dispatcher (:186 laminar / inviscid, :686 SST, :1198 k-kL, :1680 SA, :2262 lctm2015).  The sweeps
+    // read mu / mu_t / F1 (and, for sa and lctm2015, the velocity gradients) as arrays, which only the staged form of the viscous path keeps.
     const char* e = getenv("F3D_GRADIENTS");
     if (cfg->mu_ref != 0.0 && e && strcmp(e, "fused") == 0) return F3D_ERR_UNSUPPORTED;
   }

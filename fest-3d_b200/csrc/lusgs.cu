@@ -1,5 +1,5 @@
 // Implicit LU-SGS update (time_step_accuracy = implicit) for laminar / inviscid flow, the SST models, Spalart-Allmaras and k-kL: SURVEY.md
-// 8(f) rank 4 (laminar) and the other routines of the reference's dispatcher except the lctm2015 one.
+// 8(f) rank 4 (laminar) and the other four routines of the reference's dispatcher (SST, k-kL, SA, SST + lctm2015).
 //
 // Reference: src/lusgs.f90:134-183 (update_with_lusgs), :186-488 (update_laminar_variables), :491-630 (Flux), :633-683
 // (SpectralRadius), :686-1024 (update_SST_variables), :1027-1196 (SSTFlux), :1198-1512 (update_KKL_variables), :1515-1677 (KKLFlux),
@@ -28,7 +28,7 @@ namespace f3d {
 namespace {
 
 struct LFace { double A, nx, ny, nz, vol, mmu, tmu, F1; };
-enum { M_LAM = 0, M_SST = 1, M_SA = 2, M_KKL = 3 };   // which routine of lusgs.f90: :186 laminar, :686 SST, :1680 SA, :1198 k-kL
+enum { M_LAM = 0, M_SST = 1, M_SA = 2, M_KKL = 3, M_LCTM = 4 };   // which routine of lusgs.f90: :186 laminar, :686 SST, :1680 SA, :1198 k-kL, :2262 lctm2015
 
 // lusgs.f90:491-630 (Flux) / :1027-1196 (SSTFlux) / :1515-1677 (KKLFlux) / :2104-2259 (SAFlux)
 template <int NV, int MODEL>
@@ -42,7 +42,8 @@ __device__ __forceinline__ void lusgs_flux(const Params& P, const double (&ql)[N
   U[3] = ql[0] * ql[3];
   U[4] = (ql[4] / (gm - 1.0)) + (0.5 * ql[0] * (((ql[1] * ql[1]) + (ql[2] * ql[2])) + (ql[3] * ql[3])));
   if (NV >= 6) U[5] = ql[0] * ql[5];
-  if (NV == 7) U[6] = ql[0] * ql[6];
+  if (NV >= 7) U[6] = ql[0] * ql[6];
+  if (NV == 8) U[7] = ql[0] * ql[7];
 #pragma unroll
   for (int l = 0; l < NV; ++l) U[l] = U[l] + du[l];
   // Divisions by one and the same denominator are taken as multiplications with its reciprocal (U(1), Volume: 6 + 21 IEEE divisions per
@@ -54,11 +55,12 @@ __device__ __forceinline__ void lusgs_flux(const Params& P, const double (&ql)[N
   W[2] = U[2] * iU0;
   W[3] = U[3] * iU0;
   W[4] = (gm - 1.0) * (U[4] - (0.5 * (((U[1] * U[1]) + (U[2] * U[2])) + (U[3] * U[3])) * iU0));
-  if (MODEL == M_SST) {
+  if (MODEL == M_SST || MODEL == M_LCTM) {
     W[5] = U[5] * iU0;
     W[6] = U[6] * iU0;
     W[5] = W[5] + 0.5 * (1. - copysign(1.0, W[5])) * (ql[5] - W[5]);
     W[6] = W[6] + 0.5 * (1. - copysign(1.0, W[6])) * (ql[6] - W[6]);
+    if (MODEL == M_LCTM) W[NV - 1] = fmax(U[NV - 1] * iU0, 0.0);   // lusgs.f90:2715
   }
   if (MODEL == M_KKL) { W[5] = fmax(U[5] * iU0, 1e-8); W[6] = fmax(U[6] * iU0, 1e-8); }   // lusgs.f90:1551-1554
   if (MODEL == M_SA) W[5] = fmax(U[5] * iU0, 1e-8);                                          // lusgs.f90:2140-2141
@@ -73,7 +75,8 @@ __device__ __forceinline__ void lusgs_flux(const Params& P, const double (&ql)[N
   const double RhoHt = ((gm / (gm - 1.0)) * W[4]) + HalfRhoUsquare;
   Flux[4] = RhoHt * FaceNormalVelocity;
   if (NV >= 6) Flux[5] = (W[5] * Flux[0]);
-  if (NV == 7) Flux[6] = (W[6] * Flux[0]);
+  if (NV >= 7) Flux[6] = (W[6] * Flux[0]);
+  if (NV == 8) Flux[NV - 1] = (W[NV - 1] * Flux[0]);
   const double muCap = (MODEL == M_SA) ? 0.25 * (qr[0] + W[0]) * (qr[5] + W[5]) : 0.0;   // lusgs.f90:2155
   const double mu = mmu + tmu;
   const double T1 = W[4] / (W[0] * R_gas), T2 = qr[4] / (qr[0] * R_gas);
@@ -99,13 +102,17 @@ __device__ __forceinline__ void lusgs_flux(const Params& P, const double (&ql)[N
     const double dtvdx = (qr[5] - W[5]) * ax, dtvdy = (qr[5] - W[5]) * ay, dtvdz = (qr[5] - W[5]) * az;
     Flux[5] = Flux[5] + (mmu + muCap) * (dtvdx * nx + dtvdy * ny + dtvdz * nz) / kSigmaSA;
   }
-  if (NV == 7) {
+  if (NV >= 7) {
     const double dtkdx = (qr[5] - W[5]) * ax, dtkdy = (qr[5] - W[5]) * ay, dtkdz = (qr[5] - W[5]) * az;
     const double dtwdx = (qr[6] - W[6]) * ax, dtwdy = (qr[6] - W[6]) * ay, dtwdz = (qr[6] - W[6]) * az;
     const double sigma_k = (MODEL == M_KKL) ? 1.0 : kSigmaK1 * f.F1 + kSigmaK2 * (1.0 - f.F1);   // global_kkl.f90: sigma_k = sigma_phi = 1
     const double sigma_w = (MODEL == M_KKL) ? 1.0 : kSigmaW1 * f.F1 + kSigmaW2 * (1.0 - f.F1);
     Flux[5] = Flux[5] + (mmu + sigma_k * tmu) * (dtkdx * nx + dtkdy * ny + dtkdz * nz);
     Flux[6] = Flux[6] + (mmu + sigma_w * tmu) * (dtwdx * nx + dtwdy * ny + dtwdz * nz);
+  }
+  if (NV == 8) {   // lusgs.f90:2753-2755, 2777
+    const double dg = qr[NV - 1] - W[NV - 1];
+    Flux[NV - 1] = Flux[NV - 1] + (mmu + tmu) * ((dg * ax) * nx + (dg * ay) * ny + (dg * az) * nz);
   }
 #pragma unroll
   for (int l = 0; l < NV; ++l) Flux[l] = Flux[l] * Area;
@@ -176,7 +183,8 @@ __global__ void __launch_bounds__(128) k_lusgs_sweep(const Params P, const doubl
 #pragma unroll
     for (int l = 0; l < NV; ++l) Q0[l] = q[l * fs + c];
     const double vol0 = geom[(long long)G_VOL * fs + c];
-    const double m0 = mu3 ? mu3[c] : 0.0, t0 = (mu3 && MODEL != M_LAM) ? mu3[fs + c] : 0.0, f0 = (mu3 && MODEL == M_SST) ? mu3[2 * fs + c] : 0.0;
+    const double m0 = mu3 ? mu3[c] : 0.0, t0 = (mu3 && MODEL != M_LAM) ? mu3[fs + c] : 0.0,
+                 f0 = (mu3 && (MODEL == M_SST || MODEL == M_LCTM)) ? mu3[2 * fs + c] : 0.0;
     const long long n = FWD ? c - st[d] : c + st[d];
     const long long fc = FWD ? c : c + st[d];          // index of the face record
     const double sg = FWD ? -1.0 : 1.0;
@@ -186,7 +194,7 @@ __global__ void __launch_bounds__(128) k_lusgs_sweep(const Params P, const doubl
     f.vol = 0.5 * (geom[(long long)G_VOL * fs + n] + vol0);
     f.mmu = mu3 ? 0.5 * (mu3[n] + m0) : 0.0;
     f.tmu = (mu3 && MODEL != M_LAM) ? 0.5 * (mu3[fs + n] + t0) : 0.0;
-    f.F1 = (mu3 && MODEL == M_SST) ? 0.5 * (mu3[2 * fs + n] + f0) : 0.0;
+    f.F1 = (mu3 && (MODEL == M_SST || MODEL == M_LCTM)) ? 0.5 * (mu3[2 * fs + n] + f0) : 0.0;
     const double* __restrict__ src = FWD ? dqs : dq;
     double Qn[NV], DQ[NV], zero[NV], Fn[NV], Fo[NV];
 #pragma unroll
@@ -206,11 +214,34 @@ __global__ void __launch_bounds__(128) k_lusgs_sweep(const Params P, const doubl
     const double D0 = (vol0 / dt[c]) + 0.5 * s;
 #pragma unroll
     for (int l = 0; l < NV; ++l) D[l] = D0;
-    if (MODEL == M_SST) {   // lusgs.f90:830-832
+    if (MODEL == M_SST || MODEL == M_LCTM) {   // lusgs.f90:830-832, 2406-2409
       const double f0 = mu3 ? mu3[2 * fs + c] : 0.0, tw = q[6 * fs + c];
       const double beta = f0 * kBeta1 + (1.0 - f0) * kBeta2;
       D[5] = (D[5] + (kBstar * tw) * vol0);
       D[6] = (D[6] + 2.0 * beta * tw * vol0);
+    }
+    if (MODEL == M_LCTM) {   // lusgs.f90:2410-2440: derivative of the intermittency source (no pressure-gradient factor in this Re_theta)
+      const double density = q[c], tk = q[5 * fs + c], tw = q[6 * fs + c], gm_ = q[7 * fs + c], d = geom[(long long)G_DIST * fs + c], muc = mu3[c];
+      double g[3][3];
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) { g[cc][0] = grad[(3 * cc) * fs + c]; g[cc][1] = grad[(3 * cc + 1) * fs + c]; g[cc][2] = grad[(3 * cc + 2) * fs + c]; }
+      const double wx = g[2][1] - g[1][2], wy = g[0][2] - g[2][0], wz = g[1][0] - g[0][1];
+      const double vort = sqrt(wx * wx + wy * wy + wz * wz);
+      const double syz = g[2][1] + g[1][2], szx = g[0][2] + g[2][0], sxy = g[1][0] + g[0][1];
+      const double strain = sqrt(((syz * syz) + (szx * szx) + (sxy * sxy) + 2 * (g[0][0] * g[0][0]) + 2 * (g[1][1] * g[1][1]) + 2 * (g[2][2] * g[2][2])));
+      const double TuL = fmin(100.0 * sqrt(2.0 * tk / 3.0) / (tw * d), 100.0);
+      const double Re_theta = 100.0 + 1000.0 * exp(-TuL);
+      const double Rev = density * d * d * strain / muc;
+      const double RT = density * tk / (muc * tw);
+      const double hr = 0.5 * RT;
+      const double Fturb = exp(-((hr * hr) * (hr * hr)));
+      const double Fonset2 = fmin(Rev / (2.2 * Re_theta), 2.0);
+      const double r35 = RT / 3.5;
+      const double Fonset3 = fmax(1.0 - (r35 * r35 * r35), 0.0);
+      const double Fonset = fmax(Fonset2 - Fonset3, 0.0);
+      const double Dp = 100 * density * strain * Fonset * (1.0 - 2.0 * gm_);
+      const double De = 0.06 * vort * Fturb * density * (2.0 * 50.0 * gm_ - 1.0);
+      D[NV - 1] = (D[NV - 1] + (-Dp + De) * vol0);
     }
     if (MODEL == M_KKL) {   // lusgs.f90:1339-1341
       const double rho = q[c], tk = q[5 * fs + c], tkl = q[6 * fs + c], d = geom[(long long)G_DIST * fs + c], mu_c = mu3[c];
@@ -282,7 +313,8 @@ __global__ void __launch_bounds__(128) k_lusgs_apply(const Params P, double* __r
   cq[3] = qq[0] * qq[3];
   cq[4] = (qq[4] / (P.gm - 1.0)) + (0.5 * qq[0] * (((qq[1] * qq[1]) + (qq[2] * qq[2])) + (qq[3] * qq[3])));
   if (NV >= 6) cq[5] = qq[0] * qq[5];
-  if (NV == 7) cq[6] = qq[0] * qq[6];
+  if (NV >= 7) cq[6] = qq[0] * qq[6];
+  if (NV == 8) cq[NV - 1] = qq[0] * qq[NV - 1];
 #pragma unroll
   for (int l = 0; l < NV; ++l) cq[l] = cq[l] + dq[l * fs + c];
   q[c] = cq[0];
@@ -290,10 +322,11 @@ __global__ void __launch_bounds__(128) k_lusgs_apply(const Params P, double* __r
   q[2 * fs + c] = cq[2] / cq[0];
   q[3 * fs + c] = cq[3] / cq[0];
   q[4 * fs + c] = (P.gm - 1.0) * (cq[4] - (0.5 * (((cq[1] * cq[1]) + (cq[2] * cq[2])) + (cq[3] * cq[3])) / cq[0]));
-  if (MODEL == M_SST) {
+  if (MODEL == M_SST || MODEL == M_LCTM) {
     if (cq[5] > 0) q[5 * fs + c] = cq[5] / cq[0];
     if (cq[6] > 0) q[6 * fs + c] = cq[6] / cq[0];
   }
+  if (MODEL == M_LCTM) q[(NV - 1) * fs + c] = fmax(cq[NV - 1] / cq[0], 0.0);   // lusgs.f90:2663-2664: here the intermittency IS advanced
   if (MODEL == M_KKL) { q[5 * fs + c] = fmax(cq[5] / cq[0], 1.e-8); q[6 * fs + c] = fmax(cq[6] / cq[0], 1.e-8); }   // lusgs.f90:1505-1508
   if (MODEL == M_SA) q[5 * fs + c] = fmax(cq[5] / cq[0], 1.e-8);                                                     // lusgs.f90:2095-2096
 }
@@ -336,7 +369,8 @@ int launch_lusgs(Ctx* ctx) {
   if (ctx->P.L.nv == 7 && ctx->P.kkl) return lusgs_run<7, M_KKL>(ctx);
   if (ctx->P.L.nv == 7 && ctx->P.sst) return lusgs_run<7, M_SST>(ctx);
   if (ctx->P.L.nv == 6 && ctx->P.sa) return lusgs_run<6, M_SA>(ctx);
-  return F3D_ERR_UNSUPPORTED;   // lctm2015 (n_var 8): lusgs.f90:2262 is not built
+  if (ctx->P.L.nv == 8 && ctx->P.lctm) return lusgs_run<8, M_LCTM>(ctx);
+  return F3D_ERR_UNSUPPORTED;
 }
 
 }  // namespace f3d

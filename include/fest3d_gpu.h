@@ -55,7 +55,7 @@ enum {
   F3D_ERR_NEGATIVE_STATE = 8,/* rho<0, p<0 or NaN after update   update.f90:448-452 */
   F3D_ERR_GEOMETRY = 16,      /* non-positive cell volume  geometry.f90:476-494 (fest3d_gpu_setup_geometry only) */
   F3D_ERR_IO = 32,            /* checkpoint file cannot be written / read (fest3d_gpu_checkpoint_*, fest3d_gpu_restart) */
-  F3D_ERR_UNSUPPORTED = 64,  /* plusgs / saBC / implicit with lctm2015 (and kkl or lctm2015 with F3D_GRADIENTS=fused) */
+  F3D_ERR_UNSUPPORTED = 64,  /* plusgs / saBC (and kkl, lctm2015 or a viscous implicit run with F3D_GRADIENTS=fused) */
   F3D_ERR_CUDA = 128,
   F3D_ERR_ARGUMENT = 256,    /* also: an interface / periodic face that was neither linked locally nor given a communicator */
   F3D_ERR_PEER = 512         /* another rank reported an error in this call: every rank returns (Fatal_error stops the whole job) */

@@ -21,7 +21,7 @@ struct LusgsCtx {
 };
 
 static inline double fsign1(double b) { return std::copysign(1.0, b); }   // sign(1., b)
-enum { M_LAM = 0, M_SST = 1, M_SA = 2, M_KKL = 3 };
+enum { M_LAM = 0, M_SST = 1, M_SA = 2, M_KKL = 3, M_LCTM = 4 };   // M_LCTM: the SST routine + the intermittency (n_var 8)
 // global_sa.f90:6-19, global_kkl.f90:6-15
 constexpr double sa_cb1 = 0.1355, sa_cb2 = 0.6220, sa_cw2 = 0.3, sa_cw3 = 2.0, sa_cv1 = 7.1, sa_sigma = 2. / 3., sa_kappa = 0.41;
 static const double sa_cw1 = (sa_cb1 / (sa_kappa * sa_kappa)) + ((1 + sa_cb2) / sa_sigma);
@@ -40,18 +40,21 @@ static void lusgs_flux(const LusgsCtx& X, const double* ql, const double* qr, co
   U[3] = ql[0] * ql[3];
   U[4] = (ql[4] / (gm - 1.0)) + (0.5 * ql[0] * (((ql[1] * ql[1]) + (ql[2] * ql[2])) + (ql[3] * ql[3])));
   if (NV >= 6) U[5] = ql[0] * ql[5];
-  if (NV == 7) U[6] = ql[0] * ql[6];
+  if (NV >= 7) U[6] = ql[0] * ql[6];
+  if (NV == 8) U[7] = ql[0] * ql[7];
   for (int l = 0; l < NV; ++l) U[l] = U[l] + du[l];
   W[0] = U[0];
   W[1] = U[1] / U[0];
   W[2] = U[2] / U[0];
   W[3] = U[3] / U[0];
   W[4] = (gm - 1.0) * (U[4] - (0.5 * (((U[1] * U[1]) + (U[2] * U[2])) + (U[3] * U[3])) / U[0]));
-  if (MODEL == M_SST) {
+  if (MODEL == M_SST || MODEL == M_LCTM) {
     W[5] = U[5] / U[0];
     W[6] = U[6] / U[0];
+    if (MODEL == M_LCTM) W[7] = U[7] / U[0];
     W[5] = W[5] + 0.5 * (1. - fsign1(W[5])) * (ql[5] - W[5]);
     W[6] = W[6] + 0.5 * (1. - fsign1(W[6])) * (ql[6] - W[6]);
+    if (MODEL == M_LCTM) W[7] = std::fmax(W[7], 0.0);   // lusgs.f90:2715
   }
   if (MODEL == M_KKL) {   // lusgs.f90:1551-1554
     W[5] = U[5] / U[0];
@@ -76,7 +79,8 @@ static void lusgs_flux(const LusgsCtx& X, const double* ql, const double* qr, co
   const double RhoHt = ((gm / (gm - 1.0)) * W[4]) + HalfRhoUsquare;
   Flux[4] = RhoHt * FaceNormalVelocity;
   if (NV >= 6) Flux[5] = (W[5] * Flux[0]);
-  if (NV == 7) Flux[6] = (W[6] * Flux[0]);
+  if (NV >= 7) Flux[6] = (W[6] * Flux[0]);
+  if (NV == 8) Flux[7] = (W[7] * Flux[0]);
   const double muCap = (MODEL == M_SA) ? 0.25 * (P[0] + W[0]) * (P[5] + W[5]) : 0.0;   // lusgs.f90:2155
   const double mu = mmu + tmu;
   const double T1 = W[4] / (W[0] * R_gas);
@@ -104,13 +108,17 @@ static void lusgs_flux(const LusgsCtx& X, const double* ql, const double* qr, co
     const double dtvdx = (P[5] - W[5]) * nx * Area / Volume, dtvdy = (P[5] - W[5]) * ny * Area / Volume, dtvdz = (P[5] - W[5]) * nz * Area / Volume;
     Flux[5] = Flux[5] + (mmu + muCap) * (dtvdx * nx + dtvdy * ny + dtvdz * nz) / sa_sigma;
   }
-  if (NV == 7) {
+  if (NV >= 7) {
     const double dtkdx = (P[5] - W[5]) * nx * Area / Volume, dtkdy = (P[5] - W[5]) * ny * Area / Volume, dtkdz = (P[5] - W[5]) * nz * Area / Volume;
     const double dtwdx = (P[6] - W[6]) * nx * Area / Volume, dtwdy = (P[6] - W[6]) * ny * Area / Volume, dtwdz = (P[6] - W[6]) * nz * Area / Volume;
     const double sigma_k = (MODEL == M_KKL) ? kkl_sigma_k_l : sigma_k1 * f.F1 + sigma_k2 * (1.0 - f.F1);
     const double sigma_w = (MODEL == M_KKL) ? kkl_sigma_phi_l : sigma_w1 * f.F1 + sigma_w2 * (1.0 - f.F1);
     Flux[5] = Flux[5] + (mmu + sigma_k * tmu) * (dtkdx * nx + dtkdy * ny + dtkdz * nz);
     Flux[6] = Flux[6] + (mmu + sigma_w * tmu) * (dtwdx * nx + dtwdy * ny + dtwdz * nz);
+  }
+  if (NV == 8) {   // lusgs.f90:2753-2755, 2777
+    const double dgdx = (P[7] - W[7]) * nx * Area / Volume, dgdy = (P[7] - W[7]) * ny * Area / Volume, dgdz = (P[7] - W[7]) * nz * Area / Volume;
+    Flux[7] = Flux[7] + (mmu + tmu) * (dgdx * nx + dgdy * ny + dgdz * nz);
   }
   for (int l = 0; l < NV; ++l) Flux[l] = Flux[l] * Area;
 }
@@ -152,7 +160,7 @@ static void lusgs_update(Block& B) {
       F[n].vol = 0.5 * (B.cells.vol(a, b, cc) + B.cells.vol(i, j, k));
       F[n].mmu = 0.5 * (mmu(a, b, cc) + mmu(i, j, k));
       F[n].tmu = 0.5 * (tmu(a, b, cc) + tmu(i, j, k));
-      F[n].F1 = (MODEL == M_SST) ? 0.5 * (B.F1(a, b, cc) + B.F1(i, j, k)) : 0.0;
+      F[n].F1 = (MODEL == M_SST || MODEL == M_LCTM) ? 0.5 * (B.F1(a, b, cc) + B.F1(i, j, k)) : 0.0;
       double C1[3] = {B.cells.cx(a, b, cc), B.cells.cy(a, b, cc), B.cells.cz(a, b, cc)};
       L[n] = spectral_radius(X, Q[n + 1], Q[0], F[n], C1, C0);
     }
@@ -160,10 +168,32 @@ static void lusgs_update(Block& B) {
     for (int n = 0; n < 6; ++n) s = s + L[n];   // SUM(LambdaTimesArea)
     const double D0 = (B.cells.vol(i, j, k) / B.delta_t(i, j, k)) + 0.5 * s;
     for (int l = 0; l < NV; ++l) D[l] = D0;
-    if (MODEL == M_SST) {   // lusgs.f90:830-832
+    if (MODEL == M_SST || MODEL == M_LCTM) {   // lusgs.f90:830-832, 2406-2409
       const double beta = B.F1(i, j, k) * beta1 + (1.0 - B.F1(i, j, k)) * beta2;
       D[5] = (D[5] + (bstar * B.qp(i, j, k, 7)) * B.cells.vol(i, j, k));
       D[6] = (D[6] + 2.0 * beta * B.qp(i, j, k, 7) * B.cells.vol(i, j, k));
+    }
+    if (MODEL == M_LCTM) {   // lusgs.f90:2410-2440: derivative of the intermittency source (no pressure-gradient factor in this Re_theta)
+      const double density = B.qp(i, j, k, 1), d = B.dist(i, j, k), muc = B.mu(i, j, k);
+      const double ux = B.gx(i, j, k, 1), uy = B.gy(i, j, k, 1), uz = B.gz(i, j, k, 1);
+      const double vx = B.gx(i, j, k, 2), vy = B.gy(i, j, k, 2), vz = B.gz(i, j, k, 2);
+      const double wx = B.gx(i, j, k, 3), wy = B.gy(i, j, k, 3), wz = B.gz(i, j, k, 3);
+      const double vort = std::sqrt(((wy - vz) * (wy - vz) + (uz - wx) * (uz - wx) + (vx - uy) * (vx - uy)));
+      const double strain = std::sqrt(((wy + vz) * (wy + vz) + (uz + wx) * (uz + wx) + (vx + uy) * (vx + uy) + 2 * (ux * ux) + 2 * (vy * vy) + 2 * (wz * wz)));
+      const double TuL = std::fmin(100.0 * std::sqrt(2.0 * B.qp(i, j, k, 6) / 3.0) / (B.qp(i, j, k, 7) * d), 100.0);
+      const double Re_theta = 100.0 + 1000.0 * std::exp(-TuL);
+      const double Rev = density * d * d * strain / muc;
+      const double RT = density * B.qp(i, j, k, 6) / (muc * B.qp(i, j, k, 7));
+      const double hr = 0.5 * RT;
+      const double Fturb = std::exp(-((hr * hr) * (hr * hr)));
+      const double Fonset1 = Rev / (2.2 * Re_theta);
+      const double Fonset2 = std::fmin(Fonset1, 2.0);
+      const double r35 = RT / 3.5;
+      const double Fonset3 = std::fmax(1.0 - (r35 * r35 * r35), 0.0);
+      const double Fonset = std::fmax(Fonset2 - Fonset3, 0.0);
+      const double Dp = 100 * density * strain * Fonset * (1.0 - 2.0 * Q[0][7]);
+      const double De = 0.06 * vort * Fturb * density * (2.0 * 50.0 * Q[0][7] - 1.0);
+      D[7] = (D[7] + (-Dp + De) * B.cells.vol(i, j, k));
     }
     if (MODEL == M_KKL) {   // lusgs.f90:1339-1341
       const double vol = B.cells.vol(i, j, k), d = B.dist(i, j, k);
@@ -256,17 +286,19 @@ static void lusgs_update(Block& B) {
         cq[4] = (B.qp(i, j, k, 5) / (c.gm - 1.0)) +
                 (0.5 * B.qp(i, j, k, 1) * (((B.qp(i, j, k, 2) * B.qp(i, j, k, 2)) + (B.qp(i, j, k, 3) * B.qp(i, j, k, 3))) + (B.qp(i, j, k, 4) * B.qp(i, j, k, 4))));
         if (NV >= 6) cq[5] = B.qp(i, j, k, 1) * B.qp(i, j, k, 6);
-        if (NV == 7) cq[6] = B.qp(i, j, k, 1) * B.qp(i, j, k, 7);
+        if (NV >= 7) cq[6] = B.qp(i, j, k, 1) * B.qp(i, j, k, 7);
+        if (NV == 8) cq[7] = B.qp(i, j, k, 1) * B.qp(i, j, k, 8);
         for (int l = 0; l < NV; ++l) cq[l] = cq[l] + delQ(i, j, k, l + 1);
         B.qp(i, j, k, 1) = cq[0];
         B.qp(i, j, k, 2) = cq[1] / cq[0];
         B.qp(i, j, k, 3) = cq[2] / cq[0];
         B.qp(i, j, k, 4) = cq[3] / cq[0];
         B.qp(i, j, k, 5) = (c.gm - 1.0) * (cq[4] - (0.5 * (((cq[1] * cq[1]) + (cq[2] * cq[2])) + (cq[3] * cq[3])) / cq[0]));
-        if (MODEL == M_SST) {
+        if (MODEL == M_SST || MODEL == M_LCTM) {
           if (cq[5] > 0) B.qp(i, j, k, 6) = cq[5] / cq[0];
           if (cq[6] > 0) B.qp(i, j, k, 7) = cq[6] / cq[0];
         }
+        if (MODEL == M_LCTM) B.qp(i, j, k, 8) = std::fmax(cq[7] / cq[0], 0.0);   // lusgs.f90:2663-2664: here the intermittency IS advanced
         if (MODEL == M_KKL) {   // lusgs.f90:1505-1508
           B.qp(i, j, k, 6) = std::fmax(cq[5] / cq[0], 1.e-8);
           B.qp(i, j, k, 7) = std::fmax(cq[6] / cq[0], 1.e-8);
@@ -277,11 +309,12 @@ static void lusgs_update(Block& B) {
 
 }  // namespace
 
-// lusgs.f90:134-183: laminar / inviscid, sst / sst2003 (transition none | bc), kkl, sa (the dispatcher ignores transition = bc for sa);
-// the lctm2015 routine (:2262) is not restated
+// lusgs.f90:134-183: laminar / inviscid, sst / sst2003 (transition none | bc | lctm2015), kkl, sa (the dispatcher ignores transition = bc
+// for sa): every routine of the dispatcher
 int Block::update_with_lusgs() {
   if (c.turbulence == ORC_TURB_NONE) { lusgs_update<5, M_LAM>(*this); return 0; }
   if ((c.turbulence == ORC_TURB_SST || c.turbulence == ORC_TURB_SST2003) && c.transition != 2) { lusgs_update<7, M_SST>(*this); return 0; }
+  if ((c.turbulence == ORC_TURB_SST || c.turbulence == ORC_TURB_SST2003) && c.transition == 2) { lusgs_update<8, M_LCTM>(*this); return 0; }
   if (c.turbulence == ORC_TURB_KKL) { lusgs_update<7, M_KKL>(*this); return 0; }
   if (c.turbulence == ORC_TURB_SA) { lusgs_update<6, M_SA>(*this); return 0; }
   return 64;
