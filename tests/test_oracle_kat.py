@@ -717,3 +717,130 @@ def test_sst_source_against_numpy(oracle, case_mod, turbulence):
         scale = np.abs(balance[v]) + np.abs(res[v]) + np.abs(wv)
         assert np.abs(S_vol[v] - wv).max() <= 2e-12 * scale.max(), v
         assert np.abs(wv).max() > 1e-3 * np.abs(res[v]).max(), v
+
+
+def test_laminar_viscous_flux_against_numpy(oracle, case_mod):
+    """compute_viscous_fluxes_laminar (viscous.f90:144-325) restated in numpy -- face gradient = mean of the two cell gradients corrected so
+    that its component along the line of centres equals the finite difference, Stokes stress, Fourier heat flux -- against the difference of
+    the oracle's face fluxes with and without viscosity on the same state (the boundary fills do not depend on mu for a laminar case)."""
+    import importlib
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    # mu_ref = 0.5 Pa s: a viscous flux of the size of the inviscid one, so that the difference of the two runs resolves it to ~1e-12
+    blocks = syn.make_duct_blocks(None, n3=(9, 7, 6), turbulence="none", mu_ref=0.5)
+    inv = syn.make_duct_blocks(None, n3=(9, 7, 6), turbulence="none", mu_ref=0.0)
+    inv[0].qp[:] = blocks[0].qp
+    blk = blocks[0]
+    fl = blk.flow
+    w, wi = oracle.OracleWorld(blocks), oracle.OracleWorld(inv)
+    assert w.residual(1)[0] == 0 and wi.residual(1)[0] == 0
+    nv = 5
+    full = (blk.kmx + 5, blk.jmx + 5, blk.imx + 5)
+    q = w.get_state(0)
+    assert np.array_equal(q, wi.get_state(0))
+    mu = w.aux(0, 1, full)
+    gshape = (4, blk.kmx + 1, blk.jmx + 1, blk.imx + 1)
+    g = [w.aux(0, 30 + d, gshape) for d in range(3)]              # g[d][component u, v, w, T][cells 0..imx]
+    T = q[4] / (q[0] * fl.R_gas)
+    cen = blk.cells[..., 1:4]
+    shapes = {0: (nv, blk.kmx - 1, blk.jmx - 1, blk.imx), 1: (nv, blk.kmx - 1, blk.jmx, blk.imx - 1), 2: (nv, blk.kmx, blk.jmx - 1, blk.imx - 1)}
+    faces = {0: blk.Ifaces, 1: blk.Jfaces, 2: blk.Kfaces}
+    worst = 0.0
+    for d in range(3):
+        Fv = wi.aux(0, 20 + d, shapes[d]) - w.aux(0, 20 + d, shapes[d])       # F_inviscid - (F_inviscid - F_viscous A) = viscous flux x area
+        # faces 1..mx along d, cells 1..m-1 across: in the -2-based full arrays the high cell of face f is index f + 2, in the 0-based
+        # gradient arrays index f
+        def sl(off, full_array):
+            base = 2 if full_array else 0
+            ks = slice(base + 1, base + blk.kmx) if d != 2 else slice(base + 1 + off, base + blk.kmx + 1 + off)
+            js = slice(base + 1, base + blk.jmx) if d != 1 else slice(base + 1 + off, base + blk.jmx + 1 + off)
+            is_ = slice(base + 1, base + blk.imx) if d != 0 else slice(base + 1 + off, base + blk.imx + 1 + off)
+            return ks, js, is_
+        hi_f, lo_f, hi_g, lo_g = sl(0, True), sl(-1, True), sl(0, False), sl(-1, False)
+        dr = cen[hi_f] - cen[lo_f]
+        dLR = np.sqrt((dr ** 2).sum(-1))
+        comps = [q[1], q[2], q[3], T]
+        G = np.empty((4, 3) + dLR.shape)
+        for c in range(4):
+            avg = np.stack([0.5 * (g[x][c][lo_g] + g[x][c][hi_g]) for x in range(3)])
+            delta = comps[c][hi_f] - comps[c][lo_f]
+            ncomp = (delta - (avg * np.moveaxis(dr, -1, 0)).sum(0)) / dLR
+            G[c] = avg + ncomp * np.moveaxis(dr, -1, 0) / dLR
+        mu_f = 0.5 * (mu[lo_f] + mu[hi_f])
+        div = G[0, 0] + G[1, 1] + G[2, 2]
+        tau = [[mu_f * (G[a, b] + G[b, a]) - (2.0 / 3.0) * mu_f * div * (a == b) for b in range(3)] for a in range(3)]
+        K = mu_f / fl.Pr * fl.gm * fl.R_gas / (fl.gm - 1.0)
+        vel = [0.5 * (q[1 + a][lo_f] + q[1 + a][hi_f]) for a in range(3)]
+        fa = faces[d][hi_f]
+        A, n = fa[..., 0], [fa[..., 1], fa[..., 2], fa[..., 3]]
+        want = np.zeros((nv,) + dLR.shape)
+        for a in range(3):
+            want[1 + a] = sum(tau[a][b] * n[b] for b in range(3)) * A
+        want[4] = sum((sum(tau[a][b] * vel[a] for a in range(3)) + K * G[3, b]) * n[b] for b in range(3)) * A
+        # flux masks: wall-like faces have the INVISCID flux zeroed, not the viscous one, so every face compares
+        scale = np.abs(want).reshape(nv, -1).max(axis=1)
+        for v in range(1, 5):
+            err = np.abs(Fv[v] - want[v]).max() / scale[v]
+            worst = max(worst, err)
+            assert err < 1e-10, (d, v, err)
+        assert np.abs(Fv[0]).max() <= 1e-12 * np.abs(w.aux(0, 20 + d, shapes[d])[0]).max()
+    assert worst > 0.0
+
+
+def test_sa_source_against_numpy(oracle, case_mod):
+    """add_sa_source (source.f90:835-983) restated in numpy, with its kept defect -- the low K face enters the density gradient with
+    (nx, nx, nx) as its normal (:901) -- against what the oracle subtracted from the flux balance."""
+    import importlib
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    blocks = syn.make_duct_blocks(None, n3=(9, 7, 6), turbulence="sa")
+    blk = blocks[0]
+    blk.qp[5] *= 30.0
+    w = oracle.OracleWorld(blocks)
+    err, res = w.residual(1)
+    assert err == 0
+    res = res[0]
+    nv = 6
+    full = (blk.kmx + 5, blk.jmx + 5, blk.imx + 5)
+    F = w.aux(0, 20, (nv, blk.kmx - 1, blk.jmx - 1, blk.imx))
+    G = w.aux(0, 21, (nv, blk.kmx - 1, blk.jmx, blk.imx - 1))
+    H = w.aux(0, 22, (nv, blk.kmx, blk.jmx - 1, blk.imx - 1))
+    balance = (F[..., 1:] - F[..., :-1]) + (G[:, :, 1:, :] - G[:, :, :-1, :]) + (H[:, 1:] - H[:, :-1])
+    S_vol = (balance - res)[5]
+    gshape = (5, blk.kmx + 1, blk.jmx + 1, blk.imx + 1)
+    gx, gy, gz = (w.aux(0, 30 + d, gshape)[:, 1:-1, 1:-1, 1:-1] for d in range(3))
+    Ki, Ji, Ii = slice(3, blk.kmx + 2), slice(3, blk.jmx + 2), slice(3, blk.imx + 2)
+    K0, J0, I0 = slice(2, blk.kmx + 1), slice(2, blk.jmx + 1), slice(2, blk.imx + 1)
+    K1, J1, I1 = slice(4, blk.kmx + 3), slice(4, blk.jmx + 3), slice(4, blk.imx + 3)
+    qf = w.get_state(0)
+    rho_f = qf[0]
+    rho, tv = rho_f[Ki, Ji, Ii], qf[5][Ki, Ji, Ii]
+    mu = w.aux(0, 1, full)[Ki, Ji, Ii]
+    d, vol = blk.dist[Ki, Ji, Ii], blk.cells[Ki, Ji, Ii, 0]
+    IF, JF, KF = blk.Ifaces, blk.Jfaces, blk.Kfaces
+    gradrho = []
+    for dd in range(3):
+        kn = KF[Ki, Ji, Ii, 1]                     # the defect: nx of the low K face for every component
+        gradrho.append((-(rho_f[Ki, Ji, I0] + rho) * IF[Ki, Ji, Ii, 1 + dd] * IF[Ki, Ji, Ii, 0] - (rho_f[Ki, J0, Ii] + rho) * JF[Ki, Ji, Ii, 1 + dd] * JF[Ki, Ji, Ii, 0]
+                        - (rho_f[K0, Ji, Ii] + rho) * kn * KF[Ki, Ji, Ii, 0] + (rho_f[Ki, Ji, I1] + rho) * IF[Ki, Ji, I1, 1 + dd] * IF[Ki, Ji, I1, 0]
+                        + (rho_f[Ki, J1, Ii] + rho) * JF[Ki, J1, Ii, 1 + dd] * JF[Ki, J1, Ii, 0] + (rho_f[K1, Ji, Ii] + rho) * KF[K1, Ji, Ii, 1 + dd] * KF[K1, Ji, Ii, 0]) / (2.0 * vol))
+    cb1, cb2, cw2, cw3, cv1, sigma, kappa = 0.1355, 0.6220, 0.3, 2.0, 7.1, 2.0 / 3.0, 0.41
+    cw1 = cb1 / kappa ** 2 + (1 + cb2) / sigma
+    vort = np.sqrt((gy[2] - gz[1]) ** 2 + (gz[0] - gx[2]) ** 2 + (gx[1] - gy[0]) ** 2)
+    CD1 = cb2 * (gx[4] ** 2 + gy[4] ** 2 + gz[4] ** 2)
+    CD2 = gradrho[0] * gx[4] + gradrho[1] * gy[4] + gradrho[2] * gz[4]
+    kd2 = (kappa * d) ** 2
+    nu = mu / rho
+    xi = tv / nu
+    fv1 = xi ** 3 / (xi ** 3 + cv1 ** 3)
+    fv2 = 1 - xi / (1 + xi * fv1)
+    scap = np.maximum(vort + tv * fv2 / kd2, 0.3 * vort)
+    r = np.minimum(tv / (scap * kd2), 10.0)
+    g = r + cw2 * (r ** 6 - r)
+    fw = g * ((1 + cw3 ** 6) / (g ** 6 + cw3 ** 6)) ** (1.0 / 6.0)
+    want = (rho * cb1 * scap * tv - rho * cw1 * fw * (tv / d) ** 2 + rho * CD1 / sigma - CD2 * (nu + tv) / sigma) * vol
+    scale = np.abs(balance[5]) + np.abs(res[5]) + np.abs(want)
+    assert np.abs(S_vol - want).max() <= 5e-12 * scale.max()
+    assert np.abs(want).max() > 1e-3 * np.abs(res[5]).max()
+    # the defect is visible at this resolution: with the true normal of the low K face the cross-diffusion term differs
+    true_k = [-(rho_f[K0, Ji, Ii] + rho) * (KF[Ki, Ji, Ii, 1 + dd] - KF[Ki, Ji, Ii, 1]) * KF[Ki, Ji, Ii, 0] / (2.0 * vol) for dd in range(3)]
+    dCD2 = true_k[0] * gx[4] + true_k[1] * gy[4] + true_k[2] * gz[4]
+    assert np.abs(dCD2 * (nu + tv) / sigma * vol).max() > 1e-6 * scale.max()
