@@ -867,3 +867,68 @@ def test_sa_source_against_numpy(oracle, case_mod):
     true_k = [-(rho_f[K0, Ji, Ii] + rho) * (KF[Ki, Ji, Ii, 1 + dd] - KF[Ki, Ji, Ii, 1]) * KF[Ki, Ji, Ii, 0] / (2.0 * vol) for dd in range(3)]
     dCD2 = true_k[0] * gx[4] + true_k[1] * gy[4] + true_k[2] * gz[4]
     assert np.abs(dCD2 * (nu + tv) / sigma * vol).max() > 1e-6 * scale.max()
+
+
+@pytest.mark.parametrize("turbulence", ["none", "sst", "sa"])
+def test_update_against_numpy(oracle, case_mod, turbulence):
+    """update_with (update.f90:367-485, "conservative" branch) restated in numpy for the single-stage integrator: conservative variables,
+    point-implicit scaling of the turbulence residuals (sst: 1 + beta omega dt and 1 + 2 beta omega dt with the F1-blended beta; sa: the
+    production / destruction factor with rho nu-tilde where the model has nu-tilde, as the reference writes it), u2 = u1 - R dt / V, back to
+    primitive variables, positivity rules -- from the oracle's own residual, time step, F1, mu and gradients."""
+    import importlib
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    blocks = syn.make_duct_blocks(None, n3=(9, 7, 6), turbulence=turbulence, time_step_accuracy="none", CFL=0.7)
+    blk = blocks[0]
+    fl = blk.flow
+    w, w2 = oracle.OracleWorld(blocks), oracle.OracleWorld(blocks)
+    err, res = w.residual(1)
+    assert err == 0 and w2.step(1)[0] == 0
+    R = res[0]
+    nv = blk.n_var
+    Ki, Ji, Ii = slice(3, blk.kmx + 2), slice(3, blk.jmx + 2), slice(3, blk.imx + 2)
+    q0, q1 = w.get_state(0)[:, Ki, Ji, Ii], w2.get_state(0)[:, Ki, Ji, Ii]
+    dt = w2.aux(0, 0, (blk.kmx - 1, blk.jmx - 1, blk.imx - 1))
+    vol = blk.cells[Ki, Ji, Ii, 0]
+    full = (blk.kmx + 5, blk.jmx + 5, blk.imx + 5)
+    gm = fl.gm
+    u1 = q0.copy()
+    u1[1:] = q0[1:] * q0[0]
+    u1[4] = (q0[4] * q0[0] / (gm - 1) + 0.5 * (u1[1] ** 2 + u1[2] ** 2 + u1[3] ** 2)) / q0[0]
+    Rr = R.copy()
+    if turbulence == "sst":
+        F1 = w2.aux(0, 3, full)[Ki, Ji, Ii]
+        beta = 0.075 * F1 + (1 - F1) * 0.0828
+        Rr[5] = R[5] / (1 + beta * q0[6] * dt)
+        Rr[6] = R[6] / (1 + 2 * beta * q0[6] * dt)
+    if turbulence == "sa":
+        mu = w2.aux(0, 1, full)[Ki, Ji, Ii]
+        gshape = (5, blk.kmx + 1, blk.jmx + 1, blk.imx + 1)
+        gx, gy, gz = (w2.aux(0, 30 + d, gshape)[:, 1:-1, 1:-1, 1:-1] for d in range(3))
+        vort = np.sqrt((gy[2] - gz[1]) ** 2 + (gz[0] - gx[2]) ** 2 + (gx[1] - gy[0]) ** 2)
+        d = blk.dist[Ki, Ji, Ii]
+        cb1, cb2, cw2, cw3, cv1, sigma, kappa = 0.1355, 0.6220, 0.3, 2.0, 7.1, 2.0 / 3.0, 0.41
+        cw1 = cb1 / kappa ** 2 + (1 + cb2) / sigma
+        kd2 = (kappa * d) ** 2
+        x = u1[5]                                   # rho * nu-tilde, used where the model has nu-tilde (update.f90:405-420, reproduced)
+        xi = x * q0[0] / mu
+        fv1 = xi ** 3 / (xi ** 3 + cv1 ** 3)
+        fv2 = 1 - xi / (1 + xi * fv1)
+        scap = vort + x * fv2 / kd2
+        r = np.minimum(x / (scap * kd2), 10.0)
+        g = r + cw2 * (r ** 6 - r)
+        fw = g * ((1 + cw3 ** 6) / (g ** 6 + cw3 ** 6)) ** (1.0 / 6.0)
+        Rr[5] = R[5] / (1 + ((-u1[0] * cb1 * scap) + (2 * u1[0] * cw1 * fw * x / d ** 2)) * dt)
+    u2 = u1 - Rr * (dt / vol)
+    u2[1:] = u2[1:] / u2[0]
+    u2[4] = (gm - 1) * u2[0] * (u2[4] - 0.5 * (u2[1] ** 2 + u2[2] ** 2 + u2[3] ** 2))
+    want = q0.copy()
+    want[:5] = u2[:5]
+    if turbulence == "sst":
+        want[5] = np.where(u2[5] >= 0, u2[5], q0[5])
+        want[6] = np.where(u2[6] >= 0, u2[6], q0[6])
+    if turbulence == "sa":
+        want[5] = np.maximum(u2[5], 1e-12)
+    for v in range(nv):
+        scale = np.abs(q0[v]).max() + 1e-300
+        assert np.abs(q1[v] - want[v]).max() <= 2e-13 * scale, (v, np.abs(q1[v] - want[v]).max() / scale)
+        assert np.abs(q1[v] - q0[v]).max() > 1e-9 * scale or v in (3,), v          # the step moved the variable
