@@ -932,3 +932,63 @@ def test_update_against_numpy(oracle, case_mod, turbulence):
         scale = np.abs(q0[v]).max() + 1e-300
         assert np.abs(q1[v] - want[v]).max() <= 2e-13 * scale, (v, np.abs(q1[v] - want[v]).max() / scale)
         assert np.abs(q1[v] - q0[v]).max() > 1e-9 * scale or v in (3,), v          # the step moved the variable
+
+
+def test_lusgs_two_cells_against_numpy(oracle, case_mod):
+    """The coupling terms of the LU-SGS sweeps (lusgs.f90:296-312, 426-447) on an inviscid block of two cells in i, written out in numpy: the
+    forward sweep gives cell 2 the flux change its low neighbour's correction causes, the backward sweep hands cell 2's correction back to
+    cell 1.  Flux (:491-630) reduces to the Euler flux of the neighbour state advanced by its correction, through the shared face."""
+    import importlib
+    syn = importlib.import_module("fest3d_b200.synthetic")
+    blocks = syn.make_duct_blocks(None, n3=(2, 1, 1), turbulence="none", mu_ref=0.0, time_step_accuracy="implicit", CFL=4.0)
+    blk = blocks[0]
+    gm = blk.flow.gm
+    w, w2 = oracle.OracleWorld(blocks), oracle.OracleWorld(blocks)
+    err, res = w.residual(1)
+    assert err == 0 and w2.step(1)[0] == 0
+    q0, q1 = w.get_state(0), w2.get_state(0)
+    dt = w2.aux(0, 0, (1, 1, 2))[0, 0]
+    R = res[0][:, 0, 0, :]                           # [var, cell]
+    cells = [(3, 3, 3), (3, 3, 4)]                   # (k, j, i) of the two cells in the -2-based arrays
+
+    def cons(qv):
+        return np.array([qv[0], qv[0] * qv[1], qv[0] * qv[2], qv[0] * qv[3], qv[4] / (gm - 1) + 0.5 * qv[0] * np.dot(qv[1:4], qv[1:4])])
+
+    def flux(ql, du, A, n):                          # Euler flux of (ql advanced by du) through a face of area A and normal n
+        U = cons(ql) + du
+        rho, vel = U[0], U[1:4] / U[0]
+        p = (gm - 1) * (U[4] - 0.5 * np.dot(U[1:4], U[1:4]) / U[0])
+        un = np.dot(vel, n)
+        return np.array([rho * un, *(rho * vel * un + p * n), (gm / (gm - 1) * p + 0.5 * rho * np.dot(vel, vel)) * un]) * A
+
+    def lam(qa, qb, A, n):                           # SpectralRadius without viscosity
+        return (abs(0.5 * np.dot(qa[1:4] + qb[1:4], n)) + 0.5 * (np.sqrt(gm * qa[4] / qa[0]) + np.sqrt(gm * qb[4] / qb[0]))) * A
+
+    def faces_of(c):
+        k, j, i = c
+        return [(blk.Ifaces[k, j, i], (k, j, i - 1)), (blk.Jfaces[k, j, i], (k, j - 1, i)), (blk.Kfaces[k, j, i], (k - 1, j, i)),
+                (blk.Ifaces[k, j, i + 1], (k, j, i + 1)), (blk.Jfaces[k, j + 1, i], (k, j + 1, i)), (blk.Kfaces[k + 1, j, i], (k + 1, j, i))]
+
+    D = []
+    for c in cells:
+        s_ = sum(lam(q0[(slice(None),) + nb], q0[(slice(None),) + c], f[0], f[1:4]) for f, nb in faces_of(c))
+        D.append(blk.cells[c][0] / dt[cells.index(c)] + 0.5 * s_)
+    qa, qb = q0[(slice(None),) + cells[0]], q0[(slice(None),) + cells[1]]
+    fI = blk.Ifaces[3, 3, 4]                          # the face the two cells share
+    A, n = fI[0], fI[1:4]
+    lamI = lam(qa, qb, A, n)
+    zero = np.zeros(5)
+    dqs1 = -R[:, 0] / D[0]
+    dF = flux(qa, dqs1, A, -n) - flux(qa, zero, A, -n)          # low face of cell 2: outward normal -n
+    dqs2 = (-R[:, 1] - 0.5 * (dF - lamI * dqs1)) / D[1]
+    dq2 = dqs2
+    dB = flux(qb, dq2, A, n) - flux(qb, zero, A, n)             # high face of cell 1
+    dq1 = dqs1 - 0.5 * (dB - lamI * dq2) / D[0]
+    for c, dq in zip(cells, (dq1, dq2)):
+        U = cons(q0[(slice(None),) + c]) + dq
+        want = np.array([U[0], *(U[1:4] / U[0]), (gm - 1) * (U[4] - 0.5 * np.dot(U[1:4], U[1:4]) / U[0])])
+        got = q1[(slice(None),) + c]
+        assert np.allclose(got, want, rtol=1e-12, atol=1e-12 * np.abs(want).max()), (c, got, want)
+    # the coupling is not negligible: without it cell 1 would land elsewhere
+    U = cons(qa) + dqs1
+    assert abs(U[0] - q1[0][cells[0]]) > 1e-8 * abs(U[0])
