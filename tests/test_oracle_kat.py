@@ -719,8 +719,9 @@ def test_sst_source_against_numpy(oracle, case_mod, turbulence):
         assert np.abs(wv).max() > 1e-3 * np.abs(res[v]).max(), v
 
 
-@pytest.mark.parametrize("turbulence", ["none", "sst"])
-def test_viscous_flux_against_numpy(oracle, case_mod, turbulence):
+@pytest.mark.parametrize("turbulence,bc,wall_T", [("none", [-3, -4, -6, -6, -6, -6], 0.0), ("sst", [-3, -4, -6, -6, -6, -6], 0.0),
+                                                  ("none", [-3, -4, -5, -5, -6, -5], 0.0), ("none", [-8, -4, -5, -6, -5, -6], 350.0)])
+def test_viscous_flux_against_numpy(oracle, case_mod, turbulence, bc, wall_T):
     """compute_viscous_fluxes_laminar (viscous.f90:144-325) and, for sst, compute_viscous_fluxes_sst (:328-447) restated in numpy -- face
     gradient = mean of the two cell gradients corrected so that its component along the line of centres equals the finite difference, Stokes
     stress with mu + mu_t, Fourier heat flux with mu/Pr + mu_t/Pr_t, the -2/3 rho k normal stress and the F1-blended diffusion of k and omega
@@ -733,8 +734,9 @@ def test_viscous_flux_against_numpy(oracle, case_mod, turbulence):
     # reconstruction and the fills of these boundary types work variable by variable.
     blocks = syn.make_duct_blocks(None, n3=(9, 7, 6), turbulence=turbulence, mu_ref=0.5)
     inv = syn.make_duct_blocks(None, n3=(9, 7, 6), turbulence="none", mu_ref=0.0)
-    for b_ in (blocks[0], inv[0]):
-        b_.bc_id = [-3, -4, -6, -6, -6, -6]
+    for b_ in (blocks[0], inv[0]):          # laminar no-slip walls (adiabatic: gradient rule -grad T; isothermal: fixed wall temperature) too
+        b_.bc_id = list(bc)
+        b_.fixed[7, :] = wall_T
         b_.build_geometry()
     if turbulence == "sst":
         blocks[0].qp[5] *= 1e4          # mu_t of the size of mu
